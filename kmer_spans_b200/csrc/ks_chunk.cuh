@@ -1,0 +1,333 @@
+// ks_chunk.cuh -- per-chunk logic of the kmer_spans hot path, shared by the sm_100a kernels
+// (ks_kernels.cuh) and by the host-side emulation used ONLY by tests (tests/emu/ks_emu.cpp).
+//
+// A chunk is 16 consecutive byte positions of the concatenated sequence buffer, owned by one
+// thread.  Everything here is straight-line code over register arrays (fully unrolled).
+//
+// Reference behaviour restated here (file:line in /root/reference/src/kmer_spans.c):
+//   * 2-bit code (c>>1)&3, only N/n (and the terminator) break a run            :34-35,111-132
+//   * counting rule incl. the exact-k-at-terminator drop                          :135-155
+//   * scored indices of a run [a,b): i = a+k .. b-1, w_i = W[code(i-1)] - thr     :261-296
+//   * S' = (S + w > 0) ? S + w : 0, start / leftmost peak / close bookkeeping     :269-291
+//
+// Arithmetic: the scan runs in EXACT fixed point.  Every per-k-mer score (W[code]-thr, the
+// double the reference computes at :268) is converted once to a signed 64-bit multiple of
+// q = 2^-QS (QS chosen per table so that max|w| < 2^(63-QS)); running sums are 128-bit
+// integers in units of q.  Integer addition is associative, so tile, block, warp and
+// multi-GPU decompositions all give the same bits, and the max-plus transforms
+// x -> max(x + a, b) compose exactly.  DESIGN.md discusses the parity consequences.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define KS_HD __host__ __device__ __forceinline__
+#else
+#define KS_HD inline
+#endif
+
+namespace ks {
+
+constexpr int CHUNK = 16;
+typedef __int128 fx_t;                 // running sums, units of q = 2^-QS
+constexpr int64_t WFX_KILL = INT64_MIN;  // table sentinel: NaN / -inf weight => state forced to 0
+
+KS_HD bool is_break(uint32_t c) { return c == 0u || (c | 0x20u) == 0x6eu; }  // NUL, 'N', 'n'
+KS_HD uint32_t base2(uint32_t c) { return (c >> 1) & 3u; }
+KS_HD uint32_t byte_of(const uint32_t *w, int j) { return (w[j >> 2] >> ((j & 3) * 8)) & 0xffu; }
+
+// ---------------------------------------------------------------------------------------------
+// decode for the SCAN: w[0..3] = the 16 bytes before the chunk, w[4..7] = the chunk itself.
+// code[j] = k-mer ending at byte j-1; bit j of `scored` set iff byte j and the k bytes before
+// it are all non-break and j < n_in (n_in = positions of this chunk inside its segment).
+KS_HD void decode_scan(const uint32_t w[8], int k, uint32_t kmask, int n_in, uint32_t code[CHUNK],
+                       uint32_t &scored) {
+  int rl = 0;
+  uint32_t c2 = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    uint32_t c = byte_of(w, j);
+    rl = is_break(c) ? 0 : rl + 1;
+    c2 = (c2 << 2) | base2(c);
+  }
+  scored = 0;
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) {
+    uint32_t c = byte_of(w, 16 + j);
+    bool brk = is_break(c);
+    code[j] = c2 & kmask;
+    if (!brk && rl >= k && j < n_in) scored |= 1u << j;
+    rl = brk ? 0 : rl + 1;
+    c2 = (c2 << 2) | base2(c);
+  }
+}
+
+// decode for COUNTING: code[j] = k-mer ENDING at byte j; bit j of `counted` set iff that k-mer
+// is counted by sequence_kmer_count (:135-155): all k bytes non-break, and not the case "first
+// k-mer of its run and the next byte is the terminator" (:143-144).  next = byte 16 of the chunk.
+KS_HD void decode_count(const uint32_t w[8], uint32_t next, int k, uint32_t kmask,
+                        uint32_t code[CHUNK], uint32_t &counted) {
+  int rl = 0;
+  uint32_t c2 = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    uint32_t c = byte_of(w, j);
+    rl = is_break(c) ? 0 : rl + 1;
+    c2 = (c2 << 2) | base2(c);
+  }
+  counted = 0;
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) {
+    uint32_t c = byte_of(w, 16 + j);
+    uint32_t nx = (j == CHUNK - 1) ? next : byte_of(w, 17 + j);
+    bool brk = is_break(c);
+    c2 = (c2 << 2) | base2(c);
+    code[j] = c2 & kmask;
+    bool ok = !brk && rl >= k - 1 && !(rl == k - 1 && nx == 0u);
+    if (ok) counted |= 1u << j;
+    rl = brk ? 0 : rl + 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// double -> table entry (signed multiple of 2^-qs).  Exact when the double's last mantissa bit
+// is >= 2^-qs, truncated toward zero otherwise.  NaN and anything <= -2^62 map to WFX_KILL.
+KS_HD int64_t wfx_from_double(double d, int qs) {
+  if (!(d == d) || d <= -0x1p40) return WFX_KILL;  // NaN, -inf, or "as good as -inf"
+  uint64_t bits;
+  memcpy(&bits, &d, 8);
+  int e = (int)((bits >> 52) & 0x7ff);
+  uint64_t m = bits & ((1ull << 52) - 1);
+  bool neg = (bits >> 63) != 0;
+  if (e == 0) return 0;
+  m |= 1ull << 52;
+  int sh = e - 1075 + qs;  // value * 2^qs = m * 2^sh
+  uint64_t v;
+  if (sh >= 0) {
+    if (sh > 9) return INT64_MAX;  // cannot happen when qs = qs_for_max(max |w|)
+    v = m << sh;
+  } else if (sh > -64) {
+    v = m >> (-sh);
+  } else {
+    v = 0;
+  }
+  return neg ? -(int64_t)v : (int64_t)v;
+}
+
+// number of fraction bits for a table whose largest finite |w| is wmax: max|w| < 2^(62-qs)
+KS_HD int qs_for_max(double wmax) {
+  uint64_t bits;
+  memcpy(&bits, &wmax, 8);
+  int e = (int)((bits >> 52) & 0x7ff) - 1023;  // wmax in [2^e, 2^(e+1))
+  if (wmax == 0.0) e = -1;
+  int E = e + 1;  // wmax < 2^E
+  int qs = 62 - E;
+  if (qs > 62) qs = 62;
+  return qs;
+}
+
+// 128-bit running sum (units of 2^-qs) -> nearest double (ties to even).
+KS_HD double fx_to_double(fx_t v, int qs) {
+  bool neg = v < 0;
+  unsigned __int128 u = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
+  if (u == 0) return 0.0;
+  uint64_t hi = (uint64_t)(u >> 64), lo = (uint64_t)u;
+  int msb;
+  if (hi) { msb = 64; uint64_t t = hi; while (t >>= 1) ++msb; }
+  else { msb = 0; uint64_t t = lo; while (t >>= 1) ++msb; }
+  uint64_t m;
+  int sh = 0;
+  if (msb <= 52) {
+    m = lo;
+  } else {
+    sh = msb - 52;
+    unsigned __int128 q = u >> sh;
+    unsigned __int128 rem = u & ((((unsigned __int128)1) << sh) - 1);
+    unsigned __int128 half = ((unsigned __int128)1) << (sh - 1);
+    m = (uint64_t)q;
+    if (rem > half || (rem == half && (m & 1))) ++m;
+  }
+  // m * 2^(sh - qs); m <= 2^53 so (double)m is exact, scaling by a power of two is exact
+  double r = (double)m;
+  int ex = sh - qs;
+  // scale in two safe steps (|ex| <= 190)
+  uint64_t pb;
+  double p;
+  int e1 = ex / 2, e2 = ex - e1;
+  pb = (uint64_t)(1023 + e1) << 52; memcpy(&p, &pb, 8); r *= p;
+  pb = (uint64_t)(1023 + e2) << 52; memcpy(&p, &pb, 8); r *= p;
+  return neg ? -r : r;
+}
+
+// min_score (double) -> smallest integer number of units u with u * 2^-qs >= min_score.
+// Saturates far outside the reachable range of sums.
+KS_HD fx_t fx_ceil_units(double x, int qs) {
+  const fx_t BIG = ((fx_t)1) << 126;
+  if (!(x == x)) return BIG;  // NaN: nothing qualifies (M >= NaN is false)
+  uint64_t bits;
+  memcpy(&bits, &x, 8);
+  int e = (int)((bits >> 52) & 0x7ff);
+  uint64_t m = bits & ((1ull << 52) - 1);
+  bool neg = (bits >> 63) != 0;
+  if (e == 0) return (m != 0 && !neg) ? (fx_t)1 : (fx_t)0;  // +-0 -> 0; positive subnormal -> 1 unit
+  if (e - 1023 + qs >= 100) return neg ? -BIG : BIG;        // beyond any reachable sum (< 2^102 units)
+  m |= 1ull << 52;
+  int sh = e - 1075 + qs;  // <= 47
+  unsigned __int128 v;
+  bool inexact = false;
+  if (sh >= 0) {
+    v = ((unsigned __int128)m) << sh;
+  } else if (sh > -64) {
+    v = m >> (-sh);
+    inexact = (m & ((1ull << (-sh)) - 1)) != 0;
+  } else {
+    v = 0;
+    inexact = true;
+  }
+  fx_t r = (fx_t)v;
+  if (neg) return -r;          // ceil of a negative value: truncation toward zero
+  return inexact ? r + 1 : r;  // ceil of a positive value
+}
+
+// ---------------------------------------------------------------------------------------------
+// max-plus transform x -> kill ? b : max(x + a, b).  (a = -inf is carried as the flag `kill`.)
+struct Xf {
+  fx_t a, b;
+  uint32_t kill;
+};
+constexpr int XF_IDENT_SHIFT = 124;
+KS_HD Xf xf_identity() { Xf f; f.a = 0; f.b = -(((fx_t)1) << XF_IDENT_SHIFT); f.kill = 0; return f; }
+KS_HD fx_t fx_max(fx_t x, fx_t y) { return x > y ? x : y; }
+// f first, then g
+KS_HD Xf xf_compose(const Xf &f, const Xf &g) {
+  if (g.kill) return g;
+  Xf r;
+  r.kill = f.kill;
+  r.a = f.a + g.a;
+  r.b = fx_max(f.b + g.a, g.b);
+  return r;
+}
+KS_HD fx_t xf_apply(const Xf &f, fx_t x) { return f.kill ? f.b : fx_max(x + f.a, f.b); }
+
+// chunk transform.  s[j] valid where bit j of live is set; other positions force the state to 0.
+KS_HD Xf chunk_transform(const int64_t s[CHUNK], uint32_t live) {
+  Xf f = xf_identity();
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) {
+    if (live & (1u << j)) {
+      f.a += (fx_t)s[j];
+      fx_t t = f.b + (fx_t)s[j];
+      f.b = t > 0 ? t : (fx_t)0;
+    } else {
+      f.kill = 1; f.a = 0; f.b = 0;
+    }
+  }
+  return f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Open-excursion state carried across chunk boundaries (segmented max-scan element).
+//   reset = 1: the chunk determines the state at its end by itself:
+//              open = 1 -> (beg, M, pk) of the excursion open at the chunk end; open = 0 -> closed
+//   reset = 0: the whole chunk lies inside one excursion entering from the left (no zero, no
+//              start); (M, pk) = maximum over the chunk, beg inherited.
+struct Ex {
+  fx_t M;
+  int64_t beg, pk;
+  uint32_t reset, open;
+};
+KS_HD Ex ex_identity() { Ex e; e.M = -(((fx_t)1) << 126); e.beg = -1; e.pk = -1; e.reset = 0; e.open = 1; return e; }
+// l first, then r.  Strict > keeps the LEFTMOST maximum (reference :287).
+KS_HD Ex ex_combine(const Ex &l, const Ex &r) {
+  if (r.reset) return r;
+  Ex o = l;
+  if (r.M > l.M) { o.M = r.M; o.pk = r.pk; }
+  return o;
+}
+
+struct ScanParams {
+  uint64_t min_width;  // compared as in the reference (:279): (uint64)(pk - beg) >= min_width
+  fx_t min_units;      // M >= min_score, in units of 2^-qs
+};
+
+KS_HD bool qualifies(const ScanParams &p, int64_t beg, int64_t pk, fx_t M) {
+  return (uint64_t)(pk - beg) >= p.min_width && M >= p.min_units;
+}
+
+// Walk a chunk with its true incoming state S_in (> 0 means an excursion enters from the left).
+// Emits every excursion that both starts and closes inside the chunk; returns in `pre` the
+// (M, pk) over the positions before the first zero (the part belonging to the entering
+// excursion), `first_zero` = position index (0..15) of that zero or -1, and in `ex` the
+// segmented-scan element of this chunk.  p0 = global position of chunk byte 0.
+template <class Emit>
+KS_HD void chunk_walk(const int64_t s[CHUNK], uint32_t live, fx_t S_in, int64_t p0,
+                      const ScanParams &prm, Emit &emit, Ex &ex, fx_t &preM, int64_t &prePk,
+                      int &first_zero) {
+  fx_t S = S_in;
+  fx_t M = -(((fx_t)1) << 126);
+  int64_t pk = -1, beg = -1;
+  bool started = false;  // a start happened inside this chunk
+  first_zero = -1;
+  preM = M; prePk = -1;
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) {
+    fx_t Sn = 0;
+    if (live & (1u << j)) {
+      Sn = S + (fx_t)s[j];
+      Sn = Sn > 0 ? Sn : (fx_t)0;
+    }
+    if (S == 0 && Sn > 0) { started = true; beg = p0 + j; pk = p0 + j; M = Sn; }
+    if (Sn == 0) {
+      if (S > 0) {  // close at p0 + j
+        if (started) {
+          if (qualifies(prm, beg, pk, M)) emit(beg, pk, (int64_t)(p0 + j), M);
+        }
+      }
+      if (first_zero < 0) { first_zero = j; preM = M; prePk = pk; }
+    } else if (Sn > M) {
+      M = Sn; pk = p0 + j;
+    }
+    S = Sn;
+  }
+  if (first_zero < 0) { preM = M; prePk = pk; }
+  // segmented-scan element
+  if (S > 0) {
+    ex.open = 1;
+    ex.M = M; ex.pk = pk;
+    if (started) { ex.reset = 1; ex.beg = beg; }
+    else { ex.reset = 0; ex.beg = -1; }
+  } else {
+    ex.reset = 1; ex.open = 0; ex.M = -(((fx_t)1) << 126); ex.beg = -1; ex.pk = -1;
+  }
+}
+
+// After the exclusive segmented scan: finish the excursion that ENTERED this chunk (S_in > 0)
+// and closes at its first zero.
+template <class Emit>
+KS_HD void chunk_finish_entering(fx_t S_in, const Ex &ex_in, fx_t preM, int64_t prePk, int first_zero,
+                                 int64_t p0, const ScanParams &prm, Emit &emit) {
+  if (S_in > 0 && first_zero >= 0) {
+    fx_t M = ex_in.M;
+    int64_t pk = ex_in.pk;
+    if (preM > M) { M = preM; pk = prePk; }
+    if (qualifies(prm, ex_in.beg, pk, M)) emit(ex_in.beg, pk, (int64_t)(p0 + first_zero), M);
+  }
+}
+
+// Next-level segment spawned by a qualifying excursion (beg, pk, c): the reference restarts the
+// scan with S = 0 at pk + 1 (:281-282,303) and by the re-synchronisation lemma is back
+// on the parent trajectory at c, so the child scan covers [pk + 1, c].  Without in-scan counting a
+// child that is too short to hold a qualifying excursion is dropped.
+KS_HD bool child_segment(int64_t pk, int64_t c, uint64_t min_width, bool inscan, int64_t &start,
+                         int64_t &len) {
+  start = pk + 1;
+  len = c - pk;
+  if (inscan) return true;
+  int64_t room = c - pk - 2;  // largest possible pk' - beg' inside (pk, c)
+  return room >= 0 && (uint64_t)room >= min_width;
+}
+// chunks a segment occupies: one spare position after its end so that an excursion still open at
+// the last position is closed inside the segment's own chunks
+KS_HD int64_t segment_chunks(int64_t len) { return len / CHUNK + 1; }
+
+}  // namespace ks

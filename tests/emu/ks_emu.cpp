@@ -1,0 +1,189 @@
+// ks_emu.cpp -- HOST EMULATION of the GPU algorithm, TEST INFRASTRUCTURE ONLY.
+//
+// It drives the very same per-chunk functions the sm_100a kernels use (csrc/ks_chunk.cuh,
+// csrc/ks_rankseg.h), folding chunks left to right where the kernels use warp/block scans and a
+// decoupled look-back.  Because the scan arithmetic is exact (integer), the fold order does not
+// matter, so the emulation must agree with the GPU bit for bit.  It lets the CPU-only test tier
+// check the level-wise restatement (chunk transforms, excursion carry, restart-at-peak child
+// segments, exact rank pieces) against the oracle without a GPU.  The product never loads it.
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+
+#include "../../kmer_spans_b200/csrc/ks_chunk.cuh"
+#include "../../kmer_spans_b200/csrc/ks_layout.h"
+#include "../../kmer_spans_b200/csrc/ks_rankseg.h"
+
+using namespace ks;
+
+static void load_words(const uint8_t *buf, int64_t p0, uint32_t w[8]) {
+  memcpy(w, buf + p0 - 16, 32);
+}
+
+extern "C" {
+
+int64_t emu_layout_total(const int64_t *lens, int nseq, int64_t *starts) {
+  return ks_layout_total(lens, nseq, starts);
+}
+
+// counting pass over the whole buffer
+void emu_count(const uint8_t *buf, int64_t ntot, int k, int32_t *counts, uint64_t *nwords) {
+  uint32_t kmask = (1u << (2 * k)) - 1u;
+  uint64_t n = 0;
+  for (int64_t p0 = 16; p0 < ntot; p0 += 16) {
+    uint32_t w[8], code[16], counted;
+    load_words(buf, p0, w);
+    uint32_t next = (p0 + 16 < ntot + KS_SLACK) ? buf[p0 + 16] : 0;
+    decode_count(w, next, k, kmask, code, counted);
+    for (int j = 0; j < 16; ++j)
+      if (counted & (1u << j)) { counts[code[j]]++; ++n; }
+  }
+  *nwords = n;
+}
+
+// exact ranks: stable order, run-length groups, linear pieces, closed-form evaluation
+void emu_rank_exact(const int32_t *counts, int k, double total, double *ranks) {
+  size_t n = (size_t)1 << (2 * k);
+  if (total == 0) {
+    for (size_t i = 0; i < n; ++i) ranks[i] = NAN;
+    ranks[0] = 0;
+    return;
+  }
+  std::vector<uint32_t> idx(n);
+  for (size_t i = 0; i < n; ++i) idx[i] = (uint32_t)i;
+  std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return counts[a] < counts[b]; });
+  std::vector<uint32_t> gcount;
+  std::vector<uint64_t> gstart;
+  for (size_t i = 0; i < n; ++i)
+    if (i == 0 || counts[idx[i]] != counts[idx[i - 1]]) { gcount.push_back((uint32_t)counts[idx[i]]); gstart.push_back(i); }
+  gstart.push_back(n);
+  std::vector<uint32_t> seg_first;
+  std::vector<RankSeg> segs;
+  build_rank_segments(gcount.data(), gstart.data(), gcount.size(), total, seg_first, segs);
+  size_t g = 0;
+  for (size_t p = 0; p < n; ++p) {
+    while (gstart[g + 1] <= p) ++g;
+    uint64_t j = p - gstart[g];
+    uint32_t lo = seg_first[g], hi = seg_first[g + 1];
+    // last piece with j0 <= j
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (segs[mid].j0 <= j) lo = mid; else hi = mid; }
+    ranks[idx[p]] = fma((double)(j - segs[lo].j0), segs[lo].inc, segs[lo].x0);
+  }
+}
+
+int emu_num_rank_segments(const int32_t *counts, int k, double total) {
+  size_t n = (size_t)1 << (2 * k);
+  std::vector<int32_t> c(counts, counts + n);
+  std::sort(c.begin(), c.end());
+  std::vector<uint32_t> gcount;
+  std::vector<uint64_t> gstart;
+  for (size_t i = 0; i < n; ++i)
+    if (i == 0 || c[i] != c[i - 1]) { gcount.push_back((uint32_t)c[i]); gstart.push_back(i); }
+  gstart.push_back(n);
+  std::vector<uint32_t> seg_first;
+  std::vector<RankSeg> segs;
+  build_rank_segments(gcount.data(), gstart.data(), gcount.size(), total, seg_first, segs);
+  return (int)segs.size();
+}
+
+struct Rec { int64_t beg, pk, c; fx_t M; };
+struct Emit {
+  std::vector<Rec> *out;
+  void operator()(int64_t beg, int64_t pk, int64_t c, fx_t M) { out->push_back({beg, pk, c, M}); }
+};
+
+// Returns 0, or 1 when a weight is +inf / >= 2^40 (rejected by the product too).
+// Outputs (malloc'ed, caller frees with emu_free): beg, pk (global positions), score.
+int emu_scan(const uint8_t *buf, int64_t ntot, int k, const double *W, double thr, uint64_t min_width,
+             double min_score, int32_t *inscan, int64_t *n_out, int64_t **beg_out, int64_t **pk_out,
+             double **score_out, int *levels_out, int64_t *revisits_out) {
+  size_t nk = (size_t)1 << (2 * k);
+  uint32_t kmask = (uint32_t)(nk - 1);
+  // table: w = fl(W - thr) as the reference computes it (:268), then exact fixed point
+  double wmax = 0;
+  for (size_t i = 0; i < nk; ++i) {
+    double w = W[i] - thr;
+    if (w >= 0x1p40) return 1;
+    if (w == w && w > -0x1p40 && fabs(w) > wmax) wmax = fabs(w);
+  }
+  int qs = qs_for_max(wmax);
+  std::vector<int64_t> wfx(nk);
+  for (size_t i = 0; i < nk; ++i) wfx[i] = wfx_from_double(W[i] - thr, qs);
+  ScanParams prm;
+  prm.min_width = min_width;
+  prm.min_units = fx_ceil_units(min_score, qs);
+
+  std::vector<Rec> all;
+  std::vector<std::pair<int64_t, int64_t>> segs;  // start, len
+  segs.push_back({16, ntot - 16});
+  int level = 0;
+  int64_t revisits = 0;
+  while (!segs.empty()) {
+    std::vector<Rec> recs;
+    Emit emit{&recs};
+    for (auto &sg : segs) {
+      int64_t nchunks = (level == 0) ? sg.second / 16 : segment_chunks(sg.second);
+      fx_t S = 0;
+      Ex E = ex_identity();
+      E.reset = 1; E.open = 0;
+      for (int64_t ci = 0; ci < nchunks; ++ci) {
+        int64_t p0 = sg.first + 16 * ci;
+        int64_t rem = sg.first + sg.second - p0;
+        int n_in = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
+        uint32_t w[8], code[16], scored;
+        load_words(buf, p0, w);
+        decode_scan(w, k, kmask, n_in, code, scored);
+        int64_t s[16];
+        uint32_t live = 0;
+        for (int j = 0; j < 16; ++j) {
+          s[j] = 0;
+          if (scored & (1u << j)) {
+            if (inscan) inscan[code[j]]++;
+            if (level > 0) ++revisits;
+            int64_t v = wfx[code[j]];
+            if (v != WFX_KILL) { s[j] = v; live |= 1u << j; }
+          }
+        }
+        Xf f = chunk_transform(s, live);
+        Ex ex;
+        fx_t preM;
+        int64_t prePk;
+        int fz;
+        chunk_walk(s, live, S, p0, prm, emit, ex, preM, prePk, fz);
+        chunk_finish_entering(S, E, preM, prePk, fz, p0, prm, emit);
+        S = xf_apply(f, S);
+        E = ex_combine(E, ex);
+      }
+    }
+    segs.clear();
+    for (auto &r : recs) {
+      int64_t st, ln;
+      if (child_segment(r.pk, r.c, min_width, inscan != nullptr, st, ln)) segs.push_back({st, ln});
+      all.push_back(r);
+    }
+    ++level;
+    if (level > 100000) break;
+  }
+  std::sort(all.begin(), all.end(), [](const Rec &a, const Rec &b) { return a.beg < b.beg; });
+  int64_t n = (int64_t)all.size();
+  *n_out = n;
+  *beg_out = (int64_t *)malloc(sizeof(int64_t) * (n + 1));
+  *pk_out = (int64_t *)malloc(sizeof(int64_t) * (n + 1));
+  *score_out = (double *)malloc(sizeof(double) * (n + 1));
+  for (int64_t i = 0; i < n; ++i) {
+    (*beg_out)[i] = all[i].beg;
+    (*pk_out)[i] = all[i].pk;
+    (*score_out)[i] = fx_to_double(all[i].M, qs);
+  }
+  if (levels_out) *levels_out = level;
+  if (revisits_out) *revisits_out = revisits;
+  return 0;
+}
+
+void emu_free(void *p) { free(p); }
+
+double emu_fx_roundtrip(double d, int qs) { return fx_to_double((fx_t)wfx_from_double(d, qs), qs); }
+}

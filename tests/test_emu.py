@@ -1,0 +1,161 @@
+"""CPU tier: the level-wise, exact-fixed-point restatement the kernels implement (driven through
+tests/emu, which folds the SAME per-chunk functions the kernels use) against the oracle."""
+import numpy as np
+import pytest
+
+from kmer_spans_b200 import synth
+from tests.emu.emu import Emu
+from tests.test_oracle import planted, rand_seq
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return Emu()
+
+
+def assert_spans(a, b, exact_scores):
+    assert a["pos"].tolist() == b["pos"].tolist()
+    if exact_scores:
+        assert a["score"].tobytes() == b["score"].tobytes()
+    else:
+        # spec tolerance is 1e-6 relative (BASELINE.json north_star); the exact sum differs from the
+        # reference's sequentially rounded sum by its accumulated rounding only (~1e-12 on 1 Mb excursions)
+        np.testing.assert_allclose(a["score"], b["score"], rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 11])
+def test_emu_counts(emu, oracle, k):
+    rng = np.random.default_rng(500 + k)
+    for trial in range(25):
+        seqs = [rand_seq(rng, int(rng.integers(0, 300)), p_n=rng.choice([0, 0.05, 0.3]),
+                         alphabet=rng.choice([b"ACGT", b"ACGTacgtRYKMSWBDHVUu-*."]))
+                for _ in range(int(rng.integers(1, 6)))]
+        seqs += [b"ACGTACGTACGTACGTACGT"[:k], b"NN" + b"ACGTACGTACGTACGTACGT"[:k],
+                 b"ACGTACGTACGTACGTACGT"[:k] + b"N", b"ACGTACGTACGTACGTACGT"[:k + 1], b""]
+        n1, c1 = oracle.kmer_counts(seqs, k)
+        n2, c2 = emu.count(seqs, k)
+        # the oracle skips sequences shorter than k up front; such sequences hold no k-mer anyway
+        assert n1 == n2
+        assert (c1 == c2).all()
+
+
+@pytest.mark.parametrize("k", [2, 4, 6, 8, 10])
+def test_emu_ranks_bitexact(emu, oracle, ref, k):
+    rng = np.random.default_rng(600 + k)
+    for trial in range(6):
+        s = planted(rng, int(rng.integers(4 ** min(k, 6), 60 * 4 ** min(k, 6))))
+        n, c = oracle.kmer_counts(s, k)
+        if n == 0:
+            continue
+        a = emu.rank(c, k, n)
+        assert a.tobytes() == oracle.rank(c, k, n).tobytes()
+        assert a.tobytes() == ref.rank_kmers_w(c, k, n).tobytes()
+
+
+def test_emu_ranks_adversarial_counts(emu, oracle):
+    """count tables built to stress the linear-piece construction: huge tie groups, half-way
+    addends, binade crossings, tiny and huge totals"""
+    rng = np.random.default_rng(9)
+    k = 9
+    n = 4 ** k
+    for trial in range(40):
+        kind = trial % 8
+        if kind == 0:
+            c = np.full(n, int(rng.integers(1, 5)), np.int32)
+        elif kind == 1:
+            c = rng.poisson(rng.uniform(0.2, 30), n).astype(np.int32)
+        elif kind == 2:
+            c = (rng.pareto(1.2, n) * 3).astype(np.int32)
+        elif kind == 3:
+            c = np.zeros(n, np.int32); c[rng.integers(0, n, 50)] = rng.integers(1, 2 ** 20, 50)
+        elif kind == 4:
+            c = (2 ** rng.integers(0, 12, n)).astype(np.int32)
+        elif kind == 5:
+            c = rng.integers(0, 3, n).astype(np.int32)
+        elif kind == 6:
+            c = np.ones(n, np.int32); c[: n // 2] = 3
+        else:
+            c = rng.integers(0, 2 ** 31 - 1, n).astype(np.int32) // int(rng.integers(1, 2 ** 20))
+        total = float(c.astype(np.int64).sum())
+        if kind == 4:
+            total = float(2 ** int(rng.integers(20, 40)))  # power-of-two totals give half-way addends
+        if total == 0:
+            continue
+        a = emu.rank(c, k, total)
+        b = oracle.rank(c, k, total)
+        assert a.tobytes() == b.tobytes(), (trial, kind)
+        assert emu.num_rank_segments(c, k, total) < 40 * (len(np.unique(c)) + 64)
+
+
+def test_fx_roundtrip(emu):
+    rng = np.random.default_rng(3)
+    for qs in (62, 58, 50, 30):
+        lim = 2.0 ** (62 - qs)
+        x = rng.uniform(-lim, lim, 2000) * rng.choice([1, 1e-3, 1e-6], 2000)
+        x = x[np.abs(x) < lim]
+        y = np.array([emu.lib.emu_fx_roundtrip(float(v), qs) for v in x])
+        assert np.all(np.abs(x - y) <= 2.0 ** -qs)
+        big = x[np.abs(x) >= lim * 2.0 ** -9]
+        yb = np.array([emu.lib.emu_fx_roundtrip(float(v), qs) for v in big])
+        assert (big == yb).all()  # exact whenever the double's last bit is >= 2^-qs
+
+
+CASES = [(2, 0.5, 20, 10), (3, 0.75, 20, 10), (4, 0.75, 5, 2), (5, 0.5, 0, 0), (6, 0.6, 10, 3),
+         (8, 0.75, 100, 20), (4, 0.5, -1, 0), (3, 0.9, 0, 0.5), (7, 0.5, 3, 1), (10, 0.75, 30, 5)]
+
+
+@pytest.mark.parametrize("k,thr,mw,ms", CASES)
+def test_emu_low_comp_vs_oracle(emu, oracle, k, thr, mw, ms):
+    rng = np.random.default_rng(700 + k)
+    for trial in range(10):
+        seqs = [planted(rng, int(rng.integers(50, 8000))) for _ in range(int(rng.integers(1, 5)))]
+        if trial % 3 == 0:
+            seqs.insert(1, b"ACG"[: k - 1])
+        o = oracle.low_comp(seqs, k, mw, ms, thr)
+        e = emu.scan(seqs, k, o["ranks"], thr, mw, ms)
+        assert_spans(e, o, exact_scores=False)
+
+
+@pytest.mark.parametrize("k", [2, 5, 8])
+def test_emu_kmer_regions_vs_oracle(emu, oracle, k):
+    """user weights through the kmer_regions_r semantics: threshold 0, in-scan counts (T8)"""
+    rng = np.random.default_rng(800 + k)
+    for trial in range(12):
+        seqs = [planted(rng, int(rng.integers(50, 6000))) for _ in range(int(rng.integers(1, 4)))]
+        kind = trial % 4
+        if kind == 0:
+            W = rng.choice([-1.0, 1.0], 4 ** k, p=[0.7, 0.3])
+        elif kind == 1:
+            W = rng.normal(-0.3, 1.0, 4 ** k)
+        elif kind == 2:
+            n, c = oracle.kmer_counts(seqs, k)
+            W = oracle.scores(c, k, n, 2)          # +-1 around the median: long excursions, deep restarts
+        else:
+            W = rng.normal(-0.2, 1.0, 4 ** k)
+            W[rng.integers(0, 4 ** k, 3)] = np.nan  # NaN weights clamp the state to 0 (reference :270)
+            W[rng.integers(0, 4 ** k, 2)] = -np.inf
+        mw, ms = [(0, 0), (10, 3), (30, 8)][trial % 3]
+        o = oracle.kmer_regions(seqs, k, W, mw, ms)
+        e = emu.scan(seqs, k, W, 0.0, mw, ms, inscan=True)
+        assert_spans(e, o, exact_scores=(kind in (0, 2)))
+        assert (e["counts"] == o["counts"]).all()
+
+
+def test_emu_config1_both_modes(emu, oracle):
+    """BASELINE.json configs[0] at full size: +-1 mode (giant excursions) and rank mode"""
+    seq = synth.config1()[0].tobytes()
+    n, c = oracle.kmer_counts(seq, 8)
+    W = oracle.scores(c, 8, n, 2)
+    o = oracle.kmer_regions([seq], 8, W, 100, 20)
+    e = emu.scan([seq], 8, W, 0.0, 100, 20, inscan=True)
+    assert_spans(e, o, exact_scores=True)
+    assert (e["counts"] == o["counts"]).all()
+    o = oracle.low_comp([seq], 8, 100, 20, 0.75)
+    e = emu.scan([seq], 8, o["ranks"], 0.75, 100, 20)
+    assert len(o["pos"]) > 20
+    assert_spans(e, o, exact_scores=False)
+    # log2 mode
+    W = oracle.scores(c, 8, n, 1)
+    o = oracle.kmer_regions([seq], 8, W, 100, 20)
+    e = emu.scan([seq], 8, W, 0.0, 100, 20)
+    assert_spans(e, o, exact_scores=False)

@@ -1,0 +1,174 @@
+"""Pins the CPU oracle (oracle/ks_oracle.c): against the reference's own known answers and
+against the unmodified reference compiled into oracle/_ref (bit-exact, doubles included)."""
+import numpy as np
+import pytest
+
+from kmer_spans_b200 import synth
+
+
+def rand_seq(rng, n, p_n=0.0, alphabet=b"ACGT"):
+    s = np.frombuffer(alphabet, np.uint8)[rng.integers(0, len(alphabet), n)]
+    if p_n > 0:
+        # N runs of random length
+        i = 0
+        while i < n:
+            if rng.random() < p_n:
+                ln = int(rng.integers(1, 12))
+                s[i:i + ln] = ord("N") if rng.random() < 0.7 else ord("n")
+                i += ln
+            i += int(rng.integers(1, 40))
+    return s.tobytes()
+
+
+def planted(rng, n):
+    s = np.frombuffer(rand_seq(rng, n), np.uint8).copy()
+    for _ in range(max(1, n // 400)):
+        unit = np.frombuffer(rand_seq(rng, int(rng.integers(1, 9))), np.uint8)
+        ln = int(rng.integers(20, 200))
+        p = int(rng.integers(0, max(1, n - ln)))
+        s[p:p + ln] = np.tile(unit, ln // len(unit) + 1)[:ln][: len(s[p:p + ln])]
+    for _ in range(n // 300):
+        p = int(rng.integers(0, n))
+        s[p:p + int(rng.integers(1, 8))] = ord("N")
+    return s.tobytes()
+
+
+# ---- the reference's own known answers ------------------------------------------------------
+def test_ka1_dinucleotide_counts(oracle):
+    """test.R:365-375: CGCCAATGCG, k=2."""
+    n, c = oracle.kmer_counts(b"CGCCAATGCG", 2)
+    names = [oracle.kmer_seq(2, i) for i in range(16)]
+    got = {a: int(b) for a, b in zip(names, c) if b}
+    assert got == {"CG": 2, "GC": 2, "CC": 1, "CA": 1, "AA": 1, "AT": 1, "TG": 1}
+    assert n == 9
+
+
+def test_ka2_n_splitting(oracle):
+    """test.R:66-77: counts(seq + N*36 + seq) == 2 * counts(seq), k=2."""
+    rng = np.random.default_rng(7)
+    s = rand_seq(rng, 5000)
+    _, c1 = oracle.kmer_counts(s, 2)
+    _, c2 = oracle.kmer_counts(s + b"N" * 36 + s, 2)
+    assert (c2 == 2 * c1).all()
+
+
+def test_ka3_kmer_order(oracle):
+    """kmer_spans.R:81-83: order A, C, T, G."""
+    assert [oracle.kmer_seq(2, i) for i in range(16)] == \
+        "AA AC AT AG CA CC CT CG TA TC TT TG GA GC GT GG".split()
+    assert oracle.kmer_seq(3, 0b100111) == "TCG"
+
+
+def test_t6_exact_k_tail(oracle):
+    assert oracle.kmer_counts(b"ACG", 3)[0] == 0
+    assert oracle.kmer_counts(b"ACGNNACG", 3)[0] == 1
+    assert oracle.kmer_counts(b"ACGT", 3)[0] == 2
+
+
+def test_t7_coordinates(oracle):
+    """(AG)x50 + random, k=2, +-1 weights -> start=2, end=101, score=100."""
+    W = -np.ones(16)
+    names = [oracle.kmer_seq(2, i) for i in range(16)]
+    W[names.index("AG")] = 1
+    W[names.index("GA")] = 1
+    s = b"AG" * 50 + b"CCCCCCCCCCCCCCCCCCCCCCCCCCCCCCCC"
+    r = oracle.kmer_regions([s], 2, W, 20, 10)
+    assert r["pos"].tolist() == [[0, 2, 100]] or r["pos"].tolist() == [[0, 2, 101]]
+    assert r["score"][0, 0] in (99.0, 100.0)
+
+
+# ---- restatement vs the compiled reference ---------------------------------------------------
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8])
+def test_counts_match_reference(oracle, ref, k):
+    rng = np.random.default_rng(100 + k)
+    for trial in range(40):
+        n = int(rng.integers(0, 400))
+        seqs = [rand_seq(rng, int(rng.integers(0, max(1, n))), p_n=rng.choice([0, 0.05, 0.3]),
+                         alphabet=rng.choice([b"ACGT", b"ACGTacgtRYKMSWBDHVUu-*."]))
+                for _ in range(int(rng.integers(1, 5)))]
+        if trial % 5 == 0:
+            seqs.append(b"ACGTACGTACGTACGTACGT"[:k])           # exactly k, at the terminator
+            seqs.append(b"N" * 3 + b"ACGTACGTACGTACGTACGT"[:k])
+            seqs.append(b"ACGTACGTACGTACGTACGT"[:k] + b"N")   # exactly k, followed by N
+            seqs.append(b"AC"[: max(0, k - 1)] + b"NNN")       # T10 shape
+        n1, c1 = oracle.kmer_counts(seqs, k)
+        got = ref.call_kmer_counts(seqs, k) if seqs else None
+        assert n1 == got["n"]
+        assert (c1 == got["counts"]).all()
+
+
+@pytest.mark.parametrize("k", [2, 4, 6, 8, 10])
+def test_ranks_match_reference_bitexact(oracle, ref, k):
+    rng = np.random.default_rng(200 + k)
+    for trial in range(6):
+        s = planted(rng, int(rng.integers(4 ** min(k, 6), 40 * 4 ** min(k, 6))))
+        n, c = oracle.kmer_counts(s, k)
+        if n == 0:
+            continue
+        a = oracle.rank(c, k, n)
+        b = ref.rank_kmers_w(c, k, n)
+        assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("k,thr,mw,ms", [(2, 0.5, 20, 10), (3, 0.75, 20, 10), (4, 0.75, 5, 2),
+                                         (5, 0.5, 0, 0), (6, 0.6, 10, 3), (8, 0.75, 100, 20),
+                                         (4, 0.5, -1, 0), (3, 0.9, 0, 0.5)])
+def test_low_comp_matches_reference_bitexact(oracle, ref, k, thr, mw, ms):
+    rng = np.random.default_rng(300 + k)
+    for trial in range(12):
+        seqs = [planted(rng, int(rng.integers(50, 6000))) for _ in range(int(rng.integers(1, 4)))]
+        if trial % 3 == 0:
+            seqs.insert(1, b"ACG"[: k - 1])  # skipped (len < k), seq_id must still advance
+        a = oracle.low_comp(seqs, k, mw, ms, thr)
+        b = ref.call_kmer_low_comp_regions(seqs, k, mw, ms, thr)
+        assert (a["n"] == b["n"]).all()
+        assert (a["counts"] == b["counts"]).all()
+        assert a["ranks"].tobytes() == b["ranks"].tobytes()
+        assert a["pos"].tolist() == b["pos"].tolist()
+        assert a["score"].tobytes() == b["score"].tobytes()
+
+
+@pytest.mark.parametrize("k", [2, 5, 8])
+def test_kmer_regions_matches_reference_bitexact(oracle, ref, k):
+    rng = np.random.default_rng(400 + k)
+    for trial in range(12):
+        seqs = [planted(rng, int(rng.integers(50, 5000))) for _ in range(int(rng.integers(1, 4)))]
+        kind = trial % 3
+        if kind == 0:
+            W = rng.choice([-1.0, 1.0], 4 ** k, p=[0.7, 0.3])
+        elif kind == 1:
+            W = rng.normal(-0.3, 1.0, 4 ** k)
+        else:
+            n, c = oracle.kmer_counts(seqs, k)
+            W = oracle.scores(c, k, n, 2)
+        mw, ms = [(0, 0), (10, 3), (30, 8)][trial % 3]
+        a = oracle.kmer_regions(seqs, k, W, mw, ms)
+        b = ref.call_kmer_regions_r(seqs, k, W, mw, ms)
+        assert a["n"] == b["n"]
+        assert (a["counts"] == b["counts"]).all()   # in-scan counts incl. rescans
+        assert a["pos"].tolist() == b["pos"].tolist()
+        assert a["score"].tobytes() == b["score"].tobytes()
+
+
+def test_config1_against_reference(oracle, ref):
+    """BASELINE.json configs[0] (1 Mb, k=8, +-1 mode through kmer_regions_r), full size."""
+    seq = synth.config1()[0].tobytes()
+    n, c = oracle.kmer_counts(seq, 8)
+    W = oracle.scores(c, 8, n, 2)
+    a = oracle.kmer_regions([seq], 8, W, 100, 20)
+    b = ref.call_kmer_regions_r([seq], 8, W, 100, 20)
+    assert len(a["pos"]) > 20
+    assert a["pos"].tolist() == b["pos"].tolist()
+    assert a["score"].tobytes() == b["score"].tobytes()
+    assert (a["counts"] == b["counts"]).all()
+    lc_a = oracle.low_comp([seq], 8, 100, 20, 0.75)
+    lc_b = ref.call_kmer_low_comp_regions([seq], 8, 100, 20, 0.75)
+    assert lc_a["pos"].tolist() == lc_b["pos"].tolist()
+    assert lc_a["ranks"].tobytes() == lc_b["ranks"].tobytes()
+
+
+def test_reference_error_paths(ref):
+    with pytest.raises(RuntimeError, match="threshold must be between"):
+        ref.call_kmer_low_comp_regions([b"ACGT"], 2, 1, 1.0, 1.0)
+    with pytest.raises(RuntimeError, match="positive integer"):
+        ref.call_kmer_counts([b"ACGT"], 0)
