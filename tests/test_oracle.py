@@ -157,12 +157,13 @@ def test_config1_against_reference(oracle, ref):
     W = oracle.scores(c, 8, n, 2)
     a = oracle.kmer_regions([seq], 8, W, 100, 20)
     b = ref.call_kmer_regions_r([seq], 8, W, 100, 20)
-    assert len(a["pos"]) > 20
+    assert len(a["pos"]) >= 2   # +-1 around the median has no negative drift: run-sized spans
     assert a["pos"].tolist() == b["pos"].tolist()
     assert a["score"].tobytes() == b["score"].tobytes()
     assert (a["counts"] == b["counts"]).all()
     lc_a = oracle.low_comp([seq], 8, 100, 20, 0.75)
     lc_b = ref.call_kmer_low_comp_regions([seq], 8, 100, 20, 0.75)
+    assert len(lc_a["pos"]) > 20
     assert lc_a["pos"].tolist() == lc_b["pos"].tolist()
     assert lc_a["ranks"].tobytes() == lc_b["ranks"].tobytes()
 
