@@ -1,0 +1,131 @@
+/* kspans.h -- C ABI of the B200-native kmer_spans hot path (count -> score -> scan -> spans).
+ *
+ * Plain C: pointers and sizes only, no R, torch or C++ types.  The shared library that exports
+ * these symbols (kmer_spans_b200/csrc/libkspans_cuda.so) contains hand-written sm_100a kernels
+ * and NO CPU fallback: every compute entry point returns KS_ERR_CUDA when no device is usable.
+ *
+ * Each entry point names the reference interface it replaces
+ * (file:line in lmjakt/kmer_spans, src/kmer_spans.c unless stated otherwise).
+ * INTEGRATION.md shows the .Call glue (r/src/kmer_spans_glue.c) that binds them into R.
+ *
+ * Conventions shared by all calls
+ *  - sequences are (pointer, length) pairs; a NUL byte inside [ptr, ptr+len) is treated as the
+ *    string terminator the reference stops at (:121,140,261) for that run (R strings never hold one)
+ *  - only 'N'/'n' break a run; every other byte maps through (c>>1)&3: A0 C1 T2 G3   (:34-35)
+ *  - sequences shorter than k are skipped but keep their 0-based seq_id             (:478,533,595)
+ *  - k in 1..15; count tables are int32[4^k], score tables double[4^k], index = 2-bit code
+ *  - span coordinates follow the reference exactly: int32, 0-based seq_id,
+ *    start/end = 1-based position of the last base of the first-positive / peak k-mer
+ */
+#ifndef KSPANS_H
+#define KSPANS_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ks_ctx ks_ctx;       /* one device, one stream, cached scratch memory */
+typedef struct ks_seqset ks_seqset; /* sequences resident in HBM   */
+
+enum {
+  KS_OK = 0,
+  KS_ERR_ARG = 1,      /* argument rejected; message mirrors the reference's error() text where one exists */
+  KS_ERR_CUDA = 2,     /* no device / CUDA runtime failure: there is no CPU path */
+  KS_ERR_RANGE = 3,    /* a weight is +inf or >= 2^40 (exact fixed-point scan range) */
+  KS_ERR_NOMEM = 4
+};
+
+/* score modes of README.md:27-49.  KS_MODE_RANK is the only one the reference codes (:268). */
+enum { KS_MODE_RANK = 0, KS_MODE_LOG2 = 1, KS_MODE_SIGN = 2, KS_MODE_RANK_REL = 3 };
+
+/* Spans in the reference's own layout (struct seq_regions :46-58, as copied out at :541-542):
+ * pos   = int32[3*n], column-major 3 x n : seq_id, start, end
+ * score = double[2*n], column-major 2 x n : peak score, 0 ("entropy", always 0 :280)
+ * Order = reference discovery order = ascending (seq_id, start).  Library-owned. */
+typedef struct {
+  int32_t *pos;
+  double *score;
+  size_t n;
+} ks_spans;
+void ks_spans_free(ks_spans *s);
+
+/* -------- context ------------------------------------------------------------------------- */
+/* CUDA is initialised lazily here, never at library load (R may fork). device < 0
+ * = current device. */
+int ks_ctx_create(ks_ctx **out, int device);
+void ks_ctx_destroy(ks_ctx *ctx);
+const char *ks_last_error(const ks_ctx *ctx); /* ctx may be NULL: error of the last failed ks_ctx_create */
+void *ks_ctx_stream(ks_ctx *ctx);             /* cudaStream_t all kernels of this ctx are launched on */
+int ks_ctx_sync(ks_ctx *ctx);
+/* kernels launched through this ctx since creation (or since the last reset) */
+uint64_t ks_ctx_launches(const ks_ctx *ctx);
+void ks_ctx_reset_launches(ks_ctx *ctx);
+
+/* -------- host-buffer entry points: one per reference .Call on the path -------------------- */
+
+/* kmer_counts (:453-487): counts_out[4^k] (overwritten), *n_words = number of words counted. */
+int ks_kmer_counts(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,
+                   int32_t *counts_out, double *n_words);
+
+/* kmer_regions_r (:490-546): user weights W[4^k], threshold 0, in-scan counts that miss the last
+ * k-mer of every run and double-count rescanned positions.
+ * *nuc = sum of the lengths of the sequences with length >= k (:535). min_width is the R integer;
+ * negative values wrap to huge exactly as the reference's size_t conversion (:243,279). */
+int ks_kmer_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,
+                    const double *W, int min_width, double min_score, double *nuc,
+                    int32_t *inscan_counts_out, ks_spans *out);
+
+/* kmer_low_comp_regions (:548-621): counts -> weighted ranks (:189-202, stable (count,index) order,
+ * rank of the first k-mer in that order = 0) -> scan with score = rank - thr, 0 < thr < 1.
+ * n_out[0] = words counted, n_out[1] = 0 (:613).  counts_out / ranks_out may be NULL (not copied back). */
+int ks_kmer_low_comp_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq,
+                             int k, int min_width, double min_score, double thr, double n_out[2],
+                             int32_t *counts_out, double *ranks_out, ks_spans *out);
+
+/* Extension (no reference entry point; the reference reaches these modes by computing a weight
+ * vector in R and calling kmer_regions_r, kmer_spans.R:41-52): counts -> scores(mode) -> scan with
+ * threshold thr, everything device-resident.  scores_out may be NULL. */
+int ks_kmer_mode_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,
+                         int mode, double param, double thr, int min_width, double min_score,
+                         double *n_words, int32_t *counts_out, double *scores_out, ks_spans *out);
+
+/* rank_kmers_w (:189-202) and the README modes as a table-to-table operator on host buffers. */
+int ks_kmer_scores(ks_ctx *ctx, int k, const int32_t *counts, double total, int mode, double param,
+                   double *scores_out);
+
+/* kmer_seq (:161-171): index -> k-mer string (A,C,T,G order); host only, no device needed. */
+int ks_kmer_seq(int k, uint64_t code, char *out /* k+1 bytes */);
+
+/* -------- device-resident sequence sets (upload once, scan many times) --------------------- */
+int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, ks_seqset **out);
+/* wrap a buffer ALREADY in device memory, laid out as csrc/ks_layout.h describes
+ * (d_buf must stay valid; starts = nseq+1 host offsets as returned by ks_layout) */
+int ks_seqset_wrap(ks_ctx *ctx, const void *d_buf, int64_t total_bytes, const int64_t *lens, int nseq,
+                   ks_seqset **out);
+void ks_seqset_free(ks_seqset *s);
+int64_t ks_seqset_bases(const ks_seqset *s);      /* sum of lengths */
+int64_t ks_seqset_buffer_bytes(const ks_seqset *s);
+
+/* Stage-level device API (what bench.py times, and what the multi-GPU host composes around its
+ * collectives).  d_* arguments are DEVICE pointers owned by the caller. */
+int ks_dev_count(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts /*4^k, zeroed here*/,
+                 double *n_words);
+int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int mode, double param,
+                  double *d_scores /*4^k*/);
+int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
+                double min_score, int32_t *d_inscan_or_null, ks_spans *host_out_or_null,
+                uint64_t *n_spans);
+/* count -> scores(mode) -> scan, all resident; spans stay on the device unless host_out != NULL */
+int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double param, double thr,
+                    int min_width, double min_score, int32_t *d_counts, double *d_scores,
+                    double *n_words, ks_spans *host_out_or_null, uint64_t *n_spans);
+
+/* diagnostics of the last scan on this ctx: restart levels run and positions visited beyond level 0 */
+void ks_ctx_scan_stats(const ks_ctx *ctx, int *levels, uint64_t *revisited_chunks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

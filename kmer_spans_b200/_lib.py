@@ -1,0 +1,77 @@
+"""ctypes binding of the C ABI in include/kspans.h (kmer_spans_b200/csrc/libkspans_cuda.so).
+
+The library is the product: hand-written sm_100a kernels, no CPU path.  Loading works anywhere
+(the CPU test tier checks the exported symbols); creating a Context needs a CUDA device and
+raises otherwise.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libkspans_cuda.so")
+
+KS_OK, KS_ERR_ARG, KS_ERR_CUDA, KS_ERR_RANGE, KS_ERR_NOMEM = 0, 1, 2, 3, 4
+MODE_RANK, MODE_LOG2, MODE_SIGN, MODE_RANK_REL = 0, 1, 2, 3
+
+
+class KsSpans(C.Structure):
+    _fields_ = [("pos", C.POINTER(C.c_int32)), ("score", C.POINTER(C.c_double)), ("n", C.c_size_t)]
+
+
+class KspansError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("kspans error %d: %s" % (code, msg))
+        self.code = code
+        self.message = msg
+
+
+_lib = None
+
+_vp, _i, _d, _i64 = C.c_void_p, C.c_int, C.c_double, C.c_int64
+_pd = C.POINTER(C.c_double)
+_pu64 = C.POINTER(C.c_uint64)
+_SEQS = [C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.c_int]
+
+SIGNATURES = {
+    "ks_spans_free": (None, [C.POINTER(KsSpans)]),
+    "ks_ctx_create": (_i, [C.POINTER(_vp), _i]),
+    "ks_ctx_destroy": (None, [_vp]),
+    "ks_last_error": (C.c_char_p, [_vp]),
+    "ks_ctx_stream": (_vp, [_vp]),
+    "ks_ctx_sync": (_i, [_vp]),
+    "ks_ctx_launches": (C.c_uint64, [_vp]),
+    "ks_ctx_reset_launches": (None, [_vp]),
+    "ks_ctx_scan_stats": (None, [_vp, C.POINTER(_i), _pu64]),
+    "ks_kmer_counts": (_i, [_vp] + _SEQS + [_i, _vp, _pd]),
+    "ks_kmer_regions": (_i, [_vp] + _SEQS + [_i, _vp, _i, _d, _pd, _vp, C.POINTER(KsSpans)]),
+    "ks_kmer_low_comp_regions": (_i, [_vp] + _SEQS + [_i, _i, _d, _d, _pd, _vp, _vp, C.POINTER(KsSpans)]),
+    "ks_kmer_mode_regions": (_i, [_vp] + _SEQS + [_i, _i, _d, _d, _i, _d, _pd, _vp, _vp, C.POINTER(KsSpans)]),
+    "ks_kmer_scores": (_i, [_vp, _i, _vp, _d, _i, _d, _vp]),
+    "ks_kmer_seq": (_i, [_i, C.c_uint64, C.c_char_p]),
+    "ks_seqset_upload": (_i, [_vp] + _SEQS + [C.POINTER(_vp)]),
+    "ks_seqset_wrap": (_i, [_vp, _vp, _i64, C.POINTER(C.c_int64), _i, C.POINTER(_vp)]),
+    "ks_seqset_free": (None, [_vp]),
+    "ks_seqset_bases": (_i64, [_vp]),
+    "ks_seqset_buffer_bytes": (_i64, [_vp]),
+    "ks_dev_count": (_i, [_vp, _vp, _i, _vp, _pd]),
+    "ks_dev_scores": (_i, [_vp, _i, _vp, _d, _i, _d, _vp]),
+    "ks_dev_scan": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, _vp, C.POINTER(KsSpans), _pu64]),
+    "ks_dev_pipeline": (_i, [_vp, _vp, _i, _i, _d, _d, _i, _d, _vp, _vp, _pd, C.POINTER(KsSpans), _pu64]),
+}
+
+
+def load():
+    """Load the shared library (building it in-tree if the sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = the library does not export the ABI
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,245 @@
+"""Host-side mirror of the reference's R-facing API (kmer_spans.R) on top of the C ABI.
+
+Function names, argument meaning, result fields and error behaviour follow
+/root/reference/kmer_spans.R:18-27 (kmer.counts), :41-52 (kmer.regions), :72-79
+(kmer.low.comp.regions) and :84-86 (kmer.seq), so that parity tests read like calls into the
+reference.  R is absent from the build image; the real .Call glue is r/src/kmer_spans_glue.c.
+
+Everything computes on the GPU through libkspans_cuda.so; there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KsSpans, KspansError, MODE_LOG2, MODE_RANK, MODE_RANK_REL, MODE_SIGN  # noqa: F401
+
+
+def _as_bytes_list(seq):
+    if isinstance(seq, (bytes, bytearray, str, np.ndarray)):
+        seq = [seq]
+    out = []
+    for s in seq:
+        if isinstance(s, str):
+            s = s.encode()
+        elif isinstance(s, np.ndarray):
+            s = np.ascontiguousarray(s, np.uint8)
+        out.append(s)
+    return out
+
+
+class _SeqArgs:
+    """(char**, int64*, n) view of a list of bytes / uint8 arrays, zero-copy"""
+
+    def __init__(self, seqs):
+        self.keep = seqs
+        n = len(seqs)
+        self.ptrs = (C.c_char_p * max(n, 1))()
+        self.lens = (C.c_int64 * max(n, 1))()
+        for i, s in enumerate(seqs):
+            if isinstance(s, np.ndarray):
+                self.ptrs[i] = C.cast(s.ctypes.data, C.c_char_p)
+                self.lens[i] = s.size
+            else:
+                if not isinstance(s, bytes):
+                    s = bytes(s)
+                    seqs[i] = s  # keep the converted object alive
+                self.ptrs[i] = s
+                self.lens[i] = len(s)
+        self.n = n
+
+
+def _spans_to_numpy(lib, sp):
+    n = sp.n
+    if n:
+        pos = np.ctypeslib.as_array(sp.pos, shape=(n, 3)).copy()
+        score = np.ctypeslib.as_array(sp.score, shape=(n, 2)).copy()
+    else:
+        pos = np.zeros((0, 3), np.int32)
+        score = np.zeros((0, 2), np.float64)
+    lib.ks_spans_free(C.byref(sp))
+    return pos, score
+
+
+class Context:
+    """One GPU, one stream, cached scratch (ks_ctx)."""
+
+    def __init__(self, device=-1):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.ks_ctx_create(C.byref(h), device)
+        if rc:
+            raise KspansError(rc, self.lib.ks_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ks_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise KspansError(rc, self.lib.ks_last_error(self.h).decode())
+
+    @property
+    def stream(self):
+        return self.lib.ks_ctx_stream(self.h)
+
+    def sync(self):
+        self._ck(self.lib.ks_ctx_sync(self.h))
+
+    def launches(self):
+        return int(self.lib.ks_ctx_launches(self.h))
+
+    def reset_launches(self):
+        self.lib.ks_ctx_reset_launches(self.h)
+
+    def scan_stats(self):
+        lv, rv = C.c_int(0), C.c_uint64(0)
+        self.lib.ks_ctx_scan_stats(self.h, C.byref(lv), C.byref(rv))
+        return lv.value, rv.value
+
+    # ---- mirrors of the reference's R functions -------------------------------------------
+    def kmer_counts(self, seq, k, with_f=True):
+        """kmer.counts (kmer_spans.R:18-27): list(n = c(k, n), counts, f = counts / sum(counts))"""
+        a = _SeqArgs(_as_bytes_list(seq))
+        k = int(k)
+        if not 1 <= k <= 15:
+            raise KspansError(_lib.KS_ERR_ARG, "k must be a positive integer less than 1+MAX_K")
+        counts = np.zeros(4 ** k, np.int32)
+        n = C.c_double(0)
+        self._ck(self.lib.ks_kmer_counts(self.h, a.ptrs, a.lens, a.n, k, counts.ctypes.data, C.byref(n)))
+        out = dict(n=np.array([k, n.value]), counts=counts)
+        if with_f:
+            out["f"] = counts / counts.sum()
+        return out
+
+    def kmer_regions(self, seq, k, kmer_scores, min_width, min_score, counts=True):
+        """kmer.regions (kmer_spans.R:41-52) -> kmer_regions_r.  kmer_scores is indexed by the
+        2-bit code (the order of kmer.seq(k)); the name matching of the R wrapper is the caller's."""
+        a = _SeqArgs(_as_bytes_list(seq))
+        k = int(k)
+        W = np.ascontiguousarray(kmer_scores, np.float64)
+        if not 1 <= k <= 15:
+            raise KspansError(_lib.KS_ERR_ARG, "kmer sizes larger than or equal to 16 not currently supported")
+        if W.size != 4 ** k:
+            raise KspansError(_lib.KS_ERR_ARG, "There should be a total of 4^k scores")
+        cnt = np.zeros(4 ** k, np.int32)
+        nuc = C.c_double(0)
+        sp = KsSpans()
+        self._ck(self.lib.ks_kmer_regions(self.h, a.ptrs, a.lens, a.n, k, W.ctypes.data, int(min_width),
+                                          float(min_score), C.byref(nuc), cnt.ctypes.data if counts else None,
+                                          C.byref(sp)))
+        pos, score = _spans_to_numpy(self.lib, sp)
+        return dict(n=nuc.value, counts=cnt, pos=pos, score=score)
+
+    def kmer_low_comp_regions(self, seq, k, min_w, min_score, thr=0.75, want_tables=True):
+        """kmer.low.comp.regions (kmer_spans.R:72-79): n, counts, w.rank, pos (R x 3), score (R x 2)"""
+        a = _SeqArgs(_as_bytes_list(seq))
+        k = int(k)
+        if not 1 <= k <= 15:
+            raise KspansError(_lib.KS_ERR_ARG, "k must be between 1 and 15")
+        counts = np.zeros(4 ** k, np.int32) if want_tables else None
+        ranks = np.zeros(4 ** k, np.float64) if want_tables else None
+        n = (C.c_double * 2)()
+        sp = KsSpans()
+        self._ck(self.lib.ks_kmer_low_comp_regions(
+            self.h, a.ptrs, a.lens, a.n, k, int(min_w), float(min_score), float(thr), n,
+            counts.ctypes.data if want_tables else None, ranks.ctypes.data if want_tables else None, C.byref(sp)))
+        pos, score = _spans_to_numpy(self.lib, sp)
+        return dict(n=np.array([n[0], n[1]]), counts=counts, w_rank=ranks, pos=pos, score=score)
+
+    def kmer_mode_regions(self, seq, k, mode, min_w, min_score, thr=0.0, param=float("nan"), want_tables=True):
+        """extension: counts -> scores(mode) -> scan on the device (README.md:27-49 modes)"""
+        a = _SeqArgs(_as_bytes_list(seq))
+        k = int(k)
+        if not 1 <= k <= 15:
+            raise KspansError(_lib.KS_ERR_ARG, "k must be between 1 and 15")
+        counts = np.zeros(4 ** k, np.int32) if want_tables else None
+        scores = np.zeros(4 ** k, np.float64) if want_tables else None
+        n = C.c_double(0)
+        sp = KsSpans()
+        self._ck(self.lib.ks_kmer_mode_regions(
+            self.h, a.ptrs, a.lens, a.n, k, int(mode), float(param), float(thr), int(min_w), float(min_score),
+            C.byref(n), counts.ctypes.data if want_tables else None,
+            scores.ctypes.data if want_tables else None, C.byref(sp)))
+        pos, score = _spans_to_numpy(self.lib, sp)
+        return dict(n=n.value, counts=counts, scores=scores, pos=pos, score=score)
+
+    def kmer_scores(self, counts, k, total, mode=MODE_RANK, param=float("nan")):
+        """rank_kmers_w (src/kmer_spans.c:189-202) / README modes as a table operator"""
+        counts = np.ascontiguousarray(counts, np.int32)
+        W = np.zeros(4 ** int(k), np.float64)
+        self._ck(self.lib.ks_kmer_scores(self.h, int(k), counts.ctypes.data, float(total), int(mode), float(param),
+                                         W.ctypes.data))
+        return W
+
+    # ---- device-resident -------------------------------------------------------------------
+    def upload(self, seq):
+        return SeqSet(self, _as_bytes_list(seq))
+
+
+class SeqSet:
+    """Sequences resident in HBM (ks_seqset)."""
+
+    def __init__(self, ctx, seqs):
+        self.ctx = ctx
+        a = _SeqArgs(seqs)
+        h = C.c_void_p()
+        ctx._ck(ctx.lib.ks_seqset_upload(ctx.h, a.ptrs, a.lens, a.n, C.byref(h)))
+        self.h = h
+        self.bases = int(ctx.lib.ks_seqset_bases(h))
+        self.buffer_bytes = int(ctx.lib.ks_seqset_buffer_bytes(h))
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.ks_seqset_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def kmer_seq(k):
+    """kmer.seq (kmer_spans.R:84-86): the 4^k k-mers in table order (A, C, T, G)"""
+    lib = _lib.load()
+    k = int(k)
+    if not 1 <= k <= 16:
+        raise KspansError(_lib.KS_ERR_ARG, "k_r (%d) should be smaller than MAX_K (16) and larger than 0" % k)
+    buf = C.create_string_buffer(k + 1)
+    out = []
+    for i in range(4 ** k):
+        lib.ks_kmer_seq(k, i, buf)
+        out.append(buf.value.decode())
+    return out
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+def kmer_counts(seq, k, with_f=True):
+    return default_context().kmer_counts(seq, k, with_f)
+
+
+def kmer_regions(seq, k, kmer_scores, min_width, min_score):
+    return default_context().kmer_regions(seq, k, kmer_scores, min_width, min_score)
+
+
+def kmer_low_comp_regions(seq, k, min_w, min_score, thr=0.75):
+    return default_context().kmer_low_comp_regions(seq, k, min_w, min_score, thr)

@@ -1,0 +1,848 @@
+// ks_api.cu -- C ABI (include/kspans.h) and host orchestration of the sm_100a kernels.
+//
+// Host work here is control plane only: buffer management, launch sequencing, the O(#distinct
+// counts) piece table of the exact rank closed form, and result marshaling.  Every per-base and
+// per-k-mer computation runs in the kernels of ks_kernels.cuh / ks_sort.cuh.  There is no CPU
+// compute path: without a usable device every entry point fails with KS_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/kspans.h"
+#include "ks_kernels.cuh"
+#include "ks_layout.h"
+#include "ks_rankseg.h"
+#include "ks_sort.cuh"
+
+using namespace ks;
+
+namespace {
+
+std::string g_create_error;
+
+struct DBuf {  // grow-only device buffer
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes, bool keep = false, cudaStream_t st = 0) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t ncap = bytes + bytes / 4 + 256;
+    void *np = nullptr;
+    cudaError_t e = cudaMalloc(&np, ncap);
+    if (e != cudaSuccess) return e;
+    if (keep && p && cap) {
+      e = cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { cudaFree(np); return e; }
+    }
+    if (p) cudaFree(p);
+    p = np;
+    cap = ncap;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct ks_seqset {
+  ks_ctx *ctx = nullptr;
+  uint8_t *d_buf = nullptr;  // layout of ks_layout.h
+  bool owned = false;
+  int64_t total = 0;         // bytes of the layout (multiple of 16)
+  int64_t bases = 0;
+  int nseq = 0;
+  std::vector<int64_t> lens, starts;  // starts: nseq + 1
+  int64_t *d_starts = nullptr;
+};
+
+struct ks_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int last_levels = 0;
+  uint64_t last_revisit_chunks = 0;
+  uint32_t epoch = 0;
+  unsigned int tile_base = 0;
+  bool counter_init = false;
+  // scan scratch
+  DBuf wfx, prm, xf_status, xf_agg, xf_inc, ex_status, ex_agg, ex_inc, tile_counter;
+  size_t tiles_cap = 0;
+  DBuf rec_beg, rec_pk, rec_c, rec_mhi, rec_mlo, rec_count;
+  size_t rec_cap = 0;
+  DBuf seg_start, seg_len, seg_chunks, seg_chunk0, scan_tmp;
+  DBuf sort_keys_a, sort_keys_b, sort_vals_a, sort_vals_b, sort_hist, sort_scan;
+  DBuf out_pos, out_score;
+  // score scratch
+  DBuf sc_keys_a, sc_keys_b, sc_vals_a, sc_vals_b, sc_small, sc_gcount, sc_gstart, sc_segfirst, sc_segj0,
+      sc_segx0, sc_seginc, sc_lut;
+  // staging / misc
+  void *pinned = nullptr;
+  size_t pinned_cap = 0;
+  DBuf tmp_counts, tmp_scores, tmp_inscan, nwords;
+
+  int fail(int code, const char *fmt, ...) {
+    char b[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(b, sizeof b, fmt, ap);
+    va_end(ap);
+    err = b;
+    return code;
+  }
+};
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return ctx->fail(KS_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, \
+                       __LINE__, cudaGetErrorString(e_));                                     \
+  } while (0)
+#define LAUNCHED(n) (ctx->launches += (uint64_t)(n))
+
+static inline unsigned grid_for(size_t n, int threads, unsigned cap = 148u * 16u) {
+  size_t g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (unsigned)g;
+}
+static inline unsigned blocks_exact(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+static int check_k(ks_ctx *ctx, int k) {
+  if (k < 1 || k > 15) return ctx->fail(KS_ERR_ARG, "k must be a positive integer less than 16 (got %d)", k);
+  return KS_OK;
+}
+
+// ================================================================================================
+extern "C" {
+
+void ks_spans_free(ks_spans *s) {
+  if (!s) return;
+  free(s->pos);
+  free(s->score);
+  s->pos = nullptr;
+  s->score = nullptr;
+  s->n = 0;
+}
+
+int ks_ctx_create(ks_ctx **out, int device) {
+  if (!out) return KS_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                     "); kspans has no CPU path";
+    cudaGetLastError();
+    return KS_ERR_CUDA;
+  }
+  if (device < 0) {
+    e = cudaGetDevice(&device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return KS_ERR_CUDA; }
+  }
+  if (device >= ndev) { g_create_error = "device index out of range"; return KS_ERR_ARG; }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return KS_ERR_CUDA; }
+  ks_ctx *ctx = new ks_ctx();
+  ctx->device = device;
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return KS_ERR_CUDA; }
+  *out = ctx;
+  return KS_OK;
+}
+
+void ks_ctx_destroy(ks_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DBuf *all[] = {&ctx->wfx, &ctx->prm, &ctx->xf_status, &ctx->xf_agg, &ctx->xf_inc, &ctx->ex_status,
+                 &ctx->ex_agg, &ctx->ex_inc, &ctx->tile_counter, &ctx->rec_beg, &ctx->rec_pk, &ctx->rec_c,
+                 &ctx->rec_mhi, &ctx->rec_mlo, &ctx->rec_count, &ctx->seg_start, &ctx->seg_len,
+                 &ctx->seg_chunks, &ctx->seg_chunk0, &ctx->scan_tmp, &ctx->sort_keys_a, &ctx->sort_keys_b,
+                 &ctx->sort_vals_a, &ctx->sort_vals_b, &ctx->sort_hist, &ctx->sort_scan, &ctx->out_pos,
+                 &ctx->out_score, &ctx->sc_keys_a, &ctx->sc_keys_b, &ctx->sc_vals_a, &ctx->sc_vals_b,
+                 &ctx->sc_small, &ctx->sc_gcount, &ctx->sc_gstart, &ctx->sc_segfirst, &ctx->sc_segj0,
+                 &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->tmp_counts, &ctx->tmp_scores,
+                 &ctx->tmp_inscan, &ctx->nwords};
+  for (DBuf *b : all) b->release();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *ks_last_error(const ks_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+void *ks_ctx_stream(ks_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int ks_ctx_sync(ks_ctx *ctx) {
+  if (!ctx) return KS_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return KS_OK;
+}
+uint64_t ks_ctx_launches(const ks_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void ks_ctx_reset_launches(ks_ctx *ctx) { if (ctx) ctx->launches = 0; }
+void ks_ctx_scan_stats(const ks_ctx *ctx, int *levels, uint64_t *revisited_chunks) {
+  if (levels) *levels = ctx ? ctx->last_levels : 0;
+  if (revisited_chunks) *revisited_chunks = ctx ? ctx->last_revisit_chunks : 0;
+}
+
+int ks_kmer_seq(int k, uint64_t code, char *out) {
+  static const char nuc[4] = {'A', 'C', 'T', 'G'};
+  if (k < 1 || k > 16 || !out) return KS_ERR_ARG;
+  out[k] = 0;
+  for (int j = k - 1; j >= 0; --j) { out[j] = nuc[code & 3]; code >>= 2; }
+  return KS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sequence sets
+static int seqset_common(ks_ctx *ctx, const int64_t *lens, int nseq, ks_seqset *s) {
+  s->ctx = ctx;
+  s->nseq = nseq;
+  s->lens.assign(lens, lens + nseq);
+  s->starts.resize((size_t)nseq + 1);
+  s->total = ks_layout_total(lens, nseq, s->starts.data());
+  s->bases = 0;
+  for (int i = 0; i < nseq; ++i) {
+    if (lens[i] < 0 || lens[i] > 2147483646LL) return ctx->fail(KS_ERR_ARG, "sequence %d: length out of range", i);
+    s->bases += lens[i];
+  }
+  CK(cudaMalloc(&s->d_starts, sizeof(int64_t) * ((size_t)nseq + 1)));
+  CK(cudaMemcpyAsync(s->d_starts, s->starts.data(), sizeof(int64_t) * ((size_t)nseq + 1),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  return KS_OK;
+}
+
+int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, ks_seqset **out) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!out || !seqs || !lens || nseq < 1)
+    return ctx->fail(KS_ERR_ARG, "seq_r must be a character vector of length at least one");
+  CK(cudaSetDevice(ctx->device));
+  ks_seqset *s = new ks_seqset();
+  int rc = seqset_common(ctx, lens, nseq, s);
+  if (rc) { ks_seqset_free(s); return rc; }
+  cudaError_t e = cudaMalloc(&s->d_buf, (size_t)s->total + KS_SLACK);
+  if (e != cudaSuccess) { ks_seqset_free(s); return ctx->fail(KS_ERR_NOMEM, "cudaMalloc(%lld) failed", (long long)s->total); }
+  s->owned = true;
+  cudaStream_t st = ctx->stream;
+  e = cudaMemsetAsync(s->d_buf, 0, (size_t)s->total + KS_SLACK, st);
+  if (e != cudaSuccess) { ks_seqset_free(s); CK(e); }
+  // large sequences go straight from the caller's memory; small ones are packed into pinned
+  // staging windows (two halves, alternating) so that 100k contigs do not cost 100k copies
+  const int64_t DIRECT = 4ll << 20;
+  const size_t HALF = 16u << 20;
+  if (!ctx->pinned) {
+    e = cudaMallocHost(&ctx->pinned, 2 * HALF);
+    if (e != cudaSuccess) { ks_seqset_free(s); CK(e); }
+    ctx->pinned_cap = 2 * HALF;
+  }
+  cudaEvent_t ev[2];
+  cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+  bool ev_used[2] = {false, false};
+  int half = 0;
+  size_t fill = 0;
+  int64_t win_start = -1;  // global offset the current window maps to
+  char *win = (char *)ctx->pinned;
+  auto flush = [&]() -> cudaError_t {
+    if (fill == 0) return cudaSuccess;
+    cudaError_t ee = cudaMemcpyAsync(s->d_buf + win_start, win, fill, cudaMemcpyHostToDevice, st);
+    if (ee != cudaSuccess) return ee;
+    cudaEventRecord(ev[half], st);
+    ev_used[half] = true;
+    half ^= 1;
+    win = (char *)ctx->pinned + (size_t)half * HALF;
+    if (ev_used[half]) ee = cudaEventSynchronize(ev[half]);
+    fill = 0;
+    win_start = -1;
+    return ee;
+  };
+  e = cudaSuccess;
+  for (int i = 0; i < nseq && e == cudaSuccess; ++i) {
+    int64_t ln = lens[i];
+    if (ln == 0) continue;
+    if (ln >= DIRECT) {
+      e = flush();
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(s->d_buf + s->starts[i], seqs[i], (size_t)ln, cudaMemcpyHostToDevice, st);
+      continue;
+    }
+    // contiguous with the window?  (separator bytes between sequences are copied as zeros)
+    if (fill && (s->starts[i] != win_start + (int64_t)fill + 1 || fill + 1 + (size_t)ln > HALF)) e = flush();
+    if (e != cudaSuccess) break;
+    if (fill == 0) win_start = s->starts[i];
+    else win[fill++] = 0;
+    memcpy(win + fill, seqs[i], (size_t)ln);
+    fill += (size_t)ln;
+  }
+  if (e == cudaSuccess) e = flush();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  if (e != cudaSuccess) { ks_seqset_free(s); CK(e); }
+  *out = s;
+  return KS_OK;
+}
+
+int ks_seqset_wrap(ks_ctx *ctx, const void *d_buf, int64_t total_bytes, const int64_t *lens, int nseq,
+                   ks_seqset **out) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!out || !d_buf || !lens || nseq < 1) return ctx->fail(KS_ERR_ARG, "ks_seqset_wrap: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  ks_seqset *s = new ks_seqset();
+  int rc = seqset_common(ctx, lens, nseq, s);
+  if (rc) { ks_seqset_free(s); return rc; }
+  if (total_bytes < s->total + KS_SLACK) {
+    ks_seqset_free(s);
+    return ctx->fail(KS_ERR_ARG, "ks_seqset_wrap: buffer holds %lld bytes, layout needs %lld", (long long)total_bytes,
+                     (long long)(s->total + KS_SLACK));
+  }
+  s->d_buf = (uint8_t *)d_buf;
+  s->owned = false;
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = s;
+  return KS_OK;
+}
+
+void ks_seqset_free(ks_seqset *s) {
+  if (!s) return;
+  if (s->ctx) cudaSetDevice(s->ctx->device);
+  if (s->owned && s->d_buf) cudaFree(s->d_buf);
+  if (s->d_starts) cudaFree(s->d_starts);
+  delete s;
+}
+int64_t ks_seqset_bases(const ks_seqset *s) { return s ? s->bases : 0; }
+int64_t ks_seqset_buffer_bytes(const ks_seqset *s) { return s ? s->total + KS_SLACK : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// stage: count
+int ks_dev_count(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, double *n_words) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!s || !d_counts) return ctx->fail(KS_ERR_ARG, "ks_dev_count: null argument");
+  int rc = check_k(ctx, k);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  size_t n = (size_t)1 << (2 * k);
+  CK(ctx->nwords.ensure(sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(d_counts, 0, n * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
+  int64_t nchunks = (s->total - 16) / 16;
+  count_kernel<<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
+      s->d_buf, nchunks, k, (uint32_t)(n - 1), d_counts, ctx->nwords.as<unsigned long long>());
+  LAUNCHED(1);
+  CK(cudaGetLastError());
+  unsigned long long nw = 0;
+  CK(cudaMemcpyAsync(&nw, ctx->nwords.p, sizeof nw, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (n_words) *n_words = (double)nw;
+  return KS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage: score tables
+int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int mode, double param,
+                  double *d_scores) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!d_counts || !d_scores) return ctx->fail(KS_ERR_ARG, "ks_dev_scores: null argument");
+  int rc = check_k(ctx, k);
+  if (rc) return rc;
+  if (mode < KS_MODE_RANK || mode > KS_MODE_RANK_REL) return ctx->fail(KS_ERR_ARG, "unknown score mode %d", mode);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)1 << (2 * k);
+  const bool rank_mode = (mode == KS_MODE_RANK || mode == KS_MODE_RANK_REL);
+  if (rank_mode && total == 0) {
+    // 0/0 addends: every rank but the first in sort order (k-mer 0) is NaN (:200)
+    fill_nan_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(d_scores, n);
+    LAUNCHED(1);
+    CK(cudaGetLastError());
+  } else {
+    // 1. stable (count, index) order
+    CK(ctx->sc_keys_a.ensure(n * 4));
+    CK(ctx->sc_keys_b.ensure(n * 4));
+    CK(ctx->sc_vals_a.ensure(n * 4));
+    CK(ctx->sc_vals_b.ensure(n * 4));
+    size_t nb = radix_nblocks(n);
+    CK(ctx->sort_hist.ensure((256 * nb + 2) * 4));
+    CK(ctx->sort_scan.ensure(exclusive_scan_scratch_elems(256 * nb) * 4));
+    CK(ctx->sc_small.ensure(64));
+    CK(cudaMemsetAsync(ctx->sc_small.p, 0, 64, st));
+    uint32_t *d_max = ctx->sc_small.as<uint32_t>();
+    uint32_t *d_ngroups = d_max + 1;
+    CK(cudaMemcpyAsync(ctx->sc_keys_a.p, d_counts, n * 4, cudaMemcpyDeviceToDevice, st));
+    max_u32_kernel<<<grid_for(n, 256), 256, 0, st>>>(ctx->sc_keys_a.as<uint32_t>(), n, d_max);
+    LAUNCHED(1);
+    uint32_t maxc = 0;
+    CK(cudaMemcpyAsync(&maxc, d_max, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int nbits = 0;
+    while (nbits < 32 && (maxc >> nbits) != 0) ++nbits;
+    RadixScratch rs{ctx->sort_hist.as<uint32_t>(), ctx->sort_scan.as<uint32_t>()};
+    uint32_t *skeys = nullptr, *svals = nullptr;
+    LAUNCHED(radix_sort_pairs<uint32_t>(ctx->sc_keys_a.as<uint32_t>(), ctx->sc_vals_a.as<uint32_t>(),
+                                        ctx->sc_keys_b.as<uint32_t>(), ctx->sc_vals_b.as<uint32_t>(), n, nbits,
+                                        true, rs, st, &skeys, &svals));
+    CK(cudaGetLastError());
+    // 2. run-length table of the sorted counts (#distinct counts <= sqrt(2 * total) + 1)
+    size_t gcap = (size_t)(sqrt(2.0 * (total > 0 ? total : 1.0)) + 16.0);
+    if (gcap > n) gcap = n;
+    if (gcap < 16) gcap = 16;
+    std::vector<uint32_t> gcount, gstart32;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      CK(ctx->sc_gcount.ensure((gcap + 1) * 4));
+      CK(ctx->sc_gstart.ensure((gcap + 1) * 4));
+      CK(cudaMemsetAsync(d_ngroups, 0, 4, st));
+      rle_heads_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(skeys, n, ctx->sc_gcount.as<uint32_t>(),
+                                                             ctx->sc_gstart.as<uint32_t>(), d_ngroups,
+                                                             (uint32_t)gcap);
+      LAUNCHED(1);
+      uint32_t ng = 0;
+      CK(cudaMemcpyAsync(&ng, d_ngroups, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (ng > gcap) { gcap = ng; continue; }
+      gcount.resize(ng);
+      gstart32.resize(ng);
+      CK(cudaMemcpyAsync(gcount.data(), ctx->sc_gcount.p, (size_t)ng * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(gstart32.data(), ctx->sc_gstart.p, (size_t)ng * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      break;
+    }
+    const size_t ng = gcount.size();
+    {  // appended in arbitrary order: order the (few) groups by start position
+      std::vector<uint32_t> ord(ng);
+      for (size_t i = 0; i < ng; ++i) ord[i] = (uint32_t)i;
+      std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return gstart32[a] < gstart32[b]; });
+      std::vector<uint32_t> c2(ng), s2(ng);
+      for (size_t i = 0; i < ng; ++i) { c2[i] = gcount[ord[i]]; s2[i] = gstart32[ord[i]]; }
+      gcount.swap(c2);
+      gstart32.swap(s2);
+    }
+    std::vector<uint64_t> gstart(ng + 1);
+    for (size_t i = 0; i < ng; ++i) gstart[i] = gstart32[i];
+    gstart[ng] = n;
+    if (rank_mode) {
+      // 3a. linear pieces of the sequential accumulation (ks_rankseg.h), evaluated on the device
+      std::vector<uint32_t> seg_first;
+      std::vector<RankSeg> segs;
+      build_rank_segments(gcount.data(), gstart.data(), ng, total, seg_first, segs);
+      size_t nsg = segs.size();
+      std::vector<unsigned long long> j0(nsg);
+      std::vector<double> x0(nsg), inc(nsg);
+      for (size_t i = 0; i < nsg; ++i) { j0[i] = segs[i].j0; x0[i] = segs[i].x0; inc[i] = segs[i].inc; }
+      gstart32.push_back((uint32_t)n);
+      CK(ctx->sc_gstart.ensure((ng + 1) * 4));
+      CK(ctx->sc_segfirst.ensure((ng + 1) * 4));
+      CK(ctx->sc_segj0.ensure(nsg * 8 + 8));
+      CK(ctx->sc_segx0.ensure(nsg * 8 + 8));
+      CK(ctx->sc_seginc.ensure(nsg * 8 + 8));
+      CK(cudaMemcpyAsync(ctx->sc_gstart.p, gstart32.data(), (ng + 1) * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->sc_segfirst.p, seg_first.data(), (ng + 1) * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->sc_segj0.p, j0.data(), nsg * 8, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->sc_segx0.p, x0.data(), nsg * 8, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->sc_seginc.p, inc.data(), nsg * 8, cudaMemcpyHostToDevice, st));
+      rank_eval_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(
+          svals, n, ctx->sc_gstart.as<uint32_t>(), (uint32_t)ng, ctx->sc_segfirst.as<uint32_t>(),
+          ctx->sc_segj0.as<unsigned long long>(), ctx->sc_segx0.as<double>(), ctx->sc_seginc.as<double>(),
+          d_scores);
+      LAUNCHED(1);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(st));  // host vectors above must outlive the copies
+    } else {
+      // 3b. pure functions of the count: one libm evaluation per DISTINCT count on the host
+      //     (README.md:27-42; conventions in DESIGN.md), broadcast to the table on the device
+      auto count_at = [&](uint64_t p) -> double {  // count at sorted position p
+        size_t g = std::upper_bound(gstart.begin(), gstart.end(), p) - gstart.begin() - 1;
+        return (double)(int32_t)gcount[g];
+      };
+      double f_lo = count_at(n / 2 - 1) / total, f_hi = count_at(n / 2) / total;
+      double f_med = (f_lo + f_hi) / 2.0;
+      std::vector<double> lut(ng);
+      for (size_t g = 0; g < ng; ++g) {
+        double f = (double)(int32_t)gcount[g] / total;
+        if (mode == KS_MODE_LOG2) lut[g] = log2(f / f_med);
+        else {
+          double f_t = isfinite(param) ? param : f_med;
+          lut[g] = f >= f_t ? 1.0 : -1.0;
+        }
+      }
+      CK(ctx->sc_gcount.ensure((ng + 1) * 4));
+      CK(ctx->sc_lut.ensure(ng * 8 + 8));
+      CK(cudaMemcpyAsync(ctx->sc_gcount.p, gcount.data(), ng * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->sc_lut.p, lut.data(), ng * 8, cudaMemcpyHostToDevice, st));
+      lut_apply_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_counts), n,
+                                                             ctx->sc_gcount.as<uint32_t>(), (uint32_t)ng,
+                                                             ctx->sc_lut.as<double>(), d_scores);
+      LAUNCHED(1);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(st));
+    }
+  }
+  if (mode == KS_MODE_RANK_REL) {
+    affine_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(d_scores, n, param, param);
+    LAUNCHED(1);
+    CK(cudaGetLastError());
+  }
+  return KS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage: scan + spans
+static int ensure_tiles(ks_ctx *ctx, size_t tiles) {
+  if (tiles <= ctx->tiles_cap) return KS_OK;
+  size_t t = tiles + tiles / 4 + 64;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->xf_status.ensure(t * 4));
+  CK(ctx->ex_status.ensure(t * 4));
+  CK(ctx->xf_agg.ensure(t * 40));
+  CK(ctx->xf_inc.ensure(t * 16));
+  CK(ctx->ex_agg.ensure(t * 40));
+  CK(ctx->ex_inc.ensure(t * 40));
+  CK(cudaMemsetAsync(ctx->xf_status.p, 0, ctx->xf_status.cap, st));
+  CK(cudaMemsetAsync(ctx->ex_status.p, 0, ctx->ex_status.cap, st));
+  ctx->epoch = 0;  // fresh, zeroed status words
+  ctx->tiles_cap = t;
+  return KS_OK;
+}
+
+static int ensure_recs(ks_ctx *ctx, size_t cap) {
+  if (cap <= ctx->rec_cap) return KS_OK;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->rec_beg.ensure(cap * 8, true, st));
+  CK(ctx->rec_pk.ensure(cap * 8, true, st));
+  CK(ctx->rec_c.ensure(cap * 8, true, st));
+  CK(ctx->rec_mhi.ensure(cap * 8, true, st));
+  CK(ctx->rec_mlo.ensure(cap * 8, true, st));
+  ctx->rec_cap = cap;
+  return KS_OK;
+}
+
+int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
+                double min_score, int32_t *d_inscan, ks_spans *host_out, uint64_t *n_spans) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!s || !d_W) return ctx->fail(KS_ERR_ARG, "ks_dev_scan: null argument");
+  int rc = check_k(ctx, k);
+  if (rc) return rc;
+  if (host_out) { host_out->pos = nullptr; host_out->score = nullptr; host_out->n = 0; }
+  if (n_spans) *n_spans = 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t nk = (size_t)1 << (2 * k);
+  const uint64_t mw = (uint64_t)(int64_t)min_width;  // negative R integers wrap exactly like size_t (:243)
+
+  // score table -> exact fixed point
+  CK(ctx->wfx.ensure(nk * 8));
+  CK(ctx->prm.ensure(sizeof(DevScanParams)));
+  CK(ctx->tile_counter.ensure(64));
+  CK(ctx->rec_count.ensure(64));
+  DevScanParams *d_prm = ctx->prm.as<DevScanParams>();
+  CK(cudaMemsetAsync(d_prm, 0, sizeof(DevScanParams), st));
+  wmax_kernel<<<grid_for(nk, 256), 256, 0, st>>>(d_W, nk, thr, d_prm);
+  wfx_kernel<<<grid_for(nk, 256), 256, 0, st>>>(d_W, nk, thr, ctx->wfx.as<int64_t>(), d_prm, mw, min_score);
+  LAUNCHED(2);
+  CK(cudaGetLastError());
+
+  unsigned long long *d_rec_count = ctx->rec_count.as<unsigned long long>();
+  CK(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), st));
+  if (!ctx->counter_init) {
+    CK(cudaMemsetAsync(ctx->tile_counter.p, 0, 64, st));
+    ctx->counter_init = true;
+    ctx->tile_base = 0;
+  }
+
+  const int64_t dense_chunks = (s->total - 16) / 16;
+  rc = ensure_recs(ctx, std::max<size_t>((size_t)1 << 16, (size_t)(dense_chunks / 64)));
+  if (rc) return rc;
+
+  unsigned long long level_start = 0;  // records before this level
+  int64_t nseg = 0, total_chunks = dense_chunks;
+  int level = 0;
+  uint64_t revisit_chunks = 0;
+  bool count_inscan = d_inscan != nullptr;
+  for (;;) {
+    size_t tiles = (size_t)((total_chunks + TILE_THREADS - 1) / TILE_THREADS);
+    if (tiles == 0) break;
+    if (tiles > 0xfffffff0ull) return ctx->fail(KS_ERR_ARG, "input too large for one scan launch");
+    rc = ensure_tiles(ctx, tiles);
+    if (rc) return rc;
+    LevelArgs A;
+    memset(&A, 0, sizeof A);
+    A.buf = s->d_buf;
+    A.wfx = ctx->wfx.as<int64_t>();
+    A.prm = d_prm;
+    A.k = k;
+    A.kmask = (uint32_t)(nk - 1);
+    A.nseg = nseg;
+    A.seg_start = ctx->seg_start.as<int64_t>();
+    A.seg_len = ctx->seg_len.as<int64_t>();
+    A.seg_chunk0 = ctx->seg_chunk0.as<uint64_t>();
+    A.dense_start = 16;
+    A.total_chunks = total_chunks;
+    A.inscan = count_inscan ? d_inscan : nullptr;
+    A.ts.xf_status = ctx->xf_status.as<uint32_t>();
+    A.ts.xf_agg = ctx->xf_agg.as<uint64_t>();
+    A.ts.xf_inc = ctx->xf_inc.as<uint64_t>();
+    A.ts.ex_status = ctx->ex_status.as<uint32_t>();
+    A.ts.ex_agg = ctx->ex_agg.as<uint64_t>();
+    A.ts.ex_inc = ctx->ex_inc.as<uint64_t>();
+    ctx->epoch += 1;
+    if (ctx->epoch >= (1u << 30) - 1) {  // epoch space exhausted: start over with zeroed words
+      CK(cudaMemsetAsync(ctx->xf_status.p, 0, ctx->xf_status.cap, st));
+      CK(cudaMemsetAsync(ctx->ex_status.p, 0, ctx->ex_status.cap, st));
+      ctx->epoch = 1;
+    }
+    A.epoch = ctx->epoch;
+    A.tile_counter = ctx->tile_counter.as<unsigned int>();
+    A.tile_base = ctx->tile_base;
+    ctx->tile_base += (unsigned int)tiles;
+    A.rec_beg = ctx->rec_beg.as<int64_t>();
+    A.rec_pk = ctx->rec_pk.as<int64_t>();
+    A.rec_c = ctx->rec_c.as<int64_t>();
+    A.rec_mhi = ctx->rec_mhi.as<int64_t>();
+    A.rec_mlo = ctx->rec_mlo.as<uint64_t>();
+    A.rec_count = d_rec_count;
+    A.rec_cap = ctx->rec_cap;
+    scan_level_kernel<<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    LAUNCHED(1);
+    CK(cudaGetLastError());
+    struct { unsigned long long cnt; } hres;
+    DevScanParams hprm;
+    CK(cudaMemcpyAsync(&hres.cnt, d_rec_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (level == 0) CK(cudaMemcpyAsync(&hprm, d_prm, sizeof hprm, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (level == 0 && hprm.err)
+      return ctx->fail(KS_ERR_RANGE, "a k-mer weight is +Inf or >= 2^40: outside the exact scan range");
+    count_inscan = false;  // every position of this level has been counted, also if we must retry
+    if (hres.cnt > ctx->rec_cap) {
+      // record buffer too small: grow (keeping earlier levels), rewind the counter, redo the level
+      rc = ensure_recs(ctx, (size_t)hres.cnt + (size_t)hres.cnt / 8 + 1024);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(d_rec_count, &level_start, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      continue;
+    }
+    if (level > 0) revisit_chunks += (uint64_t)total_chunks;
+    unsigned long long n_new = hres.cnt - level_start;
+    ++level;
+    if (n_new == 0) break;
+    // child segments of the records this level emitted
+    CK(ctx->seg_start.ensure(n_new * 8));
+    CK(ctx->seg_len.ensure(n_new * 8));
+    CK(ctx->seg_chunks.ensure(n_new * 8));
+    CK(ctx->seg_chunk0.ensure((n_new + 1) * 8));
+    CK(ctx->scan_tmp.ensure(exclusive_scan_scratch_elems(n_new) * 8));
+    seg_build_kernel<<<blocks_exact(n_new, 256), 256, 0, st>>>(
+        ctx->rec_pk.as<int64_t>(), ctx->rec_c.as<int64_t>(), level_start, n_new, mw, d_inscan != nullptr,
+        ctx->seg_start.as<int64_t>(), ctx->seg_len.as<int64_t>(), ctx->seg_chunks.as<uint64_t>());
+    LAUNCHED(1);
+    LAUNCHED((exclusive_scan<uint64_t, uint64_t>(ctx->seg_chunks.as<uint64_t>(), n_new,
+                                                 ctx->seg_chunk0.as<uint64_t>(), ctx->scan_tmp.as<uint64_t>(), st)));
+    CK(cudaGetLastError());
+    uint64_t tot = 0;
+    CK(cudaMemcpyAsync(&tot, ctx->seg_chunk0.as<uint64_t>() + n_new, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    level_start = hres.cnt;
+    nseg = (int64_t)n_new;
+    total_chunks = (int64_t)tot;
+    if (d_inscan) count_inscan = true;
+    if (total_chunks == 0) break;
+  }
+  ctx->last_levels = level;
+  ctx->last_revisit_chunks = revisit_chunks;
+
+  // order by start position and convert to the reference layout
+  unsigned long long n = 0;
+  CK(cudaMemcpyAsync(&n, d_rec_count, sizeof n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (n_spans) *n_spans = n;
+  if (n == 0) return KS_OK;
+  if (n > 0xfffffff0ull) return ctx->fail(KS_ERR_NOMEM, "too many spans");
+  const uint32_t *d_perm = nullptr;
+  if (n > 1) {
+    CK(ctx->sort_keys_a.ensure(n * 8));
+    CK(ctx->sort_keys_b.ensure(n * 8));
+    CK(ctx->sort_vals_a.ensure(n * 4));
+    CK(ctx->sort_vals_b.ensure(n * 4));
+    size_t nb = radix_nblocks(n);
+    CK(ctx->sort_hist.ensure((256 * nb + 2) * 4));
+    CK(ctx->sort_scan.ensure(exclusive_scan_scratch_elems(256 * nb) * 4));
+    copy_keys_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(ctx->rec_beg.as<int64_t>(), n,
+                                                           ctx->sort_keys_a.as<uint64_t>());
+    LAUNCHED(1);
+    int nbits = 0;
+    while (nbits < 63 && ((uint64_t)s->total >> nbits) != 0) ++nbits;
+    RadixScratch rs{ctx->sort_hist.as<uint32_t>(), ctx->sort_scan.as<uint32_t>()};
+    uint64_t *skeys = nullptr;
+    uint32_t *svals = nullptr;
+    LAUNCHED(radix_sort_pairs<uint64_t>(ctx->sort_keys_a.as<uint64_t>(), ctx->sort_vals_a.as<uint32_t>(),
+                                        ctx->sort_keys_b.as<uint64_t>(), ctx->sort_vals_b.as<uint32_t>(), n,
+                                        nbits, true, rs, st, &skeys, &svals));
+    CK(cudaGetLastError());
+    d_perm = svals;
+  }
+  CK(ctx->out_pos.ensure(n * 3 * 4));
+  CK(ctx->out_score.ensure(n * 2 * 8));
+  finalize_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(
+      d_perm, n, ctx->rec_beg.as<int64_t>(), ctx->rec_pk.as<int64_t>(), ctx->rec_mhi.as<int64_t>(),
+      ctx->rec_mlo.as<uint64_t>(), s->d_starts, s->nseq, d_prm, ctx->out_pos.as<int32_t>(),
+      ctx->out_score.as<double>());
+  LAUNCHED(1);
+  CK(cudaGetLastError());
+  if (host_out) {
+    host_out->pos = (int32_t *)malloc(n * 3 * sizeof(int32_t));
+    host_out->score = (double *)malloc(n * 2 * sizeof(double));
+    if (!host_out->pos || !host_out->score) { ks_spans_free(host_out); return ctx->fail(KS_ERR_NOMEM, "out of host memory"); }
+    host_out->n = (size_t)n;
+    CK(cudaMemcpyAsync(host_out->pos, ctx->out_pos.p, n * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(host_out->score, ctx->out_score.p, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return KS_OK;
+}
+
+int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double param, double thr, int min_width,
+                    double min_score, int32_t *d_counts, double *d_scores, double *n_words,
+                    ks_spans *host_out, uint64_t *n_spans) {
+  if (!ctx) return KS_ERR_ARG;
+  double nw = 0;
+  int rc = ks_dev_count(ctx, s, k, d_counts, &nw);
+  if (rc) return rc;
+  if (n_words) *n_words = nw;
+  rc = ks_dev_scores(ctx, k, d_counts, nw, mode, param, d_scores);
+  if (rc) return rc;
+  return ks_dev_scan(ctx, s, k, d_scores, thr, min_width, min_score, nullptr, host_out, n_spans);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer entry points
+static int check_seqs(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq) {
+  if (!seqs || !lens || nseq < 1)
+    return ctx->fail(KS_ERR_ARG, "seq_r must be a character vector of length at least one");
+  return KS_OK;
+}
+
+int ks_kmer_counts(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,
+                   int32_t *counts_out, double *n_words) {
+  if (!ctx) return KS_ERR_ARG;
+  int rc = check_seqs(ctx, seqs, lens, nseq);
+  if (rc) return rc;
+  if (k < 1 || k > 15) return ctx->fail(KS_ERR_ARG, "k must be a positive integer less than 1+MAX_K");
+  if (!counts_out || !n_words) return ctx->fail(KS_ERR_ARG, "null output");
+  size_t n = (size_t)1 << (2 * k);
+  ks_seqset *ss = nullptr;
+  rc = ks_seqset_upload(ctx, seqs, lens, nseq, &ss);
+  if (rc) return rc;
+  cudaError_t e = ctx->tmp_counts.ensure(n * 4);
+  if (e != cudaSuccess) { ks_seqset_free(ss); CK(e); }
+  rc = ks_dev_count(ctx, ss, k, ctx->tmp_counts.as<int32_t>(), n_words);
+  if (!rc) {
+    e = cudaMemcpy(counts_out, ctx->tmp_counts.p, n * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = ctx->fail(KS_ERR_CUDA, "D2H counts: %s", cudaGetErrorString(e));
+  }
+  ks_seqset_free(ss);
+  return rc;
+}
+
+int ks_kmer_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k, const double *W,
+                    int min_width, double min_score, double *nuc, int32_t *inscan_counts_out, ks_spans *out) {
+  if (!ctx) return KS_ERR_ARG;
+  int rc = check_seqs(ctx, seqs, lens, nseq);
+  if (rc) return rc;
+  if (k >= 16 || k < 1)
+    return ctx->fail(KS_ERR_ARG, "kmer sizes larger than or equal to %d not currently supported", 16);
+  if (!W || !out) return ctx->fail(KS_ERR_ARG, "null argument");
+  size_t n = (size_t)1 << (2 * k);
+  if (nuc) {
+    *nuc = 0;
+    for (int i = 0; i < nseq; ++i)
+      if (lens[i] >= k) *nuc += (double)lens[i];  // :533-535
+  }
+  ks_seqset *ss = nullptr;
+  rc = ks_seqset_upload(ctx, seqs, lens, nseq, &ss);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  cudaError_t e = ctx->tmp_scores.ensure(n * 8);
+  if (e == cudaSuccess) e = ctx->tmp_inscan.ensure(n * 4);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->tmp_scores.p, W, n * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ctx->tmp_inscan.p, 0, n * 4, st);
+  if (e != cudaSuccess) { ks_seqset_free(ss); CK(e); }
+  rc = ks_dev_scan(ctx, ss, k, ctx->tmp_scores.as<double>(), 0.0, min_width, min_score,
+                   inscan_counts_out ? ctx->tmp_inscan.as<int32_t>() : nullptr, out, nullptr);
+  if (!rc && inscan_counts_out) {
+    e = cudaMemcpy(inscan_counts_out, ctx->tmp_inscan.p, n * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = ctx->fail(KS_ERR_CUDA, "D2H counts: %s", cudaGetErrorString(e));
+  }
+  ks_seqset_free(ss);
+  return rc;
+}
+
+int ks_kmer_mode_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k, int mode,
+                         double param, double thr, int min_width, double min_score, double *n_words,
+                         int32_t *counts_out, double *scores_out, ks_spans *out) {
+  if (!ctx) return KS_ERR_ARG;
+  int rc = check_seqs(ctx, seqs, lens, nseq);
+  if (rc) return rc;
+  rc = check_k(ctx, k);
+  if (rc) return rc;
+  if (!out) return ctx->fail(KS_ERR_ARG, "null argument");
+  size_t n = (size_t)1 << (2 * k);
+  ks_seqset *ss = nullptr;
+  rc = ks_seqset_upload(ctx, seqs, lens, nseq, &ss);
+  if (rc) return rc;
+  cudaError_t e = ctx->tmp_counts.ensure(n * 4);
+  if (e == cudaSuccess) e = ctx->tmp_scores.ensure(n * 8);
+  if (e != cudaSuccess) { ks_seqset_free(ss); CK(e); }
+  double nw = 0;
+  rc = ks_dev_pipeline(ctx, ss, k, mode, param, thr, min_width, min_score, ctx->tmp_counts.as<int32_t>(),
+                       ctx->tmp_scores.as<double>(), &nw, out, nullptr);
+  if (n_words) *n_words = nw;
+  if (!rc && counts_out) {
+    e = cudaMemcpy(counts_out, ctx->tmp_counts.p, n * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = ctx->fail(KS_ERR_CUDA, "D2H counts: %s", cudaGetErrorString(e));
+  }
+  if (!rc && scores_out) {
+    e = cudaMemcpy(scores_out, ctx->tmp_scores.p, n * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = ctx->fail(KS_ERR_CUDA, "D2H scores: %s", cudaGetErrorString(e));
+  }
+  ks_seqset_free(ss);
+  return rc;
+}
+
+int ks_kmer_low_comp_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,
+                             int min_width, double min_score, double thr, double n_out[2], int32_t *counts_out,
+                             double *ranks_out, ks_spans *out) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!(thr > 0 && thr < 1)) return ctx->fail(KS_ERR_ARG, "the threshold must be between 0 and 1");
+  double nw = 0;
+  int rc = ks_kmer_mode_regions(ctx, seqs, lens, nseq, k, KS_MODE_RANK, 0.0, thr, min_width, min_score, &nw,
+                                counts_out, ranks_out, out);
+  if (n_out) { n_out[0] = nw; n_out[1] = 0; }  // :613
+  return rc;
+}
+
+int ks_kmer_scores(ks_ctx *ctx, int k, const int32_t *counts, double total, int mode, double param,
+                   double *scores_out) {
+  if (!ctx) return KS_ERR_ARG;
+  int rc = check_k(ctx, k);
+  if (rc) return rc;
+  if (!counts || !scores_out) return ctx->fail(KS_ERR_ARG, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  size_t n = (size_t)1 << (2 * k);
+  CK(ctx->tmp_counts.ensure(n * 4));
+  CK(ctx->tmp_scores.ensure(n * 8));
+  CK(cudaMemcpyAsync(ctx->tmp_counts.p, counts, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  rc = ks_dev_scores(ctx, k, ctx->tmp_counts.as<int32_t>(), total, mode, param, ctx->tmp_scores.as<double>());
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(scores_out, ctx->tmp_scores.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return KS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,594 @@
+// ks_kernels.cuh -- hand-written sm_100a kernels of the kmer_spans hot path.
+//
+//   count_kernel        K1+K2: ASCII stream -> rolling 2-bit codes -> red.global.add into int32[4^k]
+//                       (replaces sequence_kmer_count, /root/reference/src/kmer_spans.c:135-155)
+//   wmax/wfx kernels    score table double[4^k] -> exact fixed-point table int64[4^k] (W - thr, :268)
+//   scan_level_kernel   K4+K5+K6: per-position gather, max-plus scan with a decoupled look-back,
+//                       excursion (start, leftmost peak, close) extraction, qualification and
+//                       compacted emission (replaces kmer_regions, :243-307, one restart level per
+//                       launch; level 0 is the dense pass over the whole buffer)
+//   seg_build_kernel    qualifying excursions -> child segments [peak+1, close] (restart at peak, :281-283)
+//   finalize_kernel     sorted records -> reference layout (seq_id, start, end | score, 0) (:95-99)
+//   rank / lut kernels  K3: score-table derivation (rank_kmers_w :189-202, README.md:27-42 modes)
+//
+// No tensor-core work exists on this path (integer / byte / gather / atomic work); see DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ks_chunk.cuh"
+
+namespace ks {
+
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_WARPS = TILE_THREADS / 32;
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t fx_lo(fx_t v) { return (uint64_t)(unsigned __int128)v; }
+__device__ __forceinline__ uint64_t fx_hi(fx_t v) { return (uint64_t)(((unsigned __int128)v) >> 64); }
+__device__ __forceinline__ fx_t fx_make(uint64_t hi, uint64_t lo) {
+  return (fx_t)((((unsigned __int128)hi) << 64) | (unsigned __int128)lo);
+}
+
+__device__ __forceinline__ fx_t shfl_fx(fx_t v, int src) {
+  uint64_t lo = __shfl_sync(0xffffffffu, (unsigned long long)fx_lo(v), src);
+  uint64_t hi = __shfl_sync(0xffffffffu, (unsigned long long)fx_hi(v), src);
+  return fx_make(hi, lo);
+}
+__device__ __forceinline__ Xf shfl_xf(const Xf &f, int src) {
+  Xf r;
+  r.a = shfl_fx(f.a, src);
+  r.b = shfl_fx(f.b, src);
+  r.kill = __shfl_sync(0xffffffffu, f.kill, src);
+  return r;
+}
+__device__ __forceinline__ Ex shfl_ex(const Ex &e, int src) {
+  Ex r;
+  r.M = shfl_fx(e.M, src);
+  r.beg = __shfl_sync(0xffffffffu, (long long)e.beg, src);
+  r.pk = __shfl_sync(0xffffffffu, (long long)e.pk, src);
+  uint32_t fl = __shfl_sync(0xffffffffu, e.reset | (e.open << 1), src);
+  r.reset = fl & 1u;
+  r.open = (fl >> 1) & 1u;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 + K2: counting.  One thread = one 16-byte chunk; grid-stride, consecutive threads read
+// consecutive 16-byte vectors (512 B per warp request).
+__global__ void __launch_bounds__(256) count_kernel(const uint8_t *__restrict__ buf, int64_t nchunks,
+                                                    int k, uint32_t kmask, int32_t *__restrict__ counts,
+                                                    unsigned long long *__restrict__ nwords) {
+  unsigned long long local = 0;
+  for (int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ci < nchunks;
+       ci += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t *p = buf + 16 * ci;  // = (chunk position p0) - 16
+    const uint4 *v = reinterpret_cast<const uint4 *>(p);
+    uint4 a = __ldg(v), b = __ldg(v + 1);
+    uint32_t next = __ldg(p + 32);
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t code[CHUNK], counted;
+    decode_count(w, next, k, kmask, code, counted);
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j)
+      if (counted & (1u << j)) atomicAdd(&counts[code[j]], 1);
+    local += __popc(counted);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  __shared__ unsigned long long sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
+    if (t) atomicAdd(nwords, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// scan parameters living in device memory (written by wfx_kernel, read by every scan launch)
+struct DevScanParams {
+  uint64_t min_width;
+  uint64_t min_lo;
+  int64_t min_hi;
+  int32_t qs;
+  int32_t err;             // 1: a weight is +inf or >= 2^40
+  unsigned long long wmax_bits;  // bits of max finite |W - thr|
+};
+
+__global__ void __launch_bounds__(256) wmax_kernel(const double *__restrict__ W, size_t n, double thr,
+                                                   DevScanParams *prm) {
+  double m = 0.0;
+  int err = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double w = W[i] - thr;
+    if (w >= 0x1p40) err = 1;
+    else if (w == w && w > -0x1p40) m = fmax(m, fabs(w));
+  }
+  unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long y = __shfl_down_sync(0xffffffffu, bits, o);
+    bits = y > bits ? y : bits;
+    err |= __shfl_down_sync(0xffffffffu, err, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (bits) atomicMax(&prm->wmax_bits, bits);
+    if (err) atomicOr(&prm->err, 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) wfx_kernel(const double *__restrict__ W, size_t n, double thr,
+                                                  int64_t *__restrict__ wfx, DevScanParams *prm,
+                                                  uint64_t min_width, double min_score) {
+  const int qs = qs_for_max(__longlong_as_double((long long)prm->wmax_bits));
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    wfx[i] = wfx_from_double(W[i] - thr, qs);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    fx_t mu = fx_ceil_units(min_score, qs);
+    prm->min_width = min_width;
+    prm->min_lo = fx_lo(mu);
+    prm->min_hi = (int64_t)fx_hi(mu);
+    prm->qs = qs;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// look-back descriptors, one set per tile.  status = (epoch << 2) | state, state 1 = aggregate of
+// this tile alone, 2 = inclusive (everything to the left folded in).  Buffers are zeroed once; a new
+// epoch per launch makes older states read as "not ready".
+struct TileState {
+  uint32_t *xf_status;
+  uint64_t *xf_agg;  // 5 per tile: a_lo, a_hi, b_lo, b_hi, kill
+  uint64_t *xf_inc;  // 2 per tile: S_lo, S_hi at the tile end
+  uint32_t *ex_status;
+  uint64_t *ex_agg;  // 5 per tile: M_lo, M_hi, beg, pk, reset | open << 1
+  uint64_t *ex_inc;  // 5 per tile
+};
+
+struct LevelArgs {
+  const uint8_t *buf;
+  const int64_t *wfx;
+  const DevScanParams *prm;
+  int k;
+  uint32_t kmask;
+  // level >= 1: nseg segments, seg_chunk0 = exclusive prefix of their chunk counts (nseg + 1)
+  int64_t nseg;
+  const int64_t *seg_start;
+  const int64_t *seg_len;
+  const uint64_t *seg_chunk0;
+  // level 0 (nseg == 0): dense pass over [dense_start, dense_start + 16 * total_chunks)
+  int64_t dense_start;
+  int64_t total_chunks;
+  int32_t *inscan;  // or NULL
+  TileState ts;
+  uint32_t epoch;
+  unsigned int *tile_counter;
+  unsigned int tile_base;
+  // emitted records (SoA), appended across levels
+  int64_t *rec_beg, *rec_pk, *rec_c, *rec_mhi;
+  uint64_t *rec_mlo;
+  unsigned long long *rec_count;
+  unsigned long long rec_cap;
+};
+
+struct DevEmit {
+  const LevelArgs *A;
+  __device__ __forceinline__ void operator()(int64_t beg, int64_t pk, int64_t c, fx_t M) const {
+    unsigned long long slot = atomicAdd(A->rec_count, 1ull);
+    if (slot < A->rec_cap) {
+      A->rec_beg[slot] = beg;
+      A->rec_pk[slot] = pk;
+      A->rec_c[slot] = c;
+      A->rec_mhi[slot] = (int64_t)fx_hi(M);
+      A->rec_mlo[slot] = fx_lo(M);
+    }
+  }
+};
+
+__device__ __forceinline__ Xf load_xf_desc(const TileState &ts, int64_t idx, uint32_t st) {
+  Xf x;
+  if ((st & 3u) == 2u) {
+    uint64_t lo = __ldcg(&ts.xf_inc[2 * idx]), hi = __ldcg(&ts.xf_inc[2 * idx + 1]);
+    x.kill = 1; x.a = 0; x.b = fx_make(hi, lo);
+  } else {
+    const uint64_t *p = &ts.xf_agg[5 * idx];
+    uint64_t alo = __ldcg(p), ahi = __ldcg(p + 1), blo = __ldcg(p + 2), bhi = __ldcg(p + 3);
+    x.kill = (uint32_t)__ldcg(p + 4);
+    x.a = fx_make(ahi, alo);
+    x.b = fx_make(bhi, blo);
+  }
+  return x;
+}
+
+// Warp-wide decoupled look-back for the max-plus transform: returns the state S at the start of
+// `tile`.  Lane L inspects tile (base - L); a transform with kill set (an inclusive value, or an
+// aggregate containing a reset) ends the walk because composition ignores everything left of it.
+__device__ __forceinline__ fx_t lookback_xf(const TileState &ts, int64_t tile, uint32_t epoch, int lane) {
+  Xf acc = xf_identity();
+  int64_t base = tile - 1;
+  for (;;) {
+    int64_t idx = base - lane;
+    Xf x;
+    if (idx < 0) {
+      x.kill = 1; x.a = 0; x.b = 0;  // before the first tile the state is 0
+    } else {
+      uint32_t st;
+      do { st = ld_acquire_u32(&ts.xf_status[idx]); } while ((st >> 2) != epoch || (st & 3u) == 0u);
+      x = load_xf_desc(ts, idx, st);
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      Xf y = shfl_xf(x, (lane + o) & 31);
+      if (lane + o < 32) x = xf_compose(y, x);  // y covers earlier tiles
+    }
+    Xf tot = shfl_xf(x, 0);
+    acc = xf_compose(tot, acc);
+    if (acc.kill) return acc.b;
+    base -= 32;
+  }
+}
+
+__device__ __forceinline__ Ex load_ex_desc(const TileState &ts, int64_t idx, uint32_t st) {
+  const uint64_t *p = ((st & 3u) == 2u) ? &ts.ex_inc[5 * idx] : &ts.ex_agg[5 * idx];
+  Ex e;
+  uint64_t mlo = __ldcg(p), mhi = __ldcg(p + 1);
+  e.M = fx_make(mhi, mlo);
+  e.beg = (int64_t)__ldcg(p + 2);
+  e.pk = (int64_t)__ldcg(p + 3);
+  uint32_t fl = (uint32_t)__ldcg(p + 4);
+  e.reset = ((st & 3u) == 2u) ? 1u : (fl & 1u);  // an inclusive state needs nothing further left
+  e.open = (fl >> 1) & 1u;
+  return e;
+}
+__device__ __forceinline__ void store_ex_desc(uint64_t *p, const Ex &e) {
+  __stcg(p, fx_lo(e.M));
+  __stcg(p + 1, fx_hi(e.M));
+  __stcg(p + 2, (uint64_t)e.beg);
+  __stcg(p + 3, (uint64_t)e.pk);
+  __stcg(p + 4, (uint64_t)(e.reset | (e.open << 1)));
+}
+
+// Look-back for the open-excursion state: returns the state at the start of `tile`.
+__device__ __forceinline__ Ex lookback_ex(const TileState &ts, int64_t tile, uint32_t epoch, int lane) {
+  Ex acc = ex_identity();
+  int64_t base = tile - 1;
+  for (;;) {
+    int64_t idx = base - lane;
+    Ex x;
+    if (idx < 0) {
+      x = ex_identity(); x.reset = 1; x.open = 0;
+    } else {
+      uint32_t st;
+      do { st = ld_acquire_u32(&ts.ex_status[idx]); } while ((st >> 2) != epoch || (st & 3u) == 0u);
+      x = load_ex_desc(ts, idx, st);
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      Ex y = shfl_ex(x, (lane + o) & 31);
+      if (lane + o < 32) x = ex_combine(y, x);
+    }
+    Ex tot = shfl_ex(x, 0);
+    acc = ex_combine(tot, acc);
+    if (acc.reset) return acc;
+    base -= 32;
+  }
+}
+
+// K4 + K5 + K6.  One CTA = one tile of 256 chunks (4096 positions), tile ids handed out in launch
+// order by an atomic counter so that a tile only ever waits on tiles that already run.
+__global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const LevelArgs A) {
+  __shared__ int64_t s_tile;
+  __shared__ Xf s_wxf[TILE_WARPS];
+  __shared__ Ex s_wex[TILE_WARPS];
+  __shared__ fx_t s_Sin;
+  __shared__ Ex s_Ein;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = (int64_t)(unsigned int)(atomicAdd(A.tile_counter, 1u) - A.tile_base);
+  __syncthreads();
+  const int64_t tile = s_tile;
+
+  ScanParams prm;
+  prm.min_width = A.prm->min_width;
+  prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
+
+  // ---- chunk -> position mapping ----
+  const int64_t q = tile * TILE_THREADS + tid;
+  int64_t p0 = 16;
+  int n_in = 0;
+  bool head = true;
+  uint32_t w[8];
+  if (A.nseg == 0) {
+    if (q < A.total_chunks) { p0 = A.dense_start + 16 * q; n_in = 16; head = (q == 0); }
+    const uint4 *v = reinterpret_cast<const uint4 *>(A.buf + p0 - 16);
+    uint4 a = __ldg(v), b = __ldg(v + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  } else {
+    if (q < A.total_chunks) {
+      int64_t lo = 0, hi = A.nseg;  // largest s in [0, nseg) with seg_chunk0[s] <= q
+      while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(&A.seg_chunk0[mid]) <= (uint64_t)q) lo = mid; else hi = mid;
+      }
+      int64_t c0 = (int64_t)__ldg(&A.seg_chunk0[lo]);
+      int64_t st = __ldg(&A.seg_start[lo]), ln = __ldg(&A.seg_len[lo]);
+      p0 = st + 16 * (q - c0);
+      int64_t rem = st + ln - p0;
+      n_in = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
+      head = (q == c0);
+    }
+    const uint32_t off = (uint32_t)(p0 & 3);
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(A.buf + (p0 - 16 - off));
+    uint32_t r[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r[i] = __ldg(wp + i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = __funnelshift_r(r[i], r[i + 1], off * 8);
+  }
+
+  // ---- decode + gather ----
+  uint32_t code[CHUNK], scored;
+  decode_scan(w, A.k, A.kmask, n_in, code, scored);
+  int64_t s[CHUNK];
+  uint32_t live = 0;
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) {
+    int64_t v = (scored & (1u << j)) ? __ldg(&A.wfx[code[j]]) : WFX_KILL;
+    s[j] = v;
+  }
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) {
+    if (s[j] != WFX_KILL) live |= 1u << j; else s[j] = 0;
+  }
+  if (A.inscan) {
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j)
+      if (scored & (1u << j)) atomicAdd(&A.inscan[code[j]], 1);
+  }
+
+  // ---- max-plus scan: chunk transform, block scan, look-back ----
+  Xf f = chunk_transform(s, live);
+  if (head) { fx_t v = xf_apply(f, 0); f.kill = 1; f.a = 0; f.b = v; }
+  Xf inc = f;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Xf y = shfl_xf(inc, (lane - o) & 31);
+    if (lane >= o) inc = xf_compose(y, inc);
+  }
+  Xf excl = shfl_xf(inc, (lane - 1) & 31);
+  if (lane == 0) excl = xf_identity();
+  if (lane == 31) s_wxf[warp] = inc;
+  __syncthreads();
+  Xf wpre = xf_identity();
+  for (int i = 0; i < warp; ++i) wpre = xf_compose(wpre, s_wxf[i]);
+  excl = xf_compose(wpre, excl);
+  if (warp == 0) {
+    Xf agg = xf_identity();
+#pragma unroll
+    for (int i = 0; i < TILE_WARPS; ++i) agg = xf_compose(agg, s_wxf[i]);
+    if (lane == 0) {
+      if (agg.kill) {  // the state at the tile end does not depend on the left: publish it at once
+        __stcg(&A.ts.xf_inc[2 * tile], fx_lo(agg.b));
+        __stcg(&A.ts.xf_inc[2 * tile + 1], fx_hi(agg.b));
+        st_release_u32(&A.ts.xf_status[tile], (A.epoch << 2) | 2u);
+      } else {
+        uint64_t *p = &A.ts.xf_agg[5 * tile];
+        __stcg(p, fx_lo(agg.a)); __stcg(p + 1, fx_hi(agg.a));
+        __stcg(p + 2, fx_lo(agg.b)); __stcg(p + 3, fx_hi(agg.b));
+        __stcg(p + 4, (uint64_t)agg.kill);
+        st_release_u32(&A.ts.xf_status[tile], (A.epoch << 2) | 1u);
+      }
+    }
+    fx_t S_tile = lookback_xf(A.ts, tile, A.epoch, lane);
+    if (lane == 0) {
+      if (!agg.kill) {
+        fx_t So = xf_apply(agg, S_tile);
+        __stcg(&A.ts.xf_inc[2 * tile], fx_lo(So));
+        __stcg(&A.ts.xf_inc[2 * tile + 1], fx_hi(So));
+        st_release_u32(&A.ts.xf_status[tile], (A.epoch << 2) | 2u);
+      }
+      s_Sin = S_tile;
+    }
+  }
+  __syncthreads();
+  const fx_t S_tile = s_Sin;
+  const fx_t S_in = head ? (fx_t)0 : xf_apply(excl, S_tile);
+
+  // ---- excursions: local walk, segmented scan of the open-excursion state, look-back ----
+  DevEmit emit{&A};
+  Ex ex;
+  fx_t preM;
+  int64_t prePk;
+  int first_zero;
+  chunk_walk(s, live, S_in, p0, prm, emit, ex, preM, prePk, first_zero);
+
+  Ex einc = ex;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Ex y = shfl_ex(einc, (lane - o) & 31);
+    if (lane >= o) einc = ex_combine(y, einc);
+  }
+  Ex eexcl = shfl_ex(einc, (lane - 1) & 31);
+  if (lane == 0) eexcl = ex_identity();
+  if (lane == 31) s_wex[warp] = einc;
+  __syncthreads();
+  Ex epre = ex_identity();
+  for (int i = 0; i < warp; ++i) epre = ex_combine(epre, s_wex[i]);
+  eexcl = ex_combine(epre, eexcl);
+  if (warp == 0) {
+    Ex agg = ex_identity();
+#pragma unroll
+    for (int i = 0; i < TILE_WARPS; ++i) agg = ex_combine(agg, s_wex[i]);
+    Ex E_tile;
+    if (S_tile > 0) {
+      // an excursion enters the tile: successors may need our aggregate while we look back
+      if (lane == 0) {
+        if (agg.reset) {
+          store_ex_desc(&A.ts.ex_inc[5 * tile], agg);
+          st_release_u32(&A.ts.ex_status[tile], (A.epoch << 2) | 2u);
+        } else {
+          store_ex_desc(&A.ts.ex_agg[5 * tile], agg);
+          st_release_u32(&A.ts.ex_status[tile], (A.epoch << 2) | 1u);
+        }
+      }
+      E_tile = lookback_ex(A.ts, tile, A.epoch, lane);
+      if (lane == 0 && !agg.reset) {
+        Ex full = ex_combine(E_tile, agg);
+        store_ex_desc(&A.ts.ex_inc[5 * tile], full);
+        st_release_u32(&A.ts.ex_status[tile], (A.epoch << 2) | 2u);
+      }
+    } else {
+      // state 0 at the tile start: nothing enters, and the first chunk makes the aggregate a reset
+      E_tile = ex_identity(); E_tile.reset = 1; E_tile.open = 0;
+      if (lane == 0) {
+        store_ex_desc(&A.ts.ex_inc[5 * tile], agg);
+        st_release_u32(&A.ts.ex_status[tile], (A.epoch << 2) | 2u);
+      }
+    }
+    if (lane == 0) s_Ein = E_tile;
+  }
+  __syncthreads();
+  if (!head) {
+    Ex E_in = ex_combine(s_Ein, eexcl);
+    chunk_finish_entering(S_in, E_in, preM, prePk, first_zero, p0, prm, emit);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// records [r0, r0 + n) of the finished level -> child segments + their chunk counts
+__global__ void __launch_bounds__(256) seg_build_kernel(const int64_t *__restrict__ rec_pk,
+                                                        const int64_t *__restrict__ rec_c,
+                                                        unsigned long long r0, unsigned long long n,
+                                                        uint64_t min_width, int inscan,
+                                                        int64_t *__restrict__ seg_start,
+                                                        int64_t *__restrict__ seg_len,
+                                                        uint64_t *__restrict__ seg_chunks) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t st, ln;
+  bool ok = child_segment(rec_pk[r0 + i], rec_c[r0 + i], min_width, inscan != 0, st, ln);
+  seg_start[i] = st;
+  seg_len[i] = ok ? ln : 0;
+  seg_chunks[i] = ok ? (uint64_t)segment_chunks(ln) : 0ull;
+}
+
+// ------------------------------------------------------------------------------------------
+// sorted record order -> reference layout.  starts = nseq + 1 global offsets (ks_layout.h).
+__global__ void __launch_bounds__(256) finalize_kernel(const uint32_t *__restrict__ perm, unsigned long long n,
+                                                       const int64_t *__restrict__ rec_beg,
+                                                       const int64_t *__restrict__ rec_pk,
+                                                       const int64_t *__restrict__ rec_mhi,
+                                                       const uint64_t *__restrict__ rec_mlo,
+                                                       const int64_t *__restrict__ starts, int nseq,
+                                                       const DevScanParams *__restrict__ prm,
+                                                       int32_t *__restrict__ pos, double *__restrict__ score) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long r = perm ? perm[i] : i;
+  int64_t beg = rec_beg[r], pk = rec_pk[r];
+  int lo = 0, hi = nseq;  // largest s with starts[s] <= beg
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (starts[mid] <= beg) lo = mid; else hi = mid;
+  }
+  pos[3 * i] = lo;
+  pos[3 * i + 1] = (int32_t)(beg - starts[lo]);
+  pos[3 * i + 2] = (int32_t)(pk - starts[lo]);
+  score[2 * i] = fx_to_double(fx_make((uint64_t)rec_mhi[r], rec_mlo[r]), prm->qs);
+  score[2 * i + 1] = 0.0;
+}
+
+__global__ void __launch_bounds__(256) copy_keys_kernel(const int64_t *__restrict__ rec_beg,
+                                                        unsigned long long n, uint64_t *__restrict__ keys) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = (uint64_t)rec_beg[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: score tables
+__global__ void __launch_bounds__(256) max_u32_kernel(const uint32_t *__restrict__ v, size_t n,
+                                                      uint32_t *__restrict__ out) {
+  uint32_t m = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = max(m, v[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// run heads of the sorted counts -> (count, first sorted position), appended unordered
+__global__ void __launch_bounds__(256) rle_heads_kernel(const uint32_t *__restrict__ keys, size_t n,
+                                                        uint32_t *__restrict__ gcount,
+                                                        uint32_t *__restrict__ gstart, uint32_t *ngroups,
+                                                        uint32_t cap) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t c = keys[i];
+  if (i == 0 || keys[i - 1] != c) {
+    uint32_t slot = atomicAdd(ngroups, 1u);
+    if (slot < cap) { gcount[slot] = c; gstart[slot] = (uint32_t)i; }
+  }
+}
+
+// rank of every k-mer from the linear pieces of ks_rankseg.h; p = position in the stable
+// (count, index) order, vals[p] = k-mer index.  gstart has ngroups + 1 entries.
+__global__ void __launch_bounds__(256) rank_eval_kernel(const uint32_t *__restrict__ vals, size_t n,
+                                                        const uint32_t *__restrict__ gstart, uint32_t ngroups,
+                                                        const uint32_t *__restrict__ seg_first,
+                                                        const unsigned long long *__restrict__ seg_j0,
+                                                        const double *__restrict__ seg_x0,
+                                                        const double *__restrict__ seg_inc,
+                                                        double *__restrict__ ranks) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  uint32_t lo = 0, hi = ngroups;  // largest g with gstart[g] <= p
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&gstart[mid]) <= p) lo = mid; else hi = mid;
+  }
+  unsigned long long j = p - __ldg(&gstart[lo]);
+  uint32_t a = __ldg(&seg_first[lo]), b = __ldg(&seg_first[lo + 1]);
+  while (b - a > 1) {
+    uint32_t mid = (a + b) >> 1;
+    if (__ldg(&seg_j0[mid]) <= j) a = mid; else b = mid;
+  }
+  ranks[vals[p]] = fma((double)(j - __ldg(&seg_j0[a])), __ldg(&seg_inc[a]), __ldg(&seg_x0[a]));
+}
+
+// W[x] = lut[group of counts[x]]  (log2 / +-1 / any pure function of the count)
+__global__ void __launch_bounds__(256) lut_apply_kernel(const uint32_t *__restrict__ counts, size_t n,
+                                                        const uint32_t *__restrict__ gcount, uint32_t ngroups,
+                                                        const double *__restrict__ lut, double *__restrict__ W) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t c = counts[i];
+  uint32_t lo = 0, hi = ngroups;  // largest g with gcount[g] <= c (exists: c is one of them)
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&gcount[mid]) <= c) lo = mid; else hi = mid;
+  }
+  W[i] = __ldg(&lut[lo]);
+}
+
+__global__ void __launch_bounds__(256) affine_kernel(double *__restrict__ W, size_t n, double sub, double div) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) W[i] = (W[i] - sub) / div;
+}
+
+__global__ void __launch_bounds__(256) fill_nan_kernel(double *__restrict__ W, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) W[i] = i == 0 ? 0.0 : __longlong_as_double(0x7ff8000000000000ll);
+}
+
+}  // namespace ks

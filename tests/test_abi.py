@@ -1,0 +1,52 @@
+"""CPU tier: the C-ABI library loads, exports every symbol include/kspans.h declares, and refuses
+to compute without a device (no CPU fallback).  No compute calls here."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "kspans.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ks_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    from kmer_spans_b200 import _lib
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libkspans_cuda.so does not export %s" % n
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    from kmer_spans_b200 import api
+    with pytest.raises(api.KspansError) as ei:
+        api.Context()
+    assert ei.value.code == 2 and "no CPU path" in str(ei.value)
+
+
+def test_kmer_seq_host_helper():
+    from kmer_spans_b200 import api
+    assert api.kmer_seq(2) == "AA AC AT AG CA CC CT CG TA TC TT TG GA GC GT GG".split()  # kmer_spans.R:81-83
+    assert api.kmer_seq(1) == ["A", "C", "T", "G"]
+
+
+def test_product_does_not_touch_the_oracle():
+    """the product package must not include, import, link or load anything under oracle/ or tests/"""
+    pkg = os.path.join(ROOT, "kmer_spans_b200")
+    pat = re.compile(r"^\s*(#\s*include|import\b|from\b)[^\n]*(oracle|ks_emu|tests[./]|_ref)|(CDLL|dlopen)[^\n]*(oracle|ks_emu|_ref)")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")):
+                for ln in open(os.path.join(dirpath, f)):
+                    code = ln.split("//")[0].split("#  ")[0]
+                    assert not pat.search(code), "%s: %s" % (f, ln.strip())

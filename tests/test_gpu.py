@@ -1,0 +1,309 @@
+"""GPU tier (-m gpu): the sm_100a path, called through the C ABI, against the CPU oracle
+(oracle/ks_oracle.c, pinned to the compiled reference by tests/test_oracle.py) on the same
+seeded inputs.
+
+Bars (BASELINE.json north_star): counts, rank tables, +-1-mode scores, span coordinates and
+in-scan counts bit-exact; log2 / rank-mode span scores within rtol 1e-9 here (spec: 1e-6) -- the
+GPU sums exactly in fixed point, the reference rounds after every addition.
+"""
+import numpy as np
+import pytest
+
+from kmer_spans_b200 import synth
+from tests.test_oracle import planted, rand_seq
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    from kmer_spans_b200 import api
+    c = api.Context()
+    yield c
+    c.close()
+
+
+def assert_spans(got, want, exact_scores, what=""):
+    gp, wp = got["pos"], want["pos"]
+    if gp.tolist() != wp.tolist():
+        n = min(len(gp), len(wp))
+        bad = next((i for i in range(n) if gp[i].tolist() != wp[i].tolist()), n)
+        raise AssertionError("%s: spans differ: got %d want %d; first difference at %d: got %s want %s" % (
+            what, len(gp), len(wp), bad, gp[bad:bad + 3].tolist(), wp[bad:bad + 3].tolist()))
+    if exact_scores:
+        assert got["score"].tobytes() == want["score"].tobytes(), what
+    else:
+        np.testing.assert_allclose(got["score"], want["score"], rtol=RTOL, atol=0, err_msg=what)
+
+
+# ---- counting ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 11, 13, 15])
+def test_counts_small(ctx, oracle, k):
+    rng = np.random.default_rng(1000 + k)
+    kk = min(k, 11)
+    for trial in range(8):
+        seqs = [rand_seq(rng, int(rng.integers(0, 3000)), p_n=rng.choice([0, 0.05, 0.3]),
+                         alphabet=rng.choice([b"ACGT", b"ACGTacgtRYKMSWBDHVUu-*."]))
+                for _ in range(int(rng.integers(1, 6)))]
+        seqs += [b"ACGTACGTACGTACGTACGT"[:k], b"NN" + b"ACGTACGTACGTACGTACGT"[:k],
+                 b"ACGTACGTACGTACGTACGT"[:k] + b"N", b"ACGTACGTACGTACGTACGT"[:k + 1], b"", b"N" * 40]
+        if k > 11:
+            seqs = seqs[:3]
+        n1, c1 = oracle.kmer_counts(seqs, k)
+        g = ctx.kmer_counts(seqs, k, with_f=False)
+        assert g["n"][1] == n1
+        assert (g["counts"] == c1).all()
+    del kk
+
+
+def test_counts_known_answers(ctx):
+    """the reference's own pins: test.R:365-375 (KA1) and test.R:66-77 (KA2)"""
+    from kmer_spans_b200 import api
+    g = ctx.kmer_counts(b"CGCCAATGCG", 2)
+    got = {a: int(b) for a, b in zip(api.kmer_seq(2), g["counts"]) if b}
+    assert got == {"CG": 2, "GC": 2, "CC": 1, "CA": 1, "AA": 1, "AT": 1, "TG": 1}
+    rng = np.random.default_rng(5)
+    s = rand_seq(rng, 100000)
+    c1 = ctx.kmer_counts(s, 2)["counts"]
+    c2 = ctx.kmer_counts(s + b"N" * 36 + s, 2)["counts"]
+    assert (c2 == 2 * c1).all()
+
+
+def test_counts_hot_kmers_and_many_contigs(ctx, oracle):
+    """poly-A / tandem arrays hammer single table entries; 3000 short contigs exercise packing"""
+    seqs = [b"A" * 200000, b"AC" * 100000, b"ACGNNACG" * 1000]
+    seqs += [s.tobytes() for s in synth.contigs(3000, seed=11, lo=20, hi=3000, k=10)]
+    for k in (4, 10):
+        n1, c1 = oracle.kmer_counts(seqs, k)
+        g = ctx.kmer_counts(seqs, k, with_f=False)
+        assert g["n"][1] == n1
+        assert (g["counts"] == c1).all()
+
+
+# ---- score tables -----------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [2, 4, 6, 8, 10])
+def test_ranks_bitexact(ctx, oracle, k):
+    rng = np.random.default_rng(1100 + k)
+    for trial in range(4):
+        s = planted(rng, int(rng.integers(4 ** min(k, 6), 60 * 4 ** min(k, 6))))
+        n, c = oracle.kmer_counts(s, k)
+        if n == 0:
+            continue
+        got = ctx.kmer_scores(c, k, n, 0)
+        assert got.tobytes() == oracle.rank(c, k, n).tobytes()
+
+
+def test_ranks_adversarial_tables(ctx, oracle):
+    rng = np.random.default_rng(9)
+    k = 9
+    n = 4 ** k
+    for trial in range(16):
+        kind = trial % 8
+        if kind == 0:
+            c = np.full(n, int(rng.integers(1, 5)), np.int32)
+        elif kind == 1:
+            c = rng.poisson(rng.uniform(0.2, 30), n).astype(np.int32)
+        elif kind == 2:
+            c = (rng.pareto(1.2, n) * 3).astype(np.int32)
+        elif kind == 3:
+            c = np.zeros(n, np.int32); c[rng.integers(0, n, 50)] = rng.integers(1, 2 ** 20, 50)
+        elif kind == 4:
+            c = (2 ** rng.integers(0, 12, n)).astype(np.int32)
+        elif kind == 5:
+            c = rng.integers(0, 3, n).astype(np.int32)
+        elif kind == 6:
+            c = np.ones(n, np.int32); c[: n // 2] = 3
+        else:
+            c = rng.integers(0, 2 ** 31 - 1, n).astype(np.int32) // int(rng.integers(1, 2 ** 20))
+        total = float(c.astype(np.int64).sum())
+        if kind == 4:
+            total = float(2 ** int(rng.integers(20, 40)))
+        if total == 0:
+            continue
+        got = ctx.kmer_scores(c, k, total, 0)
+        assert got.tobytes() == oracle.rank(c, k, total).tobytes(), (trial, kind)
+    zero = np.zeros(n, np.int32)
+    got = ctx.kmer_scores(zero, k, 0.0, 0)
+    assert got[0] == 0 and np.isnan(got[1:]).all()
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_mode_tables_bitexact(ctx, oracle, mode):
+    rng = np.random.default_rng(1200 + mode)
+    for k in (3, 6, 9):
+        s = planted(rng, 40 * 4 ** min(k, 6))
+        n, c = oracle.kmer_counts(s, k)
+        param = 0.6 if mode == 3 else float("nan")
+        got = ctx.kmer_scores(c, k, n, mode, param)
+        want = oracle.scores(c, k, n, mode, param)
+        assert got.tobytes() == want.tobytes()
+
+
+# ---- scan + spans -----------------------------------------------------------------------------
+CASES = [(2, 0.5, 20, 10), (3, 0.75, 20, 10), (4, 0.75, 5, 2), (5, 0.5, 0, 0), (6, 0.6, 10, 3),
+         (8, 0.75, 100, 20), (4, 0.5, -1, 0), (3, 0.9, 0, 0.5), (7, 0.5, 3, 1), (10, 0.75, 30, 5)]
+
+
+@pytest.mark.parametrize("k,thr,mw,ms", CASES)
+def test_low_comp_regions(ctx, oracle, k, thr, mw, ms):
+    rng = np.random.default_rng(1300 + k)
+    for trial in range(6):
+        seqs = [planted(rng, int(rng.integers(50, 30000))) for _ in range(int(rng.integers(1, 5)))]
+        if trial % 3 == 0:
+            seqs.insert(1, b"ACG"[: k - 1])  # shorter than k: skipped, seq_id still advances
+        o = oracle.low_comp(seqs, k, mw, ms, thr)
+        g = ctx.kmer_low_comp_regions(seqs, k, mw, ms, thr)
+        assert (g["n"] == o["n"]).all()
+        assert (g["counts"] == o["counts"]).all()
+        assert g["w_rank"].tobytes() == o["ranks"].tobytes()
+        assert_spans(g, o, exact_scores=False, what="k=%d thr=%g trial=%d" % (k, thr, trial))
+
+
+@pytest.mark.parametrize("k", [2, 5, 8])
+def test_kmer_regions_user_weights(ctx, oracle, k):
+    rng = np.random.default_rng(1400 + k)
+    for trial in range(12):
+        seqs = [planted(rng, int(rng.integers(50, 20000))) for _ in range(int(rng.integers(1, 4)))]
+        kind = trial % 4
+        if kind == 0:
+            W = rng.choice([-1.0, 1.0], 4 ** k, p=[0.7, 0.3])
+        elif kind == 1:
+            W = rng.normal(-0.3, 1.0, 4 ** k)
+        elif kind == 2:
+            n, c = oracle.kmer_counts(seqs, k)
+            W = oracle.scores(c, k, n, 2)
+        else:
+            W = rng.normal(-0.2, 1.0, 4 ** k)
+            W[rng.integers(0, 4 ** k, 3)] = np.nan
+            W[rng.integers(0, 4 ** k, 2)] = -np.inf
+        mw, ms = [(0, 0), (10, 3), (30, 8)][trial % 3]
+        o = oracle.kmer_regions(seqs, k, W, mw, ms)
+        g = ctx.kmer_regions(seqs, k, W, mw, ms)
+        assert g["n"] == o["n"]
+        assert_spans(g, o, exact_scores=(kind in (0, 2)), what="k=%d trial=%d" % (k, trial))
+        assert (g["counts"] == o["counts"]).all()  # in-scan counts incl. rescans
+
+
+def test_gpu_equals_host_emulation_bitexact(ctx, oracle):
+    """exact arithmetic: the kernels and the left-to-right host fold of the same chunk functions
+    (tests/emu) must agree bit for bit, scores included"""
+    from tests.emu.emu import Emu
+    emu = Emu()
+    rng = np.random.default_rng(77)
+    for k, thr in ((4, 0.5), (7, 0.75), (9, 0.6)):
+        seqs = [planted(rng, 40000), planted(rng, 5000)]
+        o = oracle.low_comp(seqs, k, 5, 1, thr)
+        e = emu.scan(seqs, k, o["ranks"], thr, 5, 1)
+        g = ctx.kmer_low_comp_regions(seqs, k, 5, 1, thr)
+        assert g["pos"].tolist() == e["pos"].tolist()
+        assert g["score"].tobytes() == e["score"].tobytes()
+        lv, rv = ctx.scan_stats()
+        assert lv == e["levels"]
+
+
+def test_config1_all_modes(ctx, oracle):
+    """BASELINE.json configs[0]: 1 Mb, k=8.  +-1 around the median gives run-sized excursions
+    (hundreds of tiles per look-back) and deep restart nesting."""
+    seq = synth.config1()[0].tobytes()
+    n, c = oracle.kmer_counts(seq, 8)
+    W = oracle.scores(c, 8, n, 2)
+    o = oracle.kmer_regions([seq], 8, W, 100, 20)
+    g = ctx.kmer_regions([seq], 8, W, 100, 20)
+    assert_spans(g, o, exact_scores=True, what="sign/user")
+    assert (g["counts"] == o["counts"]).all()
+    g = ctx.kmer_mode_regions([seq], 8, 2, 100, 20)
+    assert g["scores"].tobytes() == W.tobytes()
+    assert_spans(g, o, exact_scores=True, what="sign/fused")
+    o = oracle.low_comp([seq], 8, 100, 20, 0.75)
+    g = ctx.kmer_low_comp_regions([seq], 8, 100, 20, 0.75)
+    assert len(o["pos"]) > 20
+    assert g["w_rank"].tobytes() == o["ranks"].tobytes()
+    assert_spans(g, o, exact_scores=False, what="rank")
+    o = oracle.mode_regions([seq], 8, 1, 100, 20)
+    g = ctx.kmer_mode_regions([seq], 8, 1, 100, 20)
+    assert g["scores"].tobytes() == o["scores"].tobytes()
+    assert_spans(g, o, exact_scores=False, what="log2")
+    for thr, mw, ms in ((0.5, 0, 0), (0.5, 100, 20), (0.6, 10, 1)):  # deep rescans
+        o = oracle.low_comp([seq], 8, mw, ms, thr)
+        g = ctx.kmer_low_comp_regions([seq], 8, mw, ms, thr)
+        assert_spans(g, o, exact_scores=False, what="rank thr=%g" % thr)
+
+
+def test_contigs_all_modes(ctx, oracle):
+    """BASELINE.json configs[4] (subset): 1500 short contigs, k=10, all three modes"""
+    seqs = [s.tobytes() for s in synth.contigs(1500, seed=5, k=10)]
+    for mode, thr in ((0, 0.75), (1, 0.0), (2, 0.0)):
+        for mw in (0, 100):
+            o = oracle.mode_regions(seqs, 10, mode, mw, 20 if mw else 5, thr=thr)
+            g = ctx.kmer_mode_regions(seqs, 10, mode, mw, 20 if mw else 5, thr=thr)
+            assert g["n"] == o["n"]
+            assert (g["counts"] == o["counts"]).all()
+            assert g["scores"].tobytes() == o["scores"].tobytes()
+            assert_spans(g, o, exact_scores=(mode == 2), what="mode=%d mw=%d" % (mode, mw))
+
+
+def test_k12_20mb_rank_and_log2(ctx, oracle):
+    """BASELINE.json configs[1] scaled to 20 Mb so the oracle finishes in seconds"""
+    seq = synth.genome(20_000_000, 2, n_blocks=(5, 50_000)).tobytes()
+    o = oracle.low_comp([seq], 12, 100, 20, 0.75)
+    g = ctx.kmer_low_comp_regions([seq], 12, 100, 20, 0.75)
+    assert (g["counts"] == o["counts"]).all()
+    assert g["w_rank"].tobytes() == o["ranks"].tobytes()
+    assert len(o["pos"]) > 500
+    assert_spans(g, o, exact_scores=False, what="rank")
+    o = oracle.mode_regions([seq], 12, 1, 100, 20)
+    g = ctx.kmer_mode_regions([seq], 12, 1, 100, 20)
+    assert g["scores"].tobytes() == o["scores"].tobytes()
+    assert_spans(g, o, exact_scores=False, what="log2")
+
+
+def test_full_size_properties(ctx):
+    """BASELINE.json configs[1] at full size (250 Mb, k=12) through size-independent properties"""
+    seq = synth.config2()[0]
+    ss = ctx.upload([seq])
+    assert ss.bases == seq.size
+    del ss
+    r = ctx.kmer_low_comp_regions([seq], 12, 100, 20, 0.75)
+    counts = r["counts"]
+    assert counts.astype(np.int64).sum() == r["n"][0]                    # checksum of the table
+    assert r["n"][0] == seq.size - 5 * 50_000 - 6 * 11                    # 6 runs lose k-1 words each
+    ranks = r["w_rank"]
+    order = np.lexsort((np.arange(ranks.size), counts))
+    assert (np.diff(ranks[order]) >= 0).all()                             # ranks non-decreasing in count order
+    assert ranks[order[0]] == 0
+    top = ranks[order[-1]] + counts[order[-1]] / r["n"][0]
+    assert abs(top - 1.0) < 1e-9                                           # cumulative mass reaches 1
+    pos, score = r["pos"], r["score"]
+    assert len(pos) > 5000
+    assert (np.diff(pos[:, 1]) > 0).all()                                  # sorted by start, disjoint starts
+    assert (pos[:, 2] - pos[:, 1] >= 100).all() and (score[:, 0] >= 20).all() and (score[:, 1] == 0).all()
+    r2 = ctx.kmer_low_comp_regions([seq], 12, 100, 20, 0.75, want_tables=False)
+    assert r2["pos"].tobytes() == pos.tobytes() and r2["score"].tobytes() == score.tobytes()  # deterministic
+    # every planted tandem array (2 kb every 100 kb) is covered by a span
+    starts = np.arange(100_000 // 3, seq.size - 2000, 100_000)
+    idx = np.searchsorted(pos[:, 1], starts + 1500) - 1
+    covered = (pos[idx, 1] <= starts + 1500) & (pos[idx, 2] >= starts + 500)
+    in_n = np.array([seq[s + 1000] == ord("N") for s in starts])
+    assert covered[~in_n].mean() > 0.95
+
+
+# ---- error behaviour ----------------------------------------------------------------------------
+def test_errors(ctx):
+    from kmer_spans_b200.api import KspansError
+    with pytest.raises(KspansError, match="threshold must be between 0 and 1"):
+        ctx.kmer_low_comp_regions([b"ACGTACGT"], 2, 1, 1.0, 1.0)
+    with pytest.raises(KspansError, match="positive integer"):
+        ctx.kmer_counts([b"ACGT"], 0)
+    with pytest.raises(KspansError, match="4\\^k scores"):
+        ctx.kmer_regions([b"ACGT"], 2, np.zeros(15), 1, 1.0)
+    W = np.zeros(16)
+    W[3] = np.inf
+    with pytest.raises(KspansError) as ei:
+        ctx.kmer_regions([b"ACGTACGTAGAGAGAG"], 2, W, 1, 1.0)
+    assert ei.value.code == 3
+    r = ctx.kmer_regions([b"ACGTACGTAGAGAGAG"], 2, np.zeros(16), 1, 1.0)  # usable after an error
+    assert len(r["pos"]) == 0 and r["pos"].shape == (0, 3) and r["score"].shape == (0, 2)
