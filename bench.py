@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- Gbases/s of count + score + scan + spans (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (oracle/_ref)
+
+Workload (config.workload): BASELINE.json configs[1] -- synthetic 250 Mb chromosome-scale sequence
+with planted tandem / interspersed repeats and 5 N blocks, k=12, log2(f/f_med) score, min_width 100,
+min_score 20, one such sequence PER GPU (weak scaling; count tables all-reduced over NCCL).
+One step = one pass of the whole hot path over the resident sequence(s).
+
+  value  device-resident: sequence already in HBM, results (count table, score table, ordered span
+         list) left in HBM; timed with CUDA events on the launching stream, max over ranks.
+  e2e    through the host-buffer C-ABI call a user makes (ks_kmer_mode_regions): pinned host
+         sequence -> H2D -> pipeline -> D2H of the count table and the spans, wall clock.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K = 12
+MODE_LOG2 = 1
+MIN_W, MIN_SCORE, THR = 100, 20.0, 0.0
+N_BASES = 250_000_000
+METRIC = "Gbases/s count+score+scan+spans"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full summary, or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons of one GPU through NVML while the timed region runs"""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+        self.ok = False
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    m = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    m = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if m & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:  # NVML unavailable: report it instead of inventing numbers
+            self.err = repr(e)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_pass(seq_bytes, k=K):
+    """The reference's CPU path for this workload on ONE host thread (it has no threads):
+    sequence_kmer_count and kmer_regions are the UNMODIFIED reference (oracle/_ref); the log2 weight
+    table, which the reference computes in R, is the oracle's restatement (kso_scores).
+    Returns (seconds, n_spans, kind)."""
+    from oracle.ksoracle import Oracle
+    orc = Oracle()
+    try:
+        from oracle.ksoracle import Ref
+        ref = Ref()
+        kind = "reference"
+    except Exception:
+        ref = None
+        kind = "port"
+    t0 = time.perf_counter()
+    if ref is not None:
+        counts = np.zeros(4 ** k, np.int32)
+        n = ref.sequence_kmer_count(seq_bytes, k, counts)
+        W = orc.scores(counts, k, float(n), MODE_LOG2)
+        pos, sc, _ = ref.kmer_regions_core([seq_bytes], k, W, THR, MIN_W, MIN_SCORE)
+        nsp = len(pos)
+    else:
+        r = orc.mode_regions([seq_bytes], k, MODE_LOG2, MIN_W, MIN_SCORE, thr=THR)
+        nsp = len(r["pos"])
+    return time.perf_counter() - t0, nsp, kind
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from kmer_spans_b200 import synth
+    per_step = 150.0 / max(1, args.steps + args.warmup)
+    sample = int(min(50e6, max(2e6, per_step * 9e6)))
+    sample = min(sample, args.n_bases)
+    seq = synth.config2(args.n_bases if args.n_bases < 60_000_000 else 60_000_000, 2)[0][:sample].tobytes()
+    kind = "reference"
+    for _ in range(args.warmup):
+        _, _, kind = cpu_reference_pass(seq)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _, kind = cpu_reference_pass(seq)
+        t += dt
+    val = sample * args.steps / t / 1e9
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Gbases/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": 1, "kind": kind,
+                         "sample": "first %d bases of the config-2 sequence (seed 2), k=12, log2 mode, whole CPU "
+                                   "path per step; the reference is single-threaded" % sample},
+        "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "BASELINE.json configs[1]: synthetic %d Mb sequence per GPU with planted tandem and "
+                        "interspersed repeats, 5 N blocks; k=12; log2(f/f_med) score; min_width 100; min_score 20"
+                        % (args.n_bases // 1_000_000),
+            "k": K, "score_mode": "log2", "bases_per_gpu": args.n_bases, "sharding": "one sequence per GPU, "
+            "count table all-reduced (NCCL)" if world > 1 else "single GPU",
+            "l2": "inputs (%d MB sequence + 64 MiB count table + 128 MiB score table) exceed the 126 MB L2; "
+                  "no explicit flush" % (args.n_bases // 1_000_000)}
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-bases", type=int, default=N_BASES)
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from kmer_spans_b200 import api, synth
+    from kmer_spans_b200 import dist as ksd
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic input, pinned on the host, resident on the device -------------------------
+    seq = synth.config2(args.n_bases, 2 + rank)[0]
+    pinned = torch.from_numpy(seq).pin_memory()
+    seq_host = pinned.numpy()
+    stages = ksd.GpuStages(local_rank)
+    ctx = stages.ctx
+    stages.load([seq_host])
+    stages.alloc_tables(K)
+    counts_host = torch.empty(4 ** K, dtype=torch.int32).pin_memory()
+
+    def step():
+        n = stages.count(K)
+        total = n
+        if world > 1:
+            n_t = torch.tensor([n], dtype=torch.float64, device=dev)
+            dist.all_reduce(stages.counts, op=dist.ReduceOp.SUM)
+            dist.all_reduce(n_t, op=dist.ReduceOp.SUM)
+            total = float(n_t.item())
+        stages.scores_from_counts(K, total, MODE_LOG2, float("nan"))
+        nsp, _ = stages.scan(K, THR, MIN_W, MIN_SCORE, fetch=False)
+        return nsp
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        n_spans = step()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    time.sleep(0.15)
+    ctx.set_profile(True)
+    ctx.profile(reset=True)
+    ctx.reset_launches()
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        n_spans = step()
+    ms = ctx.timer_stop()
+    barrier()
+    launches = ctx.launches()
+    prof = ctx.profile(reset=True)
+    ctx.set_profile(False)
+    levels, revisit_chunks = ctx.scan_stats()
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = world * args.n_bases * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer entry point --------------------------------------
+    e2e_steps = args.e2e_steps or max(2, min(args.steps, 5))
+
+    def e2e_step():
+        if world == 1:
+            r = ctx.kmer_mode_regions([seq_host], K, MODE_LOG2, MIN_W, MIN_SCORE, thr=THR, want_tables=False,
+                                      counts_out=counts_host.numpy())
+            return len(r["pos"]), r["pos"].nbytes + r["score"].nbytes
+        r = ksd.run_sharded(stages, dist, [seq_host], [rank], K, MODE_LOG2, MIN_W, MIN_SCORE, thr=THR, gather=False)
+        counts_host.copy_(r["counts"], non_blocking=False)
+        return len(r["pos"]), r["pos"].nbytes + r["score"].nbytes
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    span_bytes = 0
+    for _ in range(e2e_steps):
+        _, sb = e2e_step()
+        span_bytes = sb
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_e.item())
+    e2e_val = world * args.n_bases * e2e_steps / e2e_s / 1e9
+    sampler.stop_flag = True
+    sampler.join(2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event pairs over the timed region) ---------
+    peak, peak_src = measured_peak()
+    nk = 4 ** K
+    alg = {  # algorithmic bytes per launch, DESIGN.md section 5 (1.5 B/base + 16 B/entry overall)
+        "count_kernel": 1.0 * args.n_bases + 4.0 * nk,
+        "scan_level0": 0.5 * args.n_bases + 8.0 * nk,
+    }
+    kern = {}
+    for name, (tot_ms, n) in prof.items():
+        if n:
+            kern[name] = {"ms_per_launch": tot_ms / n, "launches_per_step": n / args.steps,
+                          "ms_per_step": tot_ms / args.steps, "share_of_step": tot_ms / ms}
+    dom = max(("count_kernel", "scan_level0"), key=lambda nm: kern.get(nm, {}).get("ms_per_step", 0.0))
+    dom_ms = kern[dom]["ms_per_launch"]
+    achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(dom), "algorithmic_bytes_per_launch": alg[dom],
+                "ms_per_launch": dom_ms, "peak_source": peak_src,
+                "pipeline": {"algorithmic_bytes_per_step": 1.5 * args.n_bases + 16.0 * nk,
+                             "achieved": (1.5 * args.n_bases + 16.0 * nk) / (ms / args.steps * 1e-3) / 1e9,
+                             "frac": (1.5 * args.n_bases + 16.0 * nk) / (ms / args.steps * 1e-3) / 1e9 / peak},
+                "unit_rates": {"count_atomics_per_s": args.n_bases / (kern["count_kernel"]["ms_per_launch"] * 1e-3)
+                               if "count_kernel" in kern else None,
+                               "scan_gathers_per_s": args.n_bases / (kern["scan_level0"]["ms_per_launch"] * 1e-3)
+                               if "scan_level0" in kern else None},
+                "kernels": kern}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32 counts / int64+int128 exact fixed-point scan / f64 tables",
+        "data": "synthetic", "config": workload_config(args, world),
+        "clocks": sampler.result(),
+        "e2e": {"value": e2e_val, "unit": "Gbases/s", "h2d_bytes_per_step": int(args.n_bases),
+                "d2h_bytes_per_step": int(4 * nk + span_bytes), "steps": e2e_steps,
+                "call": "ks_kmer_mode_regions (host buffers)" if world == 1 else "dist.run_sharded (host buffers)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "spans_per_step": int(n_spans), "restart_levels": int(levels),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sample = min(args.n_bases, 25_000_000)
+        dt, nsp, kind = cpu_reference_pass(seq[:sample].tobytes())
+        out["cpu_baseline"] = {"value": sample / dt / 1e9, "unit": "Gbases/s", "cores": 1, "kind": kind,
+                               "sample": "first %d bases of the same sequence, same k / mode / thresholds, one pass "
+                                         "(%.1f s); count + scan = unmodified reference C, log2 table = oracle port"
+                                         % (sample, dt)}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

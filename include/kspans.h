@@ -122,6 +122,17 @@ int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double par
                     int min_width, double min_score, int32_t *d_counts, double *d_scores,
                     double *n_words, ks_spans *host_out_or_null, uint64_t *n_spans);
 
+/* -------- timing on the launching stream (CUDA events; what bench.py reports) ---------------- */
+int ks_ctx_timer_start(ks_ctx *ctx);
+int ks_ctx_timer_stop(ks_ctx *ctx, float *ms); /* records, synchronises, returns elapsed ms */
+/* per-kernel-class device time, measured live with event pairs around the launches.
+ * which: 0 count_kernel, 1 scan_level_kernel level 0, 2 scan_level_kernel deeper levels,
+ *        3 score-table stage (sort + rank/lut kernels, includes its host control steps), 4 wmax+wfx */
+enum { KS_PROF_COUNT = 0, KS_PROF_SCAN0 = 1, KS_PROF_SCANN = 2, KS_PROF_SCORES = 3, KS_PROF_WFX = 4, KS_PROF_N = 5 };
+void ks_ctx_set_profile(ks_ctx *ctx, int on);
+int ks_ctx_profile_get(ks_ctx *ctx, int which, double *ms_total, uint64_t *launches);
+void ks_ctx_profile_reset(ks_ctx *ctx);
+
 /* diagnostics of the last scan on this ctx: restart levels run and positions visited beyond level 0 */
 void ks_ctx_scan_stats(const ks_ctx *ctx, int *levels, uint64_t *revisited_chunks);
 

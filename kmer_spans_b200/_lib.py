@@ -42,6 +42,11 @@ SIGNATURES = {
     "ks_ctx_launches": (C.c_uint64, [_vp]),
     "ks_ctx_reset_launches": (None, [_vp]),
     "ks_ctx_scan_stats": (None, [_vp, C.POINTER(_i), _pu64]),
+    "ks_ctx_timer_start": (_i, [_vp]),
+    "ks_ctx_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
+    "ks_ctx_set_profile": (None, [_vp, _i]),
+    "ks_ctx_profile_get": (_i, [_vp, _i, _pd, _pu64]),
+    "ks_ctx_profile_reset": (None, [_vp]),
     "ks_kmer_counts": (_i, [_vp] + _SEQS + [_i, _vp, _pd]),
     "ks_kmer_regions": (_i, [_vp] + _SEQS + [_i, _vp, _i, _d, _pd, _vp, C.POINTER(KsSpans)]),
     "ks_kmer_low_comp_regions": (_i, [_vp] + _SEQS + [_i, _i, _d, _d, _pd, _vp, _vp, C.POINTER(KsSpans)]),

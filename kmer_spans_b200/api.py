@@ -105,6 +105,63 @@ class Context:
         self.lib.ks_ctx_scan_stats(self.h, C.byref(lv), C.byref(rv))
         return lv.value, rv.value
 
+    def timer_start(self):
+        self._ck(self.lib.ks_ctx_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._ck(self.lib.ks_ctx_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def set_profile(self, on=True):
+        self.lib.ks_ctx_set_profile(self.h, 1 if on else 0)
+
+    def profile(self, reset=False):
+        """{class: (total ms, launches)} measured with CUDA event pairs on the launching stream"""
+        names = ["count_kernel", "scan_level0", "scan_deeper", "scores_stage", "wfx_table"]
+        out = {}
+        for i, nm in enumerate(names):
+            ms, n = C.c_double(0), C.c_uint64(0)
+            self._ck(self.lib.ks_ctx_profile_get(self.h, i, C.byref(ms), C.byref(n)))
+            out[nm] = (ms.value, int(n.value))
+        if reset:
+            self.lib.ks_ctx_profile_reset(self.h)
+        return out
+
+    # ---- device stages on a resident SeqSet (what bench.py times) ---------------------------
+    def dev_pipeline(self, ss, k, mode, min_w, min_score, thr=0.0, param=float("nan"), d_counts=0, d_scores=0,
+                     fetch_spans=False):
+        """count -> scores(mode) -> scan with everything resident; d_counts / d_scores are device
+        pointers (int32[4^k], double[4^k]) owned by the caller"""
+        n = C.c_double(0)
+        ns = C.c_uint64(0)
+        sp = KsSpans()
+        self._ck(self.lib.ks_dev_pipeline(self.h, ss.h, int(k), int(mode), float(param), float(thr), int(min_w),
+                                          float(min_score), d_counts, d_scores, C.byref(n),
+                                          C.byref(sp) if fetch_spans else None, C.byref(ns)))
+        res = dict(n=n.value, n_spans=int(ns.value))
+        if fetch_spans:
+            res["pos"], res["score"] = _spans_to_numpy(self.lib, sp)
+        return res
+
+    def dev_count(self, ss, k, d_counts):
+        n = C.c_double(0)
+        self._ck(self.lib.ks_dev_count(self.h, ss.h, int(k), d_counts, C.byref(n)))
+        return n.value
+
+    def dev_scores(self, k, d_counts, total, mode, d_scores, param=float("nan")):
+        self._ck(self.lib.ks_dev_scores(self.h, int(k), d_counts, float(total), int(mode), float(param), d_scores))
+
+    def dev_scan(self, ss, k, d_W, thr, min_w, min_score, d_inscan=0, fetch_spans=True):
+        ns = C.c_uint64(0)
+        sp = KsSpans()
+        self._ck(self.lib.ks_dev_scan(self.h, ss.h, int(k), d_W, float(thr), int(min_w), float(min_score),
+                                      d_inscan or None, C.byref(sp) if fetch_spans else None, C.byref(ns)))
+        res = dict(n_spans=int(ns.value))
+        if fetch_spans:
+            res["pos"], res["score"] = _spans_to_numpy(self.lib, sp)
+        return res
+
     # ---- mirrors of the reference's R functions -------------------------------------------
     def kmer_counts(self, seq, k, with_f=True):
         """kmer.counts (kmer_spans.R:18-27): list(n = c(k, n), counts, f = counts / sum(counts))"""
@@ -155,20 +212,22 @@ class Context:
         pos, score = _spans_to_numpy(self.lib, sp)
         return dict(n=np.array([n[0], n[1]]), counts=counts, w_rank=ranks, pos=pos, score=score)
 
-    def kmer_mode_regions(self, seq, k, mode, min_w, min_score, thr=0.0, param=float("nan"), want_tables=True):
-        """extension: counts -> scores(mode) -> scan on the device (README.md:27-49 modes)"""
+    def kmer_mode_regions(self, seq, k, mode, min_w, min_score, thr=0.0, param=float("nan"), want_tables=True,
+                          counts_out=None, scores_out=None):
+        """extension: counts -> scores(mode) -> scan on the device (README.md:27-49 modes).
+        counts_out / scores_out: preallocated (e.g. pinned) numpy arrays to receive the tables."""
         a = _SeqArgs(_as_bytes_list(seq))
         k = int(k)
         if not 1 <= k <= 15:
             raise KspansError(_lib.KS_ERR_ARG, "k must be between 1 and 15")
-        counts = np.zeros(4 ** k, np.int32) if want_tables else None
-        scores = np.zeros(4 ** k, np.float64) if want_tables else None
+        counts = counts_out if counts_out is not None else (np.zeros(4 ** k, np.int32) if want_tables else None)
+        scores = scores_out if scores_out is not None else (np.zeros(4 ** k, np.float64) if want_tables else None)
         n = C.c_double(0)
         sp = KsSpans()
         self._ck(self.lib.ks_kmer_mode_regions(
             self.h, a.ptrs, a.lens, a.n, k, int(mode), float(param), float(thr), int(min_w), float(min_score),
-            C.byref(n), counts.ctypes.data if want_tables else None,
-            scores.ctypes.data if want_tables else None, C.byref(sp)))
+            C.byref(n), counts.ctypes.data if counts is not None else None,
+            scores.ctypes.data if scores is not None else None, C.byref(sp)))
         pos, score = _spans_to_numpy(self.lib, sp)
         return dict(n=n.value, counts=counts, scores=scores, pos=pos, score=score)
 

@@ -89,6 +89,44 @@ struct ks_ctx {
   size_t pinned_cap = 0;
   DBuf tmp_counts, tmp_scores, tmp_inscan, nwords;
 
+  // timing / profiling
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  bool profile = false;
+  struct ProfEv { int which; cudaEvent_t a, b; };
+  std::vector<ProfEv> prof_pending;
+  std::vector<cudaEvent_t> ev_pool;
+  double prof_ms[KS_PROF_N] = {0, 0, 0, 0, 0};
+  uint64_t prof_n[KS_PROF_N] = {0, 0, 0, 0, 0};
+  cudaEvent_t get_event() {
+    cudaEvent_t e = nullptr;
+    if (!ev_pool.empty()) { e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+  }
+  cudaEvent_t prof_begin() {
+    if (!profile) return nullptr;
+    cudaEvent_t a = get_event();
+    cudaEventRecord(a, stream);
+    return a;
+  }
+  void prof_end(int which, cudaEvent_t a) {
+    if (!a) return;
+    cudaEvent_t b = get_event();
+    cudaEventRecord(b, stream);
+    prof_pending.push_back({which, a, b});
+  }
+  void prof_resolve() {
+    if (prof_pending.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (auto &p : prof_pending) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { prof_ms[p.which] += ms; prof_n[p.which] += 1; }
+      ev_pool.push_back(p.a);
+      ev_pool.push_back(p.b);
+    }
+    prof_pending.clear();
+  }
+
   int fail(int code, const char *fmt, ...) {
     char b[512];
     va_list ap;
@@ -174,6 +212,10 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->tmp_counts, &ctx->tmp_scores,
                  &ctx->tmp_inscan, &ctx->nwords};
   for (DBuf *b : all) b->release();
+  ctx->prof_resolve();
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->t0) cudaEventDestroy(ctx->t0);
+  if (ctx->t1) cudaEventDestroy(ctx->t1);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -191,6 +233,36 @@ void ks_ctx_reset_launches(ks_ctx *ctx) { if (ctx) ctx->launches = 0; }
 void ks_ctx_scan_stats(const ks_ctx *ctx, int *levels, uint64_t *revisited_chunks) {
   if (levels) *levels = ctx ? ctx->last_levels : 0;
   if (revisited_chunks) *revisited_chunks = ctx ? ctx->last_revisit_chunks : 0;
+}
+
+int ks_ctx_timer_start(ks_ctx *ctx) {
+  if (!ctx) return KS_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->t0) { CK(cudaEventCreate(&ctx->t0)); CK(cudaEventCreate(&ctx->t1)); }
+  CK(cudaEventRecord(ctx->t0, ctx->stream));
+  return KS_OK;
+}
+int ks_ctx_timer_stop(ks_ctx *ctx, float *ms) {
+  if (!ctx || !ctx->t0) return KS_ERR_ARG;
+  CK(cudaEventRecord(ctx->t1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->t1));
+  float v = 0;
+  CK(cudaEventElapsedTime(&v, ctx->t0, ctx->t1));
+  if (ms) *ms = v;
+  return KS_OK;
+}
+void ks_ctx_set_profile(ks_ctx *ctx, int on) { if (ctx) ctx->profile = on != 0; }
+int ks_ctx_profile_get(ks_ctx *ctx, int which, double *ms_total, uint64_t *launches) {
+  if (!ctx || which < 0 || which >= KS_PROF_N) return KS_ERR_ARG;
+  ctx->prof_resolve();
+  if (ms_total) *ms_total = ctx->prof_ms[which];
+  if (launches) *launches = ctx->prof_n[which];
+  return KS_OK;
+}
+void ks_ctx_profile_reset(ks_ctx *ctx) {
+  if (!ctx) return;
+  ctx->prof_resolve();
+  for (int i = 0; i < KS_PROF_N; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
 }
 
 int ks_kmer_seq(int k, uint64_t code, char *out) {
@@ -335,8 +407,10 @@ int ks_dev_count(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, doub
   CK(cudaMemsetAsync(d_counts, 0, n * sizeof(int32_t), st));
   CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
   int64_t nchunks = (s->total - 16) / 16;
+  cudaEvent_t pe = ctx->prof_begin();
   count_kernel<<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
       s->d_buf, nchunks, k, (uint32_t)(n - 1), d_counts, ctx->nwords.as<unsigned long long>());
+  ctx->prof_end(KS_PROF_COUNT, pe);
   LAUNCHED(1);
   CK(cudaGetLastError());
   unsigned long long nw = 0;
@@ -359,6 +433,10 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
   cudaStream_t st = ctx->stream;
   const size_t n = (size_t)1 << (2 * k);
   const bool rank_mode = (mode == KS_MODE_RANK || mode == KS_MODE_RANK_REL);
+  struct ProfScope {
+    ks_ctx *c; cudaEvent_t a;
+    ~ProfScope() { c->prof_end(KS_PROF_SCORES, a); }
+  } prof_scope{ctx, ctx->prof_begin()};
   if (rank_mode && total == 0) {
     // 0/0 addends: every rank but the first in sort order (k-mer 0) is NaN (:200)
     fill_nan_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(d_scores, n);
@@ -544,8 +622,10 @@ int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, doubl
   CK(ctx->rec_count.ensure(64));
   DevScanParams *d_prm = ctx->prm.as<DevScanParams>();
   CK(cudaMemsetAsync(d_prm, 0, sizeof(DevScanParams), st));
+  cudaEvent_t pw = ctx->prof_begin();
   wmax_kernel<<<grid_for(nk, 256), 256, 0, st>>>(d_W, nk, thr, d_prm);
   wfx_kernel<<<grid_for(nk, 256), 256, 0, st>>>(d_W, nk, thr, ctx->wfx.as<int64_t>(), d_prm, mw, min_score);
+  ctx->prof_end(KS_PROF_WFX, pw);
   LAUNCHED(2);
   CK(cudaGetLastError());
 
@@ -609,7 +689,9 @@ int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, doubl
     A.rec_mlo = ctx->rec_mlo.as<uint64_t>();
     A.rec_count = d_rec_count;
     A.rec_cap = ctx->rec_cap;
+    cudaEvent_t ps = ctx->prof_begin();
     scan_level_kernel<<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    ctx->prof_end(level == 0 ? KS_PROF_SCAN0 : KS_PROF_SCANN, ps);
     LAUNCHED(1);
     CK(cudaGetLastError());
     struct { unsigned long long cnt; } hres;

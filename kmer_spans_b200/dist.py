@@ -1,0 +1,115 @@
+"""Multi-GPU composition of the hot path: one process per GPU (torch.distributed, NCCL over NVLink).
+
+The path shards by whole sequences (chromosomes / contigs), balanced by length:
+  count      local int32[4^k] table per rank             -> all_reduce(SUM) over NCCL   (real exchange)
+  n_words    local scalar                                -> all_reduce(SUM)
+  scores     recomputed redundantly from the reduced table (deterministic, identical on all ranks)
+  scan       each rank scans its own sequences; runs never cross sequences, so no carry crosses
+             a shard boundary and no halo is needed
+  spans      per-rank lists keep the ORIGINAL 0-based seq_id; rank 0 gathers and orders them
+This mirrors what kmer_low_comp_regions does over all sequences of one call
+(/root/reference/src/kmer_spans.c:592-612: one shared count table, then a scan per sequence).
+
+The stage functions are injectable so that the sharding / reduction / merge logic can be exercised
+with world_size-2 gloo on CPU (tests/test_dist.py) -- the stand-in stages there are test code.
+"""
+import numpy as np
+
+
+def plan_shards(lengths, world):
+    """Longest-processing-time assignment of whole sequences to ranks.
+    Returns a list (per rank) of sequence indices in ascending order."""
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    load = [0] * world
+    out = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda j: (load[j], j))
+        out[r].append(i)
+        load[r] += int(lengths[i])
+    return [sorted(x) for x in out]
+
+
+def merge_spans(parts):
+    """parts: list of (pos (n,3) with GLOBAL seq ids, score (n,2)); returns them ordered by
+    (seq_id, start) -- the reference's discovery order."""
+    pos = np.concatenate([p for p, _ in parts]) if parts else np.zeros((0, 3), np.int32)
+    score = np.concatenate([s for _, s in parts]) if parts else np.zeros((0, 2))
+    if len(pos):
+        o = np.lexsort((pos[:, 1], pos[:, 0]))
+        pos, score = pos[o], score[o]
+    return pos, score
+
+
+class GpuStages:
+    """The product stages: kernels of libkspans_cuda.so on this rank's GPU; tables live in torch
+    CUDA tensors so that torch.distributed can reduce them in place."""
+
+    def __init__(self, device):
+        import torch
+        from . import api
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.ctx = api.Context(device)
+        self.ss = None
+
+    def load(self, seqs):
+        if self.ss is not None:
+            self.ss.free()
+        self.ss = self.ctx.upload(seqs) if len(seqs) else None
+
+    def alloc_tables(self, k):
+        t = self.torch
+        self.counts = t.zeros(4 ** k, dtype=t.int32, device=self.device)
+        self.scores = t.empty(4 ** k, dtype=t.float64, device=self.device)
+        t.cuda.synchronize(self.device)
+        return self.counts
+
+    def count(self, k):
+        if self.ss is None:
+            self.counts.zero_()
+            self.torch.cuda.synchronize(self.device)
+            return 0.0
+        return self.ctx.dev_count(self.ss, k, self.counts.data_ptr())
+
+    def scores_from_counts(self, k, total, mode, param):
+        self.torch.cuda.synchronize(self.device)  # the reduced table is ready before our stream reads it
+        self.ctx.dev_scores(k, self.counts.data_ptr(), total, mode, self.scores.data_ptr(), param)
+
+    def scan(self, k, thr, min_w, min_score, fetch=True):
+        if self.ss is None:
+            return np.zeros((0, 3), np.int32), np.zeros((0, 2))
+        r = self.ctx.dev_scan(self.ss, k, self.scores.data_ptr(), thr, min_w, min_score, 0, fetch_spans=fetch)
+        if not fetch:
+            return r["n_spans"], None
+        return r["pos"], r["score"]
+
+
+def run_sharded(stages, dist, seqs_local, local_ids, k, mode, min_w, min_score, thr=0.0, param=float("nan"),
+                gather=True, fetch=True):
+    """One pass of count -> all_reduce -> scores -> scan over this rank's sequences.
+    stages: GpuStages (or a test stand-in with the same methods); dist: torch.distributed or None.
+    local_ids: original indices of seqs_local.  Returns dict(n, counts, pos, score) (spans on rank 0
+    when gather, else this rank's)."""
+    import torch
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    stages.load(seqs_local)
+    counts = stages.alloc_tables(k)
+    n_local = stages.count(k)
+    n_t = torch.tensor([n_local], dtype=torch.float64, device=counts.device)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)   # the one real exchange of this path
+        dist.all_reduce(n_t, op=dist.ReduceOp.SUM)
+    total = float(n_t.item())
+    stages.scores_from_counts(k, total, mode, param)
+    pos, score = stages.scan(k, thr, min_w, min_score, fetch=fetch)
+    if not fetch:
+        return dict(n=total, counts=counts, n_spans=pos)
+    ids = np.asarray(local_ids, np.int32)
+    if len(pos):
+        pos = pos.copy()
+        pos[:, 0] = ids[pos[:, 0]]
+    if world > 1 and gather:
+        parts = [None] * world
+        dist.all_gather_object(parts, (pos, score))
+        pos, score = merge_spans(parts)
+    return dict(n=total, counts=counts, pos=pos, score=score)
