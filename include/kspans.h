@@ -117,6 +117,11 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
 int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
                 double min_score, int32_t *d_inscan_or_null, ks_spans *host_out_or_null,
                 uint64_t *n_spans);
+/* Scan with score = f(count) for the count-derived modes: f is the function the last
+ * ks_dev_scores(mode LOG2 | SIGN) on this ctx derived (d_scores may be NULL there).  The kernel
+ * gathers the 4-byte count (table L2 resident up to k = 12) and maps it through a dense LUT. */
+int ks_dev_scan_counts(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
+                       int min_width, double min_score, ks_spans *host_out_or_null, uint64_t *n_spans);
 /* count -> scores(mode) -> scan, all resident; spans stay on the device unless host_out != NULL */
 int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double param, double thr,
                     int min_width, double min_score, int32_t *d_counts, double *d_scores,

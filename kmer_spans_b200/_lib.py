@@ -61,6 +61,7 @@ SIGNATURES = {
     "ks_dev_count": (_i, [_vp, _vp, _i, _vp, _pd]),
     "ks_dev_scores": (_i, [_vp, _i, _vp, _d, _i, _d, _vp]),
     "ks_dev_scan": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, _vp, C.POINTER(KsSpans), _pu64]),
+    "ks_dev_scan_counts": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, C.POINTER(KsSpans), _pu64]),
     "ks_dev_pipeline": (_i, [_vp, _vp, _i, _i, _d, _d, _i, _d, _vp, _vp, _pd, C.POINTER(KsSpans), _pu64]),
 }
 

@@ -162,6 +162,17 @@ class Context:
             res["pos"], res["score"] = _spans_to_numpy(self.lib, sp)
         return res
 
+    def dev_scan_counts(self, ss, k, d_counts, thr, min_w, min_score, fetch_spans=True):
+        """scan with score = f(count), f from the last dev_scores(mode LOG2 | SIGN)"""
+        ns = C.c_uint64(0)
+        sp = KsSpans()
+        self._ck(self.lib.ks_dev_scan_counts(self.h, ss.h, int(k), d_counts, float(thr), int(min_w), float(min_score),
+                                             C.byref(sp) if fetch_spans else None, C.byref(ns)))
+        res = dict(n_spans=int(ns.value))
+        if fetch_spans:
+            res["pos"], res["score"] = _spans_to_numpy(self.lib, sp)
+        return res
+
     # ---- mirrors of the reference's R functions -------------------------------------------
     def kmer_counts(self, seq, k, with_f=True):
         """kmer.counts (kmer_spans.R:18-27): list(n = c(k, n), counts, f = counts / sum(counts))"""

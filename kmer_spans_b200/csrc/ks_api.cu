@@ -84,6 +84,12 @@ struct ks_ctx {
   // score scratch
   DBuf sc_keys_a, sc_keys_b, sc_vals_a, sc_vals_b, sc_small, sc_gcount, sc_gstart, sc_segfirst, sc_segj0,
       sc_segx0, sc_seginc, sc_lut;
+  // count -> score function of the last ks_dev_scores(LOG2 | SIGN): one value per distinct count
+  DBuf lut_fx, lut_spc, lut_spv;
+  bool lut_valid = false;
+  int lut_k = 0;
+  std::vector<uint32_t> lut_gcount;
+  std::vector<double> lut_gval;
   // staging / misc
   void *pinned = nullptr;
   size_t pinned_cap = 0;
@@ -210,7 +216,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->out_score, &ctx->sc_keys_a, &ctx->sc_keys_b, &ctx->sc_vals_a, &ctx->sc_vals_b,
                  &ctx->sc_small, &ctx->sc_gcount, &ctx->sc_gstart, &ctx->sc_segfirst, &ctx->sc_segj0,
                  &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->tmp_counts, &ctx->tmp_scores,
-                 &ctx->tmp_inscan, &ctx->nwords};
+                 &ctx->tmp_inscan, &ctx->nwords, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -425,7 +431,8 @@ int ks_dev_count(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, doub
 int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int mode, double param,
                   double *d_scores) {
   if (!ctx) return KS_ERR_ARG;
-  if (!d_counts || !d_scores) return ctx->fail(KS_ERR_ARG, "ks_dev_scores: null argument");
+  const bool count_fn_mode = (mode == KS_MODE_LOG2 || mode == KS_MODE_SIGN);
+  if (!d_counts || (!d_scores && !count_fn_mode)) return ctx->fail(KS_ERR_ARG, "ks_dev_scores: null argument");
   int rc = check_k(ctx, k);
   if (rc) return rc;
   if (mode < KS_MODE_RANK || mode > KS_MODE_RANK_REL) return ctx->fail(KS_ERR_ARG, "unknown score mode %d", mode);
@@ -551,16 +558,22 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
           lut[g] = f >= f_t ? 1.0 : -1.0;
         }
       }
-      CK(ctx->sc_gcount.ensure((ng + 1) * 4));
-      CK(ctx->sc_lut.ensure(ng * 8 + 8));
-      CK(cudaMemcpyAsync(ctx->sc_gcount.p, gcount.data(), ng * 4, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(ctx->sc_lut.p, lut.data(), ng * 8, cudaMemcpyHostToDevice, st));
-      lut_apply_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_counts), n,
-                                                             ctx->sc_gcount.as<uint32_t>(), (uint32_t)ng,
-                                                             ctx->sc_lut.as<double>(), d_scores);
-      LAUNCHED(1);
-      CK(cudaGetLastError());
-      CK(cudaStreamSynchronize(st));
+      ctx->lut_gcount = gcount;
+      ctx->lut_gval = lut;
+      ctx->lut_valid = true;
+      ctx->lut_k = k;
+      if (d_scores) {  // the per-k-mer table itself (an output; the scan gathers counts + LUT instead)
+        CK(ctx->sc_gcount.ensure((ng + 1) * 4));
+        CK(ctx->sc_lut.ensure(ng * 8 + 8));
+        CK(cudaMemcpyAsync(ctx->sc_gcount.p, gcount.data(), ng * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->sc_lut.p, lut.data(), ng * 8, cudaMemcpyHostToDevice, st));
+        lut_apply_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_counts), n,
+                                                               ctx->sc_gcount.as<uint32_t>(), (uint32_t)ng,
+                                                               ctx->sc_lut.as<double>(), d_scores);
+        LAUNCHED(1);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+      }
     }
   }
   if (mode == KS_MODE_RANK_REL) {
@@ -577,15 +590,12 @@ static int ensure_tiles(ks_ctx *ctx, size_t tiles) {
   if (tiles <= ctx->tiles_cap) return KS_OK;
   size_t t = tiles + tiles / 4 + 64;
   cudaStream_t st = ctx->stream;
-  CK(ctx->xf_status.ensure(t * 4));
-  CK(ctx->ex_status.ensure(t * 4));
-  CK(ctx->xf_agg.ensure(t * 40));
-  CK(ctx->xf_inc.ensure(t * 16));
-  CK(ctx->ex_agg.ensure(t * 40));
-  CK(ctx->ex_inc.ensure(t * 40));
-  CK(cudaMemsetAsync(ctx->xf_status.p, 0, ctx->xf_status.cap, st));
-  CK(cudaMemsetAsync(ctx->ex_status.p, 0, ctx->ex_status.cap, st));
-  ctx->epoch = 0;  // fresh, zeroed status words
+  DBuf *d[4] = {&ctx->xf_agg, &ctx->xf_inc, &ctx->ex_agg, &ctx->ex_inc};  // xfA, xfB, exA, exB
+  for (DBuf *b : d) {
+    CK(b->ensure(t * 16));
+    CK(cudaMemsetAsync(b->p, 0, b->cap, st));
+  }
+  ctx->epoch = 0;  // fresh, zeroed tags
   ctx->tiles_cap = t;
   return KS_OK;
 }
@@ -602,33 +612,24 @@ static int ensure_recs(ks_ctx *ctx, size_t cap) {
   return KS_OK;
 }
 
-int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
-                double min_score, int32_t *d_inscan, ks_spans *host_out, uint64_t *n_spans) {
-  if (!ctx) return KS_ERR_ARG;
-  if (!s || !d_W) return ctx->fail(KS_ERR_ARG, "ks_dev_scan: null argument");
-  int rc = check_k(ctx, k);
-  if (rc) return rc;
-  if (host_out) { host_out->pos = nullptr; host_out->score = nullptr; host_out->n = 0; }
-  if (n_spans) *n_spans = 0;
-  CK(cudaSetDevice(ctx->device));
+namespace {
+struct ScanTable {  // what scan_level_kernel gathers from
+  bool use_lut = false;
+  const uint32_t *counts = nullptr;
+  uint32_t lut_size = 0, sp_n = 0;
+};
+}  // namespace
+
+// Level loop + ordering + marshaling.  The fixed-point table (ctx->wfx, or ctx->lut_fx + sparse list)
+// and the DevScanParams block (ctx->prm) have been prepared on the stream by the caller.
+static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &tab, uint64_t mw,
+                     int32_t *d_inscan, ks_spans *host_out, uint64_t *n_spans) {
+  int rc = KS_OK;
   cudaStream_t st = ctx->stream;
   const size_t nk = (size_t)1 << (2 * k);
-  const uint64_t mw = (uint64_t)(int64_t)min_width;  // negative R integers wrap exactly like size_t (:243)
-
-  // score table -> exact fixed point
-  CK(ctx->wfx.ensure(nk * 8));
-  CK(ctx->prm.ensure(sizeof(DevScanParams)));
+  DevScanParams *d_prm = ctx->prm.as<DevScanParams>();
   CK(ctx->tile_counter.ensure(64));
   CK(ctx->rec_count.ensure(64));
-  DevScanParams *d_prm = ctx->prm.as<DevScanParams>();
-  CK(cudaMemsetAsync(d_prm, 0, sizeof(DevScanParams), st));
-  cudaEvent_t pw = ctx->prof_begin();
-  wmax_kernel<<<grid_for(nk, 256), 256, 0, st>>>(d_W, nk, thr, d_prm);
-  wfx_kernel<<<grid_for(nk, 256), 256, 0, st>>>(d_W, nk, thr, ctx->wfx.as<int64_t>(), d_prm, mw, min_score);
-  ctx->prof_end(KS_PROF_WFX, pw);
-  LAUNCHED(2);
-  CK(cudaGetLastError());
-
   unsigned long long *d_rec_count = ctx->rec_count.as<unsigned long long>();
   CK(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), st));
   if (!ctx->counter_init) {
@@ -638,6 +639,8 @@ int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, doubl
   }
 
   const int64_t dense_chunks = (s->total - 16) / 16;
+  if (s->total >= (1ll << 32))
+    return ctx->fail(KS_ERR_ARG, "one scan covers at most 2^32 bytes of sequence per GPU (shard the input)");
   rc = ensure_recs(ctx, std::max<size_t>((size_t)1 << 16, (size_t)(dense_chunks / 64)));
   if (rc) return rc;
 
@@ -656,6 +659,12 @@ int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, doubl
     memset(&A, 0, sizeof A);
     A.buf = s->d_buf;
     A.wfx = ctx->wfx.as<int64_t>();
+    A.counts = tab.counts;
+    A.lut = ctx->lut_fx.as<int64_t>();
+    A.lut_size = tab.lut_size;
+    A.sp_count = ctx->lut_spc.as<uint32_t>();
+    A.sp_val = ctx->lut_spv.as<int64_t>();
+    A.sp_n = tab.sp_n;
     A.prm = d_prm;
     A.k = k;
     A.kmask = (uint32_t)(nk - 1);
@@ -666,16 +675,16 @@ int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, doubl
     A.dense_start = 16;
     A.total_chunks = total_chunks;
     A.inscan = count_inscan ? d_inscan : nullptr;
-    A.ts.xf_status = ctx->xf_status.as<uint32_t>();
-    A.ts.xf_agg = ctx->xf_agg.as<uint64_t>();
-    A.ts.xf_inc = ctx->xf_inc.as<uint64_t>();
-    A.ts.ex_status = ctx->ex_status.as<uint32_t>();
-    A.ts.ex_agg = ctx->ex_agg.as<uint64_t>();
-    A.ts.ex_inc = ctx->ex_inc.as<uint64_t>();
+    A.ts.xfA = ctx->xf_agg.as<uint4>();
+    A.ts.xfB = ctx->xf_inc.as<uint4>();
+    A.ts.exA = ctx->ex_agg.as<uint4>();
+    A.ts.exB = ctx->ex_inc.as<uint4>();
     ctx->epoch += 1;
-    if (ctx->epoch >= (1u << 30) - 1) {  // epoch space exhausted: start over with zeroed words
-      CK(cudaMemsetAsync(ctx->xf_status.p, 0, ctx->xf_status.cap, st));
-      CK(cudaMemsetAsync(ctx->ex_status.p, 0, ctx->ex_status.cap, st));
+    if (ctx->epoch >= (1u << 28) - 1) {  // epoch space exhausted: start over with zeroed tags
+      CK(cudaMemsetAsync(ctx->xf_agg.p, 0, ctx->xf_agg.cap, st));
+      CK(cudaMemsetAsync(ctx->xf_inc.p, 0, ctx->xf_inc.cap, st));
+      CK(cudaMemsetAsync(ctx->ex_agg.p, 0, ctx->ex_agg.cap, st));
+      CK(cudaMemsetAsync(ctx->ex_inc.p, 0, ctx->ex_inc.cap, st));
       ctx->epoch = 1;
     }
     A.epoch = ctx->epoch;
@@ -690,7 +699,8 @@ int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, doubl
     A.rec_count = d_rec_count;
     A.rec_cap = ctx->rec_cap;
     cudaEvent_t ps = ctx->prof_begin();
-    scan_level_kernel<<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    if (tab.use_lut) scan_level_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else scan_level_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     ctx->prof_end(level == 0 ? KS_PROF_SCAN0 : KS_PROF_SCANN, ps);
     LAUNCHED(1);
     CK(cudaGetLastError());
@@ -789,6 +799,97 @@ int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, doubl
   return KS_OK;
 }
 
+int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
+                double min_score, int32_t *d_inscan, ks_spans *host_out, uint64_t *n_spans) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!s || !d_W) return ctx->fail(KS_ERR_ARG, "ks_dev_scan: null argument");
+  int rc = check_k(ctx, k);
+  if (rc) return rc;
+  if (host_out) { host_out->pos = nullptr; host_out->score = nullptr; host_out->n = 0; }
+  if (n_spans) *n_spans = 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t nk = (size_t)1 << (2 * k);
+  const uint64_t mw = (uint64_t)(int64_t)min_width;  // negative R integers wrap exactly like size_t (:243)
+  // score table -> exact fixed point (W - thr as the reference computes it at :268)
+  CK(ctx->wfx.ensure(nk * 8));
+  CK(ctx->prm.ensure(sizeof(DevScanParams)));
+  DevScanParams *d_prm = ctx->prm.as<DevScanParams>();
+  CK(cudaMemsetAsync(d_prm, 0, sizeof(DevScanParams), st));
+  cudaEvent_t pw = ctx->prof_begin();
+  wmax_kernel<<<grid_for(nk, 256), 256, 0, st>>>(d_W, nk, thr, d_prm);
+  wfx_kernel<<<grid_for(nk, 256), 256, 0, st>>>(d_W, nk, thr, ctx->wfx.as<int64_t>(), d_prm, mw, min_score);
+  ctx->prof_end(KS_PROF_WFX, pw);
+  LAUNCHED(2);
+  CK(cudaGetLastError());
+  ScanTable tab;
+  return scan_core(ctx, s, k, tab, mw, d_inscan, host_out, n_spans);
+}
+
+// Scan with score = f(count): the count -> score function is the one the last
+// ks_dev_scores(mode LOG2 | SIGN) on this ctx derived (cached per distinct count on the host).
+// The kernel gathers the 4-byte count (table stays L2 resident up to k = 12) instead of an 8-byte score.
+int ks_dev_scan_counts(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
+                       int min_width, double min_score, ks_spans *host_out, uint64_t *n_spans) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!s || !d_counts) return ctx->fail(KS_ERR_ARG, "ks_dev_scan_counts: null argument");
+  int rc = check_k(ctx, k);
+  if (rc) return rc;
+  if (!ctx->lut_valid || ctx->lut_k != k)
+    return ctx->fail(KS_ERR_ARG, "ks_dev_scan_counts: call ks_dev_scores with mode LOG2 or SIGN for this k first");
+  if (host_out) { host_out->pos = nullptr; host_out->score = nullptr; host_out->n = 0; }
+  if (n_spans) *n_spans = 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const uint64_t mw = (uint64_t)(int64_t)min_width;
+  cudaEvent_t pw = ctx->prof_begin();
+  const size_t ng = ctx->lut_gcount.size();
+  // host: range check, scale, parameters (O(#distinct counts))
+  double wmax = 0;
+  for (size_t g = 0; g < ng; ++g) {
+    double w = ctx->lut_gval[g] - thr;
+    if (w >= 0x1p40) return ctx->fail(KS_ERR_RANGE, "a k-mer score is +Inf or >= 2^40 (median frequency 0?): outside the exact scan range");
+    if (w == w && w > -0x1p40 && fabs(w) > wmax) wmax = fabs(w);
+  }
+  DevScanParams hp;
+  memset(&hp, 0, sizeof hp);
+  hp.qs = qs_for_max(wmax);
+  fx_t mu = fx_ceil_units(min_score, hp.qs);
+  hp.min_width = mw;
+  hp.min_lo = (uint64_t)(unsigned __int128)mu;
+  hp.min_hi = (int64_t)(uint64_t)(((unsigned __int128)mu) >> 64);
+  uint32_t maxc = ng ? ctx->lut_gcount[ng - 1] : 0;
+  uint32_t lut_size = maxc < (1u << 16) ? maxc + 1 : (1u << 16);
+  size_t sp_first = std::lower_bound(ctx->lut_gcount.begin(), ctx->lut_gcount.end(), lut_size) - ctx->lut_gcount.begin();
+  uint32_t sp_n = (uint32_t)(ng - sp_first);
+  CK(ctx->prm.ensure(sizeof(DevScanParams)));
+  CK(ctx->lut_fx.ensure((size_t)lut_size * 8 + 8));
+  CK(ctx->lut_spc.ensure((size_t)sp_n * 4 + 8));
+  CK(ctx->lut_spv.ensure((size_t)sp_n * 8 + 8));
+  CK(ctx->sc_gcount.ensure((ng + 1) * 4));
+  CK(ctx->sc_lut.ensure(ng * 8 + 8));
+  CK(cudaMemcpyAsync(ctx->prm.p, &hp, sizeof hp, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->sc_gcount.p, ctx->lut_gcount.data(), ng * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->sc_lut.p, ctx->lut_gval.data(), ng * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->lut_fx.p, 0, (size_t)lut_size * 8, st));
+  if (ng) {
+    lut_build_kernel<<<blocks_exact(ng, 256), 256, 0, st>>>(ctx->sc_gcount.as<uint32_t>(), ctx->sc_lut.as<double>(),
+                                                           (uint32_t)ng, thr, hp.qs, lut_size, ctx->lut_fx.as<int64_t>(),
+                                                           ctx->lut_spc.as<uint32_t>(), ctx->lut_spv.as<int64_t>(),
+                                                           (uint32_t)sp_first);
+    LAUNCHED(1);
+  }
+  ctx->prof_end(KS_PROF_WFX, pw);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));  // hp lives on this stack frame
+  ScanTable tab;
+  tab.use_lut = true;
+  tab.counts = reinterpret_cast<const uint32_t *>(d_counts);
+  tab.lut_size = lut_size;
+  tab.sp_n = sp_n;
+  return scan_core(ctx, s, k, tab, mw, nullptr, host_out, n_spans);
+}
+
 int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double param, double thr, int min_width,
                     double min_score, int32_t *d_counts, double *d_scores, double *n_words,
                     ks_spans *host_out, uint64_t *n_spans) {
@@ -799,6 +900,8 @@ int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double par
   if (n_words) *n_words = nw;
   rc = ks_dev_scores(ctx, k, d_counts, nw, mode, param, d_scores);
   if (rc) return rc;
+  if (mode == KS_MODE_LOG2 || mode == KS_MODE_SIGN)
+    return ks_dev_scan_counts(ctx, s, k, d_counts, thr, min_width, min_score, host_out, n_spans);
   return ks_dev_scan(ctx, s, k, d_scores, thr, min_width, min_score, nullptr, host_out, n_spans);
 }
 

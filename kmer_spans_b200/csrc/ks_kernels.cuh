@@ -32,6 +32,29 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
 __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// streaming (evict-first) 128-bit load for the sequence: it is read once per pass and must not push
+// the count / score table out of L2
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) { return __ldcs(p); }
+// L2 evict-last policy for the tables that are gathered / reduced at random
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void red_add_u32_keep(int32_t *addr, uint32_t v, uint64_t pol) {
+  asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(addr), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint32_t ldg_u32_keep(const uint32_t *addr, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(addr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int64_t ldg_s64_keep(const int64_t *addr, uint64_t pol) {
+  int64_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(addr), "l"(pol));
+  return v;
+}
+
 __device__ __forceinline__ uint64_t fx_lo(fx_t v) { return (uint64_t)(unsigned __int128)v; }
 __device__ __forceinline__ uint64_t fx_hi(fx_t v) { return (uint64_t)(((unsigned __int128)v) >> 64); }
 __device__ __forceinline__ fx_t fx_make(uint64_t hi, uint64_t lo) {
@@ -68,18 +91,19 @@ __global__ void __launch_bounds__(256) count_kernel(const uint8_t *__restrict__ 
                                                     int k, uint32_t kmask, int32_t *__restrict__ counts,
                                                     unsigned long long *__restrict__ nwords) {
   unsigned long long local = 0;
+  const uint64_t keep = l2_policy_evict_last();
   for (int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ci < nchunks;
        ci += (int64_t)gridDim.x * blockDim.x) {
     const uint8_t *p = buf + 16 * ci;  // = (chunk position p0) - 16
     const uint4 *v = reinterpret_cast<const uint4 *>(p);
-    uint4 a = __ldg(v), b = __ldg(v + 1);
+    uint4 a = ld_stream_u4(v), b = ld_stream_u4(v + 1);
     uint32_t next = __ldg(p + 32);
     uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     uint32_t code[CHUNK], counted;
     decode_count(w, next, k, kmask, code, counted);
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j)
-      if (counted & (1u << j)) atomicAdd(&counts[code[j]], 1);
+      if (counted & (1u << j)) red_add_u32_keep(&counts[code[j]], 1u, keep);
     local += __popc(counted);
   }
 #pragma unroll
@@ -143,21 +167,50 @@ __global__ void __launch_bounds__(256) wfx_kernel(const double *__restrict__ W, 
 }
 
 // ------------------------------------------------------------------------------------------
-// look-back descriptors, one set per tile.  status = (epoch << 2) | state, state 1 = aggregate of
-// this tile alone, 2 = inclusive (everything to the left folded in).  Buffers are zeroed once; a new
-// epoch per launch makes older states read as "not ready".
+// look-back descriptors: 16-byte self-validating words {tag, 96-bit payload}, written and read with
+// single 128-bit accesses, so a reader needs ONE L2 round trip per window and no fences.
+//   tag = epoch << 4 | open << 3 | kill/reset << 2 | state      state 1 = aggregate of this tile alone,
+//                                                               2 = inclusive (everything to the left folded in)
+// Buffers are zeroed once; a new epoch per launch makes older words read as "not ready".
+// 96-bit payloads bound the running sums to |S| < 2^95 units, i.e. < 2^32 positions per scan.
 struct TileState {
-  uint32_t *xf_status;
-  uint64_t *xf_agg;  // 5 per tile: a_lo, a_hi, b_lo, b_hi, kill
-  uint64_t *xf_inc;  // 2 per tile: S_lo, S_hi at the tile end
-  uint32_t *ex_status;
-  uint64_t *ex_agg;  // 5 per tile: M_lo, M_hi, beg, pk, reset | open << 1
-  uint64_t *ex_inc;  // 5 per tile
+  uint4 *xfA;  // aggregate: a
+  uint4 *xfB;  // aggregate: b (+kill in the tag)   | inclusive: S at the tile end
+  uint4 *exA;  // M
+  uint4 *exB;  // beg (48 bit) | pk (48 bit)
 };
+
+__device__ __forceinline__ uint4 ld_desc(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_desc(uint4 *p, uint32_t tag, uint32_t hi, uint64_t lo) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(tag), "r"(hi),
+               "r"((uint32_t)lo), "r"((uint32_t)(lo >> 32)) : "memory");
+}
+__device__ __forceinline__ void st_desc_fx(uint4 *p, uint32_t tag, fx_t v) {
+  st_desc(p, tag, (uint32_t)fx_hi(v), fx_lo(v));
+}
+__device__ __forceinline__ fx_t desc_fx(const uint4 &d) {  // sign-extend the 96-bit payload
+  return fx_make((uint64_t)(int64_t)(int32_t)d.y, ((uint64_t)d.w << 32) | d.z);
+}
+constexpr uint32_t TAG_AGG = 1u, TAG_INC = 2u, TAG_KILL = 4u, TAG_OPEN = 8u;
+constexpr int64_t POS48_NONE = (1ll << 48) - 1;
 
 struct LevelArgs {
   const uint8_t *buf;
-  const int64_t *wfx;
+  const int64_t *wfx;         // table mode: exact fixed-point score per k-mer (W - thr)
+  // LUT mode (score is a function of the count): gather the int32 count (4 B/entry, L2 resident at
+  // k <= 12), then the score from a dense count -> score table; counts >= lut_size use the sorted
+  // sparse list (sp_count, sp_val)
+  const uint32_t *counts;
+  const int64_t *lut;
+  uint32_t lut_size;
+  const uint32_t *sp_count;
+  const int64_t *sp_val;
+  uint32_t sp_n;
   const DevScanParams *prm;
   int k;
   uint32_t kmask;
@@ -195,103 +248,112 @@ struct DevEmit {
   }
 };
 
-__device__ __forceinline__ Xf load_xf_desc(const TileState &ts, int64_t idx, uint32_t st) {
-  Xf x;
-  if ((st & 3u) == 2u) {
-    uint64_t lo = __ldcg(&ts.xf_inc[2 * idx]), hi = __ldcg(&ts.xf_inc[2 * idx + 1]);
-    x.kill = 1; x.a = 0; x.b = fx_make(hi, lo);
-  } else {
-    const uint64_t *p = &ts.xf_agg[5 * idx];
-    uint64_t alo = __ldcg(p), ahi = __ldcg(p + 1), blo = __ldcg(p + 2), bhi = __ldcg(p + 3);
-    x.kill = (uint32_t)__ldcg(p + 4);
-    x.a = fx_make(ahi, alo);
-    x.b = fx_make(bhi, blo);
-  }
-  return x;
-}
-
-// Warp-wide decoupled look-back for the max-plus transform: returns the state S at the start of
-// `tile`.  Lane L inspects tile (base - L); a transform with kill set (an inclusive value, or an
-// aggregate containing a reset) ends the walk because composition ignores everything left of it.
-__device__ __forceinline__ fx_t lookback_xf(const TileState &ts, int64_t tile, uint32_t epoch, int lane) {
+// CTA-wide decoupled look-back for the max-plus transform: returns (to every thread) the state S at
+// the start of `tile`.  Thread i inspects tile (base - i), so one window covers TILE_THREADS
+// predecessors; a transform with kill set (an inclusive value, or an aggregate containing a reset)
+// ends the walk because composition ignores everything left of it.
+template <int kThreads>
+__device__ __forceinline__ fx_t lookback_xf(const TileState &ts, int64_t tile, uint32_t epoch, Xf *sh) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   Xf acc = xf_identity();
   int64_t base = tile - 1;
   for (;;) {
-    int64_t idx = base - lane;
+    int64_t idx = base - tid;
     Xf x;
-    if (idx < 0) {
-      x.kill = 1; x.a = 0; x.b = 0;  // before the first tile the state is 0
-    } else {
-      uint32_t st;
-      do { st = ld_acquire_u32(&ts.xf_status[idx]); } while ((st >> 2) != epoch || (st & 3u) == 0u);
-      x = load_xf_desc(ts, idx, st);
+    x.kill = 1; x.a = 0; x.b = 0;  // before the first tile the state is 0
+    if (idx >= 0) {
+      for (;;) {
+        uint4 B = ld_desc(&ts.xfB[idx]);
+        uint4 Aw = ld_desc(&ts.xfA[idx]);
+        if ((B.x >> 4) != epoch) continue;
+        if ((B.x & 3u) == TAG_INC) { x.b = desc_fx(B); break; }
+        if ((B.x & 3u) == TAG_AGG && (Aw.x >> 4) == epoch && (Aw.x & 3u) == TAG_AGG) {
+          x.kill = (B.x >> 2) & 1u;
+          x.a = desc_fx(Aw);
+          x.b = desc_fx(B);
+          break;
+        }
+      }
     }
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       Xf y = shfl_xf(x, (lane + o) & 31);
       if (lane + o < 32) x = xf_compose(y, x);  // y covers earlier tiles
     }
-    Xf tot = shfl_xf(x, 0);
+    if (lane == 0) sh[warp] = x;
+    __syncthreads();
+    Xf tot = sh[kThreads / 32 - 1];
+#pragma unroll
+    for (int wv = kThreads / 32 - 2; wv >= 0; --wv) tot = xf_compose(tot, sh[wv]);
+    __syncthreads();
     acc = xf_compose(tot, acc);
     if (acc.kill) return acc.b;
-    base -= 32;
+    base -= kThreads;
   }
 }
 
-__device__ __forceinline__ Ex load_ex_desc(const TileState &ts, int64_t idx, uint32_t st) {
-  const uint64_t *p = ((st & 3u) == 2u) ? &ts.ex_inc[5 * idx] : &ts.ex_agg[5 * idx];
-  Ex e;
-  uint64_t mlo = __ldcg(p), mhi = __ldcg(p + 1);
-  e.M = fx_make(mhi, mlo);
-  e.beg = (int64_t)__ldcg(p + 2);
-  e.pk = (int64_t)__ldcg(p + 3);
-  uint32_t fl = (uint32_t)__ldcg(p + 4);
-  e.reset = ((st & 3u) == 2u) ? 1u : (fl & 1u);  // an inclusive state needs nothing further left
-  e.open = (fl >> 1) & 1u;
-  return e;
-}
-__device__ __forceinline__ void store_ex_desc(uint64_t *p, const Ex &e) {
-  __stcg(p, fx_lo(e.M));
-  __stcg(p + 1, fx_hi(e.M));
-  __stcg(p + 2, (uint64_t)e.beg);
-  __stcg(p + 3, (uint64_t)e.pk);
-  __stcg(p + 4, (uint64_t)(e.reset | (e.open << 1)));
+__device__ __forceinline__ void publish_ex(const TileState &ts, int64_t tile, uint32_t epoch, uint32_t state,
+                                           const Ex &e) {
+  uint32_t tag = (epoch << 4) | (e.open ? TAG_OPEN : 0u) | (e.reset ? TAG_KILL : 0u) | state;
+  fx_t M = e.M;
+  const fx_t lo_lim = -(((fx_t)1) << 94);
+  if (M < lo_lim) M = lo_lim;
+  uint64_t b48 = (uint64_t)(e.beg < 0 ? POS48_NONE : e.beg) & 0xffffffffffffull;
+  uint64_t p48 = (uint64_t)(e.pk < 0 ? POS48_NONE : e.pk) & 0xffffffffffffull;
+  st_desc_fx(&ts.exA[tile], tag, M);
+  st_desc(&ts.exB[tile], tag, (uint32_t)(b48 >> 16), (b48 << 48) | p48);
 }
 
 // Look-back for the open-excursion state: returns the state at the start of `tile`.
-__device__ __forceinline__ Ex lookback_ex(const TileState &ts, int64_t tile, uint32_t epoch, int lane) {
+template <int kThreads>
+__device__ __forceinline__ Ex lookback_ex(const TileState &ts, int64_t tile, uint32_t epoch, Ex *sh) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   Ex acc = ex_identity();
   int64_t base = tile - 1;
   for (;;) {
-    int64_t idx = base - lane;
-    Ex x;
-    if (idx < 0) {
-      x = ex_identity(); x.reset = 1; x.open = 0;
-    } else {
-      uint32_t st;
-      do { st = ld_acquire_u32(&ts.ex_status[idx]); } while ((st >> 2) != epoch || (st & 3u) == 0u);
-      x = load_ex_desc(ts, idx, st);
+    int64_t idx = base - tid;
+    Ex x = ex_identity();
+    x.reset = 1; x.open = 0;
+    if (idx >= 0) {
+      for (;;) {
+        uint4 Aw = ld_desc(&ts.exA[idx]);
+        uint4 B = ld_desc(&ts.exB[idx]);
+        if ((Aw.x >> 4) != epoch || (Aw.x & 3u) == 0u || Aw.x != B.x) continue;
+        x.M = desc_fx(Aw);
+        uint64_t lo = ((uint64_t)B.w << 32) | B.z;
+        int64_t b48 = (int64_t)(((uint64_t)B.y << 16) | (lo >> 48));
+        int64_t p48 = (int64_t)(lo & 0xffffffffffffull);
+        x.beg = b48 == POS48_NONE ? -1 : b48;
+        x.pk = p48 == POS48_NONE ? -1 : p48;
+        x.open = (Aw.x >> 3) & 1u;
+        x.reset = ((Aw.x & 3u) == TAG_INC) ? 1u : ((Aw.x >> 2) & 1u);  // an inclusive state needs nothing further left
+        break;
+      }
     }
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       Ex y = shfl_ex(x, (lane + o) & 31);
       if (lane + o < 32) x = ex_combine(y, x);
     }
-    Ex tot = shfl_ex(x, 0);
+    if (lane == 0) sh[warp] = x;
+    __syncthreads();
+    Ex tot = sh[kThreads / 32 - 1];
+#pragma unroll
+    for (int wv = kThreads / 32 - 2; wv >= 0; --wv) tot = ex_combine(tot, sh[wv]);
+    __syncthreads();
     acc = ex_combine(tot, acc);
     if (acc.reset) return acc;
-    base -= 32;
+    base -= kThreads;
   }
 }
 
 // K4 + K5 + K6.  One CTA = one tile of 256 chunks (4096 positions), tile ids handed out in launch
 // order by an atomic counter so that a tile only ever waits on tiles that already run.
+template <bool kLut>
 __global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const LevelArgs A) {
   __shared__ int64_t s_tile;
   __shared__ Xf s_wxf[TILE_WARPS];
   __shared__ Ex s_wex[TILE_WARPS];
-  __shared__ fx_t s_Sin;
-  __shared__ Ex s_Ein;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = (int64_t)(unsigned int)(atomicAdd(A.tile_counter, 1u) - A.tile_base);
@@ -311,7 +373,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const Level
   if (A.nseg == 0) {
     if (q < A.total_chunks) { p0 = A.dense_start + 16 * q; n_in = 16; head = (q == 0); }
     const uint4 *v = reinterpret_cast<const uint4 *>(A.buf + p0 - 16);
-    uint4 a = __ldg(v), b = __ldg(v + 1);
+    uint4 a = ld_stream_u4(v), b = ld_stream_u4(v + 1);
     w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
     w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
   } else {
@@ -342,10 +404,31 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const Level
   decode_scan(w, A.k, A.kmask, n_in, code, scored);
   int64_t s[CHUNK];
   uint32_t live = 0;
+  const uint64_t keep = l2_policy_evict_last();
+  if (kLut) {
+    uint32_t c[CHUNK];
 #pragma unroll
-  for (int j = 0; j < CHUNK; ++j) {
-    int64_t v = (scored & (1u << j)) ? __ldg(&A.wfx[code[j]]) : WFX_KILL;
-    s[j] = v;
+    for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u32_keep(&A.counts[code[j]], keep) : 0u;
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) {
+      int64_t v = WFX_KILL;
+      if (scored & (1u << j)) {
+        if (c[j] < A.lut_size) {
+          v = __ldg(&A.lut[c[j]]);
+        } else {  // rare: very abundant k-mer, look it up in the sorted sparse list
+          uint32_t lo = 0, hi = A.sp_n;
+          while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&A.sp_count[mid]) <= c[j]) lo = mid; else hi = mid;
+          }
+          v = __ldg(&A.sp_val[lo]);
+        }
+      }
+      s[j] = v;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) s[j] = (scored & (1u << j)) ? ldg_s64_keep(&A.wfx[code[j]], keep) : WFX_KILL;
   }
 #pragma unroll
   for (int j = 0; j < CHUNK; ++j) {
@@ -373,36 +456,21 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const Level
   Xf wpre = xf_identity();
   for (int i = 0; i < warp; ++i) wpre = xf_compose(wpre, s_wxf[i]);
   excl = xf_compose(wpre, excl);
-  if (warp == 0) {
-    Xf agg = xf_identity();
+  Xf agg = xf_identity();
+  if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < TILE_WARPS; ++i) agg = xf_compose(agg, s_wxf[i]);
-    if (lane == 0) {
-      if (agg.kill) {  // the state at the tile end does not depend on the left: publish it at once
-        __stcg(&A.ts.xf_inc[2 * tile], fx_lo(agg.b));
-        __stcg(&A.ts.xf_inc[2 * tile + 1], fx_hi(agg.b));
-        st_release_u32(&A.ts.xf_status[tile], (A.epoch << 2) | 2u);
-      } else {
-        uint64_t *p = &A.ts.xf_agg[5 * tile];
-        __stcg(p, fx_lo(agg.a)); __stcg(p + 1, fx_hi(agg.a));
-        __stcg(p + 2, fx_lo(agg.b)); __stcg(p + 3, fx_hi(agg.b));
-        __stcg(p + 4, (uint64_t)agg.kill);
-        st_release_u32(&A.ts.xf_status[tile], (A.epoch << 2) | 1u);
-      }
-    }
-    fx_t S_tile = lookback_xf(A.ts, tile, A.epoch, lane);
-    if (lane == 0) {
-      if (!agg.kill) {
-        fx_t So = xf_apply(agg, S_tile);
-        __stcg(&A.ts.xf_inc[2 * tile], fx_lo(So));
-        __stcg(&A.ts.xf_inc[2 * tile + 1], fx_hi(So));
-        st_release_u32(&A.ts.xf_status[tile], (A.epoch << 2) | 2u);
-      }
-      s_Sin = S_tile;
+    const uint32_t tg = A.epoch << 4;
+    if (agg.kill) {  // the state at the tile end does not depend on the left: publish it at once
+      st_desc_fx(&A.ts.xfB[tile], tg | TAG_INC, agg.b);
+    } else {
+      st_desc_fx(&A.ts.xfA[tile], tg | TAG_AGG, agg.a);
+      st_desc_fx(&A.ts.xfB[tile], tg | TAG_AGG, agg.b);
     }
   }
-  __syncthreads();
-  const fx_t S_tile = s_Sin;
+  __syncthreads();  // s_wxf is reused as the look-back scratch
+  const fx_t S_tile = lookback_xf<TILE_THREADS>(A.ts, tile, A.epoch, s_wxf);
+  if (tid == 0 && !agg.kill) st_desc_fx(&A.ts.xfB[tile], (A.epoch << 4) | TAG_INC, xf_apply(agg, S_tile));
   const fx_t S_in = head ? (fx_t)0 : xf_apply(excl, S_tile);
 
   // ---- excursions: local walk, segmented scan of the open-excursion state, look-back ----
@@ -426,41 +494,22 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const Level
   Ex epre = ex_identity();
   for (int i = 0; i < warp; ++i) epre = ex_combine(epre, s_wex[i]);
   eexcl = ex_combine(epre, eexcl);
-  if (warp == 0) {
-    Ex agg = ex_identity();
+  Ex eagg = ex_identity();
+  if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < TILE_WARPS; ++i) agg = ex_combine(agg, s_wex[i]);
-    Ex E_tile;
-    if (S_tile > 0) {
-      // an excursion enters the tile: successors may need our aggregate while we look back
-      if (lane == 0) {
-        if (agg.reset) {
-          store_ex_desc(&A.ts.ex_inc[5 * tile], agg);
-          st_release_u32(&A.ts.ex_status[tile], (A.epoch << 2) | 2u);
-        } else {
-          store_ex_desc(&A.ts.ex_agg[5 * tile], agg);
-          st_release_u32(&A.ts.ex_status[tile], (A.epoch << 2) | 1u);
-        }
-      }
-      E_tile = lookback_ex(A.ts, tile, A.epoch, lane);
-      if (lane == 0 && !agg.reset) {
-        Ex full = ex_combine(E_tile, agg);
-        store_ex_desc(&A.ts.ex_inc[5 * tile], full);
-        st_release_u32(&A.ts.ex_status[tile], (A.epoch << 2) | 2u);
-      }
-    } else {
-      // state 0 at the tile start: nothing enters, and the first chunk makes the aggregate a reset
-      E_tile = ex_identity(); E_tile.reset = 1; E_tile.open = 0;
-      if (lane == 0) {
-        store_ex_desc(&A.ts.ex_inc[5 * tile], agg);
-        st_release_u32(&A.ts.ex_status[tile], (A.epoch << 2) | 2u);
-      }
-    }
-    if (lane == 0) s_Ein = E_tile;
+    for (int i = 0; i < TILE_WARPS; ++i) eagg = ex_combine(eagg, s_wex[i]);
+    // a reset aggregate (the tile holds a zero or a start, or the state entering it is 0) is final
+    publish_ex(A.ts, tile, A.epoch, (eagg.reset || !(S_tile > 0)) ? TAG_INC : TAG_AGG, eagg);
   }
-  __syncthreads();
+  __syncthreads();  // s_wex is reused as the look-back scratch
+  Ex E_tile = ex_identity();
+  E_tile.reset = 1; E_tile.open = 0;
+  if (S_tile > 0) {  // an excursion enters the tile (block-uniform)
+    E_tile = lookback_ex<TILE_THREADS>(A.ts, tile, A.epoch, s_wex);
+    if (tid == 0 && !eagg.reset) publish_ex(A.ts, tile, A.epoch, TAG_INC, ex_combine(E_tile, eagg));
+  }
   if (!head) {
-    Ex E_in = ex_combine(s_Ein, eexcl);
+    Ex E_in = ex_combine(E_tile, eexcl);
     chunk_finish_entering(S_in, E_in, preM, prePk, first_zero, p0, prm, emit);
   }
 }
@@ -579,6 +628,21 @@ __global__ void __launch_bounds__(256) lut_apply_kernel(const uint32_t *__restri
     if (__ldg(&gcount[mid]) <= c) lo = mid; else hi = mid;
   }
   W[i] = __ldg(&lut[lo]);
+}
+
+// dense count -> score table in exact fixed point: lut[c] = fx(score(c) - thr); entries of counts that
+// do not occur are never gathered.  gval = score per distinct count (host libm), gcount ascending.
+__global__ void __launch_bounds__(256) lut_build_kernel(const uint32_t *__restrict__ gcount,
+                                                        const double *__restrict__ gval, uint32_t ngroups,
+                                                        double thr, int qs, uint32_t lut_size,
+                                                        int64_t *__restrict__ lut, uint32_t *__restrict__ sp_count,
+                                                        int64_t *__restrict__ sp_val, uint32_t sp_first) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ngroups) return;
+  int64_t v = wfx_from_double(gval[g] - thr, qs);
+  uint32_t c = gcount[g];
+  if (c < lut_size) lut[c] = v;
+  else { sp_count[g - sp_first] = c; sp_val[g - sp_first] = v; }
 }
 
 __global__ void __launch_bounds__(256) affine_kernel(double *__restrict__ W, size_t n, double sub, double div) {

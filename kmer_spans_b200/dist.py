@@ -73,12 +73,16 @@ class GpuStages:
 
     def scores_from_counts(self, k, total, mode, param):
         self.torch.cuda.synchronize(self.device)  # the reduced table is ready before our stream reads it
+        self.mode = mode
         self.ctx.dev_scores(k, self.counts.data_ptr(), total, mode, self.scores.data_ptr(), param)
 
     def scan(self, k, thr, min_w, min_score, fetch=True):
         if self.ss is None:
-            return np.zeros((0, 3), np.int32), np.zeros((0, 2))
-        r = self.ctx.dev_scan(self.ss, k, self.scores.data_ptr(), thr, min_w, min_score, 0, fetch_spans=fetch)
+            return (0, None) if not fetch else (np.zeros((0, 3), np.int32), np.zeros((0, 2)))
+        if self.mode in (1, 2):  # score is a function of the count: gather counts + LUT
+            r = self.ctx.dev_scan_counts(self.ss, k, self.counts.data_ptr(), thr, min_w, min_score, fetch_spans=fetch)
+        else:
+            r = self.ctx.dev_scan(self.ss, k, self.scores.data_ptr(), thr, min_w, min_score, 0, fetch_spans=fetch)
         if not fetch:
             return r["n_spans"], None
         return r["pos"], r["score"]
