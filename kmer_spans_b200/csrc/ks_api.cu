@@ -590,7 +590,8 @@ static int ensure_tiles(ks_ctx *ctx, size_t tiles) {
   if (tiles <= ctx->tiles_cap) return KS_OK;
   size_t t = tiles + tiles / 4 + 64;
   cudaStream_t st = ctx->stream;
-  DBuf *d[4] = {&ctx->xf_agg, &ctx->xf_inc, &ctx->ex_agg, &ctx->ex_inc};  // xfA, xfB, exA, exB
+  DBuf *d[6] = {&ctx->xf_agg, &ctx->xf_inc, &ctx->ex_agg, &ctx->ex_inc,  // xfA, xfB, exA, exB
+                &ctx->xf_status, &ctx->ex_status};                          // gA, gB (one per 32 tiles, oversized)
   for (DBuf *b : d) {
     CK(b->ensure(t * 16));
     CK(cudaMemsetAsync(b->p, 0, b->cap, st));
@@ -679,12 +680,16 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.ts.xfB = ctx->xf_inc.as<uint4>();
     A.ts.exA = ctx->ex_agg.as<uint4>();
     A.ts.exB = ctx->ex_inc.as<uint4>();
+    A.ts.gA = ctx->xf_status.as<uint4>();
+    A.ts.gB = ctx->ex_status.as<uint4>();
     ctx->epoch += 1;
     if (ctx->epoch >= (1u << 28) - 1) {  // epoch space exhausted: start over with zeroed tags
       CK(cudaMemsetAsync(ctx->xf_agg.p, 0, ctx->xf_agg.cap, st));
       CK(cudaMemsetAsync(ctx->xf_inc.p, 0, ctx->xf_inc.cap, st));
       CK(cudaMemsetAsync(ctx->ex_agg.p, 0, ctx->ex_agg.cap, st));
       CK(cudaMemsetAsync(ctx->ex_inc.p, 0, ctx->ex_inc.cap, st));
+      CK(cudaMemsetAsync(ctx->xf_status.p, 0, ctx->xf_status.cap, st));
+      CK(cudaMemsetAsync(ctx->ex_status.p, 0, ctx->ex_status.cap, st));
       ctx->epoch = 1;
     }
     A.epoch = ctx->epoch;

@@ -11,9 +11,10 @@
 //   * S' = (S + w > 0) ? S + w : 0, start / leftmost peak / close bookkeeping     :269-291
 //
 // Arithmetic: the scan runs in EXACT fixed point.  Every per-k-mer score (W[code]-thr, the
-// double the reference computes at :268) is converted once to a signed 64-bit multiple of
-// q = 2^-QS (QS chosen per table so that max|w| < 2^(63-QS)); running sums are 128-bit
-// integers in units of q.  Integer addition is associative, so tile, block, warp and
+// double the reference computes at :268) is converted once to a signed multiple of
+// q = 2^-QS (QS chosen per table so that max|w| < 2^(57-QS), i.e. 57-bit table entries: exact for
+// every weight whose last mantissa bit is >= 2^-QS, truncated toward zero below); running sums
+// are 128-bit integers in units of q, partial sums inside one chunk are 64-bit.  Integer addition is associative, so tile, block, warp and
 // multi-GPU decompositions all give the same bits, and the max-plus transforms
 // x -> max(x + a, b) compose exactly.  DESIGN.md discusses the parity consequences.
 #pragma once
@@ -104,7 +105,7 @@ KS_HD int64_t wfx_from_double(double d, int qs) {
   int sh = e - 1075 + qs;  // value * 2^qs = m * 2^sh
   uint64_t v;
   if (sh >= 0) {
-    if (sh > 9) return INT64_MAX;  // cannot happen when qs = qs_for_max(max |w|)
+    if (sh > 4) return INT64_MAX;  // cannot happen when qs = qs_for_max(max |w|)
     v = m << sh;
   } else if (sh > -64) {
     v = m >> (-sh);
@@ -114,14 +115,16 @@ KS_HD int64_t wfx_from_double(double d, int qs) {
   return neg ? -(int64_t)v : (int64_t)v;
 }
 
-// number of fraction bits for a table whose largest finite |w| is wmax: max|w| < 2^(62-qs)
+// number of fraction bits for a table whose largest finite |w| is wmax: max|w| < 2^(57-qs).
+// 57-bit scores keep every partial sum of one 16-position chunk below 2^61, so the per-position
+// arithmetic inside a chunk is plain 64-bit; only the carries between chunks are 128-bit.
 KS_HD int qs_for_max(double wmax) {
   uint64_t bits;
   memcpy(&bits, &wmax, 8);
   int e = (int)((bits >> 52) & 0x7ff) - 1023;  // wmax in [2^e, 2^(e+1))
   if (wmax == 0.0) e = -1;
   int E = e + 1;  // wmax < 2^E
-  int qs = 62 - E;
+  int qs = 57 - E;
   if (qs > 62) qs = 62;
   return qs;
 }
@@ -210,18 +213,24 @@ KS_HD Xf xf_compose(const Xf &f, const Xf &g) {
 KS_HD fx_t xf_apply(const Xf &f, fx_t x) { return f.kill ? f.b : fx_max(x + f.a, f.b); }
 
 // chunk transform.  s[j] valid where bit j of live is set; other positions force the state to 0.
+// 64-bit inside the chunk (|s| < 2^57, 16 terms), widened at the end.
 KS_HD Xf chunk_transform(const int64_t s[CHUNK], uint32_t live) {
-  Xf f = xf_identity();
+  int64_t a = 0, b = -(1ll << 62);
+  uint32_t kill = 0;
 #pragma unroll
   for (int j = 0; j < CHUNK; ++j) {
     if (live & (1u << j)) {
-      f.a += (fx_t)s[j];
-      fx_t t = f.b + (fx_t)s[j];
-      f.b = t > 0 ? t : (fx_t)0;
+      a += s[j];
+      int64_t t = b + s[j];
+      b = t > 0 ? t : 0;
     } else {
-      f.kill = 1; f.a = 0; f.b = 0;
+      kill = 1; a = 0; b = 0;
     }
   }
+  Xf f;
+  f.a = (fx_t)a;
+  f.b = (fx_t)b;
+  f.kill = kill;
   return f;
 }
 
@@ -259,43 +268,51 @@ KS_HD bool qualifies(const ScanParams &p, int64_t beg, int64_t pk, fx_t M) {
 // (M, pk) over the positions before the first zero (the part belonging to the entering
 // excursion), `first_zero` = position index (0..15) of that zero or -1, and in `ex` the
 // segmented-scan element of this chunk.  p0 = global position of chunk byte 0.
+//
+// 64-bit inside the chunk: the walk runs on sigma = min(S_in, 2^62).  A chunk moves the state by
+// less than 2^61, so with S_in >= 2^62 no position reaches 0 either way and all comparisons agree;
+// maxima are shifted back by S_in - sigma when they leave the chunk.
 template <class Emit>
 KS_HD void chunk_walk(const int64_t s[CHUNK], uint32_t live, fx_t S_in, int64_t p0,
                       const ScanParams &prm, Emit &emit, Ex &ex, fx_t &preM, int64_t &prePk,
                       int &first_zero) {
-  fx_t S = S_in;
-  fx_t M = -(((fx_t)1) << 126);
+  const fx_t cap = ((fx_t)1) << 62;
+  const int64_t sigma = S_in > cap ? (1ll << 62) : (int64_t)S_in;
+  const fx_t shift = S_in - (fx_t)sigma;
+  const int64_t NEG = -(1ll << 62);
+  int64_t S = sigma;
+  int64_t M = NEG;
   int64_t pk = -1, beg = -1;
+  int64_t pM = NEG, pPk = -1;
   bool started = false;  // a start happened inside this chunk
   first_zero = -1;
-  preM = M; prePk = -1;
 #pragma unroll
   for (int j = 0; j < CHUNK; ++j) {
-    fx_t Sn = 0;
+    int64_t Sn = 0;
     if (live & (1u << j)) {
-      Sn = S + (fx_t)s[j];
-      Sn = Sn > 0 ? Sn : (fx_t)0;
+      Sn = S + s[j];
+      Sn = Sn > 0 ? Sn : 0;
     }
     if (S == 0 && Sn > 0) { started = true; beg = p0 + j; pk = p0 + j; M = Sn; }
     if (Sn == 0) {
-      if (S > 0) {  // close at p0 + j
-        if (started) {
-          if (qualifies(prm, beg, pk, M)) emit(beg, pk, (int64_t)(p0 + j), M);
-        }
+      if (S > 0 && started) {  // close at p0 + j of an excursion that started in this chunk
+        if (qualifies(prm, beg, pk, (fx_t)M)) emit(beg, pk, (int64_t)(p0 + j), (fx_t)M);
       }
-      if (first_zero < 0) { first_zero = j; preM = M; prePk = pk; }
+      if (first_zero < 0) { first_zero = j; pM = M; pPk = pk; }
     } else if (Sn > M) {
       M = Sn; pk = p0 + j;
     }
     S = Sn;
   }
-  if (first_zero < 0) { preM = M; prePk = pk; }
+  if (first_zero < 0) { pM = M; pPk = pk; }
+  preM = pM == NEG ? -(((fx_t)1) << 126) : (fx_t)pM + shift;
+  prePk = pPk;
   // segmented-scan element
   if (S > 0) {
     ex.open = 1;
-    ex.M = M; ex.pk = pk;
-    if (started) { ex.reset = 1; ex.beg = beg; }
-    else { ex.reset = 0; ex.beg = -1; }
+    ex.pk = pk;
+    if (started) { ex.reset = 1; ex.beg = beg; ex.M = (fx_t)M; }
+    else { ex.reset = 0; ex.beg = -1; ex.M = (fx_t)M + shift; }
   } else {
     ex.reset = 1; ex.open = 0; ex.M = -(((fx_t)1) << 126); ex.beg = -1; ex.pk = -1;
   }

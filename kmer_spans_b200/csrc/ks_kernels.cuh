@@ -176,9 +176,12 @@ __global__ void __launch_bounds__(256) wfx_kernel(const double *__restrict__ W, 
 struct TileState {
   uint4 *xfA;  // aggregate: a
   uint4 *xfB;  // aggregate: b (+kill in the tag)   | inclusive: S at the tile end
-  uint4 *exA;  // M
-  uint4 *exB;  // beg (48 bit) | pk (48 bit)
+  uint4 *gA;   // the same pair per GROUP of 32 consecutive tiles (second look-back level)
+  uint4 *gB;
+  uint4 *exA;  // open-excursion aggregate of the tile: M
+  uint4 *exB;  //                                       beg (48 bit) | pk (48 bit)
 };
+constexpr int GROUP_TILES = 32;
 
 __device__ __forceinline__ uint4 ld_desc(const uint4 *p) {
   uint4 v;
@@ -248,53 +251,79 @@ struct DevEmit {
   }
 };
 
-// CTA-wide decoupled look-back for the max-plus transform: returns (to every thread) the state S at
-// the start of `tile`.  Thread i inspects tile (base - i), so one window covers TILE_THREADS
-// predecessors; a transform with kill set (an inclusive value, or an aggregate containing a reset)
-// ends the walk because composition ignores everything left of it.
-template <int kThreads>
-__device__ __forceinline__ fx_t lookback_xf(const TileState &ts, int64_t tile, uint32_t epoch, Xf *sh) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  Xf acc = xf_identity();
-  int64_t base = tile - 1;
+__device__ __forceinline__ Xf poll_xf(const uint4 *dA, const uint4 *dB, int64_t idx, uint32_t epoch) {
+  Xf x;
+  x.kill = 1; x.a = 0; x.b = 0;
   for (;;) {
-    int64_t idx = base - tid;
-    Xf x;
-    x.kill = 1; x.a = 0; x.b = 0;  // before the first tile the state is 0
-    if (idx >= 0) {
-      for (;;) {
-        uint4 B = ld_desc(&ts.xfB[idx]);
-        uint4 Aw = ld_desc(&ts.xfA[idx]);
-        if ((B.x >> 4) != epoch) continue;
-        if ((B.x & 3u) == TAG_INC) { x.b = desc_fx(B); break; }
-        if ((B.x & 3u) == TAG_AGG && (Aw.x >> 4) == epoch && (Aw.x & 3u) == TAG_AGG) {
-          x.kill = (B.x >> 2) & 1u;
-          x.a = desc_fx(Aw);
-          x.b = desc_fx(B);
-          break;
-        }
-      }
+    uint4 B = ld_desc(&dB[idx]);
+    uint4 Aw = ld_desc(&dA[idx]);
+    if ((B.x >> 4) != epoch) continue;
+    if ((B.x & 3u) == TAG_INC) { x.b = desc_fx(B); break; }
+    if ((B.x & 3u) == TAG_AGG && (Aw.x >> 4) == epoch && (Aw.x & 3u) == TAG_AGG) {
+      x.kill = (B.x >> 2) & 1u;
+      x.a = desc_fx(Aw);
+      x.b = desc_fx(B);
+      break;
     }
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      Xf y = shfl_xf(x, (lane + o) & 31);
-      if (lane + o < 32) x = xf_compose(y, x);  // y covers earlier tiles
-    }
-    if (lane == 0) sh[warp] = x;
-    __syncthreads();
-    Xf tot = sh[kThreads / 32 - 1];
-#pragma unroll
-    for (int wv = kThreads / 32 - 2; wv >= 0; --wv) tot = xf_compose(tot, sh[wv]);
-    __syncthreads();
-    acc = xf_compose(tot, acc);
-    if (acc.kill) return acc.b;
-    base -= kThreads;
+  }
+  return x;
+}
+__device__ __forceinline__ void publish_xf(uint4 *dA, uint4 *dB, int64_t idx, uint32_t epoch, const Xf &f) {
+  const uint32_t tg = epoch << 4;
+  if (f.kill) {  // does not depend on anything to the left: final
+    st_desc_fx(&dB[idx], tg | TAG_INC, f.b);
+  } else {
+    st_desc_fx(&dA[idx], tg | TAG_AGG, f.a);
+    st_desc_fx(&dB[idx], tg | TAG_AGG, f.b);
   }
 }
+// ordered warp reduction: lane L holds the transform of an EARLIER range than lane L-1
+__device__ __forceinline__ Xf warp_fold_xf(Xf x, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Xf y = shfl_xf(x, (lane + o) & 31);
+    if (lane + o < 32) x = xf_compose(y, x);
+  }
+  return shfl_xf(x, 0);
+}
 
-__device__ __forceinline__ void publish_ex(const TileState &ts, int64_t tile, uint32_t epoch, uint32_t state,
-                                           const Ex &e) {
-  uint32_t tag = (epoch << 4) | (e.open ? TAG_OPEN : 0u) | (e.reset ? TAG_KILL : 0u) | state;
+// Two-level decoupled look-back for the max-plus transform, run by warp 0: returns the state S at
+// the start of `tile`.  Window 1 covers the earlier tiles of the own 32-tile group; if that is not
+// enough, window 2+ walks whole groups, 32 per step, so ~1000 tiles of lag cost two windows.
+// The last tile of a group publishes the group aggregate as soon as its window 1 is folded.
+// A transform with kill set (an inclusive value, or an aggregate containing a reset) ends the walk
+// because composition ignores everything left of it.
+__device__ __forceinline__ fx_t lookback_xf(const TileState &ts, int64_t tile, uint32_t epoch,
+                                            const Xf &agg, int lane) {
+  const int64_t g = tile / GROUP_TILES;
+  const int l = (int)(tile % GROUP_TILES);
+  if (lane == 0) publish_xf(ts.xfA, ts.xfB, tile, epoch, agg);
+  Xf x = xf_identity();
+  if (lane < l) x = poll_xf(ts.xfA, ts.xfB, tile - 1 - lane, epoch);
+  Xf acc = warp_fold_xf(x, lane);  // tiles [32 g, tile)
+  const Xf grp = xf_compose(acc, agg);  // tiles [32 g, tile]
+  const bool last = (l == GROUP_TILES - 1);
+  if (last && lane == 0) publish_xf(ts.gA, ts.gB, g, epoch, grp);
+  int64_t gbase = g - 1;
+  while (!acc.kill) {
+    int64_t idx = gbase - lane;
+    Xf y;
+    y.kill = 1; y.a = 0; y.b = 0;  // before the first tile the state is 0
+    if (idx >= 0) y = poll_xf(ts.gA, ts.gB, idx, epoch);
+    acc = xf_compose(warp_fold_xf(y, lane), acc);
+    gbase -= 32;
+  }
+  const fx_t S_tile = acc.b;
+  if (lane == 0) {
+    const fx_t S_end = xf_apply(agg, S_tile);
+    if (!agg.kill) st_desc_fx(&ts.xfB[tile], (epoch << 4) | TAG_INC, S_end);
+    if (last && !grp.kill) st_desc_fx(&ts.gB[g], (epoch << 4) | TAG_INC, S_end);
+  }
+  return S_tile;
+}
+
+__device__ __forceinline__ void publish_ex(const TileState &ts, int64_t tile, uint32_t epoch, const Ex &e) {
+  uint32_t tag = (epoch << 4) | (e.open ? TAG_OPEN : 0u) | (e.reset ? TAG_KILL : 0u) | TAG_AGG;
   fx_t M = e.M;
   const fx_t lo_lim = -(((fx_t)1) << 94);
   if (M < lo_lim) M = lo_lim;
@@ -304,14 +333,14 @@ __device__ __forceinline__ void publish_ex(const TileState &ts, int64_t tile, ui
   st_desc(&ts.exB[tile], tag, (uint32_t)(b48 >> 16), (b48 << 48) | p48);
 }
 
-// Look-back for the open-excursion state: returns the state at the start of `tile`.
-template <int kThreads>
-__device__ __forceinline__ Ex lookback_ex(const TileState &ts, int64_t tile, uint32_t epoch, Ex *sh) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Open-excursion state at the start of `tile`, resolved LAZILY: every tile publishes the aggregate
+// of its own chunks (no chain), and only a tile in which an excursion that entered from the left
+// closes walks back (warp 0, 32 tiles per step) to the tile that holds the excursion's start.
+__device__ __forceinline__ Ex lookback_ex(const TileState &ts, int64_t tile, uint32_t epoch, int lane) {
   Ex acc = ex_identity();
   int64_t base = tile - 1;
   for (;;) {
-    int64_t idx = base - tid;
+    int64_t idx = base - lane;
     Ex x = ex_identity();
     x.reset = 1; x.open = 0;
     if (idx >= 0) {
@@ -326,7 +355,7 @@ __device__ __forceinline__ Ex lookback_ex(const TileState &ts, int64_t tile, uin
         x.beg = b48 == POS48_NONE ? -1 : b48;
         x.pk = p48 == POS48_NONE ? -1 : p48;
         x.open = (Aw.x >> 3) & 1u;
-        x.reset = ((Aw.x & 3u) == TAG_INC) ? 1u : ((Aw.x >> 2) & 1u);  // an inclusive state needs nothing further left
+        x.reset = (Aw.x >> 2) & 1u;
         break;
       }
     }
@@ -335,15 +364,9 @@ __device__ __forceinline__ Ex lookback_ex(const TileState &ts, int64_t tile, uin
       Ex y = shfl_ex(x, (lane + o) & 31);
       if (lane + o < 32) x = ex_combine(y, x);
     }
-    if (lane == 0) sh[warp] = x;
-    __syncthreads();
-    Ex tot = sh[kThreads / 32 - 1];
-#pragma unroll
-    for (int wv = kThreads / 32 - 2; wv >= 0; --wv) tot = ex_combine(tot, sh[wv]);
-    __syncthreads();
-    acc = ex_combine(tot, acc);
+    acc = ex_combine(shfl_ex(x, 0), acc);
     if (acc.reset) return acc;
-    base -= kThreads;
+    base -= 32;
   }
 }
 
@@ -354,6 +377,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const Level
   __shared__ int64_t s_tile;
   __shared__ Xf s_wxf[TILE_WARPS];
   __shared__ Ex s_wex[TILE_WARPS];
+  __shared__ fx_t s_S;
+  __shared__ Ex s_E;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = (int64_t)(unsigned int)(atomicAdd(A.tile_counter, 1u) - A.tile_base);
@@ -456,24 +481,18 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const Level
   Xf wpre = xf_identity();
   for (int i = 0; i < warp; ++i) wpre = xf_compose(wpre, s_wxf[i]);
   excl = xf_compose(wpre, excl);
-  Xf agg = xf_identity();
-  if (tid == 0) {
+  if (warp == 0) {
+    Xf agg = xf_identity();
 #pragma unroll
     for (int i = 0; i < TILE_WARPS; ++i) agg = xf_compose(agg, s_wxf[i]);
-    const uint32_t tg = A.epoch << 4;
-    if (agg.kill) {  // the state at the tile end does not depend on the left: publish it at once
-      st_desc_fx(&A.ts.xfB[tile], tg | TAG_INC, agg.b);
-    } else {
-      st_desc_fx(&A.ts.xfA[tile], tg | TAG_AGG, agg.a);
-      st_desc_fx(&A.ts.xfB[tile], tg | TAG_AGG, agg.b);
-    }
+    fx_t S0 = lookback_xf(A.ts, tile, A.epoch, agg, lane);
+    if (lane == 0) s_S = S0;
   }
-  __syncthreads();  // s_wxf is reused as the look-back scratch
-  const fx_t S_tile = lookback_xf<TILE_THREADS>(A.ts, tile, A.epoch, s_wxf);
-  if (tid == 0 && !agg.kill) st_desc_fx(&A.ts.xfB[tile], (A.epoch << 4) | TAG_INC, xf_apply(agg, S_tile));
+  __syncthreads();
+  const fx_t S_tile = s_S;
   const fx_t S_in = head ? (fx_t)0 : xf_apply(excl, S_tile);
 
-  // ---- excursions: local walk, segmented scan of the open-excursion state, look-back ----
+  // ---- excursions: local walk, segmented scan of the open-excursion state, lazy look-back ----
   DevEmit emit{&A};
   Ex ex;
   fx_t preM;
@@ -494,22 +513,20 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const Level
   Ex epre = ex_identity();
   for (int i = 0; i < warp; ++i) epre = ex_combine(epre, s_wex[i]);
   eexcl = ex_combine(epre, eexcl);
-  Ex eagg = ex_identity();
-  if (tid == 0) {
+  if (warp == 0) {
+    Ex eagg = ex_identity();
 #pragma unroll
     for (int i = 0; i < TILE_WARPS; ++i) eagg = ex_combine(eagg, s_wex[i]);
-    // a reset aggregate (the tile holds a zero or a start, or the state entering it is 0) is final
-    publish_ex(A.ts, tile, A.epoch, (eagg.reset || !(S_tile > 0)) ? TAG_INC : TAG_AGG, eagg);
+    if (lane == 0) publish_ex(A.ts, tile, A.epoch, eagg);
+    Ex E0 = ex_identity();
+    E0.reset = 1; E0.open = 0;
+    // only if an excursion enters the tile AND something inside the tile ends it
+    if (S_tile > 0 && eagg.reset) E0 = lookback_ex(A.ts, tile, A.epoch, lane);
+    if (lane == 0) s_E = E0;
   }
-  __syncthreads();  // s_wex is reused as the look-back scratch
-  Ex E_tile = ex_identity();
-  E_tile.reset = 1; E_tile.open = 0;
-  if (S_tile > 0) {  // an excursion enters the tile (block-uniform)
-    E_tile = lookback_ex<TILE_THREADS>(A.ts, tile, A.epoch, s_wex);
-    if (tid == 0 && !eagg.reset) publish_ex(A.ts, tile, A.epoch, TAG_INC, ex_combine(E_tile, eagg));
-  }
+  __syncthreads();
   if (!head) {
-    Ex E_in = ex_combine(E_tile, eexcl);
+    Ex E_in = ex_combine(s_E, eexcl);
     chunk_finish_entering(S_in, E_in, preM, prePk, first_zero, p0, prm, emit);
   }
 }
