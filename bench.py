@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in self.REASONS.items():
                     if m & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.005)
         except Exception as e:  # NVML unavailable: report it instead of inventing numbers
             self.err = repr(e)
 
@@ -235,7 +235,7 @@ def main():
         n_spans = step()
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
-    time.sleep(0.15)
+    time.sleep(0.1)
     ctx.set_profile(True)
     ctx.profile(reset=True)
     ctx.reset_launches()
@@ -245,6 +245,8 @@ def main():
         n_spans = step()
     ms = ctx.timer_stop()
     barrier()
+    sampler.stop_flag = True  # NVML queries contend with CUDA API calls: sample the device-timed region only
+    sampler.join(2)
     launches = ctx.launches()
     prof = ctx.profile(reset=True)
     ctx.set_profile(False)
@@ -281,8 +283,6 @@ def main():
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_s = float(t_e.item())
     e2e_val = world * args.n_bases * e2e_steps / e2e_s / 1e9
-    sampler.stop_flag = True
-    sampler.join(2)
 
     if rank != 0:
         if world > 1:

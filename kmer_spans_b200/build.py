@@ -27,7 +27,8 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + SOURCES
+    extra = os.environ.get("KS_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB] + SOURCES
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(CSRC, "build.log"), "w") as f:

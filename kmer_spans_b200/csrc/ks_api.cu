@@ -61,6 +61,11 @@ struct ks_seqset {
   int nseq = 0;
   std::vector<int64_t> lens, starts;  // starts: nseq + 1
   int64_t *d_starts = nullptr;
+  // K1 output: 2-bit packed codes + break masks, one entry per 16 positions (written by the pack+count
+  // pass, read by every scan pass)
+  uint32_t *d_pk = nullptr;
+  uint16_t *d_brk = nullptr;
+  mutable bool packed = false;
 };
 
 struct ks_ctx {
@@ -73,6 +78,8 @@ struct ks_ctx {
   uint32_t epoch = 0;
   unsigned int tile_base = 0;
   bool counter_init = false;
+  bool scan_cfg_done = false;
+  size_t scan_max_ctas = 0;
   // scan scratch
   DBuf wfx, prm, xf_status, xf_agg, xf_inc, ex_status, ex_agg, ex_inc, tile_counter;
   size_t tiles_cap = 0;
@@ -93,7 +100,7 @@ struct ks_ctx {
   // staging / misc
   void *pinned = nullptr;
   size_t pinned_cap = 0;
-  DBuf tmp_counts, tmp_scores, tmp_inscan, nwords;
+  DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, dbg, gdone;
 
   // timing / profiling
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -216,7 +223,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->out_score, &ctx->sc_keys_a, &ctx->sc_keys_b, &ctx->sc_vals_a, &ctx->sc_vals_b,
                  &ctx->sc_small, &ctx->sc_gcount, &ctx->sc_gstart, &ctx->sc_segfirst, &ctx->sc_segj0,
                  &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->tmp_counts, &ctx->tmp_scores,
-                 &ctx->tmp_inscan, &ctx->nwords, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
+                 &ctx->tmp_inscan, &ctx->nwords, &ctx->dbg, &ctx->gdone, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -271,6 +278,17 @@ void ks_ctx_profile_reset(ks_ctx *ctx) {
   for (int i = 0; i < KS_PROF_N; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
 }
 
+// development aid (KS_EXP_TIMING builds): 16 per-phase cycle counters of scan level 0
+int ks_ctx_debug_counters(ks_ctx *ctx, uint64_t *out16, int reset) {
+  if (!ctx) return KS_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->dbg.p) { CK(ctx->dbg.ensure(16 * 8)); CK(cudaMemset(ctx->dbg.p, 0, 16 * 8)); }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (out16) CK(cudaMemcpy(out16, ctx->dbg.p, 16 * 8, cudaMemcpyDeviceToHost));
+  if (reset) CK(cudaMemset(ctx->dbg.p, 0, 16 * 8));
+  return KS_OK;
+}
+
 int ks_kmer_seq(int k, uint64_t code, char *out) {
   static const char nuc[4] = {'A', 'C', 'T', 'G'};
   if (k < 1 || k > 16 || !out) return KS_ERR_ARG;
@@ -293,6 +311,13 @@ static int seqset_common(ks_ctx *ctx, const int64_t *lens, int nseq, ks_seqset *
     s->bases += lens[i];
   }
   CK(cudaMalloc(&s->d_starts, sizeof(int64_t) * ((size_t)nseq + 1)));
+  {
+    size_t nch = (size_t)(s->total / 16) + 8;
+    CK(cudaMalloc(&s->d_pk, nch * sizeof(uint32_t)));
+    CK(cudaMalloc(&s->d_brk, nch * sizeof(uint16_t)));
+    CK(cudaMemsetAsync(s->d_pk, 0, nch * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(s->d_brk, 0xff, nch * sizeof(uint16_t), ctx->stream));  // beyond the data: all breaks
+  }
   CK(cudaMemcpyAsync(s->d_starts, s->starts.data(), sizeof(int64_t) * ((size_t)nseq + 1),
                      cudaMemcpyHostToDevice, ctx->stream));
   return KS_OK;
@@ -394,6 +419,8 @@ void ks_seqset_free(ks_seqset *s) {
   if (s->ctx) cudaSetDevice(s->ctx->device);
   if (s->owned && s->d_buf) cudaFree(s->d_buf);
   if (s->d_starts) cudaFree(s->d_starts);
+  if (s->d_pk) cudaFree(s->d_pk);
+  if (s->d_brk) cudaFree(s->d_brk);
   delete s;
 }
 int64_t ks_seqset_bases(const ks_seqset *s) { return s ? s->bases : 0; }
@@ -414,9 +441,10 @@ int ks_dev_count(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, doub
   CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
   int64_t nchunks = (s->total - 16) / 16;
   cudaEvent_t pe = ctx->prof_begin();
-  count_kernel<<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
-      s->d_buf, nchunks, k, (uint32_t)(n - 1), d_counts, ctx->nwords.as<unsigned long long>());
+  pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
+      s->d_buf, nchunks, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, d_counts, ctx->nwords.as<unsigned long long>());
   ctx->prof_end(KS_PROF_COUNT, pe);
+  s->packed = true;
   LAUNCHED(1);
   CK(cudaGetLastError());
   unsigned long long nw = 0;
@@ -596,6 +624,7 @@ static int ensure_tiles(ks_ctx *ctx, size_t tiles) {
     CK(b->ensure(t * 16));
     CK(cudaMemsetAsync(b->p, 0, b->cap, st));
   }
+  CK(ctx->gdone.ensure((t / 32 + 4) * 4));
   ctx->epoch = 0;  // fresh, zeroed tags
   ctx->tiles_cap = t;
   return KS_OK;
@@ -631,6 +660,30 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
   DevScanParams *d_prm = ctx->prm.as<DevScanParams>();
   CK(ctx->tile_counter.ensure(64));
   CK(ctx->rec_count.ensure(64));
+  if (!s->packed) {  // no counting pass ran on this set (user-supplied weights): pack only
+    int64_t nch = (s->total - 16) / 16;
+    cudaEvent_t pe = ctx->prof_begin();
+    pack_count_kernel<false><<<grid_for((size_t)nch, 256, 148u * 8u), 256, 0, st>>>(
+        s->d_buf, nch, k, (uint32_t)(nk - 1), s->d_pk, s->d_brk, nullptr, nullptr);
+    ctx->prof_end(KS_PROF_COUNT, pe);
+    LAUNCHED(1);
+    CK(cudaGetLastError());
+    s->packed = true;
+  }
+  // persistent grid: every CTA of the launch must be resident (tiles wait on earlier tiles)
+  const size_t dyn_smem = 2 * sizeof(Stash);
+  if (!ctx->scan_cfg_done) {
+    CK(cudaFuncSetAttribute(scan_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    CK(cudaFuncSetAttribute(scan_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    int occ_t = 0, occ_f = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, scan_level_kernel<true>, TILE_THREADS, dyn_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, scan_level_kernel<false>, TILE_THREADS, dyn_smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    int occ = occ_t < occ_f ? occ_t : occ_f;
+    if (occ < 1 || sms < 1) return ctx->fail(KS_ERR_CUDA, "scan kernel does not fit on this device");
+    ctx->scan_max_ctas = (size_t)occ * (size_t)sms;
+    ctx->scan_cfg_done = true;
+  }
   unsigned long long *d_rec_count = ctx->rec_count.as<unsigned long long>();
   CK(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), st));
   if (!ctx->counter_init) {
@@ -658,7 +711,9 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     if (rc) return rc;
     LevelArgs A;
     memset(&A, 0, sizeof A);
-    A.buf = s->d_buf;
+    A.pk = s->d_pk;
+    A.brk = s->d_brk;
+    A.ntiles = (int64_t)tiles;
     A.wfx = ctx->wfx.as<int64_t>();
     A.counts = tab.counts;
     A.lut = ctx->lut_fx.as<int64_t>();
@@ -682,6 +737,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.ts.exB = ctx->ex_inc.as<uint4>();
     A.ts.gA = ctx->xf_status.as<uint4>();
     A.ts.gB = ctx->ex_status.as<uint4>();
+    A.ts.gdone = ctx->gdone.as<uint32_t>();
+    CK(cudaMemsetAsync(ctx->gdone.p, 0, (tiles / 32 + 2) * 4, st));
     ctx->epoch += 1;
     if (ctx->epoch >= (1u << 28) - 1) {  // epoch space exhausted: start over with zeroed tags
       CK(cudaMemsetAsync(ctx->xf_agg.p, 0, ctx->xf_agg.cap, st));
@@ -694,8 +751,9 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     }
     A.epoch = ctx->epoch;
     A.tile_counter = ctx->tile_counter.as<unsigned int>();
+    const size_t grid = tiles < ctx->scan_max_ctas ? tiles : ctx->scan_max_ctas;
     A.tile_base = ctx->tile_base;
-    ctx->tile_base += (unsigned int)tiles;
+    ctx->tile_base += (unsigned int)(tiles + grid);  // every CTA draws ids until it sees one >= ntiles
     A.rec_beg = ctx->rec_beg.as<int64_t>();
     A.rec_pk = ctx->rec_pk.as<int64_t>();
     A.rec_c = ctx->rec_c.as<int64_t>();
@@ -703,9 +761,10 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.rec_mlo = ctx->rec_mlo.as<uint64_t>();
     A.rec_count = d_rec_count;
     A.rec_cap = ctx->rec_cap;
+    A.dbg = (level == 0 && ctx->dbg.p) ? ctx->dbg.as<unsigned long long>() : nullptr;
     cudaEvent_t ps = ctx->prof_begin();
-    if (tab.use_lut) scan_level_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else scan_level_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    if (tab.use_lut) scan_level_kernel<true><<<(unsigned)grid, TILE_THREADS, dyn_smem, st>>>(A);
+    else scan_level_kernel<false><<<(unsigned)grid, TILE_THREADS, dyn_smem, st>>>(A);
     ctx->prof_end(level == 0 ? KS_PROF_SCAN0 : KS_PROF_SCANN, ps);
     LAUNCHED(1);
     CK(cudaGetLastError());

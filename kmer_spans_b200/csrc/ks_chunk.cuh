@@ -33,61 +33,68 @@ constexpr int CHUNK = 16;
 typedef __int128 fx_t;                 // running sums, units of q = 2^-QS
 constexpr int64_t WFX_KILL = INT64_MIN;  // table sentinel: NaN / -inf weight => state forced to 0
 
-KS_HD bool is_break(uint32_t c) { return c == 0u || (c | 0x20u) == 0x6eu; }  // NUL, 'N', 'n'
-KS_HD uint32_t base2(uint32_t c) { return (c >> 1) & 3u; }
-KS_HD uint32_t byte_of(const uint32_t *w, int j) { return (w[j >> 2] >> ((j & 3) * 8)) & 0xffu; }
 
 // ---------------------------------------------------------------------------------------------
-// decode for the SCAN: w[0..3] = the 16 bytes before the chunk, w[4..7] = the chunk itself.
-// code[j] = k-mer ending at byte j-1; bit j of `scored` set iff byte j and the k bytes before
-// it are all non-break and j < n_in (n_in = positions of this chunk inside its segment).
-KS_HD void decode_scan(const uint32_t w[8], int k, uint32_t kmask, int n_in, uint32_t code[CHUNK],
-                       uint32_t &scored) {
-  int rl = 0;
-  uint32_t c2 = 0;
+// K1: 2-bit packing with N masking.  16 ASCII bytes (4 little-endian words) ->
+//   pk  : 16 x 2 bits, FIRST base most significant (so that (pk_prev << 32 | pk_cur) >> s yields
+//         rolling k-mer codes directly)
+//   brk : bit j set iff byte j breaks a run (N, n or the terminator)        (:35,112,123)
+//   nul : bit j set iff byte j is the terminator (needed only by the counting rule :143-144)
+KS_HD uint32_t zero_bytes(uint32_t v) {  // 0x80 in every byte of v that is zero (exact)
+  uint32_t t = (v & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+  return ~(t | v | 0x7f7f7f7fu);
+}
+KS_HD uint32_t nib_of_flags(uint32_t m80) {  // 0x80-per-byte flags -> 4 bits, byte 0 -> bit 0
+  return (((m80 >> 7) & 0x01010101u) * 0x01020408u) >> 24 & 0xfu;
+}
+KS_HD void pack16(const uint32_t w[4], uint32_t &pk, uint32_t &brk, uint32_t &nul) {
+  pk = 0; brk = 0; nul = 0;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    uint32_t c = byte_of(w, j);
-    rl = is_break(c) ? 0 : rl + 1;
-    c2 = (c2 << 2) | base2(c);
-  }
-  scored = 0;
-#pragma unroll
-  for (int j = 0; j < CHUNK; ++j) {
-    uint32_t c = byte_of(w, 16 + j);
-    bool brk = is_break(c);
-    code[j] = c2 & kmask;
-    if (!brk && rl >= k && j < n_in) scored |= 1u << j;
-    rl = brk ? 0 : rl + 1;
-    c2 = (c2 << 2) | base2(c);
+  for (int i = 0; i < 4; ++i) {
+    uint32_t t = (w[i] >> 1) & 0x03030303u;             // (c >> 1) & 3 per byte
+    uint32_t b = (t * 0x40100401u) >> 24;               // 4 bases, byte 0 most significant
+    pk |= b << (24 - 8 * i);
+    uint32_t z = zero_bytes(w[i]);
+    uint32_t n = zero_bytes((w[i] | 0x20202020u) ^ 0x6e6e6e6eu);
+    nul |= nib_of_flags(z) << (4 * i);
+    brk |= nib_of_flags(z | n) << (4 * i);
   }
 }
 
-// decode for COUNTING: code[j] = k-mer ENDING at byte j; bit j of `counted` set iff that k-mer
-// is counted by sequence_kmer_count (:135-155): all k bytes non-break, and not the case "first
-// k-mer of its run and the next byte is the terminator" (:143-144).  next = byte 16 of the chunk.
-KS_HD void decode_count(const uint32_t w[8], uint32_t next, int k, uint32_t kmask,
+// run masks: bit b of the result is set iff bits b-len+1 .. b of ok are all set (len in 1..16)
+KS_HD uint32_t run_ending(uint32_t ok, int len) {
+  uint32_t r = ok;
+  int have = 1;
+  while (have * 2 <= len) { r &= r << have; have *= 2; }
+  if (have < len) r &= r << (len - have);
+  return r;
+}
+
+// decode for the SCAN from packed input.  X = (pk of the 16 positions before the chunk) << 32 | pk of
+// the chunk; brk32 = brk of the 16 positions before (bits 0..15) | brk of the chunk << 16.
+// code[j] = k-mer ending at position j-1; bit j of `scored` set iff position j and the k positions
+// before it are all non-break and j < n_in.
+KS_HD void decode_scan(uint64_t X, uint32_t brk32, int k, uint32_t kmask, int n_in, uint32_t code[CHUNK],
+                       uint32_t &scored) {
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) code[j] = (uint32_t)(X >> (32 - 2 * j)) & kmask;
+  uint32_t r = run_ending(~brk32, k + 1) >> 16;
+  uint32_t inside = n_in >= 16 ? 0xffffu : ((1u << n_in) - 1u);
+  scored = r & inside;
+}
+
+// decode for COUNTING (from the ASCII chunk, packed on the fly): code[j] = k-mer ENDING at position
+// j; bit j of `counted` set iff sequence_kmer_count (:135-155) counts it: all k positions
+// non-break, and not "first k-mer of its run with the terminator right behind it" (:143-144).
+// nul32 like brk32; next_nul = position 16 (first of the next chunk) is the terminator.
+KS_HD void decode_count(uint64_t X, uint32_t brk32, uint32_t nul32, uint32_t next_nul, int k, uint32_t kmask,
                         uint32_t code[CHUNK], uint32_t &counted) {
-  int rl = 0;
-  uint32_t c2 = 0;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    uint32_t c = byte_of(w, j);
-    rl = is_break(c) ? 0 : rl + 1;
-    c2 = (c2 << 2) | base2(c);
-  }
-  counted = 0;
-#pragma unroll
-  for (int j = 0; j < CHUNK; ++j) {
-    uint32_t c = byte_of(w, 16 + j);
-    uint32_t nx = (j == CHUNK - 1) ? next : byte_of(w, 17 + j);
-    bool brk = is_break(c);
-    c2 = (c2 << 2) | base2(c);
-    code[j] = c2 & kmask;
-    bool ok = !brk && rl >= k - 1 && !(rl == k - 1 && nx == 0u);
-    if (ok) counted |= 1u << j;
-    rl = brk ? 0 : rl + 1;
-  }
+  for (int j = 0; j < CHUNK; ++j) code[j] = (uint32_t)(X >> (30 - 2 * j)) & kmask;
+  uint32_t runk = run_ending(~brk32, k);
+  uint32_t first = runk & (brk32 << k);                       // the run starts exactly k positions back
+  uint32_t nulnext = (nul32 >> 1) | (next_nul ? 0x80000000u : 0u);  // bit b: position b+1 is the terminator
+  counted = (runk & ~(first & nulnext)) >> 16;
 }
 
 // ---------------------------------------------------------------------------------------------

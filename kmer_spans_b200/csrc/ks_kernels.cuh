@@ -20,7 +20,13 @@
 
 namespace ks {
 
-constexpr int TILE_THREADS = 256;
+#ifndef KS_TILE_THREADS
+#define KS_TILE_THREADS 256
+#endif
+#ifndef KS_SCAN_MINBLOCKS
+#define KS_SCAN_MINBLOCKS 2
+#endif
+constexpr int TILE_THREADS = KS_TILE_THREADS;
 constexpr int TILE_WARPS = TILE_THREADS / 32;
 
 // ------------------------------------------------------------------------------------------
@@ -85,36 +91,52 @@ __device__ __forceinline__ Ex shfl_ex(const Ex &e, int src) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K1 + K2: counting.  One thread = one 16-byte chunk; grid-stride, consecutive threads read
-// consecutive 16-byte vectors (512 B per warp request).
-__global__ void __launch_bounds__(256) count_kernel(const uint8_t *__restrict__ buf, int64_t nchunks,
-                                                    int k, uint32_t kmask, int32_t *__restrict__ counts,
-                                                    unsigned long long *__restrict__ nwords) {
+// K1 + K2: pack + count.  One thread = one 16-byte chunk of the ASCII buffer; grid-stride, consecutive
+// threads read consecutive 16-byte vectors (512 B per warp request).  Writes the 2-bit packed codes
+// (4 B per 16 bases) and the break mask (2 B per 16 bases) that every scan pass reads instead of the
+// ASCII, and (kCount) reduces the k-mer ending at every position into the int32[4^k] table.
+template <bool kCount>
+__global__ void __launch_bounds__(256) pack_count_kernel(const uint8_t *__restrict__ buf, int64_t nchunks,
+                                                         int k, uint32_t kmask, uint32_t *__restrict__ pk_out,
+                                                         uint16_t *__restrict__ brk_out,
+                                                         int32_t *__restrict__ counts,
+                                                         unsigned long long *__restrict__ nwords) {
   unsigned long long local = 0;
   const uint64_t keep = l2_policy_evict_last();
   for (int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ci < nchunks;
        ci += (int64_t)gridDim.x * blockDim.x) {
-    const uint8_t *p = buf + 16 * ci;  // = (chunk position p0) - 16
+    const uint8_t *p = buf + 16 * ci;  // chunk ci+1 of the buffer starts at p + 16
     const uint4 *v = reinterpret_cast<const uint4 *>(p);
     uint4 a = ld_stream_u4(v), b = ld_stream_u4(v + 1);
-    uint32_t next = __ldg(p + 32);
-    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t code[CHUNK], counted;
-    decode_count(w, next, k, kmask, code, counted);
+    uint32_t wp[4] = {a.x, a.y, a.z, a.w}, wc[4] = {b.x, b.y, b.z, b.w};
+    uint32_t pkp, bp, np, pkc, bc, nc;
+    pack16(wp, pkp, bp, np);
+    pack16(wc, pkc, bc, nc);
+    pk_out[ci + 1] = pkc;
+    brk_out[ci + 1] = (uint16_t)bc;
+    if (ci == 0) { pk_out[0] = pkp; brk_out[0] = (uint16_t)bp; }
+    if (kCount) {
+      uint32_t next = __ldg(p + 32);
+      uint32_t code[CHUNK], counted;
+      decode_count(((uint64_t)pkp << 32) | pkc, bp | (bc << 16), np | (nc << 16), next == 0u, k, kmask, code,
+                   counted);
 #pragma unroll
-    for (int j = 0; j < CHUNK; ++j)
-      if (counted & (1u << j)) red_add_u32_keep(&counts[code[j]], 1u, keep);
-    local += __popc(counted);
+      for (int j = 0; j < CHUNK; ++j)
+        if (counted & (1u << j)) red_add_u32_keep(&counts[code[j]], 1u, keep);
+      local += __popc(counted);
+    }
   }
+  if (kCount) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-  __shared__ unsigned long long sm[8];
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = local;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long t = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
-    if (t) atomicAdd(nwords, t);
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    __shared__ unsigned long long sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long t = 0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
+      if (t) atomicAdd(nwords, t);
+    }
   }
 }
 
@@ -178,6 +200,7 @@ struct TileState {
   uint4 *xfB;  // aggregate: b (+kill in the tag)   | inclusive: S at the tile end
   uint4 *gA;   // the same pair per GROUP of 32 consecutive tiles (second look-back level)
   uint4 *gB;
+  uint32_t *gdone;  // per group: tiles whose aggregate is published (zeroed before every launch)
   uint4 *exA;  // open-excursion aggregate of the tile: M
   uint4 *exB;  //                                       beg (48 bit) | pk (48 bit)
 };
@@ -203,7 +226,9 @@ constexpr uint32_t TAG_AGG = 1u, TAG_INC = 2u, TAG_KILL = 4u, TAG_OPEN = 8u;
 constexpr int64_t POS48_NONE = (1ll << 48) - 1;
 
 struct LevelArgs {
-  const uint8_t *buf;
+  const uint32_t *pk;   // packed 2-bit codes, one word per 16 positions (chunk c = positions [16c, 16c+16))
+  const uint16_t *brk;  // break masks, one half-word per 16 positions
+  int64_t ntiles;
   const int64_t *wfx;         // table mode: exact fixed-point score per k-mer (W - thr)
   // LUT mode (score is a function of the count): gather the int32 count (4 B/entry, L2 resident at
   // k <= 12), then the score from a dense count -> score table; counts >= lut_size use the sorted
@@ -235,6 +260,7 @@ struct LevelArgs {
   uint64_t *rec_mlo;
   unsigned long long *rec_count;
   unsigned long long rec_cap;
+  unsigned long long *dbg;  // KS_EXP_TIMING builds: per-phase cycle sums (thread 0 of every tile)
 };
 
 struct DevEmit {
@@ -290,20 +316,19 @@ __device__ __forceinline__ Xf warp_fold_xf(Xf x, int lane) {
 // Two-level decoupled look-back for the max-plus transform, run by warp 0: returns the state S at
 // the start of `tile`.  Window 1 covers the earlier tiles of the own 32-tile group; if that is not
 // enough, window 2+ walks whole groups, 32 per step, so ~1000 tiles of lag cost two windows.
-// The last tile of a group publishes the group aggregate as soon as its window 1 is folded.
+// Group aggregates are published EARLY, by whichever tile of the group finishes its local phase last
+// (publish_group_if_last); the last tile of a group later upgrades it to the inclusive value.
 // A transform with kill set (an inclusive value, or an aggregate containing a reset) ends the walk
 // because composition ignores everything left of it.
 __device__ __forceinline__ fx_t lookback_xf(const TileState &ts, int64_t tile, uint32_t epoch,
                                             const Xf &agg, int lane) {
   const int64_t g = tile / GROUP_TILES;
   const int l = (int)(tile % GROUP_TILES);
-  if (lane == 0) publish_xf(ts.xfA, ts.xfB, tile, epoch, agg);
-  Xf x = xf_identity();
+  Xf x = xf_identity();  // (the tile's own aggregate was published at the end of its local phase)
   if (lane < l) x = poll_xf(ts.xfA, ts.xfB, tile - 1 - lane, epoch);
   Xf acc = warp_fold_xf(x, lane);  // tiles [32 g, tile)
   const Xf grp = xf_compose(acc, agg);  // tiles [32 g, tile]
   const bool last = (l == GROUP_TILES - 1);
-  if (last && lane == 0) publish_xf(ts.gA, ts.gB, g, epoch, grp);
   int64_t gbase = g - 1;
   while (!acc.kill) {
     int64_t idx = gbase - lane;
@@ -370,63 +395,69 @@ __device__ __forceinline__ Ex lookback_ex(const TileState &ts, int64_t tile, uin
   }
 }
 
-// K4 + K5 + K6.  One CTA = one tile of 256 chunks (4096 positions), tile ids handed out in launch
-// order by an atomic counter so that a tile only ever waits on tiles that already run.
+// K4 + K5 + K6.  Persistent CTAs, tile = TILE_THREADS chunks (4096 positions at 256 threads), tile ids
+// handed out in order by an atomic counter so that a tile only ever waits on tiles that already run.
+// Software pipeline per CTA:   local(t1)  local(t2) finish(t1)  local(t3) finish(t2) ...
+//   local : packed input -> codes -> table gather -> chunk transform -> block scan -> publish aggregate;
+//           everything finish() needs is stashed in shared memory
+//   finish: look-back for the state entering the tile (by now the predecessors' aggregates exist),
+//           excursion walk, segmented scan of the open-excursion state, emission
+// so the look-back latency of one tile hides behind the gather latency of the next.
+struct Stash {
+  int64_t s[CHUNK][TILE_THREADS];  // fixed-point scores, [j][thread]: conflict-free 8-byte accesses
+  fx_t ea[TILE_THREADS];           // exclusive in-tile transform of the thread: a
+  fx_t eb[TILE_THREADS];           //                                              b
+  int64_t p0[TILE_THREADS];
+  uint32_t flags[TILE_THREADS];    // live (16 bits) | head << 16 | excl.kill << 17
+  Xf agg;                          // aggregate of the tile
+  uint32_t group_last;             // this tile completed its 32-tile group
+};
+
 template <bool kLut>
-__global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const LevelArgs A) {
-  __shared__ int64_t s_tile;
-  __shared__ Xf s_wxf[TILE_WARPS];
-  __shared__ Ex s_wex[TILE_WARPS];
-  __shared__ fx_t s_S;
-  __shared__ Ex s_E;
-
+__device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Stash &st, Xf *s_wxf) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = (int64_t)(unsigned int)(atomicAdd(A.tile_counter, 1u) - A.tile_base);
-  __syncthreads();
-  const int64_t tile = s_tile;
-
-  ScanParams prm;
-  prm.min_width = A.prm->min_width;
-  prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
-
   // ---- chunk -> position mapping ----
   const int64_t q = tile * TILE_THREADS + tid;
   int64_t p0 = 16;
   int n_in = 0;
   bool head = true;
-  uint32_t w[8];
-  if (A.nseg == 0) {
-    if (q < A.total_chunks) { p0 = A.dense_start + 16 * q; n_in = 16; head = (q == 0); }
-    const uint4 *v = reinterpret_cast<const uint4 *>(A.buf + p0 - 16);
-    uint4 a = ld_stream_u4(v), b = ld_stream_u4(v + 1);
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-  } else {
-    if (q < A.total_chunks) {
+  if (q < A.total_chunks) {
+    if (A.nseg == 0) {
+      p0 = A.dense_start + 16 * q; n_in = 16; head = (q == 0);
+    } else {
       int64_t lo = 0, hi = A.nseg;  // largest s in [0, nseg) with seg_chunk0[s] <= q
       while (hi - lo > 1) {
         int64_t mid = (lo + hi) >> 1;
         if (__ldg(&A.seg_chunk0[mid]) <= (uint64_t)q) lo = mid; else hi = mid;
       }
       int64_t c0 = (int64_t)__ldg(&A.seg_chunk0[lo]);
-      int64_t st = __ldg(&A.seg_start[lo]), ln = __ldg(&A.seg_len[lo]);
-      p0 = st + 16 * (q - c0);
-      int64_t rem = st + ln - p0;
+      int64_t sst = __ldg(&A.seg_start[lo]), ln = __ldg(&A.seg_len[lo]);
+      p0 = sst + 16 * (q - c0);
+      int64_t rem = sst + ln - p0;
       n_in = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
       head = (q == c0);
     }
-    const uint32_t off = (uint32_t)(p0 & 3);
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(A.buf + (p0 - 16 - off));
-    uint32_t r[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) r[i] = __ldg(wp + i);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = __funnelshift_r(r[i], r[i + 1], off * 8);
   }
-
-  // ---- decode + gather ----
+  // ---- packed window [p0 - 16, p0 + 16) ----
+  const int64_t wq = p0 >> 4;
+  const int r = (int)(p0 & 15);
+  uint32_t hi32 = __ldg(&A.pk[wq - 1]), mid32 = __ldg(&A.pk[wq]);
+  uint32_t b0 = __ldg(&A.brk[wq - 1]), b1 = __ldg(&A.brk[wq]);
+  uint64_t X;
+  uint32_t brk32;
+  if (r == 0) {
+    X = ((uint64_t)hi32 << 32) | mid32;
+    brk32 = b0 | (b1 << 16);
+  } else {
+    uint32_t lo32 = __ldg(&A.pk[wq + 1]);
+    uint32_t b2 = __ldg(&A.brk[wq + 1]);
+    X = ((uint64_t)__funnelshift_l(mid32, hi32, 2 * r) << 32) | __funnelshift_l(lo32, mid32, 2 * r);
+    uint64_t b48 = (uint64_t)b0 | ((uint64_t)b1 << 16) | ((uint64_t)b2 << 32);
+    brk32 = (uint32_t)(b48 >> r);
+  }
+  // ---- codes + gather ----
   uint32_t code[CHUNK], scored;
-  decode_scan(w, A.k, A.kmask, n_in, code, scored);
+  decode_scan(X, brk32, A.k, A.kmask, n_in, code, scored);
   int64_t s[CHUNK];
   uint32_t live = 0;
   const uint64_t keep = l2_policy_evict_last();
@@ -464,8 +495,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const Level
     for (int j = 0; j < CHUNK; ++j)
       if (scored & (1u << j)) atomicAdd(&A.inscan[code[j]], 1);
   }
-
-  // ---- max-plus scan: chunk transform, block scan, look-back ----
+  // ---- chunk transform + block scan ----
   Xf f = chunk_transform(s, live);
   if (head) { fx_t v = xf_apply(f, 0); f.kill = 1; f.a = 0; f.b = v; }
   Xf inc = f;
@@ -477,20 +507,68 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const Level
   Xf excl = shfl_xf(inc, (lane - 1) & 31);
   if (lane == 0) excl = xf_identity();
   if (lane == 31) s_wxf[warp] = inc;
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) st.s[j][tid] = s[j];
+  st.p0[tid] = p0;
   __syncthreads();
   Xf wpre = xf_identity();
   for (int i = 0; i < warp; ++i) wpre = xf_compose(wpre, s_wxf[i]);
   excl = xf_compose(wpre, excl);
-  if (warp == 0) {
+  st.ea[tid] = excl.a;
+  st.eb[tid] = excl.b;
+  st.flags[tid] = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u);
+  if (tid == 0) {
     Xf agg = xf_identity();
 #pragma unroll
     for (int i = 0; i < TILE_WARPS; ++i) agg = xf_compose(agg, s_wxf[i]);
-    fx_t S0 = lookback_xf(A.ts, tile, A.epoch, agg, lane);
-    if (lane == 0) s_S = S0;
+    st.agg = agg;
+    publish_xf(A.ts.xfA, A.ts.xfB, tile, A.epoch, agg);
+    // the tile that completes a group publishes the group aggregate right away
+    const int64_t g = tile / GROUP_TILES;
+    int64_t gsize = A.ntiles - g * GROUP_TILES;
+    if (gsize > GROUP_TILES) gsize = GROUP_TILES;
+    uint32_t done = atomicAdd(&A.ts.gdone[g], 1u);
+    st.group_last = (gsize == GROUP_TILES && done == (uint32_t)(GROUP_TILES - 1)) ? 1u : 0u;
+  }
+  __syncthreads();  // s_wxf may be overwritten by the next local phase; the stash is complete
+  if (st.group_last && warp == 0) {
+    const int64_t g = tile / GROUP_TILES;
+    Xf x = poll_xf(A.ts.xfA, A.ts.xfB, g * GROUP_TILES + (GROUP_TILES - 1 - lane), A.epoch);
+    Xf grp = warp_fold_xf(x, lane);
+    if (lane == 0) {
+      uint4 cur = ld_desc(&A.ts.gB[g]);
+      if (!((cur.x >> 4) == A.epoch && (cur.x & 3u) == TAG_INC)) publish_xf(A.ts.gA, A.ts.gB, g, A.epoch, grp);
+    }
+  }
+}
+
+__device__ __forceinline__ void scan_finish(const LevelArgs &A, int64_t tile, const Stash &st, Ex *s_wex,
+                                            fx_t *s_S, Ex *s_E, const ScanParams &prm) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (warp == 0) {
+#if defined(KS_EXP_NO_LOOKBACK)
+    fx_t S0 = 0;
+#else
+    fx_t S0 = lookback_xf(A.ts, tile, A.epoch, st.agg, lane);
+#endif
+    if (lane == 0) *s_S = S0;
   }
   __syncthreads();
-  const fx_t S_tile = s_S;
+  const fx_t S_tile = *s_S;
+#if defined(KS_EXP_NO_WALK)
+  if (S_tile == 12345) A.rec_count[0] = 1;
+  return;
+#endif
+  const uint32_t fl = st.flags[tid];
+  const uint32_t live = fl & 0xffffu;
+  const bool head = (fl & 0x10000u) != 0;
+  const int64_t p0 = st.p0[tid];
+  Xf excl;
+  excl.a = st.ea[tid]; excl.b = st.eb[tid]; excl.kill = (fl >> 17) & 1u;
   const fx_t S_in = head ? (fx_t)0 : xf_apply(excl, S_tile);
+  int64_t s[CHUNK];
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) s[j] = st.s[j][tid];
 
   // ---- excursions: local walk, segmented scan of the open-excursion state, lazy look-back ----
   DevEmit emit{&A};
@@ -522,12 +600,47 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) scan_level_kernel(const Level
     E0.reset = 1; E0.open = 0;
     // only if an excursion enters the tile AND something inside the tile ends it
     if (S_tile > 0 && eagg.reset) E0 = lookback_ex(A.ts, tile, A.epoch, lane);
-    if (lane == 0) s_E = E0;
+    if (lane == 0) *s_E = E0;
   }
   __syncthreads();
   if (!head) {
-    Ex E_in = ex_combine(s_E, eexcl);
+    Ex E_in = ex_combine(*s_E, eexcl);
     chunk_finish_entering(S_in, E_in, preM, prePk, first_zero, p0, prm, emit);
+  }
+}
+
+template <bool kLut>
+__global__ void __launch_bounds__(TILE_THREADS, KS_SCAN_MINBLOCKS) scan_level_kernel(const LevelArgs A) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  Stash *stash = reinterpret_cast<Stash *>(dyn_smem);  // two buffers
+  __shared__ int64_t s_tile;
+  __shared__ Xf s_wxf[TILE_WARPS];
+  __shared__ Ex s_wex[TILE_WARPS];
+  __shared__ fx_t s_S;
+  __shared__ Ex s_E;
+  const int tid = threadIdx.x;
+
+  ScanParams prm;
+  prm.min_width = A.prm->min_width;
+  prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
+
+  auto next_tile = [&]() -> int64_t {
+    if (tid == 0) s_tile = (int64_t)(unsigned int)(atomicAdd(A.tile_counter, 1u) - A.tile_base);
+    __syncthreads();
+    int64_t t = s_tile;
+    __syncthreads();
+    return t;
+  };
+
+  int cur = 0;
+  int64_t tA = next_tile();
+  if (tA < A.ntiles) scan_local<kLut>(A, tA, stash[0], s_wxf);
+  while (tA < A.ntiles) {
+    int64_t tB = next_tile();
+    if (tB < A.ntiles) scan_local<kLut>(A, tB, stash[cur ^ 1], s_wxf);
+    scan_finish(A, tA, stash[cur], s_wex, &s_S, &s_E, prm);
+    tA = tB;
+    cur ^= 1;
   }
 }
 

@@ -19,8 +19,35 @@
 
 using namespace ks;
 
-static void load_words(const uint8_t *buf, int64_t p0, uint32_t w[8]) {
-  memcpy(w, buf + p0 - 16, 32);
+// K1 on the host: pack the whole buffer (chunk c = positions [16c, 16c+16))
+struct Packed {
+  std::vector<uint32_t> pk;
+  std::vector<uint16_t> brk, nul;
+};
+static Packed pack_buffer(const uint8_t *buf, int64_t ntot) {
+  Packed P;
+  int64_t nch = ntot / 16 + 4;
+  P.pk.assign(nch, 0); P.brk.assign(nch, 0xffff); P.nul.assign(nch, 0xffff);
+  for (int64_t c = 0; c < ntot / 16; ++c) {
+    uint32_t w[4], pk, b, n;
+    memcpy(w, buf + 16 * c, 16);
+    pack16(w, pk, b, n);
+    P.pk[c] = pk; P.brk[c] = (uint16_t)b; P.nul[c] = (uint16_t)n;
+  }
+  return P;
+}
+// 32 positions [p0-16, p0+16) at an arbitrary p0 >= 16, as the kernels assemble them
+static void window(const Packed &P, int64_t p0, uint64_t &X, uint32_t &brk32, uint32_t &nul32) {
+  int64_t wq = p0 >> 4;
+  int r = (int)(p0 & 15);
+  uint32_t hi = P.pk[wq - 1], mid = P.pk[wq], lo = P.pk[wq + 1];
+  uint32_t xh = r ? ((hi << (2 * r)) | (mid >> (32 - 2 * r))) : hi;
+  uint32_t xl = r ? ((mid << (2 * r)) | (lo >> (32 - 2 * r))) : mid;
+  X = ((uint64_t)xh << 32) | xl;
+  uint64_t b48 = (uint64_t)P.brk[wq - 1] | ((uint64_t)P.brk[wq] << 16) | ((uint64_t)P.brk[wq + 1] << 32);
+  uint64_t n48 = (uint64_t)P.nul[wq - 1] | ((uint64_t)P.nul[wq] << 16) | ((uint64_t)P.nul[wq + 1] << 32);
+  brk32 = (uint32_t)(b48 >> r);
+  nul32 = (uint32_t)(n48 >> r);
 }
 
 extern "C" {
@@ -33,11 +60,13 @@ int64_t emu_layout_total(const int64_t *lens, int nseq, int64_t *starts) {
 void emu_count(const uint8_t *buf, int64_t ntot, int k, int32_t *counts, uint64_t *nwords) {
   uint32_t kmask = (1u << (2 * k)) - 1u;
   uint64_t n = 0;
+  Packed P = pack_buffer(buf, ntot);
   for (int64_t p0 = 16; p0 < ntot; p0 += 16) {
-    uint32_t w[8], code[16], counted;
-    load_words(buf, p0, w);
-    uint32_t next = (p0 + 16 < ntot + KS_SLACK) ? buf[p0 + 16] : 0;
-    decode_count(w, next, k, kmask, code, counted);
+    uint32_t code[16], counted, brk32, nul32;
+    uint64_t X;
+    window(P, p0, X, brk32, nul32);
+    uint32_t next_nul = (p0 + 16 < ntot) ? (buf[p0 + 16] == 0) : 1;
+    decode_count(X, brk32, nul32, next_nul, k, kmask, code, counted);
     for (int j = 0; j < 16; ++j)
       if (counted & (1u << j)) { counts[code[j]]++; ++n; }
   }
@@ -116,6 +145,7 @@ int emu_scan(const uint8_t *buf, int64_t ntot, int k, const double *W, double th
   prm.min_width = min_width;
   prm.min_units = fx_ceil_units(min_score, qs);
 
+  Packed P = pack_buffer(buf, ntot);
   std::vector<Rec> all;
   std::vector<std::pair<int64_t, int64_t>> segs;  // start, len
   segs.push_back({16, ntot - 16});
@@ -133,9 +163,10 @@ int emu_scan(const uint8_t *buf, int64_t ntot, int k, const double *W, double th
         int64_t p0 = sg.first + 16 * ci;
         int64_t rem = sg.first + sg.second - p0;
         int n_in = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
-        uint32_t w[8], code[16], scored;
-        load_words(buf, p0, w);
-        decode_scan(w, k, kmask, n_in, code, scored);
+        uint32_t code[16], scored, brk32, nul32;
+        uint64_t X;
+        window(P, p0, X, brk32, nul32);
+        decode_scan(X, brk32, k, kmask, n_in, code, scored);
         int64_t s[16];
         uint32_t live = 0;
         for (int j = 0; j < 16; ++j) {
