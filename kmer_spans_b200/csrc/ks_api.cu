@@ -100,7 +100,7 @@ struct ks_ctx {
   // staging / misc
   void *pinned = nullptr;
   size_t pinned_cap = 0;
-  DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, dbg, gdone;
+  DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, dbg, gdone, pending;
 
   // timing / profiling
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -223,7 +223,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->out_score, &ctx->sc_keys_a, &ctx->sc_keys_b, &ctx->sc_vals_a, &ctx->sc_vals_b,
                  &ctx->sc_small, &ctx->sc_gcount, &ctx->sc_gstart, &ctx->sc_segfirst, &ctx->sc_segj0,
                  &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->tmp_counts, &ctx->tmp_scores,
-                 &ctx->tmp_inscan, &ctx->nwords, &ctx->dbg, &ctx->gdone, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
+                 &ctx->tmp_inscan, &ctx->nwords, &ctx->dbg, &ctx->gdone, &ctx->pending, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -625,6 +625,8 @@ static int ensure_tiles(ks_ctx *ctx, size_t tiles) {
     CK(cudaMemsetAsync(b->p, 0, b->cap, st));
   }
   CK(ctx->gdone.ensure((t / 32 + 4) * 4));
+  CK(ctx->pending.ensure(t * sizeof(ExPending)));
+  CK(cudaMemsetAsync(ctx->pending.p, 0, ctx->pending.cap, st));
   ctx->epoch = 0;  // fresh, zeroed tags
   ctx->tiles_cap = t;
   return KS_OK;
@@ -711,6 +713,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     if (rc) return rc;
     LevelArgs A;
     memset(&A, 0, sizeof A);
+    A.pending = ctx->pending.as<ExPending>();
     A.pk = s->d_pk;
     A.brk = s->d_brk;
     A.ntiles = (int64_t)tiles;
@@ -747,6 +750,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
       CK(cudaMemsetAsync(ctx->ex_inc.p, 0, ctx->ex_inc.cap, st));
       CK(cudaMemsetAsync(ctx->xf_status.p, 0, ctx->xf_status.cap, st));
       CK(cudaMemsetAsync(ctx->ex_status.p, 0, ctx->ex_status.cap, st));
+      CK(cudaMemsetAsync(ctx->pending.p, 0, ctx->pending.cap, st));
       ctx->epoch = 1;
     }
     A.epoch = ctx->epoch;
@@ -765,8 +769,9 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     cudaEvent_t ps = ctx->prof_begin();
     if (tab.use_lut) scan_level_kernel<true><<<(unsigned)grid, TILE_THREADS, dyn_smem, st>>>(A);
     else scan_level_kernel<false><<<(unsigned)grid, TILE_THREADS, dyn_smem, st>>>(A);
+    ex_fixup_kernel<<<blocks_exact(tiles, 8), 256, 0, st>>>(A);
     ctx->prof_end(level == 0 ? KS_PROF_SCAN0 : KS_PROF_SCANN, ps);
-    LAUNCHED(1);
+    LAUNCHED(2);
     CK(cudaGetLastError());
     struct { unsigned long long cnt; } hres;
     DevScanParams hprm;

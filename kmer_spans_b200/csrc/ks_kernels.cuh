@@ -225,7 +225,20 @@ __device__ __forceinline__ fx_t desc_fx(const uint4 &d) {  // sign-extend the 96
 constexpr uint32_t TAG_AGG = 1u, TAG_INC = 2u, TAG_KILL = 4u, TAG_OPEN = 8u;
 constexpr int64_t POS48_NONE = (1ll << 48) - 1;
 
+// An excursion that entered a tile from the left and closes inside it needs the open-excursion state
+// at the tile start.  The scan kernel never waits for it: the one thread per tile that needs it
+// leaves this record, and ex_fixup_kernel resolves it after the launch from the per-tile aggregates.
+struct __align__(16) ExPending {
+  uint64_t m_lo;
+  int64_t m_hi;   // max over the tile's positions before the close (fixed point)
+  int64_t pk;     // its leftmost position
+  int64_t c;      // close position
+  uint32_t epoch; // valid iff == launch epoch
+  uint32_t pad[3];
+};
+
 struct LevelArgs {
+  ExPending *pending;  // one slot per tile
   const uint32_t *pk;   // packed 2-bit codes, one word per 16 positions (chunk c = positions [16c, 16c+16))
   const uint16_t *brk;  // break masks, one half-word per 16 positions
   int64_t ntiles;
@@ -413,9 +426,18 @@ struct Stash {
   uint32_t group_last;             // this tile completed its 32-tile group
 };
 
+#if defined(KS_EXP_TIMING)
+#define KS_T0 long long tk_ = clock64();
+#define KS_TICK(slot) { long long n_ = clock64(); if (threadIdx.x == 0 && A.dbg) atomicAdd(A.dbg + (slot), (unsigned long long)(n_ - tk_)); tk_ = n_; }
+#else
+#define KS_T0
+#define KS_TICK(slot)
+#endif
+
 template <bool kLut>
 __device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Stash &st, Xf *s_wxf) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  KS_T0
   // ---- chunk -> position mapping ----
   const int64_t q = tile * TILE_THREADS + tid;
   int64_t p0 = 16;
@@ -456,6 +478,8 @@ __device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Sta
     brk32 = (uint32_t)(b48 >> r);
   }
   // ---- codes + gather ----
+  if (X == 0x123456789abcdefull) return;  // (keeps the loads above the tick in timing builds; never true)
+  KS_TICK(0)
   uint32_t code[CHUNK], scored;
   decode_scan(X, brk32, A.k, A.kmask, n_in, code, scored);
   int64_t s[CHUNK];
@@ -496,6 +520,7 @@ __device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Sta
       if (scored & (1u << j)) atomicAdd(&A.inscan[code[j]], 1);
   }
   // ---- chunk transform + block scan ----
+  KS_TICK(1)
   Xf f = chunk_transform(s, live);
   if (head) { fx_t v = xf_apply(f, 0); f.kill = 1; f.a = 0; f.b = v; }
   Xf inc = f;
@@ -507,10 +532,12 @@ __device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Sta
   Xf excl = shfl_xf(inc, (lane - 1) & 31);
   if (lane == 0) excl = xf_identity();
   if (lane == 31) s_wxf[warp] = inc;
+  KS_TICK(2)
 #pragma unroll
   for (int j = 0; j < CHUNK; ++j) st.s[j][tid] = s[j];
   st.p0[tid] = p0;
   __syncthreads();
+  KS_TICK(3)
   Xf wpre = xf_identity();
   for (int i = 0; i < warp; ++i) wpre = xf_compose(wpre, s_wxf[i]);
   excl = xf_compose(wpre, excl);
@@ -531,6 +558,7 @@ __device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Sta
     st.group_last = (gsize == GROUP_TILES && done == (uint32_t)(GROUP_TILES - 1)) ? 1u : 0u;
   }
   __syncthreads();  // s_wxf may be overwritten by the next local phase; the stash is complete
+  KS_TICK(4)
   if (st.group_last && warp == 0) {
     const int64_t g = tile / GROUP_TILES;
     Xf x = poll_xf(A.ts.xfA, A.ts.xfB, g * GROUP_TILES + (GROUP_TILES - 1 - lane), A.epoch);
@@ -543,8 +571,9 @@ __device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Sta
 }
 
 __device__ __forceinline__ void scan_finish(const LevelArgs &A, int64_t tile, const Stash &st, Ex *s_wex,
-                                            fx_t *s_S, Ex *s_E, const ScanParams &prm) {
+                                            fx_t *s_S, const ScanParams &prm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  KS_T0
   if (warp == 0) {
 #if defined(KS_EXP_NO_LOOKBACK)
     fx_t S0 = 0;
@@ -553,6 +582,7 @@ __device__ __forceinline__ void scan_finish(const LevelArgs &A, int64_t tile, co
 #endif
     if (lane == 0) *s_S = S0;
   }
+  KS_TICK(5)
   __syncthreads();
   const fx_t S_tile = *s_S;
 #if defined(KS_EXP_NO_WALK)
@@ -576,7 +606,9 @@ __device__ __forceinline__ void scan_finish(const LevelArgs &A, int64_t tile, co
   fx_t preM;
   int64_t prePk;
   int first_zero;
+  KS_TICK(6)
   chunk_walk(s, live, S_in, p0, prm, emit, ex, preM, prePk, first_zero);
+  KS_TICK(7)
 
   Ex einc = ex;
 #pragma unroll
@@ -591,21 +623,53 @@ __device__ __forceinline__ void scan_finish(const LevelArgs &A, int64_t tile, co
   Ex epre = ex_identity();
   for (int i = 0; i < warp; ++i) epre = ex_combine(epre, s_wex[i]);
   eexcl = ex_combine(epre, eexcl);
-  if (warp == 0) {
+  if (tid == 0) {
     Ex eagg = ex_identity();
 #pragma unroll
     for (int i = 0; i < TILE_WARPS; ++i) eagg = ex_combine(eagg, s_wex[i]);
-    if (lane == 0) publish_ex(A.ts, tile, A.epoch, eagg);
-    Ex E0 = ex_identity();
-    E0.reset = 1; E0.open = 0;
-    // only if an excursion enters the tile AND something inside the tile ends it
-    if (S_tile > 0 && eagg.reset) E0 = lookback_ex(A.ts, tile, A.epoch, lane);
-    if (lane == 0) *s_E = E0;
+    publish_ex(A.ts, tile, A.epoch, eagg);
   }
-  __syncthreads();
-  if (!head) {
-    Ex E_in = ex_combine(*s_E, eexcl);
-    chunk_finish_entering(S_in, E_in, preM, prePk, first_zero, p0, prm, emit);
+  KS_TICK(8)
+  if (!head && S_in > 0 && first_zero >= 0) {
+    if (eexcl.reset) {
+      // the entering excursion started inside this tile: everything is known
+      chunk_finish_entering(S_in, eexcl, preM, prePk, first_zero, p0, prm, emit);
+    } else {
+      // it entered the tile from the left (at most one thread per tile gets here): defer
+      fx_t M = eexcl.M;
+      int64_t pk = eexcl.pk;
+      if (preM > M) { M = preM; pk = prePk; }
+      ExPending *pe = &A.pending[tile];
+      pe->m_lo = fx_lo(M);
+      pe->m_hi = (int64_t)fx_hi(M);
+      pe->pk = pk;
+      pe->c = p0 + first_zero;
+      pe->epoch = A.epoch;
+    }
+  }
+  KS_TICK(9)
+}
+
+// One warp per tile of the finished launch: resolve the deferred entering excursion (if any) by
+// walking back over the per-tile open-excursion aggregates, 32 tiles per step, to the tile that holds
+// the excursion's start.  Every aggregate of the launch is final by now, so nothing spins.
+__global__ void __launch_bounds__(256) ex_fixup_kernel(const LevelArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile >= A.ntiles) return;
+  const ExPending pe = A.pending[tile];
+  if (pe.epoch != A.epoch) return;
+  ScanParams prm;
+  prm.min_width = A.prm->min_width;
+  prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
+  Ex E = lookback_ex(A.ts, tile, A.epoch, lane);
+  if (lane == 0) {
+    fx_t M = E.M;
+    int64_t pk = E.pk;
+    const fx_t Mp = fx_make((uint64_t)pe.m_hi, pe.m_lo);
+    if (Mp > M) { M = Mp; pk = pe.pk; }
+    DevEmit emit{&A};
+    if (E.open && qualifies(prm, E.beg, pk, M)) emit(E.beg, pk, pe.c, M);
   }
 }
 
@@ -617,7 +681,6 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_SCAN_MINBLOCKS) scan_level_ke
   __shared__ Xf s_wxf[TILE_WARPS];
   __shared__ Ex s_wex[TILE_WARPS];
   __shared__ fx_t s_S;
-  __shared__ Ex s_E;
   const int tid = threadIdx.x;
 
   ScanParams prm;
@@ -625,10 +688,13 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_SCAN_MINBLOCKS) scan_level_ke
   prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
 
   auto next_tile = [&]() -> int64_t {
+    KS_T0
     if (tid == 0) s_tile = (int64_t)(unsigned int)(atomicAdd(A.tile_counter, 1u) - A.tile_base);
     __syncthreads();
     int64_t t = s_tile;
     __syncthreads();
+    KS_TICK(10)
+    if (tid == 0 && A.dbg) atomicAdd(A.dbg + 15, 1ull);
     return t;
   };
 
@@ -638,7 +704,7 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_SCAN_MINBLOCKS) scan_level_ke
   while (tA < A.ntiles) {
     int64_t tB = next_tile();
     if (tB < A.ntiles) scan_local<kLut>(A, tB, stash[cur ^ 1], s_wxf);
-    scan_finish(A, tA, stash[cur], s_wex, &s_S, &s_E, prm);
+    scan_finish(A, tA, stash[cur], s_wex, &s_S, prm);
     tA = tB;
     cur ^= 1;
   }

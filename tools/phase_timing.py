@@ -1,4 +1,4 @@
-"""KS_EXP_TIMING builds: average cycles per tile spent in each phase of scan level 0."""
+"""KS_EXP_TIMING builds: average cycles per tile (thread 0) in each phase of scan level 0."""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -20,11 +20,11 @@ for i in range(3):
     if i == 0:
         ctx.lib.ks_ctx_debug_counters(ctx.h, out, 1)
 ctx.lib.ks_ctx_debug_counters(ctx.h, out, 0)
-names = ["load+decode+gather", "transform+warp scan+bar", "lookback / prefix", "barrier wait", "walk+ex+finish"]
-for base, who in ((0, "thread 0 (warp 0)"), (8, "thread 255 (warp 7)")):
-    nt = out[base + 5]
-    print(who, "tiles", nt)
-    tot = sum(out[base + i] for i in range(5))
-    for i, nm in enumerate(names):
-        print("   %-28s %8.0f cycles/tile  %5.1f%%" % (nm, out[base + i] / max(nt, 1), 100.0 * out[base + i] / max(tot, 1)))
-    print("   total %.0f cycles/tile" % (tot / max(nt, 1)))
+names = ["L: map + packed loads", "L: decode + gather + LUT", "L: transform + warp scan", "L: stash + barrier",
+         "L: prefix + publish + barrier", "F: look-back (warp 0)", "F: barrier + unstash", "F: walk",
+         "F: ex scan + publish + barriers", "F: finish entering", "next_tile (2 barriers + atomic)"]
+ntiles = max(out[15], 1)
+tot = sum(out[i] for i in range(11))
+print("mode", mode, "tile fetches", out[15], " total %.0f cycles/tile" % (tot / ntiles))
+for i, nm in enumerate(names):
+    print("   %-34s %8.0f cycles/tile  %5.1f%%" % (nm, out[i] / ntiles, 100.0 * out[i] / max(tot, 1)))
