@@ -163,15 +163,30 @@ INTSXP, REALSXP, STRSXP, VECSXP = 13, 14, 16, 19
 
 
 class Ref:
-    """The compiled reference.  Raises FileNotFoundError when oracle/_ref was not built."""
+    """The compiled reference (default), or any other kmer_spans.so built against the mock R API
+    (path=...: the replacement glue r/_build/kmer_spans.so), driven through mock SEXPs.
+    Raises FileNotFoundError when the library was not built."""
 
-    def __init__(self):
-        path = os.path.join(HERE, "_ref", "libkmer_spans_ref.so")
-        if not os.path.exists(path) and os.path.exists("/root/reference/src/kmer_spans.c"):
-            build()
+    def __init__(self, path=None):
+        self.is_reference = path is None
+        if path is None:
+            path = os.path.join(HERE, "_ref", "libkmer_spans_ref.so")
+            if not os.path.exists(path) and os.path.exists("/root/reference/src/kmer_spans.c"):
+                build()
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.lib = L = C.CDLL(path)
+        P = C.POINTER(_Sexp)
+        L.allocVector.restype = P
+        L.allocVector.argtypes = [C.c_int, C.c_long]
+        L.mkCharLen.restype = P
+        L.mkCharLen.argtypes = [C.c_char_p, C.c_long]
+        L.mockR_call.restype = P
+        L.mockR_call.argtypes = [C.c_void_p, C.c_int, C.POINTER(P)]
+        L.mockR_last_error.restype = C.c_char_p
+        self.P = P
+        if not self.is_reference:
+            return
         L.sequence_kmer_count.restype = C.c_size_t
         L.sequence_kmer_count.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
         L.rank_kmers_w.restype = None
@@ -182,15 +197,6 @@ class Ref:
         L.kmer_regions.argtypes = [C.c_char_p, C.c_int, C.c_size_t, C.c_size_t, C.c_double, C.c_void_p,
                                    C.c_int, C.c_double, C.POINTER(_SeqRegions), C.c_void_p]
         L.seq_regions_free.argtypes = [C.POINTER(_SeqRegions)]
-        P = C.POINTER(_Sexp)
-        L.allocVector.restype = P
-        L.allocVector.argtypes = [C.c_int, C.c_long]
-        L.mkCharLen.restype = P
-        L.mkCharLen.argtypes = [C.c_char_p, C.c_long]
-        L.mockR_call.restype = P
-        L.mockR_call.argtypes = [C.c_void_p, C.c_int, C.POINTER(P)]
-        L.mockR_last_error.restype = C.c_char_p
-        self.P = P
 
     # ---- core C functions on plain buffers ----
     def sequence_kmer_count(self, seq, k, counts):
@@ -290,6 +296,30 @@ class Ref:
         out = self._list(r)
         self.lib.mockR_free_all()
         return dict(n=out[0], counts=out[1], ranks=out[2], pos=out[3].reshape(-1, 3), score=out[4].reshape(-1, 2))
+
+    def registered(self):
+        """[(name, arity)] as registered by R_init_kmer_spans"""
+        class Def(C.Structure):
+            _fields_ = [("name", C.c_char_p), ("fun", C.c_void_p), ("n", C.c_int)]
+        self.lib.R_init_kmer_spans(None)
+        self.lib.mockR_registered.restype = C.POINTER(Def)
+        d = self.lib.mockR_registered()
+        out, i = [], 0
+        while d[i].name:
+            out.append((d[i].name.decode(), d[i].n))
+            i += 1
+        return out
+
+    def call_raw(self, name, args):
+        """args: list of ('s', [bytes]) | ('i', ints) | ('d', doubles); returns list of numpy arrays"""
+        sx = []
+        for kind, val in args:
+            sx.append(self._strsxp(_as_bytes_list(val)) if kind == "s" else
+                      self._intsxp(val) if kind == "i" else self._realsxp(val))
+        r = self._call(name, sx)
+        out = self._list(r)
+        self.lib.mockR_free_all()
+        return out
 
     def call_kmer_seq_r(self, k):
         r = self._call("kmer_seq_r", [self._intsxp(k)])

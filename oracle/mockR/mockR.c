@@ -103,6 +103,7 @@ int R_registerRoutines(DllInfo *info, const void *c, const R_CallMethodDef *call
 typedef SEXP (*fn1)(SEXP);
 typedef SEXP (*fn2)(SEXP, SEXP);
 typedef SEXP (*fn5)(SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*fn8)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 
 SEXP mockR_call(DL_FUNC fn, int nargs, SEXP *a) {
   SEXP r = NULL;
@@ -113,6 +114,7 @@ SEXP mockR_call(DL_FUNC fn, int nargs, SEXP *a) {
       case 1: r = ((fn1)fn)(a[0]); break;
       case 2: r = ((fn2)fn)(a[0], a[1]); break;
       case 5: r = ((fn5)fn)(a[0], a[1], a[2], a[3], a[4]); break;
+      case 8: r = ((fn8)fn)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]); break;
       default: snprintf(g_err, sizeof g_err, "mockR_call: unsupported arity %d", nargs);
     }
   } else {

@@ -1,0 +1,91 @@
+"""The .Call boundary: the replacement glue (r/src/kmer_spans_glue.c, built against the mock R API)
+next to the UNMODIFIED reference glue (oracle/_ref), on identical mock SEXP inputs."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.test_oracle import planted
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GLUE = os.path.join(ROOT, "r", "_build", "kmer_spans.so")
+
+
+@pytest.fixture(scope="module")
+def glue():
+    from oracle.ksoracle import Ref
+    if not os.path.exists(GLUE):
+        import subprocess
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "r")])
+    return Ref(GLUE)
+
+
+def test_registration_matches_reference(glue, ref):
+    """same six .Call names and arities (src/kmer_spans.c:795-803), plus the one extension"""
+    want = ref.registered()
+    got = glue.registered()
+    assert got[: len(want)] == want
+    assert got[len(want):] == [("kmer_mode_regions", 8)]
+
+
+def test_argument_errors_match_reference(glue, ref):
+    """validation happens before any CUDA call, with the reference's texts"""
+    bad = [
+        ("kmer_counts", [("i", 3), ("i", 2)]),
+        ("kmer_counts", [("s", [b"ACGT"]), ("d", 2.0)]),
+        ("kmer_counts", [("s", [b"ACGT"]), ("i", 0)]),
+        ("kmer_regions_r", [("s", [b"ACGT"]), ("i", 2), ("i", [1] * 16), ("i", 1), ("d", 1.0)]),
+        ("kmer_regions_r", [("s", [b"ACGT"]), ("i", 2), ("d", [1.0] * 16), ("d", 1.0), ("d", 1.0)]),
+        ("kmer_regions_r", [("s", [b"ACGT"]), ("i", 2), ("d", [1.0] * 16), ("i", 1), ("i", 1)]),
+        ("kmer_regions_r", [("s", [b"ACGT"]), ("i", 16), ("d", [1.0] * 16), ("i", 1), ("d", 1.0)]),
+        ("kmer_regions_r", [("s", [b"ACGT"]), ("i", 2), ("d", [1.0] * 15), ("i", 1), ("d", 1.0)]),
+        ("kmer_low_comp_regions", [("s", [b"ACGT"]), ("i", 2), ("i", 1), ("d", 1.0), ("d", 1.0)]),
+        ("kmer_low_comp_regions", [("s", [b"ACGT"]), ("i", 2), ("i", 1), ("d", 1.0), ("d", 0.0)]),
+        ("kmer_low_comp_regions", [("s", [b"ACGT"]), ("i", 2), ("i", 1), ("d", 1.0), ("i", 1)]),
+        ("kmer_low_comp_regions", [("s", [b"ACGT"]), ("i", 2), ("d", 1.0), ("d", 1.0), ("d", 0.5)]),
+        ("kmer_seq_r", [("i", 0)]),
+        ("kmer_seq_r", [("i", [1, 2])]),
+    ]
+    for name, args in bad:
+        with pytest.raises(RuntimeError) as e_ref:
+            ref.call_raw(name, args)
+        with pytest.raises(RuntimeError) as e_new:
+            glue.call_raw(name, args)
+        assert str(e_new.value) == str(e_ref.value), (name, args)
+
+
+def test_kmer_seq_r_matches_reference(glue, ref):
+    for k in (1, 2, 5):
+        assert glue.call_kmer_seq_r(k) == ref.call_kmer_seq_r(k)
+
+
+def test_out_of_path_entries_are_registered_stubs(glue):
+    with pytest.raises(RuntimeError, match="not part of the CUDA hot path"):
+        glue.call_raw("tr_lr_regions_r", [("s", [b"A"]), ("i", [2, 1]), ("s", [b"AA"]), ("d", 1.0), ("d", 1.0)])
+
+
+@pytest.mark.gpu
+def test_call_results_match_reference(glue, ref):
+    rng = np.random.default_rng(2024)
+    for trial in range(6):
+        k = int(rng.choice([2, 4, 7, 9]))
+        seqs = [planted(rng, int(rng.integers(50, 20000))) for _ in range(int(rng.integers(1, 5)))]
+        if trial % 2:
+            seqs.insert(1, b"AC"[: k - 1])
+        a, b = ref.call_kmer_counts(seqs, k), glue.call_kmer_counts(seqs, k)
+        assert a["n"] == b["n"] and (a["counts"] == b["counts"]).all()
+        thr, mw, ms = float(rng.choice([0.5, 0.75])), int(rng.choice([0, 10, 40])), float(rng.choice([0, 3, 10]))
+        a = ref.call_kmer_low_comp_regions(seqs, k, mw, ms, thr)
+        b = glue.call_kmer_low_comp_regions(seqs, k, mw, ms, thr)
+        assert (a["n"] == b["n"]).all() and (a["counts"] == b["counts"]).all()
+        assert a["ranks"].tobytes() == b["ranks"].tobytes()
+        assert a["pos"].tolist() == b["pos"].tolist()
+        np.testing.assert_allclose(b["score"], a["score"], rtol=1e-9)
+        W = rng.choice([-1.0, 1.0], 4 ** k, p=[0.7, 0.3])
+        a = ref.call_kmer_regions_r(seqs, k, W, mw, ms)
+        b = glue.call_kmer_regions_r(seqs, k, W, mw, ms)
+        assert a["n"] == b["n"] and (a["counts"] == b["counts"]).all()
+        assert a["pos"].tolist() == b["pos"].tolist() and a["score"].tobytes() == b["score"].tobytes()
+    out = glue.call_raw("kmer_mode_regions", [("s", seqs), ("i", 7), ("i", 1), ("d", float("nan")), ("d", 0.0),
+                                              ("i", 10), ("d", 3.0), ("i", 1)])
+    assert len(out) == 5 and out[1].size == 4 ** 7 and out[2].size == 4 ** 7
