@@ -66,6 +66,8 @@ struct ks_seqset {
   uint32_t *d_pk = nullptr;
   uint16_t *d_brk = nullptr;
   mutable bool packed = false;
+  // capacities (a set cached in the context is re-used by the host-buffer entry points)
+  size_t cap_buf = 0, cap_chunks = 0, cap_starts = 0;
 };
 
 struct ks_ctx {
@@ -98,6 +100,9 @@ struct ks_ctx {
   std::vector<uint32_t> lut_gcount;
   std::vector<double> lut_gval;
   // staging / misc
+  cudaStream_t copy_stream = nullptr;     // H2D of the sequence / D2H of tables, overlapped with kernels
+  cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
+  ks_seqset *host_set = nullptr;          // device buffers re-used by the host-buffer entry points
   void *pinned = nullptr;
   size_t pinned_cap = 0;
   DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, dbg, gdone, pending;
@@ -230,6 +235,10 @@ void ks_ctx_destroy(ks_ctx *ctx) {
   if (ctx->t0) cudaEventDestroy(ctx->t0);
   if (ctx->t1) cudaEventDestroy(ctx->t1);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->host_set) ks_seqset_free(ctx->host_set);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+  if (ctx->ev_compute) cudaEventDestroy(ctx->ev_compute);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -299,9 +308,11 @@ int ks_kmer_seq(int k, uint64_t code, char *out) {
 
 // ------------------------------------------------------------------------------------------------
 // sequence sets
-static int seqset_common(ks_ctx *ctx, const int64_t *lens, int nseq, ks_seqset *s) {
+// (re)initialise a set for these lengths; device buffers only grow
+static int seqset_prepare(ks_ctx *ctx, const int64_t *lens, int nseq, ks_seqset *s, bool own_buffer) {
   s->ctx = ctx;
   s->nseq = nseq;
+  s->packed = false;
   s->lens.assign(lens, lens + nseq);
   s->starts.resize((size_t)nseq + 1);
   s->total = ks_layout_total(lens, nseq, s->starts.data());
@@ -310,40 +321,95 @@ static int seqset_common(ks_ctx *ctx, const int64_t *lens, int nseq, ks_seqset *
     if (lens[i] < 0 || lens[i] > 2147483646LL) return ctx->fail(KS_ERR_ARG, "sequence %d: length out of range", i);
     s->bases += lens[i];
   }
-  CK(cudaMalloc(&s->d_starts, sizeof(int64_t) * ((size_t)nseq + 1)));
-  {
-    size_t nch = (size_t)(s->total / 16) + 8;
-    CK(cudaMalloc(&s->d_pk, nch * sizeof(uint32_t)));
-    CK(cudaMalloc(&s->d_brk, nch * sizeof(uint16_t)));
-    CK(cudaMemsetAsync(s->d_pk, 0, nch * sizeof(uint32_t), ctx->stream));
-    CK(cudaMemsetAsync(s->d_brk, 0xff, nch * sizeof(uint16_t), ctx->stream));  // beyond the data: all breaks
+  if ((size_t)nseq + 1 > s->cap_starts) {
+    if (s->d_starts) cudaFree(s->d_starts);
+    s->d_starts = nullptr;
+    s->cap_starts = (size_t)nseq + 1 + (size_t)nseq / 4;
+    CK(cudaMalloc(&s->d_starts, sizeof(int64_t) * s->cap_starts));
   }
   CK(cudaMemcpyAsync(s->d_starts, s->starts.data(), sizeof(int64_t) * ((size_t)nseq + 1),
                      cudaMemcpyHostToDevice, ctx->stream));
+  size_t nch = (size_t)(s->total / 16) + 8;
+  if (nch > s->cap_chunks) {
+    if (s->d_pk) cudaFree(s->d_pk);
+    if (s->d_brk) cudaFree(s->d_brk);
+    s->d_pk = nullptr; s->d_brk = nullptr;
+    s->cap_chunks = nch + nch / 8;
+    CK(cudaMalloc(&s->d_pk, s->cap_chunks * sizeof(uint32_t)));
+    CK(cudaMalloc(&s->d_brk, s->cap_chunks * sizeof(uint16_t)));
+  }
+  // beyond the data every position is a break; the pack pass overwrites chunks [0, total/16)
+  CK(cudaMemsetAsync(s->d_brk + (nch - 8), 0xff, 8 * sizeof(uint16_t), ctx->stream));
+  CK(cudaMemsetAsync(s->d_pk + (nch - 8), 0, 8 * sizeof(uint32_t), ctx->stream));
+  if (own_buffer) {
+    size_t need = (size_t)s->total + KS_SLACK;
+    if (need > s->cap_buf) {
+      if (s->d_buf && s->owned) cudaFree(s->d_buf);
+      s->d_buf = nullptr;
+      s->cap_buf = need + need / 8;
+      if (cudaMalloc(&s->d_buf, s->cap_buf) != cudaSuccess) {
+        cudaGetLastError();
+        s->cap_buf = 0;
+        return ctx->fail(KS_ERR_NOMEM, "cudaMalloc(%lld) failed", (long long)need);
+      }
+    }
+    s->owned = true;
+  }
   return KS_OK;
 }
 
-int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, ks_seqset **out) {
-  if (!ctx) return KS_ERR_ARG;
-  if (!out || !seqs || !lens || nseq < 1)
-    return ctx->fail(KS_ERR_ARG, "seq_r must be a character vector of length at least one");
-  CK(cudaSetDevice(ctx->device));
-  ks_seqset *s = new ks_seqset();
-  int rc = seqset_common(ctx, lens, nseq, s);
-  if (rc) { ks_seqset_free(s); return rc; }
-  cudaError_t e = cudaMalloc(&s->d_buf, (size_t)s->total + KS_SLACK);
-  if (e != cudaSuccess) { ks_seqset_free(s); return ctx->fail(KS_ERR_NOMEM, "cudaMalloc(%lld) failed", (long long)s->total); }
-  s->owned = true;
-  cudaStream_t st = ctx->stream;
-  e = cudaMemsetAsync(s->d_buf, 0, (size_t)s->total + KS_SLACK, st);
-  if (e != cudaSuccess) { ks_seqset_free(s); CK(e); }
+static int ensure_copy_stream(ks_ctx *ctx) {
+  if (ctx->copy_stream) return KS_OK;
+  CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
+  return KS_OK;
+}
+
+// H2D of the sequences into the layout of ks_layout.h on the copy stream.  With count_k > 0 the
+// pack+count kernel is launched on the compute stream slab by slab behind the copies (it is far
+// faster than PCIe, so counting hides completely behind the upload).
+static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const int64_t *lens, int nseq,
+                       int count_k, int32_t *d_counts) {
+  int rc = ensure_copy_stream(ctx);
+  if (rc) return rc;
+  cudaStream_t cs = ctx->copy_stream, st = ctx->stream;
+  const size_t nk = count_k ? ((size_t)1 << (2 * count_k)) : 0;
+  CK(cudaEventRecord(ctx->ev_compute, st));       // the buffers may still be read by earlier work
+  CK(cudaStreamWaitEvent(cs, ctx->ev_compute, 0));
+  CK(cudaMemsetAsync(s->d_buf, 0, (size_t)s->total + KS_SLACK, cs));
+  if (count_k) {
+    CK(ctx->nwords.ensure(sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d_counts, 0, nk * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
+  }
+  const int64_t nchunks = (s->total - 16) / 16;
+  int64_t done = 0;  // chunks [0, done) of the count grid are launched
+  const int64_t SLAB = (24ll << 20) / 16;
+  auto progress = [&](int64_t covered, bool final) -> cudaError_t {
+    if (!count_k) return cudaSuccess;
+    // chunk ci reads bytes [16 ci, 16 ci + 33): available once covered >= 16 ci + 33
+    int64_t avail = final ? nchunks : (covered - 33) / 16 + 1;
+    if (avail > nchunks) avail = nchunks;
+    if (avail <= done || (!final && avail - done < SLAB)) return cudaSuccess;
+    cudaError_t e2 = cudaEventRecord(ctx->ev_copy, cs);
+    if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(st, ctx->ev_copy, 0);
+    if (e2 != cudaSuccess) return e2;
+    cudaEvent_t pe = ctx->prof_begin();
+    pack_count_kernel<true><<<grid_for((size_t)(avail - done), 256, 148u * 8u), 256, 0, st>>>(
+        s->d_buf, done, avail - done, count_k, (uint32_t)(nk - 1), s->d_pk, s->d_brk, d_counts,
+        ctx->nwords.as<unsigned long long>());
+    ctx->prof_end(KS_PROF_COUNT, pe);
+    ctx->launches += 1;
+    done = avail;
+    return cudaGetLastError();
+  };
   // large sequences go straight from the caller's memory; small ones are packed into pinned
   // staging windows (two halves, alternating) so that 100k contigs do not cost 100k copies
   const int64_t DIRECT = 4ll << 20;
   const size_t HALF = 16u << 20;
   if (!ctx->pinned) {
-    e = cudaMallocHost(&ctx->pinned, 2 * HALF);
-    if (e != cudaSuccess) { ks_seqset_free(s); CK(e); }
+    CK(cudaMallocHost(&ctx->pinned, 2 * HALF));
     ctx->pinned_cap = 2 * HALF;
   }
   cudaEvent_t ev[2];
@@ -356,9 +422,11 @@ int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, 
   char *win = (char *)ctx->pinned;
   auto flush = [&]() -> cudaError_t {
     if (fill == 0) return cudaSuccess;
-    cudaError_t ee = cudaMemcpyAsync(s->d_buf + win_start, win, fill, cudaMemcpyHostToDevice, st);
+    cudaError_t ee = cudaMemcpyAsync(s->d_buf + win_start, win, fill, cudaMemcpyHostToDevice, cs);
     if (ee != cudaSuccess) return ee;
-    cudaEventRecord(ev[half], st);
+    ee = progress(win_start + (int64_t)fill, false);
+    if (ee != cudaSuccess) return ee;
+    cudaEventRecord(ev[half], cs);
     ev_used[half] = true;
     half ^= 1;
     win = (char *)ctx->pinned + (size_t)half * HALF;
@@ -367,14 +435,19 @@ int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, 
     win_start = -1;
     return ee;
   };
-  e = cudaSuccess;
+  cudaError_t e = cudaSuccess;
   for (int i = 0; i < nseq && e == cudaSuccess; ++i) {
     int64_t ln = lens[i];
     if (ln == 0) continue;
     if (ln >= DIRECT) {
       e = flush();
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(s->d_buf + s->starts[i], seqs[i], (size_t)ln, cudaMemcpyHostToDevice, st);
+      // in pieces, so that counting can start while the rest is still on the bus
+      const int64_t PIECE = 32ll << 20;
+      for (int64_t off = 0; off < ln && e == cudaSuccess; off += PIECE) {
+        int64_t n = ln - off < PIECE ? ln - off : PIECE;
+        e = cudaMemcpyAsync(s->d_buf + s->starts[i] + off, seqs[i] + off, (size_t)n, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = progress(s->starts[i] + off + n, false);
+      }
       continue;
     }
     // contiguous with the window?  (separator bytes between sequences are copied as zeros)
@@ -386,11 +459,41 @@ int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, 
     fill += (size_t)ln;
   }
   if (e == cudaSuccess) e = flush();
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = progress(s->total, true);
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copy, cs);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->ev_copy, 0);  // later kernels see the whole buffer
+  if (e == cudaSuccess && ev_used[0]) e = cudaEventSynchronize(ev[0]);  // staging halves are re-used next call
+  if (e == cudaSuccess && ev_used[1]) e = cudaEventSynchronize(ev[1]);
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
-  if (e != cudaSuccess) { ks_seqset_free(s); CK(e); }
+  CK(e);
+  if (count_k) s->packed = true;
+  return KS_OK;
+}
+
+int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, ks_seqset **out) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!out || !seqs || !lens || nseq < 1)
+    return ctx->fail(KS_ERR_ARG, "seq_r must be a character vector of length at least one");
+  CK(cudaSetDevice(ctx->device));
+  ks_seqset *s = new ks_seqset();
+  int rc = seqset_prepare(ctx, lens, nseq, s, true);
+  if (!rc) rc = upload_impl(ctx, s, seqs, lens, nseq, 0, nullptr);
+  if (!rc) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = ctx->fail(KS_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
+  }
+  if (rc) { ks_seqset_free(s); return rc; }
   *out = s;
+  return KS_OK;
+}
+
+// the cached set of the host-buffer entry points
+static int host_set_acquire(ks_ctx *ctx, const int64_t *lens, int nseq, ks_seqset **out) {
+  if (!ctx->host_set) ctx->host_set = new ks_seqset();
+  int rc = seqset_prepare(ctx, lens, nseq, ctx->host_set, true);
+  if (rc) return rc;
+  *out = ctx->host_set;
   return KS_OK;
 }
 
@@ -400,7 +503,7 @@ int ks_seqset_wrap(ks_ctx *ctx, const void *d_buf, int64_t total_bytes, const in
   if (!out || !d_buf || !lens || nseq < 1) return ctx->fail(KS_ERR_ARG, "ks_seqset_wrap: bad arguments");
   CK(cudaSetDevice(ctx->device));
   ks_seqset *s = new ks_seqset();
-  int rc = seqset_common(ctx, lens, nseq, s);
+  int rc = seqset_prepare(ctx, lens, nseq, s, false);
   if (rc) { ks_seqset_free(s); return rc; }
   if (total_bytes < s->total + KS_SLACK) {
     ks_seqset_free(s);
@@ -442,7 +545,7 @@ int ks_dev_count(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, doub
   int64_t nchunks = (s->total - 16) / 16;
   cudaEvent_t pe = ctx->prof_begin();
   pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
-      s->d_buf, nchunks, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, d_counts, ctx->nwords.as<unsigned long long>());
+      s->d_buf, 0, nchunks, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, d_counts, ctx->nwords.as<unsigned long long>());
   ctx->prof_end(KS_PROF_COUNT, pe);
   s->packed = true;
   LAUNCHED(1);
@@ -666,7 +769,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     int64_t nch = (s->total - 16) / 16;
     cudaEvent_t pe = ctx->prof_begin();
     pack_count_kernel<false><<<grid_for((size_t)nch, 256, 148u * 8u), 256, 0, st>>>(
-        s->d_buf, nch, k, (uint32_t)(nk - 1), s->d_pk, s->d_brk, nullptr, nullptr);
+        s->d_buf, 0, nch, k, (uint32_t)(nk - 1), s->d_pk, s->d_brk, nullptr, nullptr);
     ctx->prof_end(KS_PROF_COUNT, pe);
     LAUNCHED(1);
     CK(cudaGetLastError());
@@ -982,6 +1085,36 @@ static int check_seqs(ks_ctx *ctx, const char *const *seqs, const int64_t *lens,
   return KS_OK;
 }
 
+// upload (copy stream) with the pack+count pass running behind it (compute stream); returns the
+// words counted.  The set is the context's cached one.
+static int upload_and_count(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,
+                            int32_t *d_counts, double *n_words, ks_seqset **set) {
+  ks_seqset *ss = nullptr;
+  int rc = host_set_acquire(ctx, lens, nseq, &ss);
+  if (rc) return rc;
+  rc = upload_impl(ctx, ss, seqs, lens, nseq, k, d_counts);
+  if (rc) return rc;
+  unsigned long long nw = 0;
+  CK(cudaMemcpyAsync(&nw, ctx->nwords.p, sizeof nw, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *n_words = (double)nw;
+  *set = ss;
+  return KS_OK;
+}
+
+// D2H of a table on the copy stream, behind everything the compute stream has done so far; it
+// overlaps with the kernels that follow.  Completed by finish_copies().
+static int copy_out_async(ks_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes) {
+  CK(cudaEventRecord(ctx->ev_compute, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute, 0));
+  CK(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  return KS_OK;
+}
+static int finish_copies(ks_ctx *ctx) {
+  if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+  return KS_OK;
+}
+
 int ks_kmer_counts(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,
                    int32_t *counts_out, double *n_words) {
   if (!ctx) return KS_ERR_ARG;
@@ -989,19 +1122,15 @@ int ks_kmer_counts(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, in
   if (rc) return rc;
   if (k < 1 || k > 15) return ctx->fail(KS_ERR_ARG, "k must be a positive integer less than 1+MAX_K");
   if (!counts_out || !n_words) return ctx->fail(KS_ERR_ARG, "null output");
+  CK(cudaSetDevice(ctx->device));
   size_t n = (size_t)1 << (2 * k);
+  CK(ctx->tmp_counts.ensure(n * 4));
   ks_seqset *ss = nullptr;
-  rc = ks_seqset_upload(ctx, seqs, lens, nseq, &ss);
+  rc = upload_and_count(ctx, seqs, lens, nseq, k, ctx->tmp_counts.as<int32_t>(), n_words, &ss);
   if (rc) return rc;
-  cudaError_t e = ctx->tmp_counts.ensure(n * 4);
-  if (e != cudaSuccess) { ks_seqset_free(ss); CK(e); }
-  rc = ks_dev_count(ctx, ss, k, ctx->tmp_counts.as<int32_t>(), n_words);
-  if (!rc) {
-    e = cudaMemcpy(counts_out, ctx->tmp_counts.p, n * 4, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) rc = ctx->fail(KS_ERR_CUDA, "D2H counts: %s", cudaGetErrorString(e));
-  }
-  ks_seqset_free(ss);
-  return rc;
+  CK(cudaMemcpyAsync(counts_out, ctx->tmp_counts.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return KS_OK;
 }
 
 int ks_kmer_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k, const double *W,
@@ -1012,29 +1141,31 @@ int ks_kmer_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, i
   if (k >= 16 || k < 1)
     return ctx->fail(KS_ERR_ARG, "kmer sizes larger than or equal to %d not currently supported", 16);
   if (!W || !out) return ctx->fail(KS_ERR_ARG, "null argument");
+  CK(cudaSetDevice(ctx->device));
   size_t n = (size_t)1 << (2 * k);
   if (nuc) {
     *nuc = 0;
     for (int i = 0; i < nseq; ++i)
       if (lens[i] >= k) *nuc += (double)lens[i];  // :533-535
   }
-  ks_seqset *ss = nullptr;
-  rc = ks_seqset_upload(ctx, seqs, lens, nseq, &ss);
-  if (rc) return rc;
   cudaStream_t st = ctx->stream;
-  cudaError_t e = ctx->tmp_scores.ensure(n * 8);
-  if (e == cudaSuccess) e = ctx->tmp_inscan.ensure(n * 4);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->tmp_scores.p, W, n * 8, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(ctx->tmp_inscan.p, 0, n * 4, st);
-  if (e != cudaSuccess) { ks_seqset_free(ss); CK(e); }
+  CK(ctx->tmp_scores.ensure(n * 8));
+  CK(ctx->tmp_inscan.ensure(n * 4));
+  CK(cudaMemcpyAsync(ctx->tmp_scores.p, W, n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->tmp_inscan.p, 0, n * 4, st));
+  ks_seqset *ss = nullptr;
+  rc = host_set_acquire(ctx, lens, nseq, &ss);
+  if (rc) return rc;
+  rc = upload_impl(ctx, ss, seqs, lens, nseq, 0, nullptr);
+  if (rc) return rc;
   rc = ks_dev_scan(ctx, ss, k, ctx->tmp_scores.as<double>(), 0.0, min_width, min_score,
                    inscan_counts_out ? ctx->tmp_inscan.as<int32_t>() : nullptr, out, nullptr);
-  if (!rc && inscan_counts_out) {
-    e = cudaMemcpy(inscan_counts_out, ctx->tmp_inscan.p, n * 4, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) rc = ctx->fail(KS_ERR_CUDA, "D2H counts: %s", cudaGetErrorString(e));
+  if (rc) return rc;
+  if (inscan_counts_out) {
+    CK(cudaMemcpyAsync(inscan_counts_out, ctx->tmp_inscan.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
   }
-  ks_seqset_free(ss);
-  return rc;
+  return KS_OK;
 }
 
 int ks_kmer_mode_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k, int mode,
@@ -1046,27 +1177,28 @@ int ks_kmer_mode_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *le
   rc = check_k(ctx, k);
   if (rc) return rc;
   if (!out) return ctx->fail(KS_ERR_ARG, "null argument");
+  if (mode < KS_MODE_RANK || mode > KS_MODE_RANK_REL) return ctx->fail(KS_ERR_ARG, "unknown score mode %d", mode);
+  CK(cudaSetDevice(ctx->device));
   size_t n = (size_t)1 << (2 * k);
+  CK(ctx->tmp_counts.ensure(n * 4));
+  CK(ctx->tmp_scores.ensure(n * 8));
+  int32_t *d_counts = ctx->tmp_counts.as<int32_t>();
+  double *d_scores = ctx->tmp_scores.as<double>();
   ks_seqset *ss = nullptr;
-  rc = ks_seqset_upload(ctx, seqs, lens, nseq, &ss);
-  if (rc) return rc;
-  cudaError_t e = ctx->tmp_counts.ensure(n * 4);
-  if (e == cudaSuccess) e = ctx->tmp_scores.ensure(n * 8);
-  if (e != cudaSuccess) { ks_seqset_free(ss); CK(e); }
   double nw = 0;
-  rc = ks_dev_pipeline(ctx, ss, k, mode, param, thr, min_width, min_score, ctx->tmp_counts.as<int32_t>(),
-                       ctx->tmp_scores.as<double>(), &nw, out, nullptr);
+  rc = upload_and_count(ctx, seqs, lens, nseq, k, d_counts, &nw, &ss);   // counting hides behind the H2D
+  if (rc) return rc;
   if (n_words) *n_words = nw;
-  if (!rc && counts_out) {
-    e = cudaMemcpy(counts_out, ctx->tmp_counts.p, n * 4, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) rc = ctx->fail(KS_ERR_CUDA, "D2H counts: %s", cudaGetErrorString(e));
+  if (counts_out) { rc = copy_out_async(ctx, counts_out, d_counts, n * 4); if (rc) return rc; }  // overlaps scores + scan
+  const bool count_fn = (mode == KS_MODE_LOG2 || mode == KS_MODE_SIGN);
+  rc = ks_dev_scores(ctx, k, d_counts, nw, mode, param, (count_fn && !scores_out) ? nullptr : d_scores);
+  if (!rc && scores_out) rc = copy_out_async(ctx, scores_out, d_scores, n * 8);                  // overlaps the scan
+  if (!rc) {
+    if (count_fn) rc = ks_dev_scan_counts(ctx, ss, k, d_counts, thr, min_width, min_score, out, nullptr);
+    else rc = ks_dev_scan(ctx, ss, k, d_scores, thr, min_width, min_score, nullptr, out, nullptr);
   }
-  if (!rc && scores_out) {
-    e = cudaMemcpy(scores_out, ctx->tmp_scores.p, n * 8, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) rc = ctx->fail(KS_ERR_CUDA, "D2H scores: %s", cudaGetErrorString(e));
-  }
-  ks_seqset_free(ss);
-  return rc;
+  int rc2 = finish_copies(ctx);
+  return rc ? rc : rc2;
 }
 
 int ks_kmer_low_comp_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,

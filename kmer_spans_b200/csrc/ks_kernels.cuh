@@ -96,14 +96,15 @@ __device__ __forceinline__ Ex shfl_ex(const Ex &e, int src) {
 // (4 B per 16 bases) and the break mask (2 B per 16 bases) that every scan pass reads instead of the
 // ASCII, and (kCount) reduces the k-mer ending at every position into the int32[4^k] table.
 template <bool kCount>
-__global__ void __launch_bounds__(256) pack_count_kernel(const uint8_t *__restrict__ buf, int64_t nchunks,
-                                                         int k, uint32_t kmask, uint32_t *__restrict__ pk_out,
+__global__ void __launch_bounds__(256) pack_count_kernel(const uint8_t *__restrict__ buf, int64_t first,
+                                                         int64_t nchunks, int k, uint32_t kmask,
+                                                         uint32_t *__restrict__ pk_out,
                                                          uint16_t *__restrict__ brk_out,
                                                          int32_t *__restrict__ counts,
                                                          unsigned long long *__restrict__ nwords) {
   unsigned long long local = 0;
   const uint64_t keep = l2_policy_evict_last();
-  for (int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ci < nchunks;
+  for (int64_t ci = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ci < first + nchunks;
        ci += (int64_t)gridDim.x * blockDim.x) {
     const uint8_t *p = buf + 16 * ci;  // chunk ci+1 of the buffer starts at p + 16
     const uint4 *v = reinterpret_cast<const uint4 *>(p);
