@@ -105,7 +105,7 @@ struct ks_ctx {
   ks_seqset *host_set = nullptr;          // device buffers re-used by the host-buffer entry points
   void *pinned = nullptr;
   size_t pinned_cap = 0;
-  DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, dbg, gdone, pending;
+  DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, dbg, gdone, pending, foc_hist, foc_big;
 
   // timing / profiling
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -228,7 +228,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->out_score, &ctx->sc_keys_a, &ctx->sc_keys_b, &ctx->sc_vals_a, &ctx->sc_vals_b,
                  &ctx->sc_small, &ctx->sc_gcount, &ctx->sc_gstart, &ctx->sc_segfirst, &ctx->sc_segj0,
                  &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->tmp_counts, &ctx->tmp_scores,
-                 &ctx->tmp_inscan, &ctx->nwords, &ctx->dbg, &ctx->gdone, &ctx->pending, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
+                 &ctx->tmp_inscan, &ctx->nwords, &ctx->dbg, &ctx->gdone, &ctx->pending, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -575,6 +575,79 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
     ks_ctx *c; cudaEvent_t a;
     ~ProfScope() { c->prof_end(KS_PROF_SCORES, a); }
   } prof_scope{ctx, ctx->prof_begin()};
+  if (!rank_mode) {
+    // Count-function modes need no per-k-mer order: frequency-of-counts histogram + prefix sum.
+    const uint32_t DENSE = 1u << 16;
+    CK(ctx->sc_small.ensure(64));
+    CK(ctx->foc_hist.ensure((size_t)DENSE * 4));
+    uint32_t big_cap = 1u << 16;
+    std::vector<uint32_t> hist(DENSE), big;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      CK(ctx->foc_big.ensure((size_t)big_cap * 4));
+      CK(cudaMemsetAsync(ctx->sc_small.p, 0, 64, st));
+      CK(cudaMemsetAsync(ctx->foc_hist.p, 0, (size_t)DENSE * 4, st));
+      foc_hist_kernel<<<grid_for(n, 256, 148u * 4u), 256, 0, st>>>(
+          reinterpret_cast<const uint32_t *>(d_counts), n, ctx->foc_hist.as<uint32_t>(), DENSE,
+          ctx->foc_big.as<uint32_t>(), ctx->sc_small.as<uint32_t>(), big_cap);
+      LAUNCHED(1);
+      CK(cudaGetLastError());
+      uint32_t nbig = 0;
+      CK(cudaMemcpyAsync(&nbig, ctx->sc_small.p, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(hist.data(), ctx->foc_hist.p, (size_t)DENSE * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (nbig > big_cap) { big_cap = nbig; continue; }
+      big.resize(nbig);
+      if (nbig) CK(cudaMemcpy(big.data(), ctx->foc_big.p, (size_t)nbig * 4, cudaMemcpyDeviceToHost));
+      break;
+    }
+    std::sort(big.begin(), big.end());
+    // distinct counts ascending with multiplicities
+    std::vector<uint32_t> gcount;
+    std::vector<uint64_t> gmult;
+    for (uint32_t c = 0; c < DENSE; ++c)
+      if (hist[c]) { gcount.push_back(c); gmult.push_back(hist[c]); }
+    for (size_t i = 0; i < big.size();) {
+      size_t j = i;
+      while (j < big.size() && big[j] == big[i]) ++j;
+      gcount.push_back(big[i]);
+      gmult.push_back(j - i);
+      i = j;
+    }
+    const size_t ng = gcount.size();
+    auto count_at = [&](uint64_t pos) -> double {  // count at position pos of the ascending order
+      uint64_t acc = 0;
+      for (size_t g = 0; g < ng; ++g) { acc += gmult[g]; if (pos < acc) return (double)(int32_t)gcount[g]; }
+      return ng ? (double)(int32_t)gcount[ng - 1] : 0.0;
+    };
+    double f_lo = count_at(n / 2 - 1) / total, f_hi = count_at(n / 2) / total;
+    double f_med = (f_lo + f_hi) / 2.0;
+    std::vector<double> lut(ng);
+    for (size_t g = 0; g < ng; ++g) {
+      double f = (double)(int32_t)gcount[g] / total;
+      if (mode == KS_MODE_LOG2) lut[g] = log2(f / f_med);
+      else {
+        double f_t = isfinite(param) ? param : f_med;
+        lut[g] = f >= f_t ? 1.0 : -1.0;
+      }
+    }
+    ctx->lut_gcount = gcount;
+    ctx->lut_gval = lut;
+    ctx->lut_valid = true;
+    ctx->lut_k = k;
+    if (d_scores) {  // the per-k-mer table itself (an output; the scan gathers counts + LUT instead)
+      CK(ctx->sc_gcount.ensure((ng + 1) * 4));
+      CK(ctx->sc_lut.ensure(ng * 8 + 8));
+      CK(cudaMemcpyAsync(ctx->sc_gcount.p, gcount.data(), ng * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->sc_lut.p, lut.data(), ng * 8, cudaMemcpyHostToDevice, st));
+      lut_apply_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_counts), n,
+                                                             ctx->sc_gcount.as<uint32_t>(), (uint32_t)ng,
+                                                             ctx->sc_lut.as<double>(), d_scores);
+      LAUNCHED(1);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(st));
+    }
+    return KS_OK;
+  }
   if (rank_mode && total == 0) {
     // 0/0 addends: every rank but the first in sort order (k-mer 0) is NaN (:200)
     fill_nan_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(d_scores, n);

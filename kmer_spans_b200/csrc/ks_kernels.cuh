@@ -812,6 +812,41 @@ __global__ void __launch_bounds__(256) rank_eval_kernel(const uint32_t *__restri
   ranks[vals[p]] = fma((double)(j - __ldg(&seg_j0[a])), __ldg(&seg_inc[a]), __ldg(&seg_x0[a]));
 }
 
+// frequency-of-counts histogram h[c] (the "histogram plus prefix sum" of the north star, used by the
+// count-function modes, which need no per-k-mer order): block-private shared histogram for c < 4096
+// with warp-aggregated updates, global atomics for 4096 <= c < dense, atomic append for c >= dense.
+constexpr uint32_t FOC_SMEM_BINS = 4096;
+__global__ void __launch_bounds__(256) foc_hist_kernel(const uint32_t *__restrict__ counts, size_t n,
+                                                       uint32_t *__restrict__ hist, uint32_t dense,
+                                                       uint32_t *__restrict__ big_vals, uint32_t *big_n,
+                                                       uint32_t big_cap) {
+  __shared__ uint32_t sh[FOC_SMEM_BINS];
+  for (int i = threadIdx.x; i < (int)FOC_SMEM_BINS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const uint32_t lt = (1u << (threadIdx.x & 31)) - 1u;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t nround = (n + stride - 1) / stride;  // uniform trip count: __match_any_sync needs the whole warp
+  for (size_t it = 0; it < nround; ++it) {
+    size_t i = it * stride + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = i < n;
+    uint32_t c = ok ? counts[i] : 0xffffffffu;
+    uint32_t peers = __match_any_sync(0xffffffffu, c);
+    if (ok && (peers & lt) == 0u) {  // lowest lane of each group of equal counts
+      uint32_t m = __popc(peers);
+      if (c < FOC_SMEM_BINS) atomicAdd(&sh[c], m);
+      else if (c < dense) atomicAdd(&hist[c], m);
+      else {
+        uint32_t slot = atomicAdd(big_n, m);
+        for (uint32_t q = 0; q < m; ++q)
+          if (slot + q < big_cap) big_vals[slot + q] = c;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (int)FOC_SMEM_BINS; i += blockDim.x)
+    if (sh[i] && (uint32_t)i < dense) atomicAdd(&hist[i], sh[i]);
+}
+
 // W[x] = lut[group of counts[x]]  (log2 / +-1 / any pure function of the count)
 __global__ void __launch_bounds__(256) lut_apply_kernel(const uint32_t *__restrict__ counts, size_t n,
                                                         const uint32_t *__restrict__ gcount, uint32_t ngroups,
