@@ -539,16 +539,25 @@ __device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Sta
   st.p0[tid] = p0;
   __syncthreads();
   KS_TICK(3)
-  Xf wpre = xf_identity();
-  for (int i = 0; i < warp; ++i) wpre = xf_compose(wpre, s_wxf[i]);
-  excl = xf_compose(wpre, excl);
+  if (warp == 0) {  // exclusive scan of the warp totals by one warp: s_wxf[w] <- totals of warps < w
+    Xf ti = lane < TILE_WARPS ? s_wxf[lane] : xf_identity();
+#pragma unroll
+    for (int o = 1; o < TILE_WARPS; o <<= 1) {
+      Xf y = shfl_xf(ti, (lane - o) & 31);
+      if (lane >= o) ti = xf_compose(y, ti);
+    }
+    Xf te = shfl_xf(ti, (lane - 1) & 31);
+    if (lane == 0) te = xf_identity();
+    if (lane < TILE_WARPS) s_wxf[lane] = te;
+    if (lane == TILE_WARPS - 1) s_wxf[TILE_WARPS] = ti;  // aggregate of the tile
+  }
+  __syncthreads();
+  excl = xf_compose(s_wxf[warp], excl);
   st.ea[tid] = excl.a;
   st.eb[tid] = excl.b;
   st.flags[tid] = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u);
   if (tid == 0) {
-    Xf agg = xf_identity();
-#pragma unroll
-    for (int i = 0; i < TILE_WARPS; ++i) agg = xf_compose(agg, s_wxf[i]);
+    Xf agg = s_wxf[TILE_WARPS];
     st.agg = agg;
     publish_xf(A.ts.xfA, A.ts.xfB, tile, A.epoch, agg);
     // the tile that completes a group publishes the group aggregate right away
@@ -621,15 +630,20 @@ __device__ __forceinline__ void scan_finish(const LevelArgs &A, int64_t tile, co
   if (lane == 0) eexcl = ex_identity();
   if (lane == 31) s_wex[warp] = einc;
   __syncthreads();
-  Ex epre = ex_identity();
-  for (int i = 0; i < warp; ++i) epre = ex_combine(epre, s_wex[i]);
-  eexcl = ex_combine(epre, eexcl);
-  if (tid == 0) {
-    Ex eagg = ex_identity();
+  if (warp == 0) {
+    Ex ti = lane < TILE_WARPS ? s_wex[lane] : ex_identity();
 #pragma unroll
-    for (int i = 0; i < TILE_WARPS; ++i) eagg = ex_combine(eagg, s_wex[i]);
-    publish_ex(A.ts, tile, A.epoch, eagg);
+    for (int o = 1; o < TILE_WARPS; o <<= 1) {
+      Ex y = shfl_ex(ti, (lane - o) & 31);
+      if (lane >= o) ti = ex_combine(y, ti);
+    }
+    Ex te = shfl_ex(ti, (lane - 1) & 31);
+    if (lane == 0) te = ex_identity();
+    if (lane < TILE_WARPS) s_wex[lane] = te;
+    if (lane == TILE_WARPS - 1) publish_ex(A.ts, tile, A.epoch, ti);
   }
+  __syncthreads();
+  eexcl = ex_combine(s_wex[warp], eexcl);
   KS_TICK(8)
   if (!head && S_in > 0 && first_zero >= 0) {
     if (eexcl.reset) {
@@ -678,9 +692,9 @@ template <bool kLut>
 __global__ void __launch_bounds__(TILE_THREADS, KS_SCAN_MINBLOCKS) scan_level_kernel(const LevelArgs A) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   Stash *stash = reinterpret_cast<Stash *>(dyn_smem);  // two buffers
-  __shared__ int64_t s_tile;
-  __shared__ Xf s_wxf[TILE_WARPS];
-  __shared__ Ex s_wex[TILE_WARPS];
+  __shared__ int64_t s_tile[2];
+  __shared__ Xf s_wxf[TILE_WARPS + 1];
+  __shared__ Ex s_wex[TILE_WARPS + 1];
   __shared__ fx_t s_S;
   const int tid = threadIdx.x;
 
@@ -688,12 +702,13 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_SCAN_MINBLOCKS) scan_level_ke
   prm.min_width = A.prm->min_width;
   prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
 
+  int slot = 0;
   auto next_tile = [&]() -> int64_t {
     KS_T0
-    if (tid == 0) s_tile = (int64_t)(unsigned int)(atomicAdd(A.tile_counter, 1u) - A.tile_base);
+    if (tid == 0) s_tile[slot] = (int64_t)(unsigned int)(atomicAdd(A.tile_counter, 1u) - A.tile_base);
     __syncthreads();
-    int64_t t = s_tile;
-    __syncthreads();
+    int64_t t = s_tile[slot];
+    slot ^= 1;  // a slot is rewritten only two fetches later, with whole phases (and barriers) in between
     KS_TICK(10)
     if (tid == 0 && A.dbg) atomicAdd(A.dbg + 15, 1ull);
     return t;
