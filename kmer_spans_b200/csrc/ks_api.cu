@@ -105,7 +105,8 @@ struct ks_ctx {
   ks_seqset *host_set = nullptr;          // device buffers re-used by the host-buffer entry points
   void *pinned = nullptr;
   size_t pinned_cap = 0;
-  DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, dbg, gdone, pending, foc_hist, foc_big;
+  DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, dbg, pending, foc_hist, foc_big;
+  DBuf st_c, st_s, st_ea, st_eb, st_flags, st_p0, tile_xf, tile_S, tile_ex;
 
   // timing / profiling
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -228,7 +229,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->out_score, &ctx->sc_keys_a, &ctx->sc_keys_b, &ctx->sc_vals_a, &ctx->sc_vals_b,
                  &ctx->sc_small, &ctx->sc_gcount, &ctx->sc_gstart, &ctx->sc_segfirst, &ctx->sc_segj0,
                  &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->tmp_counts, &ctx->tmp_scores,
-                 &ctx->tmp_inscan, &ctx->nwords, &ctx->dbg, &ctx->gdone, &ctx->pending, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
+                 &ctx->tmp_inscan, &ctx->nwords, &ctx->dbg, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_S, &ctx->tile_ex, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -790,21 +791,20 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
 
 // ------------------------------------------------------------------------------------------------
 // stage: scan + spans
-static int ensure_tiles(ks_ctx *ctx, size_t tiles) {
-  if (tiles <= ctx->tiles_cap) return KS_OK;
-  size_t t = tiles + tiles / 4 + 64;
-  cudaStream_t st = ctx->stream;
-  DBuf *d[6] = {&ctx->xf_agg, &ctx->xf_inc, &ctx->ex_agg, &ctx->ex_inc,  // xfA, xfB, exA, exB
-                &ctx->xf_status, &ctx->ex_status};                          // gA, gB (one per 32 tiles, oversized)
-  for (DBuf *b : d) {
-    CK(b->ensure(t * 16));
-    CK(cudaMemsetAsync(b->p, 0, b->cap, st));
-  }
-  CK(ctx->gdone.ensure((t / 32 + 4) * 4));
-  CK(ctx->pending.ensure(t * sizeof(ExPending)));
-  CK(cudaMemsetAsync(ctx->pending.p, 0, ctx->pending.cap, st));
-  ctx->epoch = 0;  // fresh, zeroed tags
-  ctx->tiles_cap = t;
+// per-level scratch: stash (indexed by work chunk) and per-tile arrays
+static int ensure_tiles(ks_ctx *ctx, size_t tiles, bool lut_mode, bool need_p0) {
+  const size_t Q = tiles * TILE_THREADS;
+  if (lut_mode) CK(ctx->st_c.ensure(Q * 16 * 4)); else CK(ctx->st_s.ensure(Q * 16 * 8));
+  CK(ctx->st_ea.ensure(Q * 16));
+  CK(ctx->st_eb.ensure(Q * 16));
+  CK(ctx->st_flags.ensure(Q * 4));
+  if (need_p0) CK(ctx->st_p0.ensure(Q * 8));
+  CK(ctx->tile_xf.ensure(tiles * sizeof(XfRec)));
+  CK(ctx->tile_S.ensure(tiles * 16));
+  CK(ctx->tile_ex.ensure(tiles * sizeof(ExRec)));
+  size_t old = ctx->pending.cap;
+  CK(ctx->pending.ensure(tiles * sizeof(ExPending)));
+  if (ctx->pending.cap != old) CK(cudaMemsetAsync(ctx->pending.p, 0, ctx->pending.cap, ctx->stream));
   return KS_OK;
 }
 
@@ -836,7 +836,6 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
   cudaStream_t st = ctx->stream;
   const size_t nk = (size_t)1 << (2 * k);
   DevScanParams *d_prm = ctx->prm.as<DevScanParams>();
-  CK(ctx->tile_counter.ensure(64));
   CK(ctx->rec_count.ensure(64));
   if (!s->packed) {  // no counting pass ran on this set (user-supplied weights): pack only
     int64_t nch = (s->total - 16) / 16;
@@ -848,27 +847,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     CK(cudaGetLastError());
     s->packed = true;
   }
-  // persistent grid: every CTA of the launch must be resident (tiles wait on earlier tiles)
-  const size_t dyn_smem = 2 * sizeof(Stash);
-  if (!ctx->scan_cfg_done) {
-    CK(cudaFuncSetAttribute(scan_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    CK(cudaFuncSetAttribute(scan_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    int occ_t = 0, occ_f = 0, sms = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, scan_level_kernel<true>, TILE_THREADS, dyn_smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, scan_level_kernel<false>, TILE_THREADS, dyn_smem));
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-    int occ = occ_t < occ_f ? occ_t : occ_f;
-    if (occ < 1 || sms < 1) return ctx->fail(KS_ERR_CUDA, "scan kernel does not fit on this device");
-    ctx->scan_max_ctas = (size_t)occ * (size_t)sms;
-    ctx->scan_cfg_done = true;
-  }
   unsigned long long *d_rec_count = ctx->rec_count.as<unsigned long long>();
   CK(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), st));
-  if (!ctx->counter_init) {
-    CK(cudaMemsetAsync(ctx->tile_counter.p, 0, 64, st));
-    ctx->counter_init = true;
-    ctx->tile_base = 0;
-  }
 
   const int64_t dense_chunks = (s->total - 16) / 16;
   if (s->total >= (1ll << 32))
@@ -885,11 +865,10 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     size_t tiles = (size_t)((total_chunks + TILE_THREADS - 1) / TILE_THREADS);
     if (tiles == 0) break;
     if (tiles > 0xfffffff0ull) return ctx->fail(KS_ERR_ARG, "input too large for one scan launch");
-    rc = ensure_tiles(ctx, tiles);
+    rc = ensure_tiles(ctx, tiles, tab.use_lut, nseg != 0);
     if (rc) return rc;
     LevelArgs A;
     memset(&A, 0, sizeof A);
-    A.pending = ctx->pending.as<ExPending>();
     A.pk = s->d_pk;
     A.brk = s->d_brk;
     A.ntiles = (int64_t)tiles;
@@ -910,30 +889,21 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.dense_start = 16;
     A.total_chunks = total_chunks;
     A.inscan = count_inscan ? d_inscan : nullptr;
-    A.ts.xfA = ctx->xf_agg.as<uint4>();
-    A.ts.xfB = ctx->xf_inc.as<uint4>();
-    A.ts.exA = ctx->ex_agg.as<uint4>();
-    A.ts.exB = ctx->ex_inc.as<uint4>();
-    A.ts.gA = ctx->xf_status.as<uint4>();
-    A.ts.gB = ctx->ex_status.as<uint4>();
-    A.ts.gdone = ctx->gdone.as<uint32_t>();
-    CK(cudaMemsetAsync(ctx->gdone.p, 0, (tiles / 32 + 2) * 4, st));
-    ctx->epoch += 1;
-    if (ctx->epoch >= (1u << 28) - 1) {  // epoch space exhausted: start over with zeroed tags
-      CK(cudaMemsetAsync(ctx->xf_agg.p, 0, ctx->xf_agg.cap, st));
-      CK(cudaMemsetAsync(ctx->xf_inc.p, 0, ctx->xf_inc.cap, st));
-      CK(cudaMemsetAsync(ctx->ex_agg.p, 0, ctx->ex_agg.cap, st));
-      CK(cudaMemsetAsync(ctx->ex_inc.p, 0, ctx->ex_inc.cap, st));
-      CK(cudaMemsetAsync(ctx->xf_status.p, 0, ctx->xf_status.cap, st));
-      CK(cudaMemsetAsync(ctx->ex_status.p, 0, ctx->ex_status.cap, st));
-      CK(cudaMemsetAsync(ctx->pending.p, 0, ctx->pending.cap, st));
-      ctx->epoch = 1;
-    }
-    A.epoch = ctx->epoch;
-    A.tile_counter = ctx->tile_counter.as<unsigned int>();
-    const size_t grid = tiles < ctx->scan_max_ctas ? tiles : ctx->scan_max_ctas;
-    A.tile_base = ctx->tile_base;
-    ctx->tile_base += (unsigned int)(tiles + grid);  // every CTA draws ids until it sees one >= ntiles
+    A.Q = (int64_t)(tiles * TILE_THREADS);
+    A.st_c = ctx->st_c.as<uint32_t>();
+    A.st_s = ctx->st_s.as<int64_t>();
+    A.st_ea = ctx->st_ea.as<fx_t>();
+    A.st_eb = ctx->st_eb.as<fx_t>();
+    A.st_flags = ctx->st_flags.as<uint32_t>();
+    A.st_p0 = ctx->st_p0.as<int64_t>();
+    A.tile_xf = ctx->tile_xf.as<XfRec>();
+    A.tile_S = ctx->tile_S.as<fx_t>();
+    A.tile_ex = ctx->tile_ex.as<ExRec>();
+    A.pending = ctx->pending.as<ExPending>();
+    A.S_start = 0;
+    A.E_start.M = -(((fx_t)1) << 126);
+    A.E_start.beg = -1; A.E_start.pk = -1; A.E_start.reset = 1; A.E_start.open = 0;
+    A.launch_xf = nullptr;
     A.rec_beg = ctx->rec_beg.as<int64_t>();
     A.rec_pk = ctx->rec_pk.as<int64_t>();
     A.rec_c = ctx->rec_c.as<int64_t>();
@@ -941,13 +911,15 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.rec_mlo = ctx->rec_mlo.as<uint64_t>();
     A.rec_count = d_rec_count;
     A.rec_cap = ctx->rec_cap;
-    A.dbg = (level == 0 && ctx->dbg.p) ? ctx->dbg.as<unsigned long long>() : nullptr;
     cudaEvent_t ps = ctx->prof_begin();
-    if (tab.use_lut) scan_level_kernel<true><<<(unsigned)grid, TILE_THREADS, dyn_smem, st>>>(A);
-    else scan_level_kernel<false><<<(unsigned)grid, TILE_THREADS, dyn_smem, st>>>(A);
+    if (tab.use_lut) scan_gather_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else scan_gather_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    tile_scan_kernel<<<1, TSCAN_THREADS, 0, st>>>(A);
+    if (tab.use_lut) scan_walk_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else scan_walk_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     ex_fixup_kernel<<<blocks_exact(tiles, 8), 256, 0, st>>>(A);
     ctx->prof_end(level == 0 ? KS_PROF_SCAN0 : KS_PROF_SCANN, ps);
-    LAUNCHED(2);
+    LAUNCHED(4);
     CK(cudaGetLastError());
     struct { unsigned long long cnt; } hres;
     DevScanParams hprm;

@@ -221,7 +221,8 @@ KS_HD fx_t xf_apply(const Xf &f, fx_t x) { return f.kill ? f.b : fx_max(x + f.a,
 
 // chunk transform.  s[j] valid where bit j of live is set; other positions force the state to 0.
 // 64-bit inside the chunk (|s| < 2^57, 16 terms), widened at the end.
-KS_HD Xf chunk_transform(const int64_t s[CHUNK], uint32_t live) {
+template <class Scores>
+KS_HD Xf chunk_transform(const Scores &s, uint32_t live) {
   int64_t a = 0, b = -(1ll << 62);
   uint32_t kill = 0;
 #pragma unroll
@@ -279,8 +280,8 @@ KS_HD bool qualifies(const ScanParams &p, int64_t beg, int64_t pk, fx_t M) {
 // 64-bit inside the chunk: the walk runs on sigma = min(S_in, 2^62).  A chunk moves the state by
 // less than 2^61, so with S_in >= 2^62 no position reaches 0 either way and all comparisons agree;
 // maxima are shifted back by S_in - sigma when they leave the chunk.
-template <class Emit>
-KS_HD void chunk_walk(const int64_t s[CHUNK], uint32_t live, fx_t S_in, int64_t p0,
+template <class Scores, class Emit>
+KS_HD void chunk_walk(const Scores &s, uint32_t live, fx_t S_in, int64_t p0,
                       const ScanParams &prm, Emit &emit, Ex &ex, fx_t &preM, int64_t &prePk,
                       int &first_zero) {
   const fx_t cap = ((fx_t)1) << 62;

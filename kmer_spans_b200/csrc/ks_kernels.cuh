@@ -190,56 +190,32 @@ __global__ void __launch_bounds__(256) wfx_kernel(const double *__restrict__ W, 
 }
 
 // ------------------------------------------------------------------------------------------
-// look-back descriptors: 16-byte self-validating words {tag, 96-bit payload}, written and read with
-// single 128-bit accesses, so a reader needs ONE L2 round trip per window and no fences.
-//   tag = epoch << 4 | open << 3 | kill/reset << 2 | state      state 1 = aggregate of this tile alone,
-//                                                               2 = inclusive (everything to the left folded in)
-// Buffers are zeroed once; a new epoch per launch makes older words read as "not ready".
-// 96-bit payloads bound the running sums to |S| < 2^95 units, i.e. < 2^32 positions per scan.
-struct TileState {
-  uint4 *xfA;  // aggregate: a
-  uint4 *xfB;  // aggregate: b (+kill in the tag)   | inclusive: S at the tile end
-  uint4 *gA;   // the same pair per GROUP of 32 consecutive tiles (second look-back level)
-  uint4 *gB;
-  uint32_t *gdone;  // per group: tiles whose aggregate is published (zeroed before every launch)
-  uint4 *exA;  // open-excursion aggregate of the tile: M
-  uint4 *exB;  //                                       beg (48 bit) | pk (48 bit)
-};
-constexpr int GROUP_TILES = 32;
-
-__device__ __forceinline__ uint4 ld_desc(const uint4 *p) {
-  uint4 v;
-  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_desc(uint4 *p, uint32_t tag, uint32_t hi, uint64_t lo) {
-  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(tag), "r"(hi),
-               "r"((uint32_t)lo), "r"((uint32_t)(lo >> 32)) : "memory");
-}
-__device__ __forceinline__ void st_desc_fx(uint4 *p, uint32_t tag, fx_t v) {
-  st_desc(p, tag, (uint32_t)fx_hi(v), fx_lo(v));
-}
-__device__ __forceinline__ fx_t desc_fx(const uint4 &d) {  // sign-extend the 96-bit payload
-  return fx_make((uint64_t)(int64_t)(int32_t)d.y, ((uint64_t)d.w << 32) | d.z);
-}
-constexpr uint32_t TAG_AGG = 1u, TAG_INC = 2u, TAG_KILL = 4u, TAG_OPEN = 8u;
-constexpr int64_t POS48_NONE = (1ll << 48) - 1;
-
-// An excursion that entered a tile from the left and closes inside it needs the open-excursion state
-// at the tile start.  The scan kernel never waits for it: the one thread per tile that needs it
-// leaves this record, and ex_fixup_kernel resolves it after the launch from the per-tile aggregates.
+// K4 + K5 + K6: the scan of one restart level, as three spin-free kernels around a compact stash in HBM
+//   scan_gather_kernel  packed window -> codes -> table gather -> chunk transform -> block scan;
+//                       stashes the gathered values (4 B/position in LUT mode, 8 B in table mode), the
+//                       thread's exclusive in-tile transform, and the tile aggregate
+//   tile_scan_kernel    exclusive scan of the tile aggregates (one CTA): state entering every tile
+//   scan_walk_kernel    stash -> excursion walk (start, leftmost peak, close), segmented scan of the
+//                       open-excursion state, qualification, emission through an atomic cursor
+//   ex_fixup_kernel     excursions that entered a tile from the left and close in it: walk back over the
+//                       per-tile excursion aggregates to the tile that holds the start
+// An earlier single-kernel version (decoupled look-back, software-pipelined persistent CTAs) ran at
+// 27 % issue / 28 % L1tex utilisation because 120 registers and an 88 KB shared-memory stash allowed
+// 16 warps per SM and every CTA moved through its phases in lock step (profiles/r01_v3_ncu_full.md).
+// Split like this each kernel holds 3-4x the warps, the gather runs near the measured gather rate,
+// and nothing ever waits on another CTA; the price is ~6 B/position of stash traffic.
 struct __align__(16) ExPending {
   uint64_t m_lo;
   int64_t m_hi;   // max over the tile's positions before the close (fixed point)
   int64_t pk;     // its leftmost position
   int64_t c;      // close position
-  uint32_t epoch; // valid iff == launch epoch
+  uint32_t valid;
   uint32_t pad[3];
 };
+struct __align__(16) XfRec { fx_t a, b; uint32_t kill; uint32_t pad[3]; };
+struct __align__(16) ExRec { fx_t M; int64_t beg, pk; uint32_t reset, open; uint32_t pad[2]; };
 
 struct LevelArgs {
-  ExPending *pending;  // one slot per tile
   const uint32_t *pk;   // packed 2-bit codes, one word per 16 positions (chunk c = positions [16c, 16c+16))
   const uint16_t *brk;  // break masks, one half-word per 16 positions
   int64_t ntiles;
@@ -265,16 +241,26 @@ struct LevelArgs {
   int64_t dense_start;
   int64_t total_chunks;
   int32_t *inscan;  // or NULL
-  TileState ts;
-  uint32_t epoch;
-  unsigned int *tile_counter;
-  unsigned int tile_base;
+  // stash, indexed by work chunk q (Q = ntiles * TILE_THREADS): element j of chunk q at [j * Q + q]
+  int64_t Q;
+  uint32_t *st_c;     // LUT mode: gathered counts
+  int64_t *st_s;      // table mode: gathered scores
+  fx_t *st_ea, *st_eb;  // exclusive in-tile transform of the chunk
+  uint32_t *st_flags;   // live (16 bits) | head << 16 | excl.kill << 17
+  int64_t *st_p0;
+  XfRec *tile_xf;       // aggregate transform per tile
+  fx_t *tile_S;         // state entering the tile (tile_scan_kernel)
+  ExRec *tile_ex;       // open-excursion aggregate per tile (scan_walk_kernel)
+  ExPending *pending;   // one slot per tile
+  // carry-in of the whole launch (0 / closed unless a previous shard hands them over)
+  fx_t S_start;
+  ExRec E_start;
+  XfRec *launch_xf;     // out: aggregate transform of the launch (tile_scan_kernel), or NULL
   // emitted records (SoA), appended across levels
   int64_t *rec_beg, *rec_pk, *rec_c, *rec_mhi;
   uint64_t *rec_mlo;
   unsigned long long *rec_count;
   unsigned long long rec_cap;
-  unsigned long long *dbg;  // KS_EXP_TIMING builds: per-phase cycle sums (thread 0 of every tile)
 };
 
 struct DevEmit {
@@ -291,154 +277,18 @@ struct DevEmit {
   }
 };
 
-__device__ __forceinline__ Xf poll_xf(const uint4 *dA, const uint4 *dB, int64_t idx, uint32_t epoch) {
-  Xf x;
-  x.kill = 1; x.a = 0; x.b = 0;
-  for (;;) {
-    uint4 B = ld_desc(&dB[idx]);
-    uint4 Aw = ld_desc(&dA[idx]);
-    if ((B.x >> 4) != epoch) continue;
-    if ((B.x & 3u) == TAG_INC) { x.b = desc_fx(B); break; }
-    if ((B.x & 3u) == TAG_AGG && (Aw.x >> 4) == epoch && (Aw.x & 3u) == TAG_AGG) {
-      x.kill = (B.x >> 2) & 1u;
-      x.a = desc_fx(Aw);
-      x.b = desc_fx(B);
-      break;
-    }
-  }
-  return x;
-}
-__device__ __forceinline__ void publish_xf(uint4 *dA, uint4 *dB, int64_t idx, uint32_t epoch, const Xf &f) {
-  const uint32_t tg = epoch << 4;
-  if (f.kill) {  // does not depend on anything to the left: final
-    st_desc_fx(&dB[idx], tg | TAG_INC, f.b);
-  } else {
-    st_desc_fx(&dA[idx], tg | TAG_AGG, f.a);
-    st_desc_fx(&dB[idx], tg | TAG_AGG, f.b);
-  }
-}
-// ordered warp reduction: lane L holds the transform of an EARLIER range than lane L-1
-__device__ __forceinline__ Xf warp_fold_xf(Xf x, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    Xf y = shfl_xf(x, (lane + o) & 31);
-    if (lane + o < 32) x = xf_compose(y, x);
-  }
-  return shfl_xf(x, 0);
-}
-
-// Two-level decoupled look-back for the max-plus transform, run by warp 0: returns the state S at
-// the start of `tile`.  Window 1 covers the earlier tiles of the own 32-tile group; if that is not
-// enough, window 2+ walks whole groups, 32 per step, so ~1000 tiles of lag cost two windows.
-// Group aggregates are published EARLY, by whichever tile of the group finishes its local phase last
-// (publish_group_if_last); the last tile of a group later upgrades it to the inclusive value.
-// A transform with kill set (an inclusive value, or an aggregate containing a reset) ends the walk
-// because composition ignores everything left of it.
-__device__ __forceinline__ fx_t lookback_xf(const TileState &ts, int64_t tile, uint32_t epoch,
-                                            const Xf &agg, int lane) {
-  const int64_t g = tile / GROUP_TILES;
-  const int l = (int)(tile % GROUP_TILES);
-  Xf x = xf_identity();  // (the tile's own aggregate was published at the end of its local phase)
-  if (lane < l) x = poll_xf(ts.xfA, ts.xfB, tile - 1 - lane, epoch);
-  Xf acc = warp_fold_xf(x, lane);  // tiles [32 g, tile)
-  const Xf grp = xf_compose(acc, agg);  // tiles [32 g, tile]
-  const bool last = (l == GROUP_TILES - 1);
-  int64_t gbase = g - 1;
-  while (!acc.kill) {
-    int64_t idx = gbase - lane;
-    Xf y;
-    y.kill = 1; y.a = 0; y.b = 0;  // before the first tile the state is 0
-    if (idx >= 0) y = poll_xf(ts.gA, ts.gB, idx, epoch);
-    acc = xf_compose(warp_fold_xf(y, lane), acc);
-    gbase -= 32;
-  }
-  const fx_t S_tile = acc.b;
-  if (lane == 0) {
-    const fx_t S_end = xf_apply(agg, S_tile);
-    if (!agg.kill) st_desc_fx(&ts.xfB[tile], (epoch << 4) | TAG_INC, S_end);
-    if (last && !grp.kill) st_desc_fx(&ts.gB[g], (epoch << 4) | TAG_INC, S_end);
-  }
-  return S_tile;
-}
-
-__device__ __forceinline__ void publish_ex(const TileState &ts, int64_t tile, uint32_t epoch, const Ex &e) {
-  uint32_t tag = (epoch << 4) | (e.open ? TAG_OPEN : 0u) | (e.reset ? TAG_KILL : 0u) | TAG_AGG;
-  fx_t M = e.M;
-  const fx_t lo_lim = -(((fx_t)1) << 94);
-  if (M < lo_lim) M = lo_lim;
-  uint64_t b48 = (uint64_t)(e.beg < 0 ? POS48_NONE : e.beg) & 0xffffffffffffull;
-  uint64_t p48 = (uint64_t)(e.pk < 0 ? POS48_NONE : e.pk) & 0xffffffffffffull;
-  st_desc_fx(&ts.exA[tile], tag, M);
-  st_desc(&ts.exB[tile], tag, (uint32_t)(b48 >> 16), (b48 << 48) | p48);
-}
-
-// Open-excursion state at the start of `tile`, resolved LAZILY: every tile publishes the aggregate
-// of its own chunks (no chain), and only a tile in which an excursion that entered from the left
-// closes walks back (warp 0, 32 tiles per step) to the tile that holds the excursion's start.
-__device__ __forceinline__ Ex lookback_ex(const TileState &ts, int64_t tile, uint32_t epoch, int lane) {
-  Ex acc = ex_identity();
-  int64_t base = tile - 1;
-  for (;;) {
-    int64_t idx = base - lane;
-    Ex x = ex_identity();
-    x.reset = 1; x.open = 0;
-    if (idx >= 0) {
-      for (;;) {
-        uint4 Aw = ld_desc(&ts.exA[idx]);
-        uint4 B = ld_desc(&ts.exB[idx]);
-        if ((Aw.x >> 4) != epoch || (Aw.x & 3u) == 0u || Aw.x != B.x) continue;
-        x.M = desc_fx(Aw);
-        uint64_t lo = ((uint64_t)B.w << 32) | B.z;
-        int64_t b48 = (int64_t)(((uint64_t)B.y << 16) | (lo >> 48));
-        int64_t p48 = (int64_t)(lo & 0xffffffffffffull);
-        x.beg = b48 == POS48_NONE ? -1 : b48;
-        x.pk = p48 == POS48_NONE ? -1 : p48;
-        x.open = (Aw.x >> 3) & 1u;
-        x.reset = (Aw.x >> 2) & 1u;
-        break;
-      }
-    }
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      Ex y = shfl_ex(x, (lane + o) & 31);
-      if (lane + o < 32) x = ex_combine(y, x);
-    }
-    acc = ex_combine(shfl_ex(x, 0), acc);
-    if (acc.reset) return acc;
-    base -= 32;
-  }
-}
-
-// K4 + K5 + K6.  Persistent CTAs, tile = TILE_THREADS chunks (4096 positions at 256 threads), tile ids
-// handed out in order by an atomic counter so that a tile only ever waits on tiles that already run.
-// Software pipeline per CTA:   local(t1)  local(t2) finish(t1)  local(t3) finish(t2) ...
-//   local : packed input -> codes -> table gather -> chunk transform -> block scan -> publish aggregate;
-//           everything finish() needs is stashed in shared memory
-//   finish: look-back for the state entering the tile (by now the predecessors' aggregates exist),
-//           excursion walk, segmented scan of the open-excursion state, emission
-// so the look-back latency of one tile hides behind the gather latency of the next.
-struct Stash {
-  int64_t s[CHUNK][TILE_THREADS];  // fixed-point scores, [j][thread]: conflict-free 8-byte accesses
-  fx_t ea[TILE_THREADS];           // exclusive in-tile transform of the thread: a
-  fx_t eb[TILE_THREADS];           //                                              b
-  int64_t p0[TILE_THREADS];
-  uint32_t flags[TILE_THREADS];    // live (16 bits) | head << 16 | excl.kill << 17
-  Xf agg;                          // aggregate of the tile
-  uint32_t group_last;             // this tile completed its 32-tile group
-};
-
-#if defined(KS_EXP_TIMING)
-#define KS_T0 long long tk_ = clock64();
-#define KS_TICK(slot) { long long n_ = clock64(); if (threadIdx.x == 0 && A.dbg) atomicAdd(A.dbg + (slot), (unsigned long long)(n_ - tk_)); tk_ = n_; }
-#else
-#define KS_T0
-#define KS_TICK(slot)
+#ifndef KS_GATHER_MINBLOCKS
+#define KS_GATHER_MINBLOCKS 3
+#endif
+#ifndef KS_WALK_MINBLOCKS
+#define KS_WALK_MINBLOCKS 3
 #endif
 
 template <bool kLut>
-__device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Stash &st, Xf *s_wxf) {
+__global__ void __launch_bounds__(TILE_THREADS, KS_GATHER_MINBLOCKS) scan_gather_kernel(const LevelArgs A) {
+  __shared__ Xf s_wxf[TILE_WARPS + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  KS_T0
+  const int64_t tile = blockIdx.x;
   // ---- chunk -> position mapping ----
   const int64_t q = tile * TILE_THREADS + tid;
   int64_t p0 = 16;
@@ -478,14 +328,13 @@ __device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Sta
     uint64_t b48 = (uint64_t)b0 | ((uint64_t)b1 << 16) | ((uint64_t)b2 << 32);
     brk32 = (uint32_t)(b48 >> r);
   }
-  // ---- codes + gather ----
-  if (X == 0x123456789abcdefull) return;  // (keeps the loads above the tick in timing builds; never true)
-  KS_TICK(0)
+  // ---- codes, gather (16 independent loads in flight), scores, chunk transform ----
   uint32_t code[CHUNK], scored;
   decode_scan(X, brk32, A.k, A.kmask, n_in, code, scored);
-  int64_t s[CHUNK];
-  uint32_t live = 0;
   const uint64_t keep = l2_policy_evict_last();
+  uint32_t live = 0;
+  int64_t ta = 0, tb = -(1ll << 62);
+  uint32_t tkill = 0;
   if (kLut) {
     uint32_t c[CHUNK];
 #pragma unroll
@@ -505,25 +354,43 @@ __device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Sta
           v = __ldg(&A.sp_val[lo]);
         }
       }
-      s[j] = v;
+      A.st_c[(int64_t)j * A.Q + q] = c[j];
+      if (v != WFX_KILL) {
+        live |= 1u << j;
+        ta += v;
+        int64_t t = tb + v;
+        tb = t > 0 ? t : 0;
+      } else {
+        tkill = 1; ta = 0; tb = 0;
+      }
     }
   } else {
+    int64_t sv[CHUNK];
 #pragma unroll
-    for (int j = 0; j < CHUNK; ++j) s[j] = (scored & (1u << j)) ? ldg_s64_keep(&A.wfx[code[j]], keep) : WFX_KILL;
-  }
+    for (int j = 0; j < CHUNK; ++j) sv[j] = (scored & (1u << j)) ? ldg_s64_keep(&A.wfx[code[j]], keep) : WFX_KILL;
 #pragma unroll
-  for (int j = 0; j < CHUNK; ++j) {
-    if (s[j] != WFX_KILL) live |= 1u << j; else s[j] = 0;
+    for (int j = 0; j < CHUNK; ++j) {
+      int64_t v = sv[j];
+      A.st_s[(int64_t)j * A.Q + q] = v == WFX_KILL ? 0 : v;
+      if (v != WFX_KILL) {
+        live |= 1u << j;
+        ta += v;
+        int64_t t = tb + v;
+        tb = t > 0 ? t : 0;
+      } else {
+        tkill = 1; ta = 0; tb = 0;
+      }
+    }
   }
   if (A.inscan) {
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j)
       if (scored & (1u << j)) atomicAdd(&A.inscan[code[j]], 1);
   }
-  // ---- chunk transform + block scan ----
-  KS_TICK(1)
-  Xf f = chunk_transform(s, live);
+  Xf f;
+  f.a = (fx_t)ta; f.b = (fx_t)tb; f.kill = tkill;
   if (head) { fx_t v = xf_apply(f, 0); f.kill = 1; f.a = 0; f.b = v; }
+  // ---- block scan of the chunk transforms ----
   Xf inc = f;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -533,12 +400,7 @@ __device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Sta
   Xf excl = shfl_xf(inc, (lane - 1) & 31);
   if (lane == 0) excl = xf_identity();
   if (lane == 31) s_wxf[warp] = inc;
-  KS_TICK(2)
-#pragma unroll
-  for (int j = 0; j < CHUNK; ++j) st.s[j][tid] = s[j];
-  st.p0[tid] = p0;
   __syncthreads();
-  KS_TICK(3)
   if (warp == 0) {  // exclusive scan of the warp totals by one warp: s_wxf[w] <- totals of warps < w
     Xf ti = lane < TILE_WARPS ? s_wxf[lane] : xf_identity();
 #pragma unroll
@@ -549,77 +411,107 @@ __device__ __forceinline__ void scan_local(const LevelArgs &A, int64_t tile, Sta
     Xf te = shfl_xf(ti, (lane - 1) & 31);
     if (lane == 0) te = xf_identity();
     if (lane < TILE_WARPS) s_wxf[lane] = te;
-    if (lane == TILE_WARPS - 1) s_wxf[TILE_WARPS] = ti;  // aggregate of the tile
+    if (lane == TILE_WARPS - 1) {  // aggregate of the tile
+      XfRec rr;
+      rr.a = ti.a; rr.b = ti.b; rr.kill = ti.kill; rr.pad[0] = rr.pad[1] = rr.pad[2] = 0;
+      A.tile_xf[tile] = rr;
+    }
   }
   __syncthreads();
   excl = xf_compose(s_wxf[warp], excl);
-  st.ea[tid] = excl.a;
-  st.eb[tid] = excl.b;
-  st.flags[tid] = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u);
-  if (tid == 0) {
-    Xf agg = s_wxf[TILE_WARPS];
-    st.agg = agg;
-    publish_xf(A.ts.xfA, A.ts.xfB, tile, A.epoch, agg);
-    // the tile that completes a group publishes the group aggregate right away
-    const int64_t g = tile / GROUP_TILES;
-    int64_t gsize = A.ntiles - g * GROUP_TILES;
-    if (gsize > GROUP_TILES) gsize = GROUP_TILES;
-    uint32_t done = atomicAdd(&A.ts.gdone[g], 1u);
-    st.group_last = (gsize == GROUP_TILES && done == (uint32_t)(GROUP_TILES - 1)) ? 1u : 0u;
+  A.st_ea[q] = excl.a;
+  A.st_eb[q] = excl.b;
+  A.st_flags[q] = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u);
+  if (A.nseg != 0) A.st_p0[q] = p0;
+}
+
+// State entering every tile: exclusive scan of the tile aggregates with the launch's carry-in.
+// One CTA; each thread folds a contiguous block of tiles, the block totals are
+// scanned through shared memory, then every thread walks its block again.
+constexpr int TSCAN_THREADS = 512;
+__global__ void __launch_bounds__(TSCAN_THREADS) tile_scan_kernel(const LevelArgs A) {
+  __shared__ Xf sh[TSCAN_THREADS];
+  const int tid = threadIdx.x;
+  const int64_t per = (A.ntiles + TSCAN_THREADS - 1) / TSCAN_THREADS;
+  const int64_t t0 = per * tid, t1 = (t0 + per < A.ntiles) ? t0 + per : A.ntiles;
+  Xf f = xf_identity();
+  for (int64_t t = t0; t < t1; ++t) {
+    XfRec r = A.tile_xf[t];
+    Xf g; g.a = r.a; g.b = r.b; g.kill = r.kill;
+    f = xf_compose(f, g);
   }
-  __syncthreads();  // s_wxf may be overwritten by the next local phase; the stash is complete
-  KS_TICK(4)
-  if (st.group_last && warp == 0) {
-    const int64_t g = tile / GROUP_TILES;
-    Xf x = poll_xf(A.ts.xfA, A.ts.xfB, g * GROUP_TILES + (GROUP_TILES - 1 - lane), A.epoch);
-    Xf grp = warp_fold_xf(x, lane);
-    if (lane == 0) {
-      uint4 cur = ld_desc(&A.ts.gB[g]);
-      if (!((cur.x >> 4) == A.epoch && (cur.x & 3u) == TAG_INC)) publish_xf(A.ts.gA, A.ts.gB, g, A.epoch, grp);
-    }
+  sh[tid] = f;
+  __syncthreads();
+  for (int o = 1; o < TSCAN_THREADS; o <<= 1) {  // inclusive Hillis-Steele over the block totals
+    Xf y = xf_identity();
+    if (tid >= o) y = sh[tid - o];
+    __syncthreads();
+    if (tid >= o) sh[tid] = xf_compose(y, sh[tid]);
+    __syncthreads();
+  }
+  Xf pre = tid ? sh[tid - 1] : xf_identity();
+  if (tid == TSCAN_THREADS - 1 && A.launch_xf) {
+    XfRec rr;
+    rr.a = sh[tid].a; rr.b = sh[tid].b; rr.kill = sh[tid].kill; rr.pad[0] = rr.pad[1] = rr.pad[2] = 0;
+    *A.launch_xf = rr;
+  }
+  fx_t S = xf_apply(pre, A.S_start);
+  for (int64_t t = t0; t < t1; ++t) {
+    A.tile_S[t] = S;
+    XfRec r = A.tile_xf[t];
+    Xf g; g.a = r.a; g.b = r.b; g.kill = r.kill;
+    S = xf_apply(g, S);
   }
 }
 
-__device__ __forceinline__ void scan_finish(const LevelArgs &A, int64_t tile, const Stash &st, Ex *s_wex,
-                                            fx_t *s_S, const ScanParams &prm) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  KS_T0
-  if (warp == 0) {
-#if defined(KS_EXP_NO_LOOKBACK)
-    fx_t S0 = 0;
-#else
-    fx_t S0 = lookback_xf(A.ts, tile, A.epoch, st.agg, lane);
-#endif
-    if (lane == 0) *s_S = S0;
+struct StashScoresLut {  // scores of one chunk, LUT mode: count from the stash, score from the LUT
+  const LevelArgs *A;
+  int64_t q;
+  __device__ __forceinline__ int64_t operator[](int j) const {
+    uint32_t c = A->st_c[(int64_t)j * A->Q + q];
+    if (c < A->lut_size) return __ldg(&A->lut[c]);
+    uint32_t lo = 0, hi = A->sp_n;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(&A->sp_count[mid]) <= c) lo = mid; else hi = mid;
+    }
+    return __ldg(&A->sp_val[lo]);
   }
-  KS_TICK(5)
-  __syncthreads();
-  const fx_t S_tile = *s_S;
-#if defined(KS_EXP_NO_WALK)
-  if (S_tile == 12345) A.rec_count[0] = 1;
-  return;
-#endif
-  const uint32_t fl = st.flags[tid];
+};
+
+template <bool kLut>
+__global__ void __launch_bounds__(TILE_THREADS, KS_WALK_MINBLOCKS) scan_walk_kernel(const LevelArgs A) {
+  __shared__ Ex s_wex[TILE_WARPS + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tile = blockIdx.x;
+  const int64_t q = tile * TILE_THREADS + tid;
+  ScanParams prm;
+  prm.min_width = A.prm->min_width;
+  prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
+  const fx_t S_tile = A.tile_S[tile];
+  const uint32_t fl = A.st_flags[q];
   const uint32_t live = fl & 0xffffu;
   const bool head = (fl & 0x10000u) != 0;
-  const int64_t p0 = st.p0[tid];
+  const int64_t p0 = A.nseg == 0 ? A.dense_start + 16 * q : A.st_p0[q];
   Xf excl;
-  excl.a = st.ea[tid]; excl.b = st.eb[tid]; excl.kill = (fl >> 17) & 1u;
+  excl.a = A.st_ea[q]; excl.b = A.st_eb[q]; excl.kill = (fl >> 17) & 1u;
   const fx_t S_in = head ? (fx_t)0 : xf_apply(excl, S_tile);
   int64_t s[CHUNK];
+  if (kLut) {
+    StashScoresLut acc{&A, q};
 #pragma unroll
-  for (int j = 0; j < CHUNK; ++j) s[j] = st.s[j][tid];
-
-  // ---- excursions: local walk, segmented scan of the open-excursion state, lazy look-back ----
+    for (int j = 0; j < CHUNK; ++j) s[j] = (live & (1u << j)) ? acc[j] : 0;
+  } else {
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) s[j] = A.st_s[(int64_t)j * A.Q + q];
+  }
+  // ---- excursions: local walk, segmented scan of the open-excursion state ----
   DevEmit emit{&A};
   Ex ex;
   fx_t preM;
   int64_t prePk;
   int first_zero;
-  KS_TICK(6)
   chunk_walk(s, live, S_in, p0, prm, emit, ex, preM, prePk, first_zero);
-  KS_TICK(7)
-
   Ex einc = ex;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -640,11 +532,14 @@ __device__ __forceinline__ void scan_finish(const LevelArgs &A, int64_t tile, co
     Ex te = shfl_ex(ti, (lane - 1) & 31);
     if (lane == 0) te = ex_identity();
     if (lane < TILE_WARPS) s_wex[lane] = te;
-    if (lane == TILE_WARPS - 1) publish_ex(A.ts, tile, A.epoch, ti);
+    if (lane == TILE_WARPS - 1) {
+      ExRec rr;
+      rr.M = ti.M; rr.beg = ti.beg; rr.pk = ti.pk; rr.reset = ti.reset; rr.open = ti.open; rr.pad[0] = rr.pad[1] = 0;
+      A.tile_ex[tile] = rr;
+    }
   }
   __syncthreads();
   eexcl = ex_combine(s_wex[warp], eexcl);
-  KS_TICK(8)
   if (!head && S_in > 0 && first_zero >= 0) {
     if (eexcl.reset) {
       // the entering excursion started inside this tile: everything is known
@@ -654,75 +549,57 @@ __device__ __forceinline__ void scan_finish(const LevelArgs &A, int64_t tile, co
       fx_t M = eexcl.M;
       int64_t pk = eexcl.pk;
       if (preM > M) { M = preM; pk = prePk; }
-      ExPending *pe = &A.pending[tile];
-      pe->m_lo = fx_lo(M);
-      pe->m_hi = (int64_t)fx_hi(M);
-      pe->pk = pk;
-      pe->c = p0 + first_zero;
-      pe->epoch = A.epoch;
+      ExPending pe;
+      pe.m_lo = fx_lo(M);
+      pe.m_hi = (int64_t)fx_hi(M);
+      pe.pk = pk;
+      pe.c = p0 + first_zero;
+      pe.valid = 1; pe.pad[0] = pe.pad[1] = pe.pad[2] = 0;
+      A.pending[tile] = pe;
     }
   }
-  KS_TICK(9)
 }
 
-// One warp per tile of the finished launch: resolve the deferred entering excursion (if any) by
+// One warp per tile of the finished level: resolve the deferred entering excursion (if any) by
 // walking back over the per-tile open-excursion aggregates, 32 tiles per step, to the tile that holds
-// the excursion's start.  Every aggregate of the launch is final by now, so nothing spins.
+// the excursion's start (or to the launch's carry-in).
 __global__ void __launch_bounds__(256) ex_fixup_kernel(const LevelArgs A) {
   const int lane = threadIdx.x & 31;
   const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tile >= A.ntiles) return;
   const ExPending pe = A.pending[tile];
-  if (pe.epoch != A.epoch) return;
+  if (!pe.valid) return;
+  if (lane == 0) A.pending[tile].valid = 0;
   ScanParams prm;
   prm.min_width = A.prm->min_width;
   prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
-  Ex E = lookback_ex(A.ts, tile, A.epoch, lane);
+  Ex acc = ex_identity();
+  int64_t base = tile - 1;
+  for (;;) {
+    int64_t idx = base - lane;
+    Ex x;
+    if (idx >= 0) {
+      ExRec r = A.tile_ex[idx];
+      x.M = r.M; x.beg = r.beg; x.pk = r.pk; x.reset = r.reset; x.open = r.open;
+    } else {  // left of the launch: its carry-in (closed unless a previous shard handed one over)
+      x.M = A.E_start.M; x.beg = A.E_start.beg; x.pk = A.E_start.pk; x.reset = 1; x.open = A.E_start.open;
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      Ex y = shfl_ex(x, (lane + o) & 31);
+      if (lane + o < 32) x = ex_combine(y, x);
+    }
+    acc = ex_combine(shfl_ex(x, 0), acc);
+    if (acc.reset) break;
+    base -= 32;
+  }
   if (lane == 0) {
-    fx_t M = E.M;
-    int64_t pk = E.pk;
+    fx_t M = acc.M;
+    int64_t pk = acc.pk;
     const fx_t Mp = fx_make((uint64_t)pe.m_hi, pe.m_lo);
     if (Mp > M) { M = Mp; pk = pe.pk; }
     DevEmit emit{&A};
-    if (E.open && qualifies(prm, E.beg, pk, M)) emit(E.beg, pk, pe.c, M);
-  }
-}
-
-template <bool kLut>
-__global__ void __launch_bounds__(TILE_THREADS, KS_SCAN_MINBLOCKS) scan_level_kernel(const LevelArgs A) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  Stash *stash = reinterpret_cast<Stash *>(dyn_smem);  // two buffers
-  __shared__ int64_t s_tile[2];
-  __shared__ Xf s_wxf[TILE_WARPS + 1];
-  __shared__ Ex s_wex[TILE_WARPS + 1];
-  __shared__ fx_t s_S;
-  const int tid = threadIdx.x;
-
-  ScanParams prm;
-  prm.min_width = A.prm->min_width;
-  prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
-
-  int slot = 0;
-  auto next_tile = [&]() -> int64_t {
-    KS_T0
-    if (tid == 0) s_tile[slot] = (int64_t)(unsigned int)(atomicAdd(A.tile_counter, 1u) - A.tile_base);
-    __syncthreads();
-    int64_t t = s_tile[slot];
-    slot ^= 1;  // a slot is rewritten only two fetches later, with whole phases (and barriers) in between
-    KS_TICK(10)
-    if (tid == 0 && A.dbg) atomicAdd(A.dbg + 15, 1ull);
-    return t;
-  };
-
-  int cur = 0;
-  int64_t tA = next_tile();
-  if (tA < A.ntiles) scan_local<kLut>(A, tA, stash[0], s_wxf);
-  while (tA < A.ntiles) {
-    int64_t tB = next_tile();
-    if (tB < A.ntiles) scan_local<kLut>(A, tB, stash[cur ^ 1], s_wxf);
-    scan_finish(A, tA, stash[cur], s_wex, &s_S, prm);
-    tA = tB;
-    cur ^= 1;
+    if (acc.open && qualifies(prm, acc.beg, pk, M)) emit(acc.beg, pk, pe.c, M);
   }
 }
 

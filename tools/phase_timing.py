@@ -20,7 +20,7 @@ for i in range(3):
     if i == 0:
         ctx.lib.ks_ctx_debug_counters(ctx.h, out, 1)
 ctx.lib.ks_ctx_debug_counters(ctx.h, out, 0)
-names = ["L: map + packed loads", "L: decode + gather + LUT", "L: transform + warp scan", "L: stash + barrier",
+names = ["A: map + packed loads + decode + issue gathers", "C: wait counts + LUT", "L: transform + warp scan", "L: stash + barrier",
          "L: prefix + publish + barrier", "F: look-back (warp 0)", "F: barrier + unstash", "F: walk",
          "F: ex scan + publish + barriers", "F: finish entering", "next_tile (2 barriers + atomic)"]
 ntiles = max(out[15], 1)
