@@ -106,7 +106,7 @@ struct ks_ctx {
   void *pinned = nullptr;
   size_t pinned_cap = 0;
   DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, dbg, pending, foc_hist, foc_big;
-  DBuf st_c, st_s, st_ea, st_eb, st_flags, st_p0, tile_xf, tile_S, tile_ex;
+  DBuf st_c, st_s, st_ea, st_eb, st_flags, st_p0, tile_xf, tile_ex, group_xf, group_S, group_ex, pending_list, pending_count;
 
   // timing / profiling
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -229,7 +229,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->out_score, &ctx->sc_keys_a, &ctx->sc_keys_b, &ctx->sc_vals_a, &ctx->sc_vals_b,
                  &ctx->sc_small, &ctx->sc_gcount, &ctx->sc_gstart, &ctx->sc_segfirst, &ctx->sc_segj0,
                  &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->tmp_counts, &ctx->tmp_scores,
-                 &ctx->tmp_inscan, &ctx->nwords, &ctx->dbg, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_S, &ctx->tile_ex, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
+                 &ctx->tmp_inscan, &ctx->nwords, &ctx->dbg, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -800,11 +800,13 @@ static int ensure_tiles(ks_ctx *ctx, size_t tiles, bool lut_mode, bool need_p0) 
   CK(ctx->st_flags.ensure(Q * 4));
   if (need_p0) CK(ctx->st_p0.ensure(Q * 8));
   CK(ctx->tile_xf.ensure(tiles * sizeof(XfRec)));
-  CK(ctx->tile_S.ensure(tiles * 16));
+  CK(ctx->group_xf.ensure((tiles / 32 + 2) * sizeof(XfRec)));
+  CK(ctx->group_S.ensure((tiles / 32 + 2) * 16));
+  CK(ctx->group_ex.ensure((tiles / 32 + 2) * sizeof(ExRec)));
+  CK(ctx->pending_list.ensure(tiles * 4 + 64));
+  CK(ctx->pending_count.ensure(64));
   CK(ctx->tile_ex.ensure(tiles * sizeof(ExRec)));
-  size_t old = ctx->pending.cap;
   CK(ctx->pending.ensure(tiles * sizeof(ExPending)));
-  if (ctx->pending.cap != old) CK(cudaMemsetAsync(ctx->pending.p, 0, ctx->pending.cap, ctx->stream));
   return KS_OK;
 }
 
@@ -897,7 +899,13 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.st_flags = ctx->st_flags.as<uint32_t>();
     A.st_p0 = ctx->st_p0.as<int64_t>();
     A.tile_xf = ctx->tile_xf.as<XfRec>();
-    A.tile_S = ctx->tile_S.as<fx_t>();
+    A.group_xf = ctx->group_xf.as<XfRec>();
+    A.group_S = ctx->group_S.as<fx_t>();
+    A.group_ex = ctx->group_ex.as<ExRec>();
+    A.ngroups = (int64_t)((tiles + 31) / 32);
+    A.pending_list = ctx->pending_list.as<uint32_t>();
+    A.pending_count = ctx->pending_count.as<unsigned int>();
+    CK(cudaMemsetAsync(ctx->pending_count.p, 0, 4, st));
     A.tile_ex = ctx->tile_ex.as<ExRec>();
     A.pending = ctx->pending.as<ExPending>();
     A.S_start = 0;
@@ -914,12 +922,14 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     cudaEvent_t ps = ctx->prof_begin();
     if (tab.use_lut) scan_gather_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else scan_gather_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    tile_scan_kernel<<<1, TSCAN_THREADS, 0, st>>>(A);
+    group_scan_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
+    group_top_kernel<<<1, TSCAN_THREADS, 0, st>>>(A);
     if (tab.use_lut) scan_walk_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else scan_walk_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    ex_fixup_kernel<<<blocks_exact(tiles, 8), 256, 0, st>>>(A);
+    group_ex_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
+    ex_fixup_kernel<<<148, 256, 0, st>>>(A);
     ctx->prof_end(level == 0 ? KS_PROF_SCAN0 : KS_PROF_SCANN, ps);
-    LAUNCHED(4);
+    LAUNCHED(6);
     CK(cudaGetLastError());
     struct { unsigned long long cnt; } hres;
     DevScanParams hprm;

@@ -248,10 +248,15 @@ struct LevelArgs {
   fx_t *st_ea, *st_eb;  // exclusive in-tile transform of the chunk
   uint32_t *st_flags;   // live (16 bits) | head << 16 | excl.kill << 17
   int64_t *st_p0;
-  XfRec *tile_xf;       // aggregate transform per tile
-  fx_t *tile_S;         // state entering the tile (tile_scan_kernel)
+  XfRec *tile_xf;       // aggregate transform per tile; after group_scan_kernel: EXCLUSIVE within its 32-tile group
+  XfRec *group_xf;      // aggregate transform per group of 32 tiles
+  fx_t *group_S;        // state entering the group (group_top_kernel)
+  int64_t ngroups;
   ExRec *tile_ex;       // open-excursion aggregate per tile (scan_walk_kernel)
+  ExRec *group_ex;      // the same per group of 32 tiles (group_ex_kernel)
   ExPending *pending;   // one slot per tile
+  uint32_t *pending_list;        // tiles with a deferred excursion (appended by scan_walk_kernel)
+  unsigned int *pending_count;
   // carry-in of the whole launch (0 / closed unless a previous shard hands them over)
   fx_t S_start;
   ExRec E_start;
@@ -278,10 +283,10 @@ struct DevEmit {
 };
 
 #ifndef KS_GATHER_MINBLOCKS
-#define KS_GATHER_MINBLOCKS 3
+#define KS_GATHER_MINBLOCKS 4
 #endif
 #ifndef KS_WALK_MINBLOCKS
-#define KS_WALK_MINBLOCKS 3
+#define KS_WALK_MINBLOCKS 6
 #endif
 
 template <bool kLut>
@@ -354,7 +359,7 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_GATHER_MINBLOCKS) scan_gather
           v = __ldg(&A.sp_val[lo]);
         }
       }
-      A.st_c[(int64_t)j * A.Q + q] = c[j];
+      __stcs(&A.st_c[(int64_t)j * A.Q + q], c[j]);
       if (v != WFX_KILL) {
         live |= 1u << j;
         ta += v;
@@ -371,7 +376,7 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_GATHER_MINBLOCKS) scan_gather
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) {
       int64_t v = sv[j];
-      A.st_s[(int64_t)j * A.Q + q] = v == WFX_KILL ? 0 : v;
+      __stcs(&A.st_s[(int64_t)j * A.Q + q], v == WFX_KILL ? (int64_t)0 : v);
       if (v != WFX_KILL) {
         live |= 1u << j;
         ta += v;
@@ -425,18 +430,50 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_GATHER_MINBLOCKS) scan_gather
   if (A.nseg != 0) A.st_p0[q] = p0;
 }
 
-// State entering every tile: exclusive scan of the tile aggregates with the launch's carry-in.
-// One CTA; each thread folds a contiguous block of tiles, the block totals are
-// scanned through shared memory, then every thread walks its block again.
-constexpr int TSCAN_THREADS = 512;
-__global__ void __launch_bounds__(TSCAN_THREADS) tile_scan_kernel(const LevelArgs A) {
+// State entering every tile, in two tiny kernels: a warp scans the aggregates of 32 consecutive tiles
+// (tile_xf becomes the exclusive transform inside the group, group_xf the group aggregate); one CTA then
+// scans the group aggregates with the launch's carry-in.  scan_walk_kernel applies
+// S_tile = tile_xf[tile](group_S[tile / 32]).
+constexpr int GROUP_TILES = 32;
+__global__ void __launch_bounds__(256) group_scan_kernel(const LevelArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= A.ngroups) return;
+  const int64_t t = g * GROUP_TILES + lane;
+  Xf x = xf_identity();
+  if (t < A.ntiles) {
+    XfRec r = A.tile_xf[t];
+    x.a = r.a; x.b = r.b; x.kill = r.kill;
+  }
+  Xf inc = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Xf y = shfl_xf(inc, (lane - o) & 31);
+    if (lane >= o) inc = xf_compose(y, inc);
+  }
+  Xf excl = shfl_xf(inc, (lane - 1) & 31);
+  if (lane == 0) excl = xf_identity();
+  if (t < A.ntiles) {
+    XfRec r;
+    r.a = excl.a; r.b = excl.b; r.kill = excl.kill; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    A.tile_xf[t] = r;
+  }
+  if (lane == 31) {
+    XfRec r;
+    r.a = inc.a; r.b = inc.b; r.kill = inc.kill; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    A.group_xf[g] = r;
+  }
+}
+
+constexpr int TSCAN_THREADS = 256;
+__global__ void __launch_bounds__(TSCAN_THREADS) group_top_kernel(const LevelArgs A) {
   __shared__ Xf sh[TSCAN_THREADS];
   const int tid = threadIdx.x;
-  const int64_t per = (A.ntiles + TSCAN_THREADS - 1) / TSCAN_THREADS;
-  const int64_t t0 = per * tid, t1 = (t0 + per < A.ntiles) ? t0 + per : A.ntiles;
+  const int64_t per = (A.ngroups + TSCAN_THREADS - 1) / TSCAN_THREADS;
+  const int64_t t0 = per * tid, t1 = (t0 + per < A.ngroups) ? t0 + per : A.ngroups;
   Xf f = xf_identity();
   for (int64_t t = t0; t < t1; ++t) {
-    XfRec r = A.tile_xf[t];
+    XfRec r = A.group_xf[t];
     Xf g; g.a = r.a; g.b = r.b; g.kill = r.kill;
     f = xf_compose(f, g);
   }
@@ -457,8 +494,8 @@ __global__ void __launch_bounds__(TSCAN_THREADS) tile_scan_kernel(const LevelArg
   }
   fx_t S = xf_apply(pre, A.S_start);
   for (int64_t t = t0; t < t1; ++t) {
-    A.tile_S[t] = S;
-    XfRec r = A.tile_xf[t];
+    A.group_S[t] = S;
+    XfRec r = A.group_xf[t];
     Xf g; g.a = r.a; g.b = r.b; g.kill = r.kill;
     S = xf_apply(g, S);
   }
@@ -468,7 +505,7 @@ struct StashScoresLut {  // scores of one chunk, LUT mode: count from the stash,
   const LevelArgs *A;
   int64_t q;
   __device__ __forceinline__ int64_t operator[](int j) const {
-    uint32_t c = A->st_c[(int64_t)j * A->Q + q];
+    uint32_t c = __ldcs(&A->st_c[(int64_t)j * A->Q + q]);
     if (c < A->lut_size) return __ldg(&A->lut[c]);
     uint32_t lo = 0, hi = A->sp_n;
     while (hi - lo > 1) {
@@ -488,7 +525,12 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_WALK_MINBLOCKS) scan_walk_ker
   ScanParams prm;
   prm.min_width = A.prm->min_width;
   prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
-  const fx_t S_tile = A.tile_S[tile];
+  fx_t S_tile;
+  {
+    XfRec r = A.tile_xf[tile];
+    Xf tx; tx.a = r.a; tx.b = r.b; tx.kill = r.kill;
+    S_tile = xf_apply(tx, A.group_S[tile / GROUP_TILES]);
+  }
   const uint32_t fl = A.st_flags[q];
   const uint32_t live = fl & 0xffffu;
   const bool head = (fl & 0x10000u) != 0;
@@ -503,7 +545,7 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_WALK_MINBLOCKS) scan_walk_ker
     for (int j = 0; j < CHUNK; ++j) s[j] = (live & (1u << j)) ? acc[j] : 0;
   } else {
 #pragma unroll
-    for (int j = 0; j < CHUNK; ++j) s[j] = A.st_s[(int64_t)j * A.Q + q];
+    for (int j = 0; j < CHUNK; ++j) s[j] = __ldcs(&A.st_s[(int64_t)j * A.Q + q]);
   }
   // ---- excursions: local walk, segmented scan of the open-excursion state ----
   DevEmit emit{&A};
@@ -556,50 +598,81 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_WALK_MINBLOCKS) scan_walk_ker
       pe.c = p0 + first_zero;
       pe.valid = 1; pe.pad[0] = pe.pad[1] = pe.pad[2] = 0;
       A.pending[tile] = pe;
+      A.pending_list[atomicAdd(A.pending_count, 1u)] = (uint32_t)tile;
     }
   }
 }
 
-// One warp per tile of the finished level: resolve the deferred entering excursion (if any) by
-// walking back over the per-tile open-excursion aggregates, 32 tiles per step, to the tile that holds
-// the excursion's start (or to the launch's carry-in).
+// per-group fold of the tile excursion aggregates (a warp per 32 tiles), so that the fix-up below
+// crosses 1024 tiles per step
+__device__ __forceinline__ Ex ex_from(const ExRec &r) {
+  Ex x; x.M = r.M; x.beg = r.beg; x.pk = r.pk; x.reset = r.reset; x.open = r.open; return x;
+}
+__device__ __forceinline__ Ex warp_fold_ex(Ex x, int lane) {  // lane L covers an EARLIER range than lane L-1
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Ex y = shfl_ex(x, (lane + o) & 31);
+    if (lane + o < 32) x = ex_combine(y, x);
+  }
+  return shfl_ex(x, 0);
+}
+__global__ void __launch_bounds__(256) group_ex_kernel(const LevelArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= A.ngroups) return;
+  const int64_t t = g * GROUP_TILES + (31 - lane);  // lane 0 = last tile of the group
+  Ex x = ex_identity();
+  if (t < A.ntiles) x = ex_from(A.tile_ex[t]);
+  Ex f = warp_fold_ex(x, lane);
+  if (lane == 0) {
+    ExRec r;
+    r.M = f.M; r.beg = f.beg; r.pk = f.pk; r.reset = f.reset; r.open = f.open; r.pad[0] = r.pad[1] = 0;
+    A.group_ex[g] = r;
+  }
+}
+
+// One warp per deferred excursion of the finished level: walk back over the open-excursion
+// aggregates -- first the earlier tiles of the own group, then whole groups, 32 per step -- to the one
+// that holds the excursion's start (or to the launch's carry-in).  Grid-stride over the list the walk
+// kernel appended.  The aggregate algebra is associative, so a group aggregate that reports a reset
+// already describes exactly the part of the excursion after its start inside that group.
 __global__ void __launch_bounds__(256) ex_fixup_kernel(const LevelArgs A) {
   const int lane = threadIdx.x & 31;
-  const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (tile >= A.ntiles) return;
-  const ExPending pe = A.pending[tile];
-  if (!pe.valid) return;
-  if (lane == 0) A.pending[tile].valid = 0;
+  const unsigned int n = *A.pending_count;
   ScanParams prm;
   prm.min_width = A.prm->min_width;
   prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
-  Ex acc = ex_identity();
-  int64_t base = tile - 1;
-  for (;;) {
-    int64_t idx = base - lane;
-    Ex x;
-    if (idx >= 0) {
-      ExRec r = A.tile_ex[idx];
-      x.M = r.M; x.beg = r.beg; x.pk = r.pk; x.reset = r.reset; x.open = r.open;
-    } else {  // left of the launch: its carry-in (closed unless a previous shard handed one over)
-      x.M = A.E_start.M; x.beg = A.E_start.beg; x.pk = A.E_start.pk; x.reset = 1; x.open = A.E_start.open;
+  Ex estart;
+  estart.M = A.E_start.M; estart.beg = A.E_start.beg; estart.pk = A.E_start.pk; estart.reset = 1;
+  estart.open = A.E_start.open;
+  for (unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n;
+       i += gridDim.x * (blockDim.x >> 5)) {
+    const int64_t tile = A.pending_list[i];
+    const ExPending pe = A.pending[tile];
+    const int64_t g = tile / GROUP_TILES;
+    // window 1: tiles [32 g, tile) of the own group (ex_combine ignores everything left of a reset)
+    Ex x = ex_identity();
+    {
+      int64_t idx = tile - 1 - lane;
+      if (idx >= g * GROUP_TILES) x = ex_from(A.tile_ex[idx]);
     }
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      Ex y = shfl_ex(x, (lane + o) & 31);
-      if (lane + o < 32) x = ex_combine(y, x);
+    Ex acc = warp_fold_ex(x, lane);
+    // whole groups, newest first, until one holds a reset
+    int64_t gbase = g - 1;
+    while (!acc.reset) {
+      int64_t idx = gbase - lane;
+      Ex y = idx >= 0 ? ex_from(A.group_ex[idx]) : estart;
+      acc = ex_combine(warp_fold_ex(y, lane), acc);
+      gbase -= 32;
     }
-    acc = ex_combine(shfl_ex(x, 0), acc);
-    if (acc.reset) break;
-    base -= 32;
-  }
-  if (lane == 0) {
-    fx_t M = acc.M;
-    int64_t pk = acc.pk;
-    const fx_t Mp = fx_make((uint64_t)pe.m_hi, pe.m_lo);
-    if (Mp > M) { M = Mp; pk = pe.pk; }
-    DevEmit emit{&A};
-    if (acc.open && qualifies(prm, acc.beg, pk, M)) emit(acc.beg, pk, pe.c, M);
+    if (lane == 0) {
+      fx_t M = acc.M;
+      int64_t pk = acc.pk;
+      const fx_t Mp = fx_make((uint64_t)pe.m_hi, pe.m_lo);
+      if (Mp > M) { M = Mp; pk = pe.pk; }
+      DevEmit emit{&A};
+      if (acc.open && qualifies(prm, acc.beg, pk, M)) emit(acc.beg, pk, pe.c, M);
+    }
   }
 }
 
