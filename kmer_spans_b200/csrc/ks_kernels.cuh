@@ -288,9 +288,16 @@ struct DevEmit {
 #ifndef KS_WALK_MINBLOCKS
 #define KS_WALK_MINBLOCKS 6
 #endif
+#ifndef KS_GATHER_MINBLOCKS_TABLE
+#define KS_GATHER_MINBLOCKS_TABLE 3
+#endif
+#ifndef KS_WALK_MINBLOCKS_TABLE
+#define KS_WALK_MINBLOCKS_TABLE 4
+#endif
 
 template <bool kLut>
-__global__ void __launch_bounds__(TILE_THREADS, KS_GATHER_MINBLOCKS) scan_gather_kernel(const LevelArgs A) {
+__global__ void __launch_bounds__(TILE_THREADS, kLut ? KS_GATHER_MINBLOCKS : KS_GATHER_MINBLOCKS_TABLE)
+scan_gather_kernel(const LevelArgs A) {
   __shared__ Xf s_wxf[TILE_WARPS + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile = blockIdx.x;
@@ -517,7 +524,8 @@ struct StashScoresLut {  // scores of one chunk, LUT mode: count from the stash,
 };
 
 template <bool kLut>
-__global__ void __launch_bounds__(TILE_THREADS, KS_WALK_MINBLOCKS) scan_walk_kernel(const LevelArgs A) {
+__global__ void __launch_bounds__(TILE_THREADS, kLut ? KS_WALK_MINBLOCKS : KS_WALK_MINBLOCKS_TABLE)
+scan_walk_kernel(const LevelArgs A) {
   __shared__ Ex s_wex[TILE_WARPS + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile = blockIdx.x;
