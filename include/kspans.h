@@ -127,6 +127,27 @@ int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double par
                     int min_width, double min_score, int32_t *d_counts, double *d_scores,
                     double *n_words, ks_spans *host_out_or_null, uint64_t *n_spans);
 
+/* -------- one sequence set sharded across GPUs (exact stitching of the scan) -----------------------
+ * Every rank uploads (and packs) the whole set, counts and scans only its dense chunk range
+ * [chunk0, chunk0 + nchunks) of the buffer (16 positions per chunk, ks_seqset_chunks() in total) and
+ * exchanges two 48-byte carries: the shard's aggregate max-plus transform and its open-excursion
+ * aggregate.  `fn` is called on the host inside ks_dev_scan*_shard: what = 0 / 1, `mine` = this shard's
+ * 48-byte aggregate; it must fill `carry_in` with what ks_fold_carry() derives from the aggregates of
+ * ALL shards (e.g. after an all-gather).  Spans come back with global coordinates; a span is reported
+ * by the shard in which it closes. */
+typedef int (*ks_exchange_fn)(void *user, int what, const void *mine48, void *carry_in48);
+int64_t ks_seqset_chunks(const ks_seqset *s);
+int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, int64_t nchunks,
+                       int32_t *d_counts, double *n_words);
+int ks_dev_scan_shard(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
+                      double min_score, int64_t chunk0, int64_t nchunks, ks_exchange_fn fn, void *user,
+                      ks_spans *host_out_or_null, uint64_t *n_spans);
+int ks_dev_scan_counts_shard(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
+                             int min_width, double min_score, int64_t chunk0, int64_t nchunks,
+                             ks_exchange_fn fn, void *user, ks_spans *host_out_or_null, uint64_t *n_spans);
+/* host helper: carry entering shard `rank` from the 48-byte aggregates of shards 0..nranks-1 */
+int ks_fold_carry(int what, const void *all48, int nranks, int rank, void *carry_in48);
+
 /* -------- timing on the launching stream (CUDA events; what bench.py reports) ---------------- */
 int ks_ctx_timer_start(ks_ctx *ctx);
 int ks_ctx_timer_stop(ks_ctx *ctx, float *ms); /* records, synchronises, returns elapsed ms */

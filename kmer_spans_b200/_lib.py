@@ -26,6 +26,7 @@ class KspansError(RuntimeError):
 
 
 _lib = None
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
 
 _vp, _i, _d, _i64 = C.c_void_p, C.c_int, C.c_double, C.c_int64
 _pd = C.POINTER(C.c_double)
@@ -63,6 +64,11 @@ SIGNATURES = {
     "ks_dev_scores": (_i, [_vp, _i, _vp, _d, _i, _d, _vp]),
     "ks_dev_scan": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, _vp, C.POINTER(KsSpans), _pu64]),
     "ks_dev_scan_counts": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, C.POINTER(KsSpans), _pu64]),
+    "ks_seqset_chunks": (_i64, [_vp]),
+    "ks_dev_count_range": (_i, [_vp, _vp, _i, _i64, _i64, _vp, _pd]),
+    "ks_dev_scan_shard": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, _i64, _i64, _vp, _vp, C.POINTER(KsSpans), _pu64]),
+    "ks_dev_scan_counts_shard": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, _i64, _i64, _vp, _vp, C.POINTER(KsSpans), _pu64]),
+    "ks_fold_carry": (_i, [_i, _vp, _i, _i, _vp]),
     "ks_dev_pipeline": (_i, [_vp, _vp, _i, _i, _d, _d, _i, _d, _vp, _vp, _pd, C.POINTER(KsSpans), _pu64]),
 }
 

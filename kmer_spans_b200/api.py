@@ -173,6 +173,34 @@ class Context:
             res["pos"], res["score"] = _spans_to_numpy(self.lib, sp)
         return res
 
+    # ---- one set sharded over several GPUs (exact stitching) -----------------------------------
+    def dev_count_range(self, ss, k, chunk0, nchunks, d_counts):
+        n = C.c_double(0)
+        self._ck(self.lib.ks_dev_count_range(self.h, ss.h, int(k), int(chunk0), int(nchunks), d_counts, C.byref(n)))
+        return n.value
+
+    def dev_scan_shard(self, ss, k, table_ptr, thr, min_w, min_score, chunk0, nchunks, exchange, use_counts=False):
+        """Level 0 restricted to dense chunks [chunk0, chunk0 + nchunks); `exchange(what, mine48) -> carry48`
+        is called twice on the host (what = 0 transform, 1 open excursion) and must return what
+        fold_carry() derives from the aggregates of all shards."""
+        def cb(user, what, mine, carry):
+            try:
+                out = exchange(int(what), C.string_at(mine, 48))
+                C.memmove(carry, out, 48)
+                return 0
+            except Exception:  # pragma: no cover - surfaced as a C-side error
+                import traceback
+                traceback.print_exc()
+                return 1
+        cfn = _lib.EXCHANGE_FN(cb)
+        ns = C.c_uint64(0)
+        sp = KsSpans()
+        fn = self.lib.ks_dev_scan_counts_shard if use_counts else self.lib.ks_dev_scan_shard
+        self._ck(fn(self.h, ss.h, int(k), table_ptr, float(thr), int(min_w), float(min_score), int(chunk0),
+                    int(nchunks), C.cast(cfn, C.c_void_p), None, C.byref(sp), C.byref(ns)))
+        pos, score = _spans_to_numpy(self.lib, sp)
+        return dict(n_spans=int(ns.value), pos=pos, score=score)
+
     # ---- mirrors of the reference's R functions -------------------------------------------
     def kmer_counts(self, seq, k, with_f=True):
         """kmer.counts (kmer_spans.R:18-27): list(n = c(k, n), counts, f = counts / sum(counts))"""
@@ -265,6 +293,7 @@ class SeqSet:
         ctx._ck(ctx.lib.ks_seqset_upload(ctx.h, a.ptrs, a.lens, a.n, C.byref(h)))
         self.h = h
         self.bases = int(ctx.lib.ks_seqset_bases(h))
+        self.chunks = int(ctx.lib.ks_seqset_chunks(h))
         self.buffer_bytes = int(ctx.lib.ks_seqset_buffer_bytes(h))
 
     def free(self):
@@ -277,6 +306,17 @@ class SeqSet:
             self.free()
         except Exception:
             pass
+
+
+def fold_carry(what, blobs, rank):
+    """carry entering shard `rank` from the 48-byte aggregates of all shards (host, exact)"""
+    lib = _lib.load()
+    allb = b"".join(blobs)
+    out = C.create_string_buffer(48)
+    rc = lib.ks_fold_carry(int(what), allb, len(blobs), int(rank), out)
+    if rc:
+        raise KspansError(rc, "ks_fold_carry")
+    return out.raw
 
 
 def kmer_seq(k):

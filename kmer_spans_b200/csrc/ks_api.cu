@@ -106,7 +106,7 @@ struct ks_ctx {
   void *pinned = nullptr;
   size_t pinned_cap = 0;
   DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, dbg, pending, foc_hist, foc_big;
-  DBuf st_c, st_s, st_ea, st_eb, st_flags, st_p0, tile_xf, tile_ex, group_xf, group_S, group_ex, pending_list, pending_count;
+  DBuf st_c, st_s, st_ea, st_eb, st_flags, st_p0, tile_xf, tile_ex, group_xf, group_S, group_ex, pending_list, pending_count, launch_rec;
 
   // timing / profiling
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -229,7 +229,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->out_score, &ctx->sc_keys_a, &ctx->sc_keys_b, &ctx->sc_vals_a, &ctx->sc_vals_b,
                  &ctx->sc_small, &ctx->sc_gcount, &ctx->sc_gstart, &ctx->sc_segfirst, &ctx->sc_segj0,
                  &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->tmp_counts, &ctx->tmp_scores,
-                 &ctx->tmp_inscan, &ctx->nwords, &ctx->dbg, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
+                 &ctx->tmp_inscan, &ctx->nwords, &ctx->dbg, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->launch_rec, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -558,6 +558,52 @@ int ks_dev_count(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, doub
   return KS_OK;
 }
 
+int64_t ks_seqset_chunks(const ks_seqset *s) { return s ? (s->total - 16) / 16 : 0; }
+
+int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, int64_t nchunks,
+                       int32_t *d_counts, double *n_words) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!s || !d_counts) return ctx->fail(KS_ERR_ARG, "ks_dev_count_range: null argument");
+  int rc = check_k(ctx, k);
+  if (rc) return rc;
+  const int64_t total = (s->total - 16) / 16;
+  if (chunk0 < 0 || nchunks < 0 || chunk0 + nchunks > total) return ctx->fail(KS_ERR_ARG, "chunk range outside the buffer");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  size_t n = (size_t)1 << (2 * k);
+  CK(ctx->nwords.ensure(sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(d_counts, 0, n * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
+  cudaEvent_t pe = ctx->prof_begin();
+  if (nchunks) {
+    pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
+        s->d_buf, chunk0, nchunks, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, d_counts,
+        ctx->nwords.as<unsigned long long>());
+    LAUNCHED(1);
+  }
+  if (!s->packed) {  // the scan of every shard reads packed data beyond its own range: pack the rest
+    if (chunk0 > 0) {
+      pack_count_kernel<false><<<grid_for((size_t)chunk0, 256, 148u * 8u), 256, 0, st>>>(
+          s->d_buf, 0, chunk0, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, nullptr, nullptr);
+      LAUNCHED(1);
+    }
+    if (chunk0 + nchunks < total) {
+      pack_count_kernel<false><<<grid_for((size_t)(total - chunk0 - nchunks), 256, 148u * 8u), 256, 0, st>>>(
+          s->d_buf, chunk0 + nchunks, total - chunk0 - nchunks, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, nullptr,
+          nullptr);
+      LAUNCHED(1);
+    }
+  }
+  ctx->prof_end(KS_PROF_COUNT, pe);
+  CK(cudaGetLastError());
+  s->packed = true;
+  unsigned long long nw = 0;
+  CK(cudaMemcpyAsync(&nw, ctx->nwords.p, sizeof nw, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (n_words) *n_words = (double)nw;
+  return KS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // stage: score tables
 int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int mode, double param,
@@ -823,6 +869,16 @@ static int ensure_recs(ks_ctx *ctx, size_t cap) {
 }
 
 namespace {
+// Level 0 restricted to the dense chunks [chunk0, chunk0 + nchunks) of the buffer (one shard of a
+// multi-GPU run).  The carries are exchanged through `fn` on the host between the kernels: what = 0
+// hands over the shard's aggregate transform and asks for the state entering the shard, what = 1 the
+// shard's open-excursion aggregate and asks for the one entering it (ks_fold_carry computes both from
+// the gathered aggregates of all shards).
+struct ShardCtl {
+  int64_t chunk0 = 0, nchunks = 0;
+  ks_exchange_fn fn = nullptr;
+  void *user = nullptr;
+};
 struct ScanTable {  // what scan_level_kernel gathers from
   bool use_lut = false;
   const uint32_t *counts = nullptr;
@@ -833,7 +889,7 @@ struct ScanTable {  // what scan_level_kernel gathers from
 // Level loop + ordering + marshaling.  The fixed-point table (ctx->wfx, or ctx->lut_fx + sparse list)
 // and the DevScanParams block (ctx->prm) have been prepared on the stream by the caller.
 static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &tab, uint64_t mw,
-                     int32_t *d_inscan, ks_spans *host_out, uint64_t *n_spans) {
+                     int32_t *d_inscan, ks_spans *host_out, uint64_t *n_spans, const ShardCtl *sh = nullptr) {
   int rc = KS_OK;
   cudaStream_t st = ctx->stream;
   const size_t nk = (size_t)1 << (2 * k);
@@ -860,12 +916,25 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
 
   unsigned long long level_start = 0;  // records before this level
   int64_t nseg = 0, total_chunks = dense_chunks;
+  int64_t dense_chunk0 = 0;
+  if (sh) {
+    if (sh->chunk0 < 0 || sh->nchunks < 0 || sh->chunk0 + sh->nchunks > dense_chunks)
+      return ctx->fail(KS_ERR_ARG, "shard range outside the buffer");
+    dense_chunk0 = sh->chunk0;
+    total_chunks = sh->nchunks;
+    CK(ctx->launch_rec.ensure(256));
+  }
+  bool have_carry = false;  // the exchange runs once, also if level 0 has to be repeated with more room
+  fx_t S_carry = 0;
+  ExRec E_carry;
+  memset(&E_carry, 0, sizeof E_carry);
   int level = 0;
   uint64_t revisit_chunks = 0;
   bool count_inscan = d_inscan != nullptr;
   for (;;) {
     size_t tiles = (size_t)((total_chunks + TILE_THREADS - 1) / TILE_THREADS);
-    if (tiles == 0) break;
+    if (tiles == 0 && !(sh && level == 0)) break;
+    if (tiles == 0) tiles = 1;  // an empty shard still takes part in the carry exchange
     if (tiles > 0xfffffff0ull) return ctx->fail(KS_ERR_ARG, "input too large for one scan launch");
     rc = ensure_tiles(ctx, tiles, tab.use_lut, nseg != 0);
     if (rc) return rc;
@@ -888,8 +957,10 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.seg_start = ctx->seg_start.as<int64_t>();
     A.seg_len = ctx->seg_len.as<int64_t>();
     A.seg_chunk0 = ctx->seg_chunk0.as<uint64_t>();
-    A.dense_start = 16;
+    A.dense_start = 16 + 16 * dense_chunk0;
     A.total_chunks = total_chunks;
+    A.dense_first = dense_chunk0 == 0;
+    const bool exchange = sh && level == 0;
     A.inscan = count_inscan ? d_inscan : nullptr;
     A.Q = (int64_t)(tiles * TILE_THREADS);
     A.st_c = ctx->st_c.as<uint32_t>();
@@ -911,7 +982,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.S_start = 0;
     A.E_start.M = -(((fx_t)1) << 126);
     A.E_start.beg = -1; A.E_start.pk = -1; A.E_start.reset = 1; A.E_start.open = 0;
-    A.launch_xf = nullptr;
+    A.launch_xf = exchange ? ctx->launch_rec.as<XfRec>() : nullptr;
+    A.launch_ex = exchange ? reinterpret_cast<ExRec *>(ctx->launch_rec.as<char>() + 64) : nullptr;
     A.rec_beg = ctx->rec_beg.as<int64_t>();
     A.rec_pk = ctx->rec_pk.as<int64_t>();
     A.rec_c = ctx->rec_c.as<int64_t>();
@@ -924,9 +996,42 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     else scan_gather_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     group_scan_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
     group_top_kernel<<<1, TSCAN_THREADS, 0, st>>>(A);
+    if (exchange && have_carry) {
+      A.S_start = S_carry;
+      A.launch_xf = nullptr;
+      group_top_kernel<<<1, TSCAN_THREADS, 0, st>>>(A);
+      LAUNCHED(1);
+    } else if (exchange) {  // hand the shard's aggregate transform over, receive the state entering the shard
+      XfRec mine;
+      CK(cudaMemcpyAsync(&mine, A.launch_xf, sizeof mine, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      unsigned char carry[48];
+      memset(carry, 0, sizeof carry);
+      if (sh->fn(sh->user, 0, &mine, carry)) return ctx->fail(KS_ERR_ARG, "shard exchange (transform) failed");
+      memcpy(&A.S_start, carry, sizeof(fx_t));
+      S_carry = A.S_start;
+      A.launch_xf = nullptr;
+      group_top_kernel<<<1, TSCAN_THREADS, 0, st>>>(A);
+      LAUNCHED(1);
+    }
     if (tab.use_lut) scan_walk_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else scan_walk_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     group_ex_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
+    if (exchange && have_carry) {
+      A.E_start = E_carry;
+    } else if (exchange) {  // the same for the open-excursion state
+      ex_top_kernel<<<1, 32, 0, st>>>(A);
+      LAUNCHED(1);
+      ExRec mine;
+      CK(cudaMemcpyAsync(&mine, A.launch_ex, sizeof mine, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      unsigned char carry[48];
+      memset(carry, 0, sizeof carry);
+      if (sh->fn(sh->user, 1, &mine, carry)) return ctx->fail(KS_ERR_ARG, "shard exchange (excursion) failed");
+      memcpy(&A.E_start, carry, sizeof(ExRec));
+      E_carry = A.E_start;
+      have_carry = true;
+    }
     ex_fixup_kernel<<<148, 256, 0, st>>>(A);
     ctx->prof_end(level == 0 ? KS_PROF_SCAN0 : KS_PROF_SCANN, ps);
     LAUNCHED(6);
@@ -1026,8 +1131,9 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
   return KS_OK;
 }
 
-int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
-                double min_score, int32_t *d_inscan, ks_spans *host_out, uint64_t *n_spans) {
+static int scan_table_impl(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
+                           double min_score, int32_t *d_inscan, ks_spans *host_out, uint64_t *n_spans,
+                           const ShardCtl *sh) {
   if (!ctx) return KS_ERR_ARG;
   if (!s || !d_W) return ctx->fail(KS_ERR_ARG, "ks_dev_scan: null argument");
   int rc = check_k(ctx, k);
@@ -1050,14 +1156,30 @@ int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, doubl
   LAUNCHED(2);
   CK(cudaGetLastError());
   ScanTable tab;
-  return scan_core(ctx, s, k, tab, mw, d_inscan, host_out, n_spans);
+  return scan_core(ctx, s, k, tab, mw, d_inscan, host_out, n_spans, sh);
+}
+
+int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
+                double min_score, int32_t *d_inscan, ks_spans *host_out, uint64_t *n_spans) {
+  return scan_table_impl(ctx, s, k, d_W, thr, min_width, min_score, d_inscan, host_out, n_spans, nullptr);
+}
+
+int ks_dev_scan_shard(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
+                      double min_score, int64_t chunk0, int64_t nchunks, ks_exchange_fn fn, void *user,
+                      ks_spans *host_out, uint64_t *n_spans) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!fn) return ctx->fail(KS_ERR_ARG, "ks_dev_scan_shard: null exchange function");
+  ShardCtl sh;
+  sh.chunk0 = chunk0; sh.nchunks = nchunks; sh.fn = fn; sh.user = user;
+  return scan_table_impl(ctx, s, k, d_W, thr, min_width, min_score, nullptr, host_out, n_spans, &sh);
 }
 
 // Scan with score = f(count): the count -> score function is the one the last
 // ks_dev_scores(mode LOG2 | SIGN) on this ctx derived (cached per distinct count on the host).
 // The kernel gathers the 4-byte count (table stays L2 resident up to k = 12) instead of an 8-byte score.
-int ks_dev_scan_counts(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
-                       int min_width, double min_score, ks_spans *host_out, uint64_t *n_spans) {
+static int scan_counts_impl(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
+                            int min_width, double min_score, ks_spans *host_out, uint64_t *n_spans,
+                            const ShardCtl *sh) {
   if (!ctx) return KS_ERR_ARG;
   if (!s || !d_counts) return ctx->fail(KS_ERR_ARG, "ks_dev_scan_counts: null argument");
   int rc = check_k(ctx, k);
@@ -1114,7 +1236,54 @@ int ks_dev_scan_counts(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_
   tab.counts = reinterpret_cast<const uint32_t *>(d_counts);
   tab.lut_size = lut_size;
   tab.sp_n = sp_n;
-  return scan_core(ctx, s, k, tab, mw, nullptr, host_out, n_spans);
+  return scan_core(ctx, s, k, tab, mw, nullptr, host_out, n_spans, sh);
+}
+
+int ks_dev_scan_counts(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
+                       int min_width, double min_score, ks_spans *host_out, uint64_t *n_spans) {
+  return scan_counts_impl(ctx, s, k, d_counts, thr, min_width, min_score, host_out, n_spans, nullptr);
+}
+
+int ks_dev_scan_counts_shard(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
+                             int min_width, double min_score, int64_t chunk0, int64_t nchunks,
+                             ks_exchange_fn fn, void *user, ks_spans *host_out, uint64_t *n_spans) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!fn) return ctx->fail(KS_ERR_ARG, "ks_dev_scan_counts_shard: null exchange function");
+  ShardCtl sh;
+  sh.chunk0 = chunk0; sh.nchunks = nchunks; sh.fn = fn; sh.user = user;
+  return scan_counts_impl(ctx, s, k, d_counts, thr, min_width, min_score, host_out, n_spans, &sh);
+}
+
+// carry entering shard `rank`: fold of the aggregates of shards 0 .. rank-1 (host, exact integers)
+int ks_fold_carry(int what, const void *all48, int nranks, int rank, void *carry_in48) {
+  if (!all48 || !carry_in48 || rank < 0 || rank > nranks) return KS_ERR_ARG;
+  memset(carry_in48, 0, 48);
+  if (what == 0) {
+    const XfRec *r = reinterpret_cast<const XfRec *>(all48);
+    Xf f = xf_identity();
+    for (int i = 0; i < rank; ++i) {
+      Xf g; g.a = r[i].a; g.b = r[i].b; g.kill = r[i].kill;
+      f = xf_compose(f, g);
+    }
+    fx_t S = xf_apply(f, 0);
+    memcpy(carry_in48, &S, sizeof S);
+    return KS_OK;
+  }
+  if (what == 1) {
+    const ExRec *r = reinterpret_cast<const ExRec *>(all48);
+    Ex acc = ex_identity();
+    acc.reset = 1; acc.open = 0;  // left of the first shard nothing is open
+    for (int i = 0; i < rank; ++i) {
+      Ex g; g.M = r[i].M; g.beg = r[i].beg; g.pk = r[i].pk; g.reset = r[i].reset; g.open = r[i].open;
+      acc = ex_combine(acc, g);
+    }
+    ExRec out;
+    memset(&out, 0, sizeof out);
+    out.M = acc.M; out.beg = acc.beg; out.pk = acc.pk; out.reset = 1; out.open = acc.open;
+    memcpy(carry_in48, &out, sizeof out);
+    return KS_OK;
+  }
+  return KS_ERR_ARG;
 }
 
 int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double param, double thr, int min_width,

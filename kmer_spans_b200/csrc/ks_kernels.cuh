@@ -237,9 +237,11 @@ struct LevelArgs {
   const int64_t *seg_start;
   const int64_t *seg_len;
   const uint64_t *seg_chunk0;
-  // level 0 (nseg == 0): dense pass over [dense_start, dense_start + 16 * total_chunks)
+  // level 0 (nseg == 0): dense pass over [dense_start, dense_start + 16 * total_chunks); dense_first = the
+  // range starts the buffer (state 0); otherwise it continues a previous shard (carry-in S_start, E_start)
   int64_t dense_start;
   int64_t total_chunks;
+  int dense_first;
   int32_t *inscan;  // or NULL
   // stash, indexed by work chunk q (Q = ntiles * TILE_THREADS): element j of chunk q at [j * Q + q]
   int64_t Q;
@@ -260,7 +262,8 @@ struct LevelArgs {
   // carry-in of the whole launch (0 / closed unless a previous shard hands them over)
   fx_t S_start;
   ExRec E_start;
-  XfRec *launch_xf;     // out: aggregate transform of the launch (tile_scan_kernel), or NULL
+  XfRec *launch_xf;     // out: aggregate transform of the launch (group_top_kernel), or NULL
+  ExRec *launch_ex;     // out: open-excursion aggregate of the launch (ex_top_kernel), or NULL
   // emitted records (SoA), appended across levels
   int64_t *rec_beg, *rec_pk, *rec_c, *rec_mhi;
   uint64_t *rec_mlo;
@@ -308,7 +311,7 @@ scan_gather_kernel(const LevelArgs A) {
   bool head = true;
   if (q < A.total_chunks) {
     if (A.nseg == 0) {
-      p0 = A.dense_start + 16 * q; n_in = 16; head = (q == 0);
+      p0 = A.dense_start + 16 * q; n_in = 16; head = (q == 0 && A.dense_first);
     } else {
       int64_t lo = 0, hi = A.nseg;  // largest s in [0, nseg) with seg_chunk0[s] <= q
       while (hi - lo > 1) {
@@ -402,6 +405,10 @@ scan_gather_kernel(const LevelArgs A) {
   Xf f;
   f.a = (fx_t)ta; f.b = (fx_t)tb; f.kill = tkill;
   if (head) { fx_t v = xf_apply(f, 0); f.kill = 1; f.a = 0; f.b = v; }
+  // padding chunks behind the last real chunk of the launch must be transparent: the aggregates of a
+  // shard are handed to the next one
+  const bool vchunk = q >= A.total_chunks;
+  if (vchunk) f = xf_identity();
   // ---- block scan of the chunk transforms ----
   Xf inc = f;
 #pragma unroll
@@ -433,7 +440,7 @@ scan_gather_kernel(const LevelArgs A) {
   excl = xf_compose(s_wxf[warp], excl);
   A.st_ea[q] = excl.a;
   A.st_eb[q] = excl.b;
-  A.st_flags[q] = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u);
+  A.st_flags[q] = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u) | (vchunk ? 0x40000u : 0u);
   if (A.nseg != 0) A.st_p0[q] = p0;
 }
 
@@ -561,7 +568,12 @@ scan_walk_kernel(const LevelArgs A) {
   fx_t preM;
   int64_t prePk;
   int first_zero;
-  chunk_walk(s, live, S_in, p0, prm, emit, ex, preM, prePk, first_zero);
+  if (fl & 0x40000u) {  // padding chunk: transparent
+    ex = ex_identity();
+    preM = ex.M; prePk = -1; first_zero = -1;
+  } else {
+    chunk_walk(s, live, S_in, p0, prm, emit, ex, preM, prePk, first_zero);
+  }
   Ex einc = ex;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -636,6 +648,22 @@ __global__ void __launch_bounds__(256) group_ex_kernel(const LevelArgs A) {
     ExRec r;
     r.M = f.M; r.beg = f.beg; r.pk = f.pk; r.reset = f.reset; r.open = f.open; r.pad[0] = r.pad[1] = 0;
     A.group_ex[g] = r;
+  }
+}
+
+// fold of all group excursion aggregates of the launch (one warp): what the next shard needs as E_start
+__global__ void __launch_bounds__(32) ex_top_kernel(const LevelArgs A) {
+  const int lane = threadIdx.x;
+  Ex acc = ex_identity();
+  for (int64_t base = A.ngroups - 1; base >= 0 && !acc.reset; base -= 32) {
+    int64_t idx = base - lane;
+    Ex y = idx >= 0 ? ex_from(A.group_ex[idx]) : ex_identity();
+    acc = ex_combine(warp_fold_ex(y, lane), acc);
+  }
+  if (lane == 0 && A.launch_ex) {
+    ExRec r;
+    r.M = acc.M; r.beg = acc.beg; r.pk = acc.pk; r.reset = acc.reset; r.open = acc.open; r.pad[0] = r.pad[1] = 0;
+    *A.launch_ex = r;
   }
 }
 

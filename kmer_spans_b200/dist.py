@@ -117,3 +117,42 @@ def run_sharded(stages, dist, seqs_local, local_ids, k, mode, min_w, min_score, 
         dist.all_gather_object(parts, (pos, score))
         pos, score = merge_spans(parts)
     return dict(n=total, counts=counts, pos=pos, score=score)
+
+
+# --------------------------------------------------------------------------------------------------
+# One sequence set split ACROSS GPUs at arbitrary chunk boundaries (a chromosome longer than a fair
+# share): every rank uploads and packs the whole set, counts and scans only its dense chunk range, and
+# the scan is stitched exactly through two 48-byte carries per rank.
+def shard_range(total_chunks, world, rank):
+    per = -(-total_chunks // world)
+    c0 = min(rank * per, total_chunks)
+    return c0, min(per, total_chunks - c0)
+
+
+def run_split(ctx, seqs, k, mode, min_w, min_score, thr, param, rank, world, all_gather_bytes, all_reduce_counts):
+    """count(range) -> all_reduce -> scores -> sharded scan with carry exchange.
+    all_gather_bytes(blob48) -> [blob48 of every rank];  all_reduce_counts(torch int32 tensor, n) -> total n.
+    Returns this rank's spans (global coordinates; a span is reported where it closes)."""
+    import torch
+    from . import api
+    ss = ctx.upload(seqs)
+    c0, cn = shard_range(ss.chunks, world, rank)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    counts = torch.zeros(4 ** k, dtype=torch.int32, device=dev)
+    scores = torch.empty(4 ** k, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    n = ctx.dev_count_range(ss, k, c0, cn, counts.data_ptr())
+    total = all_reduce_counts(counts, n)
+    torch.cuda.synchronize()
+    ctx.dev_scores(k, counts.data_ptr(), total, mode, scores.data_ptr(), param)
+
+    def exchange(what, mine):
+        return api.fold_carry(what, all_gather_bytes(mine), rank)
+
+    use_counts = mode in (1, 2)
+    r = ctx.dev_scan_shard(ss, k, counts.data_ptr() if use_counts else scores.data_ptr(), thr, min_w, min_score,
+                           c0, cn, exchange, use_counts=use_counts)
+    r["n"] = total
+    r["counts"] = counts
+    ss.free()
+    return r

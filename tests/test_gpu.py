@@ -307,3 +307,65 @@ def test_errors(ctx):
     assert ei.value.code == 3
     r = ctx.kmer_regions([b"ACGTACGTAGAGAGAG"], 2, np.zeros(16), 1, 1.0)  # usable after an error
     assert len(r["pos"]) == 0 and r["pos"].shape == (0, 3) and r["score"].shape == (0, 2)
+
+
+# ---- one sequence set split across GPUs: exact stitching -----------------------------------------
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_split_scan_stitches_exactly(ctx, oracle, world):
+    """Virtual ranks on one GPU (one Context and one thread each; the carries meet at a barrier as they
+    would in an all-gather): counts all-reduced, level-0 scan cut at arbitrary chunk boundaries, spans
+    that cross the cuts -- including run-sized excursions in +-1 mode -- must equal the unsharded result."""
+    import threading
+    import torch
+    from kmer_spans_b200 import api
+    from kmer_spans_b200 import dist as ksd
+    rng = np.random.default_rng(4000 + world)
+    seqs = [planted(rng, 60000), planted(rng, 9000), b"ACGTN" * 5, planted(rng, 33000)]
+    for k, mode, thr, mw, ms in ((6, 0, 0.6, 10, 3), (8, 2, 0.0, 50, 10), (5, 1, 0.0, 0, 0)):
+        want = oracle.mode_regions(seqs, k, mode, mw, ms, thr=thr)
+        ctxs = [api.Context() for _ in range(world)]
+        barrier = threading.Barrier(world)
+        blobs = [None] * world
+        tables = [None] * world
+        ns = [0.0] * world
+        out = [None] * world
+        errs = []
+
+        def worker(r):
+            try:
+                def all_gather_bytes(b):
+                    blobs[r] = b
+                    barrier.wait()
+                    got = list(blobs)
+                    barrier.wait()
+                    return got
+
+                def all_reduce_counts(t, n):
+                    tables[r], ns[r] = t, n
+                    barrier.wait()
+                    if r == 0:
+                        tot = torch.stack(tables).sum(0).to(torch.int32)
+                        for x in tables:
+                            x.copy_(tot)
+                        torch.cuda.synchronize()
+                    barrier.wait()
+                    return float(sum(ns))
+
+                out[r] = ksd.run_split(ctxs[r], seqs, k, mode, mw, ms, thr, float("nan"), r, world,
+                                       all_gather_bytes, all_reduce_counts)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+                barrier.abort()
+
+        th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(120)
+        assert not errs, errs
+        assert (out[0]["counts"].cpu().numpy() == want["counts"]).all()
+        pos, score = ksd.merge_spans([(o["pos"], o["score"]) for o in out])
+        got = dict(pos=pos, score=score)
+        assert_spans(got, want, exact_scores=(mode == 2), what="world=%d k=%d mode=%d" % (world, k, mode))
+        for c in ctxs:
+            c.close()
