@@ -156,3 +156,28 @@ def run_split(ctx, seqs, k, mode, min_w, min_score, thr, param, rank, world, all
     r["counts"] = counts
     ss.free()
     return r
+
+
+def run_split_nccl(ctx, dist, seqs, k, mode, min_w, min_score, thr=0.0, param=float("nan"), gather=True):
+    """run_split with torch.distributed: NCCL all_reduce of the count table, the two 48-byte carries
+    through all_gather_object (host side, once each per scan)."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+
+    def all_gather_bytes(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+
+    def all_reduce_counts(t, n):
+        nt = torch.tensor([n], dtype=torch.float64, device=t.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(nt, op=dist.ReduceOp.SUM)
+        return float(nt.item())
+
+    r = run_split(ctx, seqs, k, mode, min_w, min_score, thr, param, rank, world, all_gather_bytes, all_reduce_counts)
+    if gather:
+        parts = [None] * world
+        dist.all_gather_object(parts, (r["pos"], r["score"]))
+        r["pos"], r["score"] = merge_spans(parts)
+    return r
