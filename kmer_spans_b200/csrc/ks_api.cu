@@ -174,6 +174,17 @@ static inline unsigned grid_for(size_t n, int threads, unsigned cap = 148u * 16u
 }
 static inline unsigned blocks_exact(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// passes of the counting kernel: slices of at most 64 MiB of the table per pass (16 at most)
+static void count_parts(int k, int *nparts, int *part_shift) {
+  size_t bytes = ((size_t)4) << (2 * k);
+  int lg = 0;
+  while ((bytes >> lg) > ((size_t)64 << 20) && lg < 4) ++lg;
+  if (lg & 1) ++lg;  // whole bases
+  if (lg > 4) lg = 4;
+  *nparts = 1 << lg;
+  *part_shift = lg ? 2 * k - lg : 32;
+}
+
 static int check_k(ks_ctx *ctx, int k) {
   if (k < 1 || k > 15) return ctx->fail(KS_ERR_ARG, "k must be a positive integer less than 16 (got %d)", k);
   return KS_OK;
@@ -385,6 +396,8 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
     CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
   }
   const int64_t nchunks = (s->total - 16) / 16;
+  int cparts = 1, cparts_shift = 32;
+  if (count_k) count_parts(count_k, &cparts, &cparts_shift);
   int64_t done = 0;  // chunks [0, done) of the count grid are launched
   const int64_t SLAB = (24ll << 20) / 16;
   auto progress = [&](int64_t covered, bool final) -> cudaError_t {
@@ -399,7 +412,7 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
     cudaEvent_t pe = ctx->prof_begin();
     pack_count_kernel<true><<<grid_for((size_t)(avail - done), 256, 148u * 8u), 256, 0, st>>>(
         s->d_buf, done, avail - done, count_k, (uint32_t)(nk - 1), s->d_pk, s->d_brk, d_counts,
-        ctx->nwords.as<unsigned long long>());
+        ctx->nwords.as<unsigned long long>(), cparts_shift, 0u);
     ctx->prof_end(KS_PROF_COUNT, pe);
     ctx->launches += 1;
     done = avail;
@@ -463,6 +476,13 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
   if (e == cudaSuccess) e = progress(s->total, true);
   if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copy, cs);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->ev_copy, 0);  // later kernels see the whole buffer
+  for (int part = 1; part < cparts && e == cudaSuccess; ++part) {  // tables beyond L2: remaining slices
+    pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
+        s->d_buf, 0, nchunks, count_k, (uint32_t)(nk - 1), s->d_pk, s->d_brk, d_counts,
+        ctx->nwords.as<unsigned long long>(), cparts_shift, (uint32_t)part);
+    ctx->launches += 1;
+    e = cudaGetLastError();
+  }
   if (e == cudaSuccess && ev_used[0]) e = cudaEventSynchronize(ev[0]);  // staging halves are re-used next call
   if (e == cudaSuccess && ev_used[1]) e = cudaEventSynchronize(ev[1]);
   cudaEventDestroy(ev[0]);
@@ -545,8 +565,14 @@ int ks_dev_count(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, doub
   CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
   int64_t nchunks = (s->total - 16) / 16;
   cudaEvent_t pe = ctx->prof_begin();
-  pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
-      s->d_buf, 0, nchunks, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, d_counts, ctx->nwords.as<unsigned long long>());
+  int nparts, part_shift;
+  count_parts(k, &nparts, &part_shift);
+  for (int part = 0; part < nparts; ++part) {
+    pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
+        s->d_buf, 0, nchunks, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, d_counts,
+        ctx->nwords.as<unsigned long long>(), part_shift, (uint32_t)part);
+    LAUNCHED(part ? 1 : 0);
+  }
   ctx->prof_end(KS_PROF_COUNT, pe);
   s->packed = true;
   LAUNCHED(1);
@@ -576,10 +602,14 @@ int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, i
   CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
   cudaEvent_t pe = ctx->prof_begin();
   if (nchunks) {
-    pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
-        s->d_buf, chunk0, nchunks, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, d_counts,
-        ctx->nwords.as<unsigned long long>());
-    LAUNCHED(1);
+    int nparts, part_shift;
+    count_parts(k, &nparts, &part_shift);
+    for (int part = 0; part < nparts; ++part) {
+      pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
+          s->d_buf, chunk0, nchunks, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, d_counts,
+          ctx->nwords.as<unsigned long long>(), part_shift, (uint32_t)part);
+      LAUNCHED(1);
+    }
   }
   if (!s->packed) {  // the scan of every shard reads packed data beyond its own range: pack the rest
     if (chunk0 > 0) {

@@ -95,13 +95,18 @@ __device__ __forceinline__ Ex shfl_ex(const Ex &e, int src) {
 // threads read consecutive 16-byte vectors (512 B per warp request).  Writes the 2-bit packed codes
 // (4 B per 16 bases) and the break mask (2 B per 16 bases) that every scan pass reads instead of the
 // ASCII, and (kCount) reduces the k-mer ending at every position into the int32[4^k] table.
+// Tables larger than L2 (k >= 13) are counted in several passes over the sequence, each pass taking only
+// the codes whose leading bits equal `part_id` (part_shift = 2k - log2(#parts)), so that the slice of the
+// table a pass touches stays L2 resident: random reductions run at 190 G/s into a resident slice but at
+// 33 G/s into a 256 MiB table (profiles/r01_unit_peaks.json).  Only the first pass writes the packed output.
 template <bool kCount>
 __global__ void __launch_bounds__(256) pack_count_kernel(const uint8_t *__restrict__ buf, int64_t first,
                                                          int64_t nchunks, int k, uint32_t kmask,
                                                          uint32_t *__restrict__ pk_out,
                                                          uint16_t *__restrict__ brk_out,
                                                          int32_t *__restrict__ counts,
-                                                         unsigned long long *__restrict__ nwords) {
+                                                         unsigned long long *__restrict__ nwords,
+                                                         int part_shift = 32, uint32_t part_id = 0) {
   unsigned long long local = 0;
   const uint64_t keep = l2_policy_evict_last();
   for (int64_t ci = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ci < first + nchunks;
@@ -113,14 +118,21 @@ __global__ void __launch_bounds__(256) pack_count_kernel(const uint8_t *__restri
     uint32_t pkp, bp, np, pkc, bc, nc;
     pack16(wp, pkp, bp, np);
     pack16(wc, pkc, bc, nc);
-    pk_out[ci + 1] = pkc;
-    brk_out[ci + 1] = (uint16_t)bc;
-    if (ci == 0) { pk_out[0] = pkp; brk_out[0] = (uint16_t)bp; }
+    if (part_id == 0) {
+      pk_out[ci + 1] = pkc;
+      brk_out[ci + 1] = (uint16_t)bc;
+      if (ci == 0) { pk_out[0] = pkp; brk_out[0] = (uint16_t)bp; }
+    }
     if (kCount) {
       uint32_t next = __ldg(p + 32);
       uint32_t code[CHUNK], counted;
       decode_count(((uint64_t)pkp << 32) | pkc, bp | (bc << 16), np | (nc << 16), next == 0u, k, kmask, code,
                    counted);
+      if (part_shift < 32) {  // keep only this pass's slice of the table
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j)
+          if ((code[j] >> part_shift) != part_id) counted &= ~(1u << j);
+      }
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j)
         if (counted & (1u << j)) red_add_u32_keep(&counts[code[j]], 1u, keep);

@@ -369,3 +369,18 @@ def test_split_scan_stitches_exactly(ctx, oracle, world):
         assert_spans(got, want, exact_scores=(mode == 2), what="world=%d k=%d mode=%d" % (world, k, mode))
         for c in ctxs:
             c.close()
+
+
+def test_k13_multipass_count_and_scan(ctx, oracle):
+    """k=13: the 256 MiB count table exceeds L2, counting runs in 4 passes over table slices"""
+    seq = synth.genome(6_000_000, 13, n_blocks=(3, 5_000)).tobytes()
+    seqs = [seq, b"ACGTTTGACCANNNACGT" * 50]
+    n1, c1 = oracle.kmer_counts(seqs, 13)
+    g = ctx.kmer_counts(seqs, 13, with_f=False)
+    assert g["n"][1] == n1
+    assert (g["counts"] == c1).all()
+    o = oracle.low_comp(seqs, 13, 100, 20, 0.75)
+    r = ctx.kmer_low_comp_regions(seqs, 13, 100, 20, 0.75)
+    assert (r["counts"] == o["counts"]).all()
+    assert r["w_rank"].tobytes() == o["ranks"].tobytes()
+    assert_spans(r, o, exact_scores=False, what="k13 rank")
