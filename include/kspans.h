@@ -159,9 +159,6 @@ void ks_ctx_set_profile(ks_ctx *ctx, int on);
 int ks_ctx_profile_get(ks_ctx *ctx, int which, double *ms_total, uint64_t *launches);
 void ks_ctx_profile_reset(ks_ctx *ctx);
 
-/* development aid: per-phase cycle sums of scan level 0 (non-zero only in KS_EXP_TIMING builds) */
-int ks_ctx_debug_counters(ks_ctx *ctx, uint64_t *out16, int reset);
-
 /* diagnostics of the last scan on this ctx: restart levels run and positions visited beyond level 0 */
 void ks_ctx_scan_stats(const ks_ctx *ctx, int *levels, uint64_t *revisited_chunks);
 

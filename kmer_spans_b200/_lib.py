@@ -48,7 +48,6 @@ SIGNATURES = {
     "ks_ctx_set_profile": (None, [_vp, _i]),
     "ks_ctx_profile_get": (_i, [_vp, _i, _pd, _pu64]),
     "ks_ctx_profile_reset": (None, [_vp]),
-    "ks_ctx_debug_counters": (_i, [_vp, _pu64, _i]),
     "ks_kmer_counts": (_i, [_vp] + _SEQS + [_i, _vp, _pd]),
     "ks_kmer_regions": (_i, [_vp] + _SEQS + [_i, _vp, _i, _d, _pd, _vp, C.POINTER(KsSpans)]),
     "ks_kmer_low_comp_regions": (_i, [_vp] + _SEQS + [_i, _i, _d, _d, _pd, _vp, _vp, C.POINTER(KsSpans)]),

@@ -333,6 +333,44 @@ def kmer_seq(k):
     return out
 
 
+# ---- k-mer count files (kmer_spans.R:3-5,135-186): int32 LE -- magic, n_k, 4^k per k, the tables -----
+KMER_MAGIC = 310572  # kmer.magic(), kmer_spans.R:5
+
+
+def write_kmers(fname, tables):
+    """the file body of kmers.to.file (kmer_spans.R:168-175) for a list of int32 count tables"""
+    tables = [np.ascontiguousarray(t, "<i4") for t in tables]
+    with open(fname, "wb") as f:
+        np.array([KMER_MAGIC, len(tables)], "<i4").tofile(f)
+        np.array([t.size for t in tables], "<i4").tofile(f)
+        for t in tables:
+            t.tofile(f)
+
+
+def read_kmers(fname):
+    """read.kmers (kmer_spans.R:178-186): dict(k=[...], counts=[...]) or False on a bad magic / count"""
+    with open(fname, "rb") as f:
+        head = np.fromfile(f, "<i4", 2)
+        if head.size < 2 or head[0] != KMER_MAGIC or head[1] < 1:
+            return False
+        sizes = np.fromfile(f, "<i4", int(head[1]))
+        counts = [np.fromfile(f, "<i4", int(n)) for n in sizes]
+    return dict(k=[int(round(np.log2(n) / 2)) for n in sizes], counts=counts)
+
+
+def kmers_to_file(ctx, seqs, out_prefix, ks, min_l=100_000):
+    """kmers.to.file (kmer_spans.R:135-176) without the Biostrings FASTA reader: counts the sequences of
+    length >= min_l for every k in `ks` on the GPU and writes <prefix>counts_<k1>_<k2>...bin"""
+    seqs = _as_bytes_list(seqs)
+    size = sum(len(s) for s in seqs)
+    keep = [s for s in seqs if len(s) >= min_l]
+    if not keep:
+        raise ValueError("No sequence after length filtering")
+    out = "%scounts_%s.bin" % (out_prefix, "_".join(str(int(k)) for k in ks))
+    write_kmers(out, [ctx.kmer_counts(keep, int(k), with_f=False)["counts"] for k in ks])
+    return dict(out=out, seq_size=size, seq_fsize=sum(len(s) for s in keep), seq_fl=len(keep))
+
+
 _default_ctx = None
 
 

@@ -77,14 +77,8 @@ struct ks_ctx {
   uint64_t launches = 0;
   int last_levels = 0;
   uint64_t last_revisit_chunks = 0;
-  uint32_t epoch = 0;
-  unsigned int tile_base = 0;
-  bool counter_init = false;
-  bool scan_cfg_done = false;
-  size_t scan_max_ctas = 0;
   // scan scratch
-  DBuf wfx, prm, xf_status, xf_agg, xf_inc, ex_status, ex_agg, ex_inc, tile_counter;
-  size_t tiles_cap = 0;
+  DBuf wfx, prm;
   DBuf rec_beg, rec_pk, rec_c, rec_mhi, rec_mlo, rec_count;
   size_t rec_cap = 0;
   DBuf seg_start, seg_len, seg_chunks, seg_chunk0, scan_tmp;
@@ -105,7 +99,7 @@ struct ks_ctx {
   ks_seqset *host_set = nullptr;          // device buffers re-used by the host-buffer entry points
   void *pinned = nullptr;
   size_t pinned_cap = 0;
-  DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, dbg, pending, foc_hist, foc_big;
+  DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, pending, foc_hist, foc_big;
   DBuf st_c, st_s, st_ea, st_eb, st_flags, st_p0, tile_xf, tile_ex, group_xf, group_S, group_ex, pending_list, pending_count, launch_rec;
 
   // timing / profiling
@@ -232,15 +226,14 @@ void ks_ctx_destroy(ks_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DBuf *all[] = {&ctx->wfx, &ctx->prm, &ctx->xf_status, &ctx->xf_agg, &ctx->xf_inc, &ctx->ex_status,
-                 &ctx->ex_agg, &ctx->ex_inc, &ctx->tile_counter, &ctx->rec_beg, &ctx->rec_pk, &ctx->rec_c,
+  DBuf *all[] = {&ctx->wfx, &ctx->prm, &ctx->rec_beg, &ctx->rec_pk, &ctx->rec_c,
                  &ctx->rec_mhi, &ctx->rec_mlo, &ctx->rec_count, &ctx->seg_start, &ctx->seg_len,
                  &ctx->seg_chunks, &ctx->seg_chunk0, &ctx->scan_tmp, &ctx->sort_keys_a, &ctx->sort_keys_b,
                  &ctx->sort_vals_a, &ctx->sort_vals_b, &ctx->sort_hist, &ctx->sort_scan, &ctx->out_pos,
                  &ctx->out_score, &ctx->sc_keys_a, &ctx->sc_keys_b, &ctx->sc_vals_a, &ctx->sc_vals_b,
                  &ctx->sc_small, &ctx->sc_gcount, &ctx->sc_gstart, &ctx->sc_segfirst, &ctx->sc_segj0,
                  &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->tmp_counts, &ctx->tmp_scores,
-                 &ctx->tmp_inscan, &ctx->nwords, &ctx->dbg, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->launch_rec, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
+                 &ctx->tmp_inscan, &ctx->nwords, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->launch_rec, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -297,17 +290,6 @@ void ks_ctx_profile_reset(ks_ctx *ctx) {
   if (!ctx) return;
   ctx->prof_resolve();
   for (int i = 0; i < KS_PROF_N; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
-}
-
-// development aid (KS_EXP_TIMING builds): 16 per-phase cycle counters of scan level 0
-int ks_ctx_debug_counters(ks_ctx *ctx, uint64_t *out16, int reset) {
-  if (!ctx) return KS_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  if (!ctx->dbg.p) { CK(ctx->dbg.ensure(16 * 8)); CK(cudaMemset(ctx->dbg.p, 0, 16 * 8)); }
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (out16) CK(cudaMemcpy(out16, ctx->dbg.p, 16 * 8, cudaMemcpyDeviceToHost));
-  if (reset) CK(cudaMemset(ctx->dbg.p, 0, 16 * 8));
-  return KS_OK;
 }
 
 int ks_kmer_seq(int k, uint64_t code, char *out) {
@@ -794,7 +776,7 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
     std::vector<uint64_t> gstart(ng + 1);
     for (size_t i = 0; i < ng; ++i) gstart[i] = gstart32[i];
     gstart[ng] = n;
-    if (rank_mode) {
+    {
       // 3a. linear pieces of the sequential accumulation (ks_rankseg.h), evaluated on the device
       std::vector<uint32_t> seg_first;
       std::vector<RankSeg> segs;
@@ -821,40 +803,6 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
       LAUNCHED(1);
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(st));  // host vectors above must outlive the copies
-    } else {
-      // 3b. pure functions of the count: one libm evaluation per DISTINCT count on the host
-      //     (README.md:27-42; conventions in DESIGN.md), broadcast to the table on the device
-      auto count_at = [&](uint64_t p) -> double {  // count at sorted position p
-        size_t g = std::upper_bound(gstart.begin(), gstart.end(), p) - gstart.begin() - 1;
-        return (double)(int32_t)gcount[g];
-      };
-      double f_lo = count_at(n / 2 - 1) / total, f_hi = count_at(n / 2) / total;
-      double f_med = (f_lo + f_hi) / 2.0;
-      std::vector<double> lut(ng);
-      for (size_t g = 0; g < ng; ++g) {
-        double f = (double)(int32_t)gcount[g] / total;
-        if (mode == KS_MODE_LOG2) lut[g] = log2(f / f_med);
-        else {
-          double f_t = isfinite(param) ? param : f_med;
-          lut[g] = f >= f_t ? 1.0 : -1.0;
-        }
-      }
-      ctx->lut_gcount = gcount;
-      ctx->lut_gval = lut;
-      ctx->lut_valid = true;
-      ctx->lut_k = k;
-      if (d_scores) {  // the per-k-mer table itself (an output; the scan gathers counts + LUT instead)
-        CK(ctx->sc_gcount.ensure((ng + 1) * 4));
-        CK(ctx->sc_lut.ensure(ng * 8 + 8));
-        CK(cudaMemcpyAsync(ctx->sc_gcount.p, gcount.data(), ng * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->sc_lut.p, lut.data(), ng * 8, cudaMemcpyHostToDevice, st));
-        lut_apply_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_counts), n,
-                                                               ctx->sc_gcount.as<uint32_t>(), (uint32_t)ng,
-                                                               ctx->sc_lut.as<double>(), d_scores);
-        LAUNCHED(1);
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(st));
-      }
     }
   }
   if (mode == KS_MODE_RANK_REL) {

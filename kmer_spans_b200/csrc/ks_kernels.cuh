@@ -30,14 +30,6 @@ constexpr int TILE_THREADS = KS_TILE_THREADS;
 constexpr int TILE_WARPS = TILE_THREADS / 32;
 
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // streaming (evict-first) 128-bit load for the sequence: it is read once per pass and must not push
 // the count / score table out of L2
 __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) { return __ldcs(p); }

@@ -50,3 +50,20 @@ def test_product_does_not_touch_the_oracle():
                 for ln in open(os.path.join(dirpath, f)):
                     code = ln.split("//")[0].split("#  ")[0]
                     assert not pat.search(code), "%s: %s" % (f, ln.strip())
+
+
+def test_kmer_count_file_format(tmp_path):
+    """kmers.to.file / read.kmers layout (kmer_spans.R:135-186): int32 LE magic 310572, n_k, sizes, tables"""
+    import numpy as np
+    from kmer_spans_b200 import api
+    t2 = np.arange(16, dtype=np.int32)
+    t3 = (np.arange(64, dtype=np.int32) * 7) % 11
+    f = tmp_path / "x.bin"
+    api.write_kmers(str(f), [t2, t3])
+    raw = np.fromfile(str(f), "<i4")
+    assert raw[:4].tolist() == [310572, 2, 16, 64] and raw.size == 4 + 16 + 64
+    r = api.read_kmers(str(f))
+    assert r["k"] == [2, 3] and (r["counts"][0] == t2).all() and (r["counts"][1] == t3).all()
+    bad = tmp_path / "bad.bin"
+    np.array([1, 2, 3], "<i4").tofile(str(bad))
+    assert api.read_kmers(str(bad)) is False

@@ -384,3 +384,15 @@ def test_k13_multipass_count_and_scan(ctx, oracle):
     assert (r["counts"] == o["counts"]).all()
     assert r["w_rank"].tobytes() == o["ranks"].tobytes()
     assert_spans(r, o, exact_scores=False, what="k13 rank")
+
+
+def test_kmers_to_file_roundtrip(ctx, oracle, tmp_path):
+    from kmer_spans_b200 import api
+    rng = np.random.default_rng(31)
+    seqs = [planted(rng, 5000), planted(rng, 300), planted(rng, 8000)]
+    info = api.kmers_to_file(ctx, seqs, str(tmp_path) + "/", [3, 6], min_l=1000)
+    assert info["seq_fl"] == 2 and info["seq_size"] == 13300
+    r = api.read_kmers(info["out"])
+    assert r["k"] == [3, 6]
+    for k, c in zip(r["k"], r["counts"]):
+        assert (c == oracle.kmer_counts([seqs[0], seqs[2]], k)[1]).all()
