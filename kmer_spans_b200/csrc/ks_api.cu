@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/kspans.h"
@@ -86,7 +87,7 @@ struct ks_ctx {
   DBuf out_pos, out_score;
   // score scratch
   DBuf sc_keys_a, sc_keys_b, sc_vals_a, sc_vals_b, sc_small, sc_gcount, sc_gstart, sc_segfirst, sc_segj0,
-      sc_segx0, sc_seginc, sc_lut;
+      sc_segx0, sc_seginc, sc_lut, sc_dense;
   // count -> score function of the last ks_dev_scores(LOG2 | SIGN): one value per distinct count
   DBuf lut_fx, lut_spc, lut_spv;
   bool lut_valid = false;
@@ -232,7 +233,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->sort_vals_a, &ctx->sort_vals_b, &ctx->sort_hist, &ctx->sort_scan, &ctx->out_pos,
                  &ctx->out_score, &ctx->sc_keys_a, &ctx->sc_keys_b, &ctx->sc_vals_a, &ctx->sc_vals_b,
                  &ctx->sc_small, &ctx->sc_gcount, &ctx->sc_gstart, &ctx->sc_segfirst, &ctx->sc_segj0,
-                 &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->tmp_counts, &ctx->tmp_scores,
+                 &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->sc_dense, &ctx->tmp_counts, &ctx->tmp_scores,
                  &ctx->tmp_inscan, &ctx->nwords, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->launch_rec, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
@@ -413,22 +414,46 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
   cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
   bool ev_used[2] = {false, false};
   int half = 0;
+  // plan: maximal groups of consecutive small sequences that fit one staging half
+  struct Item { int seq; size_t off; };
+  std::vector<Item> items;
   size_t fill = 0;
   int64_t win_start = -1;  // global offset the current window maps to
-  char *win = (char *)ctx->pinned;
+  unsigned nthreads = std::thread::hardware_concurrency();
+  if (nthreads > 8) nthreads = 8;
+  if (nthreads < 1) nthreads = 1;
   auto flush = [&]() -> cudaError_t {
     if (fill == 0) return cudaSuccess;
-    cudaError_t ee = cudaMemcpyAsync(s->d_buf + win_start, win, fill, cudaMemcpyHostToDevice, cs);
+    char *win = (char *)ctx->pinned + (size_t)half * HALF;
+    cudaError_t ee = cudaSuccess;
+    if (ev_used[half]) ee = cudaEventSynchronize(ev[half]);  // the copy that last used this half is done
+    if (ee != cudaSuccess) return ee;
+    // fill the window with several host threads (R hands over pageable, separately allocated strings)
+    auto work = [&](unsigned t) {
+      for (size_t i = t; i < items.size(); i += nthreads) {
+        const Item &it = items[i];
+        memcpy(win + it.off, seqs[it.seq], (size_t)lens[it.seq]);
+        if (it.off) win[it.off - 1] = 0;  // separator in front of every sequence but the first
+      }
+    };
+    if (nthreads > 1 && fill > (1u << 20)) {
+      std::vector<std::thread> th;
+      for (unsigned t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+      work(0);
+      for (auto &x : th) x.join();
+    } else {
+      for (unsigned t = 0; t < nthreads; ++t) work(t);
+    }
+    ee = cudaMemcpyAsync(s->d_buf + win_start, win, fill, cudaMemcpyHostToDevice, cs);
     if (ee != cudaSuccess) return ee;
     ee = progress(win_start + (int64_t)fill, false);
     if (ee != cudaSuccess) return ee;
     cudaEventRecord(ev[half], cs);
     ev_used[half] = true;
     half ^= 1;
-    win = (char *)ctx->pinned + (size_t)half * HALF;
-    if (ev_used[half]) ee = cudaEventSynchronize(ev[half]);
     fill = 0;
     win_start = -1;
+    items.clear();
     return ee;
   };
   cudaError_t e = cudaSuccess;
@@ -450,8 +475,8 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
     if (fill && (s->starts[i] != win_start + (int64_t)fill + 1 || fill + 1 + (size_t)ln > HALF)) e = flush();
     if (e != cudaSuccess) break;
     if (fill == 0) win_start = s->starts[i];
-    else win[fill++] = 0;
-    memcpy(win + fill, seqs[i], (size_t)ln);
+    else fill += 1;
+    items.push_back({i, fill});
     fill += (size_t)ln;
   }
   if (e == cudaSuccess) e = flush();
@@ -694,11 +719,17 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
     ctx->lut_valid = true;
     ctx->lut_k = k;
     if (d_scores) {  // the per-k-mer table itself (an output; the scan gathers counts + LUT instead)
+      uint32_t ndense = ng ? std::min<uint32_t>(gcount[ng - 1] + 1, DENSE) : 0;
+      std::vector<double> dense(ndense ? ndense : 1, 0.0);
+      for (size_t g = 0; g < ng && gcount[g] < ndense; ++g) dense[gcount[g]] = lut[g];
       CK(ctx->sc_gcount.ensure((ng + 1) * 4));
       CK(ctx->sc_lut.ensure(ng * 8 + 8));
+      CK(ctx->sc_dense.ensure((size_t)dense.size() * 8));
       CK(cudaMemcpyAsync(ctx->sc_gcount.p, gcount.data(), ng * 4, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(ctx->sc_lut.p, lut.data(), ng * 8, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->sc_dense.p, dense.data(), dense.size() * 8, cudaMemcpyHostToDevice, st));
       lut_apply_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_counts), n,
+                                                             ctx->sc_dense.as<double>(), ndense,
                                                              ctx->sc_gcount.as<uint32_t>(), (uint32_t)ng,
                                                              ctx->sc_lut.as<double>(), d_scores);
       LAUNCHED(1);

@@ -852,19 +852,22 @@ __global__ void __launch_bounds__(256) foc_hist_kernel(const uint32_t *__restric
     if (sh[i] && (uint32_t)i < dense) atomicAdd(&hist[i], sh[i]);
 }
 
-// W[x] = lut[group of counts[x]]  (log2 / +-1 / any pure function of the count)
+// W[x] = f(counts[x])  (log2 / +-1 / any pure function of the count): dense table for small counts,
+// binary search over the sorted distinct counts above it
 __global__ void __launch_bounds__(256) lut_apply_kernel(const uint32_t *__restrict__ counts, size_t n,
+                                                        const double *__restrict__ dense, uint32_t ndense,
                                                         const uint32_t *__restrict__ gcount, uint32_t ngroups,
                                                         const double *__restrict__ lut, double *__restrict__ W) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t c = counts[i];
+  if (c < ndense) { __stcs(&W[i], __ldg(&dense[c])); return; }
   uint32_t lo = 0, hi = ngroups;  // largest g with gcount[g] <= c (exists: c is one of them)
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
     if (__ldg(&gcount[mid]) <= c) lo = mid; else hi = mid;
   }
-  W[i] = __ldg(&lut[lo]);
+  __stcs(&W[i], __ldg(&lut[lo]));
 }
 
 // dense count -> score table in exact fixed point: lut[c] = fx(score(c) - thr); entries of counts that

@@ -396,3 +396,21 @@ def test_kmers_to_file_roundtrip(ctx, oracle, tmp_path):
     assert r["k"] == [3, 6]
     for k, c in zip(r["k"], r["counts"]):
         assert (c == oracle.kmer_counts([seqs[0], seqs[2]], k)[1]).all()
+
+
+def test_config2_full_size_parity(ctx, oracle):
+    """BASELINE.json configs[1] at FULL size (250 Mb, k=12) against the oracle: rank mode (thousands of
+    spans, two restart levels) and log2 mode (run-sized excursions).  ~40 s of CPU oracle time."""
+    seq = synth.config2()[0]
+    sb = seq.tobytes()
+    o = oracle.low_comp([sb], 12, 100, 20, 0.75)
+    g = ctx.kmer_low_comp_regions([seq], 12, 100, 20, 0.75)
+    assert (g["n"] == o["n"]).all()
+    assert (g["counts"] == o["counts"]).all()
+    assert g["w_rank"].tobytes() == o["ranks"].tobytes()
+    assert len(o["pos"]) > 10000
+    assert_spans(g, o, exact_scores=False, what="config 2 rank")
+    o = oracle.mode_regions([sb], 12, 1, 100, 20)
+    g = ctx.kmer_mode_regions([seq], 12, 1, 100, 20)
+    assert g["scores"].tobytes() == o["scores"].tobytes()
+    assert_spans(g, o, exact_scores=False, what="config 2 log2")
