@@ -15,7 +15,28 @@ from . import _lib
 from ._lib import KsSpans, KspansError, MODE_LOG2, MODE_RANK, MODE_RANK_REL, MODE_SIGN  # noqa: F401
 
 
+class SeqBatch:
+    """Many sequences stored back to back in ONE uint8 array (lens[i] bytes each, no separators): the
+    cheap way to hand 100k contigs to the C ABI from Python (pointers are computed vectorised)."""
+
+    def __init__(self, buf, lens):
+        self.buf = np.ascontiguousarray(buf, np.uint8)
+        self.lens = np.ascontiguousarray(lens, np.int64)
+        if int(self.lens.sum()) != self.buf.size:
+            raise ValueError("SeqBatch: lengths do not add up to the buffer size")
+
+    @classmethod
+    def from_list(cls, seqs):
+        seqs = [np.frombuffer(s, np.uint8) if not isinstance(s, np.ndarray) else s for s in seqs]
+        return cls(np.concatenate(seqs) if seqs else np.zeros(0, np.uint8), [s.size for s in seqs])
+
+    def __len__(self):
+        return len(self.lens)
+
+
 def _as_bytes_list(seq):
+    if isinstance(seq, SeqBatch):
+        return seq
     if isinstance(seq, (bytes, bytearray, str, np.ndarray)):
         seq = [seq]
     out = []
@@ -34,18 +55,32 @@ class _SeqArgs:
     def __init__(self, seqs):
         self.keep = seqs
         n = len(seqs)
-        self.ptrs = (C.c_char_p * max(n, 1))()
-        self.lens = (C.c_int64 * max(n, 1))()
-        for i, s in enumerate(seqs):
-            if isinstance(s, np.ndarray):
-                self.ptrs[i] = C.cast(s.ctypes.data, C.c_char_p)
-                self.lens[i] = s.size
-            else:
-                if not isinstance(s, bytes):
-                    s = bytes(s)
-                    seqs[i] = s  # keep the converted object alive
-                self.ptrs[i] = s
-                self.lens[i] = len(s)
+        ptr = np.zeros(max(n, 1), np.uint64)
+        ln = np.zeros(max(n, 1), np.int64)
+        if isinstance(seqs, SeqBatch):
+            ln[:n] = seqs.lens
+            off = np.zeros(n, np.uint64)
+            if n > 1:
+                off[1:] = np.cumsum(seqs.lens[:-1]).astype(np.uint64)
+            ptr[:n] = np.uint64(seqs.buf.ctypes.data) + off
+        elif n and all(isinstance(s, np.ndarray) for s in seqs):
+            # fast path for many contigs: no per-sequence ctypes objects
+            ptr[:n] = np.fromiter((s.__array_interface__["data"][0] for s in seqs), np.uint64, n)
+            ln[:n] = np.fromiter((s.size for s in seqs), np.int64, n)
+        else:
+            for i, s in enumerate(seqs):
+                if isinstance(s, np.ndarray):
+                    ptr[i] = s.ctypes.data
+                    ln[i] = s.size
+                else:
+                    if not isinstance(s, bytes):
+                        s = bytes(s)
+                        seqs[i] = s  # keep the converted object alive
+                    ptr[i] = C.cast(C.c_char_p(s), C.c_void_p).value or 0
+                    ln[i] = len(s)
+        self._ptr, self._len = ptr, ln
+        self.ptrs = ptr.ctypes.data_as(C.POINTER(C.c_char_p))
+        self.lens = ln.ctypes.data_as(C.POINTER(C.c_int64))
         self.n = n
 
 

@@ -414,3 +414,13 @@ def test_config2_full_size_parity(ctx, oracle):
     g = ctx.kmer_mode_regions([seq], 12, 1, 100, 20)
     assert g["scores"].tobytes() == o["scores"].tobytes()
     assert_spans(g, o, exact_scores=False, what="config 2 log2")
+
+
+def test_seqbatch_input(ctx, oracle):
+    """many contigs handed over as one buffer + lengths (api.SeqBatch)"""
+    from kmer_spans_b200 import api
+    seqs = [s.tobytes() for s in synth.contigs(300, seed=9, lo=30, hi=4000, k=7)]
+    o = oracle.low_comp(seqs, 7, 20, 4, 0.7)
+    g = ctx.kmer_low_comp_regions(api.SeqBatch.from_list(seqs), 7, 20, 4, 0.7)
+    assert (g["counts"] == o["counts"]).all()
+    assert_spans(g, o, exact_scores=False, what="seqbatch")

@@ -5,8 +5,8 @@ sys.path.insert(0, ROOT)
 import numpy as np
 from kmer_spans_b200 import api, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
-seqs = synth.contigs(n, seed=5, k=10)
-bases = sum(s.size for s in seqs)
+seqs = api.SeqBatch.from_list(synth.contigs(n, seed=5, k=10))
+bases = int(seqs.lens.sum())
 ctx = api.Context(0)
 for mode, thr in ((0, 0.75), (1, 0.0), (2, 0.0)):
     for rep in range(2):
