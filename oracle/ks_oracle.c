@@ -291,3 +291,122 @@ int kso_kmer_seq(int k, uint64_t code, char *out) {
   for (int j = k - 1; j >= 0; --j) { out[j] = nuc[code & 3]; code >>= 2; }
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * "next" rows of SURVEY 8(f): the two remaining .Call entries of the reference.
+ * Both are checked against the compiled reference in tests/test_oracle.py. */
+
+/* What init_kmer (src/kmer_spans.c:119-132) leaves in *offset for a k-mer STRING, as the callers at
+ * :691 and :747 use it: the first min(k, len) bases of the last N-free piece it looks at; it stops
+ * looking at the first piece that holds k bases.  For a clean string of k bases this is its code. */
+uint32_t kso_kmer_code(const char *s, int k) {
+  uint32_t code = 0;
+  size_t i = 0;
+  while (s[i]) {
+    code = 0;
+    int got = 0;
+    while (got < k && s[i] && !is_n((unsigned char)s[i])) { code = (code << 2) | base2((unsigned char)s[i]); ++i; ++got; }
+    if (got == k || !s[i]) break;
+    while (s[i] && is_n((unsigned char)s[i])) ++i;
+  }
+  return code;
+}
+
+/* windowed_kmer_count_distributions(_r), src/kmer_spans.c:398-449,715-793.
+ * A window is `window` consecutive bases inside one run; it starts at every s in [a, b - window] of a
+ * run [a,b).  Its value for a selected k-mer x is the number of occurrences of x lying entirely
+ * inside it, i.e. k-mers ending at e in [s+k-1, s+window-1] (:425-444).  dist[i*(window+1) + c]
+ * counts the windows with value c for selected k-mer i; pos[seq][i*len + s] (optional) holds the
+ * value of the window starting at s (:440-441).  Sequences with len <= window are left out (:775). */
+int kso_window_dist(const char *const *seqs, const int64_t *lens, int nseq, int k, const uint32_t *codes,
+                    int kmer_n, int window, int32_t *dist, int32_t *included, int32_t *const *pos) {
+  if (k < 1 || k > KSO_MAX_K || window < 2 * k || kmer_n < 1) return -1;
+  const uint32_t mask = (1u << (2 * k)) - 1u;
+  memset(dist, 0, sizeof(int32_t) * (size_t)(window + 1) * (size_t)kmer_n);
+  for (int q = 0; q < nseq; ++q) {
+    included[q] = lens[q] > window;
+    if (!included[q]) continue;
+    const char *seq = seqs[q];
+    int64_t len = c_strlen_bounded(seq, lens[q]);
+    if (pos && pos[q]) memset(pos[q], 0, sizeof(int32_t) * (size_t)lens[q] * (size_t)kmer_n);
+    int64_t a, b, from = 0;
+    while (next_run(seq, len, from, &a, &b)) {
+      from = b;
+      if (b - a < window) continue;
+      uint8_t *hit = (uint8_t *)malloc((size_t)(b - a));
+      for (int i = 0; i < kmer_n; ++i) {
+        /* hit[e-a] = the k-mer ending at e is the selected one */
+        memset(hit, 0, (size_t)(b - a));
+        uint32_t code = code_ending_at(seq, a + k - 1, k) & mask;
+        hit[k - 1] = code == codes[i];
+        for (int64_t e = a + k; e < b; ++e) {
+          code = ((code << 2) | base2((unsigned char)seq[e])) & mask;
+          hit[e - a] = code == codes[i];
+        }
+        int32_t c = 0;
+        for (int64_t e = a + k - 1; e < a + window - 1; ++e) c += hit[e - a];
+        for (int64_t s = a; s + window <= b; ++s) {
+          c += hit[s + window - 1 - a];
+          dist[(size_t)i * (size_t)(window + 1) + (size_t)c]++;
+          if (pos && pos[q]) pos[q][(size_t)i * (size_t)lens[q] + (size_t)s] = c;
+          c -= hit[s + k - 1 - a];
+        }
+      }
+      free(hit);
+    }
+  }
+  return 0;
+}
+
+/* find_kmer_tr_lr_regions / tr_lr_regions_r, src/kmer_spans.c:329-395,649-713.  `init` and `trans`
+ * are in 2-bit code order (the .Call wrapper's reordering by k-mer strings, :688-696, is the
+ * caller's job: see kso_kmer_code).  A run [a,b) starts with S = max(init[first k-mer], 0) "at"
+ * index a+k, then S_i = max(S_{i-1} + trans[code(i)], 0) for i = a+k .. b-1 (the k-mer ENDING at
+ * i, :361-362).  Every excursion that returns to 0 is tested on width only (:377) and the scan ALWAYS
+ * resumes behind its peak (:382-388); an excursion still open at the run end is tested but not
+ * re-scanned (:392-393).  Coordinates and seq_id are 1-based (:379,681).  A run is not looked at when
+ * the string ends within one base of its first k-mer (:340-341). */
+void kso_tr_lr_seq(const char *seq, int64_t len, int seq_id1, int k, const double *init, const double *trans,
+                   int min_len, kso_spans *out) {
+  len = c_strlen_bounded(seq, len);
+  const uint32_t mask = (1u << (2 * k)) - 1u;
+  int64_t a, b, from = 0;
+  while (next_run(seq, len, from, &a, &b)) {
+    from = b;
+    if (b - a < k) continue;
+    int64_t i = a + k;
+    if (i >= len || i + 1 >= len) break; /* terminator at i or i+1 ends the whole sequence (:340) */
+    uint32_t code = code_ending_at(seq, i - 1, k) & mask;
+    double S = init[code] < 0 ? 0 : init[code];
+    double M = 0;
+    int64_t pk = 0, beg = 0;
+    if (S > 0) { M = S; pk = i; beg = i; }
+    while (i < b) {
+      code = ((code << 2) | base2((unsigned char)seq[i])) & mask;
+      double Sn = S + trans[code];
+      if (Sn > M) { M = Sn; pk = i; }
+      Sn = Sn < 0 ? 0 : Sn;
+      if (S == 0 && Sn > 0) { M = Sn; pk = i; beg = i; }
+      if (Sn == 0 && S > 0) {
+        if ((int)pk - (int)beg >= min_len) spans_push(out, seq_id1, (int32_t)(1 + beg), (int32_t)(1 + pk), M);
+        i = pk; /* resume behind the peak with a clean state */
+        beg = pk;
+        pk = 0;
+        M = 0;
+        Sn = 0;
+        code = code_ending_at(seq, i, k) & mask;
+      }
+      S = Sn;
+      ++i;
+    }
+    if (M > 0 && (int)pk - (int)beg >= min_len)
+      spans_push(out, seq_id1, (int32_t)(1 + beg), (int32_t)(1 + pk), M);
+  }
+}
+
+int kso_tr_lr_regions(const char *const *seqs, const int64_t *lens, int nseq, int k, const double *init,
+                      const double *trans, int min_len, kso_spans *out) {
+  if (k < 1 || k > KSO_MAX_K || min_len < 0) return -1;
+  for (int i = 0; i < nseq; ++i) kso_tr_lr_seq(seqs[i], lens[i], i + 1, k, init, trans, min_len, out);
+  return 0;
+}

@@ -146,6 +146,46 @@ class Oracle:
         self.lib.kso_kmer_seq(k, code, buf)
         return buf.value.decode()
 
+    # ---- SURVEY 8(f) rows 3 and 4 ----
+    def kmer_code(self, kmer, k):
+        kmer = kmer.encode() if isinstance(kmer, str) else bytes(kmer)
+        self.lib.kso_kmer_code.restype = C.c_uint32
+        return int(self.lib.kso_kmer_code(C.c_char_p(kmer), C.c_int(k)))
+
+    def window_dist(self, seqs, kmers, k, window, want_pos=False):
+        """kmers: strings of length k.  Returns dict(dist (kmer_n, window+1), included, pos)"""
+        seqs = _as_bytes_list(seqs)
+        bufs, ptrs, lens = _padded(seqs)
+        codes = np.array([self.kmer_code(x, k) for x in kmers], np.uint32)
+        dist = np.zeros((len(codes), window + 1), np.int32)
+        inc = np.zeros(len(seqs), np.int32)
+        pos = [np.zeros((len(codes), len(s)), np.int32) if len(s) > window else None for s in seqs] if want_pos else None
+        pp = None
+        if want_pos:
+            pp = (C.c_void_p * len(seqs))(*[p.ctypes.data if p is not None else None for p in pos])
+        rc = self.lib.kso_window_dist(ptrs, lens, len(seqs), C.c_int(k), codes.ctypes.data_as(C.c_void_p),
+                                      C.c_int(len(codes)), C.c_int(window), dist.ctypes.data_as(C.c_void_p),
+                                      inc.ctypes.data_as(C.c_void_p), pp)
+        if rc:
+            raise ValueError("oracle window_dist rc=%d" % rc)
+        return dict(dist=dist, included=inc, pos=pos)
+
+    def tr_lr_regions(self, seqs, k, init, trans, min_len):
+        """init / trans in 2-bit code order"""
+        seqs = _as_bytes_list(seqs)
+        bufs, ptrs, lens = _padded(seqs)
+        init = np.ascontiguousarray(init, np.float64)
+        trans = np.ascontiguousarray(trans, np.float64)
+        sp = _Spans()
+        self.lib.kso_spans_init(C.byref(sp))
+        rc = self.lib.kso_tr_lr_regions(ptrs, lens, len(seqs), C.c_int(k), init.ctypes.data_as(C.c_void_p),
+                                        trans.ctypes.data_as(C.c_void_p), C.c_int(min_len), C.byref(sp))
+        pos, sc = self._spans_out(sp)
+        self.lib.kso_spans_free(C.byref(sp))
+        if rc:
+            raise ValueError("oracle tr_lr rc=%d" % rc)
+        return dict(pos=pos, score=sc)
+
 
 # ----------------------------------------------------------------------------------------------
 class _SeqRegions(C.Structure):  # struct seq_regions, /root/reference/src/kmer_spans.c:46-58
@@ -248,7 +288,11 @@ class Ref:
         return v
 
     def _np(self, sexp):
+        if not sexp:
+            return None  # list element never set (R_NilValue)
         s = sexp.contents
+        if s.type == VECSXP:
+            return self._list(sexp)
         if s.type == INTSXP:
             a = np.ctypeslib.as_array(C.cast(s.data, C.POINTER(C.c_int32)), shape=(max(s.len, 0),)).copy() if s.len else np.zeros(0, np.int32)
         elif s.type == REALSXP:
@@ -320,6 +364,18 @@ class Ref:
         out = self._list(r)
         self.lib.mockR_free_all()
         return out
+
+    def call_window_dist(self, seqs, kmers, k, window, ret_flag=0):
+        out = self.call_raw("windowed_kmer_count_distributions_r",
+                            [("s", _as_bytes_list(seqs)), ("s", _as_bytes_list(kmers)), ("i", k), ("i", window),
+                             ("i", ret_flag)])
+        return dict(dist=out[0].reshape(-1, window + 1), included=out[1], pos=out[2])
+
+    def call_tr_lr(self, seqs, k, min_len, kmers, kmer_scores, trans_scores):
+        out = self.call_raw("tr_lr_regions_r", [("s", _as_bytes_list(seqs)), ("i", [k, min_len]),
+                                                ("s", _as_bytes_list(kmers)), ("d", kmer_scores),
+                                                ("d", trans_scores)])
+        return dict(tables=out[0].reshape(2, -1), pos=out[1].reshape(-1, 3), score=out[2].reshape(-1, 2))
 
     def call_kmer_seq_r(self, k):
         r = self._call("kmer_seq_r", [self._intsxp(k)])

@@ -173,3 +173,70 @@ def test_reference_error_paths(ref):
         ref.call_kmer_low_comp_regions([b"ACGT"], 2, 1, 1.0, 1.0)
     with pytest.raises(RuntimeError, match="positive integer"):
         ref.call_kmer_counts([b"ACGT"], 0)
+
+
+# ---- the other two .Call entries --------------------------------------
+def _pos_equal(a, b, kmer_n):
+    if (a is None) != (b is None):
+        return False
+    return a is None or np.array_equal(np.asarray(a).reshape(kmer_n, -1), b)
+
+
+def test_window_dist_matches_reference(oracle, ref):
+    """windowed_kmer_count_distributions_r, src/kmer_spans.c:398-449,715-793."""
+    rng = np.random.default_rng(31)
+    for t in range(120):
+        k = int(rng.integers(1, 5))
+        window = int(rng.integers(2 * k, 40))
+        seqs = [rand_seq(rng, int(rng.integers(0, 300)), p_n=float(rng.choice([0, 0.1, 0.4])))
+                for _ in range(int(rng.integers(1, 5)))]
+        if t % 5 == 0:  # length == window is left out, window + 1 is not (:775)
+            seqs += [rand_seq(rng, window), rand_seq(rng, window + 1)]
+        kms = [oracle.kmer_seq(k, int(c)).encode() for c in rng.integers(0, 4 ** k, int(rng.integers(1, 6)))]
+        if t % 7 == 0:
+            kms.append(b"N" * k)
+        if t % 11 == 0 and k >= 2:
+            kms += [b"A" + b"N" * (k - 1), b"N" + b"C" * (k - 1)]
+        a = ref.call_window_dist(seqs, kms, k, window, 1)
+        b = oracle.window_dist(seqs, kms, k, window, True)
+        assert np.array_equal(a["dist"], b["dist"])
+        assert np.array_equal(a["included"], b["included"])
+        for x, y in zip(a["pos"], b["pos"]):
+            assert _pos_equal(x, y, len(kms))
+        assert ref.call_window_dist(seqs, kms, k, window, 0)["pos"] is None
+
+
+def test_window_dist_known_answer(oracle):
+    # ACGTACGTAA: windows of 8 start at 0, 1, 2; "AC" occurs at 0 and 4
+    r = oracle.window_dist([b"ACGTACGTAA"], [b"AC"], 2, 8, True)
+    assert r["pos"][0][0, :3].tolist() == [2, 1, 1]
+    assert r["dist"][0, :3].tolist() == [0, 2, 1]
+
+
+def test_tr_lr_matches_reference_bitexact(oracle, ref):
+    """tr_lr_regions_r, src/kmer_spans.c:329-395,649-713 (tables handed over in permuted k-mer order)."""
+    rng = np.random.default_rng(32)
+    total = 0
+    for t in range(150):
+        k = int(rng.integers(1, 5))
+        n = 4 ** k
+        seqs = [rand_seq(rng, int(rng.integers(0, 400)), p_n=float(rng.choice([0, 0.1, 0.4])))
+                for _ in range(int(rng.integers(1, 5)))]
+        if t % 3 == 0:  # the run-end rules of :340-341
+            seqs += [rand_seq(rng, k), rand_seq(rng, k + 1), rand_seq(rng, k + 2), rand_seq(rng, k) + b"N",
+                     rand_seq(rng, k) + b"NA", rand_seq(rng, k) + b"N" + rand_seq(rng, k + 3)]
+        kms = [oracle.kmer_seq(k, c).encode() for c in range(n)]
+        perm = rng.permutation(n)
+        if t % 2:
+            init, trans = rng.normal(0, 1, n), rng.normal(-0.1, 1, n)
+        else:
+            init, trans = rng.integers(-2, 3, n).astype(float), rng.integers(-2, 3, n).astype(float)
+        min_len = int(rng.choice([0, 1, 3, 10]))
+        a = ref.call_tr_lr(seqs, k, min_len, [kms[i] for i in perm], init[perm], trans[perm])
+        assert np.array_equal(a["tables"][0], init) and np.array_equal(a["tables"][1], trans)
+        assert [oracle.kmer_code(kms[i], k) for i in perm[:8]] == [int(i) for i in perm[:8]]
+        b = oracle.tr_lr_regions(seqs, k, init, trans, min_len)
+        assert np.array_equal(a["pos"], b["pos"])
+        assert np.array_equal(a["score"], b["score"])
+        total += len(b["pos"])
+    assert total > 1000
