@@ -97,6 +97,20 @@ int ks_kmer_scores(ks_ctx *ctx, int k, const int32_t *counts, double total, int 
 
 /* kmer_seq (:161-171): index -> k-mer string (A,C,T,G order); host only, no device needed. */
 int ks_kmer_seq(int k, uint64_t code, char *out /* k+1 bytes */);
+/* What init_kmer (:119-132) leaves in its offset for a k-mer STRING, as the callers at :691 and :747
+ * use it: the 2-bit code of a clean string of k bases (first base most significant).  Host only. */
+uint32_t ks_kmer_code(const char *kmer, int k);
+
+/* windowed_kmer_count_distributions_r (:715-793, core :398-449), SURVEY 8(f) row 4.
+ * codes[kmer_n] = 2-bit codes of the selected k-mers (ks_kmer_code), 1 <= k <= 15, window >= 2k.
+ * dist_out[i * (window+1) + c] = number of windows (window consecutive bases inside one run of one
+ * sequence longer than `window`) that hold c occurrences of selected k-mer i: the R matrix
+ * (window+1) x kmer_n, column-major.  included_out[nseq] = 1 for sequences longer than window (:775).
+ * pos_out: NULL, or nseq pointers; pos_out[q] (NULL for sequences left out) receives the R matrix
+ * lens[q] x kmer_n: the value of the window STARTING at each position, 0 where none starts (:440-441). */
+int ks_windowed_kmer_count_distributions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq,
+                                         int k, const uint32_t *codes, int kmer_n, int window,
+                                         int32_t *dist_out, int32_t *included_out, int32_t *const *pos_out);
 
 /* -------- device-resident sequence sets (upload once, scan many times) --------------------- */
 int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, ks_seqset **out);
@@ -122,6 +136,14 @@ int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, doubl
  * gathers the 4-byte count (table L2 resident up to k = 12) and maps it through a dense LUT. */
 int ks_dev_scan_counts(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
                        int min_width, double min_score, ks_spans *host_out_or_null, uint64_t *n_spans);
+/* windowed occurrence histograms on a resident set: d_dist = device int32[kmer_n * (window+1)]
+ * (overwritten); d_pos = NULL or device int32[kmer_n * ks_seqset_positions(s)] (overwritten), the value
+ * of the window starting at every buffer position (position of base i of sequence q:
+ * ks_seqset_start(s, q) + i).  codes are host memory. */
+int ks_dev_window_dist(ks_ctx *ctx, const ks_seqset *s, int k, const uint32_t *codes, int kmer_n, int window,
+                       int32_t *d_dist, int32_t *d_pos);
+int64_t ks_seqset_positions(const ks_seqset *s);
+int64_t ks_seqset_start(const ks_seqset *s, int seq);
 /* count -> scores(mode) -> scan, all resident; spans stay on the device unless host_out != NULL */
 int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double param, double thr,
                     int min_width, double min_score, int32_t *d_counts, double *d_scores,

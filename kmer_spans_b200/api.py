@@ -313,6 +313,45 @@ class Context:
                                          W.ctypes.data))
         return W
 
+    def window_kmer_dist(self, seq, kmers, window, freq=True, ret_flag=0):
+        """window.kmer.dist (kmer_spans.R:103-120) on windowed_kmer_count_distributions_r
+        (src/kmer_spans.c:715-793): dist = (window+1) x len(kmers) occurrence histogram (column sums
+        normalised when freq), seq_i = sequences longer than window, scores = per sequence the
+        len x kmers matrix of window values when ret_flag & 1 (None for sequences left out)."""
+        kmers = [x.encode() if isinstance(x, str) else bytes(x) for x in kmers]
+        if len({len(x) for x in kmers}) != 1:
+            raise ValueError("All kmers must be of the same size")
+        k = len(kmers[0])
+        seqs = _as_bytes_list(seq)
+        a = _SeqArgs(seqs)
+        codes = np.array([self.lib.ks_kmer_code(x, k) for x in kmers], np.uint32)
+        window = int(window)
+        dist = np.zeros((len(kmers), max(window, 0) + 1), np.int32)
+        inc = np.zeros(a.n, np.int32)
+        pos, pp = None, None
+        if int(ret_flag) & 1:
+            ln = a._len[:a.n]
+            pos = [np.zeros((len(kmers), int(l)), np.int32) if l > window else None for l in ln]
+            pp = (C.c_void_p * a.n)(*[p.ctypes.data if p is not None else None for p in pos])
+        self._ck(self.lib.ks_windowed_kmer_count_distributions(
+            self.h, a.ptrs, a.lens, a.n, k, codes.ctypes.data, len(kmers), window, dist.ctypes.data,
+            inc.ctypes.data, pp))
+        d = dist.T.copy()  # the R matrix: (window+1) x kmers
+        if freq:
+            # `dists$dist / colSums(dists$dist)` (kmer_spans.R:118): R recycles the divisor down the
+            # columns, so element (r, c) is divided by colSums[(r + c * nrow) %% ncol] -- kept as is
+            cs = d.sum(axis=0).astype(np.float64)
+            flat = d.flatten("F").astype(np.float64)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                flat = flat / np.resize(cs, flat.size)
+            d = flat.reshape(d.shape, order="F")
+        return dict(dist=d, seq_i=inc, scores=[None if p is None else p.T for p in pos] if pos is not None else None)
+
+    def dev_window_dist(self, ss, k, codes, window, d_dist, d_pos=0):
+        codes = np.ascontiguousarray(codes, np.uint32)
+        self._ck(self.lib.ks_dev_window_dist(self.h, ss.h, int(k), codes.ctypes.data, len(codes), int(window),
+                                             C.c_void_p(d_dist), C.c_void_p(d_pos) if d_pos else None))
+
     # ---- device-resident -------------------------------------------------------------------
     def upload(self, seq):
         return SeqSet(self, _as_bytes_list(seq))
@@ -330,6 +369,11 @@ class SeqSet:
         self.bases = int(ctx.lib.ks_seqset_bases(h))
         self.chunks = int(ctx.lib.ks_seqset_chunks(h))
         self.buffer_bytes = int(ctx.lib.ks_seqset_buffer_bytes(h))
+        self.positions = int(ctx.lib.ks_seqset_positions(h))
+
+    def start(self, seq):
+        """buffer position of base 0 of sequence `seq`"""
+        return int(self.ctx.lib.ks_seqset_start(self.h, int(seq)))
 
     def free(self):
         if getattr(self, "h", None):

@@ -21,6 +21,7 @@
 #include "ks_layout.h"
 #include "ks_rankseg.h"
 #include "ks_sort.cuh"
+#include "ks_window.cuh"
 
 using namespace ks;
 
@@ -101,6 +102,7 @@ struct ks_ctx {
   void *pinned = nullptr;
   size_t pinned_cap = 0;
   DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, pending, foc_hist, foc_big;
+  DBuf win_match, win_cnt, win_pre, win_scratch, win_codes, win_fix, win_hist, win_pos;
   DBuf st_c, st_s, st_ea, st_eb, st_flags, st_p0, tile_xf, tile_ex, group_xf, group_S, group_ex, pending_list, pending_count, launch_rec;
 
   // timing / profiling
@@ -234,7 +236,9 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->out_score, &ctx->sc_keys_a, &ctx->sc_keys_b, &ctx->sc_vals_a, &ctx->sc_vals_b,
                  &ctx->sc_small, &ctx->sc_gcount, &ctx->sc_gstart, &ctx->sc_segfirst, &ctx->sc_segj0,
                  &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->sc_dense, &ctx->tmp_counts, &ctx->tmp_scores,
-                 &ctx->tmp_inscan, &ctx->nwords, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->launch_rec, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv};
+                 &ctx->tmp_inscan, &ctx->nwords, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->launch_rec, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv,
+                 &ctx->win_match, &ctx->win_cnt, &ctx->win_pre, &ctx->win_scratch, &ctx->win_codes, &ctx->win_fix,
+                 &ctx->win_hist, &ctx->win_pos};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -556,6 +560,23 @@ void ks_seqset_free(ks_seqset *s) {
 }
 int64_t ks_seqset_bases(const ks_seqset *s) { return s ? s->bases : 0; }
 int64_t ks_seqset_buffer_bytes(const ks_seqset *s) { return s ? s->total + KS_SLACK : 0; }
+
+int64_t ks_seqset_positions(const ks_seqset *s) { return s ? s->total : 0; }
+int64_t ks_seqset_start(const ks_seqset *s, int seq) { return (s && seq >= 0 && seq < s->nseq) ? s->starts[seq] : -1; }
+
+// pack only (no counting pass ran on this set)
+static int ensure_packed(ks_ctx *ctx, const ks_seqset *s) {
+  if (s->packed) return KS_OK;
+  int64_t nch = (s->total - 16) / 16;
+  cudaEvent_t pe = ctx->prof_begin();
+  pack_count_kernel<false><<<grid_for((size_t)nch, 256, 148u * 8u), 256, 0, ctx->stream>>>(
+      s->d_buf, 0, nch, 1, 3u, s->d_pk, s->d_brk, nullptr, nullptr);
+  ctx->prof_end(KS_PROF_COUNT, pe);
+  LAUNCHED(1);
+  CK(cudaGetLastError());
+  s->packed = true;
+  return KS_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // stage: count
@@ -904,16 +925,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
   const size_t nk = (size_t)1 << (2 * k);
   DevScanParams *d_prm = ctx->prm.as<DevScanParams>();
   CK(ctx->rec_count.ensure(64));
-  if (!s->packed) {  // no counting pass ran on this set (user-supplied weights): pack only
-    int64_t nch = (s->total - 16) / 16;
-    cudaEvent_t pe = ctx->prof_begin();
-    pack_count_kernel<false><<<grid_for((size_t)nch, 256, 148u * 8u), 256, 0, st>>>(
-        s->d_buf, 0, nch, k, (uint32_t)(nk - 1), s->d_pk, s->d_brk, nullptr, nullptr);
-    ctx->prof_end(KS_PROF_COUNT, pe);
-    LAUNCHED(1);
-    CK(cudaGetLastError());
-    s->packed = true;
-  }
+  rc = ensure_packed(ctx, s);  // no counting pass ran on this set (user-supplied weights): pack only
+  if (rc) return rc;
   unsigned long long *d_rec_count = ctx->rec_count.as<unsigned long long>();
   CK(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), st));
 
@@ -1444,6 +1457,162 @@ int ks_kmer_low_comp_regions(ks_ctx *ctx, const char *const *seqs, const int64_t
                                 counts_out, ranks_out, out);
   if (n_out) { n_out[0] = nw; n_out[1] = 0; }  // :613
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// windowed occurrence histograms
+uint32_t ks_kmer_code(const char *s, int k) {
+  uint32_t code = 0;
+  if (!s) return 0;
+  size_t i = 0;
+  auto is_n = [](char c) { return (c | 0x20) == 'n'; };
+  while (s[i]) {  // every N-free piece restarts the code; the first piece holding k bases ends the search
+    code = 0;
+    int got = 0;
+    for (; got < k && s[i] && !is_n(s[i]); ++got, ++i) code = (code << 2) | (((unsigned char)s[i] >> 1) & 3u);
+    if (got == k || !s[i]) break;
+    while (s[i] && is_n(s[i])) ++i;
+  }
+  return code;
+}
+
+int ks_dev_window_dist(ks_ctx *ctx, const ks_seqset *s, int k, const uint32_t *codes, int kmer_n, int window,
+                       int32_t *d_dist, int32_t *d_pos) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!s || !codes || !d_dist) return ctx->fail(KS_ERR_ARG, "ks_dev_window_dist: null argument");
+  if (k < 1 || k > 15) return ctx->fail(KS_ERR_ARG, "kmer sizes larger than or equal to %d not currently supported", 16);
+  if (kmer_n < 1) return ctx->fail(KS_ERR_ARG, "kmers_r should be a character vector with at least one element");
+  if (window < 2 * k) return ctx->fail(KS_ERR_ARG, "The window size must be at least two times k");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int rc = ensure_packed(ctx, s);
+  if (rc) return rc;
+  const int64_t nch = s->total / 16;  // every chunk of the layout, front pad and tail included
+  const int64_t mstride = nch + 2, pstride = nch + 1;
+  const size_t bins = (size_t)window + 1;
+  // selected k-mers are handled in batches that keep the per-chunk scratch below ~2 GiB
+  int batch = (int)std::min<int64_t>(kmer_n, std::max<int64_t>(1, (2ll << 30) / (7 * nch + 1)));
+  CK(ctx->win_match.ensure((size_t)batch * mstride * sizeof(uint16_t)));
+  CK(ctx->win_cnt.ensure((size_t)(batch + 1) * nch));
+  CK(ctx->win_pre.ensure((size_t)(batch + 1) * pstride * sizeof(uint32_t)));
+  CK(ctx->win_scratch.ensure(exclusive_scan_scratch_elems((size_t)nch) * sizeof(uint32_t)));
+  CK(ctx->win_codes.ensure((size_t)kmer_n * sizeof(uint32_t)));
+  CK(cudaMemcpyAsync(ctx->win_codes.p, codes, (size_t)kmer_n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(d_dist, 0, bins * (size_t)kmer_n * sizeof(int32_t), st));
+  if (d_pos) CK(cudaMemsetAsync(d_pos, 0, (size_t)kmer_n * (size_t)s->total * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(ctx->win_match.p, 0, (size_t)batch * mstride * sizeof(uint16_t), st));  // spare columns stay 0
+  // sequences exactly `window` long are left out by the reference (:775) but hold one window here
+  std::vector<int64_t> fix;
+  for (int q = 0; q < s->nseq; ++q)
+    if (s->lens[q] == window) fix.push_back(s->starts[q]);
+  if (!fix.empty()) {
+    CK(ctx->win_fix.ensure(fix.size() * sizeof(int64_t)));
+    CK(cudaMemcpyAsync(ctx->win_fix.p, fix.data(), fix.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  }
+  uint8_t *d_cnt = ctx->win_cnt.as<uint8_t>();
+  uint32_t *d_pre = ctx->win_pre.as<uint32_t>();
+  uint8_t *d_brk_cnt = d_cnt + (size_t)batch * nch;
+  uint32_t *d_brk_pre = d_pre + (size_t)batch * pstride;
+  const uint32_t kmask = (uint32_t)(((uint64_t)1 << (2 * k)) - 1);
+  for (int lo = 0; lo < kmer_n; lo += batch) {
+    const int nb = std::min(batch, kmer_n - lo);
+    win_match_kernel<<<grid_for((size_t)nch, WIN_THREADS, 148u * 8u), WIN_THREADS, (size_t)nb * sizeof(uint32_t), st>>>(
+        s->d_pk, s->d_brk, nch, k, kmask, ctx->win_codes.as<uint32_t>() + lo, nb, ctx->win_match.as<uint16_t>(),
+        mstride, d_cnt, lo == 0 ? d_brk_cnt : nullptr);
+    LAUNCHED(1);
+    int nl = 0;
+    for (int i = 0; i < nb; ++i)
+      nl += exclusive_scan<uint8_t, uint32_t>(d_cnt + (size_t)i * nch, (size_t)nch, d_pre + (size_t)i * pstride,
+                                              ctx->win_scratch.as<uint32_t>(), st);
+    if (lo == 0)
+      nl += exclusive_scan<uint8_t, uint32_t>(d_brk_cnt, (size_t)nch, d_brk_pre, ctx->win_scratch.as<uint32_t>(), st);
+    LAUNCHED(nl);
+    WinArgs A;
+    A.match = ctx->win_match.as<uint16_t>();
+    A.pre = d_pre;
+    A.brk = s->d_brk;
+    A.brk_pre = d_brk_pre;
+    A.mstride = mstride;
+    A.pstride = pstride;
+    A.nch = nch;
+    A.k = k;
+    A.window = window;
+    A.kmer_n = nb;
+    A.hist = d_dist + (size_t)lo * bins;
+    A.pos = d_pos ? d_pos + (size_t)lo * (size_t)s->total : nullptr;
+    A.pos_stride = s->total;
+    size_t smem = bins * (size_t)nb * sizeof(int32_t);
+    A.use_smem = smem <= 160u * 1024u;
+    if (A.use_smem && smem > 48u * 1024u)
+      CK(cudaFuncSetAttribute(win_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    win_hist_kernel<<<grid_for((size_t)nch, WIN_THREADS, A.use_smem ? 148u * 2u : 148u * 8u), WIN_THREADS,
+                      A.use_smem ? smem : 0, st>>>(A);
+    LAUNCHED(1);
+    if (!fix.empty()) {
+      int nt = (int)fix.size() * nb;
+      win_fix_kernel<<<(nt + 127) / 128, 128, 0, st>>>(A, ctx->win_fix.as<int64_t>(), (int)fix.size());
+      LAUNCHED(1);
+    }
+    CK(cudaGetLastError());
+  }
+  return KS_OK;
+}
+
+int ks_windowed_kmer_count_distributions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq,
+                                         int k, const uint32_t *codes, int kmer_n, int window,
+                                         int32_t *dist_out, int32_t *included_out, int32_t *const *pos_out) {
+  if (!ctx) return KS_ERR_ARG;
+  int rc = check_seqs(ctx, seqs, lens, nseq);
+  if (rc) return rc;
+  if (!codes || kmer_n < 1) return ctx->fail(KS_ERR_ARG, "kmers_r should be a character vector with at least one element");
+  if (k < 1 || k > 15) return ctx->fail(KS_ERR_ARG, "kmer sizes larger than or equal to %d not currently supported", 16);
+  if (window < 2 * k) return ctx->fail(KS_ERR_ARG, "The window size must be at least two times k");
+  if (!dist_out || !included_out) return ctx->fail(KS_ERR_ARG, "null output");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  // sequences that are left out (:775) are uploaded as empty strings
+  std::vector<int64_t> eff(lens, lens + nseq);
+  bool any = false;
+  for (int q = 0; q < nseq; ++q) {
+    included_out[q] = lens[q] > window;
+    if (!included_out[q]) eff[q] = 0;
+    else any = true;
+  }
+  const size_t bins = (size_t)window + 1;
+  memset(dist_out, 0, bins * (size_t)kmer_n * sizeof(int32_t));
+  if (!any) return KS_OK;
+  ks_seqset *ss = nullptr;
+  rc = host_set_acquire(ctx, eff.data(), nseq, &ss);
+  if (rc) return rc;
+  rc = upload_impl(ctx, ss, seqs, eff.data(), nseq, 0, nullptr);
+  if (rc) return rc;
+  CK(ctx->win_hist.ensure(bins * (size_t)kmer_n * sizeof(int32_t)));
+  int32_t *d_hist = ctx->win_hist.as<int32_t>();
+  if (!pos_out) {
+    rc = ks_dev_window_dist(ctx, ss, k, codes, kmer_n, window, d_hist, nullptr);
+    if (rc) return rc;
+  } else {
+    // per-position values: as many selected k-mers per round as fit ~2 GiB of int32 rows
+    int per = (int)std::min<int64_t>(kmer_n, std::max<int64_t>(1, (2ll << 30) / (4 * ss->total)));
+    CK(ctx->win_pos.ensure((size_t)per * (size_t)ss->total * sizeof(int32_t)));
+    int32_t *d_pos = ctx->win_pos.as<int32_t>();
+    for (int lo = 0; lo < kmer_n; lo += per) {
+      const int nb = std::min(per, kmer_n - lo);
+      rc = ks_dev_window_dist(ctx, ss, k, codes + lo, nb, window, d_hist + (size_t)lo * bins, d_pos);
+      if (rc) return rc;
+      for (int q = 0; q < nseq; ++q) {
+        if (!included_out[q] || !pos_out[q]) continue;
+        for (int i = 0; i < nb; ++i)
+          CK(cudaMemcpyAsync(pos_out[q] + (size_t)(lo + i) * (size_t)lens[q],
+                             d_pos + (size_t)i * (size_t)ss->total + ss->starts[q], (size_t)lens[q] * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, st));
+      }
+      CK(cudaStreamSynchronize(st));
+    }
+  }
+  CK(cudaMemcpyAsync(dist_out, d_hist, bins * (size_t)kmer_n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return KS_OK;
 }
 
 int ks_kmer_scores(ks_ctx *ctx, int k, const int32_t *counts, double total, int mode, double param,

@@ -424,3 +424,73 @@ def test_seqbatch_input(ctx, oracle):
     g = ctx.kmer_low_comp_regions(api.SeqBatch.from_list(seqs), 7, 20, 4, 0.7)
     assert (g["counts"] == o["counts"]).all()
     assert_spans(g, o, exact_scores=False, what="seqbatch")
+
+
+# ---- windowed occurrence histograms --------------------------------------------
+def _window_case(ctx, oracle, seqs, kms, k, window, what):
+    want = oracle.window_dist(seqs, kms, k, window, True)
+    got = ctx.window_kmer_dist(seqs, kms, window, freq=False, ret_flag=1)
+    assert np.array_equal(got["dist"].T, want["dist"]), what
+    assert np.array_equal(got["seq_i"], want["included"]), what
+    for g, w in zip(got["scores"], want["pos"]):
+        assert (g is None) == (w is None), what
+        if g is not None:
+            assert np.array_equal(g.T, w), what
+    got2 = ctx.window_kmer_dist(seqs, kms, window, freq=False)
+    assert got2["scores"] is None and np.array_equal(got2["dist"].T, want["dist"]), what
+
+
+def test_window_dist_small(ctx, oracle):
+    rng = np.random.default_rng(4100)
+    for t in range(40):
+        k = int(rng.integers(1, 9))
+        window = int(rng.integers(2 * k, 200))
+        seqs = [rand_seq(rng, int(rng.integers(0, 3000)), p_n=float(rng.choice([0, 0.05, 0.3])))
+                for _ in range(int(rng.integers(1, 6)))]
+        seqs += [rand_seq(rng, window), rand_seq(rng, window + 1), b"", rand_seq(rng, window - 1)]
+        kms = [oracle.kmer_seq(k, int(c)).encode() for c in rng.integers(0, 4 ** min(k, 3), int(rng.integers(1, 7)))]
+        kms = [x[-k:] if len(x) >= k else (b"A" * (k - len(x)) + x) for x in kms]
+        if t % 4 == 0:
+            kms += [b"N" * k, kms[0]]
+        _window_case(ctx, oracle, seqs, kms, k, window, "t=%d k=%d window=%d" % (t, k, window))
+
+
+def test_window_dist_large_window_and_tandem(ctx, oracle):
+    rng = np.random.default_rng(4200)
+    s = np.frombuffer(rand_seq(rng, 120_000), np.uint8).copy()
+    s[30_000:36_000] = np.tile(np.frombuffer(b"AC", np.uint8), 3000)  # dense occurrences
+    s[80_000:80_020] = ord("N")
+    seqs = [s.tobytes(), rand_seq(rng, 50_001), rand_seq(rng, 50_000)]
+    # 50 001 bins x 1 k-mer does not fit shared memory -> global histogram path
+    _window_case(ctx, oracle, seqs, [b"AC"], 2, 50_000, "global bins")
+    _window_case(ctx, oracle, seqs, [b"AC", b"CA", b"GT", b"AA"], 2, 1000, "shared bins")
+
+
+def test_window_dist_device_stage_excludes_exact_length(ctx, oracle):
+    import torch
+    rng = np.random.default_rng(4300)
+    window, k = 64, 2
+    seqs = [rand_seq(rng, 5000, p_n=0.05), rand_seq(rng, window), rand_seq(rng, window), rand_seq(rng, 300)]
+    kms = [b"AC", b"TT", b"GA"]
+    want = oracle.window_dist(seqs, kms, k, window, True)
+    ss = ctx.upload(seqs)
+    codes = np.array([oracle.kmer_code(x, k) for x in kms], np.uint32)
+    d_dist = torch.empty((len(kms), window + 1), dtype=torch.int32, device="cuda")
+    d_pos = torch.empty((len(kms), ss.positions), dtype=torch.int32, device="cuda")
+    ctx.dev_window_dist(ss, k, codes, window, d_dist.data_ptr(), d_pos.data_ptr())
+    ctx.sync()
+    assert np.array_equal(d_dist.cpu().numpy(), want["dist"])
+    pos = d_pos.cpu().numpy()
+    for q, w in enumerate(want["pos"]):
+        st = ss.start(q)
+        got = pos[:, st:st + len(seqs[q])]
+        assert np.array_equal(got, w if w is not None else np.zeros_like(got)), q
+    ss.free()
+
+
+def test_window_dist_errors(ctx):
+    from kmer_spans_b200._lib import KspansError
+    with pytest.raises(KspansError, match="two times k"):
+        ctx.window_kmer_dist([b"ACGTACGTACGT"], [b"ACG"], 5)
+    with pytest.raises(ValueError, match="same size"):
+        ctx.window_kmer_dist([b"ACGTACGTACGT"], [b"ACG", b"AC"], 8)
