@@ -8,9 +8,9 @@
  *   kmer_regions_r/5         -> ks_kmer_regions             (reference :490-546)
  *   kmer_low_comp_regions/5  -> ks_kmer_low_comp_regions    (reference :548-621)
  *   kmer_seq_r/1             -> ks_kmer_seq (host only)     (reference :623-639)
- *   tr_lr_regions_r/5, windowed_kmer_count_distributions_r/5: outside the accelerated path
- *       (SURVEY.md section 8f); registered so that sourcing kmer_spans.R succeeds, they raise an R
- *       error that points at the reference build.
+ *   windowed_kmer_count_distributions_r/5 -> ks_windowed_kmer_count_distributions (reference :715-793)
+ *   tr_lr_regions_r/5: outside the accelerated path; registered so that
+ *       sourcing kmer_spans.R succeeds, it raises an R error that points at the reference build.
  *   kmer_mode_regions/8 (extension): counts -> scores(mode) -> scan resident on the GPU.
  *
  * Argument checks, their order and the error texts follow the reference; result lists have the
@@ -284,11 +284,67 @@ SEXP tr_lr_regions_r(SEXP a, SEXP b, SEXP c, SEXP d, SEXP e) {
         "load the reference build of kmer_spans.so for lr.regions()");
   return NULL;
 }
-SEXP windowed_kmer_count_distributions_r(SEXP a, SEXP b, SEXP c, SEXP d, SEXP e) {
-  (void)a; (void)b; (void)c; (void)d; (void)e;
-  error("windowed_kmer_count_distributions_r is not part of the CUDA hot path; "
-        "load the reference build of kmer_spans.so for window.kmer.dist()");
-  return NULL;
+/* ---- windowed_kmer_count_distributions_r (reference :715-793) -------------------------------- */
+SEXP windowed_kmer_count_distributions_r(SEXP seq_r, SEXP kmers_r, SEXP k_r, SEXP window_r, SEXP ret_flag_r) {
+  if (TYPEOF(seq_r) != STRSXP || length(seq_r) < 1)
+    error("seq_r should be a character vector with at least one element");
+  if (TYPEOF(kmers_r) != STRSXP || length(kmers_r) < 1)
+    error("kmers_r should be a character vector with at least one element");
+  if (TYPEOF(k_r) != INTSXP || length(k_r) != 1)
+    error("k_r should be an integer vector with one element");
+  if (TYPEOF(window_r) != INTSXP || length(window_r) != 1)
+    error("window_r should be an integer vector with one element");
+  if (TYPEOF(ret_flag_r) != INTSXP || length(ret_flag_r) != 1)
+    error("ret_flag_r should a single integer");
+  int k = asInteger(k_r);
+  if (k < 0 || k >= GLUE_MAX_K)
+    error("kmer sizes larger than or equal to %d not currently supported", GLUE_MAX_K);
+  int kmer_n = length(kmers_r);
+  for (int i = 0; i < kmer_n; ++i)
+    if (length(STRING_ELT(kmers_r, i)) != k) error("All kmers specified must be of the same length");
+  int window = asInteger(window_r);
+  if (window < 0 || window < 2 * k) error("The window size must be at least two times k");
+  if (k < 1) error("k must be a positive integer");
+  int want_pos = asInteger(ret_flag_r) & 1;
+  int nseq = length(seq_r);
+
+  SEXP ret = PROTECT(allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(ret, 0, allocMatrix(INTSXP, window + 1, kmer_n));
+  SET_VECTOR_ELT(ret, 1, allocVector(INTSXP, nseq));
+  uint32_t *codes = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)kmer_n);
+  int32_t **pos = NULL;
+  seq_view v;
+  int ok = view_strsxp(seq_r, &v) && codes;
+  if (ok && want_pos) {
+    /* R-owned result matrices, allocated before any CUDA work (:776-783) */
+    pos = (int32_t **)calloc((size_t)nseq, sizeof(int32_t *));
+    ok = pos != NULL;
+    if (ok) {
+      SET_VECTOR_ELT(ret, 2, allocVector(VECSXP, nseq));
+      for (int i = 0; i < nseq; ++i) {
+        if (v.len[i] <= window) continue;
+        SET_VECTOR_ELT(VECTOR_ELT(ret, 2), i, allocMatrix(INTSXP, (int)v.len[i], kmer_n));
+        pos[i] = (int32_t *)INTEGER(VECTOR_ELT(VECTOR_ELT(ret, 2), i));
+      }
+    }
+  }
+  int rc = KS_ERR_NOMEM;
+  ks_ctx *ctx = ok ? glue_ctx() : NULL;
+  if (ok && ctx) {
+    for (int i = 0; i < kmer_n; ++i) codes[i] = ks_kmer_code(CHAR(STRING_ELT(kmers_r, i)), k);
+    rc = ks_windowed_kmer_count_distributions(ctx, v.ptr, v.len, v.n, k, codes, kmer_n, window,
+                                              (int32_t *)INTEGER(VECTOR_ELT(ret, 0)),
+                                              (int32_t *)INTEGER(VECTOR_ELT(ret, 1)), pos);
+    if (rc) fail_from_ctx(ctx);
+  } else if (!ok) {
+    snprintf(g_msg, sizeof g_msg, "out of memory");
+  }
+  view_free(&v);
+  free(codes);
+  free(pos);
+  UNPROTECT(1);
+  if (rc) error("%s", g_msg);
+  return ret;
 }
 
 static const R_CallMethodDef callMethods[] = {

@@ -45,6 +45,14 @@ def test_argument_errors_match_reference(glue, ref):
         ("kmer_low_comp_regions", [("s", [b"ACGT"]), ("i", 2), ("d", 1.0), ("d", 1.0), ("d", 0.5)]),
         ("kmer_seq_r", [("i", 0)]),
         ("kmer_seq_r", [("i", [1, 2])]),
+        ("windowed_kmer_count_distributions_r", [("i", 1), ("s", [b"AC"]), ("i", 2), ("i", 8), ("i", 0)]),
+        ("windowed_kmer_count_distributions_r", [("s", [b"ACGT"]), ("i", 1), ("i", 2), ("i", 8), ("i", 0)]),
+        ("windowed_kmer_count_distributions_r", [("s", [b"ACGT"]), ("s", [b"AC"]), ("d", 2.0), ("i", 8), ("i", 0)]),
+        ("windowed_kmer_count_distributions_r", [("s", [b"ACGT"]), ("s", [b"AC"]), ("i", 2), ("i", [8, 9]), ("i", 0)]),
+        ("windowed_kmer_count_distributions_r", [("s", [b"ACGT"]), ("s", [b"AC"]), ("i", 2), ("i", 8), ("d", 0.0)]),
+        ("windowed_kmer_count_distributions_r", [("s", [b"ACGT"]), ("s", [b"AC"]), ("i", 16), ("i", 40), ("i", 0)]),
+        ("windowed_kmer_count_distributions_r", [("s", [b"ACGT"]), ("s", [b"AC", b"ACG"]), ("i", 2), ("i", 8), ("i", 0)]),
+        ("windowed_kmer_count_distributions_r", [("s", [b"ACGT"]), ("s", [b"AC"]), ("i", 2), ("i", 3), ("i", 0)]),
     ]
     for name, args in bad:
         with pytest.raises(RuntimeError) as e_ref:
@@ -62,6 +70,27 @@ def test_kmer_seq_r_matches_reference(glue, ref):
 def test_out_of_path_entries_are_registered_stubs(glue):
     with pytest.raises(RuntimeError, match="not part of the CUDA hot path"):
         glue.call_raw("tr_lr_regions_r", [("s", [b"A"]), ("i", [2, 1]), ("s", [b"AA"]), ("d", 1.0), ("d", 1.0)])
+
+
+@pytest.mark.gpu
+def test_window_dist_call_matches_reference(glue, ref):
+    rng = np.random.default_rng(2025)
+    for trial in range(6):
+        k = int(rng.choice([1, 2, 3, 5]))
+        window = int(rng.integers(2 * k, 120))
+        seqs = [planted(rng, int(rng.integers(50, 5000))) for _ in range(int(rng.integers(1, 5)))]
+        seqs += [planted(rng, window), b"ACGT"]
+        kms = [bytes(rng.choice(list(b"ACGT"), k).astype(np.uint8)) for _ in range(int(rng.integers(1, 5)))]
+        for flag in (0, 1):
+            a = ref.call_window_dist(seqs, kms, k, window, flag)
+            b = glue.call_window_dist(seqs, kms, k, window, flag)
+            assert np.array_equal(a["dist"], b["dist"]) and np.array_equal(a["included"], b["included"])
+            if flag == 0:
+                assert a["pos"] is None and b["pos"] is None
+            else:
+                for x, y in zip(a["pos"], b["pos"]):
+                    assert (x is None) == (y is None)
+                    assert x is None or np.array_equal(x, y)
 
 
 @pytest.mark.gpu
