@@ -101,6 +101,16 @@ int ks_kmer_seq(int k, uint64_t code, char *out /* k+1 bytes */);
  * use it: the 2-bit code of a clean string of k bases (first base most significant).  Host only. */
 uint32_t ks_kmer_code(const char *kmer, int k);
 
+/* tr_lr_regions_r (:649-713, core find_kmer_tr_lr_regions :329-395), SURVEY 8(f) row 3.
+ * init_scores / trans_scores: double[4^k] in 2-bit code order (the reordering by k-mer strings of
+ * :688-696 is the caller's job: table[ks_kmer_code(kmers[i], k)] = value[i]).  Every run starts with
+ * S = max(init[first k-mer], 0), then S = max(S + trans[k-mer ending at i], 0); every excursion that
+ * returns to 0 is tested on peak - start >= min_length and the scan resumes behind its peak; an
+ * excursion open at the run end is tested, not re-scanned.  Spans: seq_id, start, end all 1-based,
+ * score = peak, second score column 0.  NaN scores are rejected (KS_ERR_RANGE), -Inf is allowed. */
+int ks_tr_lr_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,
+                     const double *init_scores, const double *trans_scores, int min_length, ks_spans *out);
+
 /* windowed_kmer_count_distributions_r (:715-793, core :398-449), SURVEY 8(f) row 4.
  * codes[kmer_n] = 2-bit codes of the selected k-mers (ks_kmer_code), 1 <= k <= 15, window >= 2k.
  * dist_out[i * (window+1) + c] = number of windows (window consecutive bases inside one run of one
@@ -136,6 +146,9 @@ int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, doubl
  * gathers the 4-byte count (table L2 resident up to k = 12) and maps it through a dense LUT. */
 int ks_dev_scan_counts(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
                        int min_width, double min_score, ks_spans *host_out_or_null, uint64_t *n_spans);
+/* transition-score scan on a resident set; d_init / d_trans = device double[4^k] in code order */
+int ks_dev_tr_lr_regions(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_init, const double *d_trans,
+                         int min_length, ks_spans *host_out_or_null, uint64_t *n_spans);
 /* windowed occurrence histograms on a resident set: d_dist = device int32[kmer_n * (window+1)]
  * (overwritten); d_pos = NULL or device int32[kmer_n * ks_seqset_positions(s)] (overwritten), the value
  * of the window starting at every buffer position (position of base i of sequence q:

@@ -70,6 +70,8 @@ SIGNATURES = {
     "ks_fold_carry": (_i, [_i, _vp, _i, _i, _vp]),
     "ks_dev_pipeline": (_i, [_vp, _vp, _i, _i, _d, _d, _i, _d, _vp, _vp, _pd, C.POINTER(KsSpans), _pu64]),
     "ks_kmer_code": (C.c_uint32, [C.c_char_p, _i]),
+    "ks_tr_lr_regions": (_i, [_vp] + _SEQS + [_i, _vp, _vp, _i, C.POINTER(KsSpans)]),
+    "ks_dev_tr_lr_regions": (_i, [_vp, _vp, _i, _vp, _vp, _i, C.POINTER(KsSpans), _pu64]),
     "ks_windowed_kmer_count_distributions": (_i, [_vp] + _SEQS + [_i, _vp, _i, _i, _vp, _vp, _vp]),
     "ks_dev_window_dist": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp]),
     "ks_seqset_positions": (_i64, [_vp]),

@@ -313,6 +313,31 @@ class Context:
                                          W.ctypes.data))
         return W
 
+    def lr_regions(self, seq, params, kmers, kmer_scores, trans_scores):
+        """lr.regions (kmer_spans.R:88-99) on tr_lr_regions_r (src/kmer_spans.c:649-713): params = (k,
+        min_length); kmers = the 4^k k-mer strings in the order of the two score vectors.  Returns
+        kmer_scores = the (4^k, 2) table re-ordered to 2-bit code order (init, trans), pos (n, 3) =
+        seq.i, beg, end (all 1-based), score (n, 2)."""
+        k, min_length = int(params[0]), int(params[1])
+        n = 4 ** k
+        kmers = [x.encode() if isinstance(x, str) else bytes(x) for x in kmers]
+        ks_in = np.ascontiguousarray(kmer_scores, np.float64)
+        tr_in = np.ascontiguousarray(trans_scores, np.float64)
+        if not (1 <= k <= 15):
+            raise KspansError(1, "k should be a positive value less than MAX_K")
+        if len(kmers) != n or ks_in.size != n or tr_in.size != n:
+            raise KspansError(1, "kmers_r, freq_a, freq_b should all be 4^k long")
+        codes = np.fromiter((self.lib.ks_kmer_code(x, k) for x in kmers), np.int64, n)
+        table = np.zeros((2, n), np.float64)
+        table[0, codes] = ks_in  # later entries win, like the reference's loop (:689-696)
+        table[1, codes] = tr_in
+        a = _SeqArgs(_as_bytes_list(seq))
+        sp = KsSpans()
+        self._ck(self.lib.ks_tr_lr_regions(self.h, a.ptrs, a.lens, a.n, k, table[0].ctypes.data,
+                                           table[1].ctypes.data, min_length, C.byref(sp)))
+        pos, score = _spans_to_numpy(self.lib, sp)
+        return dict(kmer_scores=table.T.copy(), pos=pos, score=score)
+
     def window_kmer_dist(self, seq, kmers, window, freq=True, ret_flag=0):
         """window.kmer.dist (kmer_spans.R:103-120) on windowed_kmer_count_distributions_r
         (src/kmer_spans.c:715-793): dist = (window+1) x len(kmers) occurrence histogram (column sums

@@ -103,6 +103,8 @@ struct ks_ctx {
   size_t pinned_cap = 0;
   DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, pending, foc_hist, foc_big;
   DBuf win_match, win_cnt, win_pre, win_scratch, win_codes, win_fix, win_hist, win_pos;
+  DBuf st_aux, child_pk, child_c, child_count, tr_tables;
+  size_t child_cap = 0;
   DBuf st_c, st_s, st_ea, st_eb, st_flags, st_p0, tile_xf, tile_ex, group_xf, group_S, group_ex, pending_list, pending_count, launch_rec;
 
   // timing / profiling
@@ -238,7 +240,8 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->sc_dense, &ctx->tmp_counts, &ctx->tmp_scores,
                  &ctx->tmp_inscan, &ctx->nwords, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->launch_rec, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv,
                  &ctx->win_match, &ctx->win_cnt, &ctx->win_pre, &ctx->win_scratch, &ctx->win_codes, &ctx->win_fix,
-                 &ctx->win_hist, &ctx->win_pos};
+                 &ctx->win_hist, &ctx->win_pos, &ctx->st_aux, &ctx->child_pk, &ctx->child_c, &ctx->child_count,
+                 &ctx->tr_tables};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -886,6 +889,14 @@ static int ensure_tiles(ks_ctx *ctx, size_t tiles, bool lut_mode, bool need_p0) 
   return KS_OK;
 }
 
+static int ensure_children(ks_ctx *ctx, size_t cap) {
+  if (cap <= ctx->child_cap) return KS_OK;
+  CK(ctx->child_pk.ensure(cap * 8));
+  CK(ctx->child_c.ensure(cap * 8));
+  ctx->child_cap = cap;
+  return KS_OK;
+}
+
 static int ensure_recs(ks_ctx *ctx, size_t cap) {
   if (cap <= ctx->rec_cap) return KS_OK;
   cudaStream_t st = ctx->stream;
@@ -913,6 +924,7 @@ struct ScanTable {  // what scan_level_kernel gathers from
   bool use_lut = false;
   const uint32_t *counts = nullptr;
   uint32_t lut_size = 0, sp_n = 0;
+  bool tr = false;  // transition-score scan: ctx->wfx = [trans | init], every close is re-scanned
 };
 }  // namespace
 
@@ -936,6 +948,11 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
   rc = ensure_recs(ctx, std::max<size_t>((size_t)1 << 16, (size_t)(dense_chunks / 64)));
   if (rc) return rc;
 
+  if (tab.tr) {
+    CK(ctx->child_count.ensure(64));
+    rc = ensure_children(ctx, std::max<size_t>((size_t)1 << 16, (size_t)(dense_chunks / 4)));
+    if (rc) return rc;
+  }
   unsigned long long level_start = 0;  // records before this level
   int64_t nseg = 0, total_chunks = dense_chunks;
   int64_t dense_chunk0 = 0;
@@ -960,6 +977,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     if (tiles > 0xfffffff0ull) return ctx->fail(KS_ERR_ARG, "input too large for one scan launch");
     rc = ensure_tiles(ctx, tiles, tab.use_lut, nseg != 0);
     if (rc) return rc;
+    if (tab.tr) CK(ctx->st_aux.ensure(tiles * TILE_THREADS * 4));
     LevelArgs A;
     memset(&A, 0, sizeof A);
     A.pk = s->d_pk;
@@ -1013,8 +1031,18 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.rec_mlo = ctx->rec_mlo.as<uint64_t>();
     A.rec_count = d_rec_count;
     A.rec_cap = ctx->rec_cap;
+    A.tr = tab.tr ? 1 : 0;
+    A.buf = s->d_buf;
+    A.nk = (uint32_t)nk;
+    A.st_aux = ctx->st_aux.as<uint32_t>();
+    A.child_pk = ctx->child_pk.as<int64_t>();
+    A.child_c = ctx->child_c.as<int64_t>();
+    A.child_count = ctx->child_count.as<unsigned long long>();
+    A.child_cap = ctx->child_cap;
+    if (tab.tr) CK(cudaMemsetAsync(ctx->child_count.p, 0, sizeof(unsigned long long), st));
     cudaEvent_t ps = ctx->prof_begin();
-    if (tab.use_lut) scan_gather_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    if (tab.tr) scan_gather_kernel<false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (tab.use_lut) scan_gather_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else scan_gather_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     group_scan_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
     group_top_kernel<<<1, TSCAN_THREADS, 0, st>>>(A);
@@ -1036,7 +1064,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
       group_top_kernel<<<1, TSCAN_THREADS, 0, st>>>(A);
       LAUNCHED(1);
     }
-    if (tab.use_lut) scan_walk_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    if (tab.tr) scan_walk_kernel<false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (tab.use_lut) scan_walk_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else scan_walk_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     group_ex_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
     if (exchange && have_carry) {
@@ -1058,24 +1087,31 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     ctx->prof_end(level == 0 ? KS_PROF_SCAN0 : KS_PROF_SCANN, ps);
     LAUNCHED(6);
     CK(cudaGetLastError());
-    struct { unsigned long long cnt; } hres;
+    struct { unsigned long long cnt, children; } hres;
+    hres.children = 0;
     DevScanParams hprm;
     CK(cudaMemcpyAsync(&hres.cnt, d_rec_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (tab.tr)
+      CK(cudaMemcpyAsync(&hres.children, ctx->child_count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     if (level == 0) CK(cudaMemcpyAsync(&hprm, d_prm, sizeof hprm, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (level == 0 && hprm.err)
+    if (level == 0 && (hprm.err & 1))
       return ctx->fail(KS_ERR_RANGE, "a k-mer weight is +Inf or >= 2^40: outside the exact scan range");
+    if (level == 0 && tab.tr && (hprm.err & 2))
+      return ctx->fail(KS_ERR_RANGE, "a transition or k-mer score is NaN");
     count_inscan = false;  // every position of this level has been counted, also if we must retry
-    if (hres.cnt > ctx->rec_cap) {
+    if (hres.cnt > ctx->rec_cap || hres.children > ctx->child_cap) {
       // record buffer too small: grow (keeping earlier levels), rewind the counter, redo the level
-      rc = ensure_recs(ctx, (size_t)hres.cnt + (size_t)hres.cnt / 8 + 1024);
+      if (hres.cnt > ctx->rec_cap) rc = ensure_recs(ctx, (size_t)hres.cnt + (size_t)hres.cnt / 8 + 1024);
+      if (!rc && hres.children > ctx->child_cap)
+        rc = ensure_children(ctx, (size_t)hres.children + (size_t)hres.children / 8 + 1024);
       if (rc) return rc;
       CK(cudaMemcpyAsync(d_rec_count, &level_start, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
       CK(cudaStreamSynchronize(st));
       continue;
     }
     if (level > 0) revisit_chunks += (uint64_t)total_chunks;
-    unsigned long long n_new = hres.cnt - level_start;
+    unsigned long long n_new = tab.tr ? hres.children : hres.cnt - level_start;
     ++level;
     if (n_new == 0) break;
     // child segments of the records this level emitted
@@ -1084,9 +1120,14 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     CK(ctx->seg_chunks.ensure(n_new * 8));
     CK(ctx->seg_chunk0.ensure((n_new + 1) * 8));
     CK(ctx->scan_tmp.ensure(exclusive_scan_scratch_elems(n_new) * 8));
-    seg_build_kernel<<<blocks_exact(n_new, 256), 256, 0, st>>>(
-        ctx->rec_pk.as<int64_t>(), ctx->rec_c.as<int64_t>(), level_start, n_new, mw, d_inscan != nullptr,
-        ctx->seg_start.as<int64_t>(), ctx->seg_len.as<int64_t>(), ctx->seg_chunks.as<uint64_t>());
+    if (tab.tr)  // the re-scan requests were filtered when they were appended
+      seg_build_kernel<<<blocks_exact(n_new, 256), 256, 0, st>>>(
+          ctx->child_pk.as<int64_t>(), ctx->child_c.as<int64_t>(), 0, n_new, 0, 1, ctx->seg_start.as<int64_t>(),
+          ctx->seg_len.as<int64_t>(), ctx->seg_chunks.as<uint64_t>());
+    else
+      seg_build_kernel<<<blocks_exact(n_new, 256), 256, 0, st>>>(
+          ctx->rec_pk.as<int64_t>(), ctx->rec_c.as<int64_t>(), level_start, n_new, mw, d_inscan != nullptr,
+          ctx->seg_start.as<int64_t>(), ctx->seg_len.as<int64_t>(), ctx->seg_chunks.as<uint64_t>());
     LAUNCHED(1);
     LAUNCHED((exclusive_scan<uint64_t, uint64_t>(ctx->seg_chunks.as<uint64_t>(), n_new,
                                                  ctx->seg_chunk0.as<uint64_t>(), ctx->scan_tmp.as<uint64_t>(), st)));
@@ -1138,7 +1179,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
   finalize_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(
       d_perm, n, ctx->rec_beg.as<int64_t>(), ctx->rec_pk.as<int64_t>(), ctx->rec_mhi.as<int64_t>(),
       ctx->rec_mlo.as<uint64_t>(), s->d_starts, s->nseq, d_prm, ctx->out_pos.as<int32_t>(),
-      ctx->out_score.as<double>());
+      ctx->out_score.as<double>(), tab.tr ? 1 : 0);
   LAUNCHED(1);
   CK(cudaGetLastError());
   if (host_out) {
@@ -1194,6 +1235,39 @@ int ks_dev_scan_shard(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W,
   ShardCtl sh;
   sh.chunk0 = chunk0; sh.nchunks = nchunks; sh.fn = fn; sh.user = user;
   return scan_table_impl(ctx, s, k, d_W, thr, min_width, min_score, nullptr, host_out, n_spans, &sh);
+}
+
+// Transition-score scan (tr_lr_regions_r core, :329-395): d_init / d_trans are double[4^k] in 2-bit code order.
+int ks_dev_tr_lr_regions(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_init, const double *d_trans,
+                         int min_length, ks_spans *host_out, uint64_t *n_spans) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!s || !d_init || !d_trans) return ctx->fail(KS_ERR_ARG, "ks_dev_tr_lr_regions: null argument");
+  if (k < 1 || k > 15) return ctx->fail(KS_ERR_ARG, "k should be a positive value less than MAX_K");
+  if (min_length < 0) return ctx->fail(KS_ERR_ARG, "min_length should be a positive integer");
+  if (host_out) { host_out->pos = nullptr; host_out->score = nullptr; host_out->n = 0; }
+  if (n_spans) *n_spans = 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t nk = (size_t)1 << (2 * k);
+  // both tables -> one exact fixed-point table [trans | init] with a common scale; no score threshold
+  CK(ctx->wfx.ensure(2 * nk * 8));
+  CK(ctx->prm.ensure(sizeof(DevScanParams)));
+  DevScanParams *d_prm = ctx->prm.as<DevScanParams>();
+  CK(cudaMemsetAsync(d_prm, 0, sizeof(DevScanParams), st));
+  const double no_min = -INFINITY;
+  cudaEvent_t pw = ctx->prof_begin();
+  wmax_kernel<<<grid_for(nk, 256), 256, 0, st>>>(d_trans, nk, 0.0, d_prm);
+  wmax_kernel<<<grid_for(nk, 256), 256, 0, st>>>(d_init, nk, 0.0, d_prm);
+  wfx_kernel<<<grid_for(nk, 256), 256, 0, st>>>(d_trans, nk, 0.0, ctx->wfx.as<int64_t>(), d_prm,
+                                               (uint64_t)min_length, no_min);
+  wfx_kernel<<<grid_for(nk, 256), 256, 0, st>>>(d_init, nk, 0.0, ctx->wfx.as<int64_t>() + nk, d_prm,
+                                               (uint64_t)min_length, no_min);
+  ctx->prof_end(KS_PROF_WFX, pw);
+  LAUNCHED(4);
+  CK(cudaGetLastError());
+  ScanTable tab;
+  tab.tr = true;
+  return scan_core(ctx, s, k, tab, (uint64_t)min_length, nullptr, host_out, n_spans, nullptr);
 }
 
 // Scan with score = f(count): the count -> score function is the one the last
@@ -1457,6 +1531,30 @@ int ks_kmer_low_comp_regions(ks_ctx *ctx, const char *const *seqs, const int64_t
                                 counts_out, ranks_out, out);
   if (n_out) { n_out[0] = nw; n_out[1] = 0; }  // :613
   return rc;
+}
+
+// transition-score scan from host buffers
+int ks_tr_lr_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,
+                     const double *init_scores, const double *trans_scores, int min_length, ks_spans *out) {
+  if (!ctx) return KS_ERR_ARG;
+  int rc = check_seqs(ctx, seqs, lens, nseq);
+  if (rc) return rc;
+  if (k < 1 || k > 15) return ctx->fail(KS_ERR_ARG, "k should be a positive value less than MAX_K");
+  if (min_length < 0) return ctx->fail(KS_ERR_ARG, "min_length should be a positive integer");
+  if (!init_scores || !trans_scores || !out) return ctx->fail(KS_ERR_ARG, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  const size_t nk = (size_t)1 << (2 * k);
+  cudaStream_t st = ctx->stream;
+  CK(ctx->tr_tables.ensure(2 * nk * 8));
+  double *d_init = ctx->tr_tables.as<double>(), *d_trans = d_init + nk;
+  CK(cudaMemcpyAsync(d_init, init_scores, nk * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_trans, trans_scores, nk * 8, cudaMemcpyHostToDevice, st));
+  ks_seqset *ss = nullptr;
+  rc = host_set_acquire(ctx, lens, nseq, &ss);
+  if (rc) return rc;
+  rc = upload_impl(ctx, ss, seqs, lens, nseq, 0, nullptr);
+  if (rc) return rc;
+  return ks_dev_tr_lr_regions(ctx, ss, k, d_init, d_trans, min_length, out, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------

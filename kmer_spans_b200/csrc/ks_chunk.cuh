@@ -339,6 +339,79 @@ KS_HD void chunk_finish_entering(fx_t S_in, const Ex &ex_in, fx_t preM, int64_t 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Transition-score scan (find_kmer_tr_lr_regions, /root/reference/src/kmer_spans.c:329-395).
+// Same clamped scan, different bookkeeping:
+//   * `first` marks positions that carry a run's INITIAL score (the first k-mer of the run, :344-354);
+//     the reference books everything that happens there one position later (i = a + k)
+//   * `real` marks positions the reference's loop visits; a close at a real position is tested on
+//     width only (:377) and ALWAYS makes the scan resume behind the peak (:382-388) -> emit.child;
+//     a close forced by the end of the run is the terminal test (:392-393): reported, not re-scanned
+// emit.out(beg, pk, M) reports a region, emit.child(pk, c) asks for the re-scan of (pk, c].
+template <class Scores, class Emit>
+KS_HD void chunk_walk_tr(const Scores &s, uint32_t live, uint32_t first, uint32_t real, fx_t S_in, int64_t p0,
+                         const ScanParams &prm, Emit &emit, Ex &ex, fx_t &preM, int64_t &prePk,
+                         int &first_zero) {
+  const fx_t cap = ((fx_t)1) << 62;
+  const int64_t sigma = S_in > cap ? (1ll << 62) : (int64_t)S_in;
+  const fx_t shift = S_in - (fx_t)sigma;
+  const int64_t NEG = -(1ll << 62);
+  int64_t S = sigma;
+  int64_t M = NEG;
+  int64_t pk = -1, beg = -1;
+  int64_t pM = NEG, pPk = -1;
+  bool started = false;
+  first_zero = -1;
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) {
+    int64_t Sn = 0;
+    if (live & (1u << j)) {
+      Sn = S + s[j];
+      Sn = Sn > 0 ? Sn : 0;
+    }
+    const int64_t pos = p0 + j + ((first >> j) & 1u);
+    if (S == 0 && Sn > 0) { started = true; beg = pos; pk = pos; M = Sn; }
+    if (Sn == 0) {
+      if (S > 0 && started) {
+        if (qualifies(prm, beg, pk, (fx_t)M)) emit.out(beg, pk, (fx_t)M);
+        if (real & (1u << j)) emit.child(pk, (int64_t)(p0 + j), prm.min_width);
+      }
+      if (first_zero < 0) { first_zero = j; pM = M; pPk = pk; }
+    } else if (Sn > M) {
+      M = Sn; pk = pos;
+    }
+    S = Sn;
+  }
+  if (first_zero < 0) { pM = M; pPk = pk; }
+  preM = pM == NEG ? -(((fx_t)1) << 126) : (fx_t)pM + shift;
+  prePk = pPk;
+  if (S > 0) {
+    ex.open = 1;
+    ex.pk = pk;
+    if (started) { ex.reset = 1; ex.beg = beg; ex.M = (fx_t)M; }
+    else { ex.reset = 0; ex.beg = -1; ex.M = (fx_t)M + shift; }
+  } else {
+    ex.reset = 1; ex.open = 0; ex.M = -(((fx_t)1) << 126); ex.beg = -1; ex.pk = -1;
+  }
+}
+
+template <class Emit>
+KS_HD void chunk_finish_entering_tr(fx_t S_in, const Ex &ex_in, fx_t preM, int64_t prePk, int first_zero,
+                                    int64_t p0, uint32_t real, const ScanParams &prm, Emit &emit) {
+  if (S_in > 0 && first_zero >= 0) {
+    fx_t M = ex_in.M;
+    int64_t pk = ex_in.pk;
+    if (preM > M) { M = preM; pk = prePk; }
+    if (qualifies(prm, ex_in.beg, pk, M)) emit.out(ex_in.beg, pk, M);
+    if (real & (1u << first_zero)) emit.child(pk, (int64_t)(p0 + first_zero), prm.min_width);
+  }
+}
+// re-scan of (pk, c]: a region inside it has pk' - beg' <= c - pk - 2, so shorter tails are dropped
+KS_HD bool tr_child_wanted(int64_t pk, int64_t c, uint64_t min_width) {
+  int64_t room = c - pk - 2;
+  return room >= 0 && (uint64_t)room >= min_width;
+}
+
 // Next-level segment spawned by a qualifying excursion (beg, pk, c): the reference restarts the
 // scan with S = 0 at pk + 1 (:281-282,303) and by the re-synchronisation lemma is back
 // on the parent trajectory at c, so the child scan covers [pk + 1, c].  Without in-scan counting a

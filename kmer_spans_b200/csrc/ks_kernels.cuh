@@ -152,7 +152,7 @@ struct DevScanParams {
   uint64_t min_lo;
   int64_t min_hi;
   int32_t qs;
-  int32_t err;             // 1: a weight is +inf or >= 2^40
+  int32_t err;             // bit 0: a weight is +inf or >= 2^40; bit 1: a weight is NaN
   unsigned long long wmax_bits;  // bits of max finite |W - thr|
 };
 
@@ -162,8 +162,9 @@ __global__ void __launch_bounds__(256) wmax_kernel(const double *__restrict__ W,
   int err = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double w = W[i] - thr;
-    if (w >= 0x1p40) err = 1;
+    if (w >= 0x1p40) err |= 1;
     else if (w == w && w > -0x1p40) m = fmax(m, fabs(w));
+    if (!(w == w)) err |= 2;  // NaN: clamps to 0 in kmer_regions (:269), sticks in the transition scan (:362-365)
   }
   unsigned long long bits = (unsigned long long)__double_as_longlong(m);
 #pragma unroll
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(256) wmax_kernel(const double *__restrict__ W,
   }
   if ((threadIdx.x & 31) == 0) {
     if (bits) atomicMax(&prm->wmax_bits, bits);
-    if (err) atomicOr(&prm->err, 1);
+    if (err) atomicOr(&prm->err, err);
   }
 }
 
@@ -273,6 +274,15 @@ struct LevelArgs {
   uint64_t *rec_mlo;
   unsigned long long *rec_count;
   unsigned long long rec_cap;
+  // transition-score scan (tr != 0): ASCII buffer (terminator tests of :340-341), table = [trans | init]
+  // (nk entries each), per-chunk first / real masks, and the re-scan requests of the level
+  int tr;
+  const uint8_t *buf;
+  uint32_t nk;
+  uint32_t *st_aux;  // first (16 bits) | real << 16
+  int64_t *child_pk, *child_c;
+  unsigned long long *child_count;
+  unsigned long long child_cap;
 };
 
 struct DevEmit {
@@ -286,6 +296,13 @@ struct DevEmit {
       A->rec_mhi[slot] = (int64_t)fx_hi(M);
       A->rec_mlo[slot] = fx_lo(M);
     }
+  }
+  // transition-score scan: regions and re-scan requests are separate sets
+  __device__ __forceinline__ void out(int64_t beg, int64_t pk, fx_t M) const { (*this)(beg, pk, 0, M); }
+  __device__ __forceinline__ void child(int64_t pk, int64_t c, uint64_t min_width) const {
+    if (!tr_child_wanted(pk, c, min_width)) return;
+    unsigned long long slot = atomicAdd(A->child_count, 1ull);
+    if (slot < A->child_cap) { A->child_pk[slot] = pk; A->child_c[slot] = c; }
   }
 };
 
@@ -302,7 +319,7 @@ struct DevEmit {
 #define KS_WALK_MINBLOCKS_TABLE 4
 #endif
 
-template <bool kLut>
+template <bool kLut, bool kTr = false>
 __global__ void __launch_bounds__(TILE_THREADS, kLut ? KS_GATHER_MINBLOCKS : KS_GATHER_MINBLOCKS_TABLE)
 scan_gather_kernel(const LevelArgs A) {
   __shared__ Xf s_wxf[TILE_WARPS + 1];
@@ -349,7 +366,34 @@ scan_gather_kernel(const LevelArgs A) {
   }
   // ---- codes, gather (16 independent loads in flight), scores, chunk transform ----
   uint32_t code[CHUNK], scored;
-  decode_scan(X, brk32, A.k, A.kmask, n_in, code, scored);
+  uint32_t tr_first = 0;
+  if (kTr) {
+    // k-mer ENDING at every position; the first k-mer of a run carries the initial score (:344-354)
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) code[j] = (uint32_t)(X >> (30 - 2 * j)) & A.kmask;
+    const uint32_t runk = run_ending(~brk32, A.k);
+    const uint32_t first32 = runk & (brk32 << A.k);
+    const uint32_t inside = n_in >= 16 ? 0xffffu : ((1u << n_in) - 1u);
+    // a run is not looked at when the terminator sits at or right behind the base that follows its
+    // first k-mer (:340-341); first k-mers are rare, so the two ASCII bytes are read only for them
+    uint32_t dead = 0;
+    uint32_t F = (first32 >> 15) & 0x1ffffu;  // bit 0: position p0 - 1, bit j + 1: position p0 + j
+    while (F) {
+      const int b = __ffs(F) - 1;
+      F &= F - 1;
+      const int64_t f = p0 - 1 + b;
+      const uint8_t z1 = A.buf[f + 1], z2 = A.buf[f + 2];
+      if (b >= 1 && (z1 == 0 || z2 == 0)) dead |= 1u << (b - 1);
+      if (b <= 15 && z2 == 0) dead |= 1u << b;
+    }
+    tr_first = (first32 >> 16) & inside & ~dead;
+    scored = ((run_ending(~brk32, A.k + 1) >> 16) & inside & ~dead) | tr_first;
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j)
+      if (tr_first & (1u << j)) code[j] += A.nk;  // second half of the table: initial scores
+  } else {
+    decode_scan(X, brk32, A.k, A.kmask, n_in, code, scored);
+  }
   const uint64_t keep = l2_policy_evict_last();
   uint32_t live = 0;
   int64_t ta = 0, tb = -(1ll << 62);
@@ -446,6 +490,7 @@ scan_gather_kernel(const LevelArgs A) {
   A.st_eb[q] = excl.b;
   A.st_flags[q] = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u) | (vchunk ? 0x40000u : 0u);
   if (A.nseg != 0) A.st_p0[q] = p0;
+  if (kTr) A.st_aux[q] = tr_first | (scored << 16);
 }
 
 // State entering every tile, in two tiny kernels: a warp scans the aggregates of 32 consecutive tiles
@@ -534,7 +579,7 @@ struct StashScoresLut {  // scores of one chunk, LUT mode: count from the stash,
   }
 };
 
-template <bool kLut>
+template <bool kLut, bool kTr = false>
 __global__ void __launch_bounds__(TILE_THREADS, kLut ? KS_WALK_MINBLOCKS : KS_WALK_MINBLOCKS_TABLE)
 scan_walk_kernel(const LevelArgs A) {
   __shared__ Ex s_wex[TILE_WARPS + 1];
@@ -572,9 +617,14 @@ scan_walk_kernel(const LevelArgs A) {
   fx_t preM;
   int64_t prePk;
   int first_zero;
+  uint32_t tr_real = 0;
   if (fl & 0x40000u) {  // padding chunk: transparent
     ex = ex_identity();
     preM = ex.M; prePk = -1; first_zero = -1;
+  } else if (kTr) {
+    const uint32_t aux = A.st_aux[q];
+    tr_real = aux >> 16;
+    chunk_walk_tr(s, live, aux & 0xffffu, tr_real, S_in, p0, prm, emit, ex, preM, prePk, first_zero);
   } else {
     chunk_walk(s, live, S_in, p0, prm, emit, ex, preM, prePk, first_zero);
   }
@@ -609,7 +659,8 @@ scan_walk_kernel(const LevelArgs A) {
   if (!head && S_in > 0 && first_zero >= 0) {
     if (eexcl.reset) {
       // the entering excursion started inside this tile: everything is known
-      chunk_finish_entering(S_in, eexcl, preM, prePk, first_zero, p0, prm, emit);
+      if (kTr) chunk_finish_entering_tr(S_in, eexcl, preM, prePk, first_zero, p0, tr_real, prm, emit);
+      else chunk_finish_entering(S_in, eexcl, preM, prePk, first_zero, p0, prm, emit);
     } else {
       // it entered the tile from the left (at most one thread per tile gets here): defer
       fx_t M = eexcl.M;
@@ -620,7 +671,7 @@ scan_walk_kernel(const LevelArgs A) {
       pe.m_hi = (int64_t)fx_hi(M);
       pe.pk = pk;
       pe.c = p0 + first_zero;
-      pe.valid = 1; pe.pad[0] = pe.pad[1] = pe.pad[2] = 0;
+      pe.valid = 1; pe.pad[0] = kTr ? ((tr_real >> first_zero) & 1u) : 0u; pe.pad[1] = pe.pad[2] = 0;
       A.pending[tile] = pe;
       A.pending_list[atomicAdd(A.pending_count, 1u)] = (uint32_t)tile;
     }
@@ -711,7 +762,14 @@ __global__ void __launch_bounds__(256) ex_fixup_kernel(const LevelArgs A) {
       const fx_t Mp = fx_make((uint64_t)pe.m_hi, pe.m_lo);
       if (Mp > M) { M = Mp; pk = pe.pk; }
       DevEmit emit{&A};
-      if (acc.open && qualifies(prm, acc.beg, pk, M)) emit(acc.beg, pk, pe.c, M);
+      if (A.tr) {
+        if (acc.open) {
+          if (qualifies(prm, acc.beg, pk, M)) emit.out(acc.beg, pk, M);
+          if (pe.pad[0]) emit.child(pk, pe.c, prm.min_width);
+        }
+      } else if (acc.open && qualifies(prm, acc.beg, pk, M)) {
+        emit(acc.beg, pk, pe.c, M);
+      }
     }
   }
 }
@@ -743,7 +801,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const uint32_t *__restric
                                                        const uint64_t *__restrict__ rec_mlo,
                                                        const int64_t *__restrict__ starts, int nseq,
                                                        const DevScanParams *__restrict__ prm,
-                                                       int32_t *__restrict__ pos, double *__restrict__ score) {
+                                                       int32_t *__restrict__ pos, double *__restrict__ score,
+                                                       int one_based = 0) {
   unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long r = perm ? perm[i] : i;
@@ -753,9 +812,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const uint32_t *__restric
     int mid = (lo + hi) >> 1;
     if (starts[mid] <= beg) lo = mid; else hi = mid;
   }
-  pos[3 * i] = lo;
-  pos[3 * i + 1] = (int32_t)(beg - starts[lo]);
-  pos[3 * i + 2] = (int32_t)(pk - starts[lo]);
+  pos[3 * i] = lo + one_based;  // tr_lr_regions_r numbers sequences and positions from 1 (:379,681)
+  pos[3 * i + 1] = (int32_t)(beg - starts[lo]) + one_based;
+  pos[3 * i + 2] = (int32_t)(pk - starts[lo]) + one_based;
   score[2 * i] = fx_to_double(fx_make((uint64_t)rec_mhi[r], rec_mlo[r]), prm->qs);
   score[2 * i + 1] = 0.0;
 }

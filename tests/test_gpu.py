@@ -494,3 +494,73 @@ def test_window_dist_errors(ctx):
         ctx.window_kmer_dist([b"ACGTACGTACGT"], [b"ACG"], 5)
     with pytest.raises(ValueError, match="same size"):
         ctx.window_kmer_dist([b"ACGTACGTACGT"], [b"ACG", b"AC"], 8)
+
+
+# ---- transition-score scan (tr_lr_regions_r) ------------------------------------
+def _tr_case(ctx, oracle, seqs, k, init, trans, min_len, exact, what):
+    n = 4 ** k
+    kms = [oracle.kmer_seq(k, c).encode() for c in range(n)]
+    want = oracle.tr_lr_regions(seqs, k, init, trans, min_len)
+    got = ctx.lr_regions(seqs, (k, min_len), kms, init, trans)
+    assert np.array_equal(got["kmer_scores"][:, 0], init) and np.array_equal(got["kmer_scores"][:, 1], trans)
+    assert_spans(got, want, exact, what)
+    return len(want["pos"])
+
+
+def test_tr_lr_small(ctx, oracle):
+    rng = np.random.default_rng(5100)
+    total = 0
+    for t in range(60):
+        k = int(rng.integers(1, 7))
+        n = 4 ** k
+        seqs = [rand_seq(rng, int(rng.integers(0, 6000)), p_n=float(rng.choice([0, 0.05, 0.3])))
+                for _ in range(int(rng.integers(1, 5)))]
+        if t % 3 == 0:  # run-end rules (:340-341)
+            seqs += [rand_seq(rng, k), rand_seq(rng, k + 1), rand_seq(rng, k + 2), rand_seq(rng, k) + b"N",
+                     rand_seq(rng, k) + b"NA", rand_seq(rng, k) + b"N" + rand_seq(rng, k + 3),
+                     rand_seq(rng, 40) + b"NN" + rand_seq(rng, k + 1), b"", b"NNNN"]
+        exact = t % 2 == 0
+        if exact:
+            init, trans = rng.integers(-2, 3, n).astype(float), rng.integers(-2, 3, n).astype(float)
+        else:
+            init, trans = rng.normal(0, 1, n), rng.normal(-0.1, 1, n)
+        if t % 5 == 0:
+            trans[rng.integers(0, n)] = -np.inf
+            init[rng.integers(0, n)] = -np.inf
+        min_len = int(rng.choice([0, 1, 3, 10, 40]))
+        total += _tr_case(ctx, oracle, seqs, k, init, trans, min_len, exact, "t=%d k=%d min_len=%d" % (t, k, min_len))
+    assert total > 2000
+
+
+def test_tr_lr_planted_multi_tile(ctx, oracle):
+    """long excursions across many tiles, deep re-scans (min_length 0) and wide regions"""
+    rng = np.random.default_rng(5200)
+    k = 4
+    n = 4 ** k
+    seqs = [planted(rng, 300_000), planted(rng, 70_000)]
+    # log-ratio style scores: k-mers of the planted repeats score up
+    _, counts = oracle.kmer_counts(seqs, k)
+    f = (counts + 1.0) / (counts.sum() + n)
+    trans = np.log2(f * n) - 0.05
+    init = np.log2(f * n)
+    for min_len in (0, 25, 200):
+        got = _tr_case(ctx, oracle, seqs, k, init, trans, min_len, False, "planted min_len=%d" % min_len)
+        assert got > 0
+    levels, _ = ctx.scan_stats()
+    assert levels >= 2
+    # +-1 scores: exact arithmetic, long positive stretches
+    trans = np.where(counts > np.median(counts), 1.0, -1.0)
+    init = np.where(counts > np.median(counts), 2.0, -2.0)
+    _tr_case(ctx, oracle, seqs, k, init, trans, 0, True, "sign scores")
+    _tr_case(ctx, oracle, seqs, k, init, trans, 30, True, "sign scores min_len 30")
+
+
+def test_tr_lr_rejects_nan(ctx):
+    from kmer_spans_b200._lib import KspansError
+    w = np.zeros(16)
+    w[3] = np.nan
+    kms = [a + b for a in "ACTG" for b in "ACTG"]
+    with pytest.raises(KspansError, match="NaN"):
+        ctx.lr_regions([b"ACGTACGTACGTAAAA"], (2, 0), kms, np.zeros(16), w)
+    with pytest.raises(KspansError, match="4\\^k long"):
+        ctx.lr_regions([b"ACGT"], (2, 0), kms[:5], np.zeros(16), w)
