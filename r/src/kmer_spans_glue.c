@@ -8,9 +8,8 @@
  *   kmer_regions_r/5         -> ks_kmer_regions             (reference :490-546)
  *   kmer_low_comp_regions/5  -> ks_kmer_low_comp_regions    (reference :548-621)
  *   kmer_seq_r/1             -> ks_kmer_seq (host only)     (reference :623-639)
+ *   tr_lr_regions_r/5        -> ks_tr_lr_regions            (reference :649-713)
  *   windowed_kmer_count_distributions_r/5 -> ks_windowed_kmer_count_distributions (reference :715-793)
- *   tr_lr_regions_r/5: outside the accelerated path; registered so that
- *       sourcing kmer_spans.R succeeds, it raises an R error that points at the reference build.
  *   kmer_mode_regions/8 (extension): counts -> scores(mode) -> scan resident on the GPU.
  *
  * Argument checks, their order and the error texts follow the reference; result lists have the
@@ -277,13 +276,53 @@ SEXP kmer_mode_regions(SEXP seq_r, SEXP k_r, SEXP mode_r, SEXP param_r, SEXP thr
   return ret;
 }
 
-/* ---- outside the accelerated path: registered, not implemented here --------------------------- */
-SEXP tr_lr_regions_r(SEXP a, SEXP b, SEXP c, SEXP d, SEXP e) {
-  (void)a; (void)b; (void)c; (void)d; (void)e;
-  error("tr_lr_regions_r is not part of the CUDA hot path (count -> score -> scan -> spans); "
-        "load the reference build of kmer_spans.so for lr.regions()");
-  return NULL;
+/* ---- tr_lr_regions_r (reference :649-713) -------------------------------------------------------- */
+SEXP tr_lr_regions_r(SEXP seq_r, SEXP params_r, SEXP kmers_r, SEXP kmer_scores_r, SEXP trans_scores_r) {
+  if (TYPEOF(seq_r) != STRSXP || length(seq_r) < 1)
+    error("seq_r should be a character vector of of positive length");
+  if (TYPEOF(params_r) != INTSXP || length(params_r) != 2)
+    error("params_r should have two integers (k, and min_length)");
+  if (TYPEOF(kmers_r) != STRSXP) error("kmers_r should be a character vector");
+  if (TYPEOF(kmer_scores_r) != REALSXP || TYPEOF(trans_scores_r) != REALSXP)
+    error("freq_a and freq_b should be double vectors");
+  int k = INTEGER(params_r)[0];
+  int min_length = INTEGER(params_r)[1];
+  if (k < 1 || k > GLUE_MAX_K) error("k should be a positive value less than MAX_K");
+  if (k == GLUE_MAX_K) error("k = 16 overflows the reference's int table index; use k <= 15");
+  if (min_length < 0) error("min_length should be a positive integer");
+  size_t kmers_size = (size_t)1 << (2 * k);
+  if ((size_t)length(kmers_r) != kmers_size || (size_t)length(kmer_scores_r) != kmers_size ||
+      (size_t)length(trans_scores_r) != kmers_size)
+    error("kmers_r, freq_a, freq_b should all be 4^k long");
+  SEXP ret = PROTECT(allocVector(VECSXP, 3));
+  /* the two score vectors re-ordered to the 2-bit code of their k-mer strings (:688-696) */
+  SET_VECTOR_ELT(ret, 0, allocMatrix(REALSXP, (int)kmers_size, 2));
+  double *init = REAL(VECTOR_ELT(ret, 0)), *trans = init + kmers_size;
+  memset(init, 0, sizeof(double) * 2 * kmers_size);
+  for (size_t i = 0; i < kmers_size; ++i) {
+    uint32_t code = ks_kmer_code(CHAR(STRING_ELT(kmers_r, i)), k);
+    init[code] = REAL(kmer_scores_r)[i];
+    trans[code] = REAL(trans_scores_r)[i];
+  }
+  seq_view v;
+  int ok = view_strsxp(seq_r, &v);
+  ks_ctx *ctx = ok ? glue_ctx() : NULL;
+  ks_spans sp = {0};
+  int rc = KS_ERR_NOMEM;
+  if (ok && ctx) {
+    rc = ks_tr_lr_regions(ctx, v.ptr, v.len, v.n, k, init, trans, min_length, &sp);
+    if (rc) fail_from_ctx(ctx);
+  } else if (!ok) {
+    snprintf(g_msg, sizeof g_msg, "out of memory");
+  }
+  view_free(&v);
+  if (rc) { ks_spans_free(&sp); UNPROTECT(1); error("%s", g_msg); }
+  spans_to_r(ret, 1, &sp);
+  ks_spans_free(&sp);
+  UNPROTECT(1);
+  return ret;
 }
+
 /* ---- windowed_kmer_count_distributions_r (reference :715-793) -------------------------------- */
 SEXP windowed_kmer_count_distributions_r(SEXP seq_r, SEXP kmers_r, SEXP k_r, SEXP window_r, SEXP ret_flag_r) {
   if (TYPEOF(seq_r) != STRSXP || length(seq_r) < 1)

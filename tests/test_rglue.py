@@ -21,7 +21,7 @@ def glue():
 
 
 def test_registration_matches_reference(glue, ref):
-    """same six .Call names and arities (src/kmer_spans.c:795-803), plus the one extension"""
+    """same six .Call names and arities (src/kmer_spans.c:795-803), plus the one extension; none is a stub"""
     want = ref.registered()
     got = glue.registered()
     assert got[: len(want)] == want
@@ -45,6 +45,14 @@ def test_argument_errors_match_reference(glue, ref):
         ("kmer_low_comp_regions", [("s", [b"ACGT"]), ("i", 2), ("d", 1.0), ("d", 1.0), ("d", 0.5)]),
         ("kmer_seq_r", [("i", 0)]),
         ("kmer_seq_r", [("i", [1, 2])]),
+        ("tr_lr_regions_r", [("i", 1), ("i", [2, 1]), ("s", [b"AA"] * 16), ("d", [1.0] * 16), ("d", [1.0] * 16)]),
+        ("tr_lr_regions_r", [("s", [b"A"]), ("i", [2]), ("s", [b"AA"] * 16), ("d", [1.0] * 16), ("d", [1.0] * 16)]),
+        ("tr_lr_regions_r", [("s", [b"A"]), ("i", [2, 1]), ("i", [1] * 16), ("d", [1.0] * 16), ("d", [1.0] * 16)]),
+        ("tr_lr_regions_r", [("s", [b"A"]), ("i", [2, 1]), ("s", [b"AA"] * 16), ("i", [1] * 16), ("d", [1.0] * 16)]),
+        ("tr_lr_regions_r", [("s", [b"A"]), ("i", [0, 1]), ("s", [b"AA"] * 16), ("d", [1.0] * 16), ("d", [1.0] * 16)]),
+        ("tr_lr_regions_r", [("s", [b"A"]), ("i", [2, -1]), ("s", [b"AA"] * 16), ("d", [1.0] * 16), ("d", [1.0] * 16)]),
+        ("tr_lr_regions_r", [("s", [b"A"]), ("i", [2, 1]), ("s", [b"AA"] * 15), ("d", [1.0] * 16), ("d", [1.0] * 16)]),
+        ("tr_lr_regions_r", [("s", [b"A"]), ("i", [2, 1]), ("s", [b"AA"] * 16), ("d", [1.0] * 16), ("d", [1.0] * 15)]),
         ("windowed_kmer_count_distributions_r", [("i", 1), ("s", [b"AC"]), ("i", 2), ("i", 8), ("i", 0)]),
         ("windowed_kmer_count_distributions_r", [("s", [b"ACGT"]), ("i", 1), ("i", 2), ("i", 8), ("i", 0)]),
         ("windowed_kmer_count_distributions_r", [("s", [b"ACGT"]), ("s", [b"AC"]), ("d", 2.0), ("i", 8), ("i", 0)]),
@@ -67,9 +75,22 @@ def test_kmer_seq_r_matches_reference(glue, ref):
         assert glue.call_kmer_seq_r(k) == ref.call_kmer_seq_r(k)
 
 
-def test_out_of_path_entries_are_registered_stubs(glue):
-    with pytest.raises(RuntimeError, match="not part of the CUDA hot path"):
-        glue.call_raw("tr_lr_regions_r", [("s", [b"A"]), ("i", [2, 1]), ("s", [b"AA"]), ("d", 1.0), ("d", 1.0)])
+@pytest.mark.gpu
+def test_tr_lr_call_matches_reference(glue, ref, oracle):
+    rng = np.random.default_rng(2026)
+    for trial in range(6):
+        k = int(rng.choice([1, 2, 3, 5]))
+        n = 4 ** k
+        seqs = [planted(rng, int(rng.integers(50, 8000))) for _ in range(int(rng.integers(1, 5)))]
+        seqs += [b"ACGTACGTAC"[:k + 1], b"ACGT"]
+        kms = [oracle.kmer_seq(k, c).encode() for c in range(n)]
+        perm = rng.permutation(n)
+        init, trans = rng.integers(-2, 3, n).astype(float), rng.integers(-3, 3, n).astype(float)
+        min_len = int(rng.choice([0, 5, 30]))
+        a = ref.call_tr_lr(seqs, k, min_len, [kms[i] for i in perm], init[perm], trans[perm])
+        b = glue.call_tr_lr(seqs, k, min_len, [kms[i] for i in perm], init[perm], trans[perm])
+        assert np.array_equal(a["tables"], b["tables"])
+        assert a["pos"].tolist() == b["pos"].tolist() and a["score"].tobytes() == b["score"].tobytes()
 
 
 @pytest.mark.gpu
