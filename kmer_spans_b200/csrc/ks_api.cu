@@ -104,6 +104,7 @@ struct ks_ctx {
   DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, pending, foc_hist, foc_big;
   DBuf win_match, win_cnt, win_pre, win_scratch, win_codes, win_fix, win_hist, win_pos;
   DBuf st_aux, child_pk, child_c, child_count, tr_tables;
+  DBuf st_mn, st_mx, st_bm, detail, detail_count;
   size_t child_cap = 0;
   DBuf st_c, st_s, st_ea, st_eb, st_flags, st_p0, tile_xf, tile_ex, group_xf, group_S, group_ex, pending_list, pending_count, launch_rec;
 
@@ -241,7 +242,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->tmp_inscan, &ctx->nwords, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->launch_rec, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv,
                  &ctx->win_match, &ctx->win_cnt, &ctx->win_pre, &ctx->win_scratch, &ctx->win_codes, &ctx->win_fix,
                  &ctx->win_hist, &ctx->win_pos, &ctx->st_aux, &ctx->child_pk, &ctx->child_c, &ctx->child_count,
-                 &ctx->tr_tables};
+                 &ctx->tr_tables, &ctx->st_mn, &ctx->st_mx, &ctx->st_bm, &ctx->detail, &ctx->detail_count};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -963,6 +964,11 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     total_chunks = sh->nchunks;
     CK(ctx->launch_rec.ensure(256));
   }
+  // With min_width >= 15 no excursion inside one 16-position chunk can qualify: the walk then works on
+  // per-chunk summaries (scan_walk_fast_kernel) and only a short list of chunks is walked position by
+  // position.  A level whose list overflows is redone with the general walk.
+  const bool fast_ok = !tab.tr && mw >= 15 && getenv("KS_NO_FAST_WALK") == nullptr;
+  bool fast = fast_ok;
   bool have_carry = false;  // the exchange runs once, also if level 0 has to be repeated with more room
   fx_t S_carry = 0;
   ExRec E_carry;
@@ -978,6 +984,15 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     rc = ensure_tiles(ctx, tiles, tab.use_lut, nseg != 0);
     if (rc) return rc;
     if (tab.tr) CK(ctx->st_aux.ensure(tiles * TILE_THREADS * 4));
+    const size_t detail_cap = tiles + tiles * TILE_THREADS / 16 + 64;
+    if (fast) {
+      CK(ctx->st_mn.ensure(tiles * TILE_THREADS * 8));
+      CK(ctx->st_mx.ensure(tiles * TILE_THREADS * 8));
+      CK(ctx->st_bm.ensure(tiles * TILE_THREADS * 8));
+      CK(ctx->detail.ensure(detail_cap * sizeof(DetailEntry)));
+      CK(ctx->detail_count.ensure(64));
+      CK(cudaMemsetAsync(ctx->detail_count.p, 0, 4, st));
+    }
     LevelArgs A;
     memset(&A, 0, sizeof A);
     A.pk = s->d_pk;
@@ -1031,6 +1046,12 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.rec_mlo = ctx->rec_mlo.as<uint64_t>();
     A.rec_count = d_rec_count;
     A.rec_cap = ctx->rec_cap;
+    A.st_mn = ctx->st_mn.as<int64_t>();
+    A.st_mx = ctx->st_mx.as<int64_t>();
+    A.st_bm = ctx->st_bm.as<int64_t>();
+    A.detail = ctx->detail.as<DetailEntry>();
+    A.detail_count = ctx->detail_count.as<unsigned int>();
+    A.detail_cap = (unsigned int)std::min<size_t>(detail_cap, 0xffffffffu);
     A.tr = tab.tr ? 1 : 0;
     A.buf = s->d_buf;
     A.nk = (uint32_t)nk;
@@ -1042,6 +1063,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     if (tab.tr) CK(cudaMemsetAsync(ctx->child_count.p, 0, sizeof(unsigned long long), st));
     cudaEvent_t ps = ctx->prof_begin();
     if (tab.tr) scan_gather_kernel<false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (fast && tab.use_lut) scan_gather_kernel<true, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (fast) scan_gather_kernel<false, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (tab.use_lut) scan_gather_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else scan_gather_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     group_scan_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
@@ -1065,9 +1088,28 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
       LAUNCHED(1);
     }
     if (tab.tr) scan_walk_kernel<false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (fast) scan_walk_fast_kernel<<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (tab.use_lut) scan_walk_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else scan_walk_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     group_ex_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
+    unsigned int n_detail = 0;
+    if (fast) {
+      // the list is short (one entry per tile at most, plus the rare wide excursions): its length decides
+      // the grid of the detail kernel, and an overflow sends the level back to the general walk
+      CK(cudaMemcpyAsync(&n_detail, ctx->detail_count.p, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (n_detail > A.detail_cap) {
+        fast = false;
+        CK(cudaMemcpyAsync(d_rec_count, &level_start, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+        count_inscan = false;
+        continue;
+      }
+      if (n_detail) {
+        if (tab.use_lut) scan_detail_kernel<true><<<blocks_exact(n_detail, 128), 128, 0, st>>>(A);
+        else scan_detail_kernel<false><<<blocks_exact(n_detail, 128), 128, 0, st>>>(A);
+        LAUNCHED(1);
+      }
+    }
     if (exchange && have_carry) {
       A.E_start = E_carry;
     } else if (exchange) {  // the same for the open-excursion state
@@ -1110,6 +1152,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
       CK(cudaStreamSynchronize(st));
       continue;
     }
+    fast = fast_ok;
     if (level > 0) revisit_chunks += (uint64_t)total_chunks;
     unsigned long long n_new = tab.tr ? hres.children : hres.cnt - level_start;
     ++level;

@@ -220,6 +220,14 @@ struct __align__(16) ExPending {
 struct __align__(16) XfRec { fx_t a, b; uint32_t kill; uint32_t pad[3]; };
 struct __align__(16) ExRec { fx_t M; int64_t beg, pk; uint32_t reset, open; uint32_t pad[2]; };
 
+// a chunk handed from scan_walk_fast_kernel to scan_detail_kernel: the state entering it and the
+// open-excursion state in front of it (reset = 0: the excursion entered the tile from the left)
+struct __align__(16) DetailEntry {
+  fx_t S_in, M;
+  int64_t q, beg, pk, tile;
+  uint32_t reset, pad[3];
+};
+
 struct LevelArgs {
   const uint32_t *pk;   // packed 2-bit codes, one word per 16 positions (chunk c = positions [16c, 16c+16))
   const uint16_t *brk;  // break masks, one half-word per 16 positions
@@ -274,6 +282,12 @@ struct LevelArgs {
   uint64_t *rec_mlo;
   unsigned long long *rec_count;
   unsigned long long rec_cap;
+  // fast walk (min_width >= 15): per-chunk summary written by the gather kernel and the list
+  // of chunks whose entering excursion closes and might qualify
+  int64_t *st_mn, *st_mx, *st_bm;
+  struct DetailEntry *detail;
+  unsigned int *detail_count;
+  unsigned int detail_cap;
   // transition-score scan (tr != 0): ASCII buffer (terminator tests of :340-341), table = [trans | init]
   // (nk entries each), per-chunk first / real masks, and the re-scan requests of the level
   int tr;
@@ -318,9 +332,43 @@ struct DevEmit {
 #ifndef KS_WALK_MINBLOCKS_TABLE
 #define KS_WALK_MINBLOCKS_TABLE 4
 #endif
+#ifndef KS_GATHER_MINBLOCKS_SUMM
+#define KS_GATHER_MINBLOCKS_SUMM 4
+#endif
+#ifndef KS_GATHER_MINBLOCKS_TABLE_SUMM
+#define KS_GATHER_MINBLOCKS_TABLE_SUMM 3
+#endif
+#ifndef KS_WALKFAST_MINBLOCKS
+#define KS_WALKFAST_MINBLOCKS 8
+#endif
 
-template <bool kLut, bool kTr = false>
-__global__ void __launch_bounds__(TILE_THREADS, kLut ? KS_GATHER_MINBLOCKS : KS_GATHER_MINBLOCKS_TABLE)
+// per-position update of the chunk summary used by the fast walk: P = running sum (ta), its min / max /
+// leftmost argmax, and the zero-start trajectory Bz with the start, peak and leftmost peak position of
+// its current excursion
+struct ChunkSumm {
+  int64_t mn, mx, Bz, bM;
+  uint32_t am, bbeg, bpk;
+  __device__ __forceinline__ void init() {
+    mn = 1ll << 62; mx = -(1ll << 62); Bz = 0; bM = 0; am = 0; bbeg = 0; bpk = 0;
+  }
+  __device__ __forceinline__ void step(int j, bool live, int64_t v, int64_t ta) {
+    mn = ta < mn ? ta : mn;
+    if (ta > mx) { mx = ta; am = (uint32_t)j; }
+    int64_t t = Bz + v;
+    const int64_t Bn = (live && t > 0) ? t : 0;
+    if (Bz == 0 && Bn > 0) { bbeg = (uint32_t)j; bpk = (uint32_t)j; bM = Bn; }
+    else if (Bn > bM) { bM = Bn; bpk = (uint32_t)j; }
+    Bz = Bn;
+  }
+  __device__ __forceinline__ uint32_t flag_bits() const {
+    return (am << 19) | (bbeg << 23) | (bpk << 27) | (Bz > 0 ? 0x80000000u : 0u);
+  }
+};
+
+template <bool kLut, bool kTr = false, bool kSumm = false>
+__global__ void __launch_bounds__(TILE_THREADS,
+                                  kSumm ? (kLut ? KS_GATHER_MINBLOCKS_SUMM : KS_GATHER_MINBLOCKS_TABLE_SUMM)
+                                        : (kLut ? KS_GATHER_MINBLOCKS : KS_GATHER_MINBLOCKS_TABLE))
 scan_gather_kernel(const LevelArgs A) {
   __shared__ Xf s_wxf[TILE_WARPS + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -398,6 +446,8 @@ scan_gather_kernel(const LevelArgs A) {
   uint32_t live = 0;
   int64_t ta = 0, tb = -(1ll << 62);
   uint32_t tkill = 0;
+  ChunkSumm sm;
+  if (kSumm) sm.init();
   if (kLut) {
     uint32_t c[CHUNK];
 #pragma unroll
@@ -426,6 +476,7 @@ scan_gather_kernel(const LevelArgs A) {
       } else {
         tkill = 1; ta = 0; tb = 0;
       }
+      if (kSumm) sm.step(j, v != WFX_KILL, v, ta);
     }
   } else {
     int64_t sv[CHUNK];
@@ -443,6 +494,7 @@ scan_gather_kernel(const LevelArgs A) {
       } else {
         tkill = 1; ta = 0; tb = 0;
       }
+      if (kSumm) sm.step(j, v != WFX_KILL, v, ta);
     }
   }
   if (A.inscan) {
@@ -488,7 +540,14 @@ scan_gather_kernel(const LevelArgs A) {
   excl = xf_compose(s_wxf[warp], excl);
   A.st_ea[q] = excl.a;
   A.st_eb[q] = excl.b;
-  A.st_flags[q] = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u) | (vchunk ? 0x40000u : 0u);
+  uint32_t flags = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u) | (vchunk ? 0x40000u : 0u);
+  if (kSumm) {
+    flags |= sm.flag_bits();
+    A.st_mn[q] = sm.mn;
+    A.st_mx[q] = sm.mx;
+    A.st_bm[q] = sm.bM;
+  }
+  A.st_flags[q] = flags;
   if (A.nseg != 0) A.st_p0[q] = p0;
   if (kTr) A.st_aux[q] = tr_first | (scored << 16);
 }
@@ -675,6 +734,152 @@ scan_walk_kernel(const LevelArgs A) {
       A.pending[tile] = pe;
       A.pending_list[atomicAdd(A.pending_count, 1u)] = (uint32_t)tile;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast walk (min_width >= 15).  An excursion that starts and closes inside one 16-position chunk cannot
+// qualify then, so per chunk only two things matter, and both follow from the summary the gather kernel
+// left behind without looking at the positions again:
+//   * the open-excursion element of the chunk: with the entering state S_in the trajectory is
+//     S_j = max(S_in + P_j, Bz_j); it reaches 0 inside the chunk iff a position is forced to 0 or
+//     S_in + min P <= 0, and from that point on it IS the zero-start trajectory Bz.  No zero: the chunk
+//     lies inside the entering excursion, (M, pk) = (S_in + max P, leftmost argmax).  Zero: the element
+//     is the state of Bz at the chunk end.
+//   * whether the entering excursion closes here.  Its peak lies at or before p0 + 15, so unless
+//     p0 + 15 - start >= min_width (and its score bound reaches min_score) it cannot qualify; the rare
+//     survivors, and the one excursion per tile whose start lies in an earlier tile, go to
+//     scan_detail_kernel, which walks just those chunks position by position.
+__global__ void __launch_bounds__(TILE_THREADS, KS_WALKFAST_MINBLOCKS) scan_walk_fast_kernel(const LevelArgs A) {
+  __shared__ Ex s_wex[TILE_WARPS + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tile = blockIdx.x;
+  const int64_t q = tile * TILE_THREADS + tid;
+  fx_t S_tile;
+  {
+    XfRec r = A.tile_xf[tile];
+    Xf tx; tx.a = r.a; tx.b = r.b; tx.kill = r.kill;
+    S_tile = xf_apply(tx, A.group_S[tile / GROUP_TILES]);
+  }
+  const uint32_t fl = A.st_flags[q];
+  const uint32_t live = fl & 0xffffu;
+  const bool head = (fl & 0x10000u) != 0;
+  const int64_t p0 = A.nseg == 0 ? A.dense_start + 16 * q : A.st_p0[q];
+  Xf excl;
+  excl.a = A.st_ea[q]; excl.b = A.st_eb[q]; excl.kill = (fl >> 17) & 1u;
+  const fx_t S_in = head ? (fx_t)0 : xf_apply(excl, S_tile);
+  const int64_t mx = A.st_mx[q];
+  Ex ex;
+  bool closing = false;
+  if (fl & 0x40000u) {  // padding chunk: transparent
+    ex = ex_identity();
+  } else {
+    const bool zero = head || S_in <= 0 || live != 0xffffu || S_in + (fx_t)A.st_mn[q] <= 0;
+    if (!zero) {
+      ex.reset = 0; ex.open = 1; ex.beg = -1;
+      ex.M = S_in + (fx_t)mx;
+      ex.pk = p0 + ((fl >> 19) & 15u);
+    } else if (fl & 0x80000000u) {
+      ex.reset = 1; ex.open = 1;
+      ex.beg = p0 + ((fl >> 23) & 15u);
+      ex.pk = p0 + ((fl >> 27) & 15u);
+      ex.M = (fx_t)A.st_bm[q];
+    } else {
+      ex.reset = 1; ex.open = 0; ex.M = -(((fx_t)1) << 126); ex.beg = -1; ex.pk = -1;
+    }
+    closing = !head && S_in > 0 && zero;
+  }
+  Ex einc = ex;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Ex y = shfl_ex(einc, (lane - o) & 31);
+    if (lane >= o) einc = ex_combine(y, einc);
+  }
+  Ex eexcl = shfl_ex(einc, (lane - 1) & 31);
+  if (lane == 0) eexcl = ex_identity();
+  if (lane == 31) s_wex[warp] = einc;
+  __syncthreads();
+  if (warp == 0) {
+    Ex ti = lane < TILE_WARPS ? s_wex[lane] : ex_identity();
+#pragma unroll
+    for (int o = 1; o < TILE_WARPS; o <<= 1) {
+      Ex y = shfl_ex(ti, (lane - o) & 31);
+      if (lane >= o) ti = ex_combine(y, ti);
+    }
+    Ex te = shfl_ex(ti, (lane - 1) & 31);
+    if (lane == 0) te = ex_identity();
+    if (lane < TILE_WARPS) s_wex[lane] = te;
+    if (lane == TILE_WARPS - 1) {
+      ExRec rr;
+      rr.M = ti.M; rr.beg = ti.beg; rr.pk = ti.pk; rr.reset = ti.reset; rr.open = ti.open; rr.pad[0] = rr.pad[1] = 0;
+      A.tile_ex[tile] = rr;
+    }
+  }
+  __syncthreads();
+  if (!closing) return;
+  eexcl = ex_combine(s_wex[warp], eexcl);
+  if (eexcl.reset) {
+    // start known: the peak lies at or before p0 + 15 and is at most max(M so far, S_in + max P)
+    if ((uint64_t)(p0 + 15 - eexcl.beg) < A.prm->min_width) return;
+    const fx_t bound = fx_max(eexcl.M, S_in + (fx_t)mx);
+    if (bound < fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo)) return;
+  }
+  const unsigned int slot = atomicAdd(A.detail_count, 1u);
+  if (slot < A.detail_cap) {
+    DetailEntry e;
+    e.S_in = S_in; e.M = eexcl.M; e.q = q; e.beg = eexcl.beg; e.pk = eexcl.pk; e.tile = tile;
+    e.reset = eexcl.reset; e.pad[0] = e.pad[1] = e.pad[2] = 0;
+    A.detail[slot] = e;
+  }
+}
+
+// the chunks scan_walk_fast_kernel could not decide: position-by-position walk of the entering excursion
+template <bool kLut>
+__global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
+  unsigned int n = *A.detail_count;
+  if (n > A.detail_cap) n = A.detail_cap;
+  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const DetailEntry e = A.detail[i];
+  const int64_t q = e.q;
+  ScanParams prm;
+  prm.min_width = A.prm->min_width;
+  prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
+  const uint32_t fl = A.st_flags[q];
+  const uint32_t live = fl & 0xffffu;
+  const int64_t p0 = A.nseg == 0 ? A.dense_start + 16 * q : A.st_p0[q];
+  int64_t s[CHUNK];
+  if (kLut) {
+    StashScoresLut acc{&A, q};
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) s[j] = (live & (1u << j)) ? acc[j] : 0;
+  } else {
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) s[j] = __ldcs(&A.st_s[(int64_t)j * A.Q + q]);
+  }
+  DevEmit emit{&A};
+  Ex ex;
+  fx_t preM;
+  int64_t prePk;
+  int first_zero;
+  chunk_walk(s, live, e.S_in, p0, prm, emit, ex, preM, prePk, first_zero);
+  if (first_zero < 0) return;  // cannot happen: the fast walk saw a zero in this chunk
+  if (e.reset) {
+    Ex ein;
+    ein.M = e.M; ein.beg = e.beg; ein.pk = e.pk; ein.reset = 1; ein.open = 1;
+    chunk_finish_entering(e.S_in, ein, preM, prePk, first_zero, p0, prm, emit);
+  } else {
+    fx_t M = e.M;
+    int64_t pk = e.pk;
+    if (preM > M) { M = preM; pk = prePk; }
+    ExPending pe;
+    pe.m_lo = fx_lo(M);
+    pe.m_hi = (int64_t)fx_hi(M);
+    pe.pk = pk;
+    pe.c = p0 + first_zero;
+    pe.valid = 1; pe.pad[0] = pe.pad[1] = pe.pad[2] = 0;
+    A.pending[e.tile] = pe;
+    A.pending_list[atomicAdd(A.pending_count, 1u)] = (uint32_t)e.tile;
   }
 }
 

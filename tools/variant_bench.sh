@@ -3,7 +3,6 @@
 set -e
 cd "$(dirname "$0")/.."
 KS_NVCC_EXTRA="$1" python kmer_spans_b200/build.py --force > gpurun_out/build_$2.log 2>&1
-grep -A2 "scan_level_kernel" kmer_spans_b200/csrc/build.log | grep -E "registers" | head -2
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/bench_$2.log 2> gpurun_out/bench_$2.err || tail -5 gpurun_out/bench_$2.err
 python - <<PY
 import json
