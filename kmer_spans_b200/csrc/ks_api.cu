@@ -105,6 +105,10 @@ struct ks_ctx {
   DBuf win_match, win_cnt, win_pre, win_scratch, win_codes, win_fix, win_hist, win_pos;
   DBuf st_aux, child_pk, child_c, child_count, tr_tables;
   DBuf st_mn, st_mx, st_bm, detail, detail_count;
+  // class table of the last ks_dev_scores(LOG2 | SIGN): index of every k-mer's count among the distinct counts
+  DBuf cls, cls_dense;
+  const void *cls_counts = nullptr;  // the count table it was derived from
+  size_t cls_n = 0;
   size_t child_cap = 0;
   DBuf st_c, st_s, st_ea, st_eb, st_flags, st_p0, tile_xf, tile_ex, group_xf, group_S, group_ex, pending_list, pending_count, launch_rec;
 
@@ -242,7 +246,8 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->tmp_inscan, &ctx->nwords, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->launch_rec, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv,
                  &ctx->win_match, &ctx->win_cnt, &ctx->win_pre, &ctx->win_scratch, &ctx->win_codes, &ctx->win_fix,
                  &ctx->win_hist, &ctx->win_pos, &ctx->st_aux, &ctx->child_pk, &ctx->child_c, &ctx->child_count,
-                 &ctx->tr_tables, &ctx->st_mn, &ctx->st_mx, &ctx->st_bm, &ctx->detail, &ctx->detail_count};
+                 &ctx->tr_tables, &ctx->st_mn, &ctx->st_mx, &ctx->st_bm, &ctx->detail, &ctx->detail_count,
+                 &ctx->cls, &ctx->cls_dense};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -743,6 +748,27 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
     ctx->lut_gval = lut;
     ctx->lut_valid = true;
     ctx->lut_k = k;
+    // class table for the scan: 2 bytes per k-mer instead of the 4-byte count (stays L2 resident at k = 12)
+    ctx->cls_counts = nullptr;
+    if (ng && ng <= 65535 && getenv("KS_NO_CLASS_TABLE") == nullptr) {
+      uint32_t ndense = std::min<uint32_t>(gcount[ng - 1] + 1, DENSE);
+      std::vector<uint16_t> dense(ndense, 0);
+      for (size_t g = 0; g < ng && gcount[g] < ndense; ++g) dense[gcount[g]] = (uint16_t)g;
+      CK(ctx->cls.ensure(n * 2));
+      CK(ctx->cls_dense.ensure((size_t)ndense * 2));
+      CK(ctx->sc_gcount.ensure((ng + 1) * 4));
+      CK(cudaMemcpyAsync(ctx->cls_dense.p, dense.data(), (size_t)ndense * 2, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->sc_gcount.p, gcount.data(), ng * 4, cudaMemcpyHostToDevice, st));
+      class_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_counts), n,
+                                                          ctx->cls_dense.as<uint16_t>(), ndense,
+                                                          ctx->sc_gcount.as<uint32_t>(), (uint32_t)ng,
+                                                          ctx->cls.as<uint16_t>());
+      LAUNCHED(1);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(st));  // `dense` lives on this stack frame
+      ctx->cls_counts = d_counts;
+      ctx->cls_n = n;
+    }
     if (d_scores) {  // the per-k-mer table itself (an output; the scan gathers counts + LUT instead)
       uint32_t ndense = ng ? std::min<uint32_t>(gcount[ng - 1] + 1, DENSE) : 0;
       std::vector<double> dense(ndense ? ndense : 1, 0.0);
@@ -925,6 +951,7 @@ struct ScanTable {  // what scan_level_kernel gathers from
   bool use_lut = false;
   const uint32_t *counts = nullptr;
   uint32_t lut_size = 0, sp_n = 0;
+  bool use_cls = false;  // class mode: ctx->cls + per-class table in ctx->lut_fx
   bool tr = false;  // transition-score scan: ctx->wfx = [trans | init], every close is re-scanned
 };
 }  // namespace
@@ -1000,6 +1027,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.ntiles = (int64_t)tiles;
     A.wfx = ctx->wfx.as<int64_t>();
     A.counts = tab.counts;
+    A.cls = ctx->cls.as<uint16_t>();
     A.lut = ctx->lut_fx.as<int64_t>();
     A.lut_size = tab.lut_size;
     A.sp_count = ctx->lut_spc.as<uint32_t>();
@@ -1062,11 +1090,13 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.child_cap = ctx->child_cap;
     if (tab.tr) CK(cudaMemsetAsync(ctx->child_count.p, 0, sizeof(unsigned long long), st));
     cudaEvent_t ps = ctx->prof_begin();
-    if (tab.tr) scan_gather_kernel<false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (fast && tab.use_lut) scan_gather_kernel<true, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (fast) scan_gather_kernel<false, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (tab.use_lut) scan_gather_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else scan_gather_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    if (tab.tr) scan_gather_kernel<0, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (fast && tab.use_cls) scan_gather_kernel<2, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (fast && tab.use_lut) scan_gather_kernel<1, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (fast) scan_gather_kernel<0, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (tab.use_cls) scan_gather_kernel<2><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (tab.use_lut) scan_gather_kernel<1><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else scan_gather_kernel<0><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     group_scan_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
     group_top_kernel<<<1, TSCAN_THREADS, 0, st>>>(A);
     if (exchange && have_carry) {
@@ -1087,10 +1117,11 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
       group_top_kernel<<<1, TSCAN_THREADS, 0, st>>>(A);
       LAUNCHED(1);
     }
-    if (tab.tr) scan_walk_kernel<false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    if (tab.tr) scan_walk_kernel<0, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (fast) scan_walk_fast_kernel<<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (tab.use_lut) scan_walk_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else scan_walk_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (tab.use_cls) scan_walk_kernel<2><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (tab.use_lut) scan_walk_kernel<1><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else scan_walk_kernel<0><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     group_ex_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
     unsigned int n_detail = 0;
     if (fast) {
@@ -1105,8 +1136,9 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
         continue;
       }
       if (n_detail) {
-        if (tab.use_lut) scan_detail_kernel<true><<<blocks_exact(n_detail, 128), 128, 0, st>>>(A);
-        else scan_detail_kernel<false><<<blocks_exact(n_detail, 128), 128, 0, st>>>(A);
+        if (tab.use_cls) scan_detail_kernel<2><<<blocks_exact(n_detail, 128), 128, 0, st>>>(A);
+        else if (tab.use_lut) scan_detail_kernel<1><<<blocks_exact(n_detail, 128), 128, 0, st>>>(A);
+        else scan_detail_kernel<0><<<blocks_exact(n_detail, 128), 128, 0, st>>>(A);
         LAUNCHED(1);
       }
     }
@@ -1346,6 +1378,22 @@ static int scan_counts_impl(ks_ctx *ctx, const ks_seqset *s, int k, const int32_
   hp.min_width = mw;
   hp.min_lo = (uint64_t)(unsigned __int128)mu;
   hp.min_hi = (int64_t)(uint64_t)(((unsigned __int128)mu) >> 64);
+  if (ctx->cls_counts == (const void *)d_counts && ctx->cls_n == ((size_t)1 << (2 * k)) && ng && ng <= 65535) {
+    // class mode: one table entry per distinct count, gathered through the 2-byte class table
+    std::vector<int64_t> fx(ng);
+    for (size_t g = 0; g < ng; ++g) fx[g] = wfx_from_double(ctx->lut_gval[g] - thr, hp.qs);
+    CK(ctx->prm.ensure(sizeof(DevScanParams)));
+    CK(ctx->lut_fx.ensure(ng * 8 + 8));
+    CK(cudaMemcpyAsync(ctx->prm.p, &hp, sizeof hp, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->lut_fx.p, fx.data(), ng * 8, cudaMemcpyHostToDevice, st));
+    ctx->prof_end(KS_PROF_WFX, pw);
+    CK(cudaStreamSynchronize(st));  // hp, fx live on this stack frame
+    ScanTable tab;
+    tab.use_lut = true;
+    tab.use_cls = true;
+    tab.lut_size = (uint32_t)ng;
+    return scan_core(ctx, s, k, tab, mw, nullptr, host_out, n_spans, sh);
+  }
   uint32_t maxc = ng ? ctx->lut_gcount[ng - 1] : 0;
   uint32_t lut_size = maxc < (1u << 16) ? maxc + 1 : (1u << 16);
   size_t sp_first = std::lower_bound(ctx->lut_gcount.begin(), ctx->lut_gcount.end(), lut_size) - ctx->lut_gcount.begin();

@@ -47,6 +47,11 @@ __device__ __forceinline__ uint32_t ldg_u32_keep(const uint32_t *addr, uint64_t 
   asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(addr), "l"(pol));
   return v;
 }
+__device__ __forceinline__ uint32_t ldg_u16_keep(const uint16_t *addr, uint64_t pol) {
+  unsigned short v;
+  asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(addr), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ int64_t ldg_s64_keep(const int64_t *addr, uint64_t pol) {
   int64_t v;
   asm volatile("ld.global.nc.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(addr), "l"(pol));
@@ -237,6 +242,7 @@ struct LevelArgs {
   // k <= 12), then the score from a dense count -> score table; counts >= lut_size use the sorted
   // sparse list (sp_count, sp_val)
   const uint32_t *counts;
+  const uint16_t *cls;  // class mode (kLut == 2): index of the k-mer's count among the distinct counts, lut[cls]
   const int64_t *lut;
   uint32_t lut_size;
   const uint32_t *sp_count;
@@ -365,7 +371,7 @@ struct ChunkSumm {
   }
 };
 
-template <bool kLut, bool kTr = false, bool kSumm = false>
+template <int kLut, bool kTr = false, bool kSumm = false>
 __global__ void __launch_bounds__(TILE_THREADS,
                                   kSumm ? (kLut ? KS_GATHER_MINBLOCKS_SUMM : KS_GATHER_MINBLOCKS_TABLE_SUMM)
                                         : (kLut ? KS_GATHER_MINBLOCKS : KS_GATHER_MINBLOCKS_TABLE))
@@ -448,7 +454,27 @@ scan_gather_kernel(const LevelArgs A) {
   uint32_t tkill = 0;
   ChunkSumm sm;
   if (kSumm) sm.init();
-  if (kLut) {
+  if (kLut == 2) {
+    // class mode: 2-byte gather (the 4^k x 2 B table stays L2 resident where the 4 B count table does not)
+    uint32_t c[CHUNK];
+    uint16_t *st16 = reinterpret_cast<uint16_t *>(A.st_c);
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u16_keep(&A.cls[code[j]], keep) : 0u;
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) {
+      const int64_t v = (scored & (1u << j)) ? __ldg(&A.lut[c[j]]) : WFX_KILL;
+      __stcs(&st16[(int64_t)j * A.Q + q], (uint16_t)c[j]);
+      if (v != WFX_KILL) {
+        live |= 1u << j;
+        ta += v;
+        int64_t t = tb + v;
+        tb = t > 0 ? t : 0;
+      } else {
+        tkill = 1; ta = 0; tb = 0;
+      }
+      if (kSumm) sm.step(j, v != WFX_KILL, v, ta);
+    }
+  } else if (kLut) {
     uint32_t c[CHUNK];
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u32_keep(&A.counts[code[j]], keep) : 0u;
@@ -638,7 +664,16 @@ struct StashScoresLut {  // scores of one chunk, LUT mode: count from the stash,
   }
 };
 
-template <bool kLut, bool kTr = false>
+struct StashScoresCls {  // class mode: 2-byte class from the stash, score from the per-class table
+  const LevelArgs *A;
+  int64_t q;
+  __device__ __forceinline__ int64_t operator[](int j) const {
+    const uint16_t *st16 = reinterpret_cast<const uint16_t *>(A->st_c);
+    return __ldg(&A->lut[__ldcs(&st16[(int64_t)j * A->Q + q])]);
+  }
+};
+
+template <int kLut, bool kTr = false>
 __global__ void __launch_bounds__(TILE_THREADS, kLut ? KS_WALK_MINBLOCKS : KS_WALK_MINBLOCKS_TABLE)
 scan_walk_kernel(const LevelArgs A) {
   __shared__ Ex s_wex[TILE_WARPS + 1];
@@ -662,7 +697,11 @@ scan_walk_kernel(const LevelArgs A) {
   excl.a = A.st_ea[q]; excl.b = A.st_eb[q]; excl.kill = (fl >> 17) & 1u;
   const fx_t S_in = head ? (fx_t)0 : xf_apply(excl, S_tile);
   int64_t s[CHUNK];
-  if (kLut) {
+  if (kLut == 2) {
+    StashScoresCls acc{&A, q};
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) s[j] = (live & (1u << j)) ? acc[j] : 0;
+  } else if (kLut) {
     StashScoresLut acc{&A, q};
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) s[j] = (live & (1u << j)) ? acc[j] : 0;
@@ -834,7 +873,7 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_WALKFAST_MINBLOCKS) scan_walk
 }
 
 // the chunks scan_walk_fast_kernel could not decide: position-by-position walk of the entering excursion
-template <bool kLut>
+template <int kLut>
 __global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
   unsigned int n = *A.detail_count;
   if (n > A.detail_cap) n = A.detail_cap;
@@ -849,7 +888,11 @@ __global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
   const uint32_t live = fl & 0xffffu;
   const int64_t p0 = A.nseg == 0 ? A.dense_start + 16 * q : A.st_p0[q];
   int64_t s[CHUNK];
-  if (kLut) {
+  if (kLut == 2) {
+    StashScoresCls acc{&A, q};
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) s[j] = (live & (1u << j)) ? acc[j] : 0;
+  } else if (kLut) {
     StashScoresLut acc{&A, q};
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) s[j] = (live & (1u << j)) ? acc[j] : 0;
@@ -1147,6 +1190,29 @@ __global__ void __launch_bounds__(256) lut_build_kernel(const uint32_t *__restri
   uint32_t c = gcount[g];
   if (c < lut_size) lut[c] = v;
   else { sp_count[g - sp_first] = c; sp_val[g - sp_first] = v; }
+}
+
+// count -> class (index among the distinct counts, ascending): dense table for small counts, binary
+// search in the sorted distinct counts otherwise
+__global__ void __launch_bounds__(256) class_apply_kernel(const uint32_t *__restrict__ counts, size_t n,
+                                                          const uint16_t *__restrict__ dense, uint32_t ndense,
+                                                          const uint32_t *__restrict__ gcount, uint32_t ngroups,
+                                                          uint16_t *__restrict__ cls) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t c = counts[i];
+    uint32_t g;
+    if (c < ndense) {
+      g = __ldg(&dense[c]);
+    } else {
+      uint32_t lo = 0, hi = ngroups;
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&gcount[mid]) <= c) lo = mid; else hi = mid;
+      }
+      g = lo;
+    }
+    cls[i] = (uint16_t)g;
+  }
 }
 
 __global__ void __launch_bounds__(256) affine_kernel(double *__restrict__ W, size_t n, double sub, double div) {
