@@ -105,6 +105,12 @@ struct ks_ctx {
   DBuf win_match, win_cnt, win_pre, win_scratch, win_codes, win_fix, win_hist, win_pos;
   DBuf st_aux, child_pk, child_c, child_count, tr_tables;
   DBuf st_mn, st_mx, st_bm, detail, detail_count;
+  // pinned host scratch for the small control-plane tables (histogram readback, count -> class / score
+  // tables, scan parameters): asynchronous copies without a synchronisation per table
+  char *hpin = nullptr;
+  static constexpr size_t HPIN_HIST = 0, HPIN_SMALL = 256u << 10, HPIN_CLS = 320u << 10, HPIN_GCOUNT = 512u << 10,
+                          HPIN_DENSE = 768u << 10, HPIN_LUT = 1280u << 10, HPIN_PRM = 1792u << 10,
+                          HPIN_BYTES = 2048u << 10;
   // class table of the last ks_dev_scores(LOG2 | SIGN): index of every k-mer's count among the distinct counts
   DBuf cls, cls_dense;
   const void *cls_counts = nullptr;  // the count table it was derived from
@@ -254,6 +260,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
   if (ctx->t0) cudaEventDestroy(ctx->t0);
   if (ctx->t1) cudaEventDestroy(ctx->t1);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->hpin) cudaFreeHost(ctx->hpin);
   if (ctx->host_set) ks_seqset_free(ctx->host_set);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
@@ -589,7 +596,12 @@ static int ensure_packed(ks_ctx *ctx, const ks_seqset *s) {
 
 // ------------------------------------------------------------------------------------------------
 // stage: count
+static int dev_count_impl(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, double *n_words, bool sync);
 int ks_dev_count(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, double *n_words) {
+  return dev_count_impl(ctx, s, k, d_counts, n_words, true);
+}
+// sync = false: the number of words stays in ctx->nwords for the stage that follows on the stream
+static int dev_count_impl(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, double *n_words, bool sync) {
   if (!ctx) return KS_ERR_ARG;
   if (!s || !d_counts) return ctx->fail(KS_ERR_ARG, "ks_dev_count: null argument");
   int rc = check_k(ctx, k);
@@ -614,6 +626,7 @@ int ks_dev_count(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, doub
   s->packed = true;
   LAUNCHED(1);
   CK(cudaGetLastError());
+  if (!sync) return KS_OK;
   unsigned long long nw = 0;
   CK(cudaMemcpyAsync(&nw, ctx->nwords.p, sizeof nw, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -671,11 +684,33 @@ int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, i
   return KS_OK;
 }
 
+static int ensure_hpin(ks_ctx *ctx) {
+  if (ctx->hpin) return KS_OK;
+  CK(cudaMallocHost((void **)&ctx->hpin, ks_ctx::HPIN_BYTES));
+  return KS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // stage: score tables
+static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double total, bool total_on_device,
+                           int mode, double param, double *d_scores, double *total_out);
 int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int mode, double param,
                   double *d_scores) {
+  return dev_scores_impl(ctx, k, d_counts, total, false, mode, param, d_scores, nullptr);
+}
+// total_on_device: the number of words is still in ctx->nwords (the count pass was not synchronised);
+// it is read back together with the histogram
+static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double total, bool total_on_device,
+                           int mode, double param, double *d_scores, double *total_out) {
   if (!ctx) return KS_ERR_ARG;
+  if (total_on_device && mode != KS_MODE_LOG2 && mode != KS_MODE_SIGN) {
+    unsigned long long nw = 0;
+    CK(cudaMemcpyAsync(&nw, ctx->nwords.p, sizeof nw, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    total = (double)nw;
+    total_on_device = false;
+  }
+  if (total_out && !total_on_device) *total_out = total;
   const bool count_fn_mode = (mode == KS_MODE_LOG2 || mode == KS_MODE_SIGN);
   if (!d_counts || (!d_scores && !count_fn_mode)) return ctx->fail(KS_ERR_ARG, "ks_dev_scores: null argument");
   int rc = check_k(ctx, k);
@@ -695,7 +730,11 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
     CK(ctx->sc_small.ensure(64));
     CK(ctx->foc_hist.ensure((size_t)DENSE * 4));
     uint32_t big_cap = 1u << 16;
-    std::vector<uint32_t> hist(DENSE), big;
+    rc = ensure_hpin(ctx);
+    if (rc) return rc;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(ctx->hpin + ks_ctx::HPIN_HIST);
+    uint32_t *hsmall = reinterpret_cast<uint32_t *>(ctx->hpin + ks_ctx::HPIN_SMALL);
+    std::vector<uint32_t> big;
     for (int attempt = 0; attempt < 2; ++attempt) {
       CK(ctx->foc_big.ensure((size_t)big_cap * 4));
       CK(cudaMemsetAsync(ctx->sc_small.p, 0, 64, st));
@@ -705,10 +744,18 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
           ctx->foc_big.as<uint32_t>(), ctx->sc_small.as<uint32_t>(), big_cap);
       LAUNCHED(1);
       CK(cudaGetLastError());
-      uint32_t nbig = 0;
-      CK(cudaMemcpyAsync(&nbig, ctx->sc_small.p, 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(hist.data(), ctx->foc_hist.p, (size_t)DENSE * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(hsmall, ctx->sc_small.p, 4, cudaMemcpyDeviceToHost, st));
+      if (total_on_device) CK(cudaMemcpyAsync(hsmall + 2, ctx->nwords.p, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(hist, ctx->foc_hist.p, (size_t)DENSE * 4, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
+      const uint32_t nbig = hsmall[0];
+      if (total_on_device) {
+        unsigned long long nw;
+        memcpy(&nw, hsmall + 2, 8);
+        total = (double)nw;
+        total_on_device = false;
+        if (total_out) *total_out = total;
+      }
       if (nbig > big_cap) { big_cap = nbig; continue; }
       big.resize(nbig);
       if (nbig) CK(cudaMemcpy(big.data(), ctx->foc_big.p, (size_t)nbig * 4, cudaMemcpyDeviceToHost));
@@ -752,40 +799,58 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
     ctx->cls_counts = nullptr;
     if (ng && ng <= 65535 && getenv("KS_NO_CLASS_TABLE") == nullptr) {
       uint32_t ndense = std::min<uint32_t>(gcount[ng - 1] + 1, DENSE);
-      std::vector<uint16_t> dense(ndense, 0);
+      // staged in pinned memory: every earlier copy out of it completed before the synchronisation above
+      uint16_t *dense = reinterpret_cast<uint16_t *>(ctx->hpin + ks_ctx::HPIN_CLS);
+      uint32_t *gc_pin = reinterpret_cast<uint32_t *>(ctx->hpin + ks_ctx::HPIN_GCOUNT);
+      memset(dense, 0, (size_t)ndense * 2);
       for (size_t g = 0; g < ng && gcount[g] < ndense; ++g) dense[gcount[g]] = (uint16_t)g;
+      memcpy(gc_pin, gcount.data(), ng * 4);
       CK(ctx->cls.ensure(n * 2));
       CK(ctx->cls_dense.ensure((size_t)ndense * 2));
       CK(ctx->sc_gcount.ensure((ng + 1) * 4));
-      CK(cudaMemcpyAsync(ctx->cls_dense.p, dense.data(), (size_t)ndense * 2, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(ctx->sc_gcount.p, gcount.data(), ng * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->cls_dense.p, dense, (size_t)ndense * 2, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->sc_gcount.p, gc_pin, ng * 4, cudaMemcpyHostToDevice, st));
       class_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_counts), n,
                                                           ctx->cls_dense.as<uint16_t>(), ndense,
                                                           ctx->sc_gcount.as<uint32_t>(), (uint32_t)ng,
                                                           ctx->cls.as<uint16_t>());
       LAUNCHED(1);
       CK(cudaGetLastError());
-      CK(cudaStreamSynchronize(st));  // `dense` lives on this stack frame
       ctx->cls_counts = d_counts;
       ctx->cls_n = n;
     }
     if (d_scores) {  // the per-k-mer table itself (an output; the scan gathers counts + LUT instead)
       uint32_t ndense = ng ? std::min<uint32_t>(gcount[ng - 1] + 1, DENSE) : 0;
-      std::vector<double> dense(ndense ? ndense : 1, 0.0);
+      const bool staged = ng <= 65536;  // pinned staging: no synchronisation needed behind the copies
+      std::vector<double> dense_v;
+      double *dense = reinterpret_cast<double *>(ctx->hpin + ks_ctx::HPIN_DENSE);
+      double *lut_src = reinterpret_cast<double *>(ctx->hpin + ks_ctx::HPIN_LUT);
+      uint32_t *gc_src = reinterpret_cast<uint32_t *>(ctx->hpin + ks_ctx::HPIN_GCOUNT);
+      if (!staged) {
+        dense_v.assign(ndense ? ndense : 1, 0.0);
+        dense = dense_v.data();
+        lut_src = lut.data();
+        gc_src = gcount.data();
+      } else {
+        memcpy(lut_src, lut.data(), ng * 8);
+        memcpy(gc_src, gcount.data(), ng * 4);
+      }
+      const size_t dense_n = ndense ? ndense : 1;
+      memset(dense, 0, dense_n * 8);
       for (size_t g = 0; g < ng && gcount[g] < ndense; ++g) dense[gcount[g]] = lut[g];
       CK(ctx->sc_gcount.ensure((ng + 1) * 4));
       CK(ctx->sc_lut.ensure(ng * 8 + 8));
-      CK(ctx->sc_dense.ensure((size_t)dense.size() * 8));
-      CK(cudaMemcpyAsync(ctx->sc_gcount.p, gcount.data(), ng * 4, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(ctx->sc_lut.p, lut.data(), ng * 8, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(ctx->sc_dense.p, dense.data(), dense.size() * 8, cudaMemcpyHostToDevice, st));
+      CK(ctx->sc_dense.ensure(dense_n * 8));
+      CK(cudaMemcpyAsync(ctx->sc_gcount.p, gc_src, ng * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->sc_lut.p, lut_src, ng * 8, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->sc_dense.p, dense, dense_n * 8, cudaMemcpyHostToDevice, st));
       lut_apply_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_counts), n,
                                                              ctx->sc_dense.as<double>(), ndense,
                                                              ctx->sc_gcount.as<uint32_t>(), (uint32_t)ng,
                                                              ctx->sc_lut.as<double>(), d_scores);
       LAUNCHED(1);
       CK(cudaGetLastError());
-      CK(cudaStreamSynchronize(st));
+      if (!staged) CK(cudaStreamSynchronize(st));
     }
     return KS_OK;
   }
@@ -982,6 +1047,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     if (rc) return rc;
   }
   unsigned long long level_start = 0;  // records before this level
+  unsigned long long rec_total = 0;    // records after the last completed level
   int64_t nseg = 0, total_chunks = dense_chunks;
   int64_t dense_chunk0 = 0;
   if (sh) {
@@ -1123,24 +1189,14 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     else if (tab.use_lut) scan_walk_kernel<1><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else scan_walk_kernel<0><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     group_ex_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
-    unsigned int n_detail = 0;
     if (fast) {
-      // the list is short (one entry per tile at most, plus the rare wide excursions): its length decides
-      // the grid of the detail kernel, and an overflow sends the level back to the general walk
-      CK(cudaMemcpyAsync(&n_detail, ctx->detail_count.p, 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      if (n_detail > A.detail_cap) {
-        fast = false;
-        CK(cudaMemcpyAsync(d_rec_count, &level_start, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-        count_inscan = false;
-        continue;
-      }
-      if (n_detail) {
-        if (tab.use_cls) scan_detail_kernel<2><<<blocks_exact(n_detail, 128), 128, 0, st>>>(A);
-        else if (tab.use_lut) scan_detail_kernel<1><<<blocks_exact(n_detail, 128), 128, 0, st>>>(A);
-        else scan_detail_kernel<0><<<blocks_exact(n_detail, 128), 128, 0, st>>>(A);
-        LAUNCHED(1);
-      }
+      // the list is short (one entry per tile at most, plus the rare wide excursions); the kernel reads
+      // its length on the device and strides over it, so no host round trip sits between the kernels
+      const unsigned dgrid = (unsigned)std::min<size_t>(blocks_exact(tiles + 1024, 128), 148u * 8u);
+      if (tab.use_cls) scan_detail_kernel<2><<<dgrid, 128, 0, st>>>(A);
+      else if (tab.use_lut) scan_detail_kernel<1><<<dgrid, 128, 0, st>>>(A);
+      else scan_detail_kernel<0><<<dgrid, 128, 0, st>>>(A);
+      LAUNCHED(1);
     }
     if (exchange && have_carry) {
       A.E_start = E_carry;
@@ -1163,8 +1219,10 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     CK(cudaGetLastError());
     struct { unsigned long long cnt, children; } hres;
     hres.children = 0;
+    unsigned int n_detail = 0;
     DevScanParams hprm;
     CK(cudaMemcpyAsync(&hres.cnt, d_rec_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (fast) CK(cudaMemcpyAsync(&n_detail, ctx->detail_count.p, 4, cudaMemcpyDeviceToHost, st));
     if (tab.tr)
       CK(cudaMemcpyAsync(&hres.children, ctx->child_count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     if (level == 0) CK(cudaMemcpyAsync(&hprm, d_prm, sizeof hprm, cudaMemcpyDeviceToHost, st));
@@ -1174,6 +1232,13 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     if (level == 0 && tab.tr && (hprm.err & 2))
       return ctx->fail(KS_ERR_RANGE, "a transition or k-mer score is NaN");
     count_inscan = false;  // every position of this level has been counted, also if we must retry
+    if (fast && n_detail > A.detail_cap) {
+      // more undecided chunks than the list holds: redo the level with the general walk
+      fast = false;
+      CK(cudaMemcpyAsync(d_rec_count, &level_start, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      continue;
+    }
     if (hres.cnt > ctx->rec_cap || hres.children > ctx->child_cap) {
       // record buffer too small: grow (keeping earlier levels), rewind the counter, redo the level
       if (hres.cnt > ctx->rec_cap) rc = ensure_recs(ctx, (size_t)hres.cnt + (size_t)hres.cnt / 8 + 1024);
@@ -1185,6 +1250,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
       continue;
     }
     fast = fast_ok;
+    rec_total = hres.cnt;
     if (level > 0) revisit_chunks += (uint64_t)total_chunks;
     unsigned long long n_new = tab.tr ? hres.children : hres.cnt - level_start;
     ++level;
@@ -1220,9 +1286,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
   ctx->last_revisit_chunks = revisit_chunks;
 
   // order by start position and convert to the reference layout
-  unsigned long long n = 0;
-  CK(cudaMemcpyAsync(&n, d_rec_count, sizeof n, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  const unsigned long long n = rec_total;  // read back at the end of the last level
   if (n_spans) *n_spans = n;
   if (n == 0) return KS_OK;
   if (n > 0xfffffff0ull) return ctx->fail(KS_ERR_NOMEM, "too many spans");
@@ -1380,14 +1444,19 @@ static int scan_counts_impl(ks_ctx *ctx, const ks_seqset *s, int k, const int32_
   hp.min_hi = (int64_t)(uint64_t)(((unsigned __int128)mu) >> 64);
   if (ctx->cls_counts == (const void *)d_counts && ctx->cls_n == ((size_t)1 << (2 * k)) && ng && ng <= 65535) {
     // class mode: one table entry per distinct count, gathered through the 2-byte class table
-    std::vector<int64_t> fx(ng);
+    // staged in pinned memory; the last scan on this context ended with a synchronisation, so nothing
+    // still reads these regions
+    rc = ensure_hpin(ctx);
+    if (rc) return rc;
+    int64_t *fx = reinterpret_cast<int64_t *>(ctx->hpin + ks_ctx::HPIN_LUT);
+    DevScanParams *hp_pin = reinterpret_cast<DevScanParams *>(ctx->hpin + ks_ctx::HPIN_PRM);
     for (size_t g = 0; g < ng; ++g) fx[g] = wfx_from_double(ctx->lut_gval[g] - thr, hp.qs);
+    *hp_pin = hp;
     CK(ctx->prm.ensure(sizeof(DevScanParams)));
     CK(ctx->lut_fx.ensure(ng * 8 + 8));
-    CK(cudaMemcpyAsync(ctx->prm.p, &hp, sizeof hp, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->lut_fx.p, fx.data(), ng * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->prm.p, hp_pin, sizeof hp, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->lut_fx.p, fx, ng * 8, cudaMemcpyHostToDevice, st));
     ctx->prof_end(KS_PROF_WFX, pw);
-    CK(cudaStreamSynchronize(st));  // hp, fx live on this stack frame
     ScanTable tab;
     tab.use_lut = true;
     tab.use_cls = true;
@@ -1478,11 +1547,12 @@ int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double par
                     ks_spans *host_out, uint64_t *n_spans) {
   if (!ctx) return KS_ERR_ARG;
   double nw = 0;
-  int rc = ks_dev_count(ctx, s, k, d_counts, &nw);
+  // the word count is read back together with the first table the score stage needs on the host
+  int rc = dev_count_impl(ctx, s, k, d_counts, nullptr, false);
+  if (rc) return rc;
+  rc = dev_scores_impl(ctx, k, d_counts, 0.0, true, mode, param, d_scores, &nw);
   if (rc) return rc;
   if (n_words) *n_words = nw;
-  rc = ks_dev_scores(ctx, k, d_counts, nw, mode, param, d_scores);
-  if (rc) return rc;
   if (mode == KS_MODE_LOG2 || mode == KS_MODE_SIGN)
     return ks_dev_scan_counts(ctx, s, k, d_counts, thr, min_width, min_score, host_out, n_spans);
   return ks_dev_scan(ctx, s, k, d_scores, thr, min_width, min_score, nullptr, host_out, n_spans);

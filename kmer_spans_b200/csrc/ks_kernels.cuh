@@ -877,8 +877,7 @@ template <int kLut>
 __global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
   unsigned int n = *A.detail_count;
   if (n > A.detail_cap) n = A.detail_cap;
-  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
   const DetailEntry e = A.detail[i];
   const int64_t q = e.q;
   ScanParams prm;
@@ -906,7 +905,7 @@ __global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
   int64_t prePk;
   int first_zero;
   chunk_walk(s, live, e.S_in, p0, prm, emit, ex, preM, prePk, first_zero);
-  if (first_zero < 0) return;  // cannot happen: the fast walk saw a zero in this chunk
+  if (first_zero < 0) continue;  // cannot happen: the fast walk saw a zero in this chunk
   if (e.reset) {
     Ex ein;
     ein.M = e.M; ein.beg = e.beg; ein.pk = e.pk; ein.reset = 1; ein.open = 1;
@@ -923,6 +922,7 @@ __global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
     pe.valid = 1; pe.pad[0] = pe.pad[1] = pe.pad[2] = 0;
     A.pending[e.tile] = pe;
     A.pending_list[atomicAdd(A.pending_count, 1u)] = (uint32_t)e.tile;
+  }
   }
 }
 
