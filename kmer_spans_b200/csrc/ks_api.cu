@@ -1670,10 +1670,12 @@ int ks_kmer_mode_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *le
   rc = upload_and_count(ctx, seqs, lens, nseq, k, d_counts, &nw, &ss);   // counting hides behind the H2D
   if (rc) return rc;
   if (n_words) *n_words = nw;
-  if (counts_out) { rc = copy_out_async(ctx, counts_out, d_counts, n * 4); if (rc) return rc; }  // overlaps scores + scan
   const bool count_fn = (mode == KS_MODE_LOG2 || mode == KS_MODE_SIGN);
   rc = ks_dev_scores(ctx, k, d_counts, nw, mode, param, (count_fn && !scores_out) ? nullptr : d_scores);
-  if (!rc && scores_out) rc = copy_out_async(ctx, scores_out, d_scores, n * 8);                  // overlaps the scan
+  // the table copies go out only now: the score stage reads small tables back, and a 64 MiB copy in front
+  // of them on the device-to-host engine would stall it for a millisecond; both copies overlap the scan
+  if (!rc && counts_out) rc = copy_out_async(ctx, counts_out, d_counts, n * 4);
+  if (!rc && scores_out) rc = copy_out_async(ctx, scores_out, d_scores, n * 8);
   if (!rc) {
     if (count_fn) rc = ks_dev_scan_counts(ctx, ss, k, d_counts, thr, min_width, min_score, out, nullptr);
     else rc = ks_dev_scan(ctx, ss, k, d_scores, thr, min_width, min_score, nullptr, out, nullptr);
