@@ -105,6 +105,12 @@ struct ks_ctx {
   DBuf win_match, win_cnt, win_pre, win_scratch, win_codes, win_fix, win_hist, win_pos;
   DBuf st_aux, child_pk, child_c, child_count, tr_tables;
   DBuf st_mn, st_mx, st_bm, detail, detail_count;
+  // table copies into pageable host memory (what R hands over): a helper thread stages them through the
+  // pinned windows and spreads the final memcpy over several threads while the scan runs
+  struct OutJob { void *dst; const void *src; size_t bytes; };
+  std::vector<OutJob> out_jobs;
+  std::thread out_thread;
+  int out_rc = 0;
   // pinned host scratch for the small control-plane tables (histogram readback, count -> class / score
   // tables, scan parameters): asynchronous copies without a synchronisation per table
   char *hpin = nullptr;
@@ -241,6 +247,7 @@ int ks_ctx_create(ks_ctx **out, int device) {
 void ks_ctx_destroy(ks_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->out_thread.joinable()) ctx->out_thread.join();
   cudaStreamSynchronize(ctx->stream);
   DBuf *all[] = {&ctx->wfx, &ctx->prm, &ctx->rec_beg, &ctx->rec_pk, &ctx->rec_c,
                  &ctx->rec_mhi, &ctx->rec_mlo, &ctx->rec_count, &ctx->seg_start, &ctx->seg_len,
@@ -381,6 +388,12 @@ static int ensure_copy_stream(ks_ctx *ctx) {
   return KS_OK;
 }
 
+static bool host_ptr_is_pinned(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 // H2D of the sequences into the layout of ks_layout.h on the copy stream.  With count_k > 0 the
 // pack+count kernel is launched on the compute stream slab by slab behind the copies (it is far
 // faster than PCIe, so counting hides completely behind the upload).
@@ -435,7 +448,7 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
   bool ev_used[2] = {false, false};
   int half = 0;
   // plan: maximal groups of consecutive small sequences that fit one staging half
-  struct Item { int seq; size_t off; };
+  struct Item { const char *src; size_t len; size_t off; bool sep; };  // sep: zero the byte in front (separator)
   std::vector<Item> items;
   size_t fill = 0;
   int64_t win_start = -1;  // global offset the current window maps to
@@ -452,8 +465,8 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
     auto work = [&](unsigned t) {
       for (size_t i = t; i < items.size(); i += nthreads) {
         const Item &it = items[i];
-        memcpy(win + it.off, seqs[it.seq], (size_t)lens[it.seq]);
-        if (it.off) win[it.off - 1] = 0;  // separator in front of every sequence but the first
+        memcpy(win + it.off, it.src, it.len);
+        if (it.sep) win[it.off - 1] = 0;  // separator in front of every sequence but the first of the window
       }
     };
     if (nthreads > 1 && fill > (1u << 20)) {
@@ -480,6 +493,24 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
   for (int i = 0; i < nseq && e == cudaSuccess; ++i) {
     int64_t ln = lens[i];
     if (ln == 0) continue;
+    if (ln >= DIRECT && !host_ptr_is_pinned(seqs[i])) {
+      // a long sequence in pageable memory (what R hands over): the driver would stage it at a few GB/s;
+      // packed into the pinned windows by the host threads it moves near the PCIe rate
+      e = flush();
+      const size_t SUB = 1u << 20;  // granule of the per-thread memcpy
+      for (int64_t off = 0; off < ln && e == cudaSuccess;) {
+        if (fill == HALF) { e = flush(); if (e != cudaSuccess) break; }
+        if (fill == 0) win_start = s->starts[i] + off;
+        size_t room = HALF - fill;
+        size_t take = (size_t)(ln - off) < room ? (size_t)(ln - off) : room;
+        for (size_t a = 0; a < take; a += SUB)
+          items.push_back({seqs[i] + off + (int64_t)a, take - a < SUB ? take - a : SUB, fill + a, false});
+        fill += take;
+        off += (int64_t)take;
+      }
+      if (e == cudaSuccess) e = flush();
+      continue;
+    }
     if (ln >= DIRECT) {
       e = flush();
       // in pieces, so that counting can start while the rest is still on the bus
@@ -494,9 +525,10 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
     // contiguous with the window?  (separator bytes between sequences are copied as zeros)
     if (fill && (s->starts[i] != win_start + (int64_t)fill + 1 || fill + 1 + (size_t)ln > HALF)) e = flush();
     if (e != cudaSuccess) break;
+    bool sep = false;
     if (fill == 0) win_start = s->starts[i];
-    else fill += 1;
-    items.push_back({i, fill});
+    else { fill += 1; sep = true; }
+    items.push_back({seqs[i], (size_t)ln, fill, sep});
     fill += (size_t)ln;
   }
   if (e == cudaSuccess) e = flush();
@@ -1588,11 +1620,76 @@ static int upload_and_count(ks_ctx *ctx, const char *const *seqs, const int64_t 
 static int copy_out_async(ks_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes) {
   CK(cudaEventRecord(ctx->ev_compute, ctx->stream));
   CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute, 0));
-  CK(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  if (host_ptr_is_pinned(host_dst) || bytes < (4u << 20) || !ctx->pinned) {
+    CK(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    return KS_OK;
+  }
+  ctx->out_jobs.push_back({host_dst, dev_src, bytes});  // pageable destination: staged by start_staged_copies()
   return KS_OK;
 }
+// A device-to-host copy into pageable memory runs at a few GB/s; staged through the two pinned windows
+// (the upload is done with them by now) with the final memcpy spread over host threads it runs near the
+// PCIe rate, and in a helper thread it overlaps the scan.
+static void start_staged_copies(ks_ctx *ctx) {
+  if (ctx->out_jobs.empty()) return;
+  ctx->out_rc = 0;
+  ctx->out_thread = std::thread([ctx]() {
+    cudaSetDevice(ctx->device);
+    const size_t HALF = ctx->pinned_cap / 2;
+    cudaEvent_t ev[2];
+    cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+    unsigned nthreads = std::thread::hardware_concurrency();
+    nthreads = nthreads > 6 ? 6 : (nthreads < 1 ? 1 : nthreads);
+    auto spread = [&](char *dst, const char *src, size_t len) {
+      std::vector<std::thread> th;
+      const size_t per = (len + nthreads - 1) / nthreads;
+      for (unsigned t = 1; t < nthreads; ++t) {
+        size_t a = (size_t)t * per;
+        if (a >= len) break;
+        size_t b = a + per < len ? a + per : len;
+        th.emplace_back([=]() { memcpy(dst + a, src + a, b - a); });
+      }
+      memcpy(dst, src, per < len ? per : len);
+      for (auto &x : th) x.join();
+    };
+    cudaError_t e = cudaSuccess;
+    for (const auto &job : ctx->out_jobs) {
+      size_t prev_off = 0, prev_len = 0;
+      int half = 0;
+      bool have_prev = false;
+      for (size_t off = 0; off < job.bytes && e == cudaSuccess; off += HALF) {
+        const size_t len = job.bytes - off < HALF ? job.bytes - off : HALF;
+        char *win = (char *)ctx->pinned + (size_t)half * HALF;
+        e = cudaMemcpyAsync(win, (const char *)job.src + off, len, cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[half], ctx->copy_stream);
+        if (have_prev && e == cudaSuccess) {  // the other window is complete: hand it over while this one fills
+          e = cudaEventSynchronize(ev[half ^ 1]);
+          if (e == cudaSuccess) spread((char *)job.dst + prev_off, (char *)ctx->pinned + (size_t)(half ^ 1) * HALF, prev_len);
+        }
+        prev_off = off; prev_len = len; have_prev = true;
+        half ^= 1;
+      }
+      if (have_prev && e == cudaSuccess) {
+        e = cudaEventSynchronize(ev[half ^ 1]);
+        if (e == cudaSuccess) spread((char *)job.dst + prev_off, (char *)ctx->pinned + (size_t)(half ^ 1) * HALF, prev_len);
+      }
+      if (e != cudaSuccess) break;
+    }
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (e != cudaSuccess) ctx->out_rc = (int)e;
+  });
+}
 static int finish_copies(ks_ctx *ctx) {
+  if (ctx->out_thread.joinable()) ctx->out_thread.join();
+  ctx->out_jobs.clear();
   if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+  if (ctx->out_rc) {
+    cudaError_t e = (cudaError_t)ctx->out_rc;
+    ctx->out_rc = 0;
+    return ctx->fail(KS_ERR_CUDA, "copy of a result table to the host failed: %s", cudaGetErrorString(e));
+  }
   return KS_OK;
 }
 
@@ -1609,9 +1706,10 @@ int ks_kmer_counts(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, in
   ks_seqset *ss = nullptr;
   rc = upload_and_count(ctx, seqs, lens, nseq, k, ctx->tmp_counts.as<int32_t>(), n_words, &ss);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(counts_out, ctx->tmp_counts.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  return KS_OK;
+  rc = copy_out_async(ctx, counts_out, ctx->tmp_counts.p, n * 4);
+  start_staged_copies(ctx);
+  int rc2 = finish_copies(ctx);
+  return rc ? rc : rc2;
 }
 
 int ks_kmer_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k, const double *W,
@@ -1643,8 +1741,10 @@ int ks_kmer_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, i
                    inscan_counts_out ? ctx->tmp_inscan.as<int32_t>() : nullptr, out, nullptr);
   if (rc) return rc;
   if (inscan_counts_out) {
-    CK(cudaMemcpyAsync(inscan_counts_out, ctx->tmp_inscan.p, n * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    rc = copy_out_async(ctx, inscan_counts_out, ctx->tmp_inscan.p, n * 4);
+    start_staged_copies(ctx);
+    int rc2 = finish_copies(ctx);
+    return rc ? rc : rc2;
   }
   return KS_OK;
 }
@@ -1676,6 +1776,7 @@ int ks_kmer_mode_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *le
   // of them on the device-to-host engine would stall it for a millisecond; both copies overlap the scan
   if (!rc && counts_out) rc = copy_out_async(ctx, counts_out, d_counts, n * 4);
   if (!rc && scores_out) rc = copy_out_async(ctx, scores_out, d_scores, n * 8);
+  start_staged_copies(ctx);
   if (!rc) {
     if (count_fn) rc = ks_dev_scan_counts(ctx, ss, k, d_counts, thr, min_width, min_score, out, nullptr);
     else rc = ks_dev_scan(ctx, ss, k, d_scores, thr, min_width, min_score, nullptr, out, nullptr);

@@ -23,3 +23,6 @@ print("upload only: %.2f ms" % tm(lambda: ctx.upload([pinned]).free()))
 print("kmer_counts (pinned in, pageable out): %.2f ms" % tm(lambda: ctx.kmer_counts([pinned], 12, with_f=False)))
 print("mode_regions no tables: %.2f ms" % tm(lambda: ctx.kmer_mode_regions([pinned], 12, 1, 100, 20.0, want_tables=False)))
 print("mode_regions counts_out pinned: %.2f ms" % tm(lambda: ctx.kmer_mode_regions([pinned], 12, 1, 100, 20.0, want_tables=False, counts_out=counts_host)))
+co = np.zeros(4 ** 12, np.int32); so = np.zeros(4 ** 12, np.float64)
+print("mode_regions log2, counts + scores to pageable numpy: %.2f ms" % tm(lambda: ctx.kmer_mode_regions([pinned], 12, 1, 100, 20.0, want_tables=True)))
+print("low_comp (rank), counts + ranks to pageable numpy (the R call): %.2f ms" % tm(lambda: ctx.kmer_low_comp_regions([seq], 12, 100, 20.0)))
