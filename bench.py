@@ -215,6 +215,10 @@ def main():
     counts_host = torch.empty(4 ** K, dtype=torch.int32).pin_memory()
 
     def step():
+        if world == 1:  # one C-ABI call: ks_dev_pipeline (count -> scores -> scan, everything resident)
+            r = ctx.dev_pipeline(stages.ss, K, MODE_LOG2, MIN_W, MIN_SCORE, thr=THR,
+                                 d_counts=stages.counts.data_ptr(), d_scores=stages.scores.data_ptr())
+            return r["n_spans"]
         n = stages.count(K)
         total = n
         if world > 1:

@@ -153,6 +153,14 @@ struct ks_ctx {
   void prof_resolve() {
     if (prof_pending.empty()) return;
     cudaStreamSynchronize(stream);
+    if (getenv("KS_PROF_GAPS")) {  // debugging aid: idle time between consecutive profiled stages
+      for (size_t i = 0; i + 1 < prof_pending.size(); ++i) {
+        float g = 0;
+        if (cudaEventElapsedTime(&g, prof_pending[i].b, prof_pending[i + 1].a) == cudaSuccess)
+          fprintf(stderr, "[ks gaps] after stage %d before stage %d: %.3f ms\n", prof_pending[i].which,
+                  prof_pending[i + 1].which, g);
+      }
+    }
     for (auto &p : prof_pending) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { prof_ms[p.which] += ms; prof_n[p.which] += 1; }
@@ -1065,7 +1073,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
   rc = ensure_packed(ctx, s);  // no counting pass ran on this set (user-supplied weights): pack only
   if (rc) return rc;
   unsigned long long *d_rec_count = ctx->rec_count.as<unsigned long long>();
-  CK(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(d_rec_count, 0, 2 * sizeof(unsigned long long), st));
 
   const int64_t dense_chunks = (s->total - 16) / 16;
   if (s->total >= (1ll << 32))
@@ -1172,6 +1180,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.rec_mlo = ctx->rec_mlo.as<uint64_t>();
     A.rec_count = d_rec_count;
     A.rec_cap = ctx->rec_cap;
+    A.inscan_mode = d_inscan != nullptr;
+    CK(cudaMemsetAsync(d_rec_count + 1, 0, sizeof(unsigned long long), st));
     A.st_mn = ctx->st_mn.as<int64_t>();
     A.st_mx = ctx->st_mx.as<int64_t>();
     A.st_bm = ctx->st_bm.as<int64_t>();
@@ -1249,11 +1259,11 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     ctx->prof_end(level == 0 ? KS_PROF_SCAN0 : KS_PROF_SCANN, ps);
     LAUNCHED(6);
     CK(cudaGetLastError());
-    struct { unsigned long long cnt, children; } hres;
+    struct { unsigned long long cnt, child_chunks, children; } hres;
     hres.children = 0;
     unsigned int n_detail = 0;
     DevScanParams hprm;
-    CK(cudaMemcpyAsync(&hres.cnt, d_rec_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hres.cnt, d_rec_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     if (fast) CK(cudaMemcpyAsync(&n_detail, ctx->detail_count.p, 4, cudaMemcpyDeviceToHost, st));
     if (tab.tr)
       CK(cudaMemcpyAsync(&hres.children, ctx->child_count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1287,6 +1297,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     unsigned long long n_new = tab.tr ? hres.children : hres.cnt - level_start;
     ++level;
     if (n_new == 0) break;
+    if (!tab.tr && hres.child_chunks == 0) break;  // no record of this level spawns a re-scan
     // child segments of the records this level emitted
     CK(ctx->seg_start.ensure(n_new * 8));
     CK(ctx->seg_len.ensure(n_new * 8));
@@ -1323,7 +1334,13 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
   if (n == 0) return KS_OK;
   if (n > 0xfffffff0ull) return ctx->fail(KS_ERR_NOMEM, "too many spans");
   const uint32_t *d_perm = nullptr;
-  if (n > 1) {
+  if (n > 1 && n <= (unsigned long long)SMALL_SORT_MAX) {
+    CK(ctx->sort_vals_a.ensure(n * 4));
+    small_sort_kernel<<<1, 1024, 0, st>>>(ctx->rec_beg.as<int64_t>(), (unsigned int)n, ctx->sort_vals_a.as<uint32_t>());
+    LAUNCHED(1);
+    CK(cudaGetLastError());
+    d_perm = ctx->sort_vals_a.as<uint32_t>();
+  } else if (n > 1) {
     CK(ctx->sort_keys_a.ensure(n * 8));
     CK(ctx->sort_keys_b.ensure(n * 8));
     CK(ctx->sort_vals_a.ensure(n * 4));

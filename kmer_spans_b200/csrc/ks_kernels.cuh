@@ -286,8 +286,9 @@ struct LevelArgs {
   // emitted records (SoA), appended across levels
   int64_t *rec_beg, *rec_pk, *rec_c, *rec_mhi;
   uint64_t *rec_mlo;
-  unsigned long long *rec_count;
+  unsigned long long *rec_count;  // [0] records, [1] chunks of the child segments they spawn
   unsigned long long rec_cap;
+  int inscan_mode;                // in-scan counting asked for: every child segment is re-scanned
   // fast walk (min_width >= 15): per-chunk summary written by the gather kernel and the list
   // of chunks whose entering excursion closes and might qualify
   int64_t *st_mn, *st_mx, *st_bm;
@@ -316,6 +317,11 @@ struct DevEmit {
       A->rec_mhi[slot] = (int64_t)fx_hi(M);
       A->rec_mlo[slot] = fx_lo(M);
     }
+    // tell the host at the end of the level whether any re-scan follows at all (spans are rare: most
+    // levels end here, without building the segment table)
+    int64_t st, ln;
+    if (!A->tr && child_segment(pk, c, A->prm->min_width, A->inscan_mode != 0, st, ln))
+      atomicAdd(A->rec_count + 1, (unsigned long long)segment_chunks(ln));
   }
   // transition-score scan: regions and re-scan requests are separate sets
   __device__ __forceinline__ void out(int64_t beg, int64_t pk, fx_t M) const { (*this)(beg, pk, 0, M); }
@@ -1065,6 +1071,26 @@ __global__ void __launch_bounds__(256) finalize_kernel(const uint32_t *__restric
   pos[3 * i + 2] = (int32_t)(pk - starts[lo]) + one_based;
   score[2 * i] = fx_to_double(fx_make((uint64_t)rec_mhi[r], rec_mlo[r]), prm->qs);
   score[2 * i + 1] = 0.0;
+}
+
+// few records (the usual case: spans are rare): rank every start among all starts in one CTA instead of
+// the ~25 launches of the multi-pass radix sort.  perm[rank] = record id; starts are distinct, ties (never
+// expected) keep record order.
+constexpr int SMALL_SORT_MAX = 4096;
+__global__ void __launch_bounds__(1024) small_sort_kernel(const int64_t *__restrict__ rec_beg, unsigned int n,
+                                                          uint32_t *__restrict__ perm) {
+  __shared__ int64_t key[SMALL_SORT_MAX];
+  for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) key[i] = rec_beg[i];
+  __syncthreads();
+  for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t mine = key[i];
+    unsigned int r = 0;
+    for (unsigned int j = 0; j < n; ++j) {
+      const int64_t o = key[j];
+      r += (o < mine || (o == mine && j < i)) ? 1u : 0u;
+    }
+    perm[r] = i;
+  }
 }
 
 __global__ void __launch_bounds__(256) copy_keys_kernel(const int64_t *__restrict__ rec_beg,
