@@ -455,21 +455,91 @@ scan_gather_kernel(const LevelArgs A) {
     decode_scan(X, brk32, A.k, A.kmask, n_in, code, scored);
   }
   const uint64_t keep = l2_policy_evict_last();
+  // ---- gather: 16 independent loads per thread ----
+  uint32_t c[CHUNK];   // class (kLut == 2) or count (kLut == 1)
+  int64_t sv[CHUNK];   // score (table mode)
+  if (kLut == 2) {
+    // class mode: 2-byte gather (the 4^k x 2 B table stays L2 resident where the 4 B count table does not)
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u16_keep(&A.cls[code[j]], keep) : 0u;
+  } else if (kLut) {
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u32_keep(&A.counts[code[j]], keep) : 0u;
+  } else {
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) sv[j] = (scored & (1u << j)) ? ldg_s64_keep(&A.wfx[code[j]], keep) : WFX_KILL;
+  }
+  // value of a SCORED position (WFX_KILL = the table says "force the state to 0")
+  auto value = [&](int j) -> int64_t {
+    if (kLut == 2) return __ldg(&A.lut[c[j]]);
+    if (kLut) {
+      if (c[j] < A.lut_size) return __ldg(&A.lut[c[j]]);
+      uint32_t lo = 0, hi = A.sp_n;  // rare: very abundant k-mer, look it up in the sorted sparse list
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&A.sp_count[mid]) <= c[j]) lo = mid; else hi = mid;
+      }
+      return __ldg(&A.sp_val[lo]);
+    }
+    return sv[j];
+  };
+  auto stash = [&](int j, int64_t v) {
+    if (kLut == 2) __stcs(&reinterpret_cast<uint16_t *>(A.st_c)[(int64_t)j * A.Q + q], (uint16_t)c[j]);
+    else if (kLut) __stcs(&A.st_c[(int64_t)j * A.Q + q], c[j]);
+    else __stcs(&A.st_s[(int64_t)j * A.Q + q], v == WFX_KILL ? (int64_t)0 : v);
+  };
   uint32_t live = 0;
   int64_t ta = 0, tb = -(1ll << 62);
   uint32_t tkill = 0;
-  ChunkSumm sm;
-  if (kSumm) sm.init();
-  if (kLut == 2) {
-    // class mode: 2-byte gather (the 4^k x 2 B table stays L2 resident where the 4 B count table does not)
-    uint32_t c[CHUNK];
-    uint16_t *st16 = reinterpret_cast<uint16_t *>(A.st_c);
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u16_keep(&A.cls[code[j]], keep) : 0u;
+  int64_t sum_mn = 0, sum_mx = 0, sum_bm = 0;
+  uint32_t sum_bits = 0;
+  bool general = !kSumm || scored != 0xffffu;
+  if (kSumm && !general) {
+    // Fast chunk (every position scored, no forced zero: almost all of a genome).  Everything follows
+    // from the prefix sums P_j alone, with one 64-bit add and four compares per position:
+    //   mnT = min_j P_j           -> transform b = P_15 - mnT, zero test of the fast walk
+    //   zero-start trajectory Bz_j = P_j - min(0, mnT_j); Bz_j == 0 iff P_j <= mnT_{j-1} and P_j <= 0
+    //   bMx = max of P since the last zero of Bz (its position bpk), jz = last zero
+    //   mx = max_j P_j with its leftmost position am
+    int64_t P = 0, mnT = 1ll << 62, bMx = 0, mx = -(1ll << 62);
+    uint32_t am = 0, bpk = 0, jz1 = 0;  // jz1 = last zero + 1 = start of the open excursion of Bz
+    bool bad = false;
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) {
-      const int64_t v = (scored & (1u << j)) ? __ldg(&A.lut[c[j]]) : WFX_KILL;
-      __stcs(&st16[(int64_t)j * A.Q + q], (uint16_t)c[j]);
+      const int64_t v = value(j);
+      stash(j, v);
+      bad = bad || ((int32_t)(v >> 32) == INT32_MIN);  // WFX_KILL is the only entry with this high word
+      P += v;
+      const bool newmin = P <= mnT;
+      mnT = newmin ? P : mnT;
+      const bool isz = newmin && P <= 0;
+      const bool up = isz || P > bMx;
+      bMx = up ? P : bMx;
+      bpk = up ? (uint32_t)j : bpk;
+      jz1 = isz ? (uint32_t)(j + 1) : jz1;
+      if (P > mx) { mx = P; am = (uint32_t)j; }
+    }
+    general = bad;
+    if (!bad) {
+      live = 0xffffu;
+      ta = P;
+      tb = P - mnT;
+      const int64_t m0 = mnT < 0 ? mnT : 0;
+      sum_mn = mnT;
+      sum_mx = mx;
+      sum_bm = bMx - m0;
+      const bool open = jz1 != (uint32_t)CHUNK;
+      sum_bits = (am << 19) | ((jz1 & 15u) << 23) | (bpk << 27) | (open ? 0x80000000u : 0u);
+    }
+  }
+  if (general) {
+    ChunkSumm sm;
+    if (kSumm) sm.init();
+    live = 0; ta = 0; tb = -(1ll << 62); tkill = 0;
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) {
+      const int64_t v = (scored & (1u << j)) ? value(j) : WFX_KILL;
+      stash(j, v);
       if (v != WFX_KILL) {
         live |= 1u << j;
         ta += v;
@@ -480,54 +550,7 @@ scan_gather_kernel(const LevelArgs A) {
       }
       if (kSumm) sm.step(j, v != WFX_KILL, v, ta);
     }
-  } else if (kLut) {
-    uint32_t c[CHUNK];
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u32_keep(&A.counts[code[j]], keep) : 0u;
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j) {
-      int64_t v = WFX_KILL;
-      if (scored & (1u << j)) {
-        if (c[j] < A.lut_size) {
-          v = __ldg(&A.lut[c[j]]);
-        } else {  // rare: very abundant k-mer, look it up in the sorted sparse list
-          uint32_t lo = 0, hi = A.sp_n;
-          while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(&A.sp_count[mid]) <= c[j]) lo = mid; else hi = mid;
-          }
-          v = __ldg(&A.sp_val[lo]);
-        }
-      }
-      __stcs(&A.st_c[(int64_t)j * A.Q + q], c[j]);
-      if (v != WFX_KILL) {
-        live |= 1u << j;
-        ta += v;
-        int64_t t = tb + v;
-        tb = t > 0 ? t : 0;
-      } else {
-        tkill = 1; ta = 0; tb = 0;
-      }
-      if (kSumm) sm.step(j, v != WFX_KILL, v, ta);
-    }
-  } else {
-    int64_t sv[CHUNK];
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j) sv[j] = (scored & (1u << j)) ? ldg_s64_keep(&A.wfx[code[j]], keep) : WFX_KILL;
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j) {
-      int64_t v = sv[j];
-      __stcs(&A.st_s[(int64_t)j * A.Q + q], v == WFX_KILL ? (int64_t)0 : v);
-      if (v != WFX_KILL) {
-        live |= 1u << j;
-        ta += v;
-        int64_t t = tb + v;
-        tb = t > 0 ? t : 0;
-      } else {
-        tkill = 1; ta = 0; tb = 0;
-      }
-      if (kSumm) sm.step(j, v != WFX_KILL, v, ta);
-    }
+    if (kSumm) { sum_mn = sm.mn; sum_mx = sm.mx; sum_bm = sm.bM; sum_bits = sm.flag_bits(); }
   }
   if (A.inscan) {
 #pragma unroll
@@ -574,10 +597,10 @@ scan_gather_kernel(const LevelArgs A) {
   A.st_eb[q] = excl.b;
   uint32_t flags = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u) | (vchunk ? 0x40000u : 0u);
   if (kSumm) {
-    flags |= sm.flag_bits();
-    A.st_mn[q] = sm.mn;
-    A.st_mx[q] = sm.mx;
-    A.st_bm[q] = sm.bM;
+    flags |= sum_bits;
+    A.st_mn[q] = sum_mn;
+    A.st_mx[q] = sum_mx;
+    A.st_bm[q] = sum_bm;
   }
   A.st_flags[q] = flags;
   if (A.nseg != 0) A.st_p0[q] = p0;
