@@ -1003,9 +1003,11 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
 // ------------------------------------------------------------------------------------------------
 // stage: scan + spans
 // per-level scratch: stash (indexed by work chunk) and per-tile arrays
-static int ensure_tiles(ks_ctx *ctx, size_t tiles, bool lut_mode, bool need_p0) {
+static int ensure_tiles(ks_ctx *ctx, size_t tiles, bool lut_mode, bool need_p0, bool need_stash) {
   const size_t Q = tiles * TILE_THREADS;
-  if (lut_mode) CK(ctx->st_c.ensure(Q * 16 * 4)); else CK(ctx->st_s.ensure(Q * 16 * 8));
+  if (need_stash) {  // per-position stash: only the position-by-position walk reads it
+    if (lut_mode) CK(ctx->st_c.ensure(Q * 16 * 4)); else CK(ctx->st_s.ensure(Q * 16 * 8));
+  }
   CK(ctx->st_ea.ensure(Q * 16));
   CK(ctx->st_eb.ensure(Q * 16));
   CK(ctx->st_flags.ensure(Q * 4));
@@ -1114,7 +1116,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     if (tiles == 0 && !(sh && level == 0)) break;
     if (tiles == 0) tiles = 1;  // an empty shard still takes part in the carry exchange
     if (tiles > 0xfffffff0ull) return ctx->fail(KS_ERR_ARG, "input too large for one scan launch");
-    rc = ensure_tiles(ctx, tiles, tab.use_lut, nseg != 0);
+    rc = ensure_tiles(ctx, tiles, tab.use_lut, nseg != 0, !fast);
     if (rc) return rc;
     if (tab.tr) CK(ctx->st_aux.ensure(tiles * TILE_THREADS * 4));
     const size_t detail_cap = tiles + tiles * TILE_THREADS / 16 + 64;

@@ -377,6 +377,25 @@ struct ChunkSumm {
   }
 };
 
+// packed codes and break bits of positions [p0 - 16, p0 + 16): X holds 32 x 2 bits (position p0 - 16 most
+// significant), brk32 bit b = position p0 - 16 + b.  p0 need not be chunk aligned (child segments).
+__device__ __forceinline__ void load_window(const LevelArgs &A, int64_t p0, uint64_t &X, uint32_t &brk32) {
+  const int64_t wq = p0 >> 4;
+  const int r = (int)(p0 & 15);
+  uint32_t hi32 = __ldg(&A.pk[wq - 1]), mid32 = __ldg(&A.pk[wq]);
+  uint32_t b0 = __ldg(&A.brk[wq - 1]), b1 = __ldg(&A.brk[wq]);
+  if (r == 0) {
+    X = ((uint64_t)hi32 << 32) | mid32;
+    brk32 = b0 | (b1 << 16);
+  } else {
+    uint32_t lo32 = __ldg(&A.pk[wq + 1]);
+    uint32_t b2 = __ldg(&A.brk[wq + 1]);
+    X = ((uint64_t)__funnelshift_l(mid32, hi32, 2 * r) << 32) | __funnelshift_l(lo32, mid32, 2 * r);
+    uint64_t b48 = (uint64_t)b0 | ((uint64_t)b1 << 16) | ((uint64_t)b2 << 32);
+    brk32 = (uint32_t)(b48 >> r);
+  }
+}
+
 template <int kLut, bool kTr = false, bool kSumm = false>
 __global__ void __launch_bounds__(TILE_THREADS,
                                   kSumm ? (kLut ? KS_GATHER_MINBLOCKS_SUMM : KS_GATHER_MINBLOCKS_TABLE_SUMM)
@@ -408,22 +427,9 @@ scan_gather_kernel(const LevelArgs A) {
     }
   }
   // ---- packed window [p0 - 16, p0 + 16) ----
-  const int64_t wq = p0 >> 4;
-  const int r = (int)(p0 & 15);
-  uint32_t hi32 = __ldg(&A.pk[wq - 1]), mid32 = __ldg(&A.pk[wq]);
-  uint32_t b0 = __ldg(&A.brk[wq - 1]), b1 = __ldg(&A.brk[wq]);
   uint64_t X;
   uint32_t brk32;
-  if (r == 0) {
-    X = ((uint64_t)hi32 << 32) | mid32;
-    brk32 = b0 | (b1 << 16);
-  } else {
-    uint32_t lo32 = __ldg(&A.pk[wq + 1]);
-    uint32_t b2 = __ldg(&A.brk[wq + 1]);
-    X = ((uint64_t)__funnelshift_l(mid32, hi32, 2 * r) << 32) | __funnelshift_l(lo32, mid32, 2 * r);
-    uint64_t b48 = (uint64_t)b0 | ((uint64_t)b1 << 16) | ((uint64_t)b2 << 32);
-    brk32 = (uint32_t)(b48 >> r);
-  }
+  load_window(A, p0, X, brk32);
   // ---- codes, gather (16 independent loads in flight), scores, chunk transform ----
   uint32_t code[CHUNK], scored;
   uint32_t tr_first = 0;
@@ -484,6 +490,7 @@ scan_gather_kernel(const LevelArgs A) {
     return sv[j];
   };
   auto stash = [&](int j, int64_t v) {
+    if (kSumm) return;  // the fast walk works on the chunk summary; scan_detail_kernel gathers again
     if (kLut == 2) __stcs(&reinterpret_cast<uint16_t *>(A.st_c)[(int64_t)j * A.Q + q], (uint16_t)c[j]);
     else if (kLut) __stcs(&A.st_c[(int64_t)j * A.Q + q], c[j]);
     else __stcs(&A.st_s[(int64_t)j * A.Q + q], v == WFX_KILL ? (int64_t)0 : v);
@@ -915,18 +922,35 @@ __global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
   const uint32_t fl = A.st_flags[q];
   const uint32_t live = fl & 0xffffu;
   const int64_t p0 = A.nseg == 0 ? A.dense_start + 16 * q : A.st_p0[q];
+  // the gather kernel kept only the summary of this chunk: decode and gather its positions again
+  uint64_t X;
+  uint32_t brk32;
+  load_window(A, p0, X, brk32);
   int64_t s[CHUNK];
-  if (kLut == 2) {
-    StashScoresCls acc{&A, q};
 #pragma unroll
-    for (int j = 0; j < CHUNK; ++j) s[j] = (live & (1u << j)) ? acc[j] : 0;
-  } else if (kLut) {
-    StashScoresLut acc{&A, q};
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j) s[j] = (live & (1u << j)) ? acc[j] : 0;
-  } else {
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j) s[j] = __ldcs(&A.st_s[(int64_t)j * A.Q + q]);
+  for (int j = 0; j < CHUNK; ++j) {
+    int64_t v = 0;
+    if (live & (1u << j)) {
+      const uint32_t code = (uint32_t)(X >> (32 - 2 * j)) & A.kmask;  // k-mer ending at position j - 1
+      if (kLut == 2) {
+        v = __ldg(&A.lut[__ldg(&A.cls[code])]);
+      } else if (kLut) {
+        const uint32_t c = __ldg(&A.counts[code]);
+        if (c < A.lut_size) {
+          v = __ldg(&A.lut[c]);
+        } else {
+          uint32_t lo = 0, hi = A.sp_n;
+          while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&A.sp_count[mid]) <= c) lo = mid; else hi = mid;
+          }
+          v = __ldg(&A.sp_val[lo]);
+        }
+      } else {
+        v = __ldg(&A.wfx[code]);
+      }
+    }
+    s[j] = v;
   }
   DevEmit emit{&A};
   Ex ex;
