@@ -1119,7 +1119,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     rc = ensure_tiles(ctx, tiles, tab.use_lut, nseg != 0, !fast);
     if (rc) return rc;
     if (tab.tr) CK(ctx->st_aux.ensure(tiles * TILE_THREADS * 4));
-    const size_t detail_cap = tiles + tiles * TILE_THREADS / 16 + 64;
+    size_t detail_cap = tiles + tiles * TILE_THREADS / 16 + 64;
+    if (const char *e = getenv("KS_DETAIL_CAP")) detail_cap = (size_t)atoll(e);  // tests: force the overflow path
     if (fast) {
       CK(ctx->st_mn.ensure(tiles * TILE_THREADS * 8));
       CK(ctx->st_mx.ensure(tiles * TILE_THREADS * 8));

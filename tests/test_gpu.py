@@ -587,3 +587,17 @@ def test_fast_and_general_paths_agree_with_oracle(ctx, oracle, mode, monkeypatch
             got = ctx.kmer_mode_regions(seqs, k, mode, mw, ms, thr=thr)
             assert_spans(got, want, mode == 2, "mode %d mw %d env %s" % (mode, mw, sorted(env)))
     assert len(want["pos"]) >= 0
+
+
+def test_detail_list_overflow_falls_back_to_general_walk(ctx, oracle, monkeypatch):
+    """a list of undecided chunks that does not fit sends the level to the position-by-position walk"""
+    rng = np.random.default_rng(6200)
+    seqs = [planted(rng, 300_000)]
+    want = oracle.mode_regions(seqs, 5, 0, 15, 1.0, thr=0.55)
+    assert len(want["pos"]) > 20
+    monkeypatch.setenv("KS_DETAIL_CAP", "3")
+    got = ctx.kmer_mode_regions(seqs, 5, 0, 15, 1.0, thr=0.55)
+    monkeypatch.delenv("KS_DETAIL_CAP")
+    assert_spans(got, want, False, "overflow fallback")
+    got = ctx.kmer_mode_regions(seqs, 5, 0, 15, 1.0, thr=0.55)
+    assert_spans(got, want, False, "fast path")
