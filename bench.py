@@ -219,14 +219,13 @@ def main():
             r = ctx.dev_pipeline(stages.ss, K, MODE_LOG2, MIN_W, MIN_SCORE, thr=THR,
                                  d_counts=stages.counts.data_ptr(), d_scores=stages.scores.data_ptr())
             return r["n_spans"]
-        n = stages.count(K)
-        total = n
-        if world > 1:
-            n_t = torch.tensor([n], dtype=torch.float64, device=dev)
+        # N > 1: count -> all-reduce of the count table (NCCL, issued on the ctx stream) -> scores -> scan;
+        # no host synchronisation before the score stage reads its histogram back
+        stages.count_async(K)
+        with torch.cuda.stream(stages.stream()):
             dist.all_reduce(stages.counts, op=dist.ReduceOp.SUM)
-            dist.all_reduce(n_t, op=dist.ReduceOp.SUM)
-            total = float(n_t.item())
-        stages.scores_from_counts(K, total, MODE_LOG2, float("nan"))
+            dist.all_reduce(stages.nwords, op=dist.ReduceOp.SUM)
+        stages.scores_from_counts_dev(K, MODE_LOG2, float("nan"))
         nsp, _ = stages.scan(K, THR, MIN_W, MIN_SCORE, fetch=False)
         return nsp
 

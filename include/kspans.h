@@ -141,6 +141,13 @@ int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int
 int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
                 double min_score, int32_t *d_inscan_or_null, ks_spans *host_out_or_null,
                 uint64_t *n_spans);
+/* The same two stages without a host round trip, for compositions that sum the count table and the word
+ * count with a collective on the ctx stream (kmer_spans_b200/dist.py): ks_dev_count_async leaves the word
+ * count in device memory (*d_nwords, uint64), ks_dev_scores_devtotal takes the total from device memory
+ * and reads it back together with the first table the score stage needs (*total_out, may be NULL). */
+int ks_dev_count_async(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, uint64_t *d_nwords);
+int ks_dev_scores_devtotal(ks_ctx *ctx, int k, const int32_t *d_counts, const uint64_t *d_total, int mode,
+                           double param, double *d_scores, double *total_out);
 /* Scan with score = f(count) for the count-derived modes: f is the function the last
  * ks_dev_scores(mode LOG2 | SIGN) on this ctx derived (d_scores may be NULL there).  The kernel
  * gathers the 4-byte count (table L2 resident up to k = 12) and maps it through a dense LUT. */

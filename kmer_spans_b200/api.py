@@ -184,6 +184,17 @@ class Context:
         self._ck(self.lib.ks_dev_count(self.h, ss.h, int(k), d_counts, C.byref(n)))
         return n.value
 
+    def dev_count_async(self, ss, k, d_counts, d_nwords):
+        """count without a host round trip; the word count is left at device pointer d_nwords (uint64)"""
+        self._ck(self.lib.ks_dev_count_async(self.h, ss.h, int(k), C.c_void_p(d_counts), C.c_void_p(d_nwords)))
+
+    def dev_scores_devtotal(self, k, d_counts, d_total, mode, d_scores, param=float("nan")):
+        """scores with the total taken from device memory; returns the total"""
+        t = C.c_double(0)
+        self._ck(self.lib.ks_dev_scores_devtotal(self.h, int(k), C.c_void_p(d_counts), C.c_void_p(d_total), int(mode),
+                                                 float(param), C.c_void_p(d_scores) if d_scores else None, C.byref(t)))
+        return t.value
+
     def dev_scores(self, k, d_counts, total, mode, d_scores, param=float("nan")):
         self._ck(self.lib.ks_dev_scores(self.h, int(k), d_counts, float(total), int(mode), float(param), d_scores))
 

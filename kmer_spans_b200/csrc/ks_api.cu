@@ -674,6 +674,16 @@ static int dev_count_impl(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_cou
   return KS_OK;
 }
 
+// multi-GPU composition without host round trips: the word count stays on the device (it is summed by a
+// collective on the same stream) and is read back together with the first table the score stage needs
+int ks_dev_count_async(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, uint64_t *d_nwords) {
+  int rc = dev_count_impl(ctx, s, k, d_counts, nullptr, false);
+  if (rc) return rc;
+  if (d_nwords)
+    CK(cudaMemcpyAsync(d_nwords, ctx->nwords.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  return KS_OK;
+}
+
 int64_t ks_seqset_chunks(const ks_seqset *s) { return s ? (s->total - 16) / 16 : 0; }
 
 int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, int64_t nchunks,
@@ -737,6 +747,15 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
 int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int mode, double param,
                   double *d_scores) {
   return dev_scores_impl(ctx, k, d_counts, total, false, mode, param, d_scores, nullptr);
+}
+int ks_dev_scores_devtotal(ks_ctx *ctx, int k, const int32_t *d_counts, const uint64_t *d_total, int mode,
+                           double param, double *d_scores, double *total_out) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!d_total) return ctx->fail(KS_ERR_ARG, "ks_dev_scores_devtotal: null argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->nwords.ensure(sizeof(unsigned long long)));
+  CK(cudaMemcpyAsync(ctx->nwords.p, d_total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  return dev_scores_impl(ctx, k, d_counts, 0.0, true, mode, param, d_scores, total_out);
 }
 // total_on_device: the number of words is still in ctx->nwords (the count pass was not synchronised);
 // it is read back together with the histogram

@@ -71,6 +71,32 @@ class GpuStages:
             return 0.0
         return self.ctx.dev_count(self.ss, k, self.counts.data_ptr())
 
+    # ---- the same stages without host round trips (one stream carries kernels and collectives) ----
+    def stream(self):
+        """the ctx stream as a torch stream: collectives issued under it are ordered with the kernels"""
+        if getattr(self, "_ext", None) is None:
+            self._ext = self.torch.cuda.ExternalStream(int(self.ctx.stream), device=self.device)
+        return self._ext
+
+    def count_async(self, k):
+        """counts into self.counts, words into self.nwords (int64 tensor, 1 element), nothing synchronised"""
+        t = self.torch
+        if getattr(self, "nwords", None) is None:
+            self.nwords = t.zeros(1, dtype=t.int64, device=self.device)
+            t.cuda.synchronize(self.device)
+        if self.ss is None:
+            with t.cuda.stream(self.stream()):
+                self.counts.zero_()
+                self.nwords.zero_()
+            return
+        self.ctx.dev_count_async(self.ss, k, self.counts.data_ptr(), self.nwords.data_ptr())
+
+    def scores_from_counts_dev(self, k, mode, param):
+        """scores from self.counts / self.nwords as they are on the ctx stream; returns the total"""
+        self.mode = mode
+        return self.ctx.dev_scores_devtotal(k, self.counts.data_ptr(), self.nwords.data_ptr(), mode,
+                                            self.scores.data_ptr(), param)
+
     def scores_from_counts(self, k, total, mode, param):
         self.torch.cuda.synchronize(self.device)  # the reduced table is ready before our stream reads it
         self.mode = mode
@@ -98,13 +124,22 @@ def run_sharded(stages, dist, seqs_local, local_ids, k, mode, min_w, min_score, 
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     stages.load(seqs_local)
     counts = stages.alloc_tables(k)
-    n_local = stages.count(k)
-    n_t = torch.tensor([n_local], dtype=torch.float64, device=counts.device)
-    if world > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)   # the one real exchange of this path
-        dist.all_reduce(n_t, op=dist.ReduceOp.SUM)
-    total = float(n_t.item())
-    stages.scores_from_counts(k, total, mode, param)
+    if hasattr(stages, "count_async"):
+        # kernels and collectives on one stream: no host synchronisation until the score stage reads back
+        stages.count_async(k)
+        if world > 1:
+            with torch.cuda.stream(stages.stream()):
+                dist.all_reduce(counts, op=dist.ReduceOp.SUM)   # the one real exchange of this path
+                dist.all_reduce(stages.nwords, op=dist.ReduceOp.SUM)
+        total = stages.scores_from_counts_dev(k, mode, param)
+    else:
+        n_local = stages.count(k)
+        n_t = torch.tensor([n_local], dtype=torch.float64, device=counts.device)
+        if world > 1:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+            dist.all_reduce(n_t, op=dist.ReduceOp.SUM)
+        total = float(n_t.item())
+        stages.scores_from_counts(k, total, mode, param)
     pos, score = stages.scan(k, thr, min_w, min_score, fetch=fetch)
     if not fetch:
         return dict(n=total, counts=counts, n_spans=pos)
