@@ -124,6 +124,12 @@ int ks_windowed_kmer_count_distributions(ks_ctx *ctx, const char *const *seqs, c
 
 /* -------- device-resident sequence sets (upload once, scan many times) --------------------- */
 int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, ks_seqset **out);
+/* Upload new sequences into an existing (library-owned) set, re-using its device buffers.  count_k > 0:
+ * the pack+count pass runs behind the copies, d_counts[4^k] is overwritten and the word count is left at
+ * d_nwords (device uint64, may be NULL).  Asynchronous: pinned host buffers must stay valid until the
+ * next synchronising call on this ctx. */
+int ks_seqset_reupload(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const int64_t *lens, int nseq,
+                       int count_k, int32_t *d_counts, uint64_t *d_nwords);
 /* wrap a buffer ALREADY in device memory, laid out as csrc/ks_layout.h describes
  * (d_buf must stay valid; starts = nseq+1 host offsets as returned by ks_layout) */
 int ks_seqset_wrap(ks_ctx *ctx, const void *d_buf, int64_t total_bytes, const int64_t *lens, int nseq,

@@ -56,6 +56,7 @@ SIGNATURES = {
     "ks_kmer_seq": (_i, [_i, C.c_uint64, C.c_char_p]),
     "ks_seqset_upload": (_i, [_vp] + _SEQS + [C.POINTER(_vp)]),
     "ks_seqset_wrap": (_i, [_vp, _vp, _i64, C.POINTER(C.c_int64), _i, C.POINTER(_vp)]),
+    "ks_seqset_reupload": (_i, [_vp, _vp] + _SEQS + [_i, _vp, _vp]),
     "ks_seqset_free": (None, [_vp]),
     "ks_seqset_bases": (_i64, [_vp]),
     "ks_seqset_buffer_bytes": (_i64, [_vp]),

@@ -406,6 +406,20 @@ class SeqSet:
         self.chunks = int(ctx.lib.ks_seqset_chunks(h))
         self.buffer_bytes = int(ctx.lib.ks_seqset_buffer_bytes(h))
         self.positions = int(ctx.lib.ks_seqset_positions(h))
+        self._keep = a
+
+    def reupload(self, seqs, count_k=0, d_counts=0, d_nwords=0):
+        """new sequences into the same device buffers; count_k > 0 counts behind the copies (asynchronous)"""
+        ctx = self.ctx
+        a = _SeqArgs(_as_bytes_list(seqs))
+        ctx._ck(ctx.lib.ks_seqset_reupload(ctx.h, self.h, a.ptrs, a.lens, a.n, int(count_k),
+                                           C.c_void_p(d_counts) if d_counts else None,
+                                           C.c_void_p(d_nwords) if d_nwords else None))
+        self._keep = a  # the copies may still be reading these buffers
+        self.bases = int(ctx.lib.ks_seqset_bases(self.h))
+        self.chunks = int(ctx.lib.ks_seqset_chunks(self.h))
+        self.buffer_bytes = int(ctx.lib.ks_seqset_buffer_bytes(self.h))
+        self.positions = int(ctx.lib.ks_seqset_positions(self.h))
 
     def start(self, seq):
         """buffer position of base 0 of sequence `seq`"""

@@ -576,6 +576,29 @@ int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, 
   return KS_OK;
 }
 
+// Upload new sequences into an existing set (device buffers are re-used, they only grow).  With count_k > 0
+// the pack+count pass runs behind the copies (d_counts is overwritten) and the word count is left at
+// d_nwords (device uint64, may be NULL).  Nothing is synchronised: pinned host buffers must stay valid until
+// the next synchronising call on this ctx.
+int ks_seqset_reupload(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const int64_t *lens, int nseq,
+                       int count_k, int32_t *d_counts, uint64_t *d_nwords) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!s || !seqs || !lens || nseq < 1)
+    return ctx->fail(KS_ERR_ARG, "seq_r must be a character vector of length at least one");
+  if (!s->owned && s->d_buf) return ctx->fail(KS_ERR_ARG, "ks_seqset_reupload: the set wraps a caller-owned buffer");
+  if (count_k) {
+    int rc = check_k(ctx, count_k);
+    if (rc) return rc;
+    if (!d_counts) return ctx->fail(KS_ERR_ARG, "ks_seqset_reupload: null count table");
+  }
+  CK(cudaSetDevice(ctx->device));
+  int rc = seqset_prepare(ctx, lens, nseq, s, true);
+  if (!rc) rc = upload_impl(ctx, s, seqs, lens, nseq, count_k, d_counts);
+  if (!rc && count_k && d_nwords)
+    CK(cudaMemcpyAsync(d_nwords, ctx->nwords.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  return rc;
+}
+
 // the cached set of the host-buffer entry points
 static int host_set_acquire(ks_ctx *ctx, const int64_t *lens, int nseq, ks_seqset **out) {
   if (!ctx->host_set) ctx->host_set = new ks_seqset();

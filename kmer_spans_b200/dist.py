@@ -59,10 +59,26 @@ class GpuStages:
 
     def alloc_tables(self, k):
         t = self.torch
-        self.counts = t.zeros(4 ** k, dtype=t.int32, device=self.device)
-        self.scores = t.empty(4 ** k, dtype=t.float64, device=self.device)
-        t.cuda.synchronize(self.device)
+        if getattr(self, "_tables_k", None) != k:  # kept between calls; every stage overwrites them
+            self.counts = t.zeros(4 ** k, dtype=t.int32, device=self.device)
+            self.scores = t.empty(4 ** k, dtype=t.float64, device=self.device)
+            self.nwords = t.zeros(1, dtype=t.int64, device=self.device)
+            t.cuda.synchronize(self.device)
+            self._tables_k = k
         return self.counts
+
+    def load_and_count(self, seqs, k):
+        """upload into the resident set (buffers re-used) with the pack+count pass running behind the copies;
+        counts -> self.counts, words -> self.nwords; nothing synchronised"""
+        if not len(seqs):
+            self.load(seqs)
+            self.count_async(k)
+            return
+        if self.ss is None:
+            self.ss = self.ctx.upload(seqs)
+            self.count_async(k)
+            return
+        self.ss.reupload(seqs, k, self.counts.data_ptr(), self.nwords.data_ptr())
 
     def count(self, k):
         if self.ss is None:
@@ -122,17 +138,18 @@ def run_sharded(stages, dist, seqs_local, local_ids, k, mode, min_w, min_score, 
     when gather, else this rank's)."""
     import torch
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
-    stages.load(seqs_local)
-    counts = stages.alloc_tables(k)
-    if hasattr(stages, "count_async"):
+    if hasattr(stages, "load_and_count"):
         # kernels and collectives on one stream: no host synchronisation until the score stage reads back
-        stages.count_async(k)
+        counts = stages.alloc_tables(k)
+        stages.load_and_count(seqs_local, k)
         if world > 1:
             with torch.cuda.stream(stages.stream()):
                 dist.all_reduce(counts, op=dist.ReduceOp.SUM)   # the one real exchange of this path
                 dist.all_reduce(stages.nwords, op=dist.ReduceOp.SUM)
         total = stages.scores_from_counts_dev(k, mode, param)
     else:
+        stages.load(seqs_local)
+        counts = stages.alloc_tables(k)
         n_local = stages.count(k)
         n_t = torch.tensor([n_local], dtype=torch.float64, device=counts.device)
         if world > 1:
