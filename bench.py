@@ -270,8 +270,8 @@ def main():
             r = ctx.kmer_mode_regions([seq_host], K, MODE_LOG2, MIN_W, MIN_SCORE, thr=THR, want_tables=False,
                                       counts_out=counts_host.numpy())
             return len(r["pos"]), r["pos"].nbytes + r["score"].nbytes
-        r = ksd.run_sharded(stages, dist, [seq_host], [rank], K, MODE_LOG2, MIN_W, MIN_SCORE, thr=THR, gather=False)
-        counts_host.copy_(r["counts"], non_blocking=False)
+        r = ksd.run_sharded(stages, dist, [seq_host], [rank], K, MODE_LOG2, MIN_W, MIN_SCORE, thr=THR, gather=False,
+                            counts_host=counts_host)
         return len(r["pos"]), r["pos"].nbytes + r["score"].nbytes
 
     e2e_step()

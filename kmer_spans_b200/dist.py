@@ -131,11 +131,12 @@ class GpuStages:
 
 
 def run_sharded(stages, dist, seqs_local, local_ids, k, mode, min_w, min_score, thr=0.0, param=float("nan"),
-                gather=True, fetch=True):
+                gather=True, fetch=True, counts_host=None):
     """One pass of count -> all_reduce -> scores -> scan over this rank's sequences.
     stages: GpuStages (or a test stand-in with the same methods); dist: torch.distributed or None.
     local_ids: original indices of seqs_local.  Returns dict(n, counts, pos, score) (spans on rank 0
-    when gather, else this rank's)."""
+    when gather, else this rank's).  counts_host: optional pinned int32 tensor that receives the reduced count
+    table; the copy runs on a side stream behind the score stage and overlaps the scan."""
     import torch
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     if hasattr(stages, "load_and_count"):
@@ -157,7 +158,21 @@ def run_sharded(stages, dist, seqs_local, local_ids, k, mode, min_w, min_score, 
             dist.all_reduce(n_t, op=dist.ReduceOp.SUM)
         total = float(n_t.item())
         stages.scores_from_counts(k, total, mode, param)
+    side = None
+    if counts_host is not None and hasattr(stages, "stream"):
+        side = getattr(stages, "_side", None)
+        if side is None:
+            side = stages._side = torch.cuda.Stream(device=counts.device)
+        ev = torch.cuda.Event()
+        ev.record(stages.stream())
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            counts_host.copy_(counts, non_blocking=True)
+    elif counts_host is not None:
+        counts_host.copy_(counts)
     pos, score = stages.scan(k, thr, min_w, min_score, fetch=fetch)
+    if side is not None:
+        side.synchronize()
     if not fetch:
         return dict(n=total, counts=counts, n_spans=pos)
     ids = np.asarray(local_ids, np.int32)
