@@ -1965,12 +1965,13 @@ int ks_dev_window_dist(ks_ctx *ctx, const ks_seqset *s, int k, const uint32_t *c
     A.hist = d_dist + (size_t)lo * bins;
     A.pos = d_pos ? d_pos + (size_t)lo * (size_t)s->total : nullptr;
     A.pos_stride = s->total;
-    size_t smem = bins * (size_t)nb * sizeof(int32_t);
+    // a CTA handles WIN_KB selected k-mers (gridDim.y batches): its bins stay small enough for 4+ CTAs per SM
+    size_t smem = bins * (size_t)std::min(nb, WIN_KB) * sizeof(int32_t);
     A.use_smem = smem <= 160u * 1024u;
     if (A.use_smem && smem > 48u * 1024u)
       CK(cudaFuncSetAttribute(win_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    win_hist_kernel<<<grid_for((size_t)nch, WIN_THREADS, A.use_smem ? 148u * 2u : 148u * 8u), WIN_THREADS,
-                      A.use_smem ? smem : 0, st>>>(A);
+    dim3 wgrid(grid_for((size_t)nch, WIN_THREADS, 148u * 4u), (unsigned)((nb + WIN_KB - 1) / WIN_KB));
+    win_hist_kernel<<<wgrid, WIN_THREADS, A.use_smem ? smem : 0, st>>>(A);
     LAUNCHED(1);
     if (!fix.empty()) {
       int nt = (int)fix.size() * nb;

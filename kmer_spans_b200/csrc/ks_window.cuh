@@ -75,11 +75,16 @@ __device__ __forceinline__ uint32_t win_prefix_at(uint32_t pre, uint32_t m32, in
   return pre + __popc(m32 & ((2u << off) - 1u));  // off <= 30
 }
 
+// gridDim.y = batches of WIN_KB selected k-mers: a CTA keeps only its batch's bins in shared memory, so
+// several CTAs fit an SM
+constexpr int WIN_KB = 4;
 __global__ void __launch_bounds__(WIN_THREADS) win_hist_kernel(WinArgs A) {
   extern __shared__ int32_t s_hist[];
   const int bins = A.window + 1;
+  const int i0 = blockIdx.y * WIN_KB;
+  const int i1 = min(A.kmer_n, i0 + WIN_KB);
   if (A.use_smem) {
-    for (int i = threadIdx.x; i < bins * A.kmer_n; i += blockDim.x) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < bins * (i1 - i0); i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
   }
   const int64_t npos = A.nch * 16;
@@ -92,36 +97,38 @@ __global__ void __launch_bounds__(WIN_THREADS) win_hist_kernel(WinArgs A) {
     const int64_t ch = bh >> 4, cl = bl >> 4;
     const int oh = (int)(bh & 15), ol = (int)(bl & 15);
     const bool two_h = ch + 1 < A.nch;  // the second chunk of the upper end exists
-    uint32_t mh = A.brk[ch] | (two_h ? (uint32_t)A.brk[ch + 1] << 16 : 0xffff0000u);
-    uint32_t ml = A.brk[cl] | ((uint32_t)A.brk[cl + 1] << 16);
-    const uint32_t ph = A.brk_pre[ch], pl = A.brk_pre[cl];
+    const uint32_t mh = A.brk[ch] | (two_h ? (uint32_t)A.brk[ch + 1] << 16 : 0xffff0000u);
+    const uint32_t ml = A.brk[cl] | ((uint32_t)A.brk[cl + 1] << 16);
     uint32_t ok = 0;
+    {
+      // breaks inside the window of start j, updated incrementally: one bit enters, one leaves
+      int32_t nb = (int32_t)(win_prefix_at(A.brk_pre[ch], mh, oh) - win_prefix_at(A.brk_pre[cl], ml, ol));
 #pragma unroll
-    for (int j = 0; j < CHUNK; ++j) {
-      bool inside = s0 + j + A.window <= npos;
-      uint32_t nb = win_prefix_at(ph, mh, oh + j) - win_prefix_at(pl, ml, ol + j);
-      ok |= (inside && nb == 0u ? 1u : 0u) << j;
+      for (int j = 0; j < CHUNK; ++j) {
+        if (j) nb += (int32_t)((mh >> (oh + j)) & 1u) - (int32_t)((ml >> (ol + j)) & 1u);
+        ok |= ((s0 + j + A.window <= npos && nb == 0) ? 1u : 0u) << j;
+      }
     }
     if (!ok) continue;
     const int64_t vl = s0 + A.k - 2;  // matches ending at or before s + k - 2 are outside the window
     const int64_t cvl = vl >> 4;
     const int ovl = (int)(vl & 15);
-    for (int i = 0; i < A.kmer_n; ++i) {
+    for (int i = i0; i < i1; ++i) {
       const uint16_t *m = A.match + (int64_t)i * A.mstride;
       const uint32_t *p = A.pre + (int64_t)i * A.pstride;
       const uint32_t m_h = m[ch] | ((uint32_t)m[ch + 1] << 16);   // match rows carry two spare zero columns
       const uint32_t m_l = m[cvl] | ((uint32_t)m[cvl + 1] << 16);
-      const uint32_t p_h = p[ch], p_l = p[cvl];
-      int32_t *h = A.use_smem ? s_hist + i * bins : A.hist + (int64_t)i * bins;
+      int32_t *h = A.use_smem ? s_hist + (i - i0) * bins : A.hist + (int64_t)i * bins;
       int32_t *po = A.pos ? A.pos + (int64_t)i * A.pos_stride + s0 : nullptr;
       // neighbouring windows mostly hold the same value: add runs of equal values at once
-      uint32_t run_v = 0xffffffffu;
+      int32_t v = (int32_t)(win_prefix_at(p[ch], m_h, oh) - win_prefix_at(p[cvl], m_l, ovl));
+      int32_t run_v = -1;
       int run_n = 0;
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j) {
+        if (j) v += (int32_t)((m_h >> (oh + j)) & 1u) - (int32_t)((m_l >> (ovl + j)) & 1u);
         if (!(ok & (1u << j))) continue;
-        uint32_t v = win_prefix_at(p_h, m_h, oh + j) - win_prefix_at(p_l, m_l, ovl + j);
-        if (po) po[j] = (int32_t)v;
+        if (po) po[j] = v;
         if (v != run_v) {
           if (run_n) atomicAdd(&h[run_v], run_n);
           run_v = v;
@@ -134,9 +141,9 @@ __global__ void __launch_bounds__(WIN_THREADS) win_hist_kernel(WinArgs A) {
   }
   if (A.use_smem) {
     __syncthreads();
-    for (int i = threadIdx.x; i < bins * A.kmer_n; i += blockDim.x) {
+    for (int i = threadIdx.x; i < bins * (i1 - i0); i += blockDim.x) {
       int32_t v = s_hist[i];
-      if (v) atomicAdd(&A.hist[i], v);
+      if (v) atomicAdd(&A.hist[(int64_t)i0 * bins + i], v);
     }
   }
 }
