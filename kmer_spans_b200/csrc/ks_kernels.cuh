@@ -1,15 +1,18 @@
 // ks_kernels.cuh -- hand-written sm_100a kernels of the kmer_spans hot path.
 //
-//   count_kernel        K1+K2: ASCII stream -> rolling 2-bit codes -> red.global.add into int32[4^k]
+//   pack_count_kernel   K1+K2: ASCII stream -> 2-bit packed codes + break masks, rolling codes ->
+//                       red.global.add into int32[4^k]
 //                       (replaces sequence_kmer_count, /root/reference/src/kmer_spans.c:135-155)
 //   wmax/wfx kernels    score table double[4^k] -> exact fixed-point table int64[4^k] (W - thr, :268)
-//   scan_level_kernel   K4+K5+K6: per-position gather, max-plus scan with a decoupled look-back,
-//                       excursion (start, leftmost peak, close) extraction, qualification and
-//                       compacted emission (replaces kmer_regions, :243-307, one restart level per
-//                       launch; level 0 is the dense pass over the whole buffer)
+//   scan kernels        K4+K5+K6, one restart level per launch sequence (replaces kmer_regions, :243-307):
+//                       scan_gather_kernel (gather + chunk transform + in-tile scan [+ chunk summary]),
+//                       group_scan / group_top (state entering every tile), scan_walk_fast_kernel +
+//                       scan_detail_kernel (summary-based walk, min_width >= 15) or scan_walk_kernel
+//                       (position-by-position walk; also the transition-score scan, :329-395),
+//                       group_ex / ex_fixup (excursions that cross tiles)
 //   seg_build_kernel    qualifying excursions -> child segments [peak+1, close] (restart at peak, :281-283)
-//   finalize_kernel     sorted records -> reference layout (seq_id, start, end | score, 0) (:95-99)
-//   rank / lut kernels  K3: score-table derivation (rank_kmers_w :189-202, README.md:27-42 modes)
+//   small_sort / finalize  records ordered by start -> reference layout (seq_id, start, end | score, 0) (:95-99)
+//   rank / lut / class kernels  K3: score-table derivation (rank_kmers_w :189-202, README.md:27-42 modes)
 //
 // No tensor-core work exists on this path (integer / byte / gather / atomic work); see DESIGN.md.
 #pragma once
@@ -200,20 +203,21 @@ __global__ void __launch_bounds__(256) wfx_kernel(const double *__restrict__ W, 
 }
 
 // ------------------------------------------------------------------------------------------
-// K4 + K5 + K6: the scan of one restart level, as three spin-free kernels around a compact stash in HBM
-//   scan_gather_kernel  packed window -> codes -> table gather -> chunk transform -> block scan;
-//                       stashes the gathered values (4 B/position in LUT mode, 8 B in table mode), the
-//                       thread's exclusive in-tile transform, and the tile aggregate
-//   tile_scan_kernel    exclusive scan of the tile aggregates (one CTA): state entering every tile
-//   scan_walk_kernel    stash -> excursion walk (start, leftmost peak, close), segmented scan of the
-//                       open-excursion state, qualification, emission through an atomic cursor
+// K4 + K5 + K6: the scan of one restart level, as spin-free kernels around per-chunk records in HBM
+//   scan_gather_kernel  packed window -> codes -> table gather -> chunk transform -> block scan; stores the
+//                       thread's exclusive in-tile transform, the tile aggregate and either the per-chunk
+//                       summary (fast walk) or the gathered values (2 / 4 / 8 B per position)
+//   group_scan/top      exclusive scan of the tile aggregates: state entering every tile
+//   scan_walk_fast_kernel / scan_detail_kernel   summary-based walk (min_width >= 15)
+//   scan_walk_kernel    per-position values -> excursion walk (start, leftmost peak, close), segmented scan
+//                       of the open-excursion state, qualification, emission through an atomic cursor
 //   ex_fixup_kernel     excursions that entered a tile from the left and close in it: walk back over the
 //                       per-tile excursion aggregates to the tile that holds the start
 // An earlier single-kernel version (decoupled look-back, software-pipelined persistent CTAs) ran at
 // 27 % issue / 28 % L1tex utilisation because 120 registers and an 88 KB shared-memory stash allowed
 // 16 warps per SM and every CTA moved through its phases in lock step (profiles/r01_v3_ncu_full.md).
-// Split like this each kernel holds 3-4x the warps, the gather runs near the measured gather rate,
-// and nothing ever waits on another CTA; the price is ~6 B/position of stash traffic.
+// Split like this each kernel holds 3-4x the warps, the gather runs at 84 % L1TEX utilisation
+// (profiles/r01_v7_ncu_full.md), and nothing ever waits on another CTA.
 struct __align__(16) ExPending {
   uint64_t m_lo;
   int64_t m_hi;   // max over the tile's positions before the close (fixed point)
