@@ -161,12 +161,12 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
-def workload_config(args, world):
+def workload_config(args, world, exchange="NCCL"):
     return {"workload": "BASELINE.json configs[1]: synthetic %d Mb sequence per GPU with planted tandem and "
                         "interspersed repeats, 5 N blocks; k=12; log2(f/f_med) score; min_width 100; min_score 20"
                         % (args.n_bases // 1_000_000),
             "k": K, "score_mode": "log2", "bases_per_gpu": args.n_bases, "sharding": "one sequence per GPU, "
-            "count table all-reduced (NCCL)" if world > 1 else "single GPU",
+            "count tables summed across GPUs: %s" % exchange if world > 1 else "single GPU",
             "l2": "inputs (%d MB sequence + 64 MiB count table + 128 MiB score table) exceed the 126 MB L2; "
                   "no explicit flush" % (args.n_bases // 1_000_000)}
 
@@ -211,7 +211,7 @@ def main():
     stages = ksd.GpuStages(local_rank)
     ctx = stages.ctx
     stages.load([seq_host])
-    stages.alloc_tables(K)
+    stages.alloc_tables(K, dist if world > 1 else None)
     counts_host = torch.empty(4 ** K, dtype=torch.int32).pin_memory()
 
     def step():
@@ -222,9 +222,7 @@ def main():
         # N > 1: count -> all-reduce of the count table (NCCL, issued on the ctx stream) -> scores -> scan;
         # no host synchronisation before the score stage reads its histogram back
         stages.count_async(K)
-        with torch.cuda.stream(stages.stream()):
-            dist.all_reduce(stages.counts, op=dist.ReduceOp.SUM)
-            dist.all_reduce(stages.nwords, op=dist.ReduceOp.SUM)
+        stages.reduce_counts(dist)
         stages.scores_from_counts_dev(K, MODE_LOG2, float("nan"))
         nsp, _ = stages.scan(K, THR, MIN_W, MIN_SCORE, fetch=False)
         return nsp
@@ -325,7 +323,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32 counts / int64+int128 exact fixed-point scan / f64 tables",
-        "data": "synthetic", "config": workload_config(args, world),
+        "data": "synthetic", "config": workload_config(args, world, stages.peer_sum_kind()),
         "clocks": sampler.result(),
         "e2e": {"value": e2e_val, "unit": "Gbases/s", "h2d_bytes_per_step": int(args.n_bases),
                 "d2h_bytes_per_step": int(4 * nk + span_bytes), "steps": e2e_steps,

@@ -154,6 +154,12 @@ int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, doubl
 int ks_dev_count_async(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, uint64_t *d_nwords);
 int ks_dev_scores_devtotal(ks_ctx *ctx, int k, const int32_t *d_counts, const uint64_t *d_total, int mode,
                            double param, double *d_scores, double *total_out);
+/* Sum of the count tables of all ranks over NVLink / NVSwitch peer memory in one kernel (csrc/ks_xgpu.cuh):
+ * tables[nranks] = every rank's buffer of n_u64 64-bit words (pairs of int32 counters, then the u64 word
+ * count) as mapped into this process (symmetric memory), mc_table = its NVSwitch multicast address or NULL
+ * (then plain peer loads / stores are used).  Rank `rank` reduces its slice and writes the sums into every
+ * rank's buffer.  The caller places a cross-GPU barrier on the ctx stream before and after the call. */
+int ks_dev_xsum(ks_ctx *ctx, void *const *tables, int nranks, int rank, void *mc_table, uint64_t n_u64);
 /* Scan with score = f(count) for the count-derived modes: f is the function the last
  * ks_dev_scores(mode LOG2 | SIGN) on this ctx derived (d_scores may be NULL there).  The kernel
  * gathers the 4-byte count (table L2 resident up to k = 12) and maps it through a dense LUT. */

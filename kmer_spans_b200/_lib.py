@@ -63,6 +63,7 @@ SIGNATURES = {
     "ks_dev_count": (_i, [_vp, _vp, _i, _vp, _pd]),
     "ks_dev_scores": (_i, [_vp, _i, _vp, _d, _i, _d, _vp]),
     "ks_dev_count_async": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "ks_dev_xsum": (_i, [_vp, _vp, _i, _i, _vp, C.c_uint64]),
     "ks_dev_scores_devtotal": (_i, [_vp, _i, _vp, _vp, _i, _d, _vp, _pd]),
     "ks_dev_scan": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, _vp, C.POINTER(KsSpans), _pu64]),
     "ks_dev_scan_counts": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, C.POINTER(KsSpans), _pu64]),

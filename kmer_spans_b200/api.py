@@ -188,6 +188,13 @@ class Context:
         """count without a host round trip; the word count is left at device pointer d_nwords (uint64)"""
         self._ck(self.lib.ks_dev_count_async(self.h, ss.h, int(k), C.c_void_p(d_counts), C.c_void_p(d_nwords)))
 
+    def dev_xsum(self, peer_ptrs, rank, mc_ptr, n_u64):
+        """sum of the count buffers of all ranks over peer memory (ks_dev_xsum); peer_ptrs: device addresses
+        of every rank's buffer as mapped into this process"""
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        self._ck(self.lib.ks_dev_xsum(self.h, arr, len(peer_ptrs), int(rank), C.c_void_p(int(mc_ptr)) if mc_ptr else None,
+                                      int(n_u64)))
+
     def dev_scores_devtotal(self, k, d_counts, d_total, mode, d_scores, param=float("nan")):
         """scores with the total taken from device memory; returns the total"""
         t = C.c_double(0)

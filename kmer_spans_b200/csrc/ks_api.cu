@@ -22,6 +22,7 @@
 #include "ks_rankseg.h"
 #include "ks_sort.cuh"
 #include "ks_window.cuh"
+#include "ks_xgpu.cuh"
 
 using namespace ks;
 
@@ -704,6 +705,36 @@ int ks_dev_count_async(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts
   if (rc) return rc;
   if (d_nwords)
     CK(cudaMemcpyAsync(d_nwords, ctx->nwords.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  return KS_OK;
+}
+
+// Sum of the count tables of all ranks over peer memory (ks_xgpu.cuh).  tables[nranks] = the address of every
+// rank's buffer of n_u64 64-bit words (pairs of int32 counters, the word count last) as mapped into THIS
+// process; mc_table = multicast address of the same buffer or NULL.  Rank `rank` sums its slice.  The caller
+// puts a cross-GPU barrier on the ctx stream before and after.
+int ks_dev_xsum(ks_ctx *ctx, void *const *tables, int nranks, int rank, void *mc_table, uint64_t n_u64) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!tables || nranks < 1 || nranks > XSUM_MAX_RANKS || rank < 0 || rank >= nranks)
+    return ctx->fail(KS_ERR_ARG, "ks_dev_xsum: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  // slices in units of 2 words (16-byte vectors); the last rank takes the remainder
+  const uint64_t pairs = n_u64 / 2, per = (pairs + nranks - 1) / nranks;
+  uint64_t first = std::min<uint64_t>((uint64_t)rank * per, pairs) * 2;
+  uint64_t last = std::min<uint64_t>((uint64_t)(rank + 1) * per, pairs) * 2;
+  if (rank == nranks - 1) last = n_u64;
+  const uint64_t count = last - first;
+  if (count == 0) return KS_OK;
+  if (mc_table) {
+    xsum_multicast_kernel<<<grid_for((size_t)(count / 4 + 1), 256, 148u * 8u), 256, 0, ctx->stream>>>(
+        reinterpret_cast<uint64_t *>(mc_table), (size_t)first, (size_t)count);
+  } else {
+    XsumPeers P;
+    for (int r = 0; r < nranks; ++r) P.table[r] = reinterpret_cast<uint64_t *>(tables[r]);
+    xsum_peer_kernel<<<grid_for((size_t)(count / 2 + 1), 256, 148u * 4u), 256, 0, ctx->stream>>>(P, nranks, (size_t)first,
+                                                                                         (size_t)count);
+  }
+  LAUNCHED(1);
+  CK(cudaGetLastError());
   return KS_OK;
 }
 

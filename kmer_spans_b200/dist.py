@@ -13,6 +13,8 @@ This mirrors what kmer_low_comp_regions does over all sequences of one call
 The stage functions are injectable so that the sharding / reduction / merge logic can be exercised
 with world_size-2 gloo on CPU (tests/test_dist.py) -- the stand-in stages there are test code.
 """
+import os
+
 import numpy as np
 
 
@@ -57,15 +59,59 @@ class GpuStages:
             self.ss.free()
         self.ss = self.ctx.upload(seqs) if len(seqs) else None
 
-    def alloc_tables(self, k):
+    def alloc_tables(self, k, dist=None):
+        """count / score tables, kept between calls.  With a process group (world > 1) the count table and the
+        word count live in ONE symmetric-memory buffer mapped by every rank, so that reduce_counts() can sum
+        them over NVLink / NVSwitch peer memory (csrc/ks_xgpu.cuh); if that cannot be set up the tables are
+        plain tensors and reduce_counts() uses NCCL."""
         t = self.torch
-        if getattr(self, "_tables_k", None) != k:  # kept between calls; every stage overwrites them
-            self.counts = t.zeros(4 ** k, dtype=t.int32, device=self.device)
-            self.scores = t.empty(4 ** k, dtype=t.float64, device=self.device)
+        if getattr(self, "_tables_k", None) == k:
+            return self.counts
+        n = 4 ** k
+        self._peer = None
+        world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+        if world > 1 and os.environ.get("KS_PEER_SUM", "1") != "0":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                buf = symm.empty(n + 2, dtype=t.int32, device=self.device)
+                hdl = symm.rendezvous(buf, dist.group.WORLD)
+                buf.zero_()
+                mc = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
+                if os.environ.get("KS_PEER_SUM", "1") == "p2p":  # measurement: plain peer loads / stores
+                    mc = 0
+                self._peer = dict(hdl=hdl, buf=buf, ptrs=[int(p) for p in hdl.buffer_ptrs], mc=mc,
+                                  rank=dist.get_rank(), n_u64=n // 2 + 1)
+                self.counts = buf[:n]
+                self.nwords = buf[n:n + 2].view(t.int64)
+            except Exception as e:  # no symmetric memory on this system: NCCL does the sum
+                self._peer = None
+                self._peer_error = repr(e)
+        if self._peer is None:
+            self.counts = t.zeros(n, dtype=t.int32, device=self.device)
             self.nwords = t.zeros(1, dtype=t.int64, device=self.device)
-            t.cuda.synchronize(self.device)
-            self._tables_k = k
+        self.scores = t.empty(n, dtype=t.float64, device=self.device)
+        t.cuda.synchronize(self.device)
+        self._tables_k = k
         return self.counts
+
+    def reduce_counts(self, dist):
+        """sum of self.counts / self.nwords over all ranks, ordered on the ctx stream"""
+        t = self.torch
+        with t.cuda.stream(self.stream()):
+            if self._peer is not None:
+                p = self._peer
+                p["hdl"].barrier(channel=0)   # every rank has finished counting
+                self.ctx.dev_xsum(p["ptrs"], p["rank"], p["mc"], p["n_u64"])
+                p["hdl"].barrier(channel=1)   # every slice has been written everywhere
+            else:
+                dist.all_reduce(self.counts, op=dist.ReduceOp.SUM)
+                dist.all_reduce(self.nwords, op=dist.ReduceOp.SUM)
+
+    def peer_sum_kind(self):
+        if getattr(self, "_peer", None) is None:
+            return "nccl all_reduce"
+        return "one kernel over symmetric memory, " + ("NVSwitch multicast (multimem.ld_reduce / multimem.st)"
+                                                       if self._peer["mc"] else "peer loads / stores")
 
     def load_and_count(self, seqs, k):
         """upload into the resident set (buffers re-used) with the pack+count pass running behind the copies;
@@ -141,12 +187,10 @@ def run_sharded(stages, dist, seqs_local, local_ids, k, mode, min_w, min_score, 
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     if hasattr(stages, "load_and_count"):
         # kernels and collectives on one stream: no host synchronisation until the score stage reads back
-        counts = stages.alloc_tables(k)
+        counts = stages.alloc_tables(k, dist)
         stages.load_and_count(seqs_local, k)
         if world > 1:
-            with torch.cuda.stream(stages.stream()):
-                dist.all_reduce(counts, op=dist.ReduceOp.SUM)   # the one real exchange of this path
-                dist.all_reduce(stages.nwords, op=dist.ReduceOp.SUM)
+            stages.reduce_counts(dist)   # the one real exchange of this path
         total = stages.scores_from_counts_dev(k, mode, param)
     else:
         stages.load(seqs_local)
