@@ -840,6 +840,8 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
   if (!rank_mode) {
     // Count-function modes need no per-k-mer order: frequency-of-counts histogram + prefix sum.
     const uint32_t DENSE = 1u << 16;
+    if (((uintptr_t)d_counts & 15u) != 0)
+      return ctx->fail(KS_ERR_ARG, "ks_dev_scores: the count table must be 16-byte aligned");
     CK(ctx->sc_small.ensure(64));
     CK(ctx->foc_hist.ensure((size_t)DENSE * 4));
     uint32_t big_cap = 1u << 16;

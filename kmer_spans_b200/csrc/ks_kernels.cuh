@@ -1205,35 +1205,42 @@ __global__ void __launch_bounds__(256) rank_eval_kernel(const uint32_t *__restri
 // count-function modes, which need no per-k-mer order): block-private shared histogram for c < 4096
 // with warp-aggregated updates, global atomics for 4096 <= c < dense, atomic append for c >= dense.
 constexpr uint32_t FOC_SMEM_BINS = 4096;
+constexpr int FOC_COPIES = 8;  // one private copy of the low bins per warp: counts cluster around the mean
+                               // coverage, so a single copy would serialise most of a warp on a few bins
+constexpr uint32_t FOC_LOW_BINS = 1024;
 __global__ void __launch_bounds__(256) foc_hist_kernel(const uint32_t *__restrict__ counts, size_t n,
                                                        uint32_t *__restrict__ hist, uint32_t dense,
                                                        uint32_t *__restrict__ big_vals, uint32_t *big_n,
                                                        uint32_t big_cap) {
-  __shared__ uint32_t sh[FOC_SMEM_BINS];
+  __shared__ uint32_t low[FOC_COPIES][FOC_LOW_BINS];   // counts < 1024, one copy per warp
+  __shared__ uint32_t sh[FOC_SMEM_BINS];               // counts < 4096, shared by the block
+  for (int i = threadIdx.x; i < (int)(FOC_COPIES * FOC_LOW_BINS); i += blockDim.x) (&low[0][0])[i] = 0;
   for (int i = threadIdx.x; i < (int)FOC_SMEM_BINS; i += blockDim.x) sh[i] = 0;
   __syncthreads();
-  const uint32_t lt = (1u << (threadIdx.x & 31)) - 1u;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  size_t nround = (n + stride - 1) / stride;  // uniform trip count: __match_any_sync needs the whole warp
-  for (size_t it = 0; it < nround; ++it) {
-    size_t i = it * stride + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool ok = i < n;
-    uint32_t c = ok ? counts[i] : 0xffffffffu;
-    uint32_t peers = __match_any_sync(0xffffffffu, c);
-    if (ok && (peers & lt) == 0u) {  // lowest lane of each group of equal counts
-      uint32_t m = __popc(peers);
-      if (c < FOC_SMEM_BINS) atomicAdd(&sh[c], m);
-      else if (c < dense) atomicAdd(&hist[c], m);
-      else {
-        uint32_t slot = atomicAdd(big_n, m);
-        for (uint32_t q = 0; q < m; ++q)
-          if (slot + q < big_cap) big_vals[slot + q] = c;
-      }
+  uint32_t *mine = low[(threadIdx.x >> 5) & (FOC_COPIES - 1)];
+  auto add = [&](uint32_t c) {
+    if (c < FOC_LOW_BINS) atomicAdd(&mine[c], 1u);
+    else if (c < FOC_SMEM_BINS) atomicAdd(&sh[c], 1u);
+    else if (c < dense) atomicAdd(&hist[c], 1u);
+    else {
+      uint32_t slot = atomicAdd(big_n, 1u);
+      if (slot < big_cap) big_vals[slot] = c;
     }
+  };
+  // 16-byte loads: n is a power of four >= 4, the table is 16-byte aligned
+  const size_t nvec = n / 4;
+  const uint4 *v4 = reinterpret_cast<const uint4 *>(counts);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldcs(v4 + i);
+    add(v.x); add(v.y); add(v.z); add(v.w);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < (int)FOC_SMEM_BINS; i += blockDim.x)
-    if (sh[i] && (uint32_t)i < dense) atomicAdd(&hist[i], sh[i]);
+  for (int i = threadIdx.x; i < (int)FOC_SMEM_BINS; i += blockDim.x) {
+    uint32_t t = sh[i];
+    if ((uint32_t)i < FOC_LOW_BINS)
+      for (int w = 0; w < FOC_COPIES; ++w) t += low[w][i];
+    if (t && (uint32_t)i < dense) atomicAdd(&hist[i], t);
+  }
 }
 
 // W[x] = f(counts[x])  (log2 / +-1 / any pure function of the count): dense table for small counts,
