@@ -19,6 +19,7 @@
 // x -> max(x + a, b) compose exactly.  DESIGN.md discusses the parity consequences.
 #pragma once
 #include <stdint.h>
+#include <limits.h>
 #include <string.h>
 
 #ifdef __CUDACC__
@@ -337,6 +338,119 @@ KS_HD void chunk_finish_entering(fx_t S_in, const Ex &ex_in, fx_t preM, int64_t 
     if (preM > M) { M = preM; pk = prePk; }
     if (qualifies(prm, ex_in.beg, pk, M)) emit(ex_in.beg, pk, (int64_t)(p0 + first_zero), M);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chunk summaries for the fast walk (min_width >= 15: an excursion inside one chunk cannot qualify).
+// With the prefix sums P_j of a chunk and its zero-start trajectory Bz, the trajectory from the entering
+// state is S_j = max(S_in + P_j, Bz_j): it reaches 0 inside the chunk iff a position is forced to 0 or
+// S_in + min P <= 0, and from there on it IS Bz.  So per chunk it is enough to keep
+//   mn, mx + leftmost position am   min / max of P
+//   bm, bbeg, bpk, open             peak, start and leftmost peak position of the excursion Bz has open at
+//                                   the chunk end
+// bits = am << 19 | bbeg << 23 | bpk << 27 | open << 31 (stored next to the live mask in st_flags).
+struct ChunkSummary {
+  int64_t mn, mx, bm;
+  uint32_t bits;
+};
+
+// any chunk: the plain recurrences, position by position (v = WFX_KILL forces the state to 0)
+struct GeneralChunk {
+  int64_t ta, tb, mn, mx, Bz, bM;
+  uint32_t kill, live, am, bbeg, bpk;
+  KS_HD void init() {
+    ta = 0; tb = -(1ll << 62); kill = 0; live = 0;
+    mn = 1ll << 62; mx = -(1ll << 62); Bz = 0; bM = 0; am = 0; bbeg = 0; bpk = 0;
+  }
+  template <bool kSumm>
+  KS_HD void step(int j, int64_t v) {
+    const bool ok = v != WFX_KILL;
+    if (ok) {
+      live |= 1u << j;
+      ta += v;
+      int64_t t = tb + v;
+      tb = t > 0 ? t : 0;
+    } else {
+      kill = 1; ta = 0; tb = 0;
+    }
+    if (kSumm) {
+      mn = ta < mn ? ta : mn;
+      if (ta > mx) { mx = ta; am = (uint32_t)j; }
+      int64_t t = Bz + v;
+      const int64_t Bn = (ok && t > 0) ? t : 0;
+      if (Bz == 0 && Bn > 0) { bbeg = (uint32_t)j; bpk = (uint32_t)j; bM = Bn; }
+      else if (Bn > bM) { bM = Bn; bpk = (uint32_t)j; }
+      Bz = Bn;
+    }
+  }
+  KS_HD ChunkSummary summary() const {
+    ChunkSummary r;
+    r.mn = mn; r.mx = mx; r.bm = bM;
+    r.bits = (am << 19) | (bbeg << 23) | (bpk << 27) | (Bz > 0 ? 0x80000000u : 0u);
+    return r;
+  }
+};
+
+// a chunk whose 16 positions are all scored and none is forced to 0 (almost every chunk of a genome):
+// everything follows from the prefix sums alone, one 64-bit add and four compares per position:
+//   mnT = min_j P_j            -> transform b = P_15 - mnT, zero test of the fast walk
+//   Bz_j = P_j - min(0, mnT_j); Bz_j == 0 iff P_j <= mnT_{j-1} and P_j <= 0
+//   bMx = max of P since the last zero of Bz (position bpk), jz1 = last zero + 1
+//   mx = max_j P_j with its leftmost position am
+// bad: a WFX_KILL entry was met (the only table entry whose high word is INT32_MIN) -> use GeneralChunk
+struct FastChunk {
+  int64_t P, mnT, bMx, mx;
+  uint32_t am, bpk, jz1;
+  bool bad;
+  KS_HD void init() { P = 0; mnT = 1ll << 62; bMx = 0; mx = -(1ll << 62); am = 0; bpk = 0; jz1 = 0; bad = false; }
+  KS_HD void step(int j, int64_t v) {
+    bad = bad || ((int32_t)(v >> 32) == INT32_MIN);
+    P += v;
+    const bool newmin = P <= mnT;
+    mnT = newmin ? P : mnT;
+    const bool isz = newmin && P <= 0;
+    const bool up = isz || P > bMx;
+    bMx = up ? P : bMx;
+    bpk = up ? (uint32_t)j : bpk;
+    jz1 = isz ? (uint32_t)(j + 1) : jz1;
+    if (P > mx) { mx = P; am = (uint32_t)j; }
+  }
+  KS_HD int64_t a() const { return P; }
+  KS_HD int64_t b() const { return P - mnT; }
+  KS_HD ChunkSummary summary() const {
+    ChunkSummary r;
+    const int64_t m0 = mnT < 0 ? mnT : 0;
+    r.mn = mnT; r.mx = mx; r.bm = bMx - m0;
+    const bool open = jz1 != (uint32_t)CHUNK;
+    r.bits = (am << 19) | ((jz1 & 15u) << 23) | (bpk << 27) | (open ? 0x80000000u : 0u);
+    return r;
+  }
+};
+
+// open-excursion element of a chunk from its summary and the state entering it (S_in >= 0); `closing`:
+// an excursion enters the chunk and returns to 0 inside it
+KS_HD void fast_walk_element(fx_t S_in, bool head, uint32_t live, const ChunkSummary &sm, int64_t p0, Ex &ex,
+                             bool &closing) {
+  const bool zero = head || S_in <= 0 || live != 0xffffu || S_in + (fx_t)sm.mn <= 0;
+  if (!zero) {
+    ex.reset = 0; ex.open = 1; ex.beg = -1;
+    ex.M = S_in + (fx_t)sm.mx;
+    ex.pk = p0 + ((sm.bits >> 19) & 15u);
+  } else if (sm.bits & 0x80000000u) {
+    ex.reset = 1; ex.open = 1;
+    ex.beg = p0 + ((sm.bits >> 23) & 15u);
+    ex.pk = p0 + ((sm.bits >> 27) & 15u);
+    ex.M = (fx_t)sm.bm;
+  } else {
+    ex.reset = 1; ex.open = 0; ex.M = -(((fx_t)1) << 126); ex.beg = -1; ex.pk = -1;
+  }
+  closing = !head && S_in > 0 && zero;
+}
+// the entering excursion of a closing chunk cannot qualify: its peak lies at or before p0 + 15 and is at
+// most max(M so far, S_in + max P)
+KS_HD bool fast_walk_cannot_qualify(const Ex &e_in, fx_t S_in, int64_t p0, int64_t mx, const ScanParams &prm) {
+  if ((uint64_t)(p0 + 15 - e_in.beg) < prm.min_width) return true;
+  return fx_max(e_in.M, S_in + (fx_t)mx) < prm.min_units;
 }
 
 // ---------------------------------------------------------------------------------------------

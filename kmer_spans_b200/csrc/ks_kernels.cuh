@@ -358,29 +358,6 @@ struct DevEmit {
 #define KS_WALKFAST_MINBLOCKS 8
 #endif
 
-// per-position update of the chunk summary used by the fast walk: P = running sum (ta), its min / max /
-// leftmost argmax, and the zero-start trajectory Bz with the start, peak and leftmost peak position of
-// its current excursion
-struct ChunkSumm {
-  int64_t mn, mx, Bz, bM;
-  uint32_t am, bbeg, bpk;
-  __device__ __forceinline__ void init() {
-    mn = 1ll << 62; mx = -(1ll << 62); Bz = 0; bM = 0; am = 0; bbeg = 0; bpk = 0;
-  }
-  __device__ __forceinline__ void step(int j, bool live, int64_t v, int64_t ta) {
-    mn = ta < mn ? ta : mn;
-    if (ta > mx) { mx = ta; am = (uint32_t)j; }
-    int64_t t = Bz + v;
-    const int64_t Bn = (live && t > 0) ? t : 0;
-    if (Bz == 0 && Bn > 0) { bbeg = (uint32_t)j; bpk = (uint32_t)j; bM = Bn; }
-    else if (Bn > bM) { bM = Bn; bpk = (uint32_t)j; }
-    Bz = Bn;
-  }
-  __device__ __forceinline__ uint32_t flag_bits() const {
-    return (am << 19) | (bbeg << 23) | (bpk << 27) | (Bz > 0 ? 0x80000000u : 0u);
-  }
-};
-
 // packed codes and break bits of positions [p0 - 16, p0 + 16): X holds 32 x 2 bits (position p0 - 16 most
 // significant), brk32 bit b = position p0 - 16 + b.  p0 need not be chunk aligned (child segments).
 __device__ __forceinline__ void load_window(const LevelArgs &A, int64_t p0, uint64_t &X, uint32_t &brk32) {
@@ -502,66 +479,37 @@ scan_gather_kernel(const LevelArgs A) {
   uint32_t live = 0;
   int64_t ta = 0, tb = -(1ll << 62);
   uint32_t tkill = 0;
-  int64_t sum_mn = 0, sum_mx = 0, sum_bm = 0;
-  uint32_t sum_bits = 0;
   bool general = !kSumm || scored != 0xffffu;
-  if (kSumm && !general) {
-    // Fast chunk (every position scored, no forced zero: almost all of a genome).  Everything follows
-    // from the prefix sums P_j alone, with one 64-bit add and four compares per position:
-    //   mnT = min_j P_j           -> transform b = P_15 - mnT, zero test of the fast walk
-    //   zero-start trajectory Bz_j = P_j - min(0, mnT_j); Bz_j == 0 iff P_j <= mnT_{j-1} and P_j <= 0
-    //   bMx = max of P since the last zero of Bz (its position bpk), jz = last zero
-    //   mx = max_j P_j with its leftmost position am
-    int64_t P = 0, mnT = 1ll << 62, bMx = 0, mx = -(1ll << 62);
-    uint32_t am = 0, bpk = 0, jz1 = 0;  // jz1 = last zero + 1 = start of the open excursion of Bz
-    bool bad = false;
+  ChunkSummary summ;
+  summ.mn = 0; summ.mx = 0; summ.bm = 0; summ.bits = 0;
+  if (kSumm && !general) {  // every position scored: prefix-sum formulation (ks_chunk.cuh)
+    FastChunk fc;
+    fc.init();
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) {
       const int64_t v = value(j);
       stash(j, v);
-      bad = bad || ((int32_t)(v >> 32) == INT32_MIN);  // WFX_KILL is the only entry with this high word
-      P += v;
-      const bool newmin = P <= mnT;
-      mnT = newmin ? P : mnT;
-      const bool isz = newmin && P <= 0;
-      const bool up = isz || P > bMx;
-      bMx = up ? P : bMx;
-      bpk = up ? (uint32_t)j : bpk;
-      jz1 = isz ? (uint32_t)(j + 1) : jz1;
-      if (P > mx) { mx = P; am = (uint32_t)j; }
+      fc.step(j, v);
     }
-    general = bad;
-    if (!bad) {
+    general = fc.bad;
+    if (!fc.bad) {
       live = 0xffffu;
-      ta = P;
-      tb = P - mnT;
-      const int64_t m0 = mnT < 0 ? mnT : 0;
-      sum_mn = mnT;
-      sum_mx = mx;
-      sum_bm = bMx - m0;
-      const bool open = jz1 != (uint32_t)CHUNK;
-      sum_bits = (am << 19) | ((jz1 & 15u) << 23) | (bpk << 27) | (open ? 0x80000000u : 0u);
+      ta = fc.a();
+      tb = fc.b();
+      summ = fc.summary();
     }
   }
   if (general) {
-    ChunkSumm sm;
-    if (kSumm) sm.init();
-    live = 0; ta = 0; tb = -(1ll << 62); tkill = 0;
+    GeneralChunk gc;
+    gc.init();
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) {
       const int64_t v = (scored & (1u << j)) ? value(j) : WFX_KILL;
       stash(j, v);
-      if (v != WFX_KILL) {
-        live |= 1u << j;
-        ta += v;
-        int64_t t = tb + v;
-        tb = t > 0 ? t : 0;
-      } else {
-        tkill = 1; ta = 0; tb = 0;
-      }
-      if (kSumm) sm.step(j, v != WFX_KILL, v, ta);
+      gc.template step<kSumm>(j, v);
     }
-    if (kSumm) { sum_mn = sm.mn; sum_mx = sm.mx; sum_bm = sm.bM; sum_bits = sm.flag_bits(); }
+    live = gc.live; ta = gc.ta; tb = gc.tb; tkill = gc.kill;
+    if (kSumm) summ = gc.summary();
   }
   if (A.inscan) {
 #pragma unroll
@@ -608,10 +556,10 @@ scan_gather_kernel(const LevelArgs A) {
   A.st_eb[q] = excl.b;
   uint32_t flags = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u) | (vchunk ? 0x40000u : 0u);
   if (kSumm) {
-    flags |= sum_bits;
-    A.st_mn[q] = sum_mn;
-    A.st_mx[q] = sum_mx;
-    A.st_bm[q] = sum_bm;
+    flags |= summ.bits;
+    A.st_mn[q] = summ.mn;
+    A.st_mx[q] = summ.mx;
+    A.st_bm[q] = summ.bm;
   }
   A.st_flags[q] = flags;
   if (A.nseg != 0) A.st_p0[q] = p0;
@@ -847,26 +795,17 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_WALKFAST_MINBLOCKS) scan_walk
   Xf excl;
   excl.a = A.st_ea[q]; excl.b = A.st_eb[q]; excl.kill = (fl >> 17) & 1u;
   const fx_t S_in = head ? (fx_t)0 : xf_apply(excl, S_tile);
-  const int64_t mx = A.st_mx[q];
+  ChunkSummary summ;
+  summ.mx = A.st_mx[q];
+  summ.bits = fl;
   Ex ex;
   bool closing = false;
   if (fl & 0x40000u) {  // padding chunk: transparent
     ex = ex_identity();
   } else {
-    const bool zero = head || S_in <= 0 || live != 0xffffu || S_in + (fx_t)A.st_mn[q] <= 0;
-    if (!zero) {
-      ex.reset = 0; ex.open = 1; ex.beg = -1;
-      ex.M = S_in + (fx_t)mx;
-      ex.pk = p0 + ((fl >> 19) & 15u);
-    } else if (fl & 0x80000000u) {
-      ex.reset = 1; ex.open = 1;
-      ex.beg = p0 + ((fl >> 23) & 15u);
-      ex.pk = p0 + ((fl >> 27) & 15u);
-      ex.M = (fx_t)A.st_bm[q];
-    } else {
-      ex.reset = 1; ex.open = 0; ex.M = -(((fx_t)1) << 126); ex.beg = -1; ex.pk = -1;
-    }
-    closing = !head && S_in > 0 && zero;
+    summ.mn = (live == 0xffffu && S_in > 0) ? A.st_mn[q] : 0;  // only read where fast_walk_element looks at it
+    summ.bm = (fl & 0x80000000u) ? A.st_bm[q] : 0;
+    fast_walk_element(S_in, head, live, summ, p0, ex, closing);
   }
   Ex einc = ex;
 #pragma unroll
@@ -897,11 +836,11 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_WALKFAST_MINBLOCKS) scan_walk
   __syncthreads();
   if (!closing) return;
   eexcl = ex_combine(s_wex[warp], eexcl);
-  if (eexcl.reset) {
-    // start known: the peak lies at or before p0 + 15 and is at most max(M so far, S_in + max P)
-    if ((uint64_t)(p0 + 15 - eexcl.beg) < A.prm->min_width) return;
-    const fx_t bound = fx_max(eexcl.M, S_in + (fx_t)mx);
-    if (bound < fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo)) return;
+  if (eexcl.reset) {  // start known
+    ScanParams prm;
+    prm.min_width = A.prm->min_width;
+    prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
+    if (fast_walk_cannot_qualify(eexcl, S_in, p0, summ.mx, prm)) return;
   }
   const unsigned int slot = atomicAdd(A.detail_count, 1u);
   if (slot < A.detail_cap) {

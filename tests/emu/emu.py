@@ -50,6 +50,33 @@ class Emu:
         counts = np.ascontiguousarray(counts, np.int32)
         return self.lib.emu_num_rank_segments(counts.ctypes.data_as(C.c_void_p), C.c_int(k), C.c_double(total))
 
+    def scan_fast(self, seqs, k, W, thr, min_width, min_score):
+        """the summary-based walk (scan_walk_fast_kernel / scan_detail_kernel) folded on the host; every
+        summary-derived chunk element is checked against the position-by-position walk inside"""
+        buf, tot, starts = pack(seqs)
+        W = np.ascontiguousarray(W, np.float64)
+        n = C.c_int64(0)
+        pb, pp = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
+        ps = C.POINTER(C.c_double)()
+        lv = C.c_int(0)
+        nd = C.c_int64(0)
+        rc = self.lib.emu_scan_fast(buf.ctypes.data_as(C.c_void_p), C.c_int64(tot), C.c_int(k),
+                                    W.ctypes.data_as(C.c_void_p), C.c_double(thr),
+                                    C.c_uint64(min_width & (2 ** 64 - 1)), C.c_double(min_score),
+                                    C.byref(n), C.byref(pb), C.byref(pp), C.byref(ps), C.byref(lv), C.byref(nd))
+        if rc:
+            raise ValueError("emu_scan_fast rc=%d" % rc)
+        m = n.value
+        beg = np.ctypeslib.as_array(pb, shape=(m + 1,))[:m].copy()
+        pk = np.ctypeslib.as_array(pp, shape=(m + 1,))[:m].copy()
+        sc = np.ctypeslib.as_array(ps, shape=(m + 1,))[:m].copy()
+        for p in (pb, pp, ps):
+            self.lib.emu_free(p)
+        sid = np.searchsorted(starts, beg, side="right") - 1
+        pos = np.stack([sid, beg - starts[sid], pk - starts[sid]], 1).astype(np.int32) if m else np.zeros((0, 3), np.int32)
+        score = np.stack([sc, np.zeros(m)], 1) if m else np.zeros((0, 2))
+        return dict(pos=pos, score=score, levels=lv.value, detail_chunks=nd.value, chunks=tot // 16)
+
     def scan(self, seqs, k, W, thr, min_width, min_score, inscan=False):
         buf, tot, starts = pack(seqs)
         W = np.ascontiguousarray(W, np.float64)

@@ -126,9 +126,30 @@ struct Emit {
 
 // Returns 0, or 1 when a weight is +inf / >= 2^40 (rejected by the product too).
 // Outputs (malloc'ed, caller frees with emu_free): beg, pk (global positions), score.
+// fast != 0 (and min_width >= 15): the summary-based walk of scan_walk_fast_kernel / scan_detail_kernel --
+// chunk summaries from FastChunk / GeneralChunk, open-excursion elements from fast_walk_element, and the
+// position-by-position walk only for chunks whose entering excursion closes and might qualify.
+static int emu_scan_impl(const uint8_t *buf, int64_t ntot, int k, const double *W, double thr, uint64_t min_width,
+                         double min_score, int32_t *inscan, int64_t *n_out, int64_t **beg_out, int64_t **pk_out,
+                         double **score_out, int *levels_out, int64_t *revisits_out, int fast, int64_t *detail_out);
 int emu_scan(const uint8_t *buf, int64_t ntot, int k, const double *W, double thr, uint64_t min_width,
              double min_score, int32_t *inscan, int64_t *n_out, int64_t **beg_out, int64_t **pk_out,
              double **score_out, int *levels_out, int64_t *revisits_out) {
+  return emu_scan_impl(buf, ntot, k, W, thr, min_width, min_score, inscan, n_out, beg_out, pk_out, score_out,
+                       levels_out, revisits_out, 0, nullptr);
+}
+// detail_out: number of chunks that needed the position-by-position walk
+int emu_scan_fast(const uint8_t *buf, int64_t ntot, int k, const double *W, double thr, uint64_t min_width,
+                  double min_score, int64_t *n_out, int64_t **beg_out, int64_t **pk_out, double **score_out,
+                  int *levels_out, int64_t *detail_out) {
+  return emu_scan_impl(buf, ntot, k, W, thr, min_width, min_score, nullptr, n_out, beg_out, pk_out, score_out,
+                       levels_out, nullptr, 1, detail_out);
+}
+static int emu_scan_impl(const uint8_t *buf, int64_t ntot, int k, const double *W, double thr, uint64_t min_width,
+                         double min_score, int32_t *inscan, int64_t *n_out, int64_t **beg_out, int64_t **pk_out,
+                         double **score_out, int *levels_out, int64_t *revisits_out, int fast, int64_t *detail_out) {
+  if (fast && min_width < 15) fast = 0;
+  int64_t n_detail = 0;
   size_t nk = (size_t)1 << (2 * k);
   uint32_t kmask = (uint32_t)(nk - 1);
   // table: w = fl(W - thr) as the reference computes it (:268), then exact fixed point
@@ -178,13 +199,61 @@ int emu_scan(const uint8_t *buf, int64_t ntot, int k, const double *W, double th
             if (v != WFX_KILL) { s[j] = v; live |= 1u << j; }
           }
         }
-        Xf f = chunk_transform(s, live);
+        Xf f;
         Ex ex;
         fx_t preM;
         int64_t prePk;
         int fz;
-        chunk_walk(s, live, S, p0, prm, emit, ex, preM, prePk, fz);
-        chunk_finish_entering(S, E, preM, prePk, fz, p0, prm, emit);
+        if (fast) {
+          // what the gather kernel leaves behind for this chunk
+          ChunkSummary sm;
+          bool general = scored != 0xffffu;
+          uint32_t live2 = 0;
+          if (!general) {
+            FastChunk fc;
+            fc.init();
+            for (int j = 0; j < 16; ++j) fc.step(j, wfx[code[j]]);
+            general = fc.bad;
+            if (!fc.bad) { f.a = (fx_t)fc.a(); f.b = (fx_t)fc.b(); f.kill = 0; sm = fc.summary(); live2 = 0xffffu; }
+          }
+          if (general) {
+            GeneralChunk gc;
+            gc.init();
+            for (int j = 0; j < 16; ++j) gc.step<true>(j, (scored & (1u << j)) ? wfx[code[j]] : WFX_KILL);
+            f.a = (fx_t)gc.ta; f.b = (fx_t)gc.tb; f.kill = gc.kill; sm = gc.summary(); live2 = gc.live;
+          }
+          if (live2 != live) return 2;  // the two formulations must see the same live positions
+          // what the walk kernel derives from it
+          bool closing = false;
+          fast_walk_element(S, ci == 0, live, sm, p0, ex, closing);
+          {  // every summary-derived element must equal the one the position-by-position walk finds
+            std::vector<Rec> scratch;
+            Emit none{&scratch};
+            Ex ex_ref;
+            fx_t pm;
+            int64_t pp;
+            int z;
+            chunk_walk(s, live, S, p0, prm, none, ex_ref, pm, pp, z);
+            if (ex_ref.reset != ex.reset || ex_ref.open != ex.open || ex_ref.beg != ex.beg || ex_ref.pk != ex.pk ||
+                ex_ref.M != ex.M)
+              return 5;
+            if (closing != (ci != 0 && S > 0 && z >= 0)) return 6;
+          }
+          if (closing && !fast_walk_cannot_qualify(E, S, p0, sm.mx, prm)) {
+            ++n_detail;  // scan_detail_kernel: position-by-position walk of this chunk only
+            Ex ex_detail;
+            chunk_walk(s, live, S, p0, prm, emit, ex_detail, preM, prePk, fz);
+            if (fz < 0) return 3;
+            chunk_finish_entering(S, E, preM, prePk, fz, p0, prm, emit);
+            if (ex_detail.reset != ex.reset || ex_detail.open != ex.open || ex_detail.beg != ex.beg ||
+                ex_detail.pk != ex.pk || ex_detail.M != ex.M)
+              return 4;  // summary-derived element must equal the walked one
+          }
+        } else {
+          f = chunk_transform(s, live);
+          chunk_walk(s, live, S, p0, prm, emit, ex, preM, prePk, fz);
+          chunk_finish_entering(S, E, preM, prePk, fz, p0, prm, emit);
+        }
         S = xf_apply(f, S);
         E = ex_combine(E, ex);
       }
@@ -211,6 +280,7 @@ int emu_scan(const uint8_t *buf, int64_t ntot, int k, const double *W, double th
   }
   if (levels_out) *levels_out = level;
   if (revisits_out) *revisits_out = revisits;
+  if (detail_out) *detail_out = n_detail;
   return 0;
 }
 

@@ -159,3 +159,50 @@ def test_emu_config1_both_modes(emu, oracle):
     o = oracle.kmer_regions([seq], 8, W, 100, 20)
     e = emu.scan([seq], 8, W, 0.0, 100, 20)
     assert_spans(e, o, exact_scores=False)
+
+
+# ---- the summary-based ("fast") walk: chunk summaries, O(1) elements, few chunks walked in detail ----
+@pytest.mark.parametrize("k", [2, 5, 8])
+def test_emu_fast_walk_vs_oracle(emu, oracle, k):
+    """FastChunk / GeneralChunk summaries + fast_walk_element (what scan_gather_kernel<.., summ> and
+    scan_walk_fast_kernel compute) give the oracle's spans; inside, every summary-derived chunk element is
+    compared with the position-by-position walk (emu_scan_fast fails otherwise)."""
+    rng = np.random.default_rng(900 + k)
+    detail = chunks = 0
+    for trial in range(12):
+        seqs = [planted(rng, int(rng.integers(50, 9000))) for _ in range(int(rng.integers(1, 4)))]
+        kind = trial % 4
+        if kind == 0:
+            W = rng.choice([-1.0, 1.0], 4 ** k, p=[0.6, 0.4])
+        elif kind == 1:
+            W = rng.normal(-0.2, 1.0, 4 ** k)
+        elif kind == 2:
+            n, c = oracle.kmer_counts(seqs, k)
+            W = oracle.scores(c, k, n, 2)
+        else:
+            W = rng.normal(-0.1, 1.0, 4 ** k)
+            W[rng.integers(0, 4 ** k, 3)] = np.nan
+            W[rng.integers(0, 4 ** k, 2)] = -np.inf
+        mw, ms = [(15, 0), (16, 3), (40, 8), (100, 2)][trial % 4]
+        o = oracle.kmer_regions(seqs, k, W, mw, ms)
+        e = emu.scan_fast(seqs, k, W, 0.0, mw, ms)
+        assert_spans(e, o, exact_scores=(kind in (0, 2)))
+        g = emu.scan(seqs, k, W, 0.0, mw, ms)
+        assert e["pos"].tolist() == g["pos"].tolist() and e["score"].tobytes() == g["score"].tobytes()
+        detail += e["detail_chunks"]
+        chunks += e["chunks"]
+    assert detail < chunks / 4  # the position-by-position walk is the exception
+
+
+def test_emu_fast_walk_config1(emu, oracle):
+    seq = synth.config1()[0].tobytes()
+    n, c = oracle.kmer_counts(seq, 8)
+    for mode in (1, 2):
+        W = oracle.scores(c, 8, n, mode)
+        o = oracle.kmer_regions([seq], 8, W, 100, 20)
+        e = emu.scan_fast([seq], 8, W, 0.0, 100, 20)
+        assert_spans(e, o, exact_scores=(mode == 2))
+    o = oracle.low_comp([seq], 8, 100, 20, 0.75)
+    e = emu.scan_fast([seq], 8, o["ranks"], 0.75, 100, 20)
+    assert_spans(e, o, exact_scores=False)
+    assert e["detail_chunks"] < e["chunks"] / 20
