@@ -462,7 +462,8 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
   size_t fill = 0;
   int64_t win_start = -1;  // global offset the current window maps to
   unsigned nthreads = std::thread::hardware_concurrency();
-  if (nthreads > 8) nthreads = 8;
+  if (nthreads > 12) nthreads = 12;
+  if (const char *e = getenv("KS_STAGE_THREADS")) nthreads = (unsigned)atoi(e);
   if (nthreads < 1) nthreads = 1;
   auto flush = [&]() -> cudaError_t {
     if (fill == 0) return cudaSuccess;
