@@ -122,6 +122,23 @@ __global__ void __launch_bounds__(WIN_THREADS) win_hist_kernel(WinArgs A) {
       int32_t *po = A.pos ? A.pos + (int64_t)i * A.pos_stride + s0 : nullptr;
       // neighbouring windows mostly hold the same value: add runs of equal values at once
       int32_t v = (int32_t)(win_prefix_at(p[ch], m_h, oh) - win_prefix_at(p[cvl], m_l, ovl));
+      if (ok == 0xffffu && !po) {
+        // all 16 windows exist: the value changes only where the entering and the leaving match bit differ,
+        // so walk the change points (about two per 16 starts) instead of the starts
+        const uint32_t e = (m_h >> (oh + 1)) & 0x7fffu, l = (m_l >> (ovl + 1)) & 0x7fffu;  // bit j-1: start j
+        const uint32_t up = e & ~l;
+        uint32_t chg = e ^ l;
+        int start = 0;
+        while (chg) {
+          const int b = __ffs(chg) - 1;
+          chg &= chg - 1;
+          atomicAdd(&h[v], b + 1 - start);
+          start = b + 1;
+          v += ((up >> b) & 1u) ? 1 : -1;
+        }
+        atomicAdd(&h[v], CHUNK - start);
+        continue;
+      }
       int32_t run_v = -1;
       int run_n = 0;
 #pragma unroll
