@@ -77,6 +77,31 @@ class Emu:
         score = np.stack([sc, np.zeros(m)], 1) if m else np.zeros((0, 2))
         return dict(pos=pos, score=score, levels=lv.value, detail_chunks=nd.value, chunks=tot // 16)
 
+    def tr_scan(self, seqs, k, init, trans, min_len):
+        """transition-score scan (chunk_walk_tr level loop) folded on the host; 1-based ids / coordinates"""
+        buf, tot, starts = pack(seqs)
+        init = np.ascontiguousarray(init, np.float64)
+        trans = np.ascontiguousarray(trans, np.float64)
+        n = C.c_int64(0)
+        pb, pp = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
+        ps = C.POINTER(C.c_double)()
+        lv = C.c_int(0)
+        rc = self.lib.emu_tr_scan(buf.ctypes.data_as(C.c_void_p), C.c_int64(tot), C.c_int(k),
+                                  init.ctypes.data_as(C.c_void_p), trans.ctypes.data_as(C.c_void_p), C.c_int(min_len),
+                                  C.byref(n), C.byref(pb), C.byref(pp), C.byref(ps), C.byref(lv))
+        if rc:
+            raise ValueError("emu_tr_scan rc=%d" % rc)
+        m = n.value
+        beg = np.ctypeslib.as_array(pb, shape=(m + 1,))[:m].copy()
+        pk = np.ctypeslib.as_array(pp, shape=(m + 1,))[:m].copy()
+        sc = np.ctypeslib.as_array(ps, shape=(m + 1,))[:m].copy()
+        for p in (pb, pp, ps):
+            self.lib.emu_free(p)
+        sid = np.searchsorted(starts, beg, side="right") - 1
+        pos = np.stack([sid + 1, beg - starts[sid] + 1, pk - starts[sid] + 1], 1).astype(np.int32) if m else np.zeros((0, 3), np.int32)
+        score = np.stack([sc, np.zeros(m)], 1) if m else np.zeros((0, 2))
+        return dict(pos=pos, score=score, levels=lv.value)
+
     def scan(self, seqs, k, W, thr, min_width, min_score, inscan=False):
         buf, tot, starts = pack(seqs)
         W = np.ascontiguousarray(W, np.float64)

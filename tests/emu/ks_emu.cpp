@@ -284,6 +284,117 @@ static int emu_scan_impl(const uint8_t *buf, int64_t ntot, int k, const double *
   return 0;
 }
 
+// ---- transition-score scan (tr_lr_regions_r): the level loop over chunk_walk_tr, folded on the host ----
+struct TrEmit {
+  std::vector<Rec> *regions;
+  std::vector<std::pair<int64_t, int64_t>> *children;  // (start, len) of the re-scans asked for
+  void out(int64_t beg, int64_t pk, fx_t M) { regions->push_back({beg, pk, 0, M}); }
+  void child(int64_t pk, int64_t c, uint64_t min_width) {
+    if (tr_child_wanted(pk, c, min_width)) children->push_back({pk + 1, c - pk});
+  }
+};
+
+// init / trans: double[4^k] in 2-bit code order.  Outputs as emu_scan, coordinates 0-based global positions
+// (the caller adds the 1-based convention).  Returns 1 for +inf / >= 2^40, 2 for NaN entries.
+int emu_tr_scan(const uint8_t *buf, int64_t ntot, int k, const double *init, const double *trans, int min_len,
+                int64_t *n_out, int64_t **beg_out, int64_t **pk_out, double **score_out, int *levels_out) {
+  size_t nk = (size_t)1 << (2 * k);
+  uint32_t kmask = (uint32_t)(nk - 1);
+  double wmax = 0;
+  for (int t = 0; t < 2; ++t) {
+    const double *W = t ? init : trans;
+    for (size_t i = 0; i < nk; ++i) {
+      double w = W[i];
+      if (w != w) return 2;
+      if (w >= 0x1p40) return 1;
+      if (w > -0x1p40 && fabs(w) > wmax) wmax = fabs(w);
+    }
+  }
+  int qs = qs_for_max(wmax);
+  std::vector<int64_t> wfx(2 * nk);  // [trans | init], as the kernel's table
+  for (size_t i = 0; i < nk; ++i) { wfx[i] = wfx_from_double(trans[i], qs); wfx[nk + i] = wfx_from_double(init[i], qs); }
+  ScanParams prm;
+  prm.min_width = (uint64_t)min_len;
+  prm.min_units = fx_ceil_units(-INFINITY, qs);
+
+  Packed P = pack_buffer(buf, ntot);
+  std::vector<Rec> all;
+  std::vector<std::pair<int64_t, int64_t>> segs, next;
+  segs.push_back({16, ntot - 16});
+  int level = 0;
+  while (!segs.empty()) {
+    next.clear();
+    TrEmit emit{&all, &next};
+    for (auto &sg : segs) {
+      int64_t nchunks = (level == 0) ? sg.second / 16 : segment_chunks(sg.second);
+      fx_t S = 0;
+      Ex E = ex_identity();
+      E.reset = 1; E.open = 0;
+      for (int64_t ci = 0; ci < nchunks; ++ci) {
+        int64_t p0 = sg.first + 16 * ci;
+        int64_t rem = sg.first + sg.second - p0;
+        int n_in = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
+        uint32_t brk32, nul32;
+        uint64_t X;
+        window(P, p0, X, brk32, nul32);
+        // what scan_gather_kernel<0, true> decodes: the k-mer ENDING at every position, the first k-mer of a
+        // run (initial score), and the runs that are not looked at (terminator within two bytes, :340-341)
+        uint32_t code[16];
+        for (int j = 0; j < 16; ++j) code[j] = (uint32_t)(X >> (30 - 2 * j)) & kmask;
+        const uint32_t runk = run_ending(~brk32, k);
+        const uint32_t first32 = runk & (brk32 << k);
+        const uint32_t inside = n_in >= 16 ? 0xffffu : ((1u << n_in) - 1u);
+        uint32_t dead = 0;
+        uint32_t F = (first32 >> 15) & 0x1ffffu;
+        while (F) {
+          int b = __builtin_ctz(F);
+          F &= F - 1;
+          int64_t f = p0 - 1 + b;
+          uint8_t z1 = buf[f + 1], z2 = buf[f + 2];
+          if (b >= 1 && (z1 == 0 || z2 == 0)) dead |= 1u << (b - 1);
+          if (b <= 15 && z2 == 0) dead |= 1u << b;
+        }
+        const uint32_t tr_first = (first32 >> 16) & inside & ~dead;
+        const uint32_t real = ((run_ending(~brk32, k + 1) >> 16) & inside & ~dead) | tr_first;
+        int64_t s[16];
+        uint32_t live = 0;
+        for (int j = 0; j < 16; ++j) {
+          s[j] = 0;
+          if (real & (1u << j)) {
+            int64_t v = wfx[code[j] + ((tr_first >> j) & 1u ? nk : 0)];
+            if (v != WFX_KILL) { s[j] = v; live |= 1u << j; }
+          }
+        }
+        Xf f = chunk_transform(s, live);
+        Ex ex;
+        fx_t preM;
+        int64_t prePk;
+        int fz;
+        chunk_walk_tr(s, live, tr_first, real, S, p0, prm, emit, ex, preM, prePk, fz);
+        chunk_finish_entering_tr(S, E, preM, prePk, fz, p0, real, prm, emit);
+        S = xf_apply(f, S);
+        E = ex_combine(E, ex);
+      }
+    }
+    segs.swap(next);
+    ++level;
+    if (level > 100000) break;
+  }
+  std::sort(all.begin(), all.end(), [](const Rec &a, const Rec &b) { return a.beg < b.beg; });
+  int64_t n = (int64_t)all.size();
+  *n_out = n;
+  *beg_out = (int64_t *)malloc(sizeof(int64_t) * (n + 1));
+  *pk_out = (int64_t *)malloc(sizeof(int64_t) * (n + 1));
+  *score_out = (double *)malloc(sizeof(double) * (n + 1));
+  for (int64_t i = 0; i < n; ++i) {
+    (*beg_out)[i] = all[i].beg;
+    (*pk_out)[i] = all[i].pk;
+    (*score_out)[i] = fx_to_double(all[i].M, qs);
+  }
+  if (levels_out) *levels_out = level;
+  return 0;
+}
+
 void emu_free(void *p) { free(p); }
 
 double emu_fx_roundtrip(double d, int qs) { return fx_to_double((fx_t)wfx_from_double(d, qs), qs); }

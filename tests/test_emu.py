@@ -206,3 +206,36 @@ def test_emu_fast_walk_config1(emu, oracle):
     e = emu.scan_fast([seq], 8, o["ranks"], 0.75, 100, 20)
     assert_spans(e, o, exact_scores=False)
     assert e["detail_chunks"] < e["chunks"] / 20
+
+
+# ---- the transition-score scan (tr_lr_regions_r) through chunk_walk_tr ------------------------------
+def test_emu_tr_scan_vs_oracle(emu, oracle):
+    """the level loop the kernels run for find_kmer_tr_lr_regions (initial score at the first k-mer of a run,
+    bookkeeping one position later, every close re-scanned, terminal excursion reported only) against the
+    oracle restatement, which tests/test_oracle.py pins to the compiled reference"""
+    rng = np.random.default_rng(1000)
+    total = 0
+    for t in range(60):
+        k = int(rng.integers(1, 6))
+        n = 4 ** k
+        seqs = [rand_seq(rng, int(rng.integers(0, 1500)), p_n=float(rng.choice([0, 0.05, 0.3])))
+                for _ in range(int(rng.integers(1, 5)))]
+        if t % 3 == 0:
+            seqs += [rand_seq(rng, k), rand_seq(rng, k + 1), rand_seq(rng, k + 2), rand_seq(rng, k) + b"N",
+                     rand_seq(rng, k) + b"NA", rand_seq(rng, k) + b"N" + rand_seq(rng, k + 3), b"", b"NNN"]
+        exact = t % 2 == 0
+        if exact:
+            init, trans = rng.integers(-2, 3, n).astype(float), rng.integers(-2, 3, n).astype(float)
+        else:
+            init, trans = rng.normal(0, 1, n), rng.normal(-0.1, 1, n)
+        if t % 5 == 0:
+            trans[rng.integers(0, n)] = -np.inf
+            init[rng.integers(0, n)] = -np.inf
+        min_len = int(rng.choice([0, 1, 3, 10, 40]))
+        o = oracle.tr_lr_regions(seqs, k, init, trans, min_len)
+        e = emu.tr_scan(seqs, k, init, trans, min_len)
+        assert_spans(e, o, exact_scores=exact)
+        total += len(o["pos"])
+    assert total > 1500
+    with pytest.raises(ValueError, match="rc=2"):
+        emu.tr_scan([b"ACGTACGT"], 2, np.full(16, np.nan), np.zeros(16), 0)
