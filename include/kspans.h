@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-typedef struct ks_ctx ks_ctx;       /* one device, one stream, cached scratch memory */
+typedef struct ks_ctx ks_ctx;       /* one device, one stream, cached scratch memory; use from one host thread at a time */
 typedef struct ks_seqset ks_seqset; /* sequences resident in HBM   */
 
 enum {
@@ -206,7 +206,7 @@ int ks_fold_carry(int what, const void *all48, int nranks, int rank, void *carry
 int ks_ctx_timer_start(ks_ctx *ctx);
 int ks_ctx_timer_stop(ks_ctx *ctx, float *ms); /* records, synchronises, returns elapsed ms */
 /* per-kernel-class device time, measured live with event pairs around the launches.
- * which: 0 count_kernel, 1 scan_level_kernel level 0, 2 scan_level_kernel deeper levels,
+ * which: 0 pack_count_kernel, 1 scan kernels of level 0, 2 scan kernels of the deeper levels,
  *        3 score-table stage (sort + rank/lut kernels, includes its host control steps), 4 wmax+wfx */
 enum { KS_PROF_COUNT = 0, KS_PROF_SCAN0 = 1, KS_PROF_SCANN = 2, KS_PROF_SCORES = 3, KS_PROF_WFX = 4, KS_PROF_N = 5 };
 void ks_ctx_set_profile(ks_ctx *ctx, int on);

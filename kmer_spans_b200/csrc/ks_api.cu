@@ -1130,7 +1130,7 @@ struct ShardCtl {
   ks_exchange_fn fn = nullptr;
   void *user = nullptr;
 };
-struct ScanTable {  // what scan_level_kernel gathers from
+struct ScanTable {  // what scan_gather_kernel gathers from
   bool use_lut = false;
   const uint32_t *counts = nullptr;
   uint32_t lut_size = 0, sp_n = 0;
