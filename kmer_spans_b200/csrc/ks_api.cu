@@ -1953,7 +1953,7 @@ int ks_dev_window_dist(ks_ctx *ctx, const ks_seqset *s, int k, const uint32_t *c
   CK(ctx->win_match.ensure((size_t)batch * mstride * sizeof(uint16_t)));
   CK(ctx->win_cnt.ensure((size_t)(batch + 1) * nch));
   CK(ctx->win_pre.ensure((size_t)(batch + 1) * pstride * sizeof(uint32_t)));
-  CK(ctx->win_scratch.ensure(exclusive_scan_scratch_elems((size_t)nch) * sizeof(uint32_t)));
+  CK(ctx->win_scratch.ensure((size_t)(batch + 1) * exclusive_scan_scratch_elems((size_t)nch) * sizeof(uint32_t)));
   CK(ctx->win_codes.ensure((size_t)kmer_n * sizeof(uint32_t)));
   CK(cudaMemcpyAsync(ctx->win_codes.p, codes, (size_t)kmer_n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(d_dist, 0, bins * (size_t)kmer_n * sizeof(int32_t), st));
@@ -1978,11 +1978,12 @@ int ks_dev_window_dist(ks_ctx *ctx, const ks_seqset *s, int k, const uint32_t *c
         s->d_pk, s->d_brk, nch, k, kmask, ctx->win_codes.as<uint32_t>() + lo, nb, ctx->win_match.as<uint16_t>(),
         mstride, d_cnt, lo == 0 ? d_brk_cnt : nullptr);
     LAUNCHED(1);
-    int nl = 0;
-    for (int i = 0; i < nb; ++i)
-      nl += exclusive_scan<uint8_t, uint32_t>(d_cnt + (size_t)i * nch, (size_t)nch, d_pre + (size_t)i * pstride,
-                                              ctx->win_scratch.as<uint32_t>(), st);
-    if (lo == 0)
+    // the break row sits right behind the k-mer rows of a full batch: one batched scan covers it too
+    const bool with_brk = lo == 0;
+    const int rows = nb + ((with_brk && nb == batch) ? 1 : 0);
+    int nl = exclusive_scan_rows<uint8_t, uint32_t>(d_cnt, (size_t)nch, rows, (size_t)nch, d_pre, (size_t)pstride,
+                                                    ctx->win_scratch.as<uint32_t>(), st);
+    if (with_brk && nb != batch)
       nl += exclusive_scan<uint8_t, uint32_t>(d_brk_cnt, (size_t)nch, d_brk_pre, ctx->win_scratch.as<uint32_t>(), st);
     LAUNCHED(nl);
     WinArgs A;
@@ -2003,9 +2004,10 @@ int ks_dev_window_dist(ks_ctx *ctx, const ks_seqset *s, int k, const uint32_t *c
     size_t smem = bins * (size_t)std::min(nb, WIN_KB) * sizeof(int32_t);
     A.use_smem = smem <= 160u * 1024u;
     if (A.use_smem && smem > 48u * 1024u)
-      CK(cudaFuncSetAttribute(win_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CK(cudaFuncSetAttribute(win_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 wgrid(grid_for((size_t)nch, WIN_THREADS, 148u * 4u), (unsigned)((nb + WIN_KB - 1) / WIN_KB));
-    win_hist_kernel<<<wgrid, WIN_THREADS, A.use_smem ? smem : 0, st>>>(A);
+    if (A.use_smem) win_hist_kernel<true><<<wgrid, WIN_THREADS, smem, st>>>(A);
+    else win_hist_kernel<false><<<wgrid, WIN_THREADS, 0, st>>>(A);
     LAUNCHED(1);
     if (!fix.empty()) {
       int nt = (int)fix.size() * nb;

@@ -118,6 +118,82 @@ static inline int exclusive_scan(const TIn *d_in, size_t n, TOut *d_out, TOut *d
 }
 static inline size_t exclusive_scan_scratch_elems(size_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 2; }
 
+// the same scan over `rows` independent arrays at once (row r: in + r * in_stride -> out + r * out_stride,
+// n + 1 outputs each): three launches in total instead of three per row.  scratch: rows * scratch_elems(n).
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_rows(const TIn *__restrict__ in, size_t n,
+                                                                      size_t in_stride, TOut *__restrict__ sums,
+                                                                      size_t sums_stride) {
+  __shared__ TOut sm[33];
+  in += (size_t)blockIdx.y * in_stride;
+  sums += (size_t)blockIdx.y * sums_stride;
+  size_t base = (size_t)blockIdx.x * SCAN_TILE;
+  TOut acc = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    size_t idx = base + (size_t)i * SCAN_THREADS + threadIdx.x;
+    if (idx < n) acc += (TOut)in[idx];
+  }
+  TOut total;
+  block_exclusive_scan<TOut>(acc, total, sm);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+template <typename TOut>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_inplace_rows(TOut *sums, size_t m, size_t sums_stride) {
+  __shared__ TOut sm[33];
+  sums += (size_t)blockIdx.x * sums_stride;
+  TOut carry = 0;
+  for (size_t base = 0; base < m; base += SCAN_THREADS) {
+    size_t idx = base + threadIdx.x;
+    TOut v = idx < m ? sums[idx] : (TOut)0;
+    TOut total;
+    TOut ex = block_exclusive_scan<TOut>(v, total, sm);
+    if (idx < m) sums[idx] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) sums[m] = carry;
+}
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_rows(const TIn *in, size_t n, size_t in_stride,
+                                                                 const TOut *__restrict__ sums, size_t sums_stride,
+                                                                 size_t nblocks, TOut *out, size_t out_stride) {
+  __shared__ TOut sm[33];
+  in += (size_t)blockIdx.y * in_stride;
+  sums += (size_t)blockIdx.y * sums_stride;
+  out += (size_t)blockIdx.y * out_stride;
+  size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  TOut v[SCAN_ITEMS];
+  TOut acc = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    size_t idx = base + i;
+    v[i] = idx < n ? (TOut)in[idx] : (TOut)0;
+    acc += v[i];
+  }
+  TOut total;
+  TOut ex = block_exclusive_scan<TOut>(acc, total, sm) + sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    size_t idx = base + i;
+    if (idx < n) out[idx] = ex;
+    ex += v[i];
+  }
+  if (blockIdx.x == nblocks - 1 && threadIdx.x == 0) out[n] = sums[nblocks];
+}
+template <typename TIn, typename TOut>
+static inline int exclusive_scan_rows(const TIn *d_in, size_t n, int rows, size_t in_stride, TOut *d_out,
+                                      size_t out_stride, TOut *d_scratch, cudaStream_t st) {
+  if (n == 0 || rows <= 0) return 0;
+  const size_t nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+  const size_t ss = exclusive_scan_scratch_elems(n);
+  dim3 grid((unsigned)nblocks, (unsigned)rows);
+  scan_block_sums_rows<TIn, TOut><<<grid, SCAN_THREADS, 0, st>>>(d_in, n, in_stride, d_scratch, ss);
+  scan_sums_inplace_rows<TOut><<<(unsigned)rows, SCAN_THREADS, 0, st>>>(d_scratch, nblocks, ss);
+  scan_apply_rows<TIn, TOut><<<grid, SCAN_THREADS, 0, st>>>(d_in, n, in_stride, d_scratch, ss, nblocks, d_out,
+                                                             out_stride);
+  return 3;
+}
+
 // ------------------------------------------------------------------------------------------
 // stable LSD radix sort, one 8-bit digit per pass.
 constexpr int RS_THREADS = 256;

@@ -78,12 +78,13 @@ __device__ __forceinline__ uint32_t win_prefix_at(uint32_t pre, uint32_t m32, in
 // gridDim.y = batches of WIN_KB selected k-mers: a CTA keeps only its batch's bins in shared memory, so
 // several CTAs fit an SM
 constexpr int WIN_KB = 4;
+template <bool kSmem>  // compile-time address space of the bins: shared-memory reductions are native then
 __global__ void __launch_bounds__(WIN_THREADS) win_hist_kernel(WinArgs A) {
   extern __shared__ int32_t s_hist[];
   const int bins = A.window + 1;
   const int i0 = blockIdx.y * WIN_KB;
   const int i1 = min(A.kmer_n, i0 + WIN_KB);
-  if (A.use_smem) {
+  if (kSmem) {
     for (int i = threadIdx.x; i < bins * (i1 - i0); i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
   }
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(WIN_THREADS) win_hist_kernel(WinArgs A) {
       const uint32_t *p = A.pre + (int64_t)i * A.pstride;
       const uint32_t m_h = m[ch] | ((uint32_t)m[ch + 1] << 16);   // match rows carry two spare zero columns
       const uint32_t m_l = m[cvl] | ((uint32_t)m[cvl + 1] << 16);
-      int32_t *h = A.use_smem ? s_hist + (i - i0) * bins : A.hist + (int64_t)i * bins;
+      int32_t *h = kSmem ? s_hist + (i - i0) * bins : A.hist + (int64_t)i * bins;
       int32_t *po = A.pos ? A.pos + (int64_t)i * A.pos_stride + s0 : nullptr;
       // neighbouring windows mostly hold the same value: add runs of equal values at once
       int32_t v = (int32_t)(win_prefix_at(p[ch], m_h, oh) - win_prefix_at(p[cvl], m_l, ovl));
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(WIN_THREADS) win_hist_kernel(WinArgs A) {
       if (run_n) atomicAdd(&h[run_v], run_n);
     }
   }
-  if (A.use_smem) {
+  if (kSmem) {
     __syncthreads();
     for (int i = threadIdx.x; i < bins * (i1 - i0); i += blockDim.x) {
       int32_t v = s_hist[i];
