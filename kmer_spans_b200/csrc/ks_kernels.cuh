@@ -352,7 +352,7 @@ struct DevEmit {
 #define KS_GATHER_MINBLOCKS_SUMM 4
 #endif
 #ifndef KS_GATHER_MINBLOCKS_TABLE_SUMM
-#define KS_GATHER_MINBLOCKS_TABLE_SUMM 3
+#define KS_GATHER_MINBLOCKS_TABLE_SUMM 2
 #endif
 #ifndef KS_WALKFAST_MINBLOCKS
 #define KS_WALKFAST_MINBLOCKS 8
