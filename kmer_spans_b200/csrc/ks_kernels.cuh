@@ -24,7 +24,7 @@
 namespace ks {
 
 #ifndef KS_TILE_THREADS
-#define KS_TILE_THREADS 256
+#define KS_TILE_THREADS 128
 #endif
 #ifndef KS_SCAN_MINBLOCKS
 #define KS_SCAN_MINBLOCKS 2
@@ -337,25 +337,25 @@ struct DevEmit {
 };
 
 #ifndef KS_GATHER_MINBLOCKS
-#define KS_GATHER_MINBLOCKS 4
+#define KS_GATHER_MINBLOCKS 8
 #endif
 #ifndef KS_WALK_MINBLOCKS
-#define KS_WALK_MINBLOCKS 6
+#define KS_WALK_MINBLOCKS 12
 #endif
 #ifndef KS_GATHER_MINBLOCKS_TABLE
-#define KS_GATHER_MINBLOCKS_TABLE 3
+#define KS_GATHER_MINBLOCKS_TABLE 6
 #endif
 #ifndef KS_WALK_MINBLOCKS_TABLE
-#define KS_WALK_MINBLOCKS_TABLE 4
+#define KS_WALK_MINBLOCKS_TABLE 8
 #endif
 #ifndef KS_GATHER_MINBLOCKS_SUMM
-#define KS_GATHER_MINBLOCKS_SUMM 4
+#define KS_GATHER_MINBLOCKS_SUMM 8
 #endif
 #ifndef KS_GATHER_MINBLOCKS_TABLE_SUMM
-#define KS_GATHER_MINBLOCKS_TABLE_SUMM 2
+#define KS_GATHER_MINBLOCKS_TABLE_SUMM 4
 #endif
 #ifndef KS_WALKFAST_MINBLOCKS
-#define KS_WALKFAST_MINBLOCKS 8
+#define KS_WALKFAST_MINBLOCKS 16
 #endif
 
 // packed codes and break bits of positions [p0 - 16, p0 + 16): X holds 32 x 2 bits (position p0 - 16 most
