@@ -12,6 +12,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <exception>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -190,6 +192,18 @@ struct ks_ctx {
                        __LINE__, cudaGetErrorString(e_));                                     \
   } while (0)
 #define LAUNCHED(n) (ctx->launches += (uint64_t)(n))
+// no C++ exception may cross the C ABI (the caller is R / ctypes): host allocations that fail become an error code
+#define KS_TRY try {
+#define KS_CATCH(c)                                                                                     \
+  }                                                                                                     \
+  catch (const std::bad_alloc &) {                                                                      \
+    ks_ctx *c_ = (c);                                                                                   \
+    return c_ ? c_->fail(KS_ERR_NOMEM, "out of host memory") : KS_ERR_NOMEM;                            \
+  }                                                                                                     \
+  catch (const std::exception &e) {                                                                     \
+    ks_ctx *c_ = (c);                                                                                   \
+    return c_ ? c_->fail(KS_ERR_CUDA, "internal error: %s", e.what()) : KS_ERR_CUDA;                    \
+  }
 
 static inline unsigned grid_for(size_t n, int threads, unsigned cap = 148u * 16u) {
   size_t g = (n + threads - 1) / threads;
@@ -228,6 +242,7 @@ void ks_spans_free(ks_spans *s) {
 }
 
 int ks_ctx_create(ks_ctx **out, int device) {
+  KS_TRY
   if (!out) return KS_ERR_ARG;
   *out = nullptr;
   int ndev = 0;
@@ -251,6 +266,7 @@ int ks_ctx_create(ks_ctx **out, int device) {
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return KS_ERR_CUDA; }
   *out = ctx;
   return KS_OK;
+  KS_CATCH(((ks_ctx *)nullptr))
 }
 
 void ks_ctx_destroy(ks_ctx *ctx) {
@@ -288,9 +304,11 @@ void ks_ctx_destroy(ks_ctx *ctx) {
 const char *ks_last_error(const ks_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 void *ks_ctx_stream(ks_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int ks_ctx_sync(ks_ctx *ctx) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   CK(cudaStreamSynchronize(ctx->stream));
   return KS_OK;
+  KS_CATCH(ctx)
 }
 uint64_t ks_ctx_launches(const ks_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void ks_ctx_reset_launches(ks_ctx *ctx) { if (ctx) ctx->launches = 0; }
@@ -300,13 +318,16 @@ void ks_ctx_scan_stats(const ks_ctx *ctx, int *levels, uint64_t *revisited_chunk
 }
 
 int ks_ctx_timer_start(ks_ctx *ctx) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (!ctx->t0) { CK(cudaEventCreate(&ctx->t0)); CK(cudaEventCreate(&ctx->t1)); }
   CK(cudaEventRecord(ctx->t0, ctx->stream));
   return KS_OK;
+  KS_CATCH(ctx)
 }
 int ks_ctx_timer_stop(ks_ctx *ctx, float *ms) {
+  KS_TRY
   if (!ctx || !ctx->t0) return KS_ERR_ARG;
   CK(cudaEventRecord(ctx->t1, ctx->stream));
   CK(cudaEventSynchronize(ctx->t1));
@@ -314,14 +335,17 @@ int ks_ctx_timer_stop(ks_ctx *ctx, float *ms) {
   CK(cudaEventElapsedTime(&v, ctx->t0, ctx->t1));
   if (ms) *ms = v;
   return KS_OK;
+  KS_CATCH(ctx)
 }
 void ks_ctx_set_profile(ks_ctx *ctx, int on) { if (ctx) ctx->profile = on != 0; }
 int ks_ctx_profile_get(ks_ctx *ctx, int which, double *ms_total, uint64_t *launches) {
+  KS_TRY
   if (!ctx || which < 0 || which >= KS_PROF_N) return KS_ERR_ARG;
   ctx->prof_resolve();
   if (ms_total) *ms_total = ctx->prof_ms[which];
   if (launches) *launches = ctx->prof_n[which];
   return KS_OK;
+  KS_CATCH(ctx)
 }
 void ks_ctx_profile_reset(ks_ctx *ctx) {
   if (!ctx) return;
@@ -330,11 +354,13 @@ void ks_ctx_profile_reset(ks_ctx *ctx) {
 }
 
 int ks_kmer_seq(int k, uint64_t code, char *out) {
+  KS_TRY
   static const char nuc[4] = {'A', 'C', 'T', 'G'};
   if (k < 1 || k > 16 || !out) return KS_ERR_ARG;
   out[k] = 0;
   for (int j = k - 1; j >= 0; --j) { out[j] = nuc[code & 3]; code >>= 2; }
   return KS_OK;
+  KS_CATCH(((ks_ctx *)nullptr))
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -562,6 +588,7 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
 }
 
 int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, ks_seqset **out) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   if (!out || !seqs || !lens || nseq < 1)
     return ctx->fail(KS_ERR_ARG, "seq_r must be a character vector of length at least one");
@@ -576,6 +603,7 @@ int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, 
   if (rc) { ks_seqset_free(s); return rc; }
   *out = s;
   return KS_OK;
+  KS_CATCH(ctx)
 }
 
 // Upload new sequences into an existing set (device buffers are re-used, they only grow).  With count_k > 0
@@ -584,6 +612,7 @@ int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, 
 // the next synchronising call on this ctx.
 int ks_seqset_reupload(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const int64_t *lens, int nseq,
                        int count_k, int32_t *d_counts, uint64_t *d_nwords) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   if (!s || !seqs || !lens || nseq < 1)
     return ctx->fail(KS_ERR_ARG, "seq_r must be a character vector of length at least one");
@@ -599,6 +628,7 @@ int ks_seqset_reupload(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
   if (!rc && count_k && d_nwords)
     CK(cudaMemcpyAsync(d_nwords, ctx->nwords.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
   return rc;
+  KS_CATCH(ctx)
 }
 
 // the cached set of the host-buffer entry points
@@ -612,6 +642,7 @@ static int host_set_acquire(ks_ctx *ctx, const int64_t *lens, int nseq, ks_seqse
 
 int ks_seqset_wrap(ks_ctx *ctx, const void *d_buf, int64_t total_bytes, const int64_t *lens, int nseq,
                    ks_seqset **out) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   if (!out || !d_buf || !lens || nseq < 1) return ctx->fail(KS_ERR_ARG, "ks_seqset_wrap: bad arguments");
   CK(cudaSetDevice(ctx->device));
@@ -628,6 +659,7 @@ int ks_seqset_wrap(ks_ctx *ctx, const void *d_buf, int64_t total_bytes, const in
   CK(cudaStreamSynchronize(ctx->stream));
   *out = s;
   return KS_OK;
+  KS_CATCH(ctx)
 }
 
 void ks_seqset_free(ks_seqset *s) {
@@ -663,7 +695,9 @@ static int ensure_packed(ks_ctx *ctx, const ks_seqset *s) {
 // stage: count
 static int dev_count_impl(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, double *n_words, bool sync);
 int ks_dev_count(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, double *n_words) {
+  KS_TRY
   return dev_count_impl(ctx, s, k, d_counts, n_words, true);
+  KS_CATCH(ctx)
 }
 // sync = false: the number of words stays in ctx->nwords for the stage that follows on the stream
 static int dev_count_impl(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, double *n_words, bool sync) {
@@ -702,11 +736,13 @@ static int dev_count_impl(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_cou
 // multi-GPU composition without host round trips: the word count stays on the device (it is summed by a
 // collective on the same stream) and is read back together with the first table the score stage needs
 int ks_dev_count_async(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts, uint64_t *d_nwords) {
+  KS_TRY
   int rc = dev_count_impl(ctx, s, k, d_counts, nullptr, false);
   if (rc) return rc;
   if (d_nwords)
     CK(cudaMemcpyAsync(d_nwords, ctx->nwords.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
   return KS_OK;
+  KS_CATCH(ctx)
 }
 
 // Sum of the count tables of all ranks over peer memory (ks_xgpu.cuh).  tables[nranks] = the address of every
@@ -714,6 +750,7 @@ int ks_dev_count_async(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_counts
 // process; mc_table = multicast address of the same buffer or NULL.  Rank `rank` sums its slice.  The caller
 // puts a cross-GPU barrier on the ctx stream before and after.
 int ks_dev_xsum(ks_ctx *ctx, void *const *tables, int nranks, int rank, void *mc_table, uint64_t n_u64) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   if (!tables || nranks < 1 || nranks > XSUM_MAX_RANKS || rank < 0 || rank >= nranks)
     return ctx->fail(KS_ERR_ARG, "ks_dev_xsum: bad arguments");
@@ -737,12 +774,14 @@ int ks_dev_xsum(ks_ctx *ctx, void *const *tables, int nranks, int rank, void *mc
   LAUNCHED(1);
   CK(cudaGetLastError());
   return KS_OK;
+  KS_CATCH(ctx)
 }
 
 int64_t ks_seqset_chunks(const ks_seqset *s) { return s ? (s->total - 16) / 16 : 0; }
 
 int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, int64_t nchunks,
                        int32_t *d_counts, double *n_words) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   if (!s || !d_counts) return ctx->fail(KS_ERR_ARG, "ks_dev_count_range: null argument");
   int rc = check_k(ctx, k);
@@ -787,6 +826,7 @@ int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, i
   CK(cudaStreamSynchronize(st));
   if (n_words) *n_words = (double)nw;
   return KS_OK;
+  KS_CATCH(ctx)
 }
 
 static int ensure_hpin(ks_ctx *ctx) {
@@ -801,16 +841,20 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
                            int mode, double param, double *d_scores, double *total_out);
 int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int mode, double param,
                   double *d_scores) {
+  KS_TRY
   return dev_scores_impl(ctx, k, d_counts, total, false, mode, param, d_scores, nullptr);
+  KS_CATCH(ctx)
 }
 int ks_dev_scores_devtotal(ks_ctx *ctx, int k, const int32_t *d_counts, const uint64_t *d_total, int mode,
                            double param, double *d_scores, double *total_out) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   if (!d_total) return ctx->fail(KS_ERR_ARG, "ks_dev_scores_devtotal: null argument");
   CK(cudaSetDevice(ctx->device));
   CK(ctx->nwords.ensure(sizeof(unsigned long long)));
   CK(cudaMemcpyAsync(ctx->nwords.p, d_total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
   return dev_scores_impl(ctx, k, d_counts, 0.0, true, mode, param, d_scores, total_out);
+  KS_CATCH(ctx)
 }
 // total_on_device: the number of words is still in ctx->nwords (the count pass was not synchronised);
 // it is read back together with the histogram
@@ -1491,22 +1535,27 @@ static int scan_table_impl(ks_ctx *ctx, const ks_seqset *s, int k, const double 
 
 int ks_dev_scan(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
                 double min_score, int32_t *d_inscan, ks_spans *host_out, uint64_t *n_spans) {
+  KS_TRY
   return scan_table_impl(ctx, s, k, d_W, thr, min_width, min_score, d_inscan, host_out, n_spans, nullptr);
+  KS_CATCH(ctx)
 }
 
 int ks_dev_scan_shard(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
                       double min_score, int64_t chunk0, int64_t nchunks, ks_exchange_fn fn, void *user,
                       ks_spans *host_out, uint64_t *n_spans) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   if (!fn) return ctx->fail(KS_ERR_ARG, "ks_dev_scan_shard: null exchange function");
   ShardCtl sh;
   sh.chunk0 = chunk0; sh.nchunks = nchunks; sh.fn = fn; sh.user = user;
   return scan_table_impl(ctx, s, k, d_W, thr, min_width, min_score, nullptr, host_out, n_spans, &sh);
+  KS_CATCH(ctx)
 }
 
 // Transition-score scan (tr_lr_regions_r core, :329-395): d_init / d_trans are double[4^k] in 2-bit code order.
 int ks_dev_tr_lr_regions(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_init, const double *d_trans,
                          int min_length, ks_spans *host_out, uint64_t *n_spans) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   if (!s || !d_init || !d_trans) return ctx->fail(KS_ERR_ARG, "ks_dev_tr_lr_regions: null argument");
   if (k < 1 || k > 15) return ctx->fail(KS_ERR_ARG, "k should be a positive value less than MAX_K");
@@ -1535,6 +1584,7 @@ int ks_dev_tr_lr_regions(ks_ctx *ctx, const ks_seqset *s, int k, const double *d
   ScanTable tab;
   tab.tr = true;
   return scan_core(ctx, s, k, tab, (uint64_t)min_length, nullptr, host_out, n_spans, nullptr);
+  KS_CATCH(ctx)
 }
 
 // Scan with score = f(count): the count -> score function is the one the last
@@ -1625,21 +1675,26 @@ static int scan_counts_impl(ks_ctx *ctx, const ks_seqset *s, int k, const int32_
 
 int ks_dev_scan_counts(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
                        int min_width, double min_score, ks_spans *host_out, uint64_t *n_spans) {
+  KS_TRY
   return scan_counts_impl(ctx, s, k, d_counts, thr, min_width, min_score, host_out, n_spans, nullptr);
+  KS_CATCH(ctx)
 }
 
 int ks_dev_scan_counts_shard(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
                              int min_width, double min_score, int64_t chunk0, int64_t nchunks,
                              ks_exchange_fn fn, void *user, ks_spans *host_out, uint64_t *n_spans) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   if (!fn) return ctx->fail(KS_ERR_ARG, "ks_dev_scan_counts_shard: null exchange function");
   ShardCtl sh;
   sh.chunk0 = chunk0; sh.nchunks = nchunks; sh.fn = fn; sh.user = user;
   return scan_counts_impl(ctx, s, k, d_counts, thr, min_width, min_score, host_out, n_spans, &sh);
+  KS_CATCH(ctx)
 }
 
 // carry entering shard `rank`: fold of the aggregates of shards 0 .. rank-1 (host, exact integers)
 int ks_fold_carry(int what, const void *all48, int nranks, int rank, void *carry_in48) {
+  KS_TRY
   if (!all48 || !carry_in48 || rank < 0 || rank > nranks) return KS_ERR_ARG;
   memset(carry_in48, 0, 48);
   if (what == 0) {
@@ -1668,11 +1723,13 @@ int ks_fold_carry(int what, const void *all48, int nranks, int rank, void *carry
     return KS_OK;
   }
   return KS_ERR_ARG;
+  KS_CATCH(((ks_ctx *)nullptr))
 }
 
 int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double param, double thr, int min_width,
                     double min_score, int32_t *d_counts, double *d_scores, double *n_words,
                     ks_spans *host_out, uint64_t *n_spans) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   double nw = 0;
   // the word count is read back together with the first table the score stage needs on the host
@@ -1684,6 +1741,7 @@ int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double par
   if (mode == KS_MODE_LOG2 || mode == KS_MODE_SIGN)
     return ks_dev_scan_counts(ctx, s, k, d_counts, thr, min_width, min_score, host_out, n_spans);
   return ks_dev_scan(ctx, s, k, d_scores, thr, min_width, min_score, nullptr, host_out, n_spans);
+  KS_CATCH(ctx)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1730,6 +1788,7 @@ static void start_staged_copies(ks_ctx *ctx) {
   if (ctx->out_jobs.empty()) return;
   ctx->out_rc = 0;
   ctx->out_thread = std::thread([ctx]() {
+   try {
     cudaSetDevice(ctx->device);
     const size_t HALF = ctx->pinned_cap / 2;
     cudaEvent_t ev[2];
@@ -1775,6 +1834,9 @@ static void start_staged_copies(ks_ctx *ctx) {
     cudaEventDestroy(ev[0]);
     cudaEventDestroy(ev[1]);
     if (e != cudaSuccess) ctx->out_rc = (int)e;
+   } catch (...) {  // nothing may escape a thread
+    ctx->out_rc = (int)cudaErrorMemoryAllocation;
+   }
   });
 }
 static int finish_copies(ks_ctx *ctx) {
@@ -1791,6 +1853,7 @@ static int finish_copies(ks_ctx *ctx) {
 
 int ks_kmer_counts(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,
                    int32_t *counts_out, double *n_words) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   int rc = check_seqs(ctx, seqs, lens, nseq);
   if (rc) return rc;
@@ -1806,10 +1869,12 @@ int ks_kmer_counts(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, in
   start_staged_copies(ctx);
   int rc2 = finish_copies(ctx);
   return rc ? rc : rc2;
+  KS_CATCH(ctx)
 }
 
 int ks_kmer_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k, const double *W,
                     int min_width, double min_score, double *nuc, int32_t *inscan_counts_out, ks_spans *out) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   int rc = check_seqs(ctx, seqs, lens, nseq);
   if (rc) return rc;
@@ -1843,11 +1908,13 @@ int ks_kmer_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, i
     return rc ? rc : rc2;
   }
   return KS_OK;
+  KS_CATCH(ctx)
 }
 
 int ks_kmer_mode_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k, int mode,
                          double param, double thr, int min_width, double min_score, double *n_words,
                          int32_t *counts_out, double *scores_out, ks_spans *out) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   int rc = check_seqs(ctx, seqs, lens, nseq);
   if (rc) return rc;
@@ -1879,11 +1946,13 @@ int ks_kmer_mode_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *le
   }
   int rc2 = finish_copies(ctx);
   return rc ? rc : rc2;
+  KS_CATCH(ctx)
 }
 
 int ks_kmer_low_comp_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,
                              int min_width, double min_score, double thr, double n_out[2], int32_t *counts_out,
                              double *ranks_out, ks_spans *out) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   if (!(thr > 0 && thr < 1)) return ctx->fail(KS_ERR_ARG, "the threshold must be between 0 and 1");
   double nw = 0;
@@ -1891,11 +1960,13 @@ int ks_kmer_low_comp_regions(ks_ctx *ctx, const char *const *seqs, const int64_t
                                 counts_out, ranks_out, out);
   if (n_out) { n_out[0] = nw; n_out[1] = 0; }  // :613
   return rc;
+  KS_CATCH(ctx)
 }
 
 // transition-score scan from host buffers
 int ks_tr_lr_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k,
                      const double *init_scores, const double *trans_scores, int min_length, ks_spans *out) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   int rc = check_seqs(ctx, seqs, lens, nseq);
   if (rc) return rc;
@@ -1915,6 +1986,7 @@ int ks_tr_lr_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, 
   rc = upload_impl(ctx, ss, seqs, lens, nseq, 0, nullptr);
   if (rc) return rc;
   return ks_dev_tr_lr_regions(ctx, ss, k, d_init, d_trans, min_length, out, nullptr);
+  KS_CATCH(ctx)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1936,6 +2008,7 @@ uint32_t ks_kmer_code(const char *s, int k) {
 
 int ks_dev_window_dist(ks_ctx *ctx, const ks_seqset *s, int k, const uint32_t *codes, int kmer_n, int window,
                        int32_t *d_dist, int32_t *d_pos) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   if (!s || !codes || !d_dist) return ctx->fail(KS_ERR_ARG, "ks_dev_window_dist: null argument");
   if (k < 1 || k > 15) return ctx->fail(KS_ERR_ARG, "kmer sizes larger than or equal to %d not currently supported", 16);
@@ -2017,11 +2090,13 @@ int ks_dev_window_dist(ks_ctx *ctx, const ks_seqset *s, int k, const uint32_t *c
     CK(cudaGetLastError());
   }
   return KS_OK;
+  KS_CATCH(ctx)
 }
 
 int ks_windowed_kmer_count_distributions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq,
                                          int k, const uint32_t *codes, int kmer_n, int window,
                                          int32_t *dist_out, int32_t *included_out, int32_t *const *pos_out) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   int rc = check_seqs(ctx, seqs, lens, nseq);
   if (rc) return rc;
@@ -2074,10 +2149,12 @@ int ks_windowed_kmer_count_distributions(ks_ctx *ctx, const char *const *seqs, c
   CK(cudaMemcpyAsync(dist_out, d_hist, bins * (size_t)kmer_n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return KS_OK;
+  KS_CATCH(ctx)
 }
 
 int ks_kmer_scores(ks_ctx *ctx, int k, const int32_t *counts, double total, int mode, double param,
                    double *scores_out) {
+  KS_TRY
   if (!ctx) return KS_ERR_ARG;
   int rc = check_k(ctx, k);
   if (rc) return rc;
@@ -2092,6 +2169,7 @@ int ks_kmer_scores(ks_ctx *ctx, int k, const int32_t *counts, double total, int 
   CK(cudaMemcpyAsync(scores_out, ctx->tmp_scores.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return KS_OK;
+  KS_CATCH(ctx)
 }
 
 }  // extern "C"
