@@ -12,6 +12,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <exception>
 #include <new>
 #include <string>
@@ -53,6 +56,64 @@ struct DBuf {  // grow-only device buffer
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Host worker threads that live as long as the context: the staging memcpy runs once per 16 MiB window, and
+// creating threads for every window costs more than the copy.  Used by one caller thread at a time.
+struct WorkPool {
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv_start, cv_done;
+  std::function<void(unsigned)> job;
+  unsigned long gen = 0;
+  unsigned pending = 0;
+  bool stop = false;
+  unsigned size() const { return (unsigned)th.size() + 1; }  // workers + the calling thread
+  void ensure(unsigned nthreads) {
+    while (th.size() + 1 < nthreads) {
+      const unsigned id = (unsigned)th.size() + 1;
+      th.emplace_back([this, id]() {
+        unsigned long seen = 0;
+        for (;;) {
+          std::function<void(unsigned)> f;
+          {
+            std::unique_lock<std::mutex> lk(m);
+            cv_start.wait(lk, [&] { return stop || gen != seen; });
+            if (stop) return;
+            seen = gen;
+            f = job;
+          }
+          f(id);
+          {
+            std::lock_guard<std::mutex> lk(m);
+            if (--pending == 0) cv_done.notify_one();
+          }
+        }
+      });
+    }
+  }
+  // f(t) for t = 0 .. size()-1, t = 0 on the calling thread; returns when all are done
+  void run(const std::function<void(unsigned)> &f) {
+    if (th.empty()) { f(0); return; }
+    {
+      std::lock_guard<std::mutex> lk(m);
+      job = f;
+      pending = (unsigned)th.size();
+      ++gen;
+    }
+    cv_start.notify_all();
+    f(0);
+    std::unique_lock<std::mutex> lk(m);
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+  ~WorkPool() {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      stop = true;
+    }
+    cv_start.notify_all();
+    for (auto &t : th) t.join();
+  }
 };
 
 }  // namespace
@@ -110,6 +171,7 @@ struct ks_ctx {
   DBuf st_mn, st_mx, st_bm, detail, detail_count;
   // table copies into pageable host memory (what R hands over): a helper thread stages them through the
   // pinned windows and spreads the final memcpy over several threads while the scan runs
+  WorkPool pool;  // host threads of the staging copies
   struct OutJob { void *dst; const void *src; size_t bytes; };
   std::vector<OutJob> out_jobs;
   std::thread out_thread;
@@ -499,6 +561,7 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
     if (ee != cudaSuccess) return ee;
     // fill the window with several host threads (R hands over pageable, separately allocated strings)
     auto work = [&](unsigned t) {
+      if (t >= nthreads) return;  // the pool may hold more threads than this call wants
       for (size_t i = t; i < items.size(); i += nthreads) {
         const Item &it = items[i];
         memcpy(win + it.off, it.src, it.len);
@@ -506,10 +569,8 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
       }
     };
     if (nthreads > 1 && fill > (1u << 20)) {
-      std::vector<std::thread> th;
-      for (unsigned t = 1; t < nthreads; ++t) th.emplace_back(work, t);
-      work(0);
-      for (auto &x : th) x.join();
+      ctx->pool.ensure(nthreads);
+      ctx->pool.run(work);
     } else {
       for (unsigned t = 0; t < nthreads; ++t) work(t);
     }
@@ -1796,17 +1857,16 @@ static void start_staged_copies(ks_ctx *ctx) {
     cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
     unsigned nthreads = std::thread::hardware_concurrency();
     nthreads = nthreads > 6 ? 6 : (nthreads < 1 ? 1 : nthreads);
+    ctx->pool.ensure(nthreads);  // the main thread is in the scan by now and does not use the pool
     auto spread = [&](char *dst, const char *src, size_t len) {
-      std::vector<std::thread> th;
-      const size_t per = (len + nthreads - 1) / nthreads;
-      for (unsigned t = 1; t < nthreads; ++t) {
-        size_t a = (size_t)t * per;
-        if (a >= len) break;
-        size_t b = a + per < len ? a + per : len;
-        th.emplace_back([=]() { memcpy(dst + a, src + a, b - a); });
-      }
-      memcpy(dst, src, per < len ? per : len);
-      for (auto &x : th) x.join();
+      const unsigned n = ctx->pool.size();
+      const size_t per = (len + n - 1) / n;
+      ctx->pool.run([=](unsigned t) {
+        const size_t a = (size_t)t * per;
+        if (a >= len) return;
+        const size_t b = a + per < len ? a + per : len;
+        memcpy(dst + a, src + a, b - a);
+      });
     };
     cudaError_t e = cudaSuccess;
     for (const auto &job : ctx->out_jobs) {
