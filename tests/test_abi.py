@@ -67,3 +67,20 @@ def test_kmer_count_file_format(tmp_path):
     bad = tmp_path / "bad.bin"
     np.array([1, 2, 3], "<i4").tofile(str(bad))
     assert api.read_kmers(str(bad)) is False
+
+
+def test_kmer_code_host_helper_matches_oracle(oracle):
+    """ks_kmer_code (host only, no device): what init_kmer leaves in its offset for a k-mer string
+    (src/kmer_spans.c:119-132 as used at :691,747), including strings with N and short strings"""
+    import numpy as np
+    from kmer_spans_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(77)
+    for _ in range(2000):
+        k = int(rng.integers(1, 16))
+        n = int(rng.integers(0, k + 4))
+        s = bytes(rng.choice(list(b"ACGTNnacgtR"), n).astype(np.uint8)) if n else b""
+        assert lib.ks_kmer_code(s, k) == oracle.kmer_code(s, k), (s, k)
+    for k in (1, 2, 5):
+        for code in range(4 ** k):
+            assert lib.ks_kmer_code(oracle.kmer_seq(k, code).encode(), k) == code
