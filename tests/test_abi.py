@@ -84,3 +84,53 @@ def test_kmer_code_host_helper_matches_oracle(oracle):
     for k in (1, 2, 5):
         for code in range(4 ** k):
             assert lib.ks_kmer_code(oracle.kmer_seq(k, code).encode(), k) == code
+
+
+def test_fold_carry_host_helper():
+    """ks_fold_carry (host only): the state / open excursion entering shard r from the 48-byte aggregates of
+    the shards before it, against a plain Python fold of x -> kill ? b : max(x + a, b) and of the
+    leftmost-maximum rule (strict >)."""
+    import struct
+    import numpy as np
+    from kmer_spans_b200 import api
+
+    def i128(v):  # two's complement, little endian (the layout of fx_t = __int128)
+        return int(v % (1 << 128)).to_bytes(16, "little")
+
+    def from_i128(b):
+        v = int.from_bytes(b, "little")
+        return v - (1 << 128) if v >> 127 else v
+
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        n = int(rng.integers(1, 9))
+        xf = [(int(rng.integers(-10**12, 10**12)), int(rng.integers(0, 10**12)), int(rng.random() < 0.2)) for _ in range(n)]
+        blobs = [i128(a) + i128(b) + struct.pack("<I", kill) + b"\0" * 12 for a, b, kill in xf]
+        S = 0
+        for r in range(n + 1):
+            got = from_i128(api.fold_carry(0, blobs, r)[:16])
+            assert got == S, (trial, r)
+            if r < n:
+                a, b, kill = xf[r]
+                S = b if kill else max(S + a, b)
+        ex = []
+        for _ in range(n):
+            reset = int(rng.random() < 0.4)
+            opened = 1 if not reset else int(rng.random() < 0.7)
+            M = int(rng.integers(1, 10**12)) if opened else -(1 << 126)
+            beg = int(rng.integers(16, 10**9)) if (reset and opened) else -1
+            pk = int(rng.integers(16, 10**9)) if opened else -1
+            ex.append((M, beg, pk, reset, opened))
+        blobs = [i128(M) + struct.pack("<qqII", beg, pk, reset, opened) + b"\0" * 8 for M, beg, pk, reset, opened in ex]
+        acc = (-(1 << 126), -1, -1, 1, 0)  # nothing is open left of the first shard
+        for r in range(n + 1):
+            out = api.fold_carry(1, blobs, r)
+            M = from_i128(out[:16])
+            beg, pk, reset, opened = struct.unpack("<qqII", out[16:40])
+            assert (M, beg, pk, opened) == (acc[0], acc[1], acc[2], acc[4]) and reset == 1, (trial, r)
+            if r < n:
+                g = ex[r]
+                if g[3]:
+                    acc = g
+                elif g[0] > acc[0]:
+                    acc = (g[0], acc[1], g[2], acc[3], acc[4])
