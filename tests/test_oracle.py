@@ -240,3 +240,28 @@ def test_tr_lr_matches_reference_bitexact(oracle, ref):
         assert np.array_equal(a["score"], b["score"])
         total += len(b["pos"])
     assert total > 1000
+
+
+@pytest.mark.parametrize("k", [6, 8])
+def test_next_rows_match_reference_larger_k(oracle, ref, k):
+    """the two SURVEY 8(f) restatements at larger k (tables of 4^6 / 4^8 entries, longer planted sequences)"""
+    rng = np.random.default_rng(40 + k)
+    n = 4 ** k
+    kms = [oracle.kmer_seq(k, c).encode() for c in range(n)]
+    for t in range(4):
+        seqs = [planted(rng, int(rng.integers(2000, 30000))) for _ in range(3)] + [rand_seq(rng, 500, p_n=0.2)]
+        init, trans = rng.normal(0, 1, n), rng.normal(-0.15, 1, n)
+        if t % 2:
+            init, trans = np.round(init), np.round(trans)
+        min_len = int(rng.choice([0, 5, 40]))
+        a = ref.call_tr_lr(seqs, k, min_len, kms, init, trans)
+        b = oracle.tr_lr_regions(seqs, k, init, trans, min_len)
+        assert np.array_equal(a["pos"], b["pos"]) and np.array_equal(a["score"], b["score"])
+        assert len(b["pos"]) > 0
+        sel = [kms[int(c)] for c in rng.integers(0, n, 3)] + [seqs[0][100:100 + k]]
+        window = int(rng.integers(2 * k, 300))
+        a = ref.call_window_dist(seqs, sel, k, window, 1)
+        b = oracle.window_dist(seqs, sel, k, window, True)
+        assert np.array_equal(a["dist"], b["dist"]) and np.array_equal(a["included"], b["included"])
+        for x, y in zip(a["pos"], b["pos"]):
+            assert _pos_equal(x, y, len(sel))
