@@ -138,7 +138,8 @@ def run_reference(args, rank, world):
     per_step = 150.0 / max(1, args.steps + args.warmup)
     sample = int(min(50e6, max(2e6, per_step * 9e6)))
     sample = min(sample, args.n_bases)
-    seq = synth.config2(args.n_bases if args.n_bases < 60_000_000 else 60_000_000, 2)[0][:sample].tobytes()
+    # the SAME bytes the GPU arm's rank 0 runs on: a prefix of config2(n_bases, seed 2)
+    seq = synth.config2(args.n_bases, 2)[0][:sample].tobytes()
     kind = "reference"
     for _ in range(args.warmup):
         _, _, kind = cpu_reference_pass(seq)
@@ -153,8 +154,10 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/f64", "data": "synthetic",
         "config": workload_config(args, world),
         "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": 1, "kind": kind,
-                         "sample": "first %d bases of the config-2 sequence (seed 2), k=12, log2 mode, whole CPU "
-                                   "path per step; the reference is single-threaded" % sample},
+                         "sample": "first %d bases of the %d-base config-2 sequence (seed 2) the GPU arm runs on "
+                                   "(same bytes), k=12, log2 mode, whole CPU path per step; the reference is "
+                                   "single-threaded" % (sample, args.n_bases)},
+        "same_input": "prefix of the GPU arm's rank-0 sequence",
         "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -172,6 +175,72 @@ def workload_config(args, world, exchange="NCCL"):
 
 
 # --------------------------------------------------------------------------------------------------
+def parity_check(args, ctx, stages, seq_host, rank, world, dist, torch):
+    """Outside the timed region: the exact call sequence the timed loop runs, on a prefix of this rank's
+    sequence with the spans fetched, against the CPU oracle (checker only).  N = 1: ks_dev_pipeline.
+    N > 1: count_async -> reduce_counts -> scores_from_counts_dev -> scan; the reduced count table must
+    equal the sum of the per-rank oracle tables.  Returns the parity_check record."""
+    from oracle.ksoracle import Oracle
+    orc = Oracle()
+    P = int(min(args.parity_bases, args.n_bases))
+    pre = np.ascontiguousarray(seq_host[:P])
+    pre_b = pre.tobytes()
+    dev = stages.device
+    rec = {"bases_per_rank": P, "ok": False}
+    if world == 1:
+        ss = ctx.upload([pre])
+        counts = torch.zeros(4 ** K, dtype=torch.int32, device=dev)
+        scores = torch.zeros(4 ** K, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(dev)
+        want = orc.mode_regions([pre_b], K, MODE_LOG2, MIN_W, MIN_SCORE, thr=THR)
+        got = ctx.dev_pipeline(ss, K, MODE_LOG2, MIN_W, MIN_SCORE, thr=THR, d_counts=counts.data_ptr(),
+                               d_scores=scores.data_ptr(), fetch_spans=True)
+        c_ok = bool((counts.cpu().numpy() == want["counts"]).all()) and got["n"] == want["n"]
+        t_ok = scores.cpu().numpy().tobytes() == want["scores"].tobytes()
+        rec["call"] = "ks_dev_pipeline"
+        # rank mode (the mode the reference codes) through the same call
+        want_r = orc.low_comp([pre_b], K, MIN_W, MIN_SCORE, 0.75)
+        got_r = ctx.dev_pipeline(ss, K, 0, MIN_W, MIN_SCORE, thr=0.75, d_counts=counts.data_ptr(),
+                                 d_scores=scores.data_ptr(), fetch_spans=True)
+        r_ok = (scores.cpu().numpy().tobytes() == want_r["ranks"].tobytes()
+                and got_r["pos"].tolist() == want_r["pos"].tolist()
+                and bool(np.allclose(got_r["score"], want_r["score"], rtol=1e-9, atol=0)))
+        rec["rank_mode"] = {"ok": bool(r_ok), "spans": int(len(want_r["pos"]))}
+        ss.free()
+        del counts, scores
+    else:
+        stages.load([pre])
+        stages.count_async(K)
+        stages.reduce_counts(dist)
+        stages.scores_from_counts_dev(K, MODE_LOG2, float("nan"))
+        gp, gs = stages.scan(K, THR, MIN_W, MIN_SCORE, fetch=True)
+        got = {"pos": gp, "score": gs}
+        n_loc, c_loc = orc.kmer_counts([pre_b], K)
+        tot = torch.from_numpy(c_loc.astype(np.int64)).to(dev)
+        n_t = torch.tensor([n_loc], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot)
+        dist.all_reduce(n_t)
+        c_all = tot.cpu().numpy().astype(np.int32)
+        c_ok = bool((stages.counts.cpu().numpy() == c_all).all()) and int(stages.nwords.item()) == int(n_t.item())
+        W = orc.scores(c_all, K, float(n_t.item()), MODE_LOG2)
+        t_ok = stages.scores.cpu().numpy().tobytes() == W.tobytes()
+        want = orc.kmer_regions([pre_b], K, W - THR, MIN_W, MIN_SCORE)
+        rec["call"] = "count_async -> reduce_counts (%s) -> scores_from_counts_dev -> scan" % stages.peer_sum_kind()
+        r_ok = True
+        stages.load([seq_host])
+    s_ok = got["pos"].tolist() == want["pos"].tolist() and bool(
+        np.allclose(got["score"], want["score"], rtol=1e-9, atol=0))
+    ok = c_ok and t_ok and s_ok and r_ok
+    if world > 1:
+        f = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        ok = bool(f.item())
+    rec.update({"ok": bool(ok), "counts_bit_exact": bool(c_ok), "score_table_bit_exact": bool(t_ok),
+                "spans_identical": bool(s_ok), "spans": int(len(want["pos"])), "score_rtol": 1e-9,
+                "oracle": "oracle/ks_oracle.c (pinned to the compiled reference by tests/test_oracle.py)"})
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,6 +250,9 @@ def main():
     ap.add_argument("--n-bases", type=int, default=N_BASES)
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-bases", type=int, default=20_000_000)
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the rank-mode / config-1 / config-5 records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -233,6 +305,10 @@ def main():
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize(dev)
+
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(args, ctx, stages, seq_host, rank, world, dist, torch)
 
     for _ in range(args.warmup):
         n_spans = step()
@@ -287,6 +363,50 @@ def main():
     e2e_s = float(t_e.item())
     e2e_val = world * args.n_bases * e2e_steps / e2e_s / 1e9
 
+    # ---- other workloads on the same context (N = 1; device-resident, CUDA events on the ctx stream) ----
+    extra = {}
+    if world == 1 and not args.no_extra:
+        peak_x, _ = measured_peak()
+
+        def timed(ss, k, mode, thr, reps):
+            for _ in range(3):
+                ctx.dev_pipeline(ss, k, mode, MIN_W, MIN_SCORE, thr=thr, d_counts=stages.counts.data_ptr(),
+                                 d_scores=stages.scores.data_ptr())
+            ctx.set_profile(True)
+            ctx.profile(reset=True)
+            ctx.reset_launches()
+            ctx.timer_start()
+            for _ in range(reps):
+                r = ctx.dev_pipeline(ss, k, mode, MIN_W, MIN_SCORE, thr=thr, d_counts=stages.counts.data_ptr(),
+                                     d_scores=stages.scores.data_ptr())
+            t = ctx.timer_stop() / reps
+            pr = ctx.profile(reset=True)
+            ctx.set_profile(False)
+            lv, rv = ctx.scan_stats()
+            nb = ss.bases
+            alg_b = 1.5 * nb + 16.0 * 4 ** k
+            return {"ms_per_step": t, "gbases_per_s": nb / (t * 1e-3) / 1e9, "bases": nb, "k": k,
+                    "spans": int(r["n_spans"]), "restart_levels": int(lv), "launches_per_step": ctx.launches() / reps,
+                    "roofline_frac_pipeline": alg_b / (t * 1e-3) / 1e9 / peak_x,
+                    "kernels_ms_per_step": {nm: tot / reps for nm, (tot, n) in pr.items() if n}}
+
+        # the mode the reference codes (kmer_low_comp_regions: weighted rank - thr, thr = 0.75), same sequence
+        extra["rank_mode"] = dict(timed(stages.ss, K, 0, 0.75, max(3, min(args.steps, 10))),
+                                  workload="same 250 Mb sequence, k=12, weighted rank, thr 0.75")
+        # BASELINE.json configs[0]: 1 Mb, k = 8, +-1 mode
+        ss1 = ctx.upload([synth.config1()[0]])
+        extra["config1"] = dict(timed(ss1, 8, 2, 0.0, 20), workload="configs[0]: 1 Mb, k=8, +-1 (threshold) mode")
+        ss1.free()
+        # BASELINE.json configs[4], a 10 000-contig subset of the 100 000 (host generation time), k = 10
+        from kmer_spans_b200.api import SeqBatch
+        sb = SeqBatch.from_list(synth.contigs(10_000, seed=5, k=10))
+        ss5 = ctx.upload(sb)
+        extra["config5_subset"] = dict(timed(ss5, 10, 1, 0.0, 5),
+                                       workload="configs[4] subset: 10 000 contigs of 1-50 kb, k=10, log2 mode")
+        extra["config5_subset_rank"] = dict(timed(ss5, 10, 0, 0.75, 5),
+                                            workload="configs[4] subset: 10 000 contigs, k=10, rank mode thr 0.75")
+        ss5.free()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -331,6 +451,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
         "spans_per_step": int(n_spans), "restart_levels": int(levels),
+        "parity_check": parity,
+        "extra": extra,
     }
     if world == 1 and not args.no_cpu_baseline:
         sample = min(args.n_bases, 25_000_000)
@@ -342,6 +464,8 @@ def main():
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("bench.py: the timed call does NOT match the oracle: %s" % json.dumps(parity))
 
 
 if __name__ == "__main__":

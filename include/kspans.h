@@ -33,7 +33,8 @@ enum {
   KS_OK = 0,
   KS_ERR_ARG = 1,      /* argument rejected; message mirrors the reference's error() text where one exists */
   KS_ERR_CUDA = 2,     /* no device / CUDA runtime failure: there is no CPU path */
-  KS_ERR_RANGE = 3,    /* a weight is +inf or >= 2^40 (exact fixed-point scan range) */
+  KS_ERR_RANGE = 3,    /* a weight is +inf or >= 2^40, or nonzero but more than 2^57 times smaller than the largest
+                        * (exact fixed-point scan range) */
   KS_ERR_NOMEM = 4
 };
 
@@ -165,6 +166,12 @@ int ks_dev_xsum(ks_ctx *ctx, void *const *tables, int nranks, int rank, void *mc
  * gathers the 4-byte count (table L2 resident up to k = 12) and maps it through a dense LUT. */
 int ks_dev_scan_counts(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
                        int min_width, double min_score, ks_spans *host_out_or_null, uint64_t *n_spans);
+/* Scan in rank mode, score = rank - thr (the one mode the reference codes, src/kmer_spans.c:268,602-612), with
+ * the rank order the last ks_dev_scores(mode KS_MODE_RANK) on this ctx derived.  The kernel gathers the 4-byte
+ * position of the k-mer in the stable (count, index) order (4^k x 4 B, L2 resident up to k = 12) and evaluates
+ * the rank from the linear pieces of the closed form; bit-identical to ks_dev_scan on the rank table. */
+int ks_dev_scan_ranks(ks_ctx *ctx, const ks_seqset *s, int k, double thr, int min_width, double min_score,
+                      ks_spans *host_out_or_null, uint64_t *n_spans);
 /* transition-score scan on a resident set; d_init / d_trans = device double[4^k] in code order */
 int ks_dev_tr_lr_regions(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_init, const double *d_trans,
                          int min_length, ks_spans *host_out_or_null, uint64_t *n_spans);
@@ -199,6 +206,9 @@ int ks_dev_scan_shard(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W,
 int ks_dev_scan_counts_shard(ks_ctx *ctx, const ks_seqset *s, int k, const int32_t *d_counts, double thr,
                              int min_width, double min_score, int64_t chunk0, int64_t nchunks,
                              ks_exchange_fn fn, void *user, ks_spans *host_out_or_null, uint64_t *n_spans);
+int ks_dev_scan_ranks_shard(ks_ctx *ctx, const ks_seqset *s, int k, double thr, int min_width, double min_score,
+                            int64_t chunk0, int64_t nchunks, ks_exchange_fn fn, void *user,
+                            ks_spans *host_out_or_null, uint64_t *n_spans);
 /* host helper: carry entering shard `rank` from the 48-byte aggregates of shards 0..nranks-1 */
 int ks_fold_carry(int what, const void *all48, int nranks, int rank, void *carry_in48);
 

@@ -67,6 +67,8 @@ SIGNATURES = {
     "ks_dev_scores_devtotal": (_i, [_vp, _i, _vp, _vp, _i, _d, _vp, _pd]),
     "ks_dev_scan": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, _vp, C.POINTER(KsSpans), _pu64]),
     "ks_dev_scan_counts": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, C.POINTER(KsSpans), _pu64]),
+    "ks_dev_scan_ranks": (_i, [_vp, _vp, _i, _d, _i, _d, C.POINTER(KsSpans), _pu64]),
+    "ks_dev_scan_ranks_shard": (_i, [_vp, _vp, _i, _d, _i, _d, _i64, _i64, _vp, _vp, C.POINTER(KsSpans), _pu64]),
     "ks_seqset_chunks": (_i64, [_vp]),
     "ks_dev_count_range": (_i, [_vp, _vp, _i, _i64, _i64, _vp, _pd]),
     "ks_dev_scan_shard": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, _i64, _i64, _vp, _vp, C.POINTER(KsSpans), _pu64]),

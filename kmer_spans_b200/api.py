@@ -226,6 +226,17 @@ class Context:
             res["pos"], res["score"] = _spans_to_numpy(self.lib, sp)
         return res
 
+    def dev_scan_ranks(self, ss, k, thr, min_w, min_score, fetch_spans=True):
+        """scan in rank mode with the rank order of the last dev_scores(mode RANK) on this context"""
+        ns = C.c_uint64(0)
+        sp = KsSpans()
+        self._ck(self.lib.ks_dev_scan_ranks(self.h, ss.h, int(k), float(thr), int(min_w), float(min_score),
+                                            C.byref(sp) if fetch_spans else None, C.byref(ns)))
+        res = dict(n_spans=int(ns.value))
+        if fetch_spans:
+            res["pos"], res["score"] = _spans_to_numpy(self.lib, sp)
+        return res
+
     # ---- one set sharded over several GPUs (exact stitching) -----------------------------------
     def dev_count_range(self, ss, k, chunk0, nchunks, d_counts):
         n = C.c_double(0)

@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libkspans_cuda.so")
 SOURCES = ["ks_api.cu"]
-DEPS = ["ks_api.cu", "ks_kernels.cuh", "ks_chunk.cuh", "ks_sort.cuh", "ks_rankseg.h", "ks_layout.h",
-        os.path.join("..", "..", "include", "kspans.h")]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [
+    os.path.join("..", "..", "include", "kspans.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 

@@ -72,8 +72,13 @@ struct WorkPool {
   void ensure(unsigned nthreads) {
     while (th.size() + 1 < nthreads) {
       const unsigned id = (unsigned)th.size() + 1;
-      th.emplace_back([this, id]() {
-        unsigned long seen = 0;
+      unsigned long born;
+      {  // a worker created after jobs have run must not pick up the finished job of an earlier generation
+        std::lock_guard<std::mutex> lk(m);
+        born = gen;
+      }
+      th.emplace_back([this, id, born]() {
+        unsigned long seen = born;
         for (;;) {
           std::function<void(unsigned)> f;
           {
@@ -105,6 +110,7 @@ struct WorkPool {
     f(0);
     std::unique_lock<std::mutex> lk(m);
     cv_done.wait(lk, [&] { return pending == 0; });
+    job = nullptr;  // the callable may reference the caller's stack
   }
   ~WorkPool() {
     {
@@ -181,9 +187,18 @@ struct ks_ctx {
   char *hpin = nullptr;
   static constexpr size_t HPIN_HIST = 0, HPIN_SMALL = 256u << 10, HPIN_CLS = 320u << 10, HPIN_GCOUNT = 512u << 10,
                           HPIN_DENSE = 768u << 10, HPIN_LUT = 1280u << 10, HPIN_PRM = 1792u << 10,
-                          HPIN_BYTES = 2048u << 10;
+                          HPIN_FX = 2048u << 10,  // the scan's per-class fixed-point table: its own region, because the
+                                                  // score stage may still be copying out of HPIN_LUT when the scan starts
+                          HPIN_BYTES = 2560u << 10;
   // class table of the last ks_dev_scores(LOG2 | SIGN): index of every k-mer's count among the distinct counts
-  DBuf cls, cls_dense;
+  DBuf cls, cls_dense, core;
+  // rank order of the last ks_dev_scores(RANK): position of every k-mer, piece starts, bucket table (the pieces'
+  // x0 / inc stay in sc_segx0 / sc_seginc); scan_ranks_impl gathers 4-byte positions instead of 8-byte scores
+  DBuf rk_pos, rk_p0, rk_bucket;
+  bool rk_valid = false;
+  int rk_k = 0, rk_shift = 0;
+  double rk_max = 0;
+  bool core_valid = false;           // ctx->core holds the core records of ctx->cls (scan_gather_kernel, core mode)
   const void *cls_counts = nullptr;  // the count table it was derived from
   size_t cls_n = 0;
   size_t child_cap = 0;
@@ -347,7 +362,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->win_match, &ctx->win_cnt, &ctx->win_pre, &ctx->win_scratch, &ctx->win_codes, &ctx->win_fix,
                  &ctx->win_hist, &ctx->win_pos, &ctx->st_aux, &ctx->child_pk, &ctx->child_c, &ctx->child_count,
                  &ctx->tr_tables, &ctx->st_mn, &ctx->st_mx, &ctx->st_bm, &ctx->detail, &ctx->detail_count,
-                 &ctx->cls, &ctx->cls_dense};
+                 &ctx->cls, &ctx->cls_dense, &ctx->core, &ctx->rk_pos, &ctx->rk_p0, &ctx->rk_bucket};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1018,6 +1033,7 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
     ctx->lut_k = k;
     // class table for the scan: 2 bytes per k-mer instead of the 4-byte count (stays L2 resident at k = 12)
     ctx->cls_counts = nullptr;
+    ctx->core_valid = false;
     if (ng && ng <= 65535 && getenv("KS_NO_CLASS_TABLE") == nullptr) {
       uint32_t ndense = std::min<uint32_t>(gcount[ng - 1] + 1, DENSE);
       // staged in pinned memory: every earlier copy out of it completed before the synchronisation above
@@ -1039,6 +1055,16 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
       CK(cudaGetLastError());
       ctx->cls_counts = d_counts;
       ctx->cls_n = n;
+      // core records: one 8-byte gather serves two consecutive positions of the scan
+      ctx->core_valid = false;
+      if (getenv("KS_NO_CORE_TABLE") == nullptr) {
+        const size_t ncore = n / 4;
+        CK(ctx->core.ensure(ncore * sizeof(uint2)));
+        core_apply_kernel<<<grid_for(ncore, 256), 256, 0, st>>>(ctx->cls.as<uint16_t>(), ncore, ctx->core.as<uint2>());
+        LAUNCHED(1);
+        CK(cudaGetLastError());
+        ctx->core_valid = true;
+      }
     }
     if (d_scores) {  // the per-k-mer table itself (an output; the scan gathers counts + LUT instead)
       uint32_t ndense = ng ? std::min<uint32_t>(gcount[ng - 1] + 1, DENSE) : 0;
@@ -1075,6 +1101,7 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
     }
     return KS_OK;
   }
+  ctx->rk_valid = false;
   if (rank_mode && total == 0) {
     // 0/0 addends: every rank but the first in sort order (k-mer 0) is NaN (:200)
     fill_nan_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(d_scores, n);
@@ -1164,13 +1191,39 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
       CK(cudaMemcpyAsync(ctx->sc_segj0.p, j0.data(), nsg * 8, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(ctx->sc_segx0.p, x0.data(), nsg * 8, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(ctx->sc_seginc.p, inc.data(), nsg * 8, cudaMemcpyHostToDevice, st));
+      // the same pieces addressed by absolute position in the rank order, for the scan's 4-byte gather
+      const bool want_pos = mode == KS_MODE_RANK && nsg > 0 && n <= 0xffffffffull && getenv("KS_NO_RANK_POS") == nullptr;
+      std::vector<uint32_t> p0, bucket;
+      if (want_pos) {
+        p0.resize(nsg + 1);
+        for (size_t g = 0; g < ng; ++g)
+          for (uint32_t i = seg_first[g]; i < seg_first[g + 1]; ++i) p0[i] = (uint32_t)(gstart[g] + j0[i]);
+        p0[nsg] = (uint32_t)std::min<size_t>(n, 0xffffffffull);
+        const int shift = 2 * k > 10 ? 2 * k - 10 : 0;
+        bucket.assign(RK_BUCKETS + 1, (uint32_t)(nsg - 1));
+        size_t a = 0;
+        for (size_t b = 0; b <= (size_t)RK_BUCKETS && ((uint64_t)b << shift) < n; ++b) {
+          const uint64_t pos = (uint64_t)b << shift;
+          while (a + 1 < nsg && p0[a + 1] <= pos) ++a;
+          bucket[b] = (uint32_t)a;
+        }
+        CK(ctx->rk_pos.ensure(n * 4));
+        CK(ctx->rk_p0.ensure((nsg + 1) * 4));
+        CK(ctx->rk_bucket.ensure((RK_BUCKETS + 1) * 4));
+        CK(cudaMemcpyAsync(ctx->rk_p0.p, p0.data(), (nsg + 1) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->rk_bucket.p, bucket.data(), (RK_BUCKETS + 1) * 4, cudaMemcpyHostToDevice, st));
+        ctx->rk_shift = shift;
+        ctx->rk_k = k;
+        ctx->rk_max = fma((double)(n - 1 - p0[nsg - 1]), inc[nsg - 1], x0[nsg - 1]);  // rank of the last k-mer in order
+      }
       rank_eval_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(
           svals, n, ctx->sc_gstart.as<uint32_t>(), (uint32_t)ng, ctx->sc_segfirst.as<uint32_t>(),
           ctx->sc_segj0.as<unsigned long long>(), ctx->sc_segx0.as<double>(), ctx->sc_seginc.as<double>(),
-          d_scores);
+          d_scores, want_pos ? ctx->rk_pos.as<uint32_t>() : nullptr);
       LAUNCHED(1);
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(st));  // host vectors above must outlive the copies
+      ctx->rk_valid = want_pos;
     }
   }
   if (mode == KS_MODE_RANK_REL) {
@@ -1240,6 +1293,9 @@ struct ScanTable {  // what scan_gather_kernel gathers from
   const uint32_t *counts = nullptr;
   uint32_t lut_size = 0, sp_n = 0;
   bool use_cls = false;  // class mode: ctx->cls + per-class table in ctx->lut_fx
+  bool use_core = false; // ... gathered two positions at a time through ctx->core
+  bool use_rank = false; // rank mode: ctx->rk_pos + the linear pieces of the rank order
+  double rk_thr = 0;
   bool tr = false;  // transition-score scan: ctx->wfx = [trans | init], every close is re-scanned
 };
 }  // namespace
@@ -1318,6 +1374,14 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.wfx = ctx->wfx.as<int64_t>();
     A.counts = tab.counts;
     A.cls = ctx->cls.as<uint16_t>();
+    A.core = ctx->core.as<uint2>();
+    A.rk_pos = ctx->rk_pos.as<uint32_t>();
+    A.rk_p0 = ctx->rk_p0.as<uint32_t>();
+    A.rk_x0 = ctx->sc_segx0.as<double>();
+    A.rk_inc = ctx->sc_seginc.as<double>();
+    A.rk_bucket = ctx->rk_bucket.as<uint32_t>();
+    A.rk_shift = ctx->rk_shift;
+    A.rk_thr = tab.rk_thr;
     A.lut = ctx->lut_fx.as<int64_t>();
     A.lut_size = tab.lut_size;
     A.sp_count = ctx->lut_spc.as<uint32_t>();
@@ -1383,9 +1447,13 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     if (tab.tr) CK(cudaMemsetAsync(ctx->child_count.p, 0, sizeof(unsigned long long), st));
     cudaEvent_t ps = ctx->prof_begin();
     if (tab.tr) scan_gather_kernel<0, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (fast && tab.use_rank) scan_gather_kernel<3, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (tab.use_rank) scan_gather_kernel<3><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (fast && tab.use_core) scan_gather_kernel<2, false, true, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (fast && tab.use_cls) scan_gather_kernel<2, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (fast && tab.use_lut) scan_gather_kernel<1, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (fast) scan_gather_kernel<0, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (tab.use_core) scan_gather_kernel<2, false, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (tab.use_cls) scan_gather_kernel<2><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (tab.use_lut) scan_gather_kernel<1><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else scan_gather_kernel<0><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
@@ -1419,7 +1487,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
       // the list is short (one entry per tile at most, plus the rare wide excursions); the kernel reads
       // its length on the device and strides over it, so no host round trip sits between the kernels
       const unsigned dgrid = (unsigned)std::min<size_t>(blocks_exact(tiles + 1024, 128), 148u * 8u);
-      if (tab.use_cls) scan_detail_kernel<2><<<dgrid, 128, 0, st>>>(A);
+      if (tab.use_rank) scan_detail_kernel<3><<<dgrid, 128, 0, st>>>(A);
+      else if (tab.use_cls) scan_detail_kernel<2><<<dgrid, 128, 0, st>>>(A);
       else if (tab.use_lut) scan_detail_kernel<1><<<dgrid, 128, 0, st>>>(A);
       else scan_detail_kernel<0><<<dgrid, 128, 0, st>>>(A);
       LAUNCHED(1);
@@ -1455,6 +1524,9 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     CK(cudaStreamSynchronize(st));
     if (level == 0 && (hprm.err & 1))
       return ctx->fail(KS_ERR_RANGE, "a k-mer weight is +Inf or >= 2^40: outside the exact scan range");
+    if (level == 0 && (hprm.err & 4))
+      return ctx->fail(KS_ERR_RANGE, "a nonzero k-mer weight is more than 2^57 times smaller than the largest one: "
+                                     "outside the exact scan range");
     if (level == 0 && tab.tr && (hprm.err & 2))
       return ctx->fail(KS_ERR_RANGE, "a transition or k-mer score is NaN");
     count_inscan = false;  // every position of this level has been counted, also if we must retry
@@ -1683,11 +1755,11 @@ static int scan_counts_impl(ks_ctx *ctx, const ks_seqset *s, int k, const int32_
   hp.min_hi = (int64_t)(uint64_t)(((unsigned __int128)mu) >> 64);
   if (ctx->cls_counts == (const void *)d_counts && ctx->cls_n == ((size_t)1 << (2 * k)) && ng && ng <= 65535) {
     // class mode: one table entry per distinct count, gathered through the 2-byte class table
-    // staged in pinned memory; the last scan on this context ended with a synchronisation, so nothing
-    // still reads these regions
+    // staged in pinned memory (HPIN_FX / HPIN_PRM are written by this function only); the last scan on this
+    // context ended with a synchronisation, so nothing still reads these two regions
     rc = ensure_hpin(ctx);
     if (rc) return rc;
-    int64_t *fx = reinterpret_cast<int64_t *>(ctx->hpin + ks_ctx::HPIN_LUT);
+    int64_t *fx = reinterpret_cast<int64_t *>(ctx->hpin + ks_ctx::HPIN_FX);
     DevScanParams *hp_pin = reinterpret_cast<DevScanParams *>(ctx->hpin + ks_ctx::HPIN_PRM);
     for (size_t g = 0; g < ng; ++g) fx[g] = wfx_from_double(ctx->lut_gval[g] - thr, hp.qs);
     *hp_pin = hp;
@@ -1699,6 +1771,7 @@ static int scan_counts_impl(ks_ctx *ctx, const ks_seqset *s, int k, const int32_
     ScanTable tab;
     tab.use_lut = true;
     tab.use_cls = true;
+    tab.use_core = ctx->core_valid;
     tab.lut_size = (uint32_t)ng;
     return scan_core(ctx, s, k, tab, mw, nullptr, host_out, n_spans, sh);
   }
@@ -1753,6 +1826,64 @@ int ks_dev_scan_counts_shard(ks_ctx *ctx, const ks_seqset *s, int k, const int32
   KS_CATCH(ctx)
 }
 
+// Scan in rank mode (the mode the reference codes, :268,602-612): score = rank - thr with the rank table the last
+// ks_dev_scores(mode RANK) on this ctx derived.  The kernel gathers the 4-byte position of the k-mer in the rank
+// order (4^k x 4 B, L2 resident up to k = 12, against 4^k x 8 B for the score table) and evaluates the rank from
+// the linear pieces of the closed form -- the same fma that filled the rank table, so both paths agree bit for bit.
+static int scan_ranks_impl(ks_ctx *ctx, const ks_seqset *s, int k, double thr, int min_width, double min_score,
+                           ks_spans *host_out, uint64_t *n_spans, const ShardCtl *sh) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!s) return ctx->fail(KS_ERR_ARG, "ks_dev_scan_ranks: null argument");
+  int rc = check_k(ctx, k);
+  if (rc) return rc;
+  if (!ctx->rk_valid || ctx->rk_k != k)
+    return ctx->fail(KS_ERR_ARG, "ks_dev_scan_ranks: call ks_dev_scores with mode RANK for this k first");
+  if (host_out) { host_out->pos = nullptr; host_out->score = nullptr; host_out->n = 0; }
+  if (n_spans) *n_spans = 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const uint64_t mw = (uint64_t)(int64_t)min_width;
+  cudaEvent_t pw = ctx->prof_begin();
+  // ranks run from 0 (first k-mer in order) to rk_max, so max |rank - thr| sits at one of the two ends
+  const double wmax = std::max(fabs(0.0 - thr), fabs(ctx->rk_max - thr));
+  if (!(wmax < 0x1p40)) return ctx->fail(KS_ERR_RANGE, "threshold outside the exact scan range");
+  rc = ensure_hpin(ctx);
+  if (rc) return rc;
+  DevScanParams *hp = reinterpret_cast<DevScanParams *>(ctx->hpin + ks_ctx::HPIN_PRM);
+  memset(hp, 0, sizeof *hp);
+  hp->qs = qs_for_max(wmax);
+  fx_t mu = fx_ceil_units(min_score, hp->qs);
+  hp->min_width = mw;
+  hp->min_lo = (uint64_t)(unsigned __int128)mu;
+  hp->min_hi = (int64_t)(uint64_t)(((unsigned __int128)mu) >> 64);
+  CK(ctx->prm.ensure(sizeof(DevScanParams)));
+  CK(cudaMemcpyAsync(ctx->prm.p, hp, sizeof *hp, cudaMemcpyHostToDevice, st));
+  ctx->prof_end(KS_PROF_WFX, pw);
+  ScanTable tab;
+  tab.use_rank = true;
+  tab.rk_thr = thr;
+  return scan_core(ctx, s, k, tab, mw, nullptr, host_out, n_spans, sh);
+}
+
+int ks_dev_scan_ranks(ks_ctx *ctx, const ks_seqset *s, int k, double thr, int min_width, double min_score,
+                      ks_spans *host_out, uint64_t *n_spans) {
+  KS_TRY
+  return scan_ranks_impl(ctx, s, k, thr, min_width, min_score, host_out, n_spans, nullptr);
+  KS_CATCH(ctx)
+}
+
+int ks_dev_scan_ranks_shard(ks_ctx *ctx, const ks_seqset *s, int k, double thr, int min_width, double min_score,
+                            int64_t chunk0, int64_t nchunks, ks_exchange_fn fn, void *user, ks_spans *host_out,
+                            uint64_t *n_spans) {
+  KS_TRY
+  if (!ctx) return KS_ERR_ARG;
+  if (!fn) return ctx->fail(KS_ERR_ARG, "ks_dev_scan_ranks_shard: null exchange function");
+  ShardCtl sh;
+  sh.chunk0 = chunk0; sh.nchunks = nchunks; sh.fn = fn; sh.user = user;
+  return scan_ranks_impl(ctx, s, k, thr, min_width, min_score, host_out, n_spans, &sh);
+  KS_CATCH(ctx)
+}
+
 // carry entering shard `rank`: fold of the aggregates of shards 0 .. rank-1 (host, exact integers)
 int ks_fold_carry(int what, const void *all48, int nranks, int rank, void *carry_in48) {
   KS_TRY
@@ -1801,6 +1932,8 @@ int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double par
   if (n_words) *n_words = nw;
   if (mode == KS_MODE_LOG2 || mode == KS_MODE_SIGN)
     return ks_dev_scan_counts(ctx, s, k, d_counts, thr, min_width, min_score, host_out, n_spans);
+  if (mode == KS_MODE_RANK && ctx->rk_valid)  // the score stage just left the rank order on this context
+    return ks_dev_scan_ranks(ctx, s, k, thr, min_width, min_score, host_out, n_spans);
   return ks_dev_scan(ctx, s, k, d_scores, thr, min_width, min_score, nullptr, host_out, n_spans);
   KS_CATCH(ctx)
 }
@@ -2002,6 +2135,7 @@ int ks_kmer_mode_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *le
   start_staged_copies(ctx);
   if (!rc) {
     if (count_fn) rc = ks_dev_scan_counts(ctx, ss, k, d_counts, thr, min_width, min_score, out, nullptr);
+    else if (mode == KS_MODE_RANK && ctx->rk_valid) rc = ks_dev_scan_ranks(ctx, ss, k, thr, min_width, min_score, out, nullptr);
     else rc = ks_dev_scan(ctx, ss, k, d_scores, thr, min_width, min_score, nullptr, out, nullptr);
   }
   int rc2 = finish_copies(ctx);

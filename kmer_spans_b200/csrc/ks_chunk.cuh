@@ -108,8 +108,7 @@ KS_HD int64_t wfx_from_double(double d, int qs) {
   int e = (int)((bits >> 52) & 0x7ff);
   uint64_t m = bits & ((1ull << 52) - 1);
   bool neg = (bits >> 63) != 0;
-  if (e == 0) return 0;
-  m |= 1ull << 52;
+  if (e == 0) e = 1; else m |= 1ull << 52;  // subnormal: m * 2^-1074
   int sh = e - 1075 + qs;  // value * 2^qs = m * 2^sh
   uint64_t v;
   if (sh >= 0) {
@@ -133,7 +132,7 @@ KS_HD int qs_for_max(double wmax) {
   if (wmax == 0.0) e = -1;
   int E = e + 1;  // wmax < 2^E
   int qs = 57 - E;
-  if (qs > 62) qs = 62;
+  if (qs > 1100) qs = 1100;  // covers every finite double (subnormals included)
   return qs;
 }
 
@@ -180,9 +179,9 @@ KS_HD fx_t fx_ceil_units(double x, int qs) {
   int e = (int)((bits >> 52) & 0x7ff);
   uint64_t m = bits & ((1ull << 52) - 1);
   bool neg = (bits >> 63) != 0;
-  if (e == 0) return (m != 0 && !neg) ? (fx_t)1 : (fx_t)0;  // +-0 -> 0; positive subnormal -> 1 unit
+  if (e == 0 && m == 0) return 0;
   if (e - 1023 + qs >= 100) return neg ? -BIG : BIG;        // beyond any reachable sum (< 2^102 units)
-  m |= 1ull << 52;
+  if (e == 0) e = 1; else m |= 1ull << 52;                  // subnormal: m * 2^-1074
   int sh = e - 1075 + qs;  // <= 47
   unsigned __int128 v;
   bool inexact = false;

@@ -55,6 +55,11 @@ __device__ __forceinline__ uint32_t ldg_u16_keep(const uint16_t *addr, uint64_t 
   asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(addr), "l"(pol));
   return v;
 }
+__device__ __forceinline__ uint2 ldg_u32x2_keep(const uint2 *addr, uint64_t pol) {
+  uint2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(addr), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ int64_t ldg_s64_keep(const int64_t *addr, uint64_t pol) {
   int64_t v;
   asm volatile("ld.global.nc.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(addr), "l"(pol));
@@ -160,7 +165,8 @@ struct DevScanParams {
   uint64_t min_lo;
   int64_t min_hi;
   int32_t qs;
-  int32_t err;             // bit 0: a weight is +inf or >= 2^40; bit 1: a weight is NaN
+  int32_t err;             // bit 0: a weight is +inf or >= 2^40; bit 1: a weight is NaN; bit 2: a nonzero weight is
+                           // more than 2^57 below the largest one and would count as 0
   unsigned long long wmax_bits;  // bits of max finite |W - thr|
 };
 
@@ -191,8 +197,14 @@ __global__ void __launch_bounds__(256) wfx_kernel(const double *__restrict__ W, 
                                                   int64_t *__restrict__ wfx, DevScanParams *prm,
                                                   uint64_t min_width, double min_score) {
   const int qs = qs_for_max(__longlong_as_double((long long)prm->wmax_bits));
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    wfx[i] = wfx_from_double(W[i] - thr, qs);
+  bool flushed = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double w = W[i] - thr;
+    const int64_t v = wfx_from_double(w, qs);
+    wfx[i] = v;
+    flushed |= (v == 0 && w != 0.0);
+  }
+  if (__any_sync(0xffffffffu, flushed) && (threadIdx.x & 31) == 0) atomicOr(&prm->err, 4);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     fx_t mu = fx_ceil_units(min_score, qs);
     prm->min_width = min_width;
@@ -247,6 +259,19 @@ struct LevelArgs {
   // sparse list (sp_count, sp_val)
   const uint32_t *counts;
   const uint16_t *cls;  // class mode (kLut == 2): index of the k-mer's count among the distinct counts, lut[cls]
+  // core mode (kLut == 2, kCore): one 8-byte record per (k-1)-mer c = the classes (clamped to 255 = "look it up in
+  // cls") of the four k-mers a.c and of the four k-mers c.b, so ONE gather serves the two consecutive positions
+  // whose k-mers share c: half the L1TEX lookups of the 2-byte class gather, same 2 * 4^k bytes of L2
+  const uint2 *core;
+  // rank mode (kLut == 3): gather the 4-byte position p of the k-mer in the stable (count, index) order and
+  // evaluate the rank from the linear pieces of ks_rankseg.h: rank = fma(p - P0[a], inc[a], x0[a]), a = the last
+  // piece with P0[a] <= p; rk_bucket[p >> rk_shift] = piece that holds position (p >> rk_shift) << rk_shift
+  const uint32_t *rk_pos;
+  const uint32_t *rk_p0;
+  const double *rk_x0, *rk_inc;
+  const uint32_t *rk_bucket;
+  int rk_shift;
+  double rk_thr;
   const int64_t *lut;
   uint32_t lut_size;
   const uint32_t *sp_count;
@@ -354,6 +379,9 @@ struct DevEmit {
 #ifndef KS_GATHER_MINBLOCKS_TABLE_SUMM
 #define KS_GATHER_MINBLOCKS_TABLE_SUMM 4
 #endif
+#ifndef KS_GATHER_MINBLOCKS_RANK
+#define KS_GATHER_MINBLOCKS_RANK 6
+#endif
 #ifndef KS_WALKFAST_MINBLOCKS
 #define KS_WALKFAST_MINBLOCKS 16
 #endif
@@ -377,13 +405,40 @@ __device__ __forceinline__ void load_window(const LevelArgs &A, int64_t p0, uint
   }
 }
 
-template <int kLut, bool kTr = false, bool kSumm = false>
+constexpr int RK_BUCKETS = 1024;
+// exact fixed-point score of the k-mer at position p of the rank order: the double rank_eval_kernel writes into
+// the rank table, minus thr (the double the reference forms at :268), converted like every table entry
+__device__ __forceinline__ int64_t rank_value(const LevelArgs &A, const uint32_t *s_bucket, uint32_t p, int qs) {
+  const uint32_t bk = p >> A.rk_shift;
+  uint32_t a = s_bucket[bk], b = s_bucket[bk + 1] + 1;
+  while (b - a > 1) {
+    const uint32_t mid = (a + b) >> 1;
+    if (__ldg(&A.rk_p0[mid]) <= p) a = mid; else b = mid;
+  }
+  const double r = fma((double)(p - __ldg(&A.rk_p0[a])), __ldg(&A.rk_inc[a]), __ldg(&A.rk_x0[a]));
+  return wfx_from_double(r - A.rk_thr, qs);
+}
+
+constexpr uint32_t CORE_ESCAPE = 255;  // class byte of a core record: "the class is >= 255, read cls[code]"
+template <int kLut, bool kTr = false, bool kSumm = false, bool kCore = false>
 __global__ void __launch_bounds__(TILE_THREADS,
-                                  kSumm ? (kLut ? KS_GATHER_MINBLOCKS_SUMM : KS_GATHER_MINBLOCKS_TABLE_SUMM)
-                                        : (kLut ? KS_GATHER_MINBLOCKS : KS_GATHER_MINBLOCKS_TABLE))
+                                  kLut == 3 ? KS_GATHER_MINBLOCKS_RANK
+                                  : kSumm ? (kLut ? KS_GATHER_MINBLOCKS_SUMM : KS_GATHER_MINBLOCKS_TABLE_SUMM)
+                                          : (kLut ? KS_GATHER_MINBLOCKS : KS_GATHER_MINBLOCKS_TABLE))
 scan_gather_kernel(const LevelArgs A) {
   __shared__ Xf s_wxf[TILE_WARPS + 1];
+  __shared__ int64_t s_lut[kCore ? CORE_ESCAPE : 1];  // scores of the classes a core record can name
+  __shared__ uint32_t s_bucket[kLut == 3 ? RK_BUCKETS + 1 : 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (kCore) {
+    for (int i = tid; i < (int)CORE_ESCAPE; i += TILE_THREADS) s_lut[i] = (uint32_t)i < A.lut_size ? __ldg(&A.lut[i]) : 0;
+    __syncthreads();
+  }
+  if (kLut == 3) {
+    for (int i = tid; i <= RK_BUCKETS; i += TILE_THREADS) s_bucket[i] = __ldg(&A.rk_bucket[i]);
+    __syncthreads();
+  }
+  const int rk_qs = kLut == 3 ? A.prm->qs : 0;
   const int64_t tile = blockIdx.x;
   // ---- chunk -> position mapping ----
   const int64_t q = tile * TILE_THREADS + tid;
@@ -445,10 +500,30 @@ scan_gather_kernel(const LevelArgs A) {
   // ---- gather: 16 independent loads per thread ----
   uint32_t c[CHUNK];   // class (kLut == 2) or count (kLut == 1)
   int64_t sv[CHUNK];   // score (table mode)
-  if (kLut == 2) {
+  if (kLut == 2 && kCore) {
+    // core mode: positions 2i and 2i+1 score the k-mers a.c and c.b around the same (k-1)-mer c (code[2i+1] >> 2 ==
+    // code[2i] & cmask), and the record of c holds both classes: 8 gathers of 8 bytes per 16 positions
+    const uint32_t cmask = A.kmask >> 2;
+    const int ashift = 2 * A.k - 2;
+#pragma unroll
+    for (int i = 0; i < CHUNK / 2; ++i) {
+      const uint32_t need = (scored >> (2 * i)) & 3u;
+      uint2 rec = make_uint2(0u, 0u);
+      if (need) rec = ldg_u32x2_keep(&A.core[code[2 * i] & cmask], keep);
+      c[2 * i] = (need & 1u) ? __byte_perm(rec.x, 0u, 0x4440u | (code[2 * i] >> ashift)) : 0u;
+      c[2 * i + 1] = (need & 2u) ? __byte_perm(rec.y, 0u, 0x4440u | (code[2 * i + 1] & 3u)) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j)  // rare: very abundant k-mers (classes beyond the first 255 distinct counts)
+      if (c[j] == CORE_ESCAPE) c[j] = ldg_u16_keep(&A.cls[code[j]], keep);
+  } else if (kLut == 2) {
     // class mode: 2-byte gather (the 4^k x 2 B table stays L2 resident where the 4 B count table does not)
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u16_keep(&A.cls[code[j]], keep) : 0u;
+  } else if (kLut == 3) {
+    // rank mode: 4-byte position in the rank order (4^k x 4 B, L2 resident at k <= 12) instead of the 8-byte score
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u32_keep(&A.rk_pos[code[j]], keep) : 0u;
   } else if (kLut) {
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u32_keep(&A.counts[code[j]], keep) : 0u;
@@ -458,7 +533,9 @@ scan_gather_kernel(const LevelArgs A) {
   }
   // value of a SCORED position (WFX_KILL = the table says "force the state to 0")
   auto value = [&](int j) -> int64_t {
+    if (kLut == 2 && kCore) return c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&A.lut[c[j]]);
     if (kLut == 2) return __ldg(&A.lut[c[j]]);
+    if (kLut == 3) return rank_value(A, s_bucket, c[j], rk_qs);
     if (kLut) {
       if (c[j] < A.lut_size) return __ldg(&A.lut[c[j]]);
       uint32_t lo = 0, hi = A.sp_n;  // rare: very abundant k-mer, look it up in the sorted sparse list
@@ -473,7 +550,7 @@ scan_gather_kernel(const LevelArgs A) {
   auto stash = [&](int j, int64_t v) {
     if (kSumm) return;  // the fast walk works on the chunk summary; scan_detail_kernel gathers again
     if (kLut == 2) __stcs(&reinterpret_cast<uint16_t *>(A.st_c)[(int64_t)j * A.Q + q], (uint16_t)c[j]);
-    else if (kLut) __stcs(&A.st_c[(int64_t)j * A.Q + q], c[j]);
+    else if (kLut == 1) __stcs(&A.st_c[(int64_t)j * A.Q + q], c[j]);
     else __stcs(&A.st_s[(int64_t)j * A.Q + q], v == WFX_KILL ? (int64_t)0 : v);
   };
   uint32_t live = 0;
@@ -877,6 +954,8 @@ __global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
       const uint32_t code = (uint32_t)(X >> (32 - 2 * j)) & A.kmask;  // k-mer ending at position j - 1
       if (kLut == 2) {
         v = __ldg(&A.lut[__ldg(&A.cls[code])]);
+      } else if (kLut == 3) {
+        v = rank_value(A, A.rk_bucket, __ldg(&A.rk_pos[code]), A.prm->qs);
       } else if (kLut) {
         const uint32_t c = __ldg(&A.counts[code]);
         if (c < A.lut_size) {
@@ -1123,9 +1202,10 @@ __global__ void __launch_bounds__(256) rank_eval_kernel(const uint32_t *__restri
                                                         const unsigned long long *__restrict__ seg_j0,
                                                         const double *__restrict__ seg_x0,
                                                         const double *__restrict__ seg_inc,
-                                                        double *__restrict__ ranks) {
+                                                        double *__restrict__ ranks, uint32_t *__restrict__ rk_pos) {
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
+  if (rk_pos) rk_pos[vals[p]] = (uint32_t)p;  // position of every k-mer in the rank order (scan, rank mode)
   uint32_t lo = 0, hi = ngroups;  // largest g with gstart[g] <= p
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
@@ -1235,6 +1315,25 @@ __global__ void __launch_bounds__(256) class_apply_kernel(const uint32_t *__rest
       g = lo;
     }
     cls[i] = (uint16_t)g;
+  }
+}
+
+// class table -> core records (scan_gather_kernel, core mode): record of the (k-1)-mer c = classes of a.c (a = 0..3,
+// low word) and of c.b (b = 0..3, high word), one byte each, clamped to CORE_ESCAPE
+__global__ void __launch_bounds__(256) core_apply_kernel(const uint16_t *__restrict__ cls, size_t ncore,
+                                                         uint2 *__restrict__ core) {
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncore; c += (size_t)gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const uint32_t v = cls[(size_t)a * ncore + c];
+      lo |= (v < CORE_ESCAPE ? v : CORE_ESCAPE) << (8 * a);
+    }
+    const uint2 q = *reinterpret_cast<const uint2 *>(cls + 4 * c);
+    const uint32_t b4[4] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) hi |= (b4[b] < CORE_ESCAPE ? b4[b] : CORE_ESCAPE) << (8 * b);
+    core[c] = make_uint2(lo, hi);
   }
 }
 

@@ -50,3 +50,9 @@ def test_own_arm_line():
     assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] > 0
     c = d["clocks"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(c)
+    # the timed call is parity-gated against the oracle inside the run
+    pc = d["parity_check"]
+    assert pc["ok"] and pc["counts_bit_exact"] and pc["score_table_bit_exact"] and pc["spans_identical"]
+    assert pc["rank_mode"]["ok"] and pc["call"] == "ks_dev_pipeline"
+    assert {"rank_mode", "config1", "config5_subset"} <= set(d["extra"])
+    assert d["extra"]["rank_mode"]["spans"] > 0 and d["extra"]["config1"]["ms_per_step"] > 0

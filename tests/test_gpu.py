@@ -570,7 +570,8 @@ def test_tr_lr_rejects_nan(ctx):
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_fast_and_general_paths_agree_with_oracle(ctx, oracle, mode, monkeypatch):
     """min_width >= 15 takes the summary-based walk (scan_walk_fast_kernel + scan_detail_kernel), smaller
-    widths the position-by-position walk; count-derived modes gather 2-byte classes unless disabled.
+    widths the position-by-position walk; count-derived modes gather 8-byte core records (two positions per
+    gather), 2-byte classes or 4-byte counts, depending on what is disabled.
     All combinations must give the oracle's spans."""
     rng = np.random.default_rng(6100 + mode)
     seqs = [planted(rng, 400_000), planted(rng, 30_000), rand_seq(rng, 5000, p_n=0.2)]
@@ -579,8 +580,9 @@ def test_fast_and_general_paths_agree_with_oracle(ctx, oracle, mode, monkeypatch
     for mw, ms in ((14, 2.0), (15, 2.0), (16, 0.0), (100, 5.0), (0, 8.0)):
         want = oracle.mode_regions(seqs, k, mode, mw, ms, thr=thr)
         for env in ({}, {"KS_NO_FAST_WALK": "1"}, {"KS_NO_CLASS_TABLE": "1"},
-                    {"KS_NO_FAST_WALK": "1", "KS_NO_CLASS_TABLE": "1"}):
-            for name in ("KS_NO_FAST_WALK", "KS_NO_CLASS_TABLE"):
+                    {"KS_NO_FAST_WALK": "1", "KS_NO_CLASS_TABLE": "1"}, {"KS_NO_CORE_TABLE": "1"},
+                    {"KS_NO_FAST_WALK": "1", "KS_NO_CORE_TABLE": "1"}):
+            for name in ("KS_NO_FAST_WALK", "KS_NO_CLASS_TABLE", "KS_NO_CORE_TABLE"):
                 monkeypatch.delenv(name, raising=False)
             for name, val in env.items():
                 monkeypatch.setenv(name, val)

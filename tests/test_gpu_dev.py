@@ -1,0 +1,179 @@
+"""GPU tier (-m gpu): the device-resident stage API (ks_seqset_* / ks_dev_*) -- the calls bench.py times --
+against the CPU oracle on the same seeded inputs.  Same bars as tests/test_gpu.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from kmer_spans_b200 import synth
+from tests.test_gpu import assert_spans, ctx  # noqa: F401  (fixture)
+from tests.test_oracle import planted, rand_seq
+
+pytestmark = pytest.mark.gpu
+
+
+def _tables(k):
+    import torch
+    counts = torch.zeros(4 ** k, dtype=torch.int32, device="cuda")
+    scores = torch.zeros(4 ** k, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    return counts, scores
+
+
+def _inputs(seed, big=False):
+    rng = np.random.default_rng(seed)
+    if big:
+        return [synth.genome(3_000_000, seed, n_blocks=(2, 5000)).tobytes(), planted(rng, 50_000)]
+    return [planted(rng, 120_000), b"ACGTN" * 7, planted(rng, 9_000), rand_seq(rng, 3000, p_n=0.1), b"ACG"]
+
+
+@pytest.mark.parametrize("mode,k,thr,mw,ms", [(1, 12, 0.0, 100, 20.0), (0, 12, 0.75, 100, 20.0), (2, 8, 0.0, 50, 10.0),
+                                              (0, 6, 0.5, 0, 0.0), (1, 7, 0.0, 14, 1.0), (1, 10, 0.0, 100, 20.0)])
+def test_dev_pipeline_matches_oracle(ctx, oracle, mode, k, thr, mw, ms):  # noqa: F811
+    """ks_dev_pipeline: the single call `bench.py --gpus 1` times"""
+    seqs = _inputs(7000 + k, big=(k >= 10))
+    want = oracle.mode_regions(seqs, k, mode, mw, ms, thr=thr)
+    ss = ctx.upload(seqs)
+    counts, scores = _tables(k)
+    for rep in range(2):  # the second pass runs on a packed set and warm caches of the context
+        r = ctx.dev_pipeline(ss, k, mode, mw, ms, thr=thr, d_counts=counts.data_ptr(), d_scores=scores.data_ptr(),
+                             fetch_spans=True)
+        assert r["n"] == want["n"]
+        assert (counts.cpu().numpy() == want["counts"]).all()
+        assert scores.cpu().numpy().tobytes() == want["scores"].tobytes()
+        assert r["n_spans"] == len(want["pos"])
+        assert_spans(r, want, exact_scores=(mode == 2), what="dev_pipeline mode %d k %d rep %d" % (mode, k, rep))
+    r = ctx.dev_pipeline(ss, k, mode, mw, ms, thr=thr, d_counts=counts.data_ptr(), d_scores=scores.data_ptr())
+    assert r["n_spans"] == len(want["pos"])  # fetch_spans=False (what the timed loop does)
+    ss.free()
+
+
+def test_dev_stage_calls_match_oracle(ctx, oracle):  # noqa: F811
+    """ks_dev_count -> ks_dev_scores -> ks_dev_scan_counts / ks_dev_scan, and the asynchronous pair
+    ks_dev_count_async + ks_dev_scores_devtotal that the multi-GPU composition uses"""
+    import torch
+    seqs = _inputs(7100)
+    ss = ctx.upload(seqs)
+    for k, mode, thr, mw, ms in ((8, 1, 0.0, 30, 4.0), (8, 2, 0.0, 100, 10.0), (9, 0, 0.7, 20, 2.0)):
+        want = oracle.mode_regions(seqs, k, mode, mw, ms, thr=thr)
+        counts, scores = _tables(k)
+        n = ctx.dev_count(ss, k, counts.data_ptr())
+        assert n == want["n"] and (counts.cpu().numpy() == want["counts"]).all()
+        ctx.dev_scores(k, counts.data_ptr(), n, mode, scores.data_ptr())
+        ctx.sync()
+        assert scores.cpu().numpy().tobytes() == want["scores"].tobytes()
+        if mode in (1, 2):
+            r = ctx.dev_scan_counts(ss, k, counts.data_ptr(), thr, mw, ms)
+            assert_spans(r, want, mode == 2, "dev_scan_counts mode %d" % mode)
+        r = ctx.dev_scan(ss, k, scores.data_ptr(), thr, mw, ms)
+        assert_spans(r, want, mode == 2, "dev_scan mode %d" % mode)
+        # asynchronous variant: nothing synchronised between the count kernel and the score stage
+        counts2, scores2 = _tables(k)
+        nw = torch.zeros(1, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        ctx.dev_count_async(ss, k, counts2.data_ptr(), nw.data_ptr())
+        tot = ctx.dev_scores_devtotal(k, counts2.data_ptr(), nw.data_ptr(), mode, scores2.data_ptr())
+        ctx.sync()
+        assert tot == want["n"] and int(nw.item()) == int(want["n"])
+        assert (counts2.cpu().numpy() == want["counts"]).all()
+        assert scores2.cpu().numpy().tobytes() == want["scores"].tobytes()
+        if mode in (1, 2):
+            r = ctx.dev_scan_counts(ss, k, counts2.data_ptr(), thr, mw, ms)
+            assert_spans(r, want, mode == 2, "async + dev_scan_counts mode %d" % mode)
+    ss.free()
+
+
+def test_seqset_reupload_and_wrap(ctx, oracle):  # noqa: F811
+    """ks_seqset_reupload (same device buffers, pack+count behind the copies) and ks_seqset_wrap (caller-owned
+    device buffer in the layout of ks_layout.h)"""
+    import torch
+    k, mode, mw, ms = 7, 1, 20, 3.0
+    a, b = _inputs(7200), _inputs(7201)[:3]
+    ss = ctx.upload(a)
+    counts, scores = _tables(k)
+    nw = torch.zeros(1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    for seqs in (b, a, b):
+        want = oracle.mode_regions(seqs, k, mode, mw, ms)
+        ss.reupload(seqs, k, counts.data_ptr(), nw.data_ptr())
+        tot = ctx.dev_scores_devtotal(k, counts.data_ptr(), nw.data_ptr(), mode, scores.data_ptr())
+        assert tot == want["n"]
+        assert (counts.cpu().numpy() == want["counts"]).all()
+        r = ctx.dev_scan_counts(ss, k, counts.data_ptr(), 0.0, mw, ms)
+        assert_spans(r, want, False, "reupload")
+        assert ss.bases == sum(len(s) for s in seqs)
+    ss.free()
+    # wrap: the caller lays the buffer out itself
+    seqs = a
+    lens = np.array([len(s) for s in seqs], np.int64)
+    total = 16 + int(lens.sum()) + len(seqs)
+    total = (total + 15) // 16 * 16 + 16
+    host = np.zeros(total + 64, np.uint8)
+    cur = 16
+    for s in seqs:
+        host[cur:cur + len(s)] = np.frombuffer(s, np.uint8)
+        cur += len(s) + 1
+    dbuf = torch.from_numpy(host).cuda()
+    h = C.c_void_p()
+    ctx._ck(ctx.lib.ks_seqset_wrap(ctx.h, C.c_void_p(dbuf.data_ptr()), total + 64,
+                                   lens.ctypes.data_as(C.POINTER(C.c_int64)), len(seqs), C.byref(h)))
+
+    class _SS:
+        pass
+    w = _SS()
+    w.h = h
+    want = oracle.mode_regions(seqs, k, mode, mw, ms)
+    r = ctx.dev_pipeline(w, k, mode, mw, ms, d_counts=counts.data_ptr(), d_scores=scores.data_ptr(), fetch_spans=True)
+    assert (counts.cpu().numpy() == want["counts"]).all()
+    assert_spans(r, want, False, "wrap")
+    ctx.lib.ks_seqset_free(h)
+
+
+def test_core_table_escape_classes(ctx, oracle, monkeypatch):  # noqa: F811
+    """count-derived modes gather one 8-byte core record per two positions; classes beyond the first 255
+    distinct counts take the escape through the 2-byte class table.  Small k on a long sequence gives every
+    k-mer its own count (hundreds of classes), so most positions escape."""
+    rng = np.random.default_rng(7300)
+    seqs = [planted(rng, 700_000), rand_seq(rng, 40_000, p_n=0.02)]
+    for k in (1, 4, 5, 6):
+        for mode, mw, ms in ((1, 20, 1.0), (2, 16, 4.0), (1, 3, 0.5)):
+            want = oracle.mode_regions(seqs, k, mode, mw, ms)
+            ndistinct = len(np.unique(want["counts"]))
+            got = ctx.kmer_mode_regions(seqs, k, mode, mw, ms)
+            assert_spans(got, want, mode == 2, "core k %d mode %d (%d classes)" % (k, mode, ndistinct))
+            monkeypatch.setenv("KS_NO_CORE_TABLE", "1")
+            got = ctx.kmer_mode_regions(seqs, k, mode, mw, ms)
+            monkeypatch.delenv("KS_NO_CORE_TABLE")
+            assert_spans(got, want, mode == 2, "class table k %d mode %d" % (k, mode))
+    assert ndistinct > 255
+
+
+def test_rank_position_gather_equals_rank_table_scan(ctx, oracle, monkeypatch):  # noqa: F811
+    """rank mode gathers the 4-byte position in the rank order and evaluates the linear pieces of the closed
+    form; it must agree BIT FOR BIT (scores included) with the scan that gathers the 8-byte rank table, and
+    with the oracle.  Both walks (min_width < 15 / >= 15), several k (bucket shift 0 and > 0), deep rescans."""
+    import torch
+    rng = np.random.default_rng(7400)
+    seqs = [planted(rng, 300_000), planted(rng, 20_000), rand_seq(rng, 6000, p_n=0.1), b"ACGT" * 3]
+    for k, thr, mw, ms in ((3, 0.6, 20, 2.0), (5, 0.5, 0, 0.0), (6, 0.75, 15, 1.0), (8, 0.75, 100, 5.0), (9, 0.5, 30, 2.0)):
+        want = oracle.low_comp(seqs, k, mw, ms, thr)
+        got = ctx.kmer_low_comp_regions(seqs, k, mw, ms, thr)
+        assert got["w_rank"].tobytes() == want["ranks"].tobytes()
+        assert_spans(got, want, False, "rank positions k %d thr %g" % (k, thr))
+        monkeypatch.setenv("KS_NO_RANK_POS", "1")
+        tab = ctx.kmer_low_comp_regions(seqs, k, mw, ms, thr)
+        monkeypatch.delenv("KS_NO_RANK_POS")
+        assert got["pos"].tobytes() == tab["pos"].tobytes() and got["score"].tobytes() == tab["score"].tobytes()
+    # the stage call
+    k, thr, mw, ms = 7, 0.7, 25, 2.0
+    want = oracle.low_comp(seqs, k, mw, ms, thr)
+    ss = ctx.upload(seqs)
+    counts, scores = _tables(k)
+    n = ctx.dev_count(ss, k, counts.data_ptr())
+    ctx.dev_scores(k, counts.data_ptr(), n, 0, scores.data_ptr())
+    r = ctx.dev_scan_ranks(ss, k, thr, mw, ms)
+    assert_spans(r, want, False, "dev_scan_ranks")
+    r2 = ctx.dev_scan(ss, k, scores.data_ptr(), thr, mw, ms)
+    assert r["pos"].tobytes() == r2["pos"].tobytes() and r["score"].tobytes() == r2["score"].tobytes()
+    ss.free()
+    del torch
