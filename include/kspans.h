@@ -197,6 +197,15 @@ int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double par
  * ALL shards (e.g. after an all-gather).  Spans come back with global coordinates; a span is reported
  * by the shard in which it closes. */
 typedef int (*ks_exchange_fn)(void *user, int what, const void *mine48, void *carry_in48);
+/* Shard planner + sharded upload: the layout of ALL sequences is cut into nranks contiguous chunk ranges; shard
+ * `rank` owns chunks [chunk0, chunk0 + nchunks) and keeps only bytes [win_lo, win_hi) of the layout in HBM (its
+ * range plus the head of the sequence the range starts in, where the re-scans of a span closing in the range may
+ * reach).  A window set is counted with ks_dev_count_range and scanned with ks_dev_scan*_shard; coordinates and
+ * sequence ids stay global.  Replaces the per-sequence loops of src/kmer_spans.c:592-612 across GPUs. */
+int ks_plan_shard(const int64_t *lens, int nseq, int nranks, int rank, int64_t *chunk0, int64_t *nchunks,
+                  int64_t *win_lo, int64_t *win_hi);
+int ks_seqset_upload_window(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int64_t win_lo,
+                            int64_t win_hi, ks_seqset **out);
 int64_t ks_seqset_chunks(const ks_seqset *s);
 int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, int64_t nchunks,
                        int32_t *d_counts, double *n_words);
@@ -211,6 +220,37 @@ int ks_dev_scan_ranks_shard(ks_ctx *ctx, const ks_seqset *s, int k, double thr, 
                             ks_spans *host_out_or_null, uint64_t *n_spans);
 /* host helper: carry entering shard `rank` from the 48-byte aggregates of shards 0..nranks-1 */
 int ks_fold_carry(int what, const void *all48, int nranks, int rank, void *carry_in48);
+
+/* -------- several GPUs behind one call (one process, N devices; csrc/ks_multi.inc) -----------------
+ * The reference runs its loops over all sequences of a call in one process (src/kmer_spans.c:592-601 count,
+ * :604-612 scan); ks_mctx keeps that shape on N devices: the layout of all sequences is cut into N contiguous
+ * chunk ranges (ks_plan_shard), device r uploads only its window, counts its range, the tables are summed by
+ * one kernel per device over NVLink peer memory (ordered by CUDA events), scores are derived redundantly, every
+ * device scans its range and the two 48-byte carries of all shards are folded exactly, so a span that crosses a
+ * cut comes out as from one GPU.  `devices` may repeat an index (several shards on one GPU; how the single-GPU
+ * test tier exercises this).  The R glue creates one from KSPANS_DEVICES=0,1,.... */
+typedef struct ks_mctx ks_mctx;
+int ks_mctx_create(ks_mctx **out, const int *devices, int ndev);
+void ks_mctx_destroy(ks_mctx *m);
+const char *ks_mctx_last_error(const ks_mctx *m); /* m may be NULL after a failed create */
+int ks_mctx_ndev(const ks_mctx *m);
+ks_ctx *ks_mctx_ctx(ks_mctx *m, int i); /* the per-device context (profiling, launch counts) */
+/* same arguments, results and errors as ks_kmer_counts / ks_kmer_mode_regions / ks_kmer_low_comp_regions */
+int ks_m_kmer_counts(ks_mctx *m, const char *const *seqs, const int64_t *lens, int nseq, int k,
+                     int32_t *counts_out, double *n_words);
+int ks_m_kmer_mode_regions(ks_mctx *m, const char *const *seqs, const int64_t *lens, int nseq, int k, int mode,
+                           double param, double thr, int min_width, double min_score, double *n_words,
+                           int32_t *counts_out_or_null, double *scores_out_or_null, ks_spans *out);
+int ks_m_kmer_low_comp_regions(ks_mctx *m, const char *const *seqs, const int64_t *lens, int nseq, int k,
+                               int min_width, double min_score, double thr, double n_out[2],
+                               int32_t *counts_out_or_null, double *ranks_out_or_null, ks_spans *out);
+/* resident shards: ks_m_load plans the cut and uploads every device's window; ks_m_pipeline runs count -> sum ->
+ * scores(mode) -> sharded scan on them (count_only != 0: stop after the summed count table); ks_m_tables returns
+ * the device pointers of the tables device i holds afterwards (identical on every device). */
+int ks_m_load(ks_mctx *m, const char *const *seqs, const int64_t *lens, int nseq);
+int ks_m_pipeline(ks_mctx *m, int k, int mode, double param, double thr, int min_width, double min_score,
+                  double *n_words, ks_spans *out_or_null, uint64_t *n_spans, int count_only);
+int ks_m_tables(ks_mctx *m, int i, int32_t **d_counts, double **d_scores);
 
 /* -------- timing on the launching stream (CUDA events; what bench.py reports) ---------------- */
 int ks_ctx_timer_start(ks_ctx *ctx);

@@ -70,6 +70,8 @@ SIGNATURES = {
     "ks_dev_scan_ranks": (_i, [_vp, _vp, _i, _d, _i, _d, C.POINTER(KsSpans), _pu64]),
     "ks_dev_scan_ranks_shard": (_i, [_vp, _vp, _i, _d, _i, _d, _i64, _i64, _vp, _vp, C.POINTER(KsSpans), _pu64]),
     "ks_seqset_chunks": (_i64, [_vp]),
+    "ks_plan_shard": (_i, [C.POINTER(C.c_int64), _i, _i, _i] + [C.POINTER(C.c_int64)] * 4),
+    "ks_seqset_upload_window": (_i, [_vp] + _SEQS + [_i64, _i64, C.POINTER(_vp)]),
     "ks_dev_count_range": (_i, [_vp, _vp, _i, _i64, _i64, _vp, _pd]),
     "ks_dev_scan_shard": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, _i64, _i64, _vp, _vp, C.POINTER(KsSpans), _pu64]),
     "ks_dev_scan_counts_shard": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, _i64, _i64, _vp, _vp, C.POINTER(KsSpans), _pu64]),
@@ -80,6 +82,17 @@ SIGNATURES = {
     "ks_dev_tr_lr_regions": (_i, [_vp, _vp, _i, _vp, _vp, _i, C.POINTER(KsSpans), _pu64]),
     "ks_windowed_kmer_count_distributions": (_i, [_vp] + _SEQS + [_i, _vp, _i, _i, _vp, _vp, _vp]),
     "ks_dev_window_dist": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp]),
+    "ks_mctx_create": (_i, [C.POINTER(_vp), C.POINTER(_i), _i]),
+    "ks_mctx_destroy": (None, [_vp]),
+    "ks_mctx_last_error": (C.c_char_p, [_vp]),
+    "ks_mctx_ndev": (_i, [_vp]),
+    "ks_mctx_ctx": (_vp, [_vp, _i]),
+    "ks_m_kmer_counts": (_i, [_vp] + _SEQS + [_i, _vp, _pd]),
+    "ks_m_kmer_mode_regions": (_i, [_vp] + _SEQS + [_i, _i, _d, _d, _i, _d, _pd, _vp, _vp, C.POINTER(KsSpans)]),
+    "ks_m_kmer_low_comp_regions": (_i, [_vp] + _SEQS + [_i, _i, _d, _d, _pd, _vp, _vp, C.POINTER(KsSpans)]),
+    "ks_m_load": (_i, [_vp] + _SEQS),
+    "ks_m_pipeline": (_i, [_vp, _i, _i, _d, _d, _i, _d, _pd, C.POINTER(KsSpans), _pu64, _i]),
+    "ks_m_tables": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp)]),
     "ks_seqset_positions": (_i64, [_vp]),
     "ks_seqset_start": (_i64, [_vp, _i]),
 }

@@ -109,7 +109,8 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.ks_ctx_destroy(self.h)
+            if getattr(self, "_owned", True):
+                self.lib.ks_ctx_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -410,15 +411,141 @@ class Context:
     def upload(self, seq):
         return SeqSet(self, _as_bytes_list(seq))
 
+    def upload_window(self, seq, win_lo, win_hi):
+        """only bytes [win_lo, win_hi) of the layout of these sequences (one shard, see plan_shard)"""
+        return SeqSet(self, _as_bytes_list(seq), window=(int(win_lo), int(win_hi)))
+
+    def dev_scan_ranks_shard(self, ss, k, thr, min_w, min_score, chunk0, nchunks, exchange):
+        """rank-mode scan of one shard (rank order of the last dev_scores(mode RANK) on this context)"""
+        def cb(user, what, mine, carry):
+            try:
+                out = exchange(int(what), C.string_at(mine, 48))
+                C.memmove(carry, out, 48)
+                return 0
+            except Exception:  # pragma: no cover - surfaced as a C-side error
+                import traceback
+                traceback.print_exc()
+                return 1
+        cfn = _lib.EXCHANGE_FN(cb)
+        ns = C.c_uint64(0)
+        sp = KsSpans()
+        self._ck(self.lib.ks_dev_scan_ranks_shard(self.h, ss.h, int(k), float(thr), int(min_w), float(min_score),
+                                                  int(chunk0), int(nchunks), C.cast(cfn, C.c_void_p), None,
+                                                  C.byref(sp), C.byref(ns)))
+        pos, score = _spans_to_numpy(self.lib, sp)
+        return dict(n_spans=int(ns.value), pos=pos, score=score)
+
+
+class MultiContext:
+    """Several GPUs behind one call (ks_mctx): one process, N devices, sharded upload, count tables summed over
+    peer memory, scan carries folded exactly.  devices may repeat an index (several shards on one GPU)."""
+
+    def __init__(self, devices):
+        self.lib = _lib.load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.ks_mctx_create(C.byref(h), devs, len(devices))
+        if rc:
+            raise KspansError(rc, self.lib.ks_mctx_last_error(None).decode())
+        self.h = h
+        self.ndev = len(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ks_mctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise KspansError(rc, self.lib.ks_mctx_last_error(self.h).decode())
+
+    def device_context(self, i):
+        """borrowed view of the per-device context (profiling, launch counts); do not close it"""
+        c = Context.__new__(Context)
+        c.lib = self.lib
+        c._owned = False
+        c.h = C.c_void_p(self.lib.ks_mctx_ctx(self.h, int(i)))
+        return c
+
+    def kmer_counts(self, seq, k, with_f=True):
+        a = _SeqArgs(_as_bytes_list(seq))
+        k = int(k)
+        counts = np.zeros(4 ** k if 1 <= k <= 15 else 1, np.int32)
+        n = C.c_double(0)
+        self._ck(self.lib.ks_m_kmer_counts(self.h, a.ptrs, a.lens, a.n, k, counts.ctypes.data, C.byref(n)))
+        out = dict(n=np.array([k, n.value]), counts=counts)
+        if with_f:
+            out["f"] = counts / counts.sum()
+        return out
+
+    def kmer_mode_regions(self, seq, k, mode, min_w, min_score, thr=0.0, param=float("nan"), want_tables=True):
+        a = _SeqArgs(_as_bytes_list(seq))
+        k = int(k)
+        ok = 1 <= k <= 15
+        counts = np.zeros(4 ** k, np.int32) if want_tables and ok else None
+        scores = np.zeros(4 ** k, np.float64) if want_tables and ok else None
+        n = C.c_double(0)
+        sp = KsSpans()
+        self._ck(self.lib.ks_m_kmer_mode_regions(
+            self.h, a.ptrs, a.lens, a.n, k, int(mode), float(param), float(thr), int(min_w), float(min_score),
+            C.byref(n), counts.ctypes.data if counts is not None else None,
+            scores.ctypes.data if scores is not None else None, C.byref(sp)))
+        pos, score = _spans_to_numpy(self.lib, sp)
+        return dict(n=n.value, counts=counts, scores=scores, pos=pos, score=score)
+
+    def kmer_low_comp_regions(self, seq, k, min_w, min_score, thr=0.75, want_tables=True):
+        a = _SeqArgs(_as_bytes_list(seq))
+        k = int(k)
+        ok = 1 <= k <= 15
+        counts = np.zeros(4 ** k, np.int32) if want_tables and ok else None
+        ranks = np.zeros(4 ** k, np.float64) if want_tables and ok else None
+        n = (C.c_double * 2)()
+        sp = KsSpans()
+        self._ck(self.lib.ks_m_kmer_low_comp_regions(
+            self.h, a.ptrs, a.lens, a.n, k, int(min_w), float(min_score), float(thr), n,
+            counts.ctypes.data if counts is not None else None, ranks.ctypes.data if ranks is not None else None,
+            C.byref(sp)))
+        pos, score = _spans_to_numpy(self.lib, sp)
+        return dict(n=np.array([n[0], n[1]]), counts=counts, w_rank=ranks, pos=pos, score=score)
+
+    def load(self, seq):
+        a = _SeqArgs(_as_bytes_list(seq))
+        self._ck(self.lib.ks_m_load(self.h, a.ptrs, a.lens, a.n))
+
+    def pipeline(self, k, mode, min_w, min_score, thr=0.0, param=float("nan"), fetch_spans=False, count_only=False):
+        n, ns, sp = C.c_double(0), C.c_uint64(0), KsSpans()
+        self._ck(self.lib.ks_m_pipeline(self.h, int(k), int(mode), float(param), float(thr), int(min_w),
+                                        float(min_score), C.byref(n), C.byref(sp) if fetch_spans else None,
+                                        C.byref(ns), 1 if count_only else 0))
+        res = dict(n=n.value, n_spans=int(ns.value))
+        if fetch_spans:
+            res["pos"], res["score"] = _spans_to_numpy(self.lib, sp)
+        return res
+
+    def tables(self, i=0):
+        """device pointers (int32 counts, double scores) of the tables device i holds after pipeline()"""
+        c, s = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.ks_m_tables(self.h, int(i), C.byref(c), C.byref(s)))
+        return c.value, s.value
+
 
 class SeqSet:
     """Sequences resident in HBM (ks_seqset)."""
 
-    def __init__(self, ctx, seqs):
+    def __init__(self, ctx, seqs, window=None):
         self.ctx = ctx
         a = _SeqArgs(seqs)
         h = C.c_void_p()
-        ctx._ck(ctx.lib.ks_seqset_upload(ctx.h, a.ptrs, a.lens, a.n, C.byref(h)))
+        if window is None:
+            ctx._ck(ctx.lib.ks_seqset_upload(ctx.h, a.ptrs, a.lens, a.n, C.byref(h)))
+        else:
+            ctx._ck(ctx.lib.ks_seqset_upload_window(ctx.h, a.ptrs, a.lens, a.n, window[0], window[1], C.byref(h)))
         self.h = h
         self.bases = int(ctx.lib.ks_seqset_bases(h))
         self.chunks = int(ctx.lib.ks_seqset_chunks(h))
@@ -453,6 +580,17 @@ class SeqSet:
             self.free()
         except Exception:
             pass
+
+
+def plan_shard(lens, nranks, rank):
+    """(chunk0, nchunks, win_lo, win_hi) of shard `rank` of `nranks` for sequences of these lengths (ks_plan_shard)"""
+    lens = np.ascontiguousarray(lens, np.int64)
+    out = [C.c_int64(0) for _ in range(4)]
+    rc = _lib.load().ks_plan_shard(lens.ctypes.data_as(C.POINTER(C.c_int64)), len(lens), int(nranks), int(rank),
+                                   *[C.byref(o) for o in out])
+    if rc:
+        raise KspansError(rc, "ks_plan_shard: bad arguments")
+    return tuple(int(o.value) for o in out)
 
 
 def fold_carry(what, blobs, rank):

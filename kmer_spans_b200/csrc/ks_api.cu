@@ -23,6 +23,7 @@
 
 #include "../../include/kspans.h"
 #include "ks_kernels.cuh"
+#include "ks_count.cuh"
 #include "ks_layout.h"
 #include "ks_rankseg.h"
 #include "ks_sort.cuh"
@@ -128,6 +129,14 @@ struct ks_seqset {
   ks_ctx *ctx = nullptr;
   uint8_t *d_buf = nullptr;  // layout of ks_layout.h
   bool owned = false;
+  // A WINDOW set keeps only bytes [win_lo, win_hi) of the layout in HBM (one shard of a multi-GPU run: its own
+  // range plus the head of the sequence the range starts in).  d_buf / d_pk / d_brk are then VIRTUAL bases
+  // (allocation - offset), so every kernel keeps addressing by global position; *_alloc are the allocations.
+  int64_t win_lo = 0, win_hi = 0;
+  bool window = false;
+  uint8_t *buf_alloc = nullptr;
+  uint32_t *pk_alloc = nullptr;
+  uint16_t *brk_alloc = nullptr;
   int64_t total = 0;         // bytes of the layout (multiple of 16)
   int64_t bases = 0;
   int nseq = 0;
@@ -172,6 +181,8 @@ struct ks_ctx {
   void *pinned = nullptr;
   size_t pinned_cap = 0;
   DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, pending, foc_hist, foc_big;
+  DBuf bk_buf, bk_cursor;  // bucketed counting (ks_count.cuh): sub-keys per bucket, fill of every bucket
+  bool smem_attr_set = false;
   DBuf win_match, win_cnt, win_pre, win_scratch, win_codes, win_fix, win_hist, win_pos;
   DBuf st_aux, child_pk, child_c, child_count, tr_tables;
   DBuf st_mn, st_mx, st_bm, detail, detail_count;
@@ -362,7 +373,8 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->win_match, &ctx->win_cnt, &ctx->win_pre, &ctx->win_scratch, &ctx->win_codes, &ctx->win_fix,
                  &ctx->win_hist, &ctx->win_pos, &ctx->st_aux, &ctx->child_pk, &ctx->child_c, &ctx->child_count,
                  &ctx->tr_tables, &ctx->st_mn, &ctx->st_mx, &ctx->st_bm, &ctx->detail, &ctx->detail_count,
-                 &ctx->cls, &ctx->cls_dense, &ctx->core, &ctx->rk_pos, &ctx->rk_p0, &ctx->rk_bucket};
+                 &ctx->cls, &ctx->cls_dense, &ctx->core, &ctx->rk_pos, &ctx->rk_p0, &ctx->rk_bucket,
+                 &ctx->bk_buf, &ctx->bk_cursor};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -441,9 +453,113 @@ int ks_kmer_seq(int k, uint64_t code, char *out) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// stage: count.  Three ways to count (ks_count.cuh): shared-memory table (k <= 7), 1024 buckets through shared
+// memory (8 <= k <= 12), direct global reductions (k >= 13 in slices of the table, and inputs too small to pay
+// for the extra launches).  KS_COUNT_PATH = direct | smem | bucket forces one (tests, measurements).
+namespace {
+enum { COUNT_DIRECT = 0, COUNT_SMEM = 1, COUNT_BUCKET = 2 };
+struct CountRun {
+  int path = COUNT_DIRECT;
+  int k = 0;
+  int32_t *d_counts = nullptr;
+  uint32_t kmask = 0, gcap = 0;
+  int sub_bits = 0, nparts = 1, part_shift = 32;
+};
+}  // namespace
+
+// zeroes the table, the word count and (bucket path) the bucket fills; est_chunks sizes the bucket regions
+static int count_begin(ks_ctx *ctx, int k, int32_t *d_counts, int64_t est_chunks, CountRun *run) {
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)1 << (2 * k);
+  run->k = k;
+  run->d_counts = d_counts;
+  run->kmask = (uint32_t)(n - 1);
+  count_parts(k, &run->nparts, &run->part_shift);
+  int path = COUNT_DIRECT;
+  if (k <= 7 && est_chunks >= (1 << 14)) path = COUNT_SMEM;
+  else if (k >= 8 && k <= 12 && est_chunks >= (1 << 18)) path = COUNT_BUCKET;
+  if (const char *e = getenv("KS_COUNT_PATH")) {
+    if (!strcmp(e, "direct")) path = COUNT_DIRECT;
+    else if (!strcmp(e, "smem") && k <= 7) path = COUNT_SMEM;
+    else if (!strcmp(e, "bucket") && k >= 5 && k <= 12) path = COUNT_BUCKET;
+  }
+  run->path = path;
+  if (!ctx->smem_attr_set) {
+    CK(cudaFuncSetAttribute(pack_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    CK(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SCATTER_SMEM));
+    CK(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    ctx->smem_attr_set = true;
+  }
+  CK(ctx->nwords.ensure(sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(d_counts, 0, n * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
+  if (path == COUNT_BUCKET) {
+    run->sub_bits = 2 * k - BK_LOG;
+    uint64_t per = (uint64_t)(est_chunks > 0 ? est_chunks : 1) * 16 / BK_BUCKETS;
+    uint64_t gcap = per + per / 2 + per / 8 + 8192;  // 12 % granule padding + spectrum skew; the rest overflows to direct
+    if (const char *e = getenv("KS_BUCKET_CAP")) gcap = (uint64_t)atoll(e);  // tests: force the overflow path
+    gcap = (gcap + 7) & ~7ull;
+    if (gcap < 8) gcap = 8;
+    if (gcap > 0xfffffff0ull) return ctx->fail(KS_ERR_ARG, "input too large for the bucketed count");
+    run->gcap = (uint32_t)gcap;
+    CK(ctx->bk_buf.ensure((size_t)gcap * BK_BUCKETS * 2));
+    CK(ctx->bk_cursor.ensure(BK_BUCKETS * 4));
+    CK(cudaMemsetAsync(ctx->bk_cursor.p, 0, BK_BUCKETS * 4, st));
+  }
+  return KS_OK;
+}
+
+// chunks [first, first + nchunks) of the set: pack them and count (or scatter) their k-mers
+static int count_chunks(ks_ctx *ctx, const ks_seqset *s, const CountRun &run, int64_t first, int64_t nchunks) {
+  if (nchunks <= 0) return KS_OK;
+  cudaStream_t st = ctx->stream;
+  unsigned long long *nw = ctx->nwords.as<unsigned long long>();
+  if (run.path == COUNT_SMEM) {
+    const size_t smem = (size_t)4 << (2 * run.k);
+    const unsigned per_sm = smem > 32768 ? 3u : 6u;
+    const unsigned grid = (unsigned)std::min<size_t>((size_t)148 * per_sm, (size_t)((nchunks + 1023) / 1024));
+    pack_count_smem_kernel<<<grid, 256, smem, st>>>(s->d_buf, first, nchunks, run.k, run.kmask, s->d_pk, s->d_brk,
+                                                   run.d_counts, nw);
+  } else if (run.path == COUNT_BUCKET) {
+    const int64_t ntiles = (nchunks + BK_TILE_CHUNKS - 1) / BK_TILE_CHUNKS;
+    const unsigned grid = (unsigned)std::min<int64_t>(148 * 4, ntiles);
+    bucket_scatter_kernel<<<grid, BK_THREADS, BK_SCATTER_SMEM, st>>>(
+        s->d_buf, first, nchunks, run.k, run.kmask, s->d_pk, s->d_brk, run.d_counts, nw,
+        ctx->bk_buf.as<uint16_t>(), ctx->bk_cursor.as<uint32_t>(), run.gcap, run.sub_bits);
+  } else {
+    pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
+        s->d_buf, first, nchunks, run.k, run.kmask, s->d_pk, s->d_brk, run.d_counts, nw, run.part_shift, 0u);
+  }
+  LAUNCHED(1);
+  CK(cudaGetLastError());
+  return KS_OK;
+}
+
+// after the last count_chunks: phase 2 of the bucket path, or the remaining table slices of the direct path over
+// all chunks [first, first + nchunks) that were counted
+static int count_end(ks_ctx *ctx, const ks_seqset *s, const CountRun &run, int64_t first, int64_t nchunks) {
+  cudaStream_t st = ctx->stream;
+  if (run.path == COUNT_BUCKET) {
+    bucket_count_kernel<<<BK_BUCKETS, BK_COUNT_THREADS, (size_t)4 << run.sub_bits, st>>>(
+        ctx->bk_buf.as<uint16_t>(), ctx->bk_cursor.as<uint32_t>(), run.gcap, run.sub_bits, run.d_counts);
+    LAUNCHED(1);
+  } else if (run.path == COUNT_DIRECT && nchunks > 0) {
+    for (int part = 1; part < run.nparts; ++part) {  // tables beyond L2: one pass over the sequence per slice
+      pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
+          s->d_buf, first, nchunks, run.k, run.kmask, s->d_pk, s->d_brk, run.d_counts,
+          ctx->nwords.as<unsigned long long>(), run.part_shift, (uint32_t)part);
+      LAUNCHED(1);
+    }
+  }
+  CK(cudaGetLastError());
+  return KS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // sequence sets
 // (re)initialise a set for these lengths; device buffers only grow
-static int seqset_prepare(ks_ctx *ctx, const int64_t *lens, int nseq, ks_seqset *s, bool own_buffer) {
+static int seqset_prepare(ks_ctx *ctx, const int64_t *lens, int nseq, ks_seqset *s, bool own_buffer,
+                          int64_t win_lo = 0, int64_t win_hi = -1) {
   s->ctx = ctx;
   s->nseq = nseq;
   s->packed = false;
@@ -463,30 +579,43 @@ static int seqset_prepare(ks_ctx *ctx, const int64_t *lens, int nseq, ks_seqset 
   }
   CK(cudaMemcpyAsync(s->d_starts, s->starts.data(), sizeof(int64_t) * ((size_t)nseq + 1),
                      cudaMemcpyHostToDevice, ctx->stream));
-  size_t nch = (size_t)(s->total / 16) + 8;
+  if (win_hi < 0 || win_hi > s->total) win_hi = s->total;
+  if (win_lo < 0) win_lo = 0;
+  win_lo &= ~15ll;
+  win_hi = (win_hi + 15) & ~15ll;
+  if (win_hi > s->total) win_hi = s->total;
+  if (win_lo >= win_hi) { win_lo = 0; win_hi = 16; }  // an empty shard keeps the front pad only
+  s->win_lo = win_lo;
+  s->win_hi = win_hi;
+  s->window = !(win_lo == 0 && win_hi == s->total);
+  if (s->window && !own_buffer) return ctx->fail(KS_ERR_ARG, "a wrapped buffer cannot be a window set");
+  size_t nch = (size_t)((win_hi - win_lo) / 16) + 8;
   if (nch > s->cap_chunks) {
-    if (s->d_pk) cudaFree(s->d_pk);
-    if (s->d_brk) cudaFree(s->d_brk);
-    s->d_pk = nullptr; s->d_brk = nullptr;
+    if (s->pk_alloc) cudaFree(s->pk_alloc);
+    if (s->brk_alloc) cudaFree(s->brk_alloc);
+    s->pk_alloc = nullptr; s->brk_alloc = nullptr;
     s->cap_chunks = nch + nch / 8;
-    CK(cudaMalloc(&s->d_pk, s->cap_chunks * sizeof(uint32_t)));
-    CK(cudaMalloc(&s->d_brk, s->cap_chunks * sizeof(uint16_t)));
+    CK(cudaMalloc(&s->pk_alloc, s->cap_chunks * sizeof(uint32_t)));
+    CK(cudaMalloc(&s->brk_alloc, s->cap_chunks * sizeof(uint16_t)));
   }
-  // beyond the data every position is a break; the pack pass overwrites chunks [0, total/16)
-  CK(cudaMemsetAsync(s->d_brk + (nch - 8), 0xff, 8 * sizeof(uint16_t), ctx->stream));
-  CK(cudaMemsetAsync(s->d_pk + (nch - 8), 0, 8 * sizeof(uint32_t), ctx->stream));
+  s->d_pk = s->pk_alloc - win_lo / 16;
+  s->d_brk = s->brk_alloc - win_lo / 16;
+  // beyond the data every position is a break; the pack pass overwrites the resident chunks
+  CK(cudaMemsetAsync(s->brk_alloc + (nch - 8), 0xff, 8 * sizeof(uint16_t), ctx->stream));
+  CK(cudaMemsetAsync(s->pk_alloc + (nch - 8), 0, 8 * sizeof(uint32_t), ctx->stream));
   if (own_buffer) {
-    size_t need = (size_t)s->total + KS_SLACK;
+    size_t need = (size_t)(win_hi - win_lo) + KS_SLACK;
     if (need > s->cap_buf) {
-      if (s->d_buf && s->owned) cudaFree(s->d_buf);
-      s->d_buf = nullptr;
+      if (s->buf_alloc && s->owned) cudaFree(s->buf_alloc);
+      s->buf_alloc = nullptr;
       s->cap_buf = need + need / 8;
-      if (cudaMalloc(&s->d_buf, s->cap_buf) != cudaSuccess) {
+      if (cudaMalloc(&s->buf_alloc, s->cap_buf) != cudaSuccess) {
         cudaGetLastError();
         s->cap_buf = 0;
         return ctx->fail(KS_ERR_NOMEM, "cudaMalloc(%lld) failed", (long long)need);
       }
     }
+    s->d_buf = s->buf_alloc - win_lo;
     s->owned = true;
   }
   return KS_OK;
@@ -514,18 +643,16 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
   int rc = ensure_copy_stream(ctx);
   if (rc) return rc;
   cudaStream_t cs = ctx->copy_stream, st = ctx->stream;
-  const size_t nk = count_k ? ((size_t)1 << (2 * count_k)) : 0;
   CK(cudaEventRecord(ctx->ev_compute, st));       // the buffers may still be read by earlier work
   CK(cudaStreamWaitEvent(cs, ctx->ev_compute, 0));
-  CK(cudaMemsetAsync(s->d_buf, 0, (size_t)s->total + KS_SLACK, cs));
-  if (count_k) {
-    CK(ctx->nwords.ensure(sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(d_counts, 0, nk * sizeof(int32_t), st));
-    CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
-  }
+  CK(cudaMemsetAsync(s->d_buf + s->win_lo, 0, (size_t)(s->win_hi - s->win_lo) + KS_SLACK, cs));
+  if (s->window && count_k) return ctx->fail(KS_ERR_ARG, "a window set is counted by range (ks_dev_count_range)");
   const int64_t nchunks = (s->total - 16) / 16;
-  int cparts = 1, cparts_shift = 32;
-  if (count_k) count_parts(count_k, &cparts, &cparts_shift);
+  CountRun run;
+  if (count_k) {
+    rc = count_begin(ctx, count_k, d_counts, nchunks, &run);
+    if (rc) return rc;
+  }
   int64_t done = 0;  // chunks [0, done) of the count grid are launched
   const int64_t SLAB = (24ll << 20) / 16;
   auto progress = [&](int64_t covered, bool final) -> cudaError_t {
@@ -538,13 +665,10 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
     if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(st, ctx->ev_copy, 0);
     if (e2 != cudaSuccess) return e2;
     cudaEvent_t pe = ctx->prof_begin();
-    pack_count_kernel<true><<<grid_for((size_t)(avail - done), 256, 148u * 8u), 256, 0, st>>>(
-        s->d_buf, done, avail - done, count_k, (uint32_t)(nk - 1), s->d_pk, s->d_brk, d_counts,
-        ctx->nwords.as<unsigned long long>(), cparts_shift, 0u);
+    const int crc = count_chunks(ctx, s, run, done, avail - done);
     ctx->prof_end(KS_PROF_COUNT, pe);
-    ctx->launches += 1;
     done = avail;
-    return cudaGetLastError();
+    return crc ? cudaErrorUnknown : cudaSuccess;
   };
   // large sequences go straight from the caller's memory; small ones are packed into pinned
   // staging windows (two halves, alternating) so that 100k contigs do not cost 100k copies
@@ -605,6 +729,31 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
   for (int i = 0; i < nseq && e == cudaSuccess; ++i) {
     int64_t ln = lens[i];
     if (ln == 0) continue;
+    if (s->window) {
+      // only the part of the sequence inside the window travels; plain copies (a shard holds few sequences)
+      const int64_t a = std::max<int64_t>(s->starts[i], s->win_lo), b = std::min<int64_t>(s->starts[i] + ln, s->win_hi);
+      if (a >= b) continue;
+      if (!host_ptr_is_pinned(seqs[i])) {
+        e = flush();
+        const size_t SUB = 1u << 20;
+        for (int64_t off = a - s->starts[i]; off < b - s->starts[i] && e == cudaSuccess;) {
+          if (fill == HALF) { e = flush(); if (e != cudaSuccess) break; }
+          if (fill == 0) win_start = s->starts[i] + off;
+          size_t room = HALF - fill;
+          size_t take = (size_t)(b - s->starts[i] - off) < room ? (size_t)(b - s->starts[i] - off) : room;
+          for (size_t q = 0; q < take; q += SUB)
+            items.push_back({seqs[i] + off + (int64_t)q, take - q < SUB ? take - q : SUB, fill + q, false});
+          fill += take;
+          off += (int64_t)take;
+        }
+        if (e == cudaSuccess) e = flush();
+      } else {
+        e = flush();
+        if (e == cudaSuccess)
+          e = cudaMemcpyAsync(s->d_buf + a, seqs[i] + (a - s->starts[i]), (size_t)(b - a), cudaMemcpyHostToDevice, cs);
+      }
+      continue;
+    }
     if (ln >= DIRECT && !host_ptr_is_pinned(seqs[i])) {
       // a long sequence in pageable memory (what R hands over): the driver would stage it at a few GB/s;
       // packed into the pinned windows by the host threads it moves near the PCIe rate
@@ -647,12 +796,10 @@ static int upload_impl(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
   if (e == cudaSuccess) e = progress(s->total, true);
   if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copy, cs);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->ev_copy, 0);  // later kernels see the whole buffer
-  for (int part = 1; part < cparts && e == cudaSuccess; ++part) {  // tables beyond L2: remaining slices
-    pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
-        s->d_buf, 0, nchunks, count_k, (uint32_t)(nk - 1), s->d_pk, s->d_brk, d_counts,
-        ctx->nwords.as<unsigned long long>(), cparts_shift, (uint32_t)part);
-    ctx->launches += 1;
-    e = cudaGetLastError();
+  if (e == cudaSuccess && count_k) {  // phase 2 of the bucket path / remaining table slices beyond L2
+    cudaEvent_t pe = ctx->prof_begin();
+    if (count_end(ctx, s, run, 0, nchunks)) e = cudaErrorUnknown;
+    ctx->prof_end(KS_PROF_COUNT, pe);
   }
   if (e == cudaSuccess && ev_used[0]) e = cudaEventSynchronize(ev[0]);  // staging halves are re-used next call
   if (e == cudaSuccess && ev_used[1]) e = cudaEventSynchronize(ev[1]);
@@ -682,6 +829,60 @@ int ks_seqset_upload(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, 
   KS_CATCH(ctx)
 }
 
+// One shard of a multi-GPU run: the layout of ALL sequences cut into nranks contiguous ranges of
+// chunks; shard `rank` counts and scans chunks [chunk0, chunk0 + nchunks) and keeps bytes [win_lo, win_hi) of the
+// layout resident: its own range plus the head of the sequence the range starts in (a span that closes in the
+// range may have started there, and its re-scans run on this shard) and one chunk of slack behind it.
+int ks_plan_shard(const int64_t *lens, int nseq, int nranks, int rank, int64_t *chunk0, int64_t *nchunks,
+                  int64_t *win_lo, int64_t *win_hi) {
+  KS_TRY
+  if (!lens || nseq < 1 || nranks < 1 || rank < 0 || rank >= nranks) return KS_ERR_ARG;
+  std::vector<int64_t> starts((size_t)nseq + 1);
+  const int64_t total = ks_layout_total(lens, nseq, starts.data());
+  const int64_t chunks = (total - 16) / 16;
+  const int64_t per = (chunks + nranks - 1) / nranks;
+  const int64_t c0 = std::min<int64_t>((int64_t)rank * per, chunks);
+  const int64_t cn = std::min<int64_t>(per, chunks - c0);
+  if (chunk0) *chunk0 = c0;
+  if (nchunks) *nchunks = cn;
+  int64_t lo = 0, hi = 16;
+  if (cn > 0) {
+    const int64_t first_pos = 16 * c0 + 16;  // first position of the range
+    size_t i = (size_t)(std::upper_bound(starts.begin(), starts.begin() + nseq, first_pos) - starts.begin());
+    i = i ? i - 1 : 0;                       // the sequence that holds it (or the one before a separator)
+    lo = std::min<int64_t>(16 * c0, (starts[i] & ~15ll) - 16);
+    if (lo < 0) lo = 0;
+    hi = std::min<int64_t>(total, 16 * (c0 + cn) + 48);
+  }
+  if (win_lo) *win_lo = lo;
+  if (win_hi) *win_hi = hi;
+  return KS_OK;
+  KS_CATCH(((ks_ctx *)nullptr))
+}
+
+// Upload only bytes [win_lo, win_hi) of the layout of these sequences (a window set; see ks_plan_shard).  The set
+// is counted with ks_dev_count_range and scanned with ks_dev_scan*_shard on chunk ranges inside the window; span
+// coordinates and sequence ids stay global.
+int ks_seqset_upload_window(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int64_t win_lo,
+                            int64_t win_hi, ks_seqset **out) {
+  KS_TRY
+  if (!ctx) return KS_ERR_ARG;
+  if (!out || !seqs || !lens || nseq < 1)
+    return ctx->fail(KS_ERR_ARG, "seq_r must be a character vector of length at least one");
+  CK(cudaSetDevice(ctx->device));
+  ks_seqset *s = new ks_seqset();
+  int rc = seqset_prepare(ctx, lens, nseq, s, true, win_lo, win_hi);
+  if (!rc) rc = upload_impl(ctx, s, seqs, lens, nseq, 0, nullptr);
+  if (!rc) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = ctx->fail(KS_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
+  }
+  if (rc) { ks_seqset_free(s); return rc; }
+  *out = s;
+  return KS_OK;
+  KS_CATCH(ctx)
+}
+
 // Upload new sequences into an existing set (device buffers are re-used, they only grow).  With count_k > 0
 // the pack+count pass runs behind the copies (d_counts is overwritten) and the word count is left at
 // d_nwords (device uint64, may be NULL).  Nothing is synchronised: pinned host buffers must stay valid until
@@ -693,6 +894,7 @@ int ks_seqset_reupload(ks_ctx *ctx, ks_seqset *s, const char *const *seqs, const
   if (!s || !seqs || !lens || nseq < 1)
     return ctx->fail(KS_ERR_ARG, "seq_r must be a character vector of length at least one");
   if (!s->owned && s->d_buf) return ctx->fail(KS_ERR_ARG, "ks_seqset_reupload: the set wraps a caller-owned buffer");
+  if (s->window) return ctx->fail(KS_ERR_ARG, "ks_seqset_reupload: not for window sets");
   if (count_k) {
     int rc = check_k(ctx, count_k);
     if (rc) return rc;
@@ -731,6 +933,7 @@ int ks_seqset_wrap(ks_ctx *ctx, const void *d_buf, int64_t total_bytes, const in
                      (long long)(s->total + KS_SLACK));
   }
   s->d_buf = (uint8_t *)d_buf;
+  s->buf_alloc = nullptr;
   s->owned = false;
   CK(cudaStreamSynchronize(ctx->stream));
   *out = s;
@@ -741,10 +944,10 @@ int ks_seqset_wrap(ks_ctx *ctx, const void *d_buf, int64_t total_bytes, const in
 void ks_seqset_free(ks_seqset *s) {
   if (!s) return;
   if (s->ctx) cudaSetDevice(s->ctx->device);
-  if (s->owned && s->d_buf) cudaFree(s->d_buf);
+  if (s->owned && s->buf_alloc) cudaFree(s->buf_alloc);
   if (s->d_starts) cudaFree(s->d_starts);
-  if (s->d_pk) cudaFree(s->d_pk);
-  if (s->d_brk) cudaFree(s->d_brk);
+  if (s->pk_alloc) cudaFree(s->pk_alloc);
+  if (s->brk_alloc) cudaFree(s->brk_alloc);
   delete s;
 }
 int64_t ks_seqset_bases(const ks_seqset *s) { return s ? s->bases : 0; }
@@ -756,10 +959,13 @@ int64_t ks_seqset_start(const ks_seqset *s, int seq) { return (s && seq >= 0 && 
 // pack only (no counting pass ran on this set)
 static int ensure_packed(ks_ctx *ctx, const ks_seqset *s) {
   if (s->packed) return KS_OK;
-  int64_t nch = (s->total - 16) / 16;
+  const int64_t c0 = s->win_lo / 16;
+  int64_t nch = (s->win_hi - 16) / 16 - c0;
+  if (nch < 0) nch = 0;
   cudaEvent_t pe = ctx->prof_begin();
-  pack_count_kernel<false><<<grid_for((size_t)nch, 256, 148u * 8u), 256, 0, ctx->stream>>>(
-      s->d_buf, 0, nch, 1, 3u, s->d_pk, s->d_brk, nullptr, nullptr);
+  if (nch)
+    pack_count_kernel<false><<<grid_for((size_t)nch, 256, 148u * 8u), 256, 0, ctx->stream>>>(
+        s->d_buf, c0, nch, 1, 3u, s->d_pk, s->d_brk, nullptr, nullptr);
   ctx->prof_end(KS_PROF_COUNT, pe);
   LAUNCHED(1);
   CK(cudaGetLastError());
@@ -783,24 +989,17 @@ static int dev_count_impl(ks_ctx *ctx, const ks_seqset *s, int k, int32_t *d_cou
   if (rc) return rc;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  size_t n = (size_t)1 << (2 * k);
-  CK(ctx->nwords.ensure(sizeof(unsigned long long)));
-  CK(cudaMemsetAsync(d_counts, 0, n * sizeof(int32_t), st));
-  CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
+  if (s->window) return ctx->fail(KS_ERR_ARG, "a window set is counted by range (ks_dev_count_range)");
   int64_t nchunks = (s->total - 16) / 16;
+  CountRun run;
+  rc = count_begin(ctx, k, d_counts, nchunks, &run);
+  if (rc) return rc;
   cudaEvent_t pe = ctx->prof_begin();
-  int nparts, part_shift;
-  count_parts(k, &nparts, &part_shift);
-  for (int part = 0; part < nparts; ++part) {
-    pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
-        s->d_buf, 0, nchunks, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, d_counts,
-        ctx->nwords.as<unsigned long long>(), part_shift, (uint32_t)part);
-    LAUNCHED(part ? 1 : 0);
-  }
+  rc = count_chunks(ctx, s, run, 0, nchunks);
+  if (!rc) rc = count_end(ctx, s, run, 0, nchunks);
   ctx->prof_end(KS_PROF_COUNT, pe);
+  if (rc) return rc;
   s->packed = true;
-  LAUNCHED(1);
-  CK(cudaGetLastError());
   if (!sync) return KS_OK;
   unsigned long long nw = 0;
   CK(cudaMemcpyAsync(&nw, ctx->nwords.p, sizeof nw, cudaMemcpyDeviceToHost, st));
@@ -864,33 +1063,29 @@ int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, i
   if (rc) return rc;
   const int64_t total = (s->total - 16) / 16;
   if (chunk0 < 0 || nchunks < 0 || chunk0 + nchunks > total) return ctx->fail(KS_ERR_ARG, "chunk range outside the buffer");
+  if (s->window && nchunks && (16 * chunk0 < s->win_lo || 16 * (chunk0 + nchunks) + 16 > s->win_hi))
+    return ctx->fail(KS_ERR_ARG, "chunk range outside the resident window of the set");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   size_t n = (size_t)1 << (2 * k);
-  CK(ctx->nwords.ensure(sizeof(unsigned long long)));
-  CK(cudaMemsetAsync(d_counts, 0, n * sizeof(int32_t), st));
-  CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
+  CountRun run;
+  rc = count_begin(ctx, k, d_counts, nchunks, &run);
+  if (rc) return rc;
   cudaEvent_t pe = ctx->prof_begin();
-  if (nchunks) {
-    int nparts, part_shift;
-    count_parts(k, &nparts, &part_shift);
-    for (int part = 0; part < nparts; ++part) {
-      pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
-          s->d_buf, chunk0, nchunks, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, d_counts,
-          ctx->nwords.as<unsigned long long>(), part_shift, (uint32_t)part);
+  rc = count_chunks(ctx, s, run, chunk0, nchunks);
+  if (!rc) rc = count_end(ctx, s, run, chunk0, nchunks);
+  if (rc) return rc;
+  if (!s->packed) {  // the scan of every shard reads packed data beyond its own range: pack the rest of what is resident
+    const int64_t r0 = s->win_lo / 16, r1 = std::max<int64_t>(r0, (s->win_hi - 16) / 16);
+    const int64_t a1 = std::min<int64_t>(chunk0, r1), b0 = std::max<int64_t>(chunk0 + nchunks, r0);
+    if (a1 > r0) {
+      pack_count_kernel<false><<<grid_for((size_t)(a1 - r0), 256, 148u * 8u), 256, 0, st>>>(
+          s->d_buf, r0, a1 - r0, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, nullptr, nullptr);
       LAUNCHED(1);
     }
-  }
-  if (!s->packed) {  // the scan of every shard reads packed data beyond its own range: pack the rest
-    if (chunk0 > 0) {
-      pack_count_kernel<false><<<grid_for((size_t)chunk0, 256, 148u * 8u), 256, 0, st>>>(
-          s->d_buf, 0, chunk0, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, nullptr, nullptr);
-      LAUNCHED(1);
-    }
-    if (chunk0 + nchunks < total) {
-      pack_count_kernel<false><<<grid_for((size_t)(total - chunk0 - nchunks), 256, 148u * 8u), 256, 0, st>>>(
-          s->d_buf, chunk0 + nchunks, total - chunk0 - nchunks, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, nullptr,
-          nullptr);
+    if (r1 > b0) {
+      pack_count_kernel<false><<<grid_for((size_t)(r1 - b0), 256, 148u * 8u), 256, 0, st>>>(
+          s->d_buf, b0, r1 - b0, k, (uint32_t)(n - 1), s->d_pk, s->d_brk, nullptr, nullptr);
       LAUNCHED(1);
     }
   }
@@ -1329,9 +1524,12 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
   unsigned long long rec_total = 0;    // records after the last completed level
   int64_t nseg = 0, total_chunks = dense_chunks;
   int64_t dense_chunk0 = 0;
+  if (s->window && !sh) return ctx->fail(KS_ERR_ARG, "a window set is scanned by shard (ks_dev_scan*_shard)");
   if (sh) {
     if (sh->chunk0 < 0 || sh->nchunks < 0 || sh->chunk0 + sh->nchunks > dense_chunks)
       return ctx->fail(KS_ERR_ARG, "shard range outside the buffer");
+    if (s->window && sh->nchunks && (16 * sh->chunk0 < s->win_lo || 16 * (sh->chunk0 + sh->nchunks) + 16 > s->win_hi))
+      return ctx->fail(KS_ERR_ARG, "shard range outside the resident window of the set");
     dense_chunk0 = sh->chunk0;
     total_chunks = sh->nchunks;
     CK(ctx->launch_rec.ensure(256));
@@ -1395,6 +1593,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.seg_len = ctx->seg_len.as<int64_t>();
     A.seg_chunk0 = ctx->seg_chunk0.as<uint64_t>();
     A.dense_start = 16 + 16 * dense_chunk0;
+    A.pad_p0 = s->win_lo + 16;
     A.total_chunks = total_chunks;
     A.dense_first = dense_chunk0 == 0;
     const bool exchange = sh && level == 0;
@@ -2367,3 +2566,5 @@ int ks_kmer_scores(ks_ctx *ctx, int k, const int32_t *counts, double total, int 
 }
 
 }  // extern "C"
+
+#include "ks_multi.inc"

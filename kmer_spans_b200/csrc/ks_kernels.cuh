@@ -126,7 +126,9 @@ __global__ void __launch_bounds__(256) pack_count_kernel(const uint8_t *__restri
     if (part_id == 0) {
       pk_out[ci + 1] = pkc;
       brk_out[ci + 1] = (uint16_t)bc;
-      if (ci == 0) { pk_out[0] = pkp; brk_out[0] = (uint16_t)bp; }
+      // the chunk in front of the launch's first one has no thread of its own (chunk 0 of the buffer, or the
+      // first resident chunk of a window set)
+      if (ci == first) { pk_out[ci] = pkp; brk_out[ci] = (uint16_t)bp; }
     }
     if (kCount) {
       uint32_t next = __ldg(p + 32);
@@ -288,6 +290,7 @@ struct LevelArgs {
   // level 0 (nseg == 0): dense pass over [dense_start, dense_start + 16 * total_chunks); dense_first = the
   // range starts the buffer (state 0); otherwise it continues a previous shard (carry-in S_start, E_start)
   int64_t dense_start;
+  int64_t pad_p0;  // position padding chunks decode (16, or the first chunk of a window set)
   int64_t total_chunks;
   int dense_first;
   int32_t *inscan;  // or NULL
@@ -430,19 +433,31 @@ scan_gather_kernel(const LevelArgs A) {
   __shared__ int64_t s_lut[kCore ? CORE_ESCAPE : 1];  // scores of the classes a core record can name
   __shared__ uint32_t s_bucket[kLut == 3 ? RK_BUCKETS + 1 : 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // small tables that go to shared memory: the loads are issued here, the stores (and the barrier) wait until the
+  // gathers are in flight, so their latency hides behind the gathers instead of opening every CTA
+  constexpr int LUT_PER = kCore ? (int)(CORE_ESCAPE + TILE_THREADS - 1) / TILE_THREADS : 1;
+  constexpr int BKT_PER = kLut == 3 ? (RK_BUCKETS + 1 + TILE_THREADS - 1) / TILE_THREADS : 1;
+  int64_t pre_lut[LUT_PER];
+  uint32_t pre_bkt[BKT_PER];
   if (kCore) {
-    for (int i = tid; i < (int)CORE_ESCAPE; i += TILE_THREADS) s_lut[i] = (uint32_t)i < A.lut_size ? __ldg(&A.lut[i]) : 0;
-    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < LUT_PER; ++i) {
+      const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
+      pre_lut[i] = (e < CORE_ESCAPE && e < A.lut_size) ? __ldg(&A.lut[e]) : 0;
+    }
   }
   if (kLut == 3) {
-    for (int i = tid; i <= RK_BUCKETS; i += TILE_THREADS) s_bucket[i] = __ldg(&A.rk_bucket[i]);
-    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < BKT_PER; ++i) {
+      const int e = tid + i * TILE_THREADS;
+      pre_bkt[i] = e <= RK_BUCKETS ? __ldg(&A.rk_bucket[e]) : 0u;
+    }
   }
   const int rk_qs = kLut == 3 ? A.prm->qs : 0;
   const int64_t tile = blockIdx.x;
   // ---- chunk -> position mapping ----
   const int64_t q = tile * TILE_THREADS + tid;
-  int64_t p0 = 16;
+  int64_t p0 = A.pad_p0;  // padding chunks behind the last real one read a position that is always resident
   int n_in = 0;
   bool head = true;
   if (q < A.total_chunks) {
@@ -530,6 +545,22 @@ scan_gather_kernel(const LevelArgs A) {
   } else {
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) sv[j] = (scored & (1u << j)) ? ldg_s64_keep(&A.wfx[code[j]], keep) : WFX_KILL;
+  }
+  if (kCore) {
+#pragma unroll
+    for (int i = 0; i < LUT_PER; ++i) {
+      const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
+      if (e < CORE_ESCAPE) s_lut[e] = pre_lut[i];
+    }
+    __syncthreads();
+  }
+  if (kLut == 3) {
+#pragma unroll
+    for (int i = 0; i < BKT_PER; ++i) {
+      const int e = tid + i * TILE_THREADS;
+      if (e <= RK_BUCKETS) s_bucket[e] = pre_bkt[i];
+    }
+    __syncthreads();
   }
   // value of a SCORED position (WFX_KILL = the table says "force the state to 0")
   auto value = [&](int j) -> int64_t {

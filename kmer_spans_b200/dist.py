@@ -241,13 +241,16 @@ def shard_range(total_chunks, world, rank):
 
 
 def run_split(ctx, seqs, k, mode, min_w, min_score, thr, param, rank, world, all_gather_bytes, all_reduce_counts):
-    """count(range) -> all_reduce -> scores -> sharded scan with carry exchange.
+    """count(range) -> all_reduce -> scores -> sharded scan with carry exchange.  Every rank plans the same cut of
+    the layout of ALL sequences (ks_plan_shard) and uploads only its window: its own range plus the head of the
+    sequence the range starts in.
     all_gather_bytes(blob48) -> [blob48 of every rank];  all_reduce_counts(torch int32 tensor, n) -> total n.
     Returns this rank's spans (global coordinates; a span is reported where it closes)."""
     import torch
     from . import api
-    ss = ctx.upload(seqs)
-    c0, cn = shard_range(ss.chunks, world, rank)
+    lens = [len(s) for s in seqs]
+    c0, cn, lo, hi = api.plan_shard(lens, world, rank)
+    ss = ctx.upload_window(seqs, lo, hi)
     dev = torch.device("cuda", torch.cuda.current_device())
     counts = torch.zeros(4 ** k, dtype=torch.int32, device=dev)
     scores = torch.empty(4 ** k, dtype=torch.float64, device=dev)
@@ -260,25 +263,33 @@ def run_split(ctx, seqs, k, mode, min_w, min_score, thr, param, rank, world, all
     def exchange(what, mine):
         return api.fold_carry(what, all_gather_bytes(mine), rank)
 
-    use_counts = mode in (1, 2)
-    r = ctx.dev_scan_shard(ss, k, counts.data_ptr() if use_counts else scores.data_ptr(), thr, min_w, min_score,
-                           c0, cn, exchange, use_counts=use_counts)
+    if mode == 0:  # rank order left on the context by dev_scores: 4-byte position gather
+        r = ctx.dev_scan_ranks_shard(ss, k, thr, min_w, min_score, c0, cn, exchange)
+    else:
+        use_counts = mode in (1, 2)
+        r = ctx.dev_scan_shard(ss, k, counts.data_ptr() if use_counts else scores.data_ptr(), thr, min_w, min_score,
+                               c0, cn, exchange, use_counts=use_counts)
     r["n"] = total
     r["counts"] = counts
+    r["window_bytes"] = hi - lo
     ss.free()
     return r
 
 
 def run_split_nccl(ctx, dist, seqs, k, mode, min_w, min_score, thr=0.0, param=float("nan"), gather=True):
-    """run_split with torch.distributed: NCCL all_reduce of the count table, the two 48-byte carries
-    through all_gather_object (host side, once each per scan)."""
+    """run_split with torch.distributed: NCCL all_reduce of the count table, the two 48-byte carries through
+    an NCCL all-gather of a device tensor (once each per scan)."""
     import torch
     rank, world = dist.get_rank(), dist.get_world_size()
 
-    def all_gather_bytes(b):
-        out = [None] * world
-        dist.all_gather_object(out, b)
-        return out
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gathered = torch.empty(48 * world, dtype=torch.uint8, device=dev)
+
+    def all_gather_bytes(b):  # 48-byte carries through one NCCL all-gather of a device tensor
+        mine = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(dev)
+        dist.all_gather_into_tensor(gathered, mine)
+        flat = gathered.cpu().numpy().tobytes()
+        return [flat[48 * i:48 * (i + 1)] for i in range(world)]
 
     def all_reduce_counts(t, n):
         nt = torch.tensor([n], dtype=torch.float64, device=t.device)

@@ -23,11 +23,11 @@ def _tables(k):
 def _inputs(seed, big=False):
     rng = np.random.default_rng(seed)
     if big:
-        return [synth.genome(3_000_000, seed, n_blocks=(2, 5000)).tobytes(), planted(rng, 50_000)]
+        return [synth.genome(6_000_000, seed, n_blocks=(2, 5000)).tobytes(), planted(rng, 50_000)]
     return [planted(rng, 120_000), b"ACGTN" * 7, planted(rng, 9_000), rand_seq(rng, 3000, p_n=0.1), b"ACG"]
 
 
-@pytest.mark.parametrize("mode,k,thr,mw,ms", [(1, 12, 0.0, 100, 20.0), (0, 12, 0.75, 100, 20.0), (2, 8, 0.0, 50, 10.0),
+@pytest.mark.parametrize("mode,k,thr,mw,ms", [(1, 11, 0.0, 100, 20.0), (0, 12, 0.75, 100, 20.0), (2, 8, 0.0, 50, 10.0),
                                               (0, 6, 0.5, 0, 0.0), (1, 7, 0.0, 14, 1.0), (1, 10, 0.0, 100, 20.0)])
 def test_dev_pipeline_matches_oracle(ctx, oracle, mode, k, thr, mw, ms):  # noqa: F811
     """ks_dev_pipeline: the single call `bench.py --gpus 1` times"""
@@ -177,3 +177,164 @@ def test_rank_position_gather_equals_rank_table_scan(ctx, oracle, monkeypatch): 
     assert r["pos"].tobytes() == r2["pos"].tobytes() and r["score"].tobytes() == r2["score"].tobytes()
     ss.free()
     del torch
+
+
+@pytest.mark.parametrize("path", ["direct", "smem", "bucket"])
+def test_count_paths_match_oracle(ctx, oracle, path, monkeypatch):  # noqa: F811
+    """the three counting kernels (direct global reductions, shared-memory table for k <= 7, 1024 buckets through
+    shared memory for 8 <= k <= 12) on ragged inputs, IUPAC bytes, poly-A / tandem arrays (staging rows overflow
+    into the direct reduction) and with bucket regions forced to overflow"""
+    monkeypatch.setenv("KS_COUNT_PATH", path)
+    rng = np.random.default_rng(7500)
+    ks = {"direct": (2, 8, 11), "smem": (1, 3, 7), "bucket": (5, 8, 10, 12)}[path]
+    for k in ks:
+        for trial in range(3):
+            seqs = [rand_seq(rng, int(rng.integers(0, 40000)), p_n=float(rng.choice([0, 0.02, 0.3])),
+                             alphabet=rng.choice([b"ACGT", b"ACGTacgtRYKMSWBDHVUu-*."]))
+                    for _ in range(int(rng.integers(1, 6)))]
+            seqs += [b"A" * 70000, b"ACG" * 20000, b"ACGTACGTACGTACGTACGT"[:k], b"", b"N" * 40,
+                     planted(rng, 150_000)]
+            n1, c1 = oracle.kmer_counts(seqs, k)
+            g = ctx.kmer_counts(seqs, k, with_f=False)
+            assert g["n"][1] == n1 and (g["counts"] == c1).all(), (path, k, trial)
+    if path == "bucket":
+        monkeypatch.setenv("KS_BUCKET_CAP", "64")  # almost everything overflows the bucket regions
+        seqs = [planted(rng, 300_000), b"AC" * 50000]
+        for k in (8, 12):
+            n1, c1 = oracle.kmer_counts(seqs, k)
+            g = ctx.kmer_counts(seqs, k, with_f=False)
+            assert g["n"][1] == n1 and (g["counts"] == c1).all(), ("overflow", k)
+
+
+def test_count_paths_default_selection_large(ctx, oracle):  # noqa: F811
+    """inputs large enough for the default selection to take the bucketed path (>= 2^18 chunks) at k = 8, 10, 12,
+    through the resident-set call, the sharded range call and the upload-with-count path"""
+    import torch
+    seq = synth.genome(6_000_000, 77, n_blocks=(3, 4000)).tobytes()
+    seqs = [seq, b"ACGTTGCA" * 1000]
+    ss = ctx.upload(seqs)
+    for k in (8, 10, 12):
+        n1, c1 = oracle.kmer_counts(seqs, k)
+        counts, _ = _tables(k)
+        assert ctx.dev_count(ss, k, counts.data_ptr()) == n1
+        assert (counts.cpu().numpy() == c1).all(), k
+        g = ctx.kmer_counts(seqs, k, with_f=False)  # upload + count behind the copies, slab by slab
+        assert g["n"][1] == n1 and (g["counts"] == c1).all(), k
+        # two ranges of the same set (what a 2-GPU split counts) add up to the whole
+        half = ss.chunks // 2
+        a, b = _tables(k)[0], _tables(k)[0]
+        na = ctx.dev_count_range(ss, k, 0, half, a.data_ptr())
+        nb = ctx.dev_count_range(ss, k, half, ss.chunks - half, b.data_ptr())
+        assert na + nb == n1 and ((a + b).cpu().numpy() == c1).all(), k
+    ss.free()
+    del torch
+
+
+def _virtual_split(seqs, k, mode, thr, mw, ms, world):
+    """run_split with `world` virtual ranks on one GPU (one Context and one thread each; carries and tables meet
+    at a barrier as they would in an all-gather / all-reduce)"""
+    import threading
+    import torch
+    from kmer_spans_b200 import api
+    from kmer_spans_b200 import dist as ksd
+    ctxs = [api.Context() for _ in range(world)]
+    barrier = threading.Barrier(world)
+    blobs, tables, ns, out, errs = [None] * world, [None] * world, [0.0] * world, [None] * world, []
+
+    def worker(r):
+        try:
+            def all_gather_bytes(b):
+                blobs[r] = b
+                barrier.wait()
+                got = list(blobs)
+                barrier.wait()
+                return got
+
+            def all_reduce_counts(t, n):
+                tables[r], ns[r] = t, n
+                barrier.wait()
+                if r == 0:
+                    tot = torch.stack(tables).sum(0).to(torch.int32)
+                    for x in tables:
+                        x.copy_(tot)
+                    torch.cuda.synchronize()
+                barrier.wait()
+                return float(sum(ns))
+
+            out[r] = ksd.run_split(ctxs[r], seqs, k, mode, mw, ms, thr, float("nan"), r, world, all_gather_bytes,
+                                   all_reduce_counts)
+        except threading.BrokenBarrierError:
+            pass  # another rank failed first; its error is the one to report
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            errs.append("rank %d: %r\n%s" % (r, e, traceback.format_exc()))
+            barrier.abort()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(300)
+    assert not errs, "\n".join(errs)
+    pos, score = ksd.merge_spans([(o["pos"], o["score"]) for o in out])
+    counts = out[0]["counts"].cpu().numpy()
+    windows = [o["window_bytes"] for o in out]
+    for c in ctxs:
+        c.close()
+    return dict(pos=pos, score=score, counts=counts, n=out[0]["n"], windows=windows)
+
+
+def test_config3_scaled_sharded_equals_oracle(ctx, oracle):  # noqa: F811
+    """BASELINE.json configs[2] scaled down (24 human-like sequences, weighted rank, thr 0.75) cut across 8 and 5
+    virtual GPUs at arbitrary chunk boundaries, every shard holding only its window of the layout: count table,
+    and all spans must equal the CPU oracle run on the whole set.  Also log2 mode and a deep-rescan threshold."""
+    seqs = [s.tobytes() for s in synth.config3(scale=0.0012)]  # 3.7 Mb in 24 sequences
+    total_bytes = sum(len(s) for s in seqs)
+    for world, k, mode, thr, mw, ms in ((8, 10, 0, 0.75, 100, 20.0), (5, 8, 0, 0.5, 30, 3.0), (8, 9, 1, 0.0, 100, 20.0)):
+        want = oracle.mode_regions(seqs, k, mode, mw, ms, thr=thr)
+        got = _virtual_split(seqs, k, mode, thr, mw, ms, world)
+        assert got["n"] == want["n"] and (got["counts"] == want["counts"]).all()
+        assert len(want["pos"]) > 20
+        assert_spans(got, want, False, "config 3 scaled, world %d k %d mode %d" % (world, k, mode))
+        # sharded residency: a shard keeps its range plus at most the head of one sequence
+        assert max(got["windows"]) < total_bytes / world + max(len(s) for s in seqs) + 4096
+
+
+@pytest.mark.parametrize("ndev", [2, 3, 8])
+def test_multi_device_context_matches_oracle(oracle, ndev):
+    """ks_mctx: several shards behind ONE C-ABI call (here all on GPU 0: the device list may repeat an index),
+    through the same entry points as the single-GPU path -- sharded upload, per-shard counts summed by the
+    peer-memory kernel, scores per device, scan carries folded at the host barrier, spans merged"""
+    from kmer_spans_b200 import api
+    rng = np.random.default_rng(7600 + ndev)
+    m = api.MultiContext([0] * ndev)
+    seqs = [planted(rng, 90_000), planted(rng, 7_000), b"ACGTN" * 5, planted(rng, 41_000), b"AC", rand_seq(rng, 9000, p_n=0.1)]
+    for k, thr, mw, ms in ((6, 0.6, 10, 3.0), (9, 0.75, 100, 5.0), (4, 0.5, 0, 0.0)):
+        want = oracle.low_comp(seqs, k, mw, ms, thr)
+        got = m.kmer_low_comp_regions(seqs, k, mw, ms, thr)
+        assert (got["n"] == want["n"]).all() and (got["counts"] == want["counts"]).all()
+        assert got["w_rank"].tobytes() == want["ranks"].tobytes()
+        assert_spans(got, want, False, "mctx rank k %d ndev %d" % (k, ndev))
+    for mode, k, mw, ms in ((1, 7, 20, 2.0), (2, 8, 50, 10.0), (3, 5, 15, 1.0)):
+        param = 0.6 if mode == 3 else float("nan")
+        want = oracle.mode_regions(seqs, k, mode, mw, ms, param=param)
+        got = m.kmer_mode_regions(seqs, k, mode, mw, ms, param=param)
+        assert got["n"] == want["n"] and (got["counts"] == want["counts"]).all()
+        assert got["scores"].tobytes() == want["scores"].tobytes()
+        assert_spans(got, want, mode == 2, "mctx mode %d ndev %d" % (mode, ndev))
+    n1, c1 = oracle.kmer_counts(seqs, 10)
+    g = m.kmer_counts(seqs, 10, with_f=False)
+    assert g["n"][1] == n1 and (g["counts"] == c1).all()
+    # resident shards, repeated passes (what a benchmark times)
+    m.load(seqs)
+    want = oracle.mode_regions(seqs, 8, 1, 30, 4.0)
+    for rep in range(2):
+        r = m.pipeline(8, 1, 30, 4.0, fetch_spans=True)
+        assert r["n"] == want["n"]
+        assert_spans(r, want, False, "mctx resident rep %d" % rep)
+    # errors keep their text and leave the context usable
+    with pytest.raises(api.KspansError, match="threshold must be between 0 and 1"):
+        m.kmer_low_comp_regions(seqs, 6, 10, 1.0, 1.5)
+    got = m.kmer_low_comp_regions(seqs, 6, 10, 3.0, 0.6)
+    assert_spans(got, oracle.low_comp(seqs, 6, 10, 3.0, 0.6), False, "after error")
+    m.close()
