@@ -14,6 +14,10 @@
  *
  * Argument checks, their order and the error texts follow the reference; result lists have the
  * same element order and types (the R wrappers name them positionally, kmer_spans.R:21,50,75).
+ * Several GPUs: with KSPANS_DEVICES=0,1,... (two or more entries) kmer_counts, kmer_low_comp_regions and
+ * kmer_mode_regions run on a ks_mctx -- one process, the sequences of the call sharded over the listed devices,
+ * count tables summed over NVLink peer memory, spans that cross a cut stitched exactly (include/kspans.h).  The
+ * other entry points use the first listed device.
  * CUDA is initialised lazily inside the first call (never at dyn.load) and re-initialised in a
  * forked child (mclapply), see SURVEY.md section 8b.  error() is only raised after every ks_*
  * resource has been released: nothing longjmps across the CUDA library.
@@ -34,8 +38,44 @@
 #define GLUE_MAX_K 16
 
 static ks_ctx *g_ctx = NULL;
-static pid_t g_pid = 0;
+static ks_mctx *g_mctx = NULL;
+static pid_t g_pid = 0, g_mpid = 0;
 static char g_msg[600];
+
+/* device list of KSPANS_DEVICES ("0,1,2"); returns the number of entries (0: unset) */
+static int glue_devices(int *dev, int cap) {
+  const char *e = getenv("KSPANS_DEVICES");
+  int n = 0;
+  if (!e) return 0;
+  while (*e && n < cap) {
+    char *end = NULL;
+    long v = strtol(e, &end, 10);
+    if (end == e) break;
+    dev[n++] = (int)v;
+    e = (*end == ',') ? end + 1 : end;
+    if (*end && *end != ',') break;
+  }
+  return n;
+}
+
+/* multi-device context of this process when KSPANS_DEVICES names two or more devices, else NULL with g_msg
+ * empty; NULL with g_msg set = creation failed */
+static ks_mctx *glue_mctx(void) {
+  int dev[16];
+  g_msg[0] = 0;
+  int n = glue_devices(dev, 16);
+  if (n < 2) return NULL;
+  pid_t me = getpid();
+  if (g_mctx && g_mpid == me) return g_mctx;
+  g_mctx = NULL; /* inherited through fork(): unusable, not ours to destroy */
+  if (ks_mctx_create(&g_mctx, dev, n) != KS_OK) {
+    snprintf(g_msg, sizeof g_msg, "kmer_spans (CUDA): %s", ks_mctx_last_error(NULL));
+    g_mctx = NULL;
+    return NULL;
+  }
+  g_mpid = me;
+  return g_mctx;
+}
 
 /* context of this process, created on first use; a forked child gets its own */
 static ks_ctx *glue_ctx(void) {
@@ -45,6 +85,10 @@ static ks_ctx *glue_ctx(void) {
   int dev = -1;
   const char *e = getenv("KSPANS_DEVICE");
   if (e && *e) dev = atoi(e);
+  else {
+    int list[16];
+    if (glue_devices(list, 16) >= 1) dev = list[0];
+  }
   if (ks_ctx_create(&g_ctx, dev) != KS_OK) {
     snprintf(g_msg, sizeof g_msg, "kmer_spans (CUDA): %s", ks_last_error(NULL));
     g_ctx = NULL;
@@ -98,9 +142,13 @@ SEXP kmer_counts(SEXP seq_r, SEXP k_r) {
   int *counts = INTEGER(VECTOR_ELT(ret, 1));
   seq_view v;
   int ok = view_strsxp(seq_r, &v);
-  ks_ctx *ctx = ok ? glue_ctx() : NULL;
+  ks_mctx *mc = ok ? glue_mctx() : NULL;
+  ks_ctx *ctx = (ok && !mc && !g_msg[0]) ? glue_ctx() : NULL;
   int rc = KS_ERR_NOMEM;
-  if (ok && ctx) {
+  if (ok && mc) {
+    rc = ks_m_kmer_counts(mc, v.ptr, v.len, v.n, k, (int32_t *)counts, n_counts);
+    if (rc) snprintf(g_msg, sizeof g_msg, "%s", ks_mctx_last_error(mc));
+  } else if (ok && ctx) {
     rc = ks_kmer_counts(ctx, v.ptr, v.len, v.n, k, (int32_t *)counts, n_counts);
     if (rc) fail_from_ctx(ctx);
   } else if (!ok) {
@@ -196,9 +244,14 @@ SEXP kmer_low_comp_regions(SEXP seq_r, SEXP k_r, SEXP min_width_r, SEXP min_scor
   seq_view v;
   ks_spans sp = {NULL, NULL, 0};
   int ok = view_strsxp(seq_r, &v);
-  ks_ctx *ctx = ok ? glue_ctx() : NULL;
+  ks_mctx *mc = ok ? glue_mctx() : NULL;
+  ks_ctx *ctx = (ok && !mc && !g_msg[0]) ? glue_ctx() : NULL;
   int rc = KS_ERR_NOMEM;
-  if (ok && ctx) {
+  if (ok && mc) {
+    rc = ks_m_kmer_low_comp_regions(mc, v.ptr, v.len, v.n, k, min_width, min_score, threshold, n_counts,
+                                    (int32_t *)INTEGER(VECTOR_ELT(ret, 1)), REAL(VECTOR_ELT(ret, 2)), &sp);
+    if (rc) snprintf(g_msg, sizeof g_msg, "%s", ks_mctx_last_error(mc));
+  } else if (ok && ctx) {
     rc = ks_kmer_low_comp_regions(ctx, v.ptr, v.len, v.n, k, min_width, min_score, threshold, n_counts,
                                   (int32_t *)INTEGER(VECTOR_ELT(ret, 1)), REAL(VECTOR_ELT(ret, 2)), &sp);
     if (rc) fail_from_ctx(ctx);
@@ -258,9 +311,15 @@ SEXP kmer_mode_regions(SEXP seq_r, SEXP k_r, SEXP mode_r, SEXP param_r, SEXP thr
   seq_view v;
   ks_spans sp = {NULL, NULL, 0};
   int ok = view_strsxp(seq_r, &v);
-  ks_ctx *ctx = ok ? glue_ctx() : NULL;
+  ks_mctx *mc = ok ? glue_mctx() : NULL;
+  ks_ctx *ctx = (ok && !mc && !g_msg[0]) ? glue_ctx() : NULL;
   int rc = KS_ERR_NOMEM;
-  if (ok && ctx) {
+  if (ok && mc) {
+    rc = ks_m_kmer_mode_regions(mc, v.ptr, v.len, v.n, k, INTEGER(mode_r)[0], REAL(param_r)[0], REAL(thr_r)[0],
+                                INTEGER(min_width_r)[0], REAL(min_score_r)[0], REAL(VECTOR_ELT(ret, 0)),
+                                (int32_t *)INTEGER(VECTOR_ELT(ret, 1)), want ? REAL(VECTOR_ELT(ret, 2)) : NULL, &sp);
+    if (rc) snprintf(g_msg, sizeof g_msg, "%s", ks_mctx_last_error(mc));
+  } else if (ok && ctx) {
     rc = ks_kmer_mode_regions(ctx, v.ptr, v.len, v.n, k, INTEGER(mode_r)[0], REAL(param_r)[0], REAL(thr_r)[0],
                               INTEGER(min_width_r)[0], REAL(min_score_r)[0], REAL(VECTOR_ELT(ret, 0)),
                               (int32_t *)INTEGER(VECTOR_ELT(ret, 1)), want ? REAL(VECTOR_ELT(ret, 2)) : NULL, &sp);

@@ -139,3 +139,28 @@ def test_call_results_match_reference(glue, ref):
     out = glue.call_raw("kmer_mode_regions", [("s", seqs), ("i", 7), ("i", 1), ("d", float("nan")), ("d", 0.0),
                                               ("i", 10), ("d", 3.0), ("i", 1)])
     assert len(out) == 5 and out[1].size == 4 ** 7 and out[2].size == 4 ** 7
+
+
+@pytest.mark.gpu
+def test_call_results_on_several_devices(glue, ref, monkeypatch):
+    """KSPANS_DEVICES with two or more entries: the .Call entry points run on a ks_mctx (here three shards on
+    GPU 0) and must return what the reference's own glue returns on the same mock SEXPs"""
+    monkeypatch.setenv("KSPANS_DEVICES", "0,0,0")
+    rng = np.random.default_rng(2025)
+    for trial in range(4):
+        k = int(rng.choice([3, 6, 9]))
+        seqs = [planted(rng, int(rng.integers(2000, 60000))) for _ in range(int(rng.integers(1, 6)))]
+        if trial % 2:
+            seqs.insert(1, b"AC"[: k - 1])
+        a, b = ref.call_kmer_counts(seqs, k), glue.call_kmer_counts(seqs, k)
+        assert a["n"] == b["n"] and (a["counts"] == b["counts"]).all()
+        thr, mw, ms = float(rng.choice([0.5, 0.75])), int(rng.choice([0, 10, 40])), float(rng.choice([0, 3, 10]))
+        a = ref.call_kmer_low_comp_regions(seqs, k, mw, ms, thr)
+        b = glue.call_kmer_low_comp_regions(seqs, k, mw, ms, thr)
+        assert (a["n"] == b["n"]).all() and (a["counts"] == b["counts"]).all()
+        assert a["ranks"].tobytes() == b["ranks"].tobytes()
+        assert a["pos"].tolist() == b["pos"].tolist()
+        np.testing.assert_allclose(b["score"], a["score"], rtol=1e-9)
+    # an argument error raised by the multi-device path keeps the reference's text
+    with pytest.raises(Exception, match="threshold must be between 0 and 1"):
+        glue.call_kmer_low_comp_regions(seqs, 4, 10, 1.0, 1.5)
