@@ -241,6 +241,100 @@ def parity_check(args, ctx, stages, seq_host, rank, world, dist, torch):
     return rec
 
 
+def config3_record(args, stages, rank, world, dist, torch, barrier):
+    """BASELINE.json configs[2]: 24 human-like chromosomes (3.083 Gb at scale 1), k = 13, weighted rank, thr 0.75,
+    ONE set cut across the N GPUs at chunk boundaries (strong scaling): sharded residency (every rank generates
+    and uploads only the chromosomes its window touches), count tables summed across the GPUs, scan carries
+    exchanged, spans that cross a cut stitched exactly.  Before the timed passes the same code path is checked
+    against the CPU oracle on the set scaled to 1 %."""
+    from kmer_spans_b200 import api, synth
+    from kmer_spans_b200 import dist as ksd
+    dev = stages.device
+    element = synth.random_bases(np.random.default_rng(0xE1E), 300)
+
+    def build(scale, want_all=False):
+        lens = [int(mb * 1_000_000 * scale) for mb in synth.HUMAN_MB]
+        c0, cn, lo, hi = api.plan_shard(lens, world, rank)
+        starts = 16 + np.concatenate([[0], np.cumsum(np.array(lens[:-1]) + 1)])
+        data = {}
+        for i, (s0, ln) in enumerate(zip(starts, lens)):
+            if want_all or (s0 < hi and s0 + ln > lo):
+                data[i] = synth.genome(ln, 100 + i, element=element)
+        return lens, data
+
+    d = dist if world > 1 else None
+    K3, THR3 = 13, 0.75
+    # ---- parity of this code path on the scaled set (k = 12 keeps the oracle's sort short) ----
+    lens_p, data_p = build(0.01, want_all=(rank == 0))
+    run = ksd.SplitRun(stages, d, api.SparseSeqs(lens_p, data_p))
+    got = run.step(12, 0, THR3, MIN_W, MIN_SCORE)
+    parts = [(got["pos"], got["score"])]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (got["pos"], got["score"]))
+    ok = True
+    n_par = 0
+    if rank == 0:
+        from oracle.ksoracle import Oracle
+        want = Oracle().low_comp([data_p[i].tobytes() for i in range(len(lens_p))], 12, MIN_W, MIN_SCORE, THR3)
+        pos, score = ksd.merge_spans(parts)
+        ok = (bool((stages.counts.cpu().numpy() == want["counts"]).all())
+              and stages.scores.cpu().numpy().tobytes() == want["ranks"].tobytes()
+              and pos.tolist() == want["pos"].tolist()
+              and bool(np.allclose(score, want["score"], rtol=1e-9, atol=0)))
+        n_par = len(want["pos"])
+    run.free()
+    del data_p
+    # ---- the timed workload ----
+    lens, data = build(args.config3_scale)
+    seqs = api.SparseSeqs(lens, data)
+    run = ksd.SplitRun(stages, d, seqs)
+    for _ in range(2):
+        r = run.step(K3, 0, THR3, MIN_W, MIN_SCORE)
+    reps = 3
+    stages.ctx.set_profile(True)
+    stages.ctx.profile(reset=True)
+    barrier()
+    stages.ctx.timer_start()
+    for _ in range(reps):
+        r = run.step(K3, 0, THR3, MIN_W, MIN_SCORE)
+    ms = stages.ctx.timer_stop() / reps
+    barrier()
+    prof = stages.ctx.profile(reset=True)
+    stages.ctx.set_profile(False)
+    # end to end: the window goes up again from (pageable) host memory, spans come back
+    barrier()
+    t0 = time.perf_counter()
+    run.reload()
+    r = run.step(K3, 0, THR3, MIN_W, MIN_SCORE)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([ms, e2e_s, float(len(r["pos"])), float(run.hi - run.lo)], dtype=torch.float64, device=dev)
+    mx = t.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    bases = run.bases
+    run.free()
+    nk = 4 ** K3
+    peak, _ = measured_peak()
+    ms_max, e2e_max = float(mx[0].item()), float(mx[1].item())
+    alg = 1.5 * bases / world + 16.0 * nk  # per GPU: its share of the sequence, the whole table
+    return {"workload": "BASELINE.json configs[2]: 24 human-like sequences, %.3f Gb, k=13, weighted rank thr 0.75, "
+                        "min_width 100, min_score 20; one set cut across %d GPU(s) (strong scaling)"
+                        % (bases / 1e9, world),
+            "scale": args.config3_scale, "bases": bases, "n_gpus": world, "ms_per_step": ms_max,
+            "gbases_per_s": bases / (ms_max * 1e-3) / 1e9,
+            "e2e_ms": e2e_max * 1e3, "e2e_gbases_per_s": bases / e2e_max / 1e9,
+            "e2e_source": "pageable host memory, every rank uploads only its window",
+            "spans": int(t[2].item()), "max_window_bytes_per_gpu": int(mx[3].item()),
+            "roofline_frac_per_gpu": alg / (ms_max * 1e-3) / 1e9 / peak,
+            "kernels_ms_per_step_rank0": {nm: tot / reps for nm, (tot, n) in prof.items() if n},
+            "parity_check": {"ok": bool(ok), "scale": 0.01, "k": 12, "spans": int(n_par),
+                             "what": "same calls on the set scaled to 1 %: count table, rank table bit-exact, spans "
+                                     "identical to the CPU oracle run on the whole set"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -253,6 +347,8 @@ def main():
     ap.add_argument("--parity-bases", type=int, default=20_000_000)
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the rank-mode / config-1 / config-5 records")
+    ap.add_argument("--no-config3", action="store_true", help="skip the configs[2] strong-scaling record")
+    ap.add_argument("--config3-scale", type=float, default=1.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -407,6 +503,10 @@ def main():
                                             workload="configs[4] subset: 10 000 contigs, k=10, rank mode thr 0.75")
         ss5.free()
 
+    c3 = None
+    if not args.no_config3:
+        c3 = config3_record(args, stages, rank, world, dist, torch, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -453,6 +553,7 @@ def main():
         "spans_per_step": int(n_spans), "restart_levels": int(levels),
         "parity_check": parity,
         "extra": extra,
+        "config3": c3,
     }
     if world == 1 and not args.no_cpu_baseline:
         sample = min(args.n_bases, 25_000_000)
@@ -466,6 +567,8 @@ def main():
         dist.destroy_process_group()
     if parity is not None and not parity["ok"]:
         raise SystemExit("bench.py: the timed call does NOT match the oracle: %s" % json.dumps(parity))
+    if c3 is not None and not c3["parity_check"]["ok"]:
+        raise SystemExit("bench.py: the configs[2] path does NOT match the oracle")
 
 
 if __name__ == "__main__":

@@ -209,6 +209,9 @@ int ks_seqset_upload_window(ks_ctx *ctx, const char *const *seqs, const int64_t 
 int64_t ks_seqset_chunks(const ks_seqset *s);
 int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, int64_t nchunks,
                        int32_t *d_counts, double *n_words);
+/* the same without a host round trip: the word count is left in device memory (*d_nwords, uint64) */
+int ks_dev_count_range_async(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, int64_t nchunks,
+                             int32_t *d_counts, uint64_t *d_nwords);
 int ks_dev_scan_shard(ks_ctx *ctx, const ks_seqset *s, int k, const double *d_W, double thr, int min_width,
                       double min_score, int64_t chunk0, int64_t nchunks, ks_exchange_fn fn, void *user,
                       ks_spans *host_out_or_null, uint64_t *n_spans);

@@ -73,6 +73,7 @@ SIGNATURES = {
     "ks_plan_shard": (_i, [C.POINTER(C.c_int64), _i, _i, _i] + [C.POINTER(C.c_int64)] * 4),
     "ks_seqset_upload_window": (_i, [_vp] + _SEQS + [_i64, _i64, C.POINTER(_vp)]),
     "ks_dev_count_range": (_i, [_vp, _vp, _i, _i64, _i64, _vp, _pd]),
+    "ks_dev_count_range_async": (_i, [_vp, _vp, _i, _i64, _i64, _vp, _vp]),
     "ks_dev_scan_shard": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, _i64, _i64, _vp, _vp, C.POINTER(KsSpans), _pu64]),
     "ks_dev_scan_counts_shard": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, _i64, _i64, _vp, _vp, C.POINTER(KsSpans), _pu64]),
     "ks_fold_carry": (_i, [_i, _vp, _i, _i, _vp]),

@@ -34,8 +34,24 @@ class SeqBatch:
         return len(self.lens)
 
 
+class SparseSeqs:
+    """Sequences of which only some are present in host memory: lens[i] for every sequence, data {i: uint8 array}
+    for the present ones.  For window uploads (one shard of a multi-GPU run): the layout needs every length, the
+    copy touches only sequences inside the window -- a missing sequence inside it is an error of the caller."""
+
+    def __init__(self, lens, data):
+        self.lens = np.ascontiguousarray(lens, np.int64)
+        self.data = {int(i): np.ascontiguousarray(a, np.uint8) for i, a in data.items()}
+        for i, a in self.data.items():
+            if a.size != self.lens[i]:
+                raise ValueError("SparseSeqs: sequence %d has %d bytes, expected %d" % (i, a.size, self.lens[i]))
+
+    def __len__(self):
+        return len(self.lens)
+
+
 def _as_bytes_list(seq):
-    if isinstance(seq, SeqBatch):
+    if isinstance(seq, (SeqBatch, SparseSeqs)):
         return seq
     if isinstance(seq, (bytes, bytearray, str, np.ndarray)):
         seq = [seq]
@@ -57,7 +73,11 @@ class _SeqArgs:
         n = len(seqs)
         ptr = np.zeros(max(n, 1), np.uint64)
         ln = np.zeros(max(n, 1), np.int64)
-        if isinstance(seqs, SeqBatch):
+        if isinstance(seqs, SparseSeqs):
+            ln[:n] = seqs.lens
+            for i, a in seqs.data.items():
+                ptr[i] = a.ctypes.data
+        elif isinstance(seqs, SeqBatch):
             ln[:n] = seqs.lens
             off = np.zeros(n, np.uint64)
             if n > 1:
@@ -243,6 +263,11 @@ class Context:
         n = C.c_double(0)
         self._ck(self.lib.ks_dev_count_range(self.h, ss.h, int(k), int(chunk0), int(nchunks), d_counts, C.byref(n)))
         return n.value
+
+    def dev_count_range_async(self, ss, k, chunk0, nchunks, d_counts, d_nwords):
+        """the same without a host round trip; the word count is left at device pointer d_nwords (uint64)"""
+        self._ck(self.lib.ks_dev_count_range_async(self.h, ss.h, int(k), int(chunk0), int(nchunks),
+                                                   C.c_void_p(d_counts), C.c_void_p(d_nwords)))
 
     def dev_scan_shard(self, ss, k, table_ptr, thr, min_w, min_score, chunk0, nchunks, exchange, use_counts=False):
         """Level 0 restricted to dense chunks [chunk0, chunk0 + nchunks); `exchange(what, mine48) -> carry48`

@@ -205,9 +205,10 @@ struct ks_ctx {
   DBuf cls, cls_dense, core;
   // rank order of the last ks_dev_scores(RANK): position of every k-mer, piece starts, bucket table (the pieces'
   // x0 / inc stay in sc_segx0 / sc_seginc); scan_ranks_impl gathers 4-byte positions instead of 8-byte scores
-  DBuf rk_pos, rk_p0, rk_bucket;
+  DBuf rk_pos, rk_p0, rk_blob, rk_tail;
   bool rk_valid = false;
   int rk_k = 0, rk_shift = 0;
+  uint32_t rk_npieces = 0, rk_win_lo = 0, rk_win_len = 0, rk_n = 0;
   double rk_max = 0;
   bool core_valid = false;           // ctx->core holds the core records of ctx->cls (scan_gather_kernel, core mode)
   const void *cls_counts = nullptr;  // the count table it was derived from
@@ -373,7 +374,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->win_match, &ctx->win_cnt, &ctx->win_pre, &ctx->win_scratch, &ctx->win_codes, &ctx->win_fix,
                  &ctx->win_hist, &ctx->win_pos, &ctx->st_aux, &ctx->child_pk, &ctx->child_c, &ctx->child_count,
                  &ctx->tr_tables, &ctx->st_mn, &ctx->st_mx, &ctx->st_bm, &ctx->detail, &ctx->detail_count,
-                 &ctx->cls, &ctx->cls_dense, &ctx->core, &ctx->rk_pos, &ctx->rk_p0, &ctx->rk_bucket,
+                 &ctx->cls, &ctx->cls_dense, &ctx->core, &ctx->rk_pos, &ctx->rk_p0, &ctx->rk_blob, &ctx->rk_tail,
                  &ctx->bk_buf, &ctx->bk_cursor};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
@@ -1054,9 +1055,8 @@ int ks_dev_xsum(ks_ctx *ctx, void *const *tables, int nranks, int rank, void *mc
 
 int64_t ks_seqset_chunks(const ks_seqset *s) { return s ? (s->total - 16) / 16 : 0; }
 
-int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, int64_t nchunks,
-                       int32_t *d_counts, double *n_words) {
-  KS_TRY
+static int count_range_impl(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, int64_t nchunks,
+                            int32_t *d_counts, double *n_words, uint64_t *d_nwords, bool sync) {
   if (!ctx) return KS_ERR_ARG;
   if (!s || !d_counts) return ctx->fail(KS_ERR_ARG, "ks_dev_count_range: null argument");
   int rc = check_k(ctx, k);
@@ -1092,11 +1092,24 @@ int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, i
   ctx->prof_end(KS_PROF_COUNT, pe);
   CK(cudaGetLastError());
   s->packed = true;
+  if (d_nwords) CK(cudaMemcpyAsync(d_nwords, ctx->nwords.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+  if (!sync) return KS_OK;
   unsigned long long nw = 0;
   CK(cudaMemcpyAsync(&nw, ctx->nwords.p, sizeof nw, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (n_words) *n_words = (double)nw;
   return KS_OK;
+}
+int ks_dev_count_range(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, int64_t nchunks,
+                       int32_t *d_counts, double *n_words) {
+  KS_TRY
+  return count_range_impl(ctx, s, k, chunk0, nchunks, d_counts, n_words, nullptr, true);
+  KS_CATCH(ctx)
+}
+int ks_dev_count_range_async(ks_ctx *ctx, const ks_seqset *s, int k, int64_t chunk0, int64_t nchunks,
+                             int32_t *d_counts, uint64_t *d_nwords) {
+  KS_TRY
+  return count_range_impl(ctx, s, k, chunk0, nchunks, d_counts, nullptr, d_nwords, false);
   KS_CATCH(ctx)
 }
 
@@ -1387,28 +1400,49 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
       CK(cudaMemcpyAsync(ctx->sc_segx0.p, x0.data(), nsg * 8, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(ctx->sc_seginc.p, inc.data(), nsg * 8, cudaMemcpyHostToDevice, st));
       // the same pieces addressed by absolute position in the rank order, for the scan's 4-byte gather
-      const bool want_pos = mode == KS_MODE_RANK && nsg > 0 && n <= 0xffffffffull && getenv("KS_NO_RANK_POS") == nullptr;
-      std::vector<uint32_t> p0, bucket;
+      const bool want_pos = mode == KS_MODE_RANK && nsg > 0 && n < 0xffffffffull && getenv("KS_NO_RANK_POS") == nullptr;
+      std::vector<uint32_t> p0;
+      std::vector<RankSmem> blob(1);
       if (want_pos) {
         p0.resize(nsg + 1);
         for (size_t g = 0; g < ng; ++g)
           for (uint32_t i = seg_first[g]; i < seg_first[g + 1]; ++i) p0[i] = (uint32_t)(gstart[g] + j0[i]);
-        p0[nsg] = (uint32_t)std::min<size_t>(n, 0xffffffffull);
-        const int shift = 2 * k > 10 ? 2 * k - 10 : 0;
-        bucket.assign(RK_BUCKETS + 1, (uint32_t)(nsg - 1));
-        size_t a = 0;
-        for (size_t b = 0; b <= (size_t)RK_BUCKETS && ((uint64_t)b << shift) < n; ++b) {
-          const uint64_t pos = (uint64_t)b << shift;
-          while (a + 1 < nsg && p0[a + 1] <= pos) ++a;
-          bucket[b] = (uint32_t)a;
+        p0[nsg] = (uint32_t)n;
+        // window of at most RK_SMEM_PIECES consecutive pieces that covers the most positions of the rank order
+        size_t w0 = 0, w1 = std::min<size_t>(nsg, RK_SMEM_PIECES);
+        {
+          uint64_t best = (uint64_t)p0[w1] - p0[0];
+          for (size_t i = 1; i + RK_SMEM_PIECES <= nsg; ++i) {
+            const uint64_t cover = (uint64_t)p0[i + RK_SMEM_PIECES] - p0[i];
+            if (cover > best) { best = cover; w0 = i; w1 = i + RK_SMEM_PIECES; }
+          }
         }
+        const uint32_t win_lo = p0[w0], win_len = p0[w1] - p0[w0];
+        int shift = 0;
+        while (((uint64_t)RK_BUCKETS << shift) < win_len) ++shift;
+        RankSmem &im = blob[0];
+        memset(&im, 0, sizeof im);
+        {
+          size_t a = w0;
+          for (size_t bkt = 0; bkt <= (size_t)RK_BUCKETS; ++bkt) {
+            const uint64_t pos = (uint64_t)win_lo + ((uint64_t)bkt << shift);
+            while (a + 1 < w1 && p0[a + 1] <= pos) ++a;
+            im.bucket[bkt] = (uint32_t)(a - w0);
+          }
+        }
+        for (size_t i = 0; i <= (size_t)RK_SMEM_PIECES; ++i) im.p0[i] = w0 + i <= w1 ? p0[w0 + i] : 0xffffffffu;
+        for (size_t i = 0; i < (size_t)RK_SMEM_PIECES && w0 + i < w1; ++i) { im.x0[i] = x0[w0 + i]; im.inc[i] = inc[w0 + i]; }
         CK(ctx->rk_pos.ensure(n * 4));
         CK(ctx->rk_p0.ensure((nsg + 1) * 4));
-        CK(ctx->rk_bucket.ensure((RK_BUCKETS + 1) * 4));
+        CK(ctx->rk_blob.ensure(sizeof(RankSmem)));
         CK(cudaMemcpyAsync(ctx->rk_p0.p, p0.data(), (nsg + 1) * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->rk_bucket.p, bucket.data(), (RK_BUCKETS + 1) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->rk_blob.p, &im, sizeof im, cudaMemcpyHostToDevice, st));
         ctx->rk_shift = shift;
         ctx->rk_k = k;
+        ctx->rk_npieces = (uint32_t)nsg;
+        ctx->rk_win_lo = win_lo;
+        ctx->rk_win_len = win_len;
+        ctx->rk_n = (uint32_t)n;
         ctx->rk_max = fma((double)(n - 1 - p0[nsg - 1]), inc[nsg - 1], x0[nsg - 1]);  // rank of the last k-mer in order
       }
       rank_eval_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(
@@ -1577,7 +1611,11 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.rk_p0 = ctx->rk_p0.as<uint32_t>();
     A.rk_x0 = ctx->sc_segx0.as<double>();
     A.rk_inc = ctx->sc_seginc.as<double>();
-    A.rk_bucket = ctx->rk_bucket.as<uint32_t>();
+    A.rk_blob = ctx->rk_blob.p;
+    A.rk_tail = ctx->rk_tail.as<int64_t>();
+    A.rk_npieces = ctx->rk_npieces;
+    A.rk_win_lo = ctx->rk_win_lo;
+    A.rk_win_len = ctx->rk_win_len;
     A.rk_shift = ctx->rk_shift;
     A.rk_thr = tab.rk_thr;
     A.lut = ctx->lut_fx.as<int64_t>();
@@ -2057,6 +2095,25 @@ static int scan_ranks_impl(ks_ctx *ctx, const ks_seqset *s, int k, double thr, i
   hp->min_hi = (int64_t)(uint64_t)(((unsigned __int128)mu) >> 64);
   CK(ctx->prm.ensure(sizeof(DevScanParams)));
   CK(cudaMemcpyAsync(ctx->prm.p, hp, sizeof *hp, cudaMemcpyHostToDevice, st));
+  {  // finished scores of the rank-order positions outside the shared-memory window (depends on thr)
+    const uint32_t ntail = ctx->rk_n - ctx->rk_win_len;
+    CK(ctx->rk_tail.ensure((size_t)ntail * 8 + 8));
+    if (ntail) {
+      LevelArgs A;
+      memset(&A, 0, sizeof A);
+      A.prm = ctx->prm.as<DevScanParams>();
+      A.rk_p0 = ctx->rk_p0.as<uint32_t>();
+      A.rk_x0 = ctx->sc_segx0.as<double>();
+      A.rk_inc = ctx->sc_seginc.as<double>();
+      A.rk_npieces = ctx->rk_npieces;
+      A.rk_win_lo = ctx->rk_win_lo;
+      A.rk_win_len = ctx->rk_win_len;
+      A.rk_thr = thr;
+      rank_tail_kernel<<<grid_for(ntail, 256), 256, 0, st>>>(A, ntail, ctx->rk_tail.as<int64_t>());
+      LAUNCHED(1);
+      CK(cudaGetLastError());
+    }
+  }
   ctx->prof_end(KS_PROF_WFX, pw);
   ScanTable tab;
   tab.use_rank = true;

@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "ks_chunk.cuh"
 
@@ -66,6 +67,16 @@ __device__ __forceinline__ int64_t ldg_s64_keep(const int64_t *addr, uint64_t po
   return v;
 }
 
+// the per-chunk records are written once and read once: streaming (evict-first) accesses, so that 2 GB of them per
+// level do not push the gathered table out of L2
+__device__ __forceinline__ void st_stream_fx(__int128 *p, __int128 v) {
+  __stcs(reinterpret_cast<ulonglong2 *>(p),
+         make_ulonglong2((unsigned long long)(unsigned __int128)v, (unsigned long long)(((unsigned __int128)v) >> 64)));
+}
+__device__ __forceinline__ __int128 ld_stream_fx(const __int128 *p) {
+  const ulonglong2 u = __ldcs(reinterpret_cast<const ulonglong2 *>(p));
+  return (__int128)((((unsigned __int128)u.y) << 64) | (unsigned __int128)u.x);
+}
 __device__ __forceinline__ uint64_t fx_lo(fx_t v) { return (uint64_t)(unsigned __int128)v; }
 __device__ __forceinline__ uint64_t fx_hi(fx_t v) { return (uint64_t)(((unsigned __int128)v) >> 64); }
 __device__ __forceinline__ fx_t fx_make(uint64_t hi, uint64_t lo) {
@@ -266,12 +277,13 @@ struct LevelArgs {
   // whose k-mers share c: half the L1TEX lookups of the 2-byte class gather, same 2 * 4^k bytes of L2
   const uint2 *core;
   // rank mode (kLut == 3): gather the 4-byte position p of the k-mer in the stable (count, index) order and
-  // evaluate the rank from the linear pieces of ks_rankseg.h: rank = fma(p - P0[a], inc[a], x0[a]), a = the last
-  // piece with P0[a] <= p; rk_bucket[p >> rk_shift] = piece that holds position (p >> rk_shift) << rk_shift
+  // evaluate the rank from the linear pieces of ks_rankseg.h (rank_value below)
   const uint32_t *rk_pos;
   const uint32_t *rk_p0;
   const double *rk_x0, *rk_inc;
-  const uint32_t *rk_bucket;
+  const void *rk_blob;      // RankSmem image: bucket table + pieces of the window
+  const int64_t *rk_tail;   // finished scores of the positions outside the window
+  uint32_t rk_npieces, rk_win_lo, rk_win_len;
   int rk_shift;
   double rk_thr;
   const int64_t *lut;
@@ -408,18 +420,64 @@ __device__ __forceinline__ void load_window(const LevelArgs &A, int64_t p0, uint
   }
 }
 
-constexpr int RK_BUCKETS = 1024;
-// exact fixed-point score of the k-mer at position p of the rank order: the double rank_eval_kernel writes into
-// the rank table, minus thr (the double the reference forms at :268), converted like every table entry
-__device__ __forceinline__ int64_t rank_value(const LevelArgs &A, const uint32_t *s_bucket, uint32_t p, int qs) {
-  const uint32_t bk = p >> A.rk_shift;
-  uint32_t a = s_bucket[bk], b = s_bucket[bk + 1] + 1;
+constexpr int RK_LOG = 8;
+constexpr int RK_BUCKETS = 1 << RK_LOG;
+constexpr int RK_SMEM_PIECES = 95;
+// Rank mode, per position: p = position of the k-mer in the rank order (4-byte gather).  The pieces of the rank
+// order that hold the bulk of a genome's k-mers -- a WINDOW of RK_SMEM_PIECES consecutive pieces, chosen on the
+// host to cover the most positions -- are evaluated from shared memory: bucket table over the window (which piece
+// holds position win_lo + (b << shift)), then rank = fma(p - P0[a], inc[a], x0[a]), the same fma that filled the
+// rank table.  Everything outside the window (the long tail of rare, highly abundant k-mers: thousands of tiny
+// pieces) is looked up in a table of finished fixed-point scores, one entry per rank-order position outside the
+// window (rank_tail_kernel), so a repeat costs one more load instead of a binary search over global memory.
+struct __align__(16) RankSmem {  // built on the host (ks_api.cu), copied into shared memory with cp.async
+  uint32_t bucket[RK_BUCKETS + 1];      // piece index relative to the window
+  uint32_t p0[RK_SMEM_PIECES + 1];      // first rank-order position of the window's pieces (+ sentinel)
+  double x0[RK_SMEM_PIECES], inc[RK_SMEM_PIECES];
+};
+static_assert(sizeof(RankSmem) % 16 == 0, "RankSmem is copied in 16-byte pieces");
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+// w = rank - thr (finite, |w| < 2^40) -> units of 2^-qs, truncated toward zero: what wfx_from_double computes, in
+// two instructions (scaling by a power of two is exact, the conversion rounds toward zero)
+__device__ __forceinline__ int64_t rank_to_fx(double w, int qs) {
+  if (qs > 900) return wfx_from_double(w, qs);  // 2^qs would leave the double range: bit path
+  return __double2ll_rz(w * __longlong_as_double((long long)(1023 + qs) << 52));
+}
+// exact fixed-point score of the k-mer at position p of the rank order: the double rank_eval_kernel writes into the
+// rank table, minus thr (the double the reference forms at :268), converted like every table entry
+__device__ __forceinline__ int64_t rank_value_global(const LevelArgs &A, uint32_t p, int qs) {
+  uint32_t a = 0, b = A.rk_npieces;
   while (b - a > 1) {
     const uint32_t mid = (a + b) >> 1;
     if (__ldg(&A.rk_p0[mid]) <= p) a = mid; else b = mid;
   }
   const double r = fma((double)(p - __ldg(&A.rk_p0[a])), __ldg(&A.rk_inc[a]), __ldg(&A.rk_x0[a]));
-  return wfx_from_double(r - A.rk_thr, qs);
+  return rank_to_fx(r - A.rk_thr, qs);
+}
+__device__ __forceinline__ int64_t rank_value(const LevelArgs &A, const RankSmem *sm, uint32_t p, int qs) {
+  const uint32_t rel = p - A.rk_win_lo;
+  if (rel >= A.rk_win_len)  // outside the window: finished score, one load
+    return __ldg(&A.rk_tail[p < A.rk_win_lo ? p : p - A.rk_win_len]);
+  if (!sm) return rank_value_global(A, p, qs);
+  const uint32_t bk = rel >> A.rk_shift;
+  uint32_t a = sm->bucket[bk], b = sm->bucket[bk + 1] + 1;
+  while (b - a > 1) {
+    const uint32_t mid = (a + b) >> 1;
+    if (sm->p0[mid] <= p) a = mid; else b = mid;
+  }
+  const double r = fma((double)(p - sm->p0[a]), sm->inc[a], sm->x0[a]);
+  return rank_to_fx(r - A.rk_thr, qs);
+}
+// finished scores of the rank-order positions outside the window (t counts them in order)
+__global__ void __launch_bounds__(256) rank_tail_kernel(const LevelArgs A, uint32_t ntail, int64_t *__restrict__ tail) {
+  const int qs = A.prm->qs;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntail; t += gridDim.x * blockDim.x) {
+    const uint32_t p = t < A.rk_win_lo ? t : t + A.rk_win_len;
+    tail[t] = rank_value_global(A, p, qs);
+  }
 }
 
 constexpr uint32_t CORE_ESCAPE = 255;  // class byte of a core record: "the class is >= 255, read cls[code]"
@@ -431,14 +489,13 @@ __global__ void __launch_bounds__(TILE_THREADS,
 scan_gather_kernel(const LevelArgs A) {
   __shared__ Xf s_wxf[TILE_WARPS + 1];
   __shared__ int64_t s_lut[kCore ? CORE_ESCAPE : 1];  // scores of the classes a core record can name
-  __shared__ uint32_t s_bucket[kLut == 3 ? RK_BUCKETS + 1 : 1];
+  __shared__ typename std::conditional<kLut == 3, RankSmem, int>::type s_rk_store;  // rank mode only
+  const RankSmem *s_rk = kLut == 3 ? reinterpret_cast<const RankSmem *>(&s_rk_store) : nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // small tables that go to shared memory: the loads are issued here, the stores (and the barrier) wait until the
   // gathers are in flight, so their latency hides behind the gathers instead of opening every CTA
   constexpr int LUT_PER = kCore ? (int)(CORE_ESCAPE + TILE_THREADS - 1) / TILE_THREADS : 1;
-  constexpr int BKT_PER = kLut == 3 ? (RK_BUCKETS + 1 + TILE_THREADS - 1) / TILE_THREADS : 1;
   int64_t pre_lut[LUT_PER];
-  uint32_t pre_bkt[BKT_PER];
   if (kCore) {
 #pragma unroll
     for (int i = 0; i < LUT_PER; ++i) {
@@ -446,12 +503,10 @@ scan_gather_kernel(const LevelArgs A) {
       pre_lut[i] = (e < CORE_ESCAPE && e < A.lut_size) ? __ldg(&A.lut[e]) : 0;
     }
   }
-  if (kLut == 3) {
-#pragma unroll
-    for (int i = 0; i < BKT_PER; ++i) {
-      const int e = tid + i * TILE_THREADS;
-      pre_bkt[i] = e <= RK_BUCKETS ? __ldg(&A.rk_bucket[e]) : 0u;
-    }
+  if (kLut == 3) {  // asynchronous copy of the rank-order tables: no registers held, done by the time they are needed
+    for (int i = tid; i < (int)(sizeof(RankSmem) / 16); i += TILE_THREADS)
+      cp_async16(reinterpret_cast<char *>(&s_rk_store) + 16 * i, reinterpret_cast<const char *>(A.rk_blob) + 16 * i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   const int rk_qs = kLut == 3 ? A.prm->qs : 0;
   const int64_t tile = blockIdx.x;
@@ -555,18 +610,14 @@ scan_gather_kernel(const LevelArgs A) {
     __syncthreads();
   }
   if (kLut == 3) {
-#pragma unroll
-    for (int i = 0; i < BKT_PER; ++i) {
-      const int e = tid + i * TILE_THREADS;
-      if (e <= RK_BUCKETS) s_bucket[e] = pre_bkt[i];
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
   }
   // value of a SCORED position (WFX_KILL = the table says "force the state to 0")
   auto value = [&](int j) -> int64_t {
     if (kLut == 2 && kCore) return c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&A.lut[c[j]]);
     if (kLut == 2) return __ldg(&A.lut[c[j]]);
-    if (kLut == 3) return rank_value(A, s_bucket, c[j], rk_qs);
+    if (kLut == 3) return rank_value(A, s_rk, c[j], rk_qs);
     if (kLut) {
       if (c[j] < A.lut_size) return __ldg(&A.lut[c[j]]);
       uint32_t lo = 0, hi = A.sp_n;  // rare: very abundant k-mer, look it up in the sorted sparse list
@@ -660,17 +711,17 @@ scan_gather_kernel(const LevelArgs A) {
   }
   __syncthreads();
   excl = xf_compose(s_wxf[warp], excl);
-  A.st_ea[q] = excl.a;
-  A.st_eb[q] = excl.b;
+  st_stream_fx(&A.st_ea[q], excl.a);
+  st_stream_fx(&A.st_eb[q], excl.b);
   uint32_t flags = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u) | (vchunk ? 0x40000u : 0u);
   if (kSumm) {
     flags |= summ.bits;
-    A.st_mn[q] = summ.mn;
-    A.st_mx[q] = summ.mx;
-    A.st_bm[q] = summ.bm;
+    __stcs(&A.st_mn[q], (long long)summ.mn);
+    __stcs(&A.st_mx[q], (long long)summ.mx);
+    __stcs(&A.st_bm[q], (long long)summ.bm);
   }
-  A.st_flags[q] = flags;
-  if (A.nseg != 0) A.st_p0[q] = p0;
+  __stcs(&A.st_flags[q], flags);
+  if (A.nseg != 0) __stcs(&A.st_p0[q], (long long)p0);
   if (kTr) A.st_aux[q] = tr_first | (scored << 16);
 }
 
@@ -790,7 +841,7 @@ scan_walk_kernel(const LevelArgs A) {
   const bool head = (fl & 0x10000u) != 0;
   const int64_t p0 = A.nseg == 0 ? A.dense_start + 16 * q : A.st_p0[q];
   Xf excl;
-  excl.a = A.st_ea[q]; excl.b = A.st_eb[q]; excl.kill = (fl >> 17) & 1u;
+  excl.a = ld_stream_fx(&A.st_ea[q]); excl.b = ld_stream_fx(&A.st_eb[q]); excl.kill = (fl >> 17) & 1u;
   const fx_t S_in = head ? (fx_t)0 : xf_apply(excl, S_tile);
   int64_t s[CHUNK];
   if (kLut == 2) {
@@ -901,18 +952,18 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_WALKFAST_MINBLOCKS) scan_walk
   const bool head = (fl & 0x10000u) != 0;
   const int64_t p0 = A.nseg == 0 ? A.dense_start + 16 * q : A.st_p0[q];
   Xf excl;
-  excl.a = A.st_ea[q]; excl.b = A.st_eb[q]; excl.kill = (fl >> 17) & 1u;
+  excl.a = ld_stream_fx(&A.st_ea[q]); excl.b = ld_stream_fx(&A.st_eb[q]); excl.kill = (fl >> 17) & 1u;
   const fx_t S_in = head ? (fx_t)0 : xf_apply(excl, S_tile);
   ChunkSummary summ;
-  summ.mx = A.st_mx[q];
+  summ.mx = __ldcs(&A.st_mx[q]);
   summ.bits = fl;
   Ex ex;
   bool closing = false;
   if (fl & 0x40000u) {  // padding chunk: transparent
     ex = ex_identity();
   } else {
-    summ.mn = (live == 0xffffu && S_in > 0) ? A.st_mn[q] : 0;  // only read where fast_walk_element looks at it
-    summ.bm = (fl & 0x80000000u) ? A.st_bm[q] : 0;
+    summ.mn = (live == 0xffffu && S_in > 0) ? __ldcs(&A.st_mn[q]) : 0;  // only read where fast_walk_element looks at it
+    summ.bm = (fl & 0x80000000u) ? __ldcs(&A.st_bm[q]) : 0;
     fast_walk_element(S_in, head, live, summ, p0, ex, closing);
   }
   Ex einc = ex;
@@ -986,7 +1037,7 @@ __global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
       if (kLut == 2) {
         v = __ldg(&A.lut[__ldg(&A.cls[code])]);
       } else if (kLut == 3) {
-        v = rank_value(A, A.rk_bucket, __ldg(&A.rk_pos[code]), A.prm->qs);
+        v = rank_value(A, nullptr, __ldg(&A.rk_pos[code]), A.prm->qs);
       } else if (kLut) {
         const uint32_t c = __ldg(&A.counts[code]);
         if (c < A.lut_size) {

@@ -303,3 +303,60 @@ def run_split_nccl(ctx, dist, seqs, k, mode, min_w, min_score, thr=0.0, param=fl
         dist.all_gather_object(parts, (r["pos"], r["score"]))
         r["pos"], r["score"] = merge_spans(parts)
     return r
+
+
+class SplitRun:
+    """ONE sequence set cut across the ranks at chunk boundaries, resident as window sets (ks_plan_shard /
+    ks_seqset_upload_window): what BASELINE.json configs[2] (24 chromosomes over 8 GPUs) needs.  step() runs
+    count(range) -> sum of the tables (peer memory / NCCL, on the ctx stream) -> scores -> sharded scan; the two
+    48-byte carries of a scan travel through an NCCL all-gather of a device tensor."""
+
+    def __init__(self, stages, dist, seqs):
+        import torch
+        from . import api
+        self.torch, self.api, self.stages, self.ctx = torch, api, stages, stages.ctx
+        self.dist = dist if dist is not None and dist.is_initialized() and dist.get_world_size() > 1 else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
+        lens = seqs.lens if hasattr(seqs, "lens") else [len(x) for x in seqs]
+        self.c0, self.cn, self.lo, self.hi = api.plan_shard(lens, self.world, self.rank)
+        self.seqs = seqs
+        self.ss = self.ctx.upload_window(seqs, self.lo, self.hi)
+        self.bases = int(np.sum(lens))
+        if self.dist:
+            self._gathered = torch.empty(48 * self.world, dtype=torch.uint8, device=stages.device)
+
+    def reload(self):
+        """upload the window again (end-to-end timing)"""
+        self.ss.free()
+        self.ss = self.ctx.upload_window(self.seqs, self.lo, self.hi)
+
+    def _exchange(self, what, mine):
+        if not self.dist:
+            return self.api.fold_carry(what, [mine], 0)
+        t = self.torch
+        mine_t = t.frombuffer(bytearray(mine), dtype=t.uint8).to(self.stages.device)
+        self.dist.all_gather_into_tensor(self._gathered, mine_t)
+        flat = self._gathered.cpu().numpy().tobytes()
+        return self.api.fold_carry(what, [flat[48 * i:48 * (i + 1)] for i in range(self.world)], self.rank)
+
+    def step(self, k, mode, thr, min_w, min_score, param=float("nan"), fetch=False):
+        st, ctx = self.stages, self.ctx
+        st.alloc_tables(k, self.dist)
+        if getattr(st, "nwords", None) is None:
+            st.count_async(k)  # allocates the word-count tensor
+        ctx.dev_count_range_async(self.ss, k, self.c0, self.cn, st.counts.data_ptr(), st.nwords.data_ptr())
+        if self.dist:
+            st.reduce_counts(self.dist)
+        total = st.scores_from_counts_dev(k, mode, param)
+        if mode == 0:
+            r = ctx.dev_scan_ranks_shard(self.ss, k, thr, min_w, min_score, self.c0, self.cn, self._exchange)
+        else:
+            use_counts = mode in (1, 2)
+            r = ctx.dev_scan_shard(self.ss, k, st.counts.data_ptr() if use_counts else st.scores.data_ptr(), thr,
+                                   min_w, min_score, self.c0, self.cn, self._exchange, use_counts=use_counts)
+        r["n"] = total
+        return r
+
+    def free(self):
+        self.ss.free()

@@ -37,7 +37,7 @@ def test_reference_arm_line():
 def test_own_arm_line():
     # 20 Mb: at k = 12 more than half of the 4^12 k-mers must occur, or the median frequency is 0 and the
     # log2 score table holds +Inf (rejected by design)
-    d = run_bench("--steps", "3", "--warmup", "3", "--n-bases", "20000000", "--e2e-steps", "2")
+    d = run_bench("--steps", "3", "--warmup", "3", "--n-bases", "20000000", "--e2e-steps", "2", "--config3-scale", "0.02")
     assert BASE_KEYS | {"clocks", "gpu_launches", "roofline"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["data"] == "synthetic"
     assert d["value"] > 0 and d["gpu_launches"] > 0 and "workload" in d["config"]
@@ -56,3 +56,5 @@ def test_own_arm_line():
     assert pc["rank_mode"]["ok"] and pc["call"] == "ks_dev_pipeline"
     assert {"rank_mode", "config1", "config5_subset"} <= set(d["extra"])
     assert d["extra"]["rank_mode"]["spans"] > 0 and d["extra"]["config1"]["ms_per_step"] > 0
+    c3 = d["config3"]
+    assert c3["parity_check"]["ok"] and c3["spans"] > 0 and c3["ms_per_step"] > 0 and c3["n_gpus"] == 1
