@@ -141,6 +141,31 @@ class Oracle:
             raise ValueError("oracle mode_regions rc=%d" % rc)
         return dict(n=n.value, counts=counts, scores=W, pos=pos, score=sc)
 
+    def large_regions(self, seqs, k, mode, min_width, min_score, thr=0.75, param=float("nan")):
+        """large-k checker (ks_oracle_large.c, parity by extension): sparse count table, rank over the k-mers that
+        occur in (count, code) order, scan.  mode 0 rank, 2 +-1 around the frequency `param`."""
+        class _Large(C.Structure):
+            _fields_ = [("codes", C.POINTER(C.c_uint64)), ("counts", C.POINTER(C.c_uint32)),
+                        ("ranks", C.POINTER(C.c_double)), ("nd", C.c_size_t), ("total", C.c_double)]
+        seqs = _as_bytes_list(seqs)
+        bufs, ptrs, lens = _padded(seqs)
+        t = _Large()
+        sp = _Spans()
+        self.lib.kso_spans_init(C.byref(sp))
+        rc = self.lib.kso_large_regions(ptrs, lens, len(seqs), C.c_int(k), C.c_int(mode), C.c_double(param),
+                                        C.c_double(thr), C.c_int(min_width), C.c_double(min_score), C.byref(t),
+                                        C.byref(sp))
+        if rc:
+            raise ValueError("oracle large_regions rc=%d" % rc)
+        pos, sc = self._spans_out(sp)
+        self.lib.kso_spans_free(C.byref(sp))
+        nd = int(t.nd)
+        out = dict(n=t.total, nd=nd, codes=np.ctypeslib.as_array(t.codes, (max(nd, 1),))[:nd].copy(),
+                   counts=np.ctypeslib.as_array(t.counts, (max(nd, 1),))[:nd].copy(),
+                   ranks=np.ctypeslib.as_array(t.ranks, (max(nd, 1),))[:nd].copy(), pos=pos, score=sc)
+        self.lib.kso_large_free(C.byref(t))
+        return out
+
     def kmer_seq(self, k, code):
         buf = C.create_string_buffer(k + 1)
         self.lib.kso_kmer_seq(k, code, buf)

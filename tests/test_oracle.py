@@ -265,3 +265,32 @@ def test_next_rows_match_reference_larger_k(oracle, ref, k):
         assert np.array_equal(a["dist"], b["dist"]) and np.array_equal(a["included"], b["included"])
         for x, y in zip(a["pos"], b["pos"]):
             assert _pos_equal(x, y, len(sel))
+
+
+def test_large_oracle_equals_pinned_oracle_at_small_k(oracle):
+    """ks_oracle_large.c (sparse table, 64-bit codes; the checker of the k >= 16 path) run at k <= 12 must give
+    what the pinned full-table oracle gives: counts of the k-mers that occur, ranks bit for bit (absent k-mers add
+    0 to the running sum), identical spans -- so the extension to k = 16..31 changes the container, not the
+    arithmetic."""
+    rng = np.random.default_rng(8100)
+    for k, thr, mw, ms in ((3, 0.6, 10, 2.0), (7, 0.75, 30, 3.0), (9, 0.5, 0, 0.0), (12, 0.75, 20, 1.0)):
+        seqs = [planted(rng, 30000), b"ACG", rand_seq(rng, 4000, p_n=0.1), b"ACGTACGTACGTACGT"[:k], planted(rng, 9000)]
+        small = oracle.low_comp(seqs, k, mw, ms, thr)
+        large = oracle.large_regions(seqs, k, 0, mw, ms, thr=thr)
+        assert large["n"] == small["n"][0]
+        present = np.nonzero(small["counts"])[0]
+        assert (large["codes"] == present).all() and (large["counts"] == small["counts"][present]).all()
+        assert large["ranks"].tobytes() == small["ranks"][present].tobytes()
+        assert large["pos"].tolist() == small["pos"].tolist()
+        assert large["score"].tobytes() == small["score"].tobytes()
+        # +-1 mode around an explicit frequency
+        f_t = 1.5 / small["n"][0]
+        W = np.where(small["counts"] / small["n"][0] >= f_t, 1.0, -1.0)
+        a = oracle.kmer_regions(seqs, k, W, mw, ms)
+        b = oracle.large_regions(seqs, k, 2, mw, ms, thr=0.0, param=f_t)
+        assert a["pos"].tolist() == b["pos"].tolist() and a["score"].tobytes() == b["score"].tobytes()
+    # and it runs where the reference cannot: k = 21 and k = 31
+    seqs = [planted(rng, 20000), planted(rng, 3000)]
+    for k in (16, 21, 31):
+        r = oracle.large_regions(seqs, k, 0, 20, 1.0, thr=0.75)
+        assert r["nd"] <= r["n"] and r["counts"].sum() == r["n"] and (r["codes"][1:] > r["codes"][:-1]).all()
