@@ -224,6 +224,23 @@ int ks_dev_scan_ranks_shard(ks_ctx *ctx, const ks_seqset *s, int k, double thr, 
 /* host helper: carry entering shard `rank` from the 48-byte aggregates of shards 0..nranks-1 */
 int ks_fold_carry(int what, const void *all48, int nranks, int rank, void *carry_in48);
 
+/* -------- large k (BASELINE.json configs[3]: k = 21) -------------------------------------------------------
+ * Outside the reference's domain (src/kmer_spans.c:37 MAX_K 16, :139 int shift, :504 k >= 16 rejected), defined by
+ * extension: 64-bit codes, the count table is an open-addressing hash table in HBM (it holds the
+ * k-mers that occur, not 4^k entries), the score is the weighted rank over the k-mers that occur in (count, code)
+ * order -- what rank_kmers_w (:189-202) would give on the full table, where absent k-mers add 0 -- or, mode
+ * KS_MODE_SIGN, +-1 around the frequency `param`; the scan is kmer_regions (:243-307) unchanged.  k may be any
+ * value in 1..31 (k <= 15 lets tests compare this path with the direct-table path).  One GPU. */
+int ks_dev_large_regions(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double param, double thr, int min_width,
+                         double min_score, double *n_words, uint64_t *n_distinct, ks_spans *host_out_or_null,
+                         uint64_t *n_spans);
+int ks_kmer_large_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k, int mode,
+                          double param, double thr, int min_width, double min_score, double *n_words,
+                          uint64_t *n_distinct, ks_spans *out);
+/* the sparse table the last large-k call left on this ctx, in (count, code) order: n_distinct entries per array
+ * (host memory, any may be NULL) */
+int ks_large_table(ks_ctx *ctx, uint64_t *codes_out, uint32_t *counts_out, double *ranks_out);
+
 /* -------- several GPUs behind one call (one process, N devices; csrc/ks_multi.inc) -----------------
  * The reference runs its loops over all sequences of a call in one process (src/kmer_spans.c:592-601 count,
  * :604-612 scan); ks_mctx keeps that shape on N devices: the layout of all sequences is cut into N contiguous

@@ -83,6 +83,9 @@ SIGNATURES = {
     "ks_dev_tr_lr_regions": (_i, [_vp, _vp, _i, _vp, _vp, _i, C.POINTER(KsSpans), _pu64]),
     "ks_windowed_kmer_count_distributions": (_i, [_vp] + _SEQS + [_i, _vp, _i, _i, _vp, _vp, _vp]),
     "ks_dev_window_dist": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp]),
+    "ks_dev_large_regions": (_i, [_vp, _vp, _i, _i, _d, _d, _i, _d, _pd, _pu64, C.POINTER(KsSpans), _pu64]),
+    "ks_kmer_large_regions": (_i, [_vp] + _SEQS + [_i, _i, _d, _d, _i, _d, _pd, _pu64, C.POINTER(KsSpans)]),
+    "ks_large_table": (_i, [_vp, _vp, _vp, _vp]),
     "ks_mctx_create": (_i, [C.POINTER(_vp), C.POINTER(_i), _i]),
     "ks_mctx_destroy": (None, [_vp]),
     "ks_mctx_last_error": (C.c_char_p, [_vp]),

@@ -360,6 +360,35 @@ class Context:
         pos, score = _spans_to_numpy(self.lib, sp)
         return dict(n=n.value, counts=counts, scores=scores, pos=pos, score=score)
 
+    def kmer_large_regions(self, seq, k, mode, min_w, min_score, thr=0.75, param=float("nan"), want_table=False):
+        """large-k path (k up to 31; BASELINE.json configs[3]): hash-table counting, weighted rank over the k-mers
+        that occur (mode 0) or +-1 around the frequency `param` (mode 2), scan.  want_table: also return the
+        sparse table in (count, code) order (codes, counts, ranks)."""
+        a = _SeqArgs(_as_bytes_list(seq))
+        n, nd, sp = C.c_double(0), C.c_uint64(0), KsSpans()
+        self._ck(self.lib.ks_kmer_large_regions(self.h, a.ptrs, a.lens, a.n, int(k), int(mode), float(param),
+                                                float(thr), int(min_w), float(min_score), C.byref(n), C.byref(nd),
+                                                C.byref(sp)))
+        pos, score = _spans_to_numpy(self.lib, sp)
+        out = dict(n=n.value, nd=int(nd.value), pos=pos, score=score)
+        if want_table and out["nd"]:
+            codes = np.zeros(out["nd"], np.uint64)
+            counts = np.zeros(out["nd"], np.uint32)
+            ranks = np.zeros(out["nd"], np.float64)
+            self._ck(self.lib.ks_large_table(self.h, codes.ctypes.data, counts.ctypes.data, ranks.ctypes.data))
+            out.update(codes=codes, counts=counts, ranks=ranks)
+        return out
+
+    def dev_large_regions(self, ss, k, mode, min_w, min_score, thr=0.75, param=float("nan"), fetch_spans=False):
+        n, nd, ns, sp = C.c_double(0), C.c_uint64(0), C.c_uint64(0), KsSpans()
+        self._ck(self.lib.ks_dev_large_regions(self.h, ss.h, int(k), int(mode), float(param), float(thr), int(min_w),
+                                               float(min_score), C.byref(n), C.byref(nd),
+                                               C.byref(sp) if fetch_spans else None, C.byref(ns)))
+        res = dict(n=n.value, nd=int(nd.value), n_spans=int(ns.value))
+        if fetch_spans:
+            res["pos"], res["score"] = _spans_to_numpy(self.lib, sp)
+        return res
+
     def kmer_scores(self, counts, k, total, mode=MODE_RANK, param=float("nan")):
         """rank_kmers_w (src/kmer_spans.c:189-202) / README modes as a table operator"""
         counts = np.ascontiguousarray(counts, np.int32)

@@ -24,6 +24,7 @@
 #include "../../include/kspans.h"
 #include "ks_kernels.cuh"
 #include "ks_count.cuh"
+#include "ks_large.cuh"
 #include "ks_layout.h"
 #include "ks_rankseg.h"
 #include "ks_sort.cuh"
@@ -181,6 +182,13 @@ struct ks_ctx {
   void *pinned = nullptr;
   size_t pinned_cap = 0;
   DBuf tmp_counts, tmp_scores, tmp_inscan, nwords, pending, foc_hist, foc_big;
+  // large k (ks_large.cuh): hash table, composite sort keys, slot indices, ranks in (count, code) order
+  DBuf lg_slots, lg_stats, lg_comp_a, lg_comp_b, lg_slot_a, lg_slot_b, lg_ranks;
+  uint64_t lg_nd = 0, lg_mask = 0;
+  int lg_k = 0;
+  uint64_t *lg_sorted = nullptr;   // sorted keys (one of lg_comp_a / lg_comp_b): composite, or codes in code order
+  uint32_t *lg_idx = nullptr, *lg_cnt = nullptr;  // two-pass order: code-order index and count per position
+  DBuf lg_cnt_a, lg_cnt_b, lg_idx_a, lg_idx_b;
   DBuf bk_buf, bk_cursor;  // bucketed counting (ks_count.cuh): sub-keys per bucket, fill of every bucket
   bool smem_attr_set = false;
   DBuf win_match, win_cnt, win_pre, win_scratch, win_codes, win_fix, win_hist, win_pos;
@@ -375,7 +383,9 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->win_hist, &ctx->win_pos, &ctx->st_aux, &ctx->child_pk, &ctx->child_c, &ctx->child_count,
                  &ctx->tr_tables, &ctx->st_mn, &ctx->st_mx, &ctx->st_bm, &ctx->detail, &ctx->detail_count,
                  &ctx->cls, &ctx->cls_dense, &ctx->core, &ctx->rk_pos, &ctx->rk_p0, &ctx->rk_blob, &ctx->rk_tail,
-                 &ctx->bk_buf, &ctx->bk_cursor};
+                 &ctx->bk_buf, &ctx->bk_cursor, &ctx->lg_slots, &ctx->lg_stats, &ctx->lg_comp_a, &ctx->lg_comp_b,
+                 &ctx->lg_slot_a, &ctx->lg_slot_b, &ctx->lg_ranks, &ctx->lg_cnt_a, &ctx->lg_cnt_b, &ctx->lg_idx_a,
+                 &ctx->lg_idx_b};
   for (DBuf *b : all) b->release();
   ctx->prof_resolve();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1523,6 +1533,7 @@ struct ScanTable {  // what scan_gather_kernel gathers from
   uint32_t lut_size = 0, sp_n = 0;
   bool use_cls = false;  // class mode: ctx->cls + per-class table in ctx->lut_fx
   bool use_core = false; // ... gathered two positions at a time through ctx->core
+  bool use_hash = false; // large k: 64-bit codes, scores in the slots of ctx->lg_slots
   bool use_rank = false; // rank mode: ctx->rk_pos + the linear pieces of the rank order
   double rk_thr = 0;
   bool tr = false;  // transition-score scan: ctx->wfx = [trans | init], every close is re-scanned
@@ -1607,6 +1618,10 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.counts = tab.counts;
     A.cls = ctx->cls.as<uint16_t>();
     A.core = ctx->core.as<uint2>();
+    A.hslots = ctx->lg_slots.as<HashSlot>();
+    A.hmask = ctx->lg_mask;
+    A.kmask64 = k < 32 ? ((((uint64_t)1) << (2 * k)) - 1) : ~0ull;
+    A.pk_first = s->win_lo / 16;
     A.rk_pos = ctx->rk_pos.as<uint32_t>();
     A.rk_p0 = ctx->rk_p0.as<uint32_t>();
     A.rk_x0 = ctx->sc_segx0.as<double>();
@@ -1684,6 +1699,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     if (tab.tr) CK(cudaMemsetAsync(ctx->child_count.p, 0, sizeof(unsigned long long), st));
     cudaEvent_t ps = ctx->prof_begin();
     if (tab.tr) scan_gather_kernel<0, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (fast && tab.use_hash) scan_gather_kernel<4, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (tab.use_hash) scan_gather_kernel<4><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (fast && tab.use_rank) scan_gather_kernel<3, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (tab.use_rank) scan_gather_kernel<3><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (fast && tab.use_core) scan_gather_kernel<2, false, true, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
@@ -1724,7 +1741,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
       // the list is short (one entry per tile at most, plus the rare wide excursions); the kernel reads
       // its length on the device and strides over it, so no host round trip sits between the kernels
       const unsigned dgrid = (unsigned)std::min<size_t>(blocks_exact(tiles + 1024, 128), 148u * 8u);
-      if (tab.use_rank) scan_detail_kernel<3><<<dgrid, 128, 0, st>>>(A);
+      if (tab.use_hash) scan_detail_kernel<4><<<dgrid, 128, 0, st>>>(A);
+      else if (tab.use_rank) scan_detail_kernel<3><<<dgrid, 128, 0, st>>>(A);
       else if (tab.use_cls) scan_detail_kernel<2><<<dgrid, 128, 0, st>>>(A);
       else if (tab.use_lut) scan_detail_kernel<1><<<dgrid, 128, 0, st>>>(A);
       else scan_detail_kernel<0><<<dgrid, 128, 0, st>>>(A);
@@ -2137,6 +2155,256 @@ int ks_dev_scan_ranks_shard(ks_ctx *ctx, const ks_seqset *s, int k, double thr, 
   ShardCtl sh;
   sh.chunk0 = chunk0; sh.nchunks = nchunks; sh.fn = fn; sh.user = user;
   return scan_ranks_impl(ctx, s, k, thr, min_width, min_score, host_out, n_spans, &sh);
+  KS_CATCH(ctx)
+}
+
+// ------------------------------------------------------------------------------------------------
+// Large k (1 <= k <= 31 accepted, meant for k >= 16; BASELINE.json configs[3]: k = 21): hash-table counting, rank
+// over the k-mers that occur in (count, code) order (mode KS_MODE_RANK) or +-1 around the frequency `param` (mode
+// KS_MODE_SIGN), scan with the scores kept in the table's slots.  One GPU; everything stays resident.
+int ks_dev_large_regions(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double param, double thr, int min_width,
+                         double min_score, double *n_words, uint64_t *n_distinct, ks_spans *host_out,
+                         uint64_t *n_spans) {
+  KS_TRY
+  if (!ctx) return KS_ERR_ARG;
+  if (!s) return ctx->fail(KS_ERR_ARG, "ks_dev_large_regions: null argument");
+  if (k < 1 || k > 31) return ctx->fail(KS_ERR_ARG, "the large-k path takes k between 1 and 31 (got %d)", k);
+  if (mode != KS_MODE_RANK && mode != KS_MODE_SIGN)
+    return ctx->fail(KS_ERR_ARG, "the large-k path scores by weighted rank (mode 0) or +-1 around a frequency (mode 2)");
+  if (mode == KS_MODE_SIGN && !isfinite(param))
+    return ctx->fail(KS_ERR_ARG, "mode 2 at large k needs an explicit frequency threshold (the median of 4^k entries is 0)");
+  if (s->window) return ctx->fail(KS_ERR_ARG, "the large-k path runs on whole sets (one GPU)");
+  if (host_out) { host_out->pos = nullptr; host_out->score = nullptr; host_out->n = 0; }
+  if (n_spans) *n_spans = 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int rc = ensure_packed(ctx, s);
+  if (rc) return rc;
+  // ---- hash table: power of two, load factor <= 0.75 even if every position holds a new k-mer ----
+  uint64_t cap = 1024;
+  while ((double)cap * 0.75 < (double)s->bases + 1.0) cap <<= 1;
+  if (const char *e = getenv("KS_HASH_CAP")) cap = (uint64_t)atoll(e);  // tests: small tables, long probe chains
+  if (cap > (1ull << 32)) return ctx->fail(KS_ERR_ARG, "input too large for the large-k path on one GPU (2^32 slots)");
+  CK(ctx->lg_slots.ensure((size_t)cap * sizeof(HashSlot)));
+  CK(ctx->lg_stats.ensure(64));
+  CK(cudaMemsetAsync(ctx->lg_slots.p, 0, (size_t)cap * sizeof(HashSlot), st));
+  CK(cudaMemsetAsync(ctx->lg_stats.p, 0, 64, st));
+  HashArgs H;
+  H.slots = ctx->lg_slots.as<HashSlot>();
+  H.mask = cap - 1;
+  H.stats = ctx->lg_stats.as<unsigned long long>();
+  ctx->lg_mask = cap - 1;
+  ctx->lg_k = k;
+  ctx->lg_nd = 0;
+  const int64_t nch = s->total / 16 - 1;  // chunks 1 .. total/16 - 1 hold the data (chunk 0 is the front pad)
+  cudaEvent_t pe = ctx->prof_begin();
+  hash_count_kernel<<<grid_for((size_t)nch, 256, 148u * 8u), 256, 0, st>>>(s->d_pk, s->d_brk, s->d_buf, 1, nch, k, H);
+  ctx->prof_end(KS_PROF_COUNT, pe);
+  LAUNCHED(1);
+  CK(cudaGetLastError());
+  cudaEvent_t psc = ctx->prof_begin();
+  // ---- how many k-mers occur, and the largest count ----
+  hash_stats_kernel<<<grid_for((size_t)cap, 256, 148u * 8u), 256, 0, st>>>(H);
+  LAUNCHED(1);
+  unsigned long long stats[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(stats, ctx->lg_stats.p, sizeof stats, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (stats[3] & 1ull) return ctx->fail(KS_ERR_NOMEM, "the k-mer hash table is full");
+  if (stats[2] > 0x7fffffffull) return ctx->fail(KS_ERR_RANGE, "a k-mer count exceeds 2^31 - 1");
+  const double total = (double)stats[0];
+  const uint64_t nd = stats[1];
+  if (n_words) *n_words = total;
+  if (n_distinct) *n_distinct = nd;
+  ctx->lg_nd = nd;
+  ctx->lg_idx = nullptr;
+  ctx->lg_cnt = nullptr;
+  if (nd == 0) { ctx->prof_end(KS_PROF_SCORES, psc); return KS_OK; }
+  int cbits = 0;
+  while (cbits < 64 && (stats[2] >> cbits) != 0) ++cbits;
+  // ---- order (count, code).  When count and code fit one 64-bit key, ONE stable radix sort of the composite key;
+  //      otherwise codes first, then the counts (stable) with the code-order index as payload ----
+  const bool composite = 2 * k + cbits <= 64 && getenv("KS_LARGE_TWO_PASS") == nullptr;
+  CK(ctx->lg_comp_a.ensure((size_t)nd * 8));
+  CK(ctx->lg_slot_a.ensure((size_t)nd * 4));
+  CK(ctx->lg_comp_b.ensure((size_t)nd * 8));
+  CK(ctx->lg_slot_b.ensure((size_t)nd * 4));
+  unsigned long long *d_cursor = ctx->lg_stats.as<unsigned long long>() + 4;
+  hash_compact_kernel<<<grid_for((size_t)cap, 256, 148u * 8u), 256, 0, st>>>(
+      H, k, composite ? 1 : 0, ctx->lg_comp_a.as<uint64_t>(), ctx->lg_slot_a.as<uint32_t>(), nd, d_cursor);
+  LAUNCHED(1);
+  size_t nb = radix_nblocks((size_t)nd);
+  CK(ctx->sort_hist.ensure((256 * nb + 2) * 4));
+  CK(ctx->sort_scan.ensure(exclusive_scan_scratch_elems(256 * nb) * 4));
+  RadixScratch rs{ctx->sort_hist.as<uint32_t>(), ctx->sort_scan.as<uint32_t>()};
+  uint64_t *skeys = nullptr;
+  uint32_t *sslots = nullptr;
+  LAUNCHED(radix_sort_pairs<uint64_t>(ctx->lg_comp_a.as<uint64_t>(), ctx->lg_slot_a.as<uint32_t>(),
+                                      ctx->lg_comp_b.as<uint64_t>(), ctx->lg_slot_b.as<uint32_t>(), (size_t)nd,
+                                      composite ? 2 * k + cbits : 2 * k, false, rs, st, &skeys, &sslots));
+  CK(cudaGetLastError());
+  ctx->lg_sorted = skeys;
+  uint32_t *scnt = nullptr, *sidx = nullptr;
+  if (!composite) {
+    CK(ctx->lg_cnt_a.ensure((size_t)nd * 4));
+    CK(ctx->lg_cnt_b.ensure((size_t)nd * 4));
+    CK(ctx->lg_idx_a.ensure((size_t)nd * 4));
+    CK(ctx->lg_idx_b.ensure((size_t)nd * 4));
+    large_counts_kernel<<<blocks_exact((size_t)nd, 256), 256, 0, st>>>(ctx->lg_slots.as<HashSlot>(), sslots, nd,
+                                                                      ctx->lg_cnt_a.as<uint32_t>());
+    LAUNCHED(1);
+    LAUNCHED(radix_sort_pairs<uint32_t>(ctx->lg_cnt_a.as<uint32_t>(), ctx->lg_idx_a.as<uint32_t>(),
+                                        ctx->lg_cnt_b.as<uint32_t>(), ctx->lg_idx_b.as<uint32_t>(), (size_t)nd, cbits,
+                                        true, rs, st, &scnt, &sidx));
+    CK(cudaGetLastError());
+    if (cbits == 0 || sidx == nullptr) return ctx->fail(KS_ERR_CUDA, "internal: empty count sort");
+    ctx->lg_idx = sidx;
+    ctx->lg_cnt = scnt;
+  }
+  // ---- run-length table of the counts, pieces of the sequential accumulation (host, O(#distinct counts)) ----
+  size_t gcap = (size_t)(sqrt(2.0 * (total > 0 ? total : 1.0)) + 16.0);
+  CK(ctx->sc_small.ensure(64));
+  uint32_t *d_ngroups = ctx->sc_small.as<uint32_t>() + 1;
+  std::vector<uint32_t> gcount, gstart32;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    CK(ctx->sc_gcount.ensure((gcap + 1) * 4));
+    CK(ctx->sc_gstart.ensure((gcap + 1) * 4));
+    CK(cudaMemsetAsync(d_ngroups, 0, 4, st));
+    if (composite)
+      large_heads_kernel<<<blocks_exact((size_t)nd, 256), 256, 0, st>>>(skeys, nd, k, ctx->sc_gcount.as<uint32_t>(),
+                                                                       ctx->sc_gstart.as<uint32_t>(), d_ngroups,
+                                                                       (uint32_t)gcap);
+    else
+      rle_heads_kernel<<<blocks_exact((size_t)nd, 256), 256, 0, st>>>(scnt, (size_t)nd, ctx->sc_gcount.as<uint32_t>(),
+                                                                     ctx->sc_gstart.as<uint32_t>(), d_ngroups,
+                                                                     (uint32_t)gcap);
+    LAUNCHED(1);
+    uint32_t ng = 0;
+    CK(cudaMemcpyAsync(&ng, d_ngroups, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (ng > gcap) { gcap = ng; continue; }
+    gcount.resize(ng);
+    gstart32.resize(ng);
+    CK(cudaMemcpyAsync(gcount.data(), ctx->sc_gcount.p, (size_t)ng * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(gstart32.data(), ctx->sc_gstart.p, (size_t)ng * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    break;
+  }
+  const size_t ng = gcount.size();
+  {
+    std::vector<uint32_t> ord(ng);
+    for (size_t i = 0; i < ng; ++i) ord[i] = (uint32_t)i;
+    std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return gstart32[a] < gstart32[b]; });
+    std::vector<uint32_t> c2(ng), s2(ng);
+    for (size_t i = 0; i < ng; ++i) { c2[i] = gcount[ord[i]]; s2[i] = gstart32[ord[i]]; }
+    gcount.swap(c2);
+    gstart32.swap(s2);
+  }
+  std::vector<uint64_t> gstart(ng + 1);
+  for (size_t i = 0; i < ng; ++i) gstart[i] = gstart32[i];
+  gstart[ng] = nd;
+  std::vector<uint32_t> seg_first;
+  std::vector<RankSeg> segs;
+  build_rank_segments(gcount.data(), gstart.data(), ng, total, seg_first, segs);
+  const size_t nsg = segs.size();
+  std::vector<unsigned long long> j0(nsg);
+  std::vector<double> x0(nsg), inc(nsg);
+  for (size_t i = 0; i < nsg; ++i) { j0[i] = segs[i].j0; x0[i] = segs[i].x0; inc[i] = segs[i].inc; }
+  gstart32.push_back((uint32_t)std::min<uint64_t>(nd, 0xffffffffull));
+  // ---- scale of the exact scan, scores into the slots ----
+  double wmax;
+  if (mode == KS_MODE_RANK) {
+    const double rmax = fma((double)(nd - 1 - gstart[ng - 1] - j0[nsg - 1]), inc[nsg - 1], x0[nsg - 1]);
+    wmax = std::max(fabs(0.0 - thr), fabs(rmax - thr));
+  } else {
+    wmax = std::max(fabs(1.0 - thr), fabs(-1.0 - thr));
+  }
+  if (!(wmax < 0x1p40)) return ctx->fail(KS_ERR_RANGE, "threshold outside the exact scan range");
+  const uint64_t mw = (uint64_t)(int64_t)min_width;
+  DevScanParams hp;
+  memset(&hp, 0, sizeof hp);
+  hp.qs = qs_for_max(wmax);
+  fx_t mu = fx_ceil_units(min_score, hp.qs);
+  hp.min_width = mw;
+  hp.min_lo = (uint64_t)(unsigned __int128)mu;
+  hp.min_hi = (int64_t)(uint64_t)(((unsigned __int128)mu) >> 64);
+  CK(ctx->prm.ensure(sizeof(DevScanParams)));
+  CK(ctx->sc_gstart.ensure((ng + 1) * 4));
+  CK(ctx->sc_segfirst.ensure((ng + 1) * 4));
+  CK(ctx->sc_segj0.ensure(nsg * 8 + 8));
+  CK(ctx->sc_segx0.ensure(nsg * 8 + 8));
+  CK(ctx->sc_seginc.ensure(nsg * 8 + 8));
+  const bool keep_ranks = nd <= (1ull << 28);  // the rank doubles in order are kept for inspection up to 2 GiB
+  if (keep_ranks) CK(ctx->lg_ranks.ensure((size_t)nd * 8));
+  else ctx->lg_ranks.release();
+  CK(cudaMemcpyAsync(ctx->prm.p, &hp, sizeof hp, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->sc_gstart.p, gstart32.data(), (ng + 1) * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->sc_segfirst.p, seg_first.data(), (ng + 1) * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->sc_segj0.p, j0.data(), nsg * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->sc_segx0.p, x0.data(), nsg * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->sc_seginc.p, inc.data(), nsg * 8, cudaMemcpyHostToDevice, st));
+  large_eval_kernel<<<blocks_exact((size_t)nd, 256), 256, 0, st>>>(
+      skeys, sslots, sidx, scnt, nd, k, ctx->sc_gstart.as<uint32_t>(), (uint32_t)ng, ctx->sc_segfirst.as<uint32_t>(),
+      ctx->sc_segj0.as<unsigned long long>(), ctx->sc_segx0.as<double>(), ctx->sc_seginc.as<double>(), mode, total,
+      param, thr, hp.qs, ctx->lg_slots.as<HashSlot>(), keep_ranks ? ctx->lg_ranks.as<double>() : nullptr);
+  LAUNCHED(1);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));  // host vectors above must outlive the copies
+  ctx->prof_end(KS_PROF_SCORES, psc);
+  ScanTable tab;
+  tab.use_hash = true;
+  return scan_core(ctx, s, k, tab, mw, nullptr, host_out, n_spans, nullptr);
+  KS_CATCH(ctx)
+}
+
+// the sparse table of the last ks_dev_large_regions on this ctx, in (count, code) order: n_distinct entries each
+int ks_large_table(ks_ctx *ctx, uint64_t *codes_out, uint32_t *counts_out, double *ranks_out) {
+  KS_TRY
+  if (!ctx) return KS_ERR_ARG;
+  if (!ctx->lg_nd || !ctx->lg_sorted) return ctx->fail(KS_ERR_ARG, "ks_large_table: no large-k table on this context");
+  CK(cudaSetDevice(ctx->device));
+  const size_t nd = (size_t)ctx->lg_nd;
+  std::vector<uint64_t> comp(nd);
+  CK(cudaMemcpy(comp.data(), ctx->lg_sorted, nd * 8, cudaMemcpyDeviceToHost));
+  const int sh = 2 * ctx->lg_k;
+  const uint64_t kmask = (((uint64_t)1) << sh) - 1;
+  if (ctx->lg_idx) {  // two-pass order: codes sit in code order, idx / cnt in (count, code) order
+    std::vector<uint32_t> idx(nd), cnt(nd);
+    CK(cudaMemcpy(idx.data(), ctx->lg_idx, nd * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cnt.data(), ctx->lg_cnt, nd * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nd; ++i) {
+      if (codes_out) codes_out[i] = comp[idx[i]];
+      if (counts_out) counts_out[i] = cnt[i];
+    }
+  } else {
+    for (size_t i = 0; i < nd; ++i) {
+      if (codes_out) codes_out[i] = comp[i] & kmask;
+      if (counts_out) counts_out[i] = (uint32_t)(comp[i] >> sh);
+    }
+  }
+  if (ranks_out) {
+    if (!ctx->lg_ranks.p) return ctx->fail(KS_ERR_ARG, "ks_large_table: ranks are kept only up to 2^28 distinct k-mers");
+    CK(cudaMemcpy(ranks_out, ctx->lg_ranks.p, nd * 8, cudaMemcpyDeviceToHost));
+  }
+  return KS_OK;
+  KS_CATCH(ctx)
+}
+
+// host-buffer entry point of the large-k path
+int ks_kmer_large_regions(ks_ctx *ctx, const char *const *seqs, const int64_t *lens, int nseq, int k, int mode,
+                          double param, double thr, int min_width, double min_score, double *n_words,
+                          uint64_t *n_distinct, ks_spans *out) {
+  KS_TRY
+  if (!ctx) return KS_ERR_ARG;
+  if (!seqs || !lens || nseq < 1)
+    return ctx->fail(KS_ERR_ARG, "seq_r must be a character vector of length at least one");
+  if (!out) return ctx->fail(KS_ERR_ARG, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  ks_seqset *ss = nullptr;
+  int rc = host_set_acquire(ctx, lens, nseq, &ss);
+  if (rc) return rc;
+  rc = upload_impl(ctx, ss, seqs, lens, nseq, 0, nullptr);
+  if (rc) return rc;
+  return ks_dev_large_regions(ctx, ss, k, mode, param, thr, min_width, min_score, n_words, n_distinct, out, nullptr);
   KS_CATCH(ctx)
 }
 

@@ -21,6 +21,7 @@
 #include <type_traits>
 
 #include "ks_chunk.cuh"
+#include "ks_hash.cuh"
 
 namespace ks {
 
@@ -278,6 +279,10 @@ struct LevelArgs {
   const uint2 *core;
   // rank mode (kLut == 3): gather the 4-byte position p of the k-mer in the stable (count, index) order and
   // evaluate the rank from the linear pieces of ks_rankseg.h (rank_value below)
+  // large k (kLut == 4, k = 16 .. 31): 64-bit codes, the score of a k-mer sits in its slot of the hash table
+  const HashSlot *hslots;
+  uint64_t hmask, kmask64;
+  int64_t pk_first;  // first chunk of the packed arrays that exists (front of the buffer / of a window set)
   const uint32_t *rk_pos;
   const uint32_t *rk_p0;
   const double *rk_x0, *rk_inc;
@@ -484,8 +489,8 @@ constexpr uint32_t CORE_ESCAPE = 255;  // class byte of a core record: "the clas
 template <int kLut, bool kTr = false, bool kSumm = false, bool kCore = false>
 __global__ void __launch_bounds__(TILE_THREADS,
                                   kLut == 3 ? KS_GATHER_MINBLOCKS_RANK
-                                  : kSumm ? (kLut ? KS_GATHER_MINBLOCKS_SUMM : KS_GATHER_MINBLOCKS_TABLE_SUMM)
-                                          : (kLut ? KS_GATHER_MINBLOCKS : KS_GATHER_MINBLOCKS_TABLE))
+                                  : kSumm ? ((kLut == 1 || kLut == 2) ? KS_GATHER_MINBLOCKS_SUMM : KS_GATHER_MINBLOCKS_TABLE_SUMM)
+                                          : ((kLut == 1 || kLut == 2) ? KS_GATHER_MINBLOCKS : KS_GATHER_MINBLOCKS_TABLE))
 scan_gather_kernel(const LevelArgs A) {
   __shared__ Xf s_wxf[TILE_WARPS + 1];
   __shared__ int64_t s_lut[kCore ? CORE_ESCAPE : 1];  // scores of the classes a core record can name
@@ -532,14 +537,24 @@ scan_gather_kernel(const LevelArgs A) {
       head = (q == c0);
     }
   }
-  // ---- packed window [p0 - 16, p0 + 16) ----
-  uint64_t X;
-  uint32_t brk32;
-  load_window(A, p0, X, brk32);
+  // ---- packed window [p0 - 16, p0 + 16) ([p0 - 32, p0 + 16) for 64-bit codes) ----
+  uint64_t X = 0;
+  uint32_t brk32 = 0;
+  uint32_t w_hi32 = 0;
+  uint64_t w_lo64 = 0;
   // ---- codes, gather (16 independent loads in flight), scores, chunk transform ----
   uint32_t code[CHUNK], scored;
   uint32_t tr_first = 0;
-  if (kTr) {
+  if (kLut == 4) {
+    uint64_t brk48;
+    load_window_wide(A.pk, A.brk, A.pk_first, p0, w_hi32, w_lo64, brk48);
+    const uint32_t inside = n_in >= 16 ? 0xffffu : ((1u << n_in) - 1u);
+    scored = (uint32_t)(run_ending64(~brk48, A.k + 1) >> 32) & inside;  // position and the k before it: no break
+  } else {
+    load_window(A, p0, X, brk32);
+  }
+  if (kLut == 4) {
+  } else if (kTr) {
     // k-mer ENDING at every position; the first k-mer of a run carries the initial score (:344-354)
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) code[j] = (uint32_t)(X >> (30 - 2 * j)) & A.kmask;
@@ -594,7 +609,13 @@ scan_gather_kernel(const LevelArgs A) {
     // rank mode: 4-byte position in the rank order (4^k x 4 B, L2 resident at k <= 12) instead of the 8-byte score
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u32_keep(&A.rk_pos[code[j]], keep) : 0u;
-  } else if (kLut) {
+  } else if (kLut == 4) {
+    // large k: the k-mer ending at position j - 1 sits 32 - 2j bits above the low end of the 96-bit window
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j)
+      sv[j] = (scored & (1u << j)) ? hash_lookup(A.hslots, A.hmask, wide_code(w_hi32, w_lo64, 32 - 2 * j, A.kmask64))
+                                   : WFX_KILL;
+  } else if (kLut == 1) {
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u32_keep(&A.counts[code[j]], keep) : 0u;
   } else {
@@ -618,7 +639,7 @@ scan_gather_kernel(const LevelArgs A) {
     if (kLut == 2 && kCore) return c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&A.lut[c[j]]);
     if (kLut == 2) return __ldg(&A.lut[c[j]]);
     if (kLut == 3) return rank_value(A, s_rk, c[j], rk_qs);
-    if (kLut) {
+    if (kLut == 1) {
       if (c[j] < A.lut_size) return __ldg(&A.lut[c[j]]);
       uint32_t lo = 0, hi = A.sp_n;  // rare: very abundant k-mer, look it up in the sorted sparse list
       while (hi - lo > 1) {
@@ -670,7 +691,7 @@ scan_gather_kernel(const LevelArgs A) {
     live = gc.live; ta = gc.ta; tb = gc.tb; tkill = gc.kill;
     if (kSumm) summ = gc.summary();
   }
-  if (A.inscan) {
+  if (kLut != 4 && A.inscan) {
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j)
       if (scored & (1u << j)) atomicAdd(&A.inscan[code[j]], 1);
@@ -1025,20 +1046,29 @@ __global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
   const uint32_t live = fl & 0xffffu;
   const int64_t p0 = A.nseg == 0 ? A.dense_start + 16 * q : A.st_p0[q];
   // the gather kernel kept only the summary of this chunk: decode and gather its positions again
-  uint64_t X;
-  uint32_t brk32;
-  load_window(A, p0, X, brk32);
+  uint64_t X = 0;
+  uint32_t brk32 = 0;
+  uint32_t w_hi32 = 0;
+  uint64_t w_lo64 = 0;
+  if (kLut == 4) {
+    uint64_t brk48;
+    load_window_wide(A.pk, A.brk, A.pk_first, p0, w_hi32, w_lo64, brk48);
+  } else {
+    load_window(A, p0, X, brk32);
+  }
   int64_t s[CHUNK];
 #pragma unroll
   for (int j = 0; j < CHUNK; ++j) {
     int64_t v = 0;
     if (live & (1u << j)) {
       const uint32_t code = (uint32_t)(X >> (32 - 2 * j)) & A.kmask;  // k-mer ending at position j - 1
-      if (kLut == 2) {
+      if (kLut == 4) {
+        v = hash_lookup(A.hslots, A.hmask, wide_code(w_hi32, w_lo64, 32 - 2 * j, A.kmask64));
+      } else if (kLut == 2) {
         v = __ldg(&A.lut[__ldg(&A.cls[code])]);
       } else if (kLut == 3) {
         v = rank_value(A, nullptr, __ldg(&A.rk_pos[code]), A.prm->qs);
-      } else if (kLut) {
+      } else if (kLut == 1) {
         const uint32_t c = __ldg(&A.counts[code]);
         if (c < A.lut_size) {
           v = __ldg(&A.lut[c]);
