@@ -197,6 +197,17 @@ int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double par
  * ALL shards (e.g. after an all-gather).  Spans come back with global coordinates; a span is reported
  * by the shard in which it closes. */
 typedef int (*ks_exchange_fn)(void *user, int what, const void *mine48, void *carry_in48);
+/* Rank-mode score stage sliced over the devices of a multi-GPU run: the summed count table is identical on every
+ * device, so device `slice` of `nslices` sorts and ranks only its slice [slice * 4^k / nslices, (slice + 1) * 4^k /
+ * nslices) of the k-mer index space; the slices' run-length tables (count, multiplicity: a few thousand pairs) are
+ * exchanged through `fn`, called on the host: it must fill `all` with the `bytes` of every slice in slice order
+ * (an all-gather).  On return d_scores and the ctx's rank-order position table (ks_ctx_rank_positions, uint32[4^k])
+ * hold the caller's slice; the caller gathers the other slices into both.  Replaces the redundant full sort of
+ * rank_kmers_w (src/kmer_spans.c:189-202) on every device; results are bit-identical to ks_dev_scores. */
+typedef int (*ks_gather_fn)(void *user, const void *mine, size_t bytes, void *all);
+int ks_dev_scores_rank_sliced(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int slice, int nslices,
+                              ks_gather_fn fn, void *user, double *d_scores);
+void *ks_ctx_rank_positions(ks_ctx *ctx);
 /* Shard planner + sharded upload: the layout of ALL sequences is cut into nranks contiguous chunk ranges; shard
  * `rank` owns chunks [chunk0, chunk0 + nchunks) and keeps only bytes [win_lo, win_hi) of the layout in HBM (its
  * range plus the head of the sequence the range starts in, where the re-scans of a span closing in the range may

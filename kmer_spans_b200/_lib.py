@@ -27,6 +27,7 @@ class KspansError(RuntimeError):
 
 _lib = None
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
+GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
 _vp, _i, _d, _i64 = C.c_void_p, C.c_int, C.c_double, C.c_int64
 _pd = C.POINTER(C.c_double)
@@ -69,6 +70,8 @@ SIGNATURES = {
     "ks_dev_scan_counts": (_i, [_vp, _vp, _i, _vp, _d, _i, _d, C.POINTER(KsSpans), _pu64]),
     "ks_dev_scan_ranks": (_i, [_vp, _vp, _i, _d, _i, _d, C.POINTER(KsSpans), _pu64]),
     "ks_dev_scan_ranks_shard": (_i, [_vp, _vp, _i, _d, _i, _d, _i64, _i64, _vp, _vp, C.POINTER(KsSpans), _pu64]),
+    "ks_dev_scores_rank_sliced": (_i, [_vp, _i, _vp, _d, _i, _i, _vp, _vp, _vp]),
+    "ks_ctx_rank_positions": (_vp, [_vp]),
     "ks_seqset_chunks": (_i64, [_vp]),
     "ks_plan_shard": (_i, [C.POINTER(C.c_int64), _i, _i, _i] + [C.POINTER(C.c_int64)] * 4),
     "ks_seqset_upload_window": (_i, [_vp] + _SEQS + [_i64, _i64, C.POINTER(_vp)]),

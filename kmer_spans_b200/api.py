@@ -226,6 +226,26 @@ class Context:
     def dev_scores(self, k, d_counts, total, mode, d_scores, param=float("nan")):
         self._ck(self.lib.ks_dev_scores(self.h, int(k), d_counts, float(total), int(mode), float(param), d_scores))
 
+    def dev_scores_rank_sliced(self, k, d_counts, total, slice_, nslices, gather, d_scores):
+        """rank-mode score stage for ONE slice of the k-mer index space (multi-GPU); gather(bytes) -> list of the
+        blobs of all slices in slice order.  Fills d_scores and the rank-order positions for this slice only."""
+        def cb(user, mine, nbytes, out):
+            try:
+                blobs = gather(C.string_at(mine, nbytes))
+                for i, b in enumerate(blobs):
+                    C.memmove(out + i * nbytes, b, nbytes)
+                return 0
+            except Exception:  # pragma: no cover - surfaced as a C-side error
+                import traceback
+                traceback.print_exc()
+                return 1
+        cfn = _lib.GATHER_FN(cb)
+        self._ck(self.lib.ks_dev_scores_rank_sliced(self.h, int(k), C.c_void_p(d_counts), float(total), int(slice_),
+                                                    int(nslices), C.cast(cfn, C.c_void_p), None, C.c_void_p(d_scores)))
+
+    def rank_positions_ptr(self):
+        return int(self.lib.ks_ctx_rank_positions(self.h) or 0)
+
     def dev_scan(self, ss, k, d_W, thr, min_w, min_score, d_inscan=0, fetch_spans=True):
         ns = C.c_uint64(0)
         sp = KsSpans()

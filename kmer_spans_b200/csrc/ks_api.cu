@@ -1131,6 +1131,65 @@ static int ensure_hpin(ks_ctx *ctx) {
 
 // ------------------------------------------------------------------------------------------------
 // stage: score tables
+// The pieces of the rank order addressed by absolute position, for the scan's 4-byte gather (rank_value,
+// ks_kernels.cuh): piece starts, the shared-memory image (bucket table + the window of pieces that covers the most
+// positions), and the scalars the kernels need.  The vectors in `rp` must stay alive until the stream is synchronised.
+namespace {
+struct RankPosHost {
+  std::vector<uint32_t> p0;
+  std::vector<RankSmem> blob;
+};
+}  // namespace
+static int rank_positions_setup(ks_ctx *ctx, int k, size_t n, size_t ng, const std::vector<uint64_t> &gstart,
+                                const std::vector<uint32_t> &seg_first, const std::vector<unsigned long long> &j0,
+                                const std::vector<double> &x0, const std::vector<double> &inc, RankPosHost &rp) {
+  cudaStream_t st = ctx->stream;
+  const size_t nsg = j0.size();
+  std::vector<uint32_t> &p0 = rp.p0;
+  rp.blob.resize(1);
+  p0.resize(nsg + 1);
+  for (size_t g = 0; g < ng; ++g)
+    for (uint32_t i = seg_first[g]; i < seg_first[g + 1]; ++i) p0[i] = (uint32_t)(gstart[g] + j0[i]);
+  p0[nsg] = (uint32_t)n;
+  // window of at most RK_SMEM_PIECES consecutive pieces that covers the most positions of the rank order
+  size_t w0 = 0, w1 = std::min<size_t>(nsg, RK_SMEM_PIECES);
+  {
+    uint64_t best = (uint64_t)p0[w1] - p0[0];
+    for (size_t i = 1; i + RK_SMEM_PIECES <= nsg; ++i) {
+      const uint64_t cover = (uint64_t)p0[i + RK_SMEM_PIECES] - p0[i];
+      if (cover > best) { best = cover; w0 = i; w1 = i + RK_SMEM_PIECES; }
+    }
+  }
+  const uint32_t win_lo = p0[w0], win_len = p0[w1] - p0[w0];
+  int shift = 0;
+  while (((uint64_t)RK_BUCKETS << shift) < win_len) ++shift;
+  RankSmem &im = rp.blob[0];
+  memset(&im, 0, sizeof im);
+  {
+    size_t a = w0;
+    for (size_t bkt = 0; bkt <= (size_t)RK_BUCKETS; ++bkt) {
+      const uint64_t pos = (uint64_t)win_lo + ((uint64_t)bkt << shift);
+      while (a + 1 < w1 && p0[a + 1] <= pos) ++a;
+      im.bucket[bkt] = (uint32_t)(a - w0);
+    }
+  }
+  for (size_t i = 0; i <= (size_t)RK_SMEM_PIECES; ++i) im.p0[i] = w0 + i <= w1 ? p0[w0 + i] : 0xffffffffu;
+  for (size_t i = 0; i < (size_t)RK_SMEM_PIECES && w0 + i < w1; ++i) { im.x0[i] = x0[w0 + i]; im.inc[i] = inc[w0 + i]; }
+  CK(ctx->rk_pos.ensure(n * 4));
+  CK(ctx->rk_p0.ensure((nsg + 1) * 4));
+  CK(ctx->rk_blob.ensure(sizeof(RankSmem)));
+  CK(cudaMemcpyAsync(ctx->rk_p0.p, p0.data(), (nsg + 1) * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->rk_blob.p, &im, sizeof im, cudaMemcpyHostToDevice, st));
+  ctx->rk_shift = shift;
+  ctx->rk_k = k;
+  ctx->rk_npieces = (uint32_t)nsg;
+  ctx->rk_win_lo = win_lo;
+  ctx->rk_win_len = win_len;
+  ctx->rk_n = (uint32_t)n;
+  ctx->rk_max = fma((double)(n - 1 - p0[nsg - 1]), inc[nsg - 1], x0[nsg - 1]);  // rank of the last k-mer in order
+  return KS_OK;
+}
+
 static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double total, bool total_on_device,
                            int mode, double param, double *d_scores, double *total_out);
 int ks_dev_scores(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int mode, double param,
@@ -1411,49 +1470,10 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
       CK(cudaMemcpyAsync(ctx->sc_seginc.p, inc.data(), nsg * 8, cudaMemcpyHostToDevice, st));
       // the same pieces addressed by absolute position in the rank order, for the scan's 4-byte gather
       const bool want_pos = mode == KS_MODE_RANK && nsg > 0 && n < 0xffffffffull && getenv("KS_NO_RANK_POS") == nullptr;
-      std::vector<uint32_t> p0;
-      std::vector<RankSmem> blob(1);
+      RankPosHost rp;  // host images: they must outlive the copies (synchronised below)
       if (want_pos) {
-        p0.resize(nsg + 1);
-        for (size_t g = 0; g < ng; ++g)
-          for (uint32_t i = seg_first[g]; i < seg_first[g + 1]; ++i) p0[i] = (uint32_t)(gstart[g] + j0[i]);
-        p0[nsg] = (uint32_t)n;
-        // window of at most RK_SMEM_PIECES consecutive pieces that covers the most positions of the rank order
-        size_t w0 = 0, w1 = std::min<size_t>(nsg, RK_SMEM_PIECES);
-        {
-          uint64_t best = (uint64_t)p0[w1] - p0[0];
-          for (size_t i = 1; i + RK_SMEM_PIECES <= nsg; ++i) {
-            const uint64_t cover = (uint64_t)p0[i + RK_SMEM_PIECES] - p0[i];
-            if (cover > best) { best = cover; w0 = i; w1 = i + RK_SMEM_PIECES; }
-          }
-        }
-        const uint32_t win_lo = p0[w0], win_len = p0[w1] - p0[w0];
-        int shift = 0;
-        while (((uint64_t)RK_BUCKETS << shift) < win_len) ++shift;
-        RankSmem &im = blob[0];
-        memset(&im, 0, sizeof im);
-        {
-          size_t a = w0;
-          for (size_t bkt = 0; bkt <= (size_t)RK_BUCKETS; ++bkt) {
-            const uint64_t pos = (uint64_t)win_lo + ((uint64_t)bkt << shift);
-            while (a + 1 < w1 && p0[a + 1] <= pos) ++a;
-            im.bucket[bkt] = (uint32_t)(a - w0);
-          }
-        }
-        for (size_t i = 0; i <= (size_t)RK_SMEM_PIECES; ++i) im.p0[i] = w0 + i <= w1 ? p0[w0 + i] : 0xffffffffu;
-        for (size_t i = 0; i < (size_t)RK_SMEM_PIECES && w0 + i < w1; ++i) { im.x0[i] = x0[w0 + i]; im.inc[i] = inc[w0 + i]; }
-        CK(ctx->rk_pos.ensure(n * 4));
-        CK(ctx->rk_p0.ensure((nsg + 1) * 4));
-        CK(ctx->rk_blob.ensure(sizeof(RankSmem)));
-        CK(cudaMemcpyAsync(ctx->rk_p0.p, p0.data(), (nsg + 1) * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->rk_blob.p, &im, sizeof im, cudaMemcpyHostToDevice, st));
-        ctx->rk_shift = shift;
-        ctx->rk_k = k;
-        ctx->rk_npieces = (uint32_t)nsg;
-        ctx->rk_win_lo = win_lo;
-        ctx->rk_win_len = win_len;
-        ctx->rk_n = (uint32_t)n;
-        ctx->rk_max = fma((double)(n - 1 - p0[nsg - 1]), inc[nsg - 1], x0[nsg - 1]);  // rank of the last k-mer in order
+        rc = rank_positions_setup(ctx, k, n, ng, gstart, seg_first, j0, x0, inc, rp);
+        if (rc) return rc;
       }
       rank_eval_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(
           svals, n, ctx->sc_gstart.as<uint32_t>(), (uint32_t)ng, ctx->sc_segfirst.as<uint32_t>(),
@@ -1472,6 +1492,195 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
   }
   return KS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Rank-mode score stage SLICED over several devices (multi-GPU): the summed count table is the
+// same on every device, so device `slice` of `nslices` derives the rank order of its own slice of the k-mer index
+// space only -- stable sort of the slice by count, run-length table of the slice -- and the slices' run-length tables
+// (a few thousand entries) are exchanged through `fn`.  With them every device knows, for each distinct count, how many
+// k-mers hold it in all slices before its own: position in the global (count, index) order = first position of the
+// count's group + that number + the ordinal inside the slice.  The linear pieces of ks_rankseg.h are derived on every
+// device from the merged table (identical), ranks and rank-order positions are written for the slice
+// [slice * n / nslices, (slice + 1) * n / nslices) only; the caller all-gathers both tables.
+static int rank_scores_sliced(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int slice, int nslices,
+                              ks_gather_fn fn, void *user, double *d_scores) {
+  if (!ctx) return KS_ERR_ARG;
+  if (!d_counts || !d_scores || !fn || nslices < 1 || slice < 0 || slice >= nslices)
+    return ctx->fail(KS_ERR_ARG, "ks_dev_scores_rank_sliced: bad arguments");
+  int rc = check_k(ctx, k);
+  if (rc) return rc;
+  if (!(total > 0)) return ctx->fail(KS_ERR_ARG, "ks_dev_scores_rank_sliced: no k-mers counted");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)1 << (2 * k);
+  const size_t lo = n * (size_t)slice / (size_t)nslices, hi = n * (size_t)(slice + 1) / (size_t)nslices;
+  const size_t m = hi - lo;
+  ctx->rk_valid = false;
+  struct ProfScope {
+    ks_ctx *c; cudaEvent_t a;
+    ~ProfScope() { c->prof_end(KS_PROF_SCORES, a); }
+  } prof_scope{ctx, ctx->prof_begin()};
+  // 1. stable (count, index) order of the slice
+  std::vector<uint32_t> lcount, lstart;  // local run-length table: count, first local sorted position
+  uint32_t *skeys = nullptr, *svals = nullptr;
+  if (m) {
+    CK(ctx->sc_keys_a.ensure(m * 4));
+    CK(ctx->sc_keys_b.ensure(m * 4));
+    CK(ctx->sc_vals_a.ensure(m * 4));
+    CK(ctx->sc_vals_b.ensure(m * 4));
+    size_t nb = radix_nblocks(m);
+    CK(ctx->sort_hist.ensure((256 * nb + 2) * 4));
+    CK(ctx->sort_scan.ensure(exclusive_scan_scratch_elems(256 * nb) * 4));
+    CK(ctx->sc_small.ensure(64));
+    CK(cudaMemsetAsync(ctx->sc_small.p, 0, 64, st));
+    uint32_t *d_max = ctx->sc_small.as<uint32_t>();
+    uint32_t *d_ngroups = d_max + 1;
+    CK(cudaMemcpyAsync(ctx->sc_keys_a.p, d_counts + lo, m * 4, cudaMemcpyDeviceToDevice, st));
+    max_u32_kernel<<<grid_for(m, 256), 256, 0, st>>>(ctx->sc_keys_a.as<uint32_t>(), m, d_max);
+    LAUNCHED(1);
+    uint32_t maxc = 0;
+    CK(cudaMemcpyAsync(&maxc, d_max, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int nbits = 0;
+    while (nbits < 32 && (maxc >> nbits) != 0) ++nbits;
+    RadixScratch rs{ctx->sort_hist.as<uint32_t>(), ctx->sort_scan.as<uint32_t>()};
+    LAUNCHED(radix_sort_pairs<uint32_t>(ctx->sc_keys_a.as<uint32_t>(), ctx->sc_vals_a.as<uint32_t>(),
+                                        ctx->sc_keys_b.as<uint32_t>(), ctx->sc_vals_b.as<uint32_t>(), m, nbits, true,
+                                        rs, st, &skeys, &svals));
+    CK(cudaGetLastError());
+    size_t gcap = (size_t)(sqrt(2.0 * total) + 16.0);
+    if (gcap > m) gcap = m;
+    if (gcap < 16) gcap = 16;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      CK(ctx->sc_gcount.ensure((gcap + 1) * 4));
+      CK(ctx->sc_gstart.ensure((gcap + 1) * 4));
+      CK(cudaMemsetAsync(d_ngroups, 0, 4, st));
+      rle_heads_kernel<<<blocks_exact(m, 256), 256, 0, st>>>(skeys, m, ctx->sc_gcount.as<uint32_t>(),
+                                                             ctx->sc_gstart.as<uint32_t>(), d_ngroups, (uint32_t)gcap);
+      LAUNCHED(1);
+      uint32_t ngl = 0;
+      CK(cudaMemcpyAsync(&ngl, d_ngroups, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (ngl > gcap) { gcap = ngl; continue; }
+      lcount.resize(ngl);
+      lstart.resize(ngl);
+      CK(cudaMemcpyAsync(lcount.data(), ctx->sc_gcount.p, (size_t)ngl * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(lstart.data(), ctx->sc_gstart.p, (size_t)ngl * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      break;
+    }
+    std::vector<uint32_t> ord(lcount.size());
+    for (size_t i = 0; i < ord.size(); ++i) ord[i] = (uint32_t)i;
+    std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return lstart[a] < lstart[b]; });
+    std::vector<uint32_t> c2(ord.size()), s2(ord.size());
+    for (size_t i = 0; i < ord.size(); ++i) { c2[i] = lcount[ord[i]]; s2[i] = lstart[ord[i]]; }
+    lcount.swap(c2);
+    lstart.swap(s2);
+  }
+  const size_t ngl = lcount.size();
+  // 2. exchange the run-length tables: sizes first, then (count, multiplicity) pairs padded to the longest
+  std::vector<uint64_t> sizes((size_t)nslices, 0);
+  {
+    uint64_t mine = ngl;
+    if (fn(user, &mine, sizeof mine, sizes.data())) return ctx->fail(KS_ERR_ARG, "rank exchange (sizes) failed");
+  }
+  size_t maxg = 0;
+  for (uint64_t v : sizes) maxg = std::max<size_t>(maxg, (size_t)v);
+  if (maxg == 0) return ctx->fail(KS_ERR_ARG, "ks_dev_scores_rank_sliced: empty table");
+  std::vector<uint32_t> mine_pairs(2 * maxg, 0), all_pairs(2 * maxg * (size_t)nslices, 0);
+  for (size_t g = 0; g < ngl; ++g) {
+    mine_pairs[2 * g] = lcount[g];
+    mine_pairs[2 * g + 1] = (uint32_t)((g + 1 < ngl ? lstart[g + 1] : (uint32_t)m) - lstart[g]);
+  }
+  if (fn(user, mine_pairs.data(), mine_pairs.size() * 4, all_pairs.data()))
+    return ctx->fail(KS_ERR_ARG, "rank exchange (tables) failed");
+  // 3. merged table: distinct counts ascending, total multiplicity, multiplicity in the slices before this one
+  std::vector<uint32_t> gcount;
+  {
+    std::vector<uint32_t> allc;
+    for (int sidx = 0; sidx < nslices; ++sidx)
+      for (size_t g = 0; g < (size_t)sizes[sidx]; ++g) allc.push_back(all_pairs[2 * (maxg * sidx + g)]);
+    std::sort(allc.begin(), allc.end());
+    allc.erase(std::unique(allc.begin(), allc.end()), allc.end());
+    gcount.swap(allc);
+  }
+  const size_t ng = gcount.size();
+  std::vector<uint64_t> gmult(ng, 0), before(ng, 0);
+  for (int sidx = 0; sidx < nslices; ++sidx)
+    for (size_t g = 0; g < (size_t)sizes[sidx]; ++g) {
+      const uint32_t c = all_pairs[2 * (maxg * sidx + g)], mu = all_pairs[2 * (maxg * sidx + g) + 1];
+      const size_t G = (size_t)(std::lower_bound(gcount.begin(), gcount.end(), c) - gcount.begin());
+      gmult[G] += mu;
+      if (sidx < slice) before[G] += mu;
+    }
+  std::vector<uint64_t> gstart(ng + 1, 0);
+  for (size_t G = 0; G < ng; ++G) gstart[G + 1] = gstart[G] + gmult[G];
+  if (gstart[ng] != n) return ctx->fail(KS_ERR_ARG, "rank exchange: the slices do not add up to 4^k entries");
+  std::vector<uint32_t> seg_first;
+  std::vector<RankSeg> segs;
+  build_rank_segments(gcount.data(), gstart.data(), ng, total, seg_first, segs);
+  const size_t nsg = segs.size();
+  std::vector<unsigned long long> j0(nsg);
+  std::vector<double> x0(nsg), inc(nsg);
+  for (size_t i = 0; i < nsg; ++i) { j0[i] = segs[i].j0; x0[i] = segs[i].x0; inc[i] = segs[i].inc; }
+  // 4. per local group: where it sits in the global order
+  std::vector<uint32_t> lg_first(ngl + 1, 0), lg_seg0(ngl, 0), lg_seg1(ngl, 0);
+  std::vector<unsigned long long> lg_j(ngl, 0), lg_p(ngl, 0);
+  for (size_t g = 0; g < ngl; ++g) {
+    const size_t G = (size_t)(std::lower_bound(gcount.begin(), gcount.end(), lcount[g]) - gcount.begin());
+    lg_first[g] = lstart[g];
+    lg_j[g] = before[G];                 // ordinal of the slice's first member inside the global group
+    lg_p[g] = gstart[G] + before[G];     // its position in the global order
+    lg_seg0[g] = seg_first[G];
+    lg_seg1[g] = seg_first[G + 1];
+  }
+  lg_first[ngl] = (uint32_t)m;
+  RankPosHost rp;
+  const bool want_pos = n < 0xffffffffull;
+  if (want_pos) {
+    rc = rank_positions_setup(ctx, k, n, ng, gstart, seg_first, j0, x0, inc, rp);
+    if (rc) return rc;
+  }
+  if (m) {
+    CK(ctx->sc_gstart.ensure((ngl + 1) * 4));
+    CK(ctx->sc_segfirst.ensure((2 * ngl + 2) * 4));
+    CK(ctx->sc_gcount.ensure((4 * ngl + 4) * 8));
+    CK(ctx->sc_segj0.ensure(nsg * 8 + 8));
+    CK(ctx->sc_segx0.ensure(nsg * 8 + 8));
+    CK(ctx->sc_seginc.ensure(nsg * 8 + 8));
+    unsigned long long *d_lgj = ctx->sc_gcount.as<unsigned long long>();
+    unsigned long long *d_lgp = d_lgj + ngl + 1;
+    uint32_t *d_seg0 = ctx->sc_segfirst.as<uint32_t>(), *d_seg1 = d_seg0 + ngl + 1;
+    CK(cudaMemcpyAsync(ctx->sc_gstart.p, lg_first.data(), (ngl + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_lgj, lg_j.data(), ngl * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_lgp, lg_p.data(), ngl * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_seg0, lg_seg0.data(), ngl * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_seg1, lg_seg1.data(), ngl * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->sc_segj0.p, j0.data(), nsg * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->sc_segx0.p, x0.data(), nsg * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->sc_seginc.p, inc.data(), nsg * 8, cudaMemcpyHostToDevice, st));
+    rank_eval_slice_kernel<<<blocks_exact(m, 256), 256, 0, st>>>(
+        svals, m, (uint32_t)lo, ctx->sc_gstart.as<uint32_t>(), (uint32_t)ngl, d_lgj, d_lgp, d_seg0, d_seg1,
+        ctx->sc_segj0.as<unsigned long long>(), ctx->sc_segx0.as<double>(), ctx->sc_seginc.as<double>(), d_scores,
+        want_pos ? ctx->rk_pos.as<uint32_t>() : nullptr);
+    LAUNCHED(1);
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(st));  // host vectors above must outlive the copies
+  ctx->rk_valid = want_pos;
+  return KS_OK;
+}
+
+int ks_dev_scores_rank_sliced(ks_ctx *ctx, int k, const int32_t *d_counts, double total, int slice, int nslices,
+                              ks_gather_fn fn, void *user, double *d_scores) {
+  KS_TRY
+  return rank_scores_sliced(ctx, k, d_counts, total, slice, nslices, fn, user, d_scores);
+  KS_CATCH(ctx)
+}
+
+// the rank-order position table (uint32[4^k]) the last rank-mode score stage left on this ctx: after the sliced
+// stage only the caller's slice is filled, and the caller gathers the other slices into it
+void *ks_ctx_rank_positions(ks_ctx *ctx) { return ctx ? ctx->rk_pos.p : nullptr; }
 
 // ------------------------------------------------------------------------------------------------
 // stage: scan + spans

@@ -1332,6 +1332,39 @@ __global__ void __launch_bounds__(256) rank_eval_kernel(const uint32_t *__restri
   ranks[vals[p]] = fma((double)(j - __ldg(&seg_j0[a])), __ldg(&seg_inc[a]), __ldg(&seg_x0[a]));
 }
 
+// the same for ONE SLICE of the k-mer index space (multi-GPU, rank_scores_sliced): q = position in the slice's own
+// (count, index) order, vals[q] = index inside the slice.  Per local group: first local position (lg_first), ordinal of
+// its first member inside the global tie group (lg_j), its position in the global order (lg_p), the global group's
+// pieces [seg0, seg1).
+__global__ void __launch_bounds__(256) rank_eval_slice_kernel(const uint32_t *__restrict__ vals, size_t m, uint32_t lo_index,
+                                                              const uint32_t *__restrict__ lg_first, uint32_t ngl,
+                                                              const unsigned long long *__restrict__ lg_j,
+                                                              const unsigned long long *__restrict__ lg_p,
+                                                              const uint32_t *__restrict__ seg0,
+                                                              const uint32_t *__restrict__ seg1,
+                                                              const unsigned long long *__restrict__ seg_j0,
+                                                              const double *__restrict__ seg_x0,
+                                                              const double *__restrict__ seg_inc,
+                                                              double *__restrict__ ranks, uint32_t *__restrict__ rk_pos) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  uint32_t lo = 0, hi = ngl;  // largest g with lg_first[g] <= q
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&lg_first[mid]) <= q) lo = mid; else hi = mid;
+  }
+  const unsigned long long d = q - __ldg(&lg_first[lo]);
+  const unsigned long long j = __ldg(&lg_j[lo]) + d;
+  uint32_t a = __ldg(&seg0[lo]), b = __ldg(&seg1[lo]);
+  while (b - a > 1) {
+    const uint32_t mid = (a + b) >> 1;
+    if (__ldg(&seg_j0[mid]) <= j) a = mid; else b = mid;
+  }
+  const size_t idx = (size_t)lo_index + vals[q];
+  ranks[idx] = fma((double)(j - __ldg(&seg_j0[a])), __ldg(&seg_inc[a]), __ldg(&seg_x0[a]));
+  if (rk_pos) rk_pos[idx] = (uint32_t)(__ldg(&lg_p[lo]) + d);
+}
+
 // frequency-of-counts histogram h[c] (the "histogram plus prefix sum" of the north star, used by the
 // count-function modes, which need no per-k-mer order): block-private shared histogram for c < 4096
 // with warp-aggregated updates, global atomics for 4096 <= c < dense, atomic append for c >= dense.

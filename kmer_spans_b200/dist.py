@@ -348,7 +348,11 @@ class SplitRun:
         ctx.dev_count_range_async(self.ss, k, self.c0, self.cn, st.counts.data_ptr(), st.nwords.data_ptr())
         if self.dist:
             st.reduce_counts(self.dist)
-        total = st.scores_from_counts_dev(k, mode, param)
+        n = 4 ** k
+        if mode == 0 and self.dist and n % self.world == 0 and os.environ.get("KS_NO_SLICED_RANK") is None:
+            total = self._scores_rank_sliced(k)
+        else:
+            total = st.scores_from_counts_dev(k, mode, param)
         if mode == 0:
             r = ctx.dev_scan_ranks_shard(self.ss, k, thr, min_w, min_score, self.c0, self.cn, self._exchange)
         else:
@@ -357,6 +361,37 @@ class SplitRun:
                                    min_w, min_score, self.c0, self.cn, self._exchange, use_counts=use_counts)
         r["n"] = total
         return r
+
+    def _scores_rank_sliced(self, k):
+        """weighted-rank score stage with every rank sorting and ranking only its slice of the k-mer index space;
+        the slices of the rank table and of the rank-order positions are all-gathered over NCCL on the ctx stream"""
+        t, st, ctx, dist = self.torch, self.stages, self.ctx, self.dist
+        n = 4 ** k
+        ctx.sync()
+        total = float(int(st.nwords.item()))
+        st.mode = 0
+        if total == 0:
+            return st.scores_from_counts_dev(k, 0, float("nan"))
+
+        def gather(blob):
+            mine = t.frombuffer(bytearray(blob), dtype=t.uint8).to(st.device)
+            out = t.empty(len(blob) * self.world, dtype=t.uint8, device=st.device)
+            dist.all_gather_into_tensor(out, mine)
+            flat = out.cpu().numpy().tobytes()
+            return [flat[len(blob) * i:len(blob) * (i + 1)] for i in range(self.world)]
+
+        ctx.dev_scores_rank_sliced(k, st.counts.data_ptr(), total, self.rank, self.world, gather, st.scores.data_ptr())
+        per = n // self.world
+        lo = self.rank * per
+
+        class _Dev:  # the ctx's rank-order position table as a torch tensor (CUDA array interface)
+            def __init__(self, ptr, count):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+        pos = t.as_tensor(_Dev(ctx.rank_positions_ptr(), n), device=st.device)
+        with t.cuda.stream(st.stream()):
+            dist.all_gather_into_tensor(st.scores, st.scores[lo:lo + per].clone())
+            dist.all_gather_into_tensor(pos, pos[lo:lo + per].clone())
+        return total
 
     def free(self):
         self.ss.free()
