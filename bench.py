@@ -503,6 +503,25 @@ def main():
                                             workload="configs[4] subset: 10 000 contigs, k=10, rank mode thr 0.75")
         ss5.free()
 
+    # ---- where the multi-GPU step spends its exchange (CUDA events on the ctx stream, outside the timed region) ----
+    exchange_ms = None
+    if world > 1:
+        acc = np.zeros(3)
+        reps_x = 5
+        for _ in range(reps_x):
+            barrier()
+            ev = []
+            stages.count_async(K)
+            stages.reduce_counts(dist, events=ev)
+            stages.scores_from_counts_dev(K, MODE_LOG2, float("nan"))
+            stages.scan(K, THR, MIN_W, MIN_SCORE, fetch=False)
+            torch.cuda.synchronize(dev)
+            acc += [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])]
+        tx = torch.tensor(acc / reps_x, dtype=torch.float64, device=dev)
+        dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+        exchange_ms = {"wait_for_all_counts_barrier": float(tx[0].item()), "table_sum_kernel": float(tx[1].item()),
+                       "barrier_after_sum": float(tx[2].item()), "what": "max over ranks, mean of 5 steps"}
+
     c3 = None
     if not args.no_config3:
         c3 = config3_record(args, stages, rank, world, dist, torch, barrier)
@@ -554,6 +573,7 @@ def main():
         "parity_check": parity,
         "extra": extra,
         "config3": c3,
+        "exchange_ms": exchange_ms,
     }
     if world == 1 and not args.no_cpu_baseline:
         sample = min(args.n_bases, 25_000_000)

@@ -1241,8 +1241,10 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
     if (((uintptr_t)d_counts & 15u) != 0)
       return ctx->fail(KS_ERR_ARG, "ks_dev_scores: the count table must be 16-byte aligned");
     CK(ctx->sc_small.ensure(64));
-    CK(ctx->foc_hist.ensure((size_t)DENSE * 4));
+    CK(ctx->foc_hist.ensure((size_t)DENSE * 4 + 8192 * 8));  // bins + the compact (count, multiplicity) list
     uint32_t big_cap = 1u << 16;
+    uint32_t npairs = 0;
+    std::vector<uint32_t> full_hist;
     rc = ensure_hpin(ctx);
     if (rc) return rc;
     uint32_t *hist = reinterpret_cast<uint32_t *>(ctx->hpin + ks_ctx::HPIN_HIST);
@@ -1257,19 +1259,30 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
           ctx->foc_big.as<uint32_t>(), ctx->sc_small.as<uint32_t>(), big_cap);
       LAUNCHED(1);
       CK(cudaGetLastError());
-      CK(cudaMemcpyAsync(hsmall, ctx->sc_small.p, 4, cudaMemcpyDeviceToHost, st));
-      if (total_on_device) CK(cudaMemcpyAsync(hsmall + 2, ctx->nwords.p, 8, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(hist, ctx->foc_hist.p, (size_t)DENSE * 4, cudaMemcpyDeviceToHost, st));
+      // the non-empty bins as (count, multiplicity) pairs: a few hundred for a genome, against 65 536 bins
+      const uint32_t PAIR_CAP = 8192;
+      uint2 *d_pairs = reinterpret_cast<uint2 *>(ctx->foc_hist.as<uint32_t>() + DENSE);
+      foc_compact_kernel<<<64, 256, 0, st>>>(ctx->foc_hist.as<uint32_t>(), DENSE, d_pairs,
+                                            ctx->sc_small.as<uint32_t>() + 4, PAIR_CAP);
+      LAUNCHED(1);
+      CK(cudaMemcpyAsync(hsmall, ctx->sc_small.p, 32, cudaMemcpyDeviceToHost, st));
+      if (total_on_device) CK(cudaMemcpyAsync(hsmall + 8, ctx->nwords.p, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(hist, d_pairs, (size_t)PAIR_CAP * 8, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       const uint32_t nbig = hsmall[0];
+      npairs = hsmall[4];
       if (total_on_device) {
         unsigned long long nw;
-        memcpy(&nw, hsmall + 2, 8);
+        memcpy(&nw, hsmall + 8, 8);
         total = (double)nw;
         total_on_device = false;
         if (total_out) *total_out = total;
       }
       if (nbig > big_cap) { big_cap = nbig; continue; }
+      if (npairs > PAIR_CAP) {  // more distinct counts than the compact list holds: read the bins themselves
+        full_hist.resize(DENSE);
+        CK(cudaMemcpy(full_hist.data(), ctx->foc_hist.p, (size_t)DENSE * 4, cudaMemcpyDeviceToHost));
+      }
       big.resize(nbig);
       if (nbig) CK(cudaMemcpy(big.data(), ctx->foc_big.p, (size_t)nbig * 4, cudaMemcpyDeviceToHost));
       break;
@@ -1278,8 +1291,15 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
     // distinct counts ascending with multiplicities
     std::vector<uint32_t> gcount;
     std::vector<uint64_t> gmult;
-    for (uint32_t c = 0; c < DENSE; ++c)
-      if (hist[c]) { gcount.push_back(c); gmult.push_back(hist[c]); }
+    if (!full_hist.empty()) {
+      for (uint32_t c = 0; c < DENSE; ++c)
+        if (full_hist[c]) { gcount.push_back(c); gmult.push_back(full_hist[c]); }
+    } else {
+      std::vector<std::pair<uint32_t, uint32_t>> pr(npairs);
+      for (uint32_t i = 0; i < npairs; ++i) pr[i] = {hist[2 * i], hist[2 * i + 1]};
+      std::sort(pr.begin(), pr.end());
+      for (auto &q : pr) { gcount.push_back(q.first); gmult.push_back(q.second); }
+    }
     for (size_t i = 0; i < big.size();) {
       size_t j = i;
       while (j < big.size() && big[j] == big[i]) ++j;

@@ -28,7 +28,7 @@ constexpr int BK_ROUNDS = 3;    // chunks per thread and tile
 constexpr int BK_THREADS = 256;
 constexpr int BK_TILE_CHUNKS = BK_THREADS * BK_ROUNDS;  // 768 chunks = 12 288 positions, 12 per bucket on average
 constexpr uint32_t BK_PAD = 0xffffu;                    // filler of the 4-entry granules (a sub-key has <= 14 bits)
-constexpr size_t BK_SCATTER_SMEM = BK_BUCKETS * 4 + (size_t)BK_BUCKETS * BK_CAP * 2;
+constexpr size_t BK_SCATTER_SMEM = BK_BUCKETS * 4 + (size_t)BK_BUCKETS * BK_CAP * 2;  // counters + rows
 
 __device__ __forceinline__ unsigned long long block_sum_to(unsigned long long local, unsigned long long *dst) {
 #pragma unroll
@@ -126,9 +126,10 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
   const uint64_t keep = l2_policy_evict_last();
   unsigned long long local = 0;
   const int64_t ntiles = (nchunks + BK_TILE_CHUNKS - 1) / BK_TILE_CHUNKS;
+  constexpr int BPT = BK_BUCKETS / BK_THREADS;  // buckets per thread (flush)
+  for (int i = tid; i < BK_BUCKETS; i += BK_THREADS) s_cnt[i] = 0;
+  __syncthreads();
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    for (int i = tid; i < BK_BUCKETS; i += BK_THREADS) s_cnt[i] = 0;
-    __syncthreads();
     RawChunk raw[BK_ROUNDS];  // all loads of the tile in flight before the first one is used
 #pragma unroll
     for (int r = 0; r < BK_ROUNDS; ++r) {
@@ -141,12 +142,16 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
       if (ci < first + nchunks) {
         uint32_t code[CHUNK], counted;
         pack_decode_raw(raw[r], ci, first, k, kmask, pk_out, brk_out, code, counted);
+        // the 16 rank requests first, the 16 stores after: the latency of a shared-memory atomic with a result is
+        // paid once per chunk, not once per position
+        uint32_t slot[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j)
+          slot[j] = (counted & (1u << j)) ? atomicAdd(&s_cnt[code[j] >> sub_bits], 1u) : 0u;
 #pragma unroll
         for (int j = 0; j < CHUNK; ++j) {
           if (counted & (1u << j)) {
-            const uint32_t b = code[j] >> sub_bits;
-            const uint32_t slot = atomicAdd(&s_cnt[b], 1u);
-            if (slot < (uint32_t)BK_CAP) s_stage[b * BK_CAP + slot] = (uint16_t)(code[j] & submask);
+            if (slot[j] < (uint32_t)BK_CAP) s_stage[(code[j] >> sub_bits) * BK_CAP + slot[j]] = (uint16_t)(code[j] & submask);
             else red_add_u32_keep(&counts[code[j]], 1u, keep);  // the row is full: direct reduction
           }
         }
@@ -154,8 +159,10 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
       }
     }
     __syncthreads();
-    // every thread appends the rows of four buckets to the buckets' regions (granules of 4 sub-keys = 8 bytes)
-    constexpr int BPT = BK_BUCKETS / BK_THREADS;  // buckets per thread
+    // every thread appends the FULL 4-entry granules (8 bytes) of four buckets' rows to the buckets' regions; the up
+    // to three sub-keys left over move to the front of the row and wait for the next tile, so nothing is padded
+    // until the CTA's last tile
+    const bool last_tile = tile + gridDim.x >= ntiles;
     uint32_t fn[BPT], fg[BPT];
 #pragma unroll
     for (int q = 0; q < BPT; ++q) {  // the reservations first: BPT independent atomics in flight
@@ -163,35 +170,36 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
       uint32_t n = s_cnt[b];
       if (n > (uint32_t)BK_CAP) n = BK_CAP;
       fn[q] = n;
-      fg[q] = n ? atomicAdd(&bk_cursor[b], (n + 3u) & ~3u) : 0u;
+      const uint32_t take = last_tile ? ((n + 3u) & ~3u) : (n & ~3u);
+      fg[q] = take ? atomicAdd(&bk_cursor[b], take) : 0u;
     }
 #pragma unroll
     for (int q = 0; q < BPT; ++q) {
       const uint32_t b = (uint32_t)tid + (uint32_t)BK_THREADS * q;
       const uint32_t n = fn[q], g = fg[q];
-      if (n == 0) continue;
-      const uint32_t n4 = (n + 3u) & ~3u;
-      const uint16_t *row = s_stage + b * BK_CAP;
-      uint2 *dst = reinterpret_cast<uint2 *>(bk_buf + (size_t)b * gcap + g);
-      const uint2 *src = reinterpret_cast<const uint2 *>(row);
-      if (g + n4 <= gcap) {
+      uint16_t *row = s_stage + b * BK_CAP;
+      if (last_tile)
+        for (uint32_t i = n; i < ((n + 3u) & ~3u); ++i) row[i] = (uint16_t)BK_PAD;
+      const uint32_t take = last_tile ? ((n + 3u) & ~3u) : (n & ~3u);
+      uint2 *rowv = reinterpret_cast<uint2 *>(row);
+      if (take) {
+        uint2 *dst = reinterpret_cast<uint2 *>(bk_buf + (size_t)b * gcap + g);
+        if (g + take <= gcap) {
 #pragma unroll
-        for (int i = 0; i < BK_CAP / 4; ++i) {
-          if ((uint32_t)(4 * i) < n) {
-            uint2 v = src[i];
-            const uint32_t left = n - 4u * i;  // valid sub-keys of this granule; the rest becomes filler
-            if (left == 1u) { v.x |= 0xffff0000u; v.y = 0xffffffffu; }
-            else if (left == 2u) v.y = 0xffffffffu;
-            else if (left == 3u) v.y |= 0xffff0000u;
-            dst[i] = v;
-          }
+          for (int i = 0; i < BK_CAP / 4; ++i)
+            if ((uint32_t)(4 * i) < take) dst[i] = rowv[i];
+        } else {
+          // the bucket's region is full (skewed spectrum): pad what is left of it, count these sub-keys directly
+          if (g < gcap)
+            for (uint32_t i = 0; i < (gcap - g) / 4; ++i) dst[i] = make_uint2(0xffffffffu, 0xffffffffu);
+          for (uint32_t i = 0; i < take; ++i)
+            if (row[i] != (uint16_t)BK_PAD) red_add_u32_keep(&counts[(b << sub_bits) | row[i]], 1u, keep);
         }
-      } else {
-        // the bucket's region is full (skewed spectrum): pad what is left of it, count this row directly
-        if (g < gcap)
-          for (uint32_t i = 0; i < (gcap - g) / 4; ++i) dst[i] = make_uint2(0xffffffffu, 0xffffffffu);
-        for (uint32_t i = 0; i < n; ++i) red_add_u32_keep(&counts[(b << sub_bits) | row[i]], 1u, keep);
       }
+      // leftover (n - take, only before the last tile) to the front of the row
+      const uint32_t left = n - (take < n ? take : n);
+      if (left && take) rowv[0] = rowv[take / 4];
+      s_cnt[b] = left;
     }
     __syncthreads();
   }

@@ -1407,6 +1407,19 @@ __global__ void __launch_bounds__(256) foc_hist_kernel(const uint32_t *__restric
   }
 }
 
+// non-empty bins of the dense histogram -> (count, multiplicity) pairs, appended unordered: the host reads a few
+// hundred pairs instead of 65 536 bins
+__global__ void __launch_bounds__(256) foc_compact_kernel(const uint32_t *__restrict__ hist, uint32_t dense,
+                                                          uint2 *__restrict__ pairs, uint32_t *npairs, uint32_t cap) {
+  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < dense; c += gridDim.x * blockDim.x) {
+    const uint32_t h = hist[c];
+    if (h) {
+      const uint32_t at = atomicAdd(npairs, 1u);
+      if (at < cap) pairs[at] = make_uint2(c, h);
+    }
+  }
+}
+
 // W[x] = f(counts[x])  (log2 / +-1 / any pure function of the count): dense table for small counts,
 // binary search over the sorted distinct counts above it
 __global__ void __launch_bounds__(256) lut_apply_kernel(const uint32_t *__restrict__ counts, size_t n,

@@ -94,18 +94,31 @@ class GpuStages:
         self._tables_k = k
         return self.counts
 
-    def reduce_counts(self, dist):
-        """sum of self.counts / self.nwords over all ranks, ordered on the ctx stream"""
+    def reduce_counts(self, dist, events=None):
+        """sum of self.counts / self.nwords over all ranks, ordered on the ctx stream.  events: optional list that
+        receives four CUDA events (before, after the first barrier, after the sum kernel, after the second barrier)"""
         t = self.torch
+
+        def mark():
+            if events is not None:
+                e = t.cuda.Event(enable_timing=True)
+                e.record(self.stream())
+                events.append(e)
         with t.cuda.stream(self.stream()):
+            mark()
             if self._peer is not None:
                 p = self._peer
                 p["hdl"].barrier(channel=0)   # every rank has finished counting
+                mark()
                 self.ctx.dev_xsum(p["ptrs"], p["rank"], p["mc"], p["n_u64"])
+                mark()
                 p["hdl"].barrier(channel=1)   # every slice has been written everywhere
             else:
+                mark()
                 dist.all_reduce(self.counts, op=dist.ReduceOp.SUM)
                 dist.all_reduce(self.nwords, op=dist.ReduceOp.SUM)
+                mark()
+            mark()
 
     def peer_sum_kind(self):
         if getattr(self, "_peer", None) is None:
