@@ -1495,10 +1495,21 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
         rc = rank_positions_setup(ctx, k, n, ng, gstart, seg_first, j0, x0, inc, rp);
         if (rc) return rc;
       }
-      rank_eval_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(
-          svals, n, ctx->sc_gstart.as<uint32_t>(), (uint32_t)ng, ctx->sc_segfirst.as<uint32_t>(),
-          ctx->sc_segj0.as<unsigned long long>(), ctx->sc_segx0.as<double>(), ctx->sc_seginc.as<double>(),
-          d_scores, want_pos ? ctx->rk_pos.as<uint32_t>() : nullptr);
+      if (want_pos) {
+        // positions first (the one random scatter, 4 bytes), then the rank table in index order: coalesced
+        rank_pos_scatter_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(svals, n, ctx->rk_pos.as<uint32_t>());
+        RankPieces R;
+        R.p0 = ctx->rk_p0.as<uint32_t>(); R.x0 = ctx->sc_segx0.as<double>(); R.inc = ctx->sc_seginc.as<double>();
+        R.npieces = ctx->rk_npieces; R.win_lo = ctx->rk_win_lo; R.win_len = ctx->rk_win_len; R.shift = ctx->rk_shift;
+        rank_from_pos_kernel<<<grid_for(n, 256, 148u * 8u), 256, 0, st>>>(ctx->rk_pos.as<uint32_t>(), n, ctx->rk_blob.p, R,
+                                                                         d_scores);
+        LAUNCHED(1);
+      } else {
+        rank_eval_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(
+            svals, n, ctx->sc_gstart.as<uint32_t>(), (uint32_t)ng, ctx->sc_segfirst.as<uint32_t>(),
+            ctx->sc_segj0.as<unsigned long long>(), ctx->sc_segx0.as<double>(), ctx->sc_seginc.as<double>(),
+            d_scores, nullptr);
+      }
       LAUNCHED(1);
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(st));  // host vectors above must outlive the copies

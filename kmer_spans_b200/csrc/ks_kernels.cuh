@@ -453,28 +453,67 @@ __device__ __forceinline__ int64_t rank_to_fx(double w, int qs) {
 }
 // exact fixed-point score of the k-mer at position p of the rank order: the double rank_eval_kernel writes into the
 // rank table, minus thr (the double the reference forms at :268), converted like every table entry
-__device__ __forceinline__ int64_t rank_value_global(const LevelArgs &A, uint32_t p, int qs) {
-  uint32_t a = 0, b = A.rk_npieces;
+struct RankPieces {  // the rank order as linear pieces, addressed by absolute position (ks_api.cu rank_positions_setup)
+  const uint32_t *p0;
+  const double *x0, *inc;
+  uint32_t npieces, win_lo, win_len;
+  int shift;
+};
+__device__ __forceinline__ double rank_double_global(const RankPieces &R, uint32_t p) {
+  uint32_t a = 0, b = R.npieces;
   while (b - a > 1) {
     const uint32_t mid = (a + b) >> 1;
-    if (__ldg(&A.rk_p0[mid]) <= p) a = mid; else b = mid;
+    if (__ldg(&R.p0[mid]) <= p) a = mid; else b = mid;
   }
-  const double r = fma((double)(p - __ldg(&A.rk_p0[a])), __ldg(&A.rk_inc[a]), __ldg(&A.rk_x0[a]));
-  return rank_to_fx(r - A.rk_thr, qs);
+  return fma((double)(p - __ldg(&R.p0[a])), __ldg(&R.inc[a]), __ldg(&R.x0[a]));
+}
+// p inside the window [win_lo, win_lo + win_len): pieces and bucket table from shared memory
+__device__ __forceinline__ double rank_double_window(const RankPieces &R, const RankSmem *sm, uint32_t p) {
+  const uint32_t bk = (p - R.win_lo) >> R.shift;
+  uint32_t a = sm->bucket[bk], b = sm->bucket[bk + 1] + 1;
+  while (b - a > 1) {
+    const uint32_t mid = (a + b) >> 1;
+    if (sm->p0[mid] <= p) a = mid; else b = mid;
+  }
+  return fma((double)(p - sm->p0[a]), sm->inc[a], sm->x0[a]);
+}
+__device__ __forceinline__ RankPieces rank_pieces_of(const LevelArgs &A) {
+  RankPieces R;
+  R.p0 = A.rk_p0; R.x0 = A.rk_x0; R.inc = A.rk_inc;
+  R.npieces = A.rk_npieces; R.win_lo = A.rk_win_lo; R.win_len = A.rk_win_len; R.shift = A.rk_shift;
+  return R;
+}
+__device__ __forceinline__ int64_t rank_value_global(const LevelArgs &A, uint32_t p, int qs) {
+  return rank_to_fx(rank_double_global(rank_pieces_of(A), p) - A.rk_thr, qs);
 }
 __device__ __forceinline__ int64_t rank_value(const LevelArgs &A, const RankSmem *sm, uint32_t p, int qs) {
   const uint32_t rel = p - A.rk_win_lo;
   if (rel >= A.rk_win_len)  // outside the window: finished score, one load
     return __ldg(&A.rk_tail[p < A.rk_win_lo ? p : p - A.rk_win_len]);
   if (!sm) return rank_value_global(A, p, qs);
-  const uint32_t bk = rel >> A.rk_shift;
-  uint32_t a = sm->bucket[bk], b = sm->bucket[bk + 1] + 1;
-  while (b - a > 1) {
-    const uint32_t mid = (a + b) >> 1;
-    if (sm->p0[mid] <= p) a = mid; else b = mid;
+  return rank_to_fx(rank_double_window(rank_pieces_of(A), sm, p) - A.rk_thr, qs);
+}
+// the rank table in INDEX order from the rank-order positions: coalesced reads and writes (the one random access of
+// the score stage is the 4-byte scatter of the positions, rank_pos_scatter_kernel)
+__global__ void __launch_bounds__(256) rank_pos_scatter_kernel(const uint32_t *__restrict__ vals, size_t n,
+                                                               uint32_t *__restrict__ rk_pos) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) rk_pos[vals[p]] = (uint32_t)p;
+}
+__global__ void __launch_bounds__(256) rank_from_pos_kernel(const uint32_t *__restrict__ rk_pos, size_t n,
+                                                            const void *__restrict__ blob, RankPieces R,
+                                                            double *__restrict__ ranks) {
+  __shared__ RankSmem sm;
+  for (int i = threadIdx.x; i < (int)(sizeof(RankSmem) / 16); i += blockDim.x)
+    cp_async16(reinterpret_cast<char *>(&sm) + 16 * i, reinterpret_cast<const char *>(blob) + 16 * i);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t p = __ldcs(&rk_pos[x]);
+    const double r = (p - R.win_lo < R.win_len) ? rank_double_window(R, &sm, p) : rank_double_global(R, p);
+    __stcs(&ranks[x], r);
   }
-  const double r = fma((double)(p - sm->p0[a]), sm->inc[a], sm->x0[a]);
-  return rank_to_fx(r - A.rk_thr, qs);
 }
 // finished scores of the rank-order positions outside the window (t counts them in order)
 __global__ void __launch_bounds__(256) rank_tail_kernel(const LevelArgs A, uint32_t ntail, int64_t *__restrict__ tail) {
