@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in self.REASONS.items():
                     if m & bit:
                         self.reasons.add(name)
-                time.sleep(0.005)
+                time.sleep(0.002)
         except Exception as e:  # NVML unavailable: report it instead of inventing numbers
             self.err = repr(e)
 
@@ -410,7 +410,11 @@ def main():
         n_spans = step()
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
-    time.sleep(0.1)
+    for _ in range(200):  # NVML initialisation can take a while on a fresh box: sample the timed region, not the setup
+        if sampler.ok or getattr(sampler, "err", None):
+            break
+        time.sleep(0.01)
+    sampler.samples.clear()
     ctx.set_profile(True)
     ctx.profile(reset=True)
     ctx.reset_launches()
