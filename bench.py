@@ -267,7 +267,7 @@ def config3_record(args, stages, rank, world, dist, torch, barrier):
     # ---- parity of this code path on the scaled set (k = 12 keeps the oracle's sort short) ----
     lens_p, data_p = build(0.01, want_all=(rank == 0))
     run = ksd.SplitRun(stages, d, api.SparseSeqs(lens_p, data_p))
-    got = run.step(12, 0, THR3, MIN_W, MIN_SCORE)
+    got = run.step(12, 0, THR3, MIN_W, MIN_SCORE, gather_scores=True)
     parts = [(got["pos"], got["score"])]
     if world > 1:
         parts = [None] * world

@@ -277,7 +277,9 @@ int ks_m_kmer_low_comp_regions(ks_mctx *m, const char *const *seqs, const int64_
                                int32_t *counts_out_or_null, double *ranks_out_or_null, ks_spans *out);
 /* resident shards: ks_m_load plans the cut and uploads every device's window; ks_m_pipeline runs count -> sum ->
  * scores(mode) -> sharded scan on them (count_only != 0: stop after the summed count table); ks_m_tables returns
- * the device pointers of the tables device i holds afterwards (identical on every device). */
+ * the device pointers of the tables device i holds afterwards: the count table is identical on every device; so is
+ * the score table, except after a weighted-rank pipeline on several devices, where device i holds slice i of the
+ * rank table (the scan gathers rank-order positions, not ranks; ks_m_kmer_* collect the slices when asked). */
 int ks_m_load(ks_mctx *m, const char *const *seqs, const int64_t *lens, int nseq);
 int ks_m_pipeline(ks_mctx *m, int k, int mode, double param, double thr, int min_width, double min_score,
                   double *n_words, ks_spans *out_or_null, uint64_t *n_spans, int count_only);

@@ -2972,6 +2972,7 @@ int ks_dev_window_dist(ks_ctx *ctx, const ks_seqset *s, int k, const uint32_t *c
   if (k < 1 || k > 15) return ctx->fail(KS_ERR_ARG, "kmer sizes larger than or equal to %d not currently supported", 16);
   if (kmer_n < 1) return ctx->fail(KS_ERR_ARG, "kmers_r should be a character vector with at least one element");
   if (window < 2 * k) return ctx->fail(KS_ERR_ARG, "The window size must be at least two times k");
+  if (s && s->window) return ctx->fail(KS_ERR_ARG, "ks_dev_window_dist: not for window sets");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   int rc = ensure_packed(ctx, s);

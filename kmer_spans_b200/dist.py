@@ -353,7 +353,9 @@ class SplitRun:
         flat = self._gathered.cpu().numpy().tobytes()
         return self.api.fold_carry(what, [flat[48 * i:48 * (i + 1)] for i in range(self.world)], self.rank)
 
-    def step(self, k, mode, thr, min_w, min_score, param=float("nan"), fetch=False):
+    def step(self, k, mode, thr, min_w, min_score, param=float("nan"), fetch=False, gather_scores=False):
+        """gather_scores: in rank mode with the sliced score stage every rank holds only its slice of the rank table
+        (an output, not an input of the scan); True all-gathers it so that every rank holds the whole table"""
         st, ctx = self.stages, self.ctx
         st.alloc_tables(k, self.dist)
         if getattr(st, "nwords", None) is None:
@@ -363,7 +365,7 @@ class SplitRun:
             st.reduce_counts(self.dist)
         n = 4 ** k
         if mode == 0 and self.dist and n % self.world == 0 and os.environ.get("KS_NO_SLICED_RANK") is None:
-            total = self._scores_rank_sliced(k)
+            total = self._scores_rank_sliced(k, gather_scores)
         else:
             total = st.scores_from_counts_dev(k, mode, param)
         if mode == 0:
@@ -375,7 +377,7 @@ class SplitRun:
         r["n"] = total
         return r
 
-    def _scores_rank_sliced(self, k):
+    def _scores_rank_sliced(self, k, gather_scores=False):
         """weighted-rank score stage with every rank sorting and ranking only its slice of the k-mer index space;
         the slices of the rank table and of the rank-order positions are all-gathered over NCCL on the ctx stream"""
         t, st, ctx, dist = self.torch, self.stages, self.ctx, self.dist
@@ -402,7 +404,8 @@ class SplitRun:
                 self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 2}
         pos = t.as_tensor(_Dev(ctx.rank_positions_ptr(), n), device=st.device)
         with t.cuda.stream(st.stream()):
-            dist.all_gather_into_tensor(st.scores, st.scores[lo:lo + per].clone())
+            if gather_scores:
+                dist.all_gather_into_tensor(st.scores, st.scores[lo:lo + per].clone())
             dist.all_gather_into_tensor(pos, pos[lo:lo + per].clone())
         return total
 

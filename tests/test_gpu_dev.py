@@ -338,3 +338,28 @@ def test_multi_device_context_matches_oracle(oracle, ndev):
     got = m.kmer_low_comp_regions(seqs, 6, 10, 3.0, 0.6)
     assert_spans(got, oracle.low_comp(seqs, 6, 10, 3.0, 0.6), False, "after error")
     m.close()
+
+
+def test_multi_device_edge_cases(oracle):
+    """more shards than chunks (empty shards take part in every exchange), k = 1 and 2 (table slices of the sliced
+    rank stage that are empty or one entry), nothing counted at all, sequences shorter than k"""
+    from kmer_spans_b200 import api
+    m = api.MultiContext([0] * 8)
+    rng = np.random.default_rng(7700)
+    cases = [([b"ACGTACGTAGAGAGAGAGAGAGAGAGCCCT"], 2, 0.5, 2, 0.5),
+             ([rand_seq(rng, 90)], 3, 0.5, 0, 0.0),
+             ([planted(rng, 5000), b"AC"], 1, 0.5, 3, 0.2),
+             ([planted(rng, 3000), planted(rng, 200)], 2, 0.6, 5, 0.5),
+             ([b"NNNNNNNNNNNN", b"AC"], 4, 0.75, 1, 0.1)]
+    for seqs, k, thr, mw, ms in cases:
+        want = oracle.low_comp(seqs, k, mw, ms, thr)
+        got = m.kmer_low_comp_regions(seqs, k, mw, ms, thr)
+        assert (got["counts"] == want["counts"]).all() and got["n"][0] == want["n"][0]
+        # the reference's 0/0 table (nothing counted) holds NaN: compare bit patterns, NaN payloads aside
+        assert np.array_equal(np.isnan(got["w_rank"]), np.isnan(want["ranks"]))
+        ok = ~np.isnan(want["ranks"])
+        assert got["w_rank"][ok].tobytes() == want["ranks"][ok].tobytes()
+        assert_spans(got, want, False, "edge k %d" % k)
+        c = m.kmer_counts(seqs, k, with_f=False)
+        assert (c["counts"] == want["counts"]).all()
+    m.close()
