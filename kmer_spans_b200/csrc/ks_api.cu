@@ -189,6 +189,7 @@ struct ks_ctx {
   uint64_t *lg_sorted = nullptr;   // sorted keys (one of lg_comp_a / lg_comp_b): composite, or codes in code order
   uint32_t *lg_idx = nullptr, *lg_cnt = nullptr;  // two-pass order: code-order index and count per position
   DBuf lg_cnt_a, lg_cnt_b, lg_idx_a, lg_idx_b;
+  DBuf bk_table_a;         // bucketed counting: counts of the a.c k-mers per bucket, folded into the table at the end
   DBuf bk_buf, bk_cursor;  // bucketed counting (ks_count.cuh): sub-keys per bucket, fill of every bucket
   bool smem_attr_set = false;
   DBuf win_match, win_cnt, win_pre, win_scratch, win_codes, win_fix, win_hist, win_pos;
@@ -383,7 +384,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->win_hist, &ctx->win_pos, &ctx->st_aux, &ctx->child_pk, &ctx->child_c, &ctx->child_count,
                  &ctx->tr_tables, &ctx->st_mn, &ctx->st_mx, &ctx->st_bm, &ctx->detail, &ctx->detail_count,
                  &ctx->cls, &ctx->cls_dense, &ctx->core, &ctx->rk_pos, &ctx->rk_p0, &ctx->rk_blob, &ctx->rk_tail,
-                 &ctx->bk_buf, &ctx->bk_cursor, &ctx->lg_slots, &ctx->lg_stats, &ctx->lg_comp_a, &ctx->lg_comp_b,
+                 &ctx->bk_buf, &ctx->bk_cursor, &ctx->bk_table_a, &ctx->lg_slots, &ctx->lg_stats, &ctx->lg_comp_a, &ctx->lg_comp_b,
                  &ctx->lg_slot_a, &ctx->lg_slot_b, &ctx->lg_ranks, &ctx->lg_cnt_a, &ctx->lg_cnt_b, &ctx->lg_idx_a,
                  &ctx->lg_idx_b};
   for (DBuf *b : all) b->release();
@@ -492,22 +493,22 @@ static int count_begin(ks_ctx *ctx, int k, int32_t *d_counts, int64_t est_chunks
   if (const char *e = getenv("KS_COUNT_PATH")) {
     if (!strcmp(e, "direct")) path = COUNT_DIRECT;
     else if (!strcmp(e, "smem") && k <= 7) path = COUNT_SMEM;
-    else if (!strcmp(e, "bucket") && k >= 5 && k <= 12) path = COUNT_BUCKET;
+    else if (!strcmp(e, "bucket") && k >= 6 && k <= 12) path = COUNT_BUCKET;
   }
   run->path = path;
   if (!ctx->smem_attr_set) {
     CK(cudaFuncSetAttribute(pack_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     CK(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SCATTER_SMEM));
-    CK(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    CK(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
     ctx->smem_attr_set = true;
   }
   CK(ctx->nwords.ensure(sizeof(unsigned long long)));
   CK(cudaMemsetAsync(d_counts, 0, n * sizeof(int32_t), st));
   CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
   if (path == COUNT_BUCKET) {
-    run->sub_bits = 2 * k - BK_LOG;
-    uint64_t per = (uint64_t)(est_chunks > 0 ? est_chunks : 1) * 16 / BK_BUCKETS;
-    uint64_t gcap = per + per / 2 + per / 8 + 8192;  // 12 % granule padding + spectrum skew; the rest overflows to direct
+    run->sub_bits = 2 * k - 8;  // one sub-key per pair of k-mers: rest of the core + a + b
+    uint64_t per = (uint64_t)(est_chunks > 0 ? est_chunks : 1) * 8 / BK_BUCKETS;  // pairs per bucket
+    uint64_t gcap = per + per / 2 + 8192;  // spectrum skew; what does not fit overflows to the direct reduction
     if (const char *e = getenv("KS_BUCKET_CAP")) gcap = (uint64_t)atoll(e);  // tests: force the overflow path
     gcap = (gcap + 7) & ~7ull;
     if (gcap < 8) gcap = 8;
@@ -515,6 +516,7 @@ static int count_begin(ks_ctx *ctx, int k, int32_t *d_counts, int64_t est_chunks
     run->gcap = (uint32_t)gcap;
     CK(ctx->bk_buf.ensure((size_t)gcap * BK_BUCKETS * 2));
     CK(ctx->bk_cursor.ensure(BK_BUCKETS * 4));
+    CK(ctx->bk_table_a.ensure(n * 4));
     CK(cudaMemsetAsync(ctx->bk_cursor.p, 0, BK_BUCKETS * 4, st));
   }
   return KS_OK;
@@ -536,7 +538,7 @@ static int count_chunks(ks_ctx *ctx, const ks_seqset *s, const CountRun &run, in
     const unsigned grid = (unsigned)std::min<int64_t>(148 * 4, ntiles);
     bucket_scatter_kernel<<<grid, BK_THREADS, BK_SCATTER_SMEM, st>>>(
         s->d_buf, first, nchunks, run.k, run.kmask, s->d_pk, s->d_brk, run.d_counts, nw,
-        ctx->bk_buf.as<uint16_t>(), ctx->bk_cursor.as<uint32_t>(), run.gcap, run.sub_bits);
+        ctx->bk_buf.as<uint16_t>(), ctx->bk_cursor.as<uint32_t>(), run.gcap);
   } else {
     pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
         s->d_buf, first, nchunks, run.k, run.kmask, s->d_pk, s->d_brk, run.d_counts, nw, run.part_shift, 0u);
@@ -551,9 +553,12 @@ static int count_chunks(ks_ctx *ctx, const ks_seqset *s, const CountRun &run, in
 static int count_end(ks_ctx *ctx, const ks_seqset *s, const CountRun &run, int64_t first, int64_t nchunks) {
   cudaStream_t st = ctx->stream;
   if (run.path == COUNT_BUCKET) {
-    bucket_count_kernel<<<BK_BUCKETS, BK_COUNT_THREADS, (size_t)4 << run.sub_bits, st>>>(
-        ctx->bk_buf.as<uint16_t>(), ctx->bk_cursor.as<uint32_t>(), run.gcap, run.sub_bits, run.d_counts);
-    LAUNCHED(1);
+    const size_t nk = (size_t)1 << (2 * run.k);
+    bucket_count_kernel<<<BK_BUCKETS, BK_COUNT_THREADS, 2 * (nk / BK_BUCKETS) * 4, st>>>(
+        ctx->bk_buf.as<uint16_t>(), ctx->bk_cursor.as<uint32_t>(), run.gcap, run.k, run.d_counts,
+        ctx->bk_table_a.as<uint32_t>());
+    bucket_fold_kernel<<<grid_for(nk, 256, 148u * 8u), 256, 0, st>>>(run.d_counts, ctx->bk_table_a.as<uint32_t>(), run.k);
+    LAUNCHED(2);
   } else if (run.path == COUNT_DIRECT && nchunks > 0) {
     for (int part = 1; part < run.nparts; ++part) {  // tables beyond L2: one pass over the sequence per slice
       pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(

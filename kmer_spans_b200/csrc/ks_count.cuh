@@ -6,15 +6,17 @@
 // 64 KiB table at 1 630 G/s.  So:
 //   k <= 7   pack_count_smem_kernel: the whole 4^k table lives in the shared memory of every CTA (<= 64 KiB),
 //            one shared-memory atomic per base, one flush of the non-zero counters per CTA at the end.
-//   8..12    two phases over 1024 buckets = the leading 10 bits of the 2k-bit code:
-//            bucket_scatter_kernel (fused with the 2-bit packing of K1) ranks every k-mer of a 12 288-position
-//            tile inside its bucket with one shared-memory atomic, stages the remaining 2k-10 bits (<= 14, a
-//            uint16) in shared memory and appends each bucket's segment to the bucket's region in HBM with
-//            8-byte stores (2 B written + 2 B read per base instead of a 32-byte-sector L2 atomic);
-//            bucket_count_kernel then counts one bucket per CTA in a shared-memory table of 4^k / 1024 entries
-//            and adds it to the bucket's slice of the count table with plain coalesced stores.
-//            A k-mer that does not fit its staging row (24 per bucket and tile: repeats, skewed spectra) or its
-//            bucket's region falls back to the direct global reduction, so every input stays exact.
+//   8..12    two phases over 1024 buckets, ONE SUB-KEY PER TWO K-MERS: the k-mers ending at positions 2i and 2i+1
+//            are a.c and c.b around the same (k-1)-mer c (the pairing the scan's core records use), so the pair is
+//            filed under the leading 10 bits of c and travels as one uint16 = (rest of c, a, b) = 2k - 8 bits.
+//            bucket_scatter_kernel (fused with the 2-bit packing of K1) ranks every pair of a 24 576-position tile
+//            inside its bucket with one shared-memory atomic, stages the sub-key in shared memory and appends each
+//            bucket's full 8-byte granules to the bucket's region in HBM (1 B written + 1 B read per base instead of
+//            a 32-byte-sector L2 atomic per base); bucket_count_kernel then counts one bucket per CTA in two
+//            shared-memory tables of 4^k / 1024 entries -- c.b lands in the bucket's own slice of the count table,
+//            a.c in a second table owned by the same CTA -- and bucket_fold_kernel adds the second table in.
+//            A pair that does not fit its staging row (repeats, skewed spectra) or its bucket's region, and a
+//            k-mer without a partner (run boundaries), falls back to the direct global reduction: every input stays exact.
 //   >= 13    the direct kernel of ks_kernels.cuh in slices of the table (the table exceeds L2).
 #pragma once
 #include "ks_kernels.cuh"
@@ -24,10 +26,12 @@ namespace ks {
 constexpr int BK_LOG = 10;
 constexpr int BK_BUCKETS = 1 << BK_LOG;
 constexpr int BK_CAP = 24;      // staged sub-keys per bucket and tile; rows of 48 bytes (8-byte aligned)
-constexpr int BK_ROUNDS = 3;    // chunks per thread and tile
+constexpr int BK_ROUNDS = 6;    // chunks per thread and tile, loaded in two batches of three
+constexpr int BK_BATCH = 3;
 constexpr int BK_THREADS = 256;
-constexpr int BK_TILE_CHUNKS = BK_THREADS * BK_ROUNDS;  // 768 chunks = 12 288 positions, 12 per bucket on average
-constexpr uint32_t BK_PAD = 0xffffu;                    // filler of the 4-entry granules (a sub-key has <= 14 bits)
+constexpr int BK_TILE_CHUNKS = BK_THREADS * BK_ROUNDS;  // 1536 chunks = 24 576 positions = 12 288 pairs, 12 per bucket
+constexpr uint32_t BK_PAD = 0xffffu;  // filler of the last granule of a row; never a sub-key: an all-ones sub-key would
+                                      // need k = 12 with rest, a, b all ones, which is filed as two direct reductions
 constexpr size_t BK_SCATTER_SMEM = BK_BUCKETS * 4 + (size_t)BK_BUCKETS * BK_CAP * 2;  // counters + rows
 
 __device__ __forceinline__ unsigned long long block_sum_to(unsigned long long local, unsigned long long *dst) {
@@ -108,7 +112,13 @@ __global__ void __launch_bounds__(256) pack_count_smem_kernel(const uint8_t *__r
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// 8 <= k <= 12, phase 1: pack + scatter the sub-keys into their buckets
+// 8 <= k <= 12, phase 1: pack + scatter one sub-key per pair of consecutive k-mers into the buckets
+struct PairGeom {   // geometry of a sub-key for this k
+  int k;
+  int core_bits;    // 2k - 2
+  int rest_bits;    // core_bits - BK_LOG
+  __host__ __device__ explicit PairGeom(int k_) : k(k_), core_bits(2 * k_ - 2), rest_bits(2 * k_ - 2 - BK_LOG) {}
+};
 __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uint8_t *__restrict__ buf, int64_t first,
                                                                       int64_t nchunks, int k, uint32_t kmask,
                                                                       uint32_t *__restrict__ pk_out,
@@ -116,13 +126,14 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
                                                                       int32_t *__restrict__ counts,
                                                                       unsigned long long *__restrict__ nwords,
                                                                       uint16_t *__restrict__ bk_buf,
-                                                                      uint32_t *__restrict__ bk_cursor, uint32_t gcap,
-                                                                      int sub_bits) {
+                                                                      uint32_t *__restrict__ bk_cursor, uint32_t gcap) {
   extern __shared__ __align__(16) unsigned char ks_dyn_smem[];
   uint32_t *s_cnt = reinterpret_cast<uint32_t *>(ks_dyn_smem);
   uint16_t *s_stage = reinterpret_cast<uint16_t *>(ks_dyn_smem + BK_BUCKETS * 4);
   const int tid = threadIdx.x;
-  const uint32_t submask = (1u << sub_bits) - 1u;
+  const PairGeom G(k);
+  const uint32_t cmask = kmask >> 2;                        // (k-1)-mer
+  const uint32_t restmask = (1u << G.rest_bits) - 1u;
   const uint64_t keep = l2_policy_evict_last();
   unsigned long long local = 0;
   const int64_t ntiles = (nchunks + BK_TILE_CHUNKS - 1) / BK_TILE_CHUNKS;
@@ -130,29 +141,45 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
   for (int i = tid; i < BK_BUCKETS; i += BK_THREADS) s_cnt[i] = 0;
   __syncthreads();
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    RawChunk raw[BK_ROUNDS];  // all loads of the tile in flight before the first one is used
+#pragma unroll 1
+    for (int batch = 0; batch < BK_ROUNDS / BK_BATCH; ++batch) {
+      RawChunk raw[BK_BATCH];  // all loads of the batch in flight before the first one is used
 #pragma unroll
-    for (int r = 0; r < BK_ROUNDS; ++r) {
-      const int64_t ci = first + tile * BK_TILE_CHUNKS + r * BK_THREADS + tid;
-      if (ci < first + nchunks) raw[r] = load_chunk_raw(buf, ci);
-    }
+      for (int r = 0; r < BK_BATCH; ++r) {
+        const int64_t ci = first + tile * BK_TILE_CHUNKS + (batch * BK_BATCH + r) * BK_THREADS + tid;
+        if (ci < first + nchunks) raw[r] = load_chunk_raw(buf, ci);
+      }
 #pragma unroll
-    for (int r = 0; r < BK_ROUNDS; ++r) {
-      const int64_t ci = first + tile * BK_TILE_CHUNKS + r * BK_THREADS + tid;
-      if (ci < first + nchunks) {
+      for (int r = 0; r < BK_BATCH; ++r) {
+        const int64_t ci = first + tile * BK_TILE_CHUNKS + (batch * BK_BATCH + r) * BK_THREADS + tid;
+        if (ci >= first + nchunks) continue;
         uint32_t code[CHUNK], counted;
         pack_decode_raw(raw[r], ci, first, k, kmask, pk_out, brk_out, code, counted);
-        // the 16 rank requests first, the 16 stores after: the latency of a shared-memory atomic with a result is
-        // paid once per chunk, not once per position
-        uint32_t slot[CHUNK];
+        // pairs (2i, 2i+1): code[2i] = a.c, code[2i+1] = c.b.  The 8 rank requests first, the 8 stores after: the
+        // latency of a shared-memory atomic with a result is paid once per chunk, not once per pair
+        uint32_t slot[CHUNK / 2];
 #pragma unroll
-        for (int j = 0; j < CHUNK; ++j)
-          slot[j] = (counted & (1u << j)) ? atomicAdd(&s_cnt[code[j] >> sub_bits], 1u) : 0u;
+        for (int i = 0; i < CHUNK / 2; ++i) {
+          const bool both = ((counted >> (2 * i)) & 3u) == 3u;
+          slot[i] = both ? atomicAdd(&s_cnt[(code[2 * i] & cmask) >> G.rest_bits], 1u) : 0u;
+        }
 #pragma unroll
-        for (int j = 0; j < CHUNK; ++j) {
-          if (counted & (1u << j)) {
-            if (slot[j] < (uint32_t)BK_CAP) s_stage[(code[j] >> sub_bits) * BK_CAP + slot[j]] = (uint16_t)(code[j] & submask);
-            else red_add_u32_keep(&counts[code[j]], 1u, keep);  // the row is full: direct reduction
+        for (int i = 0; i < CHUNK / 2; ++i) {
+          const uint32_t m2 = (counted >> (2 * i)) & 3u;
+          if (m2 == 3u) {
+            const uint32_t c = code[2 * i] & cmask;
+            const uint32_t sub = ((c & restmask) << 4) | ((code[2 * i] >> G.core_bits) << 2) | (code[2 * i + 1] & 3u);
+            if (slot[i] < (uint32_t)BK_CAP && sub != BK_PAD) {
+              s_stage[(c >> G.rest_bits) * BK_CAP + slot[i]] = (uint16_t)sub;
+            } else {  // the row is full (or the one sub-key that looks like filler): two direct reductions.  A slot
+                      // taken for the filler look-alike stays unwritten only if sub == BK_PAD: write filler there
+              if (slot[i] < (uint32_t)BK_CAP) s_stage[(c >> G.rest_bits) * BK_CAP + slot[i]] = (uint16_t)BK_PAD;
+              red_add_u32_keep(&counts[code[2 * i]], 1u, keep);
+              red_add_u32_keep(&counts[code[2 * i + 1]], 1u, keep);
+            }
+          } else {  // a k-mer without its partner (run boundary): direct
+            if (m2 & 1u) red_add_u32_keep(&counts[code[2 * i]], 1u, keep);
+            if (m2 & 2u) red_add_u32_keep(&counts[code[2 * i + 1]], 1u, keep);
           }
         }
         local += __popc(counted);
@@ -189,11 +216,16 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
           for (int i = 0; i < BK_CAP / 4; ++i)
             if ((uint32_t)(4 * i) < take) dst[i] = rowv[i];
         } else {
-          // the bucket's region is full (skewed spectrum): pad what is left of it, count these sub-keys directly
+          // the bucket's region is full (skewed spectrum): pad what is left of it, count these pairs directly
           if (g < gcap)
             for (uint32_t i = 0; i < (gcap - g) / 4; ++i) dst[i] = make_uint2(0xffffffffu, 0xffffffffu);
-          for (uint32_t i = 0; i < take; ++i)
-            if (row[i] != (uint16_t)BK_PAD) red_add_u32_keep(&counts[(b << sub_bits) | row[i]], 1u, keep);
+          for (uint32_t i = 0; i < take; ++i) {
+            const uint32_t sub = row[i];
+            if (sub == BK_PAD) continue;
+            const uint32_t c = (b << G.rest_bits) | (sub >> 4);
+            red_add_u32_keep(&counts[(((sub >> 2) & 3u) << G.core_bits) | c], 1u, keep);  // a.c
+            red_add_u32_keep(&counts[(c << 2) | (sub & 3u)], 1u, keep);                    // c.b
+          }
         }
       }
       // leftover (n - take, only before the last tile) to the front of the row
@@ -206,38 +238,46 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
   block_sum_to(local, nwords);
 }
 
-// phase 2: one bucket per CTA, counted in shared memory (dynamic, 4 << sub_bits bytes), added to the table slice
-constexpr int BK_COUNT_THREADS = 512;
-__global__ void __launch_bounds__(BK_COUNT_THREADS, 3) bucket_count_kernel(const uint16_t *__restrict__ bk_buf,
+// phase 2: one bucket per CTA.  Two shared-memory tables of 2^(rest_bits + 2) entries: tabB[(rest, b)] counts the
+// k-mers c.b -- the bucket's own contiguous slice of the count table -- and tabA[(a, rest)] the k-mers a.c, which
+// belong to four other slices: they go, plainly stored, to the CTA's part of a second table that bucket_fold_kernel
+// adds in afterwards (an entry of the count table would otherwise have two writers).
+constexpr int BK_COUNT_THREADS = 1024;
+__global__ void __launch_bounds__(BK_COUNT_THREADS, 1) bucket_count_kernel(const uint16_t *__restrict__ bk_buf,
                                                                         const uint32_t *__restrict__ bk_cursor,
-                                                                        uint32_t gcap, int sub_bits,
-                                                                        int32_t *__restrict__ counts) {
+                                                                        uint32_t gcap, int k,
+                                                                        int32_t *__restrict__ counts,
+                                                                        uint32_t *__restrict__ table_a) {
   extern __shared__ __align__(16) unsigned char ks_dyn_smem[];
-  uint32_t *s_tab = reinterpret_cast<uint32_t *>(ks_dyn_smem);
+  const PairGeom G(k);
+  const uint32_t entries = 1u << (G.rest_bits + 2);
+  uint32_t *tabB = reinterpret_cast<uint32_t *>(ks_dyn_smem);
+  uint32_t *tabA = tabB + entries;
   const uint32_t b = blockIdx.x;
-  const uint32_t entries = 1u << sub_bits;
   uint32_t n = bk_cursor[b];
   if (n > gcap) n = gcap;
-  if (n == 0) return;
   const uint16_t *base = bk_buf + (size_t)b * gcap;  // gcap is a multiple of 8: 16-byte aligned
   const uint4 *src = reinterpret_cast<const uint4 *>(base);
   const uint32_t nv = n / 8;
   const uint4 filler = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-  constexpr int UNR = 4;
+  constexpr int UNR = 2;
   uint4 v[UNR];
   uint32_t i0 = threadIdx.x;
 #pragma unroll
   for (int u = 0; u < UNR; ++u) v[u] = (i0 + u * BK_COUNT_THREADS < nv) ? __ldcs(src + i0 + u * BK_COUNT_THREADS) : filler;
-  for (uint32_t i = threadIdx.x; i < entries; i += blockDim.x) s_tab[i] = 0;
+  for (uint32_t i = threadIdx.x; i < 2 * entries; i += blockDim.x) tabB[i] = 0;
   __syncthreads();
+  const uint32_t restmask = (1u << G.rest_bits) - 1u;
+  auto add1 = [&](uint32_t sub) {
+    if (sub == BK_PAD) return;
+    const uint32_t rest = (sub >> 4) & restmask;
+    atomicAdd(&tabB[(rest << 2) | (sub & 3u)], 1u);
+    atomicAdd(&tabA[(((sub >> 2) & 3u) << G.rest_bits) | rest], 1u);
+  };
   auto add8 = [&](const uint4 &x) {
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const uint32_t lo = w[h] & 0xffffu, hi = w[h] >> 16;
-      if (lo != BK_PAD) atomicAdd(&s_tab[lo], 1u);
-      if (hi != BK_PAD) atomicAdd(&s_tab[hi], 1u);
-    }
+    for (int h = 0; h < 4; ++h) { add1(w[h] & 0xffffu); add1(w[h] >> 16); }
   };
   for (; i0 < nv; i0 += UNR * BK_COUNT_THREADS) {
     uint4 nx[UNR];
@@ -251,15 +291,27 @@ __global__ void __launch_bounds__(BK_COUNT_THREADS, 3) bucket_count_kernel(const
 #pragma unroll
     for (int u = 0; u < UNR; ++u) v[u] = nx[u];
   }
-  if ((n & 4u) && threadIdx.x < 4) {  // n is a multiple of 4: one trailing granule
-    const uint32_t s = base[nv * 8 + threadIdx.x];
-    if (s != BK_PAD) atomicAdd(&s_tab[s], 1u);
-  }
+  if ((n & 4u) && threadIdx.x < 4) add1(base[nv * 8 + threadIdx.x]);  // n is a multiple of 4: one trailing granule
   __syncthreads();
-  uint32_t *slice = reinterpret_cast<uint32_t *>(counts) + ((size_t)b << sub_bits);
+  uint32_t *slice = reinterpret_cast<uint32_t *>(counts) + ((size_t)b << (G.rest_bits + 2));
+  uint32_t *mineA = table_a + ((size_t)b << (G.rest_bits + 2));
   for (uint32_t i = threadIdx.x; i < entries; i += blockDim.x) {
-    const uint32_t c = s_tab[i];
-    if (c) slice[i] += c;  // the slice belongs to this CTA; direct reductions of phase 1 are already in it
+    const uint32_t c = tabB[i];
+    if (c) slice[i] += c;   // the slice belongs to this CTA; direct reductions of phase 1 are already in it
+    mineA[i] = tabA[i];     // [a][rest] of this bucket
+  }
+}
+
+// counts[a.c] += tableA[bucket(c)][a][rest(c)]
+__global__ void __launch_bounds__(256) bucket_fold_kernel(int32_t *__restrict__ counts, const uint32_t *__restrict__ table_a,
+                                                          int k) {
+  const PairGeom G(k);
+  const size_t n = (size_t)1 << (2 * k);
+  const uint32_t cmask = (uint32_t)(n >> 2) - 1u, restmask = (1u << G.rest_bits) - 1u;
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t a = (uint32_t)(x >> G.core_bits), c = (uint32_t)x & cmask;
+    const uint32_t add = __ldcs(&table_a[((size_t)(c >> G.rest_bits) << (G.rest_bits + 2)) | ((size_t)a << G.rest_bits) | (c & restmask)]);
+    if (add) counts[x] += (int32_t)add;
   }
 }
 
