@@ -479,6 +479,33 @@ struct CountRun {
 };
 }  // namespace
 
+// the bucket kernels are compiled per k (shift counts and masks as immediates)
+#define KS_BUCKET_K(k, stmt)                    \
+  switch (k) {                                  \
+    case 8: { constexpr int KK = 8; stmt; } break;   \
+    case 9: { constexpr int KK = 9; stmt; } break;   \
+    case 10: { constexpr int KK = 10; stmt; } break; \
+    case 11: { constexpr int KK = 11; stmt; } break; \
+    default: { constexpr int KK = 12; stmt; } break; \
+  }
+extern "C++" {
+template <int K>
+static cudaError_t bucket_smem_attrs_k() {
+  cudaError_t e = cudaFuncSetAttribute(bucket_scatter_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)BK_SCATTER_SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(bucket_count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
+}
+}  // extern "C++"
+static cudaError_t bucket_smem_attrs() {
+  cudaError_t e;
+  if ((e = bucket_smem_attrs_k<8>()) != cudaSuccess) return e;
+  if ((e = bucket_smem_attrs_k<9>()) != cudaSuccess) return e;
+  if ((e = bucket_smem_attrs_k<10>()) != cudaSuccess) return e;
+  if ((e = bucket_smem_attrs_k<11>()) != cudaSuccess) return e;
+  return bucket_smem_attrs_k<12>();
+}
+
 // zeroes the table, the word count and (bucket path) the bucket fills; est_chunks sizes the bucket regions
 static int count_begin(ks_ctx *ctx, int k, int32_t *d_counts, int64_t est_chunks, CountRun *run) {
   cudaStream_t st = ctx->stream;
@@ -493,13 +520,12 @@ static int count_begin(ks_ctx *ctx, int k, int32_t *d_counts, int64_t est_chunks
   if (const char *e = getenv("KS_COUNT_PATH")) {
     if (!strcmp(e, "direct")) path = COUNT_DIRECT;
     else if (!strcmp(e, "smem") && k <= 7) path = COUNT_SMEM;
-    else if (!strcmp(e, "bucket") && k >= 6 && k <= 12) path = COUNT_BUCKET;
+    else if (!strcmp(e, "bucket") && k >= 8 && k <= 12) path = COUNT_BUCKET;
   }
   run->path = path;
   if (!ctx->smem_attr_set) {
     CK(cudaFuncSetAttribute(pack_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    CK(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SCATTER_SMEM));
-    CK(cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+    CK(bucket_smem_attrs());
     ctx->smem_attr_set = true;
   }
   CK(ctx->nwords.ensure(sizeof(unsigned long long)));
@@ -536,9 +562,9 @@ static int count_chunks(ks_ctx *ctx, const ks_seqset *s, const CountRun &run, in
   } else if (run.path == COUNT_BUCKET) {
     const int64_t ntiles = (nchunks + BK_TILE_CHUNKS - 1) / BK_TILE_CHUNKS;
     const unsigned grid = (unsigned)std::min<int64_t>(148 * 4, ntiles);
-    bucket_scatter_kernel<<<grid, BK_THREADS, BK_SCATTER_SMEM, st>>>(
-        s->d_buf, first, nchunks, run.k, run.kmask, s->d_pk, s->d_brk, run.d_counts, nw,
-        ctx->bk_buf.as<uint16_t>(), ctx->bk_cursor.as<uint32_t>(), run.gcap);
+    KS_BUCKET_K(run.k, (bucket_scatter_kernel<KK><<<grid, BK_THREADS, BK_SCATTER_SMEM, st>>>(
+        s->d_buf, first, nchunks, s->d_pk, s->d_brk, run.d_counts, nw, ctx->bk_buf.as<uint16_t>(),
+        ctx->bk_cursor.as<uint32_t>(), run.gcap)));
   } else {
     pack_count_kernel<true><<<grid_for((size_t)nchunks, 256, 148u * 8u), 256, 0, st>>>(
         s->d_buf, first, nchunks, run.k, run.kmask, s->d_pk, s->d_brk, run.d_counts, nw, run.part_shift, 0u);
@@ -554,10 +580,11 @@ static int count_end(ks_ctx *ctx, const ks_seqset *s, const CountRun &run, int64
   cudaStream_t st = ctx->stream;
   if (run.path == COUNT_BUCKET) {
     const size_t nk = (size_t)1 << (2 * run.k);
-    bucket_count_kernel<<<BK_BUCKETS, BK_COUNT_THREADS, 2 * (nk / BK_BUCKETS) * 4, st>>>(
-        ctx->bk_buf.as<uint16_t>(), ctx->bk_cursor.as<uint32_t>(), run.gcap, run.k, run.d_counts,
-        ctx->bk_table_a.as<uint32_t>());
-    bucket_fold_kernel<<<grid_for(nk, 256, 148u * 8u), 256, 0, st>>>(run.d_counts, ctx->bk_table_a.as<uint32_t>(), run.k);
+    KS_BUCKET_K(run.k, (bucket_count_kernel<KK><<<BK_BUCKETS, BK_COUNT_THREADS, 2 * (nk / BK_BUCKETS) * 4, st>>>(
+        ctx->bk_buf.as<uint16_t>(), ctx->bk_cursor.as<uint32_t>(), run.gcap, run.d_counts,
+        ctx->bk_table_a.as<uint32_t>())));
+    KS_BUCKET_K(run.k, (bucket_fold_kernel<KK><<<grid_for(nk / 4, 256, 148u * 8u), 256, 0, st>>>(
+        run.d_counts, ctx->bk_table_a.as<uint32_t>())));
     LAUNCHED(2);
   } else if (run.path == COUNT_DIRECT && nchunks > 0) {
     for (int part = 1; part < run.nparts; ++part) {  // tables beyond L2: one pass over the sequence per slice

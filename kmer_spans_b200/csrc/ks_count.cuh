@@ -112,77 +112,150 @@ __global__ void __launch_bounds__(256) pack_count_smem_kernel(const uint8_t *__r
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// 8 <= k <= 12, phase 1: pack + scatter one sub-key per pair of consecutive k-mers into the buckets
-struct PairGeom {   // geometry of a sub-key for this k
-  int k;
-  int core_bits;    // 2k - 2
-  int rest_bits;    // core_bits - BK_LOG
-  __host__ __device__ explicit PairGeom(int k_) : k(k_), core_bits(2 * k_ - 2), rest_bits(2 * k_ - 2 - BK_LOG) {}
+// 8 <= k <= 12, phase 1: pack + scatter one sub-key per pair of consecutive k-mers into the buckets.
+//
+// The three bases around a pair, read straight from the packed window: Y = a.c.b (2k + 2 bits), c the shared (k-1)-mer.
+//   bucket  = leading 10 bits of c            = (Y >> (REST + 2)) & 1023,  REST = 2k - 12 bits of c remain
+//   sub-key = a | rest of c | b  (2k - 8 bits) = (Y & LOW) | ((Y >> 10) & (3 << (REST + 2))),  LOW = REST + 2 ones
+// so that phase 2 indexes its c.b table with sub & LOW and its a.c table with sub >> 2.
+template <int K>
+struct PairGeom {
+  static constexpr int REST = 2 * K - 12;
+  static constexpr uint32_t LOW = (1u << (REST + 2)) - 1u;
+  static constexpr uint32_t KMASK = (uint32_t)(((uint64_t)1 << (2 * K)) - 1u);
+  static constexpr uint32_t ENTRIES = 1u << (REST + 2);  // per bucket and table = 4^K / 1024
+  __device__ static __forceinline__ uint32_t bucket4(uint32_t y) { return (y >> REST) & (1023u << 2); }  // bucket * 4
+  __device__ static __forceinline__ uint32_t sub(uint32_t y) { return (y & LOW) | ((y >> 10) & (3u << (REST + 2))); }
+  __device__ static __forceinline__ uint32_t code_ac(uint32_t bucket, uint32_t sub) {
+    return ((sub >> (REST + 2)) << (2 * K - 2)) | (bucket << REST) | ((sub >> 2) & ((1u << REST) - 1u));
+  }
+  __device__ static __forceinline__ uint32_t code_cb(uint32_t bucket, uint32_t sub) {
+    return (bucket << (REST + 2)) | (sub & LOW);
+  }
 };
+
+// "does any of the 16 bytes break a run" (N, n, terminator): exact as a yes / no, a third of the work of the flags
+__device__ __forceinline__ uint32_t any_break16(const uint32_t w[4]) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t v = w[i], x = (v | 0x20202020u) ^ 0x6e6e6e6eu;
+    acc |= ((v - 0x01010101u) & ~v) | ((x - 0x01010101u) & ~x);
+  }
+  return acc & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t pack16_codes(const uint32_t w[4]) {
+  uint32_t pk = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pk |= ((((w[i] >> 1) & 0x03030303u) * 0x40100401u) >> 24) << (24 - 8 * i);
+  return pk;
+}
+// packed codes + (brk | nul << 16) of 16 bytes; the flags only where any_break16 saw one
+__device__ __forceinline__ void pack16_lazy(const uint4 &raw, uint32_t &pk, uint32_t &flags) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  pk = pack16_codes(w);
+  flags = 0;
+  if (any_break16(w)) {
+    uint32_t pk2, brk, nul;
+    pack16(w, pk2, brk, nul);
+    flags = brk | (nul << 16);
+  }
+}
+
+template <int K>
 __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uint8_t *__restrict__ buf, int64_t first,
-                                                                      int64_t nchunks, int k, uint32_t kmask,
-                                                                      uint32_t *__restrict__ pk_out,
+                                                                      int64_t nchunks, uint32_t *__restrict__ pk_out,
                                                                       uint16_t *__restrict__ brk_out,
                                                                       int32_t *__restrict__ counts,
                                                                       unsigned long long *__restrict__ nwords,
                                                                       uint16_t *__restrict__ bk_buf,
                                                                       uint32_t *__restrict__ bk_cursor, uint32_t gcap) {
+  typedef PairGeom<K> G;
   extern __shared__ __align__(16) unsigned char ks_dyn_smem[];
   uint32_t *s_cnt = reinterpret_cast<uint32_t *>(ks_dyn_smem);
+  unsigned char *s_cnt_b = ks_dyn_smem;
   uint16_t *s_stage = reinterpret_cast<uint16_t *>(ks_dyn_smem + BK_BUCKETS * 4);
-  const int tid = threadIdx.x;
-  const PairGeom G(k);
-  const uint32_t cmask = kmask >> 2;                        // (k-1)-mer
-  const uint32_t restmask = (1u << G.rest_bits) - 1u;
+  unsigned char *s_stage_b = ks_dyn_smem + BK_BUCKETS * 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t keep = l2_policy_evict_last();
+  const int64_t end = first + nchunks;
   unsigned long long local = 0;
   const int64_t ntiles = (nchunks + BK_TILE_CHUNKS - 1) / BK_TILE_CHUNKS;
   constexpr int BPT = BK_BUCKETS / BK_THREADS;  // buckets per thread (flush)
   for (int i = tid; i < BK_BUCKETS; i += BK_THREADS) s_cnt[i] = 0;
   __syncthreads();
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // a warp owns 32 * BK_ROUNDS consecutive chunks of the tile, 32 per round: the 16 positions before a chunk are
+    // the neighbouring lane's chunk (one shuffle), those before lane 0 the last lane's of the round before, and only
+    // the very first of the warp is packed a second time
+    const int64_t wbase = first + tile * BK_TILE_CHUNKS + (int64_t)warp * (32 * BK_ROUNDS);
+    uint32_t carry_pk = 0, carry_fl = 0;
+    if (wbase < end) pack16_lazy(ld_stream_u4(reinterpret_cast<const uint4 *>(buf + 16 * wbase)), carry_pk, carry_fl);
 #pragma unroll 1
     for (int batch = 0; batch < BK_ROUNDS / BK_BATCH; ++batch) {
-      RawChunk raw[BK_BATCH];  // all loads of the batch in flight before the first one is used
+      uint4 raw[BK_BATCH];  // all loads of the batch in flight before the first one is used
 #pragma unroll
       for (int r = 0; r < BK_BATCH; ++r) {
-        const int64_t ci = first + tile * BK_TILE_CHUNKS + (batch * BK_BATCH + r) * BK_THREADS + tid;
-        if (ci < first + nchunks) raw[r] = load_chunk_raw(buf, ci);
+        const int64_t ci = wbase + (batch * BK_BATCH + r) * 32 + lane;
+        raw[r] = ci < end ? ld_stream_u4(reinterpret_cast<const uint4 *>(buf + 16 * (ci + 1))) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int r = 0; r < BK_BATCH; ++r) {
-        const int64_t ci = first + tile * BK_TILE_CHUNKS + (batch * BK_BATCH + r) * BK_THREADS + tid;
-        if (ci >= first + nchunks) continue;
-        uint32_t code[CHUNK], counted;
-        pack_decode_raw(raw[r], ci, first, k, kmask, pk_out, brk_out, code, counted);
-        // pairs (2i, 2i+1): code[2i] = a.c, code[2i+1] = c.b.  The 8 rank requests first, the 8 stores after: the
-        // latency of a shared-memory atomic with a result is paid once per chunk, not once per pair
-        uint32_t slot[CHUNK / 2];
-#pragma unroll
-        for (int i = 0; i < CHUNK / 2; ++i) {
-          const bool both = ((counted >> (2 * i)) & 3u) == 3u;
-          slot[i] = both ? atomicAdd(&s_cnt[(code[2 * i] & cmask) >> G.rest_bits], 1u) : 0u;
-        }
-#pragma unroll
-        for (int i = 0; i < CHUNK / 2; ++i) {
-          const uint32_t m2 = (counted >> (2 * i)) & 3u;
-          if (m2 == 3u) {
-            const uint32_t c = code[2 * i] & cmask;
-            const uint32_t sub = ((c & restmask) << 4) | ((code[2 * i] >> G.core_bits) << 2) | (code[2 * i + 1] & 3u);
-            if (slot[i] < (uint32_t)BK_CAP && sub != BK_PAD) {
-              s_stage[(c >> G.rest_bits) * BK_CAP + slot[i]] = (uint16_t)sub;
-            } else {  // the row is full (or the one sub-key that looks like filler): two direct reductions.  A slot
-                      // taken for the filler look-alike stays unwritten only if sub == BK_PAD: write filler there
-              if (slot[i] < (uint32_t)BK_CAP) s_stage[(c >> G.rest_bits) * BK_CAP + slot[i]] = (uint16_t)BK_PAD;
-              red_add_u32_keep(&counts[code[2 * i]], 1u, keep);
-              red_add_u32_keep(&counts[code[2 * i + 1]], 1u, keep);
-            }
-          } else {  // a k-mer without its partner (run boundary): direct
-            if (m2 & 1u) red_add_u32_keep(&counts[code[2 * i]], 1u, keep);
-            if (m2 & 2u) red_add_u32_keep(&counts[code[2 * i + 1]], 1u, keep);
-          }
+        const int64_t ci = wbase + (batch * BK_BATCH + r) * 32 + lane;
+        const bool live = ci < end;
+        uint32_t pkc, flc;
+        pack16_lazy(raw[r], pkc, flc);
+        uint32_t pkp = __shfl_up_sync(0xffffffffu, pkc, 1), flp = __shfl_up_sync(0xffffffffu, flc, 1);
+        if (lane == 0) { pkp = carry_pk; flp = carry_fl; }
+        carry_pk = __shfl_sync(0xffffffffu, pkc, 31);
+        carry_fl = __shfl_sync(0xffffffffu, flc, 31);
+        if (!live) continue;  // the lanes behind the end of the set: shuffled with, nothing else
+        pk_out[ci + 1] = pkc;
+        brk_out[ci + 1] = (uint16_t)flc;
+        if (ci == first) { pk_out[ci] = pkp; brk_out[ci] = (uint16_t)flp; }  // no thread of its own (ks_kernels.cuh)
+        uint32_t counted = 0xffffu;
+        if (flp | flc) {  // a break in sight: the full rule of sequence_kmer_count (decode_count)
+          const uint32_t brk32 = (flp & 0xffffu) | (flc << 16), nul32 = (flp >> 16) | (flc & 0xffff0000u);
+          const uint32_t runk = run_ending(~brk32, K);
+          const uint32_t head = runk & (brk32 << K);
+          const uint32_t nulnext = (nul32 >> 1) | (__ldg(buf + 16 * ci + 32) == 0u ? 0x80000000u : 0u);
+          counted = (runk & ~(head & nulnext)) >> 16;
         }
         local += __popc(counted);
+        // pair i = the k-mers ending at positions 2i and 2i + 1 of the chunk = a.c and c.b inside Y_i
+        const uint32_t paired = counted & (counted >> 1) & 0x5555u;
+        uint32_t slot[CHUNK / 2];
+        // the 8 rank requests first, the 8 stores after: the latency of a shared-memory atomic with a result is
+        // paid once per chunk, not once per pair
+#pragma unroll
+        for (int i = 0; i < CHUNK / 2; ++i) {
+          const uint32_t y = __funnelshift_r(pkc, pkp, 28 - 4 * i);
+          slot[i] = 0;
+          if (paired & (1u << (2 * i))) slot[i] = atomicAdd(reinterpret_cast<uint32_t *>(s_cnt_b + G::bucket4(y)), 1u);
+        }
+#pragma unroll
+        for (int i = 0; i < CHUNK / 2; ++i) {
+          if (!(paired & (1u << (2 * i)))) continue;
+          const uint32_t y = __funnelshift_r(pkc, pkp, 28 - 4 * i);
+          const uint32_t sub = G::sub(y);
+          const bool staged = slot[i] < (uint32_t)BK_CAP;
+          const bool filler_like = (K == 12) && sub == BK_PAD;
+          if (staged)
+            *reinterpret_cast<uint16_t *>(s_stage_b + G::bucket4(y) * (BK_CAP / 2) + slot[i] * 2) =
+                (uint16_t)(filler_like ? BK_PAD : sub);
+          if (!staged || filler_like) {  // the row is full, or the one sub-key that reads as filler: directly
+            red_add_u32_keep(&counts[(y >> 2) & G::KMASK], 1u, keep);
+            red_add_u32_keep(&counts[y & G::KMASK], 1u, keep);
+          }
+        }
+        if (counted != (paired | (paired << 1))) {  // k-mers without a partner (run boundaries): directly
+          const uint32_t single = counted & ~(paired | (paired << 1));
+#pragma unroll 1
+          for (uint32_t m = single; m; m &= m - 1) {
+            const int j = __ffs(m) - 1;
+            red_add_u32_keep(&counts[__funnelshift_r(pkc, pkp, 30 - 2 * j) & G::KMASK], 1u, keep);
+          }
+        }
       }
     }
     __syncthreads();
@@ -222,9 +295,8 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
           for (uint32_t i = 0; i < take; ++i) {
             const uint32_t sub = row[i];
             if (sub == BK_PAD) continue;
-            const uint32_t c = (b << G.rest_bits) | (sub >> 4);
-            red_add_u32_keep(&counts[(((sub >> 2) & 3u) << G.core_bits) | c], 1u, keep);  // a.c
-            red_add_u32_keep(&counts[(c << 2) | (sub & 3u)], 1u, keep);                    // c.b
+            red_add_u32_keep(&counts[G::code_ac(b, sub)], 1u, keep);
+            red_add_u32_keep(&counts[G::code_cb(b, sub)], 1u, keep);
           }
         }
       }
@@ -238,21 +310,20 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
   block_sum_to(local, nwords);
 }
 
-// phase 2: one bucket per CTA.  Two shared-memory tables of 2^(rest_bits + 2) entries: tabB[(rest, b)] counts the
-// k-mers c.b -- the bucket's own contiguous slice of the count table -- and tabA[(a, rest)] the k-mers a.c, which
-// belong to four other slices: they go, plainly stored, to the CTA's part of a second table that bucket_fold_kernel
-// adds in afterwards (an entry of the count table would otherwise have two writers).
+// phase 2: one bucket per CTA.  Two shared-memory tables of 4^k / 1024 entries: tabB[sub & LOW] counts the k-mers
+// c.b -- the bucket's own contiguous slice of the count table -- and tabA[sub >> 2] = [a][rest of c] the k-mers a.c,
+// which belong to four other slices: they go, plainly stored, to the CTA's part of a second table that
+// bucket_fold_kernel adds in afterwards (an entry of the count table would otherwise have two writers).
 constexpr int BK_COUNT_THREADS = 1024;
+template <int K>
 __global__ void __launch_bounds__(BK_COUNT_THREADS, 1) bucket_count_kernel(const uint16_t *__restrict__ bk_buf,
                                                                         const uint32_t *__restrict__ bk_cursor,
-                                                                        uint32_t gcap, int k,
-                                                                        int32_t *__restrict__ counts,
+                                                                        uint32_t gcap, int32_t *__restrict__ counts,
                                                                         uint32_t *__restrict__ table_a) {
+  typedef PairGeom<K> G;
   extern __shared__ __align__(16) unsigned char ks_dyn_smem[];
-  const PairGeom G(k);
-  const uint32_t entries = 1u << (G.rest_bits + 2);
   uint32_t *tabB = reinterpret_cast<uint32_t *>(ks_dyn_smem);
-  uint32_t *tabA = tabB + entries;
+  uint32_t *tabA = tabB + G::ENTRIES;
   const uint32_t b = blockIdx.x;
   uint32_t n = bk_cursor[b];
   if (n > gcap) n = gcap;
@@ -265,14 +336,12 @@ __global__ void __launch_bounds__(BK_COUNT_THREADS, 1) bucket_count_kernel(const
   uint32_t i0 = threadIdx.x;
 #pragma unroll
   for (int u = 0; u < UNR; ++u) v[u] = (i0 + u * BK_COUNT_THREADS < nv) ? __ldcs(src + i0 + u * BK_COUNT_THREADS) : filler;
-  for (uint32_t i = threadIdx.x; i < 2 * entries; i += blockDim.x) tabB[i] = 0;
+  for (uint32_t i = threadIdx.x; i < 2 * G::ENTRIES; i += blockDim.x) tabB[i] = 0;
   __syncthreads();
-  const uint32_t restmask = (1u << G.rest_bits) - 1u;
   auto add1 = [&](uint32_t sub) {
     if (sub == BK_PAD) return;
-    const uint32_t rest = (sub >> 4) & restmask;
-    atomicAdd(&tabB[(rest << 2) | (sub & 3u)], 1u);
-    atomicAdd(&tabA[(((sub >> 2) & 3u) << G.rest_bits) | rest], 1u);
+    atomicAdd(&tabB[sub & G::LOW], 1u);
+    atomicAdd(&tabA[sub >> 2], 1u);
   };
   auto add8 = [&](const uint4 &x) {
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
@@ -293,25 +362,31 @@ __global__ void __launch_bounds__(BK_COUNT_THREADS, 1) bucket_count_kernel(const
   }
   if ((n & 4u) && threadIdx.x < 4) add1(base[nv * 8 + threadIdx.x]);  // n is a multiple of 4: one trailing granule
   __syncthreads();
-  uint32_t *slice = reinterpret_cast<uint32_t *>(counts) + ((size_t)b << (G.rest_bits + 2));
-  uint32_t *mineA = table_a + ((size_t)b << (G.rest_bits + 2));
-  for (uint32_t i = threadIdx.x; i < entries; i += blockDim.x) {
+  uint32_t *slice = reinterpret_cast<uint32_t *>(counts) + (size_t)b * G::ENTRIES;
+  uint32_t *mineA = table_a + (size_t)b * G::ENTRIES;
+  for (uint32_t i = threadIdx.x; i < G::ENTRIES; i += blockDim.x) {
     const uint32_t c = tabB[i];
     if (c) slice[i] += c;   // the slice belongs to this CTA; direct reductions of phase 1 are already in it
     mineA[i] = tabA[i];     // [a][rest] of this bucket
   }
 }
 
-// counts[a.c] += tableA[bucket(c)][a][rest(c)]
-__global__ void __launch_bounds__(256) bucket_fold_kernel(int32_t *__restrict__ counts, const uint32_t *__restrict__ table_a,
-                                                          int k) {
-  const PairGeom G(k);
-  const size_t n = (size_t)1 << (2 * k);
-  const uint32_t cmask = (uint32_t)(n >> 2) - 1u, restmask = (1u << G.rest_bits) - 1u;
-  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t a = (uint32_t)(x >> G.core_bits), c = (uint32_t)x & cmask;
-    const uint32_t add = __ldcs(&table_a[((size_t)(c >> G.rest_bits) << (G.rest_bits + 2)) | ((size_t)a << G.rest_bits) | (c & restmask)]);
-    if (add) counts[x] += (int32_t)add;
+// counts[a.c] += tableA[bucket(c)][a][rest(c)], four consecutive c per thread (same a, same bucket for k >= 8)
+template <int K>
+__global__ void __launch_bounds__(256) bucket_fold_kernel(int32_t *__restrict__ counts, const uint32_t *__restrict__ table_a) {
+  typedef PairGeom<K> G;
+  const size_t n4 = ((size_t)1 << (2 * K)) / 4;
+  constexpr uint32_t CMASK = G::KMASK >> 2, RESTMASK = (1u << G::REST) - 1u;
+  int4 *c4 = reinterpret_cast<int4 *>(counts);
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t x = (uint32_t)(q * 4), a = x >> (2 * K - 2), c = x & CMASK;
+    const uint4 add = __ldcs(reinterpret_cast<const uint4 *>(
+        &table_a[(size_t)(c >> G::REST) * G::ENTRIES + ((size_t)a << G::REST) + (c & RESTMASK)]));
+    if (add.x | add.y | add.z | add.w) {
+      int4 v = c4[q];
+      v.x += (int)add.x; v.y += (int)add.y; v.z += (int)add.z; v.w += (int)add.w;
+      c4[q] = v;
+    }
   }
 }
 
