@@ -1856,6 +1856,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
   // position.  A level whose list overflows is redone with the general walk.
   const bool fast_ok = !tab.tr && mw >= 15 && getenv("KS_NO_FAST_WALK") == nullptr;
   bool fast = fast_ok;
+  // ... and with min_width >= 31 none inside 32 positions: level 0 then works on units of two chunks
+  const bool pair_ok = fast_ok && mw >= 31 && getenv("KS_NO_PAIR") == nullptr;
   bool have_carry = false;  // the exchange runs once, also if level 0 has to be repeated with more room
   fx_t S_carry = 0;
   ExRec E_carry;
@@ -1864,7 +1866,9 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
   uint64_t revisit_chunks = 0;
   bool count_inscan = d_inscan != nullptr;
   for (;;) {
-    size_t tiles = (size_t)((total_chunks + TILE_THREADS - 1) / TILE_THREADS);
+    const bool pair = fast && pair_ok && nseg == 0;
+    const int64_t records = pair ? (total_chunks + 1) / 2 : total_chunks;
+    size_t tiles = (size_t)((records + TILE_THREADS - 1) / TILE_THREADS);
     if (tiles == 0 && !(sh && level == 0)) break;
     if (tiles == 0) tiles = 1;  // an empty shard still takes part in the carry exchange
     if (tiles > 0xfffffff0ull) return ctx->fail(KS_ERR_ARG, "input too large for one scan launch");
@@ -1970,19 +1974,27 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.child_cap = ctx->child_cap;
     if (tab.tr) CK(cudaMemsetAsync(ctx->child_count.p, 0, sizeof(unsigned long long), st));
     cudaEvent_t ps = ctx->prof_begin();
-    if (tab.tr) scan_gather_kernel<0, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (fast && tab.use_hash) scan_gather_kernel<4, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (tab.use_hash) scan_gather_kernel<4><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (fast && tab.use_rank) scan_gather_kernel<3, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (tab.use_rank) scan_gather_kernel<3><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (fast && tab.use_core) scan_gather_kernel<2, false, true, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (fast && tab.use_cls) scan_gather_kernel<2, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (fast && tab.use_lut) scan_gather_kernel<1, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (fast) scan_gather_kernel<0, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (tab.use_core) scan_gather_kernel<2, false, false, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (tab.use_cls) scan_gather_kernel<2><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (tab.use_lut) scan_gather_kernel<1><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else scan_gather_kernel<0><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+#define KS_GATHER(...) scan_gather_kernel<__VA_ARGS__><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A)
+    if (tab.tr) KS_GATHER(0, true);
+    else if (pair && tab.use_hash) KS_GATHER(4, false, true, false, true);
+    else if (pair && tab.use_rank) KS_GATHER(3, false, true, false, true);
+    else if (pair && tab.use_core) KS_GATHER(2, false, true, true, true);
+    else if (pair && tab.use_cls) KS_GATHER(2, false, true, false, true);
+    else if (pair && tab.use_lut) KS_GATHER(1, false, true, false, true);
+    else if (pair) KS_GATHER(0, false, true, false, true);
+    else if (fast && tab.use_hash) KS_GATHER(4, false, true);
+    else if (tab.use_hash) KS_GATHER(4);
+    else if (fast && tab.use_rank) KS_GATHER(3, false, true);
+    else if (tab.use_rank) KS_GATHER(3);
+    else if (fast && tab.use_core) KS_GATHER(2, false, true, true);
+    else if (fast && tab.use_cls) KS_GATHER(2, false, true);
+    else if (fast && tab.use_lut) KS_GATHER(1, false, true);
+    else if (fast) KS_GATHER(0, false, true);
+    else if (tab.use_core) KS_GATHER(2, false, false, true);
+    else if (tab.use_cls) KS_GATHER(2);
+    else if (tab.use_lut) KS_GATHER(1);
+    else KS_GATHER(0);
+#undef KS_GATHER
     group_scan_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
     group_top_kernel<<<1, TSCAN_THREADS, 0, st>>>(A);
     if (exchange && have_carry) {
@@ -2004,7 +2016,8 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
       LAUNCHED(1);
     }
     if (tab.tr) scan_walk_kernel<0, true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
-    else if (fast) scan_walk_fast_kernel<<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (pair) scan_walk_fast_kernel<true><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
+    else if (fast) scan_walk_fast_kernel<false><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (tab.use_cls) scan_walk_kernel<2><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else if (tab.use_lut) scan_walk_kernel<1><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
     else scan_walk_kernel<0><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A);
@@ -2013,7 +2026,12 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
       // the list is short (one entry per tile at most, plus the rare wide excursions); the kernel reads
       // its length on the device and strides over it, so no host round trip sits between the kernels
       const unsigned dgrid = (unsigned)std::min<size_t>(blocks_exact(tiles + 1024, 128), 148u * 8u);
-      if (tab.use_hash) scan_detail_kernel<4><<<dgrid, 128, 0, st>>>(A);
+      if (pair && tab.use_hash) scan_detail_kernel<4, true><<<dgrid, 128, 0, st>>>(A);
+      else if (pair && tab.use_rank) scan_detail_kernel<3, true><<<dgrid, 128, 0, st>>>(A);
+      else if (pair && tab.use_cls) scan_detail_kernel<2, true><<<dgrid, 128, 0, st>>>(A);
+      else if (pair && tab.use_lut) scan_detail_kernel<1, true><<<dgrid, 128, 0, st>>>(A);
+      else if (pair) scan_detail_kernel<0, true><<<dgrid, 128, 0, st>>>(A);
+      else if (tab.use_hash) scan_detail_kernel<4><<<dgrid, 128, 0, st>>>(A);
       else if (tab.use_rank) scan_detail_kernel<3><<<dgrid, 128, 0, st>>>(A);
       else if (tab.use_cls) scan_detail_kernel<2><<<dgrid, 128, 0, st>>>(A);
       else if (tab.use_lut) scan_detail_kernel<1><<<dgrid, 128, 0, st>>>(A);

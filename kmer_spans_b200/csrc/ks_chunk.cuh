@@ -426,30 +426,89 @@ struct FastChunk {
   }
 };
 
-// open-excursion element of a chunk from its summary and the state entering it (S_in >= 0); `closing`:
-// an excursion enters the chunk and returns to 0 inside it
-KS_HD void fast_walk_element(fx_t S_in, bool head, uint32_t live, const ChunkSummary &sm, int64_t p0, Ex &ex,
-                             bool &closing) {
-  const bool zero = head || S_in <= 0 || live != 0xffffu || S_in + (fx_t)sm.mn <= 0;
+// open-excursion element of a chunk (or a unit of two chunks) from its summary and the state entering it
+// (S_in >= 0); `closing`: an excursion enters and returns to 0 inside.  am / bbeg / bpk are offsets from p0.
+KS_HD void fast_walk_element_at(fx_t S_in, bool head, bool all_live, int64_t mn, int64_t mx, int64_t bm, uint32_t am,
+                                uint32_t bbeg, uint32_t bpk, bool open, int64_t p0, Ex &ex, bool &closing) {
+  const bool zero = head || S_in <= 0 || !all_live || S_in + (fx_t)mn <= 0;
   if (!zero) {
     ex.reset = 0; ex.open = 1; ex.beg = -1;
-    ex.M = S_in + (fx_t)sm.mx;
-    ex.pk = p0 + ((sm.bits >> 19) & 15u);
-  } else if (sm.bits & 0x80000000u) {
+    ex.M = S_in + (fx_t)mx;
+    ex.pk = p0 + am;
+  } else if (open) {
     ex.reset = 1; ex.open = 1;
-    ex.beg = p0 + ((sm.bits >> 23) & 15u);
-    ex.pk = p0 + ((sm.bits >> 27) & 15u);
-    ex.M = (fx_t)sm.bm;
+    ex.beg = p0 + bbeg;
+    ex.pk = p0 + bpk;
+    ex.M = (fx_t)bm;
   } else {
     ex.reset = 1; ex.open = 0; ex.M = -(((fx_t)1) << 126); ex.beg = -1; ex.pk = -1;
   }
   closing = !head && S_in > 0 && zero;
 }
-// the entering excursion of a closing chunk cannot qualify: its peak lies at or before p0 + 15 and is at
-// most max(M so far, S_in + max P)
-KS_HD bool fast_walk_cannot_qualify(const Ex &e_in, fx_t S_in, int64_t p0, int64_t mx, const ScanParams &prm) {
-  if ((uint64_t)(p0 + 15 - e_in.beg) < prm.min_width) return true;
+KS_HD void fast_walk_element(fx_t S_in, bool head, uint32_t live, const ChunkSummary &sm, int64_t p0, Ex &ex,
+                             bool &closing) {
+  fast_walk_element_at(S_in, head, live == 0xffffu, sm.mn, sm.mx, sm.bm, (sm.bits >> 19) & 15u, (sm.bits >> 23) & 15u,
+                       (sm.bits >> 27) & 15u, (sm.bits & 0x80000000u) != 0, p0, ex, closing);
+}
+// the entering excursion of a closing chunk cannot qualify: its peak lies at or before the last position of the
+// chunk (p0 + 15; p0 + 31 for a unit of two chunks) and is at most max(M so far, S_in + max P)
+KS_HD bool fast_walk_cannot_qualify(const Ex &e_in, fx_t S_in, int64_t p0, int64_t mx, const ScanParams &prm,
+                                    int span = CHUNK) {
+  if ((uint64_t)(p0 + span - 1 - e_in.beg) < prm.min_width) return true;
   return fx_max(e_in.M, S_in + (fx_t)mx) < prm.min_units;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Units of two chunks (min_width >= 31: an excursion inside 32 positions cannot qualify either).  The gather kernel
+// then leaves one record per 32 positions -- half the block scan, half the records, half the walk.  A unit is the
+// merge of the summaries of its two chunks; offsets are relative to the first position of the unit.
+struct UnitSummary {
+  int64_t ta, tb;  // transform x -> kill ? tb : max(x + ta, tb), 64-bit (32 terms below 2^57)
+  int64_t mn, mx, bm;
+  uint32_t kill, all_live;  // all_live: every position scored, none forced to 0
+  uint32_t am, bbeg, bpk, open;
+};
+KS_HD UnitSummary unit_from_chunk(int64_t ta, int64_t tb, uint32_t kill, uint32_t live, const ChunkSummary &sm) {
+  UnitSummary u;
+  u.ta = ta; u.tb = tb; u.kill = kill; u.all_live = live == 0xffffu ? 1u : 0u;
+  u.mn = sm.mn; u.mx = sm.mx; u.bm = sm.bm;
+  u.am = (sm.bits >> 19) & 15u; u.bbeg = (sm.bits >> 23) & 15u; u.bpk = (sm.bits >> 27) & 15u; u.open = sm.bits >> 31;
+  return u;
+}
+// l = positions 0..15, r = positions 16..31
+KS_HD UnitSummary unit_merge(const UnitSummary &l, const UnitSummary &r) {
+  UnitSummary u;
+  if (r.kill) {
+    u.ta = r.ta; u.tb = r.tb; u.kill = 1;
+  } else {
+    const int64_t t = l.tb + r.ta;
+    u.ta = l.ta + r.ta; u.tb = t > r.tb ? t : r.tb; u.kill = l.kill;
+  }
+  u.all_live = l.all_live & r.all_live;
+  // extrema of the prefix sums (exact when all positions are live; an upper bound for mx otherwise, which is all
+  // the walk asks of it then)
+  const int64_t cmn = l.ta + r.mn, cmx = l.ta + r.mx;
+  u.mn = cmn < l.mn ? cmn : l.mn;
+  if (cmx > l.mx) { u.mx = cmx; u.am = CHUNK + r.am; } else { u.mx = l.mx; u.am = l.am; }
+  // zero-start trajectory: s1 enters the second chunk; if it reaches 0 there, the second chunk's own trajectory
+  // takes over, otherwise the excursion open at the end of the first chunk runs on
+  const int64_t s1 = l.kill ? l.tb : (l.ta > l.tb ? l.ta : l.tb);
+  if (s1 <= 0 || !r.all_live || s1 + r.mn <= 0) {
+    u.open = r.open; u.bm = r.bm; u.bbeg = CHUNK + r.bbeg; u.bpk = CHUNK + r.bpk;
+  } else {
+    const int64_t cand = s1 + r.mx;
+    u.open = 1; u.bbeg = l.bbeg;
+    if (cand > l.bm) { u.bm = cand; u.bpk = CHUNK + r.am; } else { u.bm = l.bm; u.bpk = l.bpk; }
+  }
+  return u;
+}
+// the unit opens a scan: whatever entered is replaced by state 0
+KS_HD void unit_make_head(UnitSummary &u) {
+  const int64_t v = u.kill ? u.tb : (u.ta > u.tb ? u.ta : u.tb);
+  u.kill = 1; u.ta = 0; u.tb = v;
+}
+KS_HD void fast_walk_unit(fx_t S_in, bool head, const UnitSummary &u, int64_t p0, Ex &ex, bool &closing) {
+  fast_walk_element_at(S_in, head, u.all_live != 0, u.mn, u.mx, u.bm, u.am, u.bbeg, u.bpk, u.open != 0, p0, ex, closing);
 }
 
 // ---------------------------------------------------------------------------------------------

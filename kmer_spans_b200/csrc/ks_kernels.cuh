@@ -525,12 +525,23 @@ __global__ void __launch_bounds__(256) rank_tail_kernel(const LevelArgs A, uint3
 }
 
 constexpr uint32_t CORE_ESCAPE = 255;  // class byte of a core record: "the class is >= 255, read cls[code]"
-template <int kLut, bool kTr = false, bool kSumm = false, bool kCore = false>
+
+// st_flags of a record.  One chunk:  live (16 bits) | head << 16 | excl.kill << 17 | padding << 18 | am << 19 |
+// bbeg << 23 | bpk << 27 | open << 31.  A unit of two chunks (kPair) has 5-bit offsets and keeps "all 32 positions
+// live" instead of the mask:  all_live | am << 1 | bbeg << 6 | bpk << 11 | head << 16 | kill << 17 | padding << 18 |
+// open << 31 (scan_detail_kernel decodes the positions of the few units it walks again).
+constexpr uint32_t FL_HEAD = 0x10000u, FL_KILL = 0x20000u, FL_PAD = 0x40000u, FL_OPEN = 0x80000000u;
+__device__ __forceinline__ uint32_t unit_flag_bits(const UnitSummary &u) {
+  return (u.all_live ? 1u : 0u) | (u.am << 1) | (u.bbeg << 6) | (u.bpk << 11) | (u.open ? FL_OPEN : 0u);
+}
+
+template <int kLut, bool kTr = false, bool kSumm = false, bool kCore = false, bool kPair = false>
 __global__ void __launch_bounds__(TILE_THREADS,
                                   kLut == 3 ? KS_GATHER_MINBLOCKS_RANK
                                   : kSumm ? ((kLut == 1 || kLut == 2) ? KS_GATHER_MINBLOCKS_SUMM : KS_GATHER_MINBLOCKS_TABLE_SUMM)
                                           : ((kLut == 1 || kLut == 2) ? KS_GATHER_MINBLOCKS : KS_GATHER_MINBLOCKS_TABLE))
 scan_gather_kernel(const LevelArgs A) {
+  static_assert(!kPair || (kSumm && !kTr), "units of two chunks exist for the summary walk only");
   __shared__ Xf s_wxf[TILE_WARPS + 1];
   __shared__ int64_t s_lut[kCore ? CORE_ESCAPE : 1];  // scores of the classes a core record can name
   __shared__ typename std::conditional<kLut == 3, RankSmem, int>::type s_rk_store;  // rank mode only
@@ -554,14 +565,30 @@ scan_gather_kernel(const LevelArgs A) {
   }
   const int rk_qs = kLut == 3 ? A.prm->qs : 0;
   const int64_t tile = blockIdx.x;
-  // ---- chunk -> position mapping ----
-  const int64_t q = tile * TILE_THREADS + tid;
-  int64_t p0 = A.pad_p0;  // padding chunks behind the last real one read a position that is always resident
-  int n_in = 0;
+  const int64_t q = tile * TILE_THREADS + tid;  // record: one chunk, or a unit of two (kPair)
+  constexpr int NSUB = kPair ? 2 : 1;
+  const uint64_t keep = l2_policy_evict_last();
+  // results of the record
+  uint32_t live = 0, tkill = 0;
+  int64_t ta = 0, tb = -(1ll << 62);
+  ChunkSummary summ;
+  summ.mn = 0; summ.mx = 0; summ.bm = 0; summ.bits = 0;
+  UnitSummary unit;
   bool head = true;
-  if (q < A.total_chunks) {
-    if (A.nseg == 0) {
-      p0 = A.dense_start + 16 * q; n_in = 16; head = (q == 0 && A.dense_first);
+  int64_t p0 = A.pad_p0;  // padding chunks behind the last real one read a position that is always resident
+  uint32_t scored = 0, tr_first = 0;
+  int nreal = 0;
+#pragma unroll
+  for (int h = 0; h < NSUB; ++h) {
+  // ---- chunk -> position mapping ----
+  const int64_t qc = kPair ? 2 * q + h : q;
+  int n_in = 0;
+  bool chead = true;
+  int64_t cp0 = A.pad_p0;
+  if (qc < A.total_chunks) {
+    ++nreal;
+    if (kPair || A.nseg == 0) {
+      cp0 = A.dense_start + 16 * qc; n_in = 16; chead = (qc == 0 && A.dense_first);
     } else {
       int64_t lo = 0, hi = A.nseg;  // largest s in [0, nseg) with seg_chunk0[s] <= q
       while (hi - lo > 1) {
@@ -570,27 +597,27 @@ scan_gather_kernel(const LevelArgs A) {
       }
       int64_t c0 = (int64_t)__ldg(&A.seg_chunk0[lo]);
       int64_t sst = __ldg(&A.seg_start[lo]), ln = __ldg(&A.seg_len[lo]);
-      p0 = sst + 16 * (q - c0);
-      int64_t rem = sst + ln - p0;
+      cp0 = sst + 16 * (q - c0);
+      int64_t rem = sst + ln - cp0;
       n_in = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
-      head = (q == c0);
+      chead = (q == c0);
     }
   }
+  if (h == 0) { p0 = cp0; head = chead; }
   // ---- packed window [p0 - 16, p0 + 16) ([p0 - 32, p0 + 16) for 64-bit codes) ----
   uint64_t X = 0;
   uint32_t brk32 = 0;
   uint32_t w_hi32 = 0;
   uint64_t w_lo64 = 0;
   // ---- codes, gather (16 independent loads in flight), scores, chunk transform ----
-  uint32_t code[CHUNK], scored;
-  uint32_t tr_first = 0;
+  uint32_t code[CHUNK];
   if (kLut == 4) {
     uint64_t brk48;
-    load_window_wide(A.pk, A.brk, A.pk_first, p0, w_hi32, w_lo64, brk48);
+    load_window_wide(A.pk, A.brk, A.pk_first, cp0, w_hi32, w_lo64, brk48);
     const uint32_t inside = n_in >= 16 ? 0xffffu : ((1u << n_in) - 1u);
     scored = (uint32_t)(run_ending64(~brk48, A.k + 1) >> 32) & inside;  // position and the k before it: no break
   } else {
-    load_window(A, p0, X, brk32);
+    load_window(A, cp0, X, brk32);
   }
   if (kLut == 4) {
   } else if (kTr) {
@@ -607,7 +634,7 @@ scan_gather_kernel(const LevelArgs A) {
     while (F) {
       const int b = __ffs(F) - 1;
       F &= F - 1;
-      const int64_t f = p0 - 1 + b;
+      const int64_t f = cp0 - 1 + b;
       const uint8_t z1 = A.buf[f + 1], z2 = A.buf[f + 2];
       if (b >= 1 && (z1 == 0 || z2 == 0)) dead |= 1u << (b - 1);
       if (b <= 15 && z2 == 0) dead |= 1u << b;
@@ -620,26 +647,35 @@ scan_gather_kernel(const LevelArgs A) {
   } else {
     decode_scan(X, brk32, A.k, A.kmask, n_in, code, scored);
   }
-  const uint64_t keep = l2_policy_evict_last();
   // ---- gather: 16 independent loads per thread ----
   uint32_t c[CHUNK];   // class (kLut == 2) or count (kLut == 1)
   int64_t sv[CHUNK];   // score (table mode)
+  bool big = false;    // core mode: a class beyond the shared-memory table was met
   if (kLut == 2 && kCore) {
     // core mode: positions 2i and 2i+1 score the k-mers a.c and c.b around the same (k-1)-mer c (code[2i+1] >> 2 ==
     // code[2i] & cmask), and the record of c holds both classes: 8 gathers of 8 bytes per 16 positions
     const uint32_t cmask = A.kmask >> 2;
     const int ashift = 2 * A.k - 2;
+    uint2 rec[CHUNK / 2];
 #pragma unroll
     for (int i = 0; i < CHUNK / 2; ++i) {
-      const uint32_t need = (scored >> (2 * i)) & 3u;
-      uint2 rec = make_uint2(0u, 0u);
-      if (need) rec = ldg_u32x2_keep(&A.core[code[2 * i] & cmask], keep);
-      c[2 * i] = (need & 1u) ? __byte_perm(rec.x, 0u, 0x4440u | (code[2 * i] >> ashift)) : 0u;
-      c[2 * i + 1] = (need & 2u) ? __byte_perm(rec.y, 0u, 0x4440u | (code[2 * i + 1] & 3u)) : 0u;
+      rec[i] = make_uint2(0u, 0u);
+      if ((scored >> (2 * i)) & 3u) rec[i] = ldg_u32x2_keep(&A.core[code[2 * i] & cmask], keep);
     }
+    uint32_t esc = 0;
 #pragma unroll
-    for (int j = 0; j < CHUNK; ++j)  // rare: very abundant k-mers (classes beyond the first 255 distinct counts)
-      if (c[j] == CORE_ESCAPE) c[j] = ldg_u16_keep(&A.cls[code[j]], keep);
+    for (int i = 0; i < CHUNK / 2; ++i) {
+      // unscored positions pick a byte of an all-zero record or a class nobody looks at
+      c[2 * i] = __byte_perm(rec[i].x, 0u, 0x4440u | (code[2 * i] >> ashift));
+      c[2 * i + 1] = __byte_perm(rec[i].y, 0u, 0x4440u | (code[2 * i + 1] & 3u));
+      esc |= (c[2 * i] + 1u) | (c[2 * i + 1] + 1u);  // bit 8 set iff one of them is CORE_ESCAPE (255)
+    }
+    if (esc & 0x100u) {  // rare: very abundant k-mers (classes beyond the first 255 distinct counts)
+      big = true;
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j)
+        if (c[j] == CORE_ESCAPE && (scored & (1u << j))) c[j] = ldg_u16_keep(&A.cls[code[j]], keep);
+    }
   } else if (kLut == 2) {
     // class mode: 2-byte gather (the 4^k x 2 B table stays L2 resident where the 4 B count table does not)
 #pragma unroll
@@ -661,17 +697,19 @@ scan_gather_kernel(const LevelArgs A) {
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) sv[j] = (scored & (1u << j)) ? ldg_s64_keep(&A.wfx[code[j]], keep) : WFX_KILL;
   }
-  if (kCore) {
+  if (h == 0) {
+    if (kCore) {
 #pragma unroll
-    for (int i = 0; i < LUT_PER; ++i) {
-      const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
-      if (e < CORE_ESCAPE) s_lut[e] = pre_lut[i];
+      for (int i = 0; i < LUT_PER; ++i) {
+        const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
+        if (e < CORE_ESCAPE) s_lut[e] = pre_lut[i];
+      }
+      __syncthreads();
     }
-    __syncthreads();
-  }
-  if (kLut == 3) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+    if (kLut == 3) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
   }
   // value of a SCORED position (WFX_KILL = the table says "force the state to 0")
   auto value = [&](int j) -> int64_t {
@@ -695,27 +733,31 @@ scan_gather_kernel(const LevelArgs A) {
     else if (kLut == 1) __stcs(&A.st_c[(int64_t)j * A.Q + q], c[j]);
     else __stcs(&A.st_s[(int64_t)j * A.Q + q], v == WFX_KILL ? (int64_t)0 : v);
   };
-  uint32_t live = 0;
-  int64_t ta = 0, tb = -(1ll << 62);
-  uint32_t tkill = 0;
+  uint32_t clive = 0, ckill = 0;
+  int64_t cta = 0, ctb = -(1ll << 62);
+  ChunkSummary csumm;
+  csumm.mn = 0; csumm.mx = 0; csumm.bm = 0; csumm.bits = 0;
   bool general = !kSumm || scored != 0xffffu;
-  ChunkSummary summ;
-  summ.mn = 0; summ.mx = 0; summ.bm = 0; summ.bits = 0;
   if (kSumm && !general) {  // every position scored: prefix-sum formulation (ks_chunk.cuh)
     FastChunk fc;
     fc.init();
+    if (kLut == 2 && kCore && !big) {  // every class in the shared-memory table: no test per position
 #pragma unroll
-    for (int j = 0; j < CHUNK; ++j) {
-      const int64_t v = value(j);
-      stash(j, v);
-      fc.step(j, v);
+      for (int j = 0; j < CHUNK; ++j) fc.step(j, s_lut[c[j]]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) {
+        const int64_t v = value(j);
+        stash(j, v);
+        fc.step(j, v);
+      }
     }
     general = fc.bad;
     if (!fc.bad) {
-      live = 0xffffu;
-      ta = fc.a();
-      tb = fc.b();
-      summ = fc.summary();
+      clive = 0xffffu;
+      cta = fc.a();
+      ctb = fc.b();
+      csumm = fc.summary();
     }
   }
   if (general) {
@@ -727,20 +769,29 @@ scan_gather_kernel(const LevelArgs A) {
       stash(j, v);
       gc.template step<kSumm>(j, v);
     }
-    live = gc.live; ta = gc.ta; tb = gc.tb; tkill = gc.kill;
-    if (kSumm) summ = gc.summary();
+    clive = gc.live; cta = gc.ta; ctb = gc.tb; ckill = gc.kill;
+    if (kSumm) csumm = gc.summary();
   }
   if (kLut != 4 && A.inscan) {
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j)
       if (scored & (1u << j)) atomicAdd(&A.inscan[code[j]], 1);
   }
+  if (!kPair) {
+    live = clive; ta = cta; tb = ctb; tkill = ckill; summ = csumm;
+  } else if (h == 0) {
+    unit = unit_from_chunk(cta, ctb, ckill, clive, csumm);
+  } else if (qc < A.total_chunks) {  // a padding chunk behind the last real one leaves the unit as it is
+    unit = unit_merge(unit, unit_from_chunk(cta, ctb, ckill, clive, csumm));
+  }
+  }  // chunks of the record
+  if (kPair) { ta = unit.ta; tb = unit.tb; tkill = unit.kill; }
   Xf f;
   f.a = (fx_t)ta; f.b = (fx_t)tb; f.kill = tkill;
   if (head) { fx_t v = xf_apply(f, 0); f.kill = 1; f.a = 0; f.b = v; }
   // padding chunks behind the last real chunk of the launch must be transparent: the aggregates of a
   // shard are handed to the next one
-  const bool vchunk = q >= A.total_chunks;
+  const bool vchunk = nreal == 0;
   if (vchunk) f = xf_identity();
   // ---- block scan of the chunk transforms ----
   Xf inc = f;
@@ -773,12 +824,20 @@ scan_gather_kernel(const LevelArgs A) {
   excl = xf_compose(s_wxf[warp], excl);
   st_stream_fx(&A.st_ea[q], excl.a);
   st_stream_fx(&A.st_eb[q], excl.b);
-  uint32_t flags = live | (head ? 0x10000u : 0u) | (excl.kill ? 0x20000u : 0u) | (vchunk ? 0x40000u : 0u);
-  if (kSumm) {
-    flags |= summ.bits;
-    __stcs(&A.st_mn[q], (long long)summ.mn);
-    __stcs(&A.st_mx[q], (long long)summ.mx);
-    __stcs(&A.st_bm[q], (long long)summ.bm);
+  uint32_t flags = (head ? FL_HEAD : 0u) | (excl.kill ? FL_KILL : 0u) | (vchunk ? FL_PAD : 0u);
+  if (kPair) {
+    flags |= unit_flag_bits(unit);
+    __stcs(&A.st_mn[q], (long long)unit.mn);
+    __stcs(&A.st_mx[q], (long long)unit.mx);
+    __stcs(&A.st_bm[q], (long long)unit.bm);
+  } else {
+    flags |= live;
+    if (kSumm) {
+      flags |= summ.bits;
+      __stcs(&A.st_mn[q], (long long)summ.mn);
+      __stcs(&A.st_mx[q], (long long)summ.mx);
+      __stcs(&A.st_bm[q], (long long)summ.bm);
+    }
   }
   __stcs(&A.st_flags[q], flags);
   if (A.nseg != 0) __stcs(&A.st_p0[q], (long long)p0);
@@ -996,6 +1055,7 @@ scan_walk_kernel(const LevelArgs A) {
 //     p0 + 15 - start >= min_width (and its score bound reaches min_score) it cannot qualify; the rare
 //     survivors, and the one excursion per tile whose start lies in an earlier tile, go to
 //     scan_detail_kernel, which walks just those chunks position by position.
+template <bool kPair>
 __global__ void __launch_bounds__(TILE_THREADS, KS_WALKFAST_MINBLOCKS) scan_walk_fast_kernel(const LevelArgs A) {
   __shared__ Ex s_wex[TILE_WARPS + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1008,23 +1068,23 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_WALKFAST_MINBLOCKS) scan_walk
     S_tile = xf_apply(tx, A.group_S[tile / GROUP_TILES]);
   }
   const uint32_t fl = A.st_flags[q];
-  const uint32_t live = fl & 0xffffu;
-  const bool head = (fl & 0x10000u) != 0;
-  const int64_t p0 = A.nseg == 0 ? A.dense_start + 16 * q : A.st_p0[q];
+  const bool all_live = kPair ? (fl & 1u) != 0 : (fl & 0xffffu) == 0xffffu;
+  const bool head = (fl & FL_HEAD) != 0;
+  const int64_t p0 = kPair ? A.dense_start + 2 * CHUNK * q : (A.nseg == 0 ? A.dense_start + 16 * q : A.st_p0[q]);
   Xf excl;
   excl.a = ld_stream_fx(&A.st_ea[q]); excl.b = ld_stream_fx(&A.st_eb[q]); excl.kill = (fl >> 17) & 1u;
   const fx_t S_in = head ? (fx_t)0 : xf_apply(excl, S_tile);
-  ChunkSummary summ;
-  summ.mx = __ldcs(&A.st_mx[q]);
-  summ.bits = fl;
+  const int64_t mx = __ldcs(&A.st_mx[q]);
   Ex ex;
   bool closing = false;
-  if (fl & 0x40000u) {  // padding chunk: transparent
+  if (fl & FL_PAD) {  // padding chunk: transparent
     ex = ex_identity();
   } else {
-    summ.mn = (live == 0xffffu && S_in > 0) ? __ldcs(&A.st_mn[q]) : 0;  // only read where fast_walk_element looks at it
-    summ.bm = (fl & 0x80000000u) ? __ldcs(&A.st_bm[q]) : 0;
-    fast_walk_element(S_in, head, live, summ, p0, ex, closing);
+    const int64_t mn = (all_live && S_in > 0) ? __ldcs(&A.st_mn[q]) : 0;  // only read where the element looks at it
+    const int64_t bm = (fl & FL_OPEN) ? __ldcs(&A.st_bm[q]) : 0;
+    const uint32_t am = kPair ? (fl >> 1) & 31u : (fl >> 19) & 15u, bbeg = kPair ? (fl >> 6) & 31u : (fl >> 23) & 15u,
+                   bpk = kPair ? (fl >> 11) & 31u : (fl >> 27) & 15u;
+    fast_walk_element_at(S_in, head, all_live, mn, mx, bm, am, bbeg, bpk, (fl & FL_OPEN) != 0, p0, ex, closing);
   }
   Ex einc = ex;
 #pragma unroll
@@ -1059,7 +1119,7 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_WALKFAST_MINBLOCKS) scan_walk
     ScanParams prm;
     prm.min_width = A.prm->min_width;
     prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
-    if (fast_walk_cannot_qualify(eexcl, S_in, p0, summ.mx, prm)) return;
+    if (fast_walk_cannot_qualify(eexcl, S_in, p0, mx, prm, kPair ? 2 * CHUNK : CHUNK)) return;
   }
   const unsigned int slot = atomicAdd(A.detail_count, 1u);
   if (slot < A.detail_cap) {
@@ -1070,8 +1130,9 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_WALKFAST_MINBLOCKS) scan_walk
   }
 }
 
-// the chunks scan_walk_fast_kernel could not decide: position-by-position walk of the entering excursion
-template <int kLut>
+// the chunks scan_walk_fast_kernel could not decide: position-by-position walk of the entering excursion.  A unit of
+// two chunks (kPair) is walked chunk by chunk until the zero that closes the excursion is met.
+template <int kLut, bool kPair = false>
 __global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
   unsigned int n = *A.detail_count;
   if (n > A.detail_cap) n = A.detail_cap;
@@ -1082,19 +1143,27 @@ __global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
   prm.min_width = A.prm->min_width;
   prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
   const uint32_t fl = A.st_flags[q];
-  const uint32_t live = fl & 0xffffu;
-  const int64_t p0 = A.nseg == 0 ? A.dense_start + 16 * q : A.st_p0[q];
+  DevEmit emit{&A};
+  fx_t S_in = e.S_in, preM = -(((fx_t)1) << 126);
+  int64_t prePk = -1, p0 = 0;
+  int first_zero = -1;
+  for (int h = 0; h < (kPair ? 2 : 1) && first_zero < 0; ++h) {
+  if (kPair && 2 * q + h >= A.total_chunks) break;
+  p0 = kPair ? A.dense_start + 2 * CHUNK * q + CHUNK * h : (A.nseg == 0 ? A.dense_start + 16 * q : A.st_p0[q]);
   // the gather kernel kept only the summary of this chunk: decode and gather its positions again
   uint64_t X = 0;
   uint32_t brk32 = 0;
   uint32_t w_hi32 = 0;
   uint64_t w_lo64 = 0;
+  uint32_t live = fl & 0xffffu;
   if (kLut == 4) {
     uint64_t brk48;
     load_window_wide(A.pk, A.brk, A.pk_first, p0, w_hi32, w_lo64, brk48);
+    if (kPair) live = (uint32_t)(run_ending64(~brk48, A.k + 1) >> 32) & 0xffffu;
   } else {
     load_window(A, p0, X, brk32);
-  }
+    if (kPair) live = run_ending(~brk32, A.k + 1) >> 16;  // a unit keeps no mask: the scored positions, then minus
+  }                                                        // those the table forces to 0 (below)
   int64_t s[CHUNK];
 #pragma unroll
   for (int j = 0; j < CHUNK; ++j) {
@@ -1122,15 +1191,20 @@ __global__ void __launch_bounds__(128) scan_detail_kernel(const LevelArgs A) {
       } else {
         v = __ldg(&A.wfx[code]);
       }
+      if (kPair && v == WFX_KILL) { v = 0; live &= ~(1u << j); }
     }
     s[j] = v;
   }
-  DevEmit emit{&A};
   Ex ex;
-  fx_t preM;
-  int64_t prePk;
-  int first_zero;
-  chunk_walk(s, live, e.S_in, p0, prm, emit, ex, preM, prePk, first_zero);
+  fx_t pm;
+  int64_t pp;
+  chunk_walk(s, live, S_in, p0, prm, emit, ex, pm, pp, first_zero);
+  if (pm > preM) { preM = pm; prePk = pp; }
+  if (kPair && first_zero < 0) {  // no zero: every position live, the state leaves the chunk unclamped
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) S_in += (fx_t)s[j];
+  }
+  }
   if (first_zero < 0) continue;  // cannot happen: the fast walk saw a zero in this chunk
   if (e.reset) {
     Ex ein;

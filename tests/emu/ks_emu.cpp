@@ -180,6 +180,104 @@ static int emu_scan_impl(const uint8_t *buf, int64_t ntot, int k, const double *
       fx_t S = 0;
       Ex E = ex_identity();
       E.reset = 1; E.open = 0;
+      if (fast && level == 0 && min_width >= 31 && !getenv("KS_NO_PAIR")) {
+        // units of two chunks (scan_gather_kernel<..., kPair>): one merged summary per 32 positions
+        for (int64_t u = 0; u < (nchunks + 1) / 2; ++u) {
+          const int64_t p0u = sg.first + 32 * u;
+          UnitSummary U;
+          int64_t sv[2][16];
+          uint32_t lv[2] = {0, 0};
+          int nsub = 0;
+          for (int h = 0; h < 2; ++h) {
+            const int64_t ci = 2 * u + h;
+            if (ci >= nchunks) break;
+            ++nsub;
+            const int64_t p0 = p0u + 16 * h;
+            uint32_t code[16], scored, brk32, nul32;
+            uint64_t X;
+            window(P, p0, X, brk32, nul32);
+            decode_scan(X, brk32, k, kmask, 16, code, scored);
+            for (int j = 0; j < 16; ++j) {
+              sv[h][j] = 0;
+              if (scored & (1u << j)) {
+                int64_t v = wfx[code[j]];
+                if (v != WFX_KILL) { sv[h][j] = v; lv[h] |= 1u << j; }
+              }
+            }
+            ChunkSummary sm;
+            UnitSummary uc;
+            bool general = scored != 0xffffu;
+            if (!general) {
+              FastChunk fc;
+              fc.init();
+              for (int j = 0; j < 16; ++j) fc.step(j, wfx[code[j]]);
+              general = fc.bad;
+              if (!fc.bad) { sm = fc.summary(); uc = unit_from_chunk(fc.a(), fc.b(), 0, 0xffffu, sm); }
+            }
+            if (general) {
+              GeneralChunk gc;
+              gc.init();
+              for (int j = 0; j < 16; ++j) gc.step<true>(j, (scored & (1u << j)) ? wfx[code[j]] : WFX_KILL);
+              if (gc.live != lv[h]) return 2;
+              sm = gc.summary();
+              uc = unit_from_chunk(gc.ta, gc.tb, gc.kill, gc.live, sm);
+            }
+            U = h == 0 ? uc : unit_merge(U, uc);
+          }
+          const bool head = u == 0;
+          if (head) unit_make_head(U);
+          Ex ex;
+          bool closing = false;
+          fast_walk_unit(S, head, U, p0u, ex, closing);
+          // reference: the two chunks walked position by position with their true entering states
+          fx_t Sc = S;
+          Ex ex_ref = ex_identity();
+          bool zero_ref = false;
+          {
+            std::vector<Rec> scratch;
+            Emit none{&scratch};
+            for (int h = 0; h < nsub; ++h) {
+              Ex e1;
+              fx_t pm;
+              int64_t pp;
+              int z;
+              chunk_walk(sv[h], lv[h], Sc, p0u + 16 * h, prm, none, e1, pm, pp, z);
+              ex_ref = h == 0 ? e1 : ex_combine(ex_ref, e1);
+              zero_ref = zero_ref || z >= 0;
+              Sc = xf_apply(chunk_transform(sv[h], lv[h]), Sc);
+            }
+            if (!scratch.empty()) return 7;  // an excursion inside 32 positions cannot qualify
+          }
+          if (ex_ref.reset != ex.reset || ex_ref.open != ex.open || ex_ref.beg != ex.beg || ex_ref.pk != ex.pk ||
+              ex_ref.M != ex.M)
+            return 5;
+          if (closing != (!head && S > 0 && zero_ref)) return 6;
+          Xf fu;
+          fu.a = (fx_t)U.ta; fu.b = (fx_t)U.tb; fu.kill = U.kill;
+          if (xf_apply(fu, S) != Sc) return 8;  // merged transform == the chunks' transforms chained
+          if (closing && !fast_walk_cannot_qualify(E, S, p0u, U.mx, prm, 32)) {
+            ++n_detail;  // scan_detail_kernel<..., kPair>: first chunk, then the second if no zero was met
+            fx_t Sd = S, accM = -(((fx_t)1) << 126);
+            int64_t accPk = -1;
+            int fz = -1;
+            int64_t pz = 0;
+            for (int h = 0; h < nsub && fz < 0; ++h) {
+              Ex exd;
+              fx_t preM;
+              int64_t prePk;
+              chunk_walk(sv[h], lv[h], Sd, p0u + 16 * h, prm, emit, exd, preM, prePk, fz);
+              if (preM > accM) { accM = preM; accPk = prePk; }
+              pz = p0u + 16 * h;
+              if (fz < 0) { for (int j = 0; j < 16; ++j) Sd += (fx_t)sv[h][j]; }
+            }
+            if (fz < 0) return 3;
+            chunk_finish_entering(S, E, accM, accPk, fz, pz, prm, emit);
+          }
+          S = Sc;
+          E = ex_combine(E, ex);
+        }
+        continue;
+      }
       for (int64_t ci = 0; ci < nchunks; ++ci) {
         int64_t p0 = sg.first + 16 * ci;
         int64_t rem = sg.first + sg.second - p0;

@@ -194,6 +194,36 @@ def test_emu_fast_walk_vs_oracle(emu, oracle, k):
     assert detail < chunks / 4  # the position-by-position walk is the exception
 
 
+@pytest.mark.parametrize("k", [3, 6])
+def test_emu_pair_units_vs_oracle(emu, oracle, k, monkeypatch):
+    """min_width >= 31: units of two chunks (unit_merge + fast_walk_unit, what scan_gather_kernel<..., kPair> leaves
+    behind).  Every merged element, closing flag and transform is compared with the chunk-by-chunk walk inside
+    emu_scan_fast; the spans must equal the oracle's and those of the single-chunk formulation."""
+    rng = np.random.default_rng(4100 + k)
+    for trial in range(24):
+        seqs = [planted(rng, int(rng.integers(40, 6000))) for _ in range(int(rng.integers(1, 4)))]
+        kind = trial % 4
+        if kind == 0:
+            W = rng.choice([-1.0, 1.0], 4 ** k, p=[0.55, 0.45])
+        elif kind == 1:
+            W = rng.normal(-0.1, 1.0, 4 ** k)
+        elif kind == 2:
+            n, c = oracle.kmer_counts(seqs, k)
+            W = oracle.scores(c, k, n, 2)
+        else:
+            W = rng.normal(0.0, 1.0, 4 ** k)
+            W[rng.integers(0, 4 ** k, 3)] = np.nan
+            W[rng.integers(0, 4 ** k, 2)] = -np.inf
+        mw, ms = [(31, 0), (32, 1), (40, 4), (64, 0), (100, 2), (31, 6)][trial % 6]
+        o = oracle.kmer_regions(seqs, k, W, mw, ms)
+        e = emu.scan_fast(seqs, k, W, 0.0, mw, ms)
+        assert_spans(e, o, exact_scores=(kind in (0, 2)))
+        monkeypatch.setenv("KS_NO_PAIR", "1")
+        g = emu.scan_fast(seqs, k, W, 0.0, mw, ms)
+        monkeypatch.delenv("KS_NO_PAIR")
+        assert e["pos"].tolist() == g["pos"].tolist() and e["score"].tobytes() == g["score"].tobytes()
+
+
 def test_emu_fast_walk_config1(emu, oracle):
     seq = synth.config1()[0].tobytes()
     n, c = oracle.kmer_counts(seq, 8)
