@@ -191,7 +191,7 @@ struct ks_ctx {
   DBuf lg_cnt_a, lg_cnt_b, lg_idx_a, lg_idx_b;
   DBuf bk_table_a;         // bucketed counting: counts of the a.c k-mers per bucket, folded into the table at the end
   DBuf bk_buf, bk_cursor;  // bucketed counting (ks_count.cuh): sub-keys per bucket, fill of every bucket
-  bool smem_attr_set = false;
+  bool smem_attr_set = false, core_attr_set = false;
   DBuf win_match, win_cnt, win_pre, win_scratch, win_codes, win_fix, win_hist, win_pos;
   DBuf st_aux, child_pk, child_c, child_count, tr_tables;
   DBuf st_mn, st_mx, st_bm, detail, detail_count;
@@ -1757,9 +1757,10 @@ static int ensure_tiles(ks_ctx *ctx, size_t tiles, bool lut_mode, bool need_p0, 
   CK(ctx->st_eb.ensure(Q * 16));
   CK(ctx->st_flags.ensure(Q * 4));
   if (need_p0) CK(ctx->st_p0.ensure(Q * 8));
-  CK(ctx->tile_xf.ensure(tiles * sizeof(XfRec)));
-  CK(ctx->group_xf.ensure((tiles / 32 + 2) * sizeof(XfRec)));
-  CK(ctx->group_S.ensure((tiles / 32 + 2) * 16));
+  const size_t xf_tiles = tiles * TILE_WARPS;  // room for warp tiles (scan_gather_core_kernel)
+  CK(ctx->tile_xf.ensure(xf_tiles * sizeof(XfRec)));
+  CK(ctx->group_xf.ensure((xf_tiles / 32 + 2) * sizeof(XfRec)));
+  CK(ctx->group_S.ensure((xf_tiles / 32 + 2) * 16));
   CK(ctx->group_ex.ensure((tiles / 32 + 2) * sizeof(ExRec)));
   CK(ctx->pending_list.ensure(tiles * 4 + 64));
   CK(ctx->pending_count.ensure(64));
@@ -1939,6 +1940,10 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.group_S = ctx->group_S.as<fx_t>();
     A.group_ex = ctx->group_ex.as<ExRec>();
     A.ngroups = (int64_t)((tiles + 31) / 32);
+    const bool core_pipe = pair && tab.use_core && !count_inscan && getenv("KS_NO_CORE_PIPE") == nullptr;
+    A.xf_log = core_pipe ? 5 : TILE_LOG;
+    A.xf_ntiles = core_pipe ? (int64_t)tiles * TILE_WARPS : (int64_t)tiles;
+    A.xf_ngroups = (A.xf_ntiles + 31) / 32;
     A.pending_list = ctx->pending_list.as<uint32_t>();
     A.pending_count = ctx->pending_count.as<unsigned int>();
     CK(cudaMemsetAsync(ctx->pending_count.p, 0, 4, st));
@@ -1978,7 +1983,13 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     if (tab.tr) KS_GATHER(0, true);
     else if (pair && tab.use_hash) KS_GATHER(4, false, true, false, true);
     else if (pair && tab.use_rank) KS_GATHER(3, false, true, false, true);
-    else if (pair && tab.use_core) KS_GATHER(2, false, true, true, true);
+    else if (core_pipe) {
+      if (!ctx->core_attr_set) {  // 34 KB of shared memory per CTA: ask for the large carve-out once
+        CK(cudaFuncSetAttribute(scan_gather_core_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ctx->core_attr_set = true;
+      }
+      scan_gather_core_kernel<<<(unsigned)std::min<size_t>(tiles, (size_t)148 * KS_CORE_MINBLOCKS), TILE_THREADS, 0, st>>>(A);
+    } else if (pair && tab.use_core) KS_GATHER(2, false, true, true, true);
     else if (pair && tab.use_cls) KS_GATHER(2, false, true, false, true);
     else if (pair && tab.use_lut) KS_GATHER(1, false, true, false, true);
     else if (pair) KS_GATHER(0, false, true, false, true);
@@ -1995,7 +2006,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     else if (tab.use_lut) KS_GATHER(1);
     else KS_GATHER(0);
 #undef KS_GATHER
-    group_scan_kernel<<<blocks_exact((size_t)A.ngroups, 8), 256, 0, st>>>(A);
+    group_scan_kernel<<<blocks_exact((size_t)A.xf_ngroups, 8), 256, 0, st>>>(A);
     group_top_kernel<<<1, TSCAN_THREADS, 0, st>>>(A);
     if (exchange && have_carry) {
       A.S_start = S_carry;

@@ -400,10 +400,12 @@ struct GeneralChunk {
 struct FastChunk {
   int64_t P, mnT, bMx, mx;
   uint32_t am, bpk, jz1;
-  bool bad;
-  KS_HD void init() { P = 0; mnT = 1ll << 62; bMx = 0; mx = -(1ll << 62); am = 0; bpk = 0; jz1 = 0; bad = false; }
+  int32_t hmin;  // smallest high word met: INT32_MIN iff a WFX_KILL entry was among the values
+  KS_HD void init() { P = 0; mnT = 1ll << 62; bMx = 0; mx = -(1ll << 62); am = 0; bpk = 0; jz1 = 0; hmin = 0; }
+  KS_HD bool bad() const { return hmin == INT32_MIN; }
   KS_HD void step(int j, int64_t v) {
-    bad = bad || ((int32_t)(v >> 32) == INT32_MIN);
+    const int32_t vh = (int32_t)(v >> 32);
+    hmin = vh < hmin ? vh : hmin;
     P += v;
     const bool newmin = P <= mnT;
     mnT = newmin ? P : mnT;

@@ -33,6 +33,8 @@ namespace ks {
 #endif
 constexpr int TILE_THREADS = KS_TILE_THREADS;
 constexpr int TILE_WARPS = TILE_THREADS / 32;
+constexpr int TILE_LOG = TILE_THREADS == 64 ? 6 : TILE_THREADS == 128 ? 7 : TILE_THREADS == 256 ? 8 : -1;
+static_assert(TILE_LOG > 0 && (1 << TILE_LOG) == TILE_THREADS, "KS_TILE_THREADS: 64, 128 or 256");
 
 // ------------------------------------------------------------------------------------------
 // streaming (evict-first) 128-bit load for the sequence: it is read once per pass and must not push
@@ -322,6 +324,10 @@ struct LevelArgs {
   XfRec *group_xf;      // aggregate transform per group of 32 tiles
   fx_t *group_S;        // state entering the group (group_top_kernel)
   int64_t ngroups;
+  // the tiles of the TRANSFORM scan (tile_xf / group_xf / group_S) cover 1 << xf_log records each: the CTA tiles of
+  // scan_gather_kernel (xf_log = TILE_LOG, xf_ntiles = ntiles) or the warp tiles of scan_gather_core_kernel (5)
+  int xf_log;
+  int64_t xf_ntiles, xf_ngroups;
   ExRec *tile_ex;       // open-excursion aggregate per tile (scan_walk_kernel)
   ExRec *group_ex;      // the same per group of 32 tiles (group_ex_kernel)
   ExPending *pending;   // one slot per tile
@@ -401,6 +407,9 @@ struct DevEmit {
 #endif
 #ifndef KS_GATHER_MINBLOCKS_RANK
 #define KS_GATHER_MINBLOCKS_RANK 6
+#endif
+#ifndef KS_GATHER_MINBLOCKS_PAIR
+#define KS_GATHER_MINBLOCKS_PAIR 6
 #endif
 #ifndef KS_WALKFAST_MINBLOCKS
 #define KS_WALKFAST_MINBLOCKS 16
@@ -538,11 +547,12 @@ __device__ __forceinline__ uint32_t unit_flag_bits(const UnitSummary &u) {
 template <int kLut, bool kTr = false, bool kSumm = false, bool kCore = false, bool kPair = false>
 __global__ void __launch_bounds__(TILE_THREADS,
                                   kLut == 3 ? KS_GATHER_MINBLOCKS_RANK
+                                  : (kPair && kLut == 2 && kCore) ? KS_GATHER_MINBLOCKS_PAIR
                                   : kSumm ? ((kLut == 1 || kLut == 2) ? KS_GATHER_MINBLOCKS_SUMM : KS_GATHER_MINBLOCKS_TABLE_SUMM)
                                           : ((kLut == 1 || kLut == 2) ? KS_GATHER_MINBLOCKS : KS_GATHER_MINBLOCKS_TABLE))
 scan_gather_kernel(const LevelArgs A) {
   static_assert(!kPair || (kSumm && !kTr), "units of two chunks exist for the summary walk only");
-  __shared__ Xf s_wxf[TILE_WARPS + 1];
+  __shared__ Xf s_wxf[TILE_WARPS];
   __shared__ int64_t s_lut[kCore ? CORE_ESCAPE : 1];  // scores of the classes a core record can name
   __shared__ typename std::conditional<kLut == 3, RankSmem, int>::type s_rk_store;  // rank mode only
   const RankSmem *s_rk = kLut == 3 ? reinterpret_cast<const RankSmem *>(&s_rk_store) : nullptr;
@@ -567,6 +577,9 @@ scan_gather_kernel(const LevelArgs A) {
   const int64_t tile = blockIdx.x;
   const int64_t q = tile * TILE_THREADS + tid;  // record: one chunk, or a unit of two (kPair)
   constexpr int NSUB = kPair ? 2 : 1;
+  // core mode on units: the gathers of BOTH chunks are issued before the first chunk is worked on, so a thread
+  // waits for memory once per 32 positions (the other modes hold too many registers per chunk for that)
+  constexpr bool kAhead = kPair && kLut == 2 && kCore;
   const uint64_t keep = l2_policy_evict_last();
   // results of the record
   uint32_t live = 0, tkill = 0;
@@ -576,215 +589,241 @@ scan_gather_kernel(const LevelArgs A) {
   UnitSummary unit;
   bool head = true;
   int64_t p0 = A.pad_p0;  // padding chunks behind the last real one read a position that is always resident
-  uint32_t scored = 0, tr_first = 0;
+  uint32_t tr_first = 0;
   int nreal = 0;
-#pragma unroll
-  for (int h = 0; h < NSUB; ++h) {
-  // ---- chunk -> position mapping ----
-  const int64_t qc = kPair ? 2 * q + h : q;
-  int n_in = 0;
-  bool chead = true;
-  int64_t cp0 = A.pad_p0;
-  if (qc < A.total_chunks) {
-    ++nreal;
-    if (kPair || A.nseg == 0) {
-      cp0 = A.dense_start + 16 * qc; n_in = 16; chead = (qc == 0 && A.dense_first);
-    } else {
-      int64_t lo = 0, hi = A.nseg;  // largest s in [0, nseg) with seg_chunk0[s] <= q
-      while (hi - lo > 1) {
-        int64_t mid = (lo + hi) >> 1;
-        if (__ldg(&A.seg_chunk0[mid]) <= (uint64_t)q) lo = mid; else hi = mid;
+  // ---- per chunk: what the issue step leaves for the work step ----
+  uint64_t Xs[NSUB];          // packed window [p0 - 16, p0 + 16)
+  uint32_t scoreds[NSUB];
+  uint32_t w_hi32s[NSUB];     // 64-bit codes: [p0 - 32, p0 + 16)
+  uint64_t w_lo64s[NSUB];
+  uint2 recs[NSUB][kCore ? CHUNK / 2 : 1];            // core mode: record of the (k-1)-mer under positions 2i, 2i+1
+  uint32_t cs[NSUB][(kLut == 1 || kLut == 2 || kLut == 3) ? CHUNK : 1];  // class / count / rank position
+  int64_t svs[NSUB][(kLut == 0 || kLut == 4) ? CHUNK : 1];                // score (table mode, hash mode)
+
+  // ---- issue: chunk -> position mapping, packed window, codes, gather (up to 16 independent loads) ----
+  auto issue = [&](const int h) {
+    const int64_t qc = kPair ? 2 * q + h : q;
+    int n_in = 0;
+    bool chead = true;
+    int64_t cp0 = A.pad_p0;
+    if (qc < A.total_chunks) {
+      ++nreal;
+      if (kPair || A.nseg == 0) {
+        cp0 = A.dense_start + 16 * qc; n_in = 16; chead = (qc == 0 && A.dense_first);
+      } else {
+        int64_t lo = 0, hi = A.nseg;  // largest s in [0, nseg) with seg_chunk0[s] <= q
+        while (hi - lo > 1) {
+          int64_t mid = (lo + hi) >> 1;
+          if (__ldg(&A.seg_chunk0[mid]) <= (uint64_t)q) lo = mid; else hi = mid;
+        }
+        int64_t c0 = (int64_t)__ldg(&A.seg_chunk0[lo]);
+        int64_t sst = __ldg(&A.seg_start[lo]), ln = __ldg(&A.seg_len[lo]);
+        cp0 = sst + 16 * (q - c0);
+        int64_t rem = sst + ln - cp0;
+        n_in = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
+        chead = (q == c0);
       }
-      int64_t c0 = (int64_t)__ldg(&A.seg_chunk0[lo]);
-      int64_t sst = __ldg(&A.seg_start[lo]), ln = __ldg(&A.seg_len[lo]);
-      cp0 = sst + 16 * (q - c0);
-      int64_t rem = sst + ln - cp0;
-      n_in = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
-      chead = (q == c0);
     }
-  }
-  if (h == 0) { p0 = cp0; head = chead; }
-  // ---- packed window [p0 - 16, p0 + 16) ([p0 - 32, p0 + 16) for 64-bit codes) ----
-  uint64_t X = 0;
-  uint32_t brk32 = 0;
-  uint32_t w_hi32 = 0;
-  uint64_t w_lo64 = 0;
-  // ---- codes, gather (16 independent loads in flight), scores, chunk transform ----
-  uint32_t code[CHUNK];
-  if (kLut == 4) {
-    uint64_t brk48;
-    load_window_wide(A.pk, A.brk, A.pk_first, cp0, w_hi32, w_lo64, brk48);
-    const uint32_t inside = n_in >= 16 ? 0xffffu : ((1u << n_in) - 1u);
-    scored = (uint32_t)(run_ending64(~brk48, A.k + 1) >> 32) & inside;  // position and the k before it: no break
-  } else {
-    load_window(A, cp0, X, brk32);
-  }
-  if (kLut == 4) {
-  } else if (kTr) {
-    // k-mer ENDING at every position; the first k-mer of a run carries the initial score (:344-354)
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j) code[j] = (uint32_t)(X >> (30 - 2 * j)) & A.kmask;
-    const uint32_t runk = run_ending(~brk32, A.k);
-    const uint32_t first32 = runk & (brk32 << A.k);
-    const uint32_t inside = n_in >= 16 ? 0xffffu : ((1u << n_in) - 1u);
-    // a run is not looked at when the terminator sits at or right behind the base that follows its
-    // first k-mer (:340-341); first k-mers are rare, so the two ASCII bytes are read only for them
-    uint32_t dead = 0;
-    uint32_t F = (first32 >> 15) & 0x1ffffu;  // bit 0: position p0 - 1, bit j + 1: position p0 + j
-    while (F) {
-      const int b = __ffs(F) - 1;
-      F &= F - 1;
-      const int64_t f = cp0 - 1 + b;
-      const uint8_t z1 = A.buf[f + 1], z2 = A.buf[f + 2];
-      if (b >= 1 && (z1 == 0 || z2 == 0)) dead |= 1u << (b - 1);
-      if (b <= 15 && z2 == 0) dead |= 1u << b;
+    if (h == 0) { p0 = cp0; head = chead; }
+    uint64_t X = 0;
+    uint32_t brk32 = 0, scored = 0;
+    uint32_t code[CHUNK];
+    if (kLut == 4) {
+      uint64_t brk48;
+      load_window_wide(A.pk, A.brk, A.pk_first, cp0, w_hi32s[h], w_lo64s[h], brk48);
+      const uint32_t inside = n_in >= 16 ? 0xffffu : ((1u << n_in) - 1u);
+      scored = (uint32_t)(run_ending64(~brk48, A.k + 1) >> 32) & inside;  // position and the k before it: no break
+    } else {
+      load_window(A, cp0, X, brk32);
     }
-    tr_first = (first32 >> 16) & inside & ~dead;
-    scored = ((run_ending(~brk32, A.k + 1) >> 16) & inside & ~dead) | tr_first;
+    if (kLut == 4) {
+    } else if (kTr) {
+      // k-mer ENDING at every position; the first k-mer of a run carries the initial score (:344-354)
 #pragma unroll
-    for (int j = 0; j < CHUNK; ++j)
-      if (tr_first & (1u << j)) code[j] += A.nk;  // second half of the table: initial scores
-  } else {
-    decode_scan(X, brk32, A.k, A.kmask, n_in, code, scored);
-  }
-  // ---- gather: 16 independent loads per thread ----
-  uint32_t c[CHUNK];   // class (kLut == 2) or count (kLut == 1)
-  int64_t sv[CHUNK];   // score (table mode)
-  bool big = false;    // core mode: a class beyond the shared-memory table was met
-  if (kLut == 2 && kCore) {
-    // core mode: positions 2i and 2i+1 score the k-mers a.c and c.b around the same (k-1)-mer c (code[2i+1] >> 2 ==
-    // code[2i] & cmask), and the record of c holds both classes: 8 gathers of 8 bytes per 16 positions
-    const uint32_t cmask = A.kmask >> 2;
-    const int ashift = 2 * A.k - 2;
-    uint2 rec[CHUNK / 2];
-#pragma unroll
-    for (int i = 0; i < CHUNK / 2; ++i) {
-      rec[i] = make_uint2(0u, 0u);
-      if ((scored >> (2 * i)) & 3u) rec[i] = ldg_u32x2_keep(&A.core[code[2 * i] & cmask], keep);
-    }
-    uint32_t esc = 0;
-#pragma unroll
-    for (int i = 0; i < CHUNK / 2; ++i) {
-      // unscored positions pick a byte of an all-zero record or a class nobody looks at
-      c[2 * i] = __byte_perm(rec[i].x, 0u, 0x4440u | (code[2 * i] >> ashift));
-      c[2 * i + 1] = __byte_perm(rec[i].y, 0u, 0x4440u | (code[2 * i + 1] & 3u));
-      esc |= (c[2 * i] + 1u) | (c[2 * i + 1] + 1u);  // bit 8 set iff one of them is CORE_ESCAPE (255)
-    }
-    if (esc & 0x100u) {  // rare: very abundant k-mers (classes beyond the first 255 distinct counts)
-      big = true;
+      for (int j = 0; j < CHUNK; ++j) code[j] = (uint32_t)(X >> (30 - 2 * j)) & A.kmask;
+      const uint32_t runk = run_ending(~brk32, A.k);
+      const uint32_t first32 = runk & (brk32 << A.k);
+      const uint32_t inside = n_in >= 16 ? 0xffffu : ((1u << n_in) - 1u);
+      // a run is not looked at when the terminator sits at or right behind the base that follows its
+      // first k-mer (:340-341); first k-mers are rare, so the two ASCII bytes are read only for them
+      uint32_t dead = 0;
+      uint32_t F = (first32 >> 15) & 0x1ffffu;  // bit 0: position p0 - 1, bit j + 1: position p0 + j
+      while (F) {
+        const int b = __ffs(F) - 1;
+        F &= F - 1;
+        const int64_t f = cp0 - 1 + b;
+        const uint8_t z1 = A.buf[f + 1], z2 = A.buf[f + 2];
+        if (b >= 1 && (z1 == 0 || z2 == 0)) dead |= 1u << (b - 1);
+        if (b <= 15 && z2 == 0) dead |= 1u << b;
+      }
+      tr_first = (first32 >> 16) & inside & ~dead;
+      scored = ((run_ending(~brk32, A.k + 1) >> 16) & inside & ~dead) | tr_first;
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j)
-        if (c[j] == CORE_ESCAPE && (scored & (1u << j))) c[j] = ldg_u16_keep(&A.cls[code[j]], keep);
+        if (tr_first & (1u << j)) code[j] += A.nk;  // second half of the table: initial scores
+    } else {
+      decode_scan(X, brk32, A.k, A.kmask, n_in, code, scored);
     }
-  } else if (kLut == 2) {
-    // class mode: 2-byte gather (the 4^k x 2 B table stays L2 resident where the 4 B count table does not)
+    Xs[h] = X;
+    scoreds[h] = scored;
+    if (kLut == 2 && kCore) {
+      // core mode: positions 2i and 2i+1 score the k-mers a.c and c.b around the same (k-1)-mer c (code[2i+1] >> 2
+      // == code[2i] & cmask), and the record of c holds both classes: 8 gathers of 8 bytes per 16 positions
+      const uint32_t cmask = A.kmask >> 2;
 #pragma unroll
-    for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u16_keep(&A.cls[code[j]], keep) : 0u;
-  } else if (kLut == 3) {
-    // rank mode: 4-byte position in the rank order (4^k x 4 B, L2 resident at k <= 12) instead of the 8-byte score
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u32_keep(&A.rk_pos[code[j]], keep) : 0u;
-  } else if (kLut == 4) {
-    // large k: the k-mer ending at position j - 1 sits 32 - 2j bits above the low end of the 96-bit window
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j)
-      sv[j] = (scored & (1u << j)) ? hash_lookup(A.hslots, A.hmask, wide_code(w_hi32, w_lo64, 32 - 2 * j, A.kmask64))
-                                   : WFX_KILL;
-  } else if (kLut == 1) {
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j) c[j] = (scored & (1u << j)) ? ldg_u32_keep(&A.counts[code[j]], keep) : 0u;
-  } else {
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j) sv[j] = (scored & (1u << j)) ? ldg_s64_keep(&A.wfx[code[j]], keep) : WFX_KILL;
-  }
-  if (h == 0) {
-    if (kCore) {
-#pragma unroll
-      for (int i = 0; i < LUT_PER; ++i) {
-        const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
-        if (e < CORE_ESCAPE) s_lut[e] = pre_lut[i];
+      for (int i = 0; i < CHUNK / 2; ++i) {
+        recs[h][i] = make_uint2(0u, 0u);
+        if ((scored >> (2 * i)) & 3u) recs[h][i] = ldg_u32x2_keep(&A.core[code[2 * i] & cmask], keep);
       }
-      __syncthreads();
-    }
-    if (kLut == 3) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();
-    }
-  }
-  // value of a SCORED position (WFX_KILL = the table says "force the state to 0")
-  auto value = [&](int j) -> int64_t {
-    if (kLut == 2 && kCore) return c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&A.lut[c[j]]);
-    if (kLut == 2) return __ldg(&A.lut[c[j]]);
-    if (kLut == 3) return rank_value(A, s_rk, c[j], rk_qs);
-    if (kLut == 1) {
-      if (c[j] < A.lut_size) return __ldg(&A.lut[c[j]]);
-      uint32_t lo = 0, hi = A.sp_n;  // rare: very abundant k-mer, look it up in the sorted sparse list
-      while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(&A.sp_count[mid]) <= c[j]) lo = mid; else hi = mid;
-      }
-      return __ldg(&A.sp_val[lo]);
-    }
-    return sv[j];
-  };
-  auto stash = [&](int j, int64_t v) {
-    if (kSumm) return;  // the fast walk works on the chunk summary; scan_detail_kernel gathers again
-    if (kLut == 2) __stcs(&reinterpret_cast<uint16_t *>(A.st_c)[(int64_t)j * A.Q + q], (uint16_t)c[j]);
-    else if (kLut == 1) __stcs(&A.st_c[(int64_t)j * A.Q + q], c[j]);
-    else __stcs(&A.st_s[(int64_t)j * A.Q + q], v == WFX_KILL ? (int64_t)0 : v);
-  };
-  uint32_t clive = 0, ckill = 0;
-  int64_t cta = 0, ctb = -(1ll << 62);
-  ChunkSummary csumm;
-  csumm.mn = 0; csumm.mx = 0; csumm.bm = 0; csumm.bits = 0;
-  bool general = !kSumm || scored != 0xffffu;
-  if (kSumm && !general) {  // every position scored: prefix-sum formulation (ks_chunk.cuh)
-    FastChunk fc;
-    fc.init();
-    if (kLut == 2 && kCore && !big) {  // every class in the shared-memory table: no test per position
+    } else if (kLut == 2) {
+      // class mode: 2-byte gather (the 4^k x 2 B table stays L2 resident where the 4 B count table does not)
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j) fc.step(j, s_lut[c[j]]);
+      for (int j = 0; j < CHUNK; ++j) cs[h][j] = (scored & (1u << j)) ? ldg_u16_keep(&A.cls[code[j]], keep) : 0u;
+    } else if (kLut == 3) {
+      // rank mode: 4-byte position in the rank order (4^k x 4 B, L2 resident at k <= 12), not the 8-byte score
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) cs[h][j] = (scored & (1u << j)) ? ldg_u32_keep(&A.rk_pos[code[j]], keep) : 0u;
+    } else if (kLut == 4) {
+      // large k: the k-mer ending at position j - 1 sits 32 - 2j bits above the low end of the 96-bit window
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j)
+        svs[h][j] = (scored & (1u << j))
+                        ? hash_lookup(A.hslots, A.hmask, wide_code(w_hi32s[h], w_lo64s[h], 32 - 2 * j, A.kmask64))
+                        : WFX_KILL;
+    } else if (kLut == 1) {
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) cs[h][j] = (scored & (1u << j)) ? ldg_u32_keep(&A.counts[code[j]], keep) : 0u;
     } else {
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j) {
-        const int64_t v = value(j);
-        stash(j, v);
-        fc.step(j, v);
+      for (int j = 0; j < CHUNK; ++j)
+        svs[h][j] = (scored & (1u << j)) ? ldg_s64_keep(&A.wfx[code[j]], keep) : WFX_KILL;
+    }
+  };
+
+  // ---- work: classes -> scores, chunk transform and summary, merged into the record ----
+  auto work = [&](const int h) {
+    const uint64_t X = Xs[h];
+    const uint32_t scored = scoreds[h];
+    // codes are needed again only off the beaten path (escape classes, in-scan counts)
+    auto code_at = [&](int j) -> uint32_t { return (uint32_t)(X >> (32 - 2 * j)) & A.kmask; };
+    uint32_t c[(kLut == 1 || kLut == 2 || kLut == 3) ? CHUNK : 1];
+    bool big = false;  // core mode: a class beyond the shared-memory table was met
+    if (kLut == 2 && kCore) {
+      const int ashift = 2 * A.k + 30;  // a of the pair i sits 2k - 2 bits above the low end of its code
+      uint32_t esc = 0;
+#pragma unroll
+      for (int i = 0; i < CHUNK / 2; ++i) {
+        // unscored positions pick a byte of an all-zero record or a class nobody looks at
+        c[2 * i] = __byte_perm(recs[h][i].x, 0u, 0x4440u | ((uint32_t)(X >> (ashift - 4 * i)) & 3u));
+        c[2 * i + 1] = __byte_perm(recs[h][i].y, 0u, 0x4440u | ((uint32_t)(X >> (30 - 4 * i)) & 3u));
+        esc |= (c[2 * i] + 1u) | (c[2 * i + 1] + 1u);  // bit 8 set iff one of them is CORE_ESCAPE (255)
+      }
+      if (esc & 0x100u) {  // rare: very abundant k-mers (classes beyond the first 255 distinct counts)
+        big = true;
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j)
+          if (c[j] == CORE_ESCAPE && (scored & (1u << j))) c[j] = ldg_u16_keep(&A.cls[code_at(j)], keep);
+      }
+    } else if (kLut == 1 || kLut == 2 || kLut == 3) {
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) c[j] = cs[h][j];
+    }
+    // value of a SCORED position (WFX_KILL = the table says "force the state to 0")
+    auto value = [&](int j) -> int64_t {
+      if (kLut == 2 && kCore) return c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&A.lut[c[j]]);
+      if (kLut == 2) return __ldg(&A.lut[c[j]]);
+      if (kLut == 3) return rank_value(A, s_rk, c[j], rk_qs);
+      if (kLut == 1) {
+        if (c[j] < A.lut_size) return __ldg(&A.lut[c[j]]);
+        uint32_t lo = 0, hi = A.sp_n;  // rare: very abundant k-mer, look it up in the sorted sparse list
+        while (hi - lo > 1) {
+          uint32_t mid = (lo + hi) >> 1;
+          if (__ldg(&A.sp_count[mid]) <= c[j]) lo = mid; else hi = mid;
+        }
+        return __ldg(&A.sp_val[lo]);
+      }
+      return svs[h][j];
+    };
+    auto stash = [&](int j, int64_t v) {
+      if (kSumm) return;  // the fast walk works on the chunk summary; scan_detail_kernel gathers again
+      if (kLut == 2) __stcs(&reinterpret_cast<uint16_t *>(A.st_c)[(int64_t)j * A.Q + q], (uint16_t)c[j]);
+      else if (kLut == 1) __stcs(&A.st_c[(int64_t)j * A.Q + q], c[j]);
+      else __stcs(&A.st_s[(int64_t)j * A.Q + q], v == WFX_KILL ? (int64_t)0 : v);
+    };
+    uint32_t clive = 0, ckill = 0;
+    int64_t cta = 0, ctb = -(1ll << 62);
+    ChunkSummary csumm;
+    csumm.mn = 0; csumm.mx = 0; csumm.bm = 0; csumm.bits = 0;
+    bool general = !kSumm || scored != 0xffffu;
+    if (kSumm && !general) {  // every position scored: prefix-sum formulation (ks_chunk.cuh)
+      FastChunk fc;
+      fc.init();
+      if (kLut == 2 && kCore && !big) {  // every class in the shared-memory table: no test per position
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) fc.step(j, s_lut[c[j]]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+          const int64_t v = value(j);
+          stash(j, v);
+          fc.step(j, v);
+        }
+      }
+      general = fc.bad();
+      if (!fc.bad()) {
+        clive = 0xffffu;
+        cta = fc.a();
+        ctb = fc.b();
+        csumm = fc.summary();
       }
     }
-    general = fc.bad;
-    if (!fc.bad) {
-      clive = 0xffffu;
-      cta = fc.a();
-      ctb = fc.b();
-      csumm = fc.summary();
-    }
-  }
-  if (general) {
-    GeneralChunk gc;
-    gc.init();
+    if (general) {
+      GeneralChunk gc;
+      gc.init();
 #pragma unroll
-    for (int j = 0; j < CHUNK; ++j) {
-      const int64_t v = (scored & (1u << j)) ? value(j) : WFX_KILL;
-      stash(j, v);
-      gc.template step<kSumm>(j, v);
+      for (int j = 0; j < CHUNK; ++j) {
+        const int64_t v = (scored & (1u << j)) ? value(j) : WFX_KILL;
+        stash(j, v);
+        gc.template step<kSumm>(j, v);
+      }
+      clive = gc.live; cta = gc.ta; ctb = gc.tb; ckill = gc.kill;
+      if (kSumm) csumm = gc.summary();
     }
-    clive = gc.live; cta = gc.ta; ctb = gc.tb; ckill = gc.kill;
-    if (kSumm) csumm = gc.summary();
-  }
-  if (kLut != 4 && A.inscan) {
+    if (kLut != 4 && !kTr && A.inscan) {
 #pragma unroll
-    for (int j = 0; j < CHUNK; ++j)
-      if (scored & (1u << j)) atomicAdd(&A.inscan[code[j]], 1);
+      for (int j = 0; j < CHUNK; ++j)
+        if (scored & (1u << j)) atomicAdd(&A.inscan[code_at(j)], 1);
+    }
+    if (!kPair) {
+      live = clive; ta = cta; tb = ctb; tkill = ckill; summ = csumm;
+    } else if (h == 0) {
+      unit = unit_from_chunk(cta, ctb, ckill, clive, csumm);
+    } else if (2 * q + h < A.total_chunks) {  // a padding chunk behind the last real one leaves the unit as it is
+      unit = unit_merge(unit, unit_from_chunk(cta, ctb, ckill, clive, csumm));
+    }
+  };
+
+#pragma unroll
+  for (int h = 0; h < NSUB; ++h)
+    if (h == 0 || kAhead) issue(h);
+  // the small tables: their loads were issued at the top, the gathers are in flight now
+  if (kCore) {
+#pragma unroll
+    for (int i = 0; i < LUT_PER; ++i) {
+      const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
+      if (e < CORE_ESCAPE) s_lut[e] = pre_lut[i];
+    }
+    __syncthreads();
   }
-  if (!kPair) {
-    live = clive; ta = cta; tb = ctb; tkill = ckill; summ = csumm;
-  } else if (h == 0) {
-    unit = unit_from_chunk(cta, ctb, ckill, clive, csumm);
-  } else if (qc < A.total_chunks) {  // a padding chunk behind the last real one leaves the unit as it is
-    unit = unit_merge(unit, unit_from_chunk(cta, ctb, ckill, clive, csumm));
+  if (kLut == 3) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
   }
-  }  // chunks of the record
+#pragma unroll
+  for (int h = 0; h < NSUB; ++h) {
+    if (h > 0 && !kAhead) issue(h);
+    work(h);
+  }
   if (kPair) { ta = unit.ta; tb = unit.tb; tkill = unit.kill; }
   Xf f;
   f.a = (fx_t)ta; f.b = (fx_t)tb; f.kill = tkill;
@@ -804,24 +843,18 @@ scan_gather_kernel(const LevelArgs A) {
   if (lane == 0) excl = xf_identity();
   if (lane == 31) s_wxf[warp] = inc;
   __syncthreads();
-  if (warp == 0) {  // exclusive scan of the warp totals by one warp: s_wxf[w] <- totals of warps < w
-    Xf ti = lane < TILE_WARPS ? s_wxf[lane] : xf_identity();
-#pragma unroll
-    for (int o = 1; o < TILE_WARPS; o <<= 1) {
-      Xf y = shfl_xf(ti, (lane - o) & 31);
-      if (lane >= o) ti = xf_compose(y, ti);
-    }
-    Xf te = shfl_xf(ti, (lane - 1) & 31);
-    if (lane == 0) te = xf_identity();
-    if (lane < TILE_WARPS) s_wxf[lane] = te;
-    if (lane == TILE_WARPS - 1) {  // aggregate of the tile
+  {  // totals of the warps before this one: at most TILE_WARPS - 1 compositions, folded by every warp for itself
+     // (one barrier; a second-level scan by one warp would keep the others waiting at a second one)
+    Xf pre = xf_identity();
+    for (int w = 0; w < warp; ++w) pre = xf_compose(pre, s_wxf[w]);
+    excl = xf_compose(pre, excl);
+    if (warp == TILE_WARPS - 1 && lane == 31) {  // aggregate of the tile
+      const Xf ti = xf_compose(pre, inc);
       XfRec rr;
       rr.a = ti.a; rr.b = ti.b; rr.kill = ti.kill; rr.pad[0] = rr.pad[1] = rr.pad[2] = 0;
       A.tile_xf[tile] = rr;
     }
   }
-  __syncthreads();
-  excl = xf_compose(s_wxf[warp], excl);
   st_stream_fx(&A.st_ea[q], excl.a);
   st_stream_fx(&A.st_eb[q], excl.b);
   uint32_t flags = (head ? FL_HEAD : 0u) | (excl.kill ? FL_KILL : 0u) | (vchunk ? FL_PAD : 0u);
@@ -841,7 +874,206 @@ scan_gather_kernel(const LevelArgs A) {
   }
   __stcs(&A.st_flags[q], flags);
   if (A.nseg != 0) __stcs(&A.st_p0[q], (long long)p0);
-  if (kTr) A.st_aux[q] = tr_first | (scored << 16);
+  if (kTr) A.st_aux[q] = tr_first | (scoreds[0] << 16);
+}
+
+// ------------------------------------------------------------------------------------------
+// Level 0 of the default path (class mode through core records, units of two chunks): the same records as
+// scan_gather_kernel<2, false, true, true, true>, produced by persistent CTAs that keep the gathers of the NEXT chunk
+// in flight while the current one is worked on.  A gather is a cp.async from the core table into the thread's own
+// slots of a shared-memory stage (no registers held while it is under way, no barrier: a thread reads only what it
+// copied itself); the packed words of the tile after next are loaded a step earlier still.  The plain kernel
+// alternates "wait for 16 gathers" and "1 300 instructions" per warp and the two hardly overlap: measured, gathers
+// alone 0.69 ms, instructions alone 0.45 ms, together 0.93 ms.
+// The copies are 16 bytes (.cg) -- the aligned PAIR of 8-byte records holding the wanted one: measured
+// (tools/unit_peaks3.cu, profiles/r02_unit_peaks3.json) 8-byte cp.async gathers run at 137 G/s, 16-byte ones at
+// the 284 G/s of ld.global.
+#ifndef KS_CORE_MINBLOCKS
+#define KS_CORE_MINBLOCKS 6
+#endif
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, uint32_t src_bytes) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+struct CoreWin { uint32_t pk0, pk1, pk2, b0, b1, b2; };       // packed words / break masks around a unit
+struct CoreFlight { uint64_t X0, X1; uint32_t scored; };      // windows and scored positions of its two chunks
+struct CoreChunkOut { int64_t ta, tb; ChunkSummary sm; uint32_t kill, live; };
+// the exceptions (a break in the chunk, a class beyond the shared-memory table, a table entry that forces the state
+// to 0): kept out of line so that the loop of the kernel stays small enough for the instruction cache
+__device__ __noinline__ void core_chunk_general(const uint16_t *__restrict__ cls, const int64_t *__restrict__ lut,
+                                                uint32_t kmask, int k, const int64_t *s_lut, const uint4 *recs,
+                                                uint64_t X, uint32_t scored, CoreChunkOut *out) {
+  const uint64_t keep = l2_policy_evict_last();
+  const int ashift = 2 * k + 30;
+  // three rounds of independent loads (records, escaped classes, scores), then the recurrences
+  uint32_t c[CHUNK];
+#pragma unroll
+  for (int i = 0; i < CHUNK / 2; ++i) {
+    const uint32_t half = (uint32_t)(X >> (32 - 4 * i)) & 1u;
+    const uint2 rec = *reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(recs + (size_t)i * TILE_THREADS) + 8 * half);
+    c[2 * i] = __byte_perm(rec.x, 0u, 0x4440u | ((uint32_t)(X >> (ashift - 4 * i)) & 3u));
+    c[2 * i + 1] = __byte_perm(rec.y, 0u, 0x4440u | ((uint32_t)(X >> (30 - 4 * i)) & 3u));
+  }
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j)
+    if (c[j] == CORE_ESCAPE && (scored & (1u << j))) c[j] = ldg_u16_keep(&cls[(uint32_t)(X >> (32 - 2 * j)) & kmask], keep);
+  int64_t v[CHUNK];
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j)
+    v[j] = !(scored & (1u << j)) ? WFX_KILL : (c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&lut[c[j]]));
+  if (scored == 0xffffu) {
+    FastChunk fc;
+    fc.init();
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) fc.step(j, v[j]);
+    if (!fc.bad()) {
+      out->ta = fc.a(); out->tb = fc.b(); out->kill = 0; out->live = 0xffffu; out->sm = fc.summary();
+      return;
+    }
+  }
+  GeneralChunk gc;
+  gc.init();
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) gc.template step<true>(j, v[j]);
+  out->ta = gc.ta; out->tb = gc.tb; out->kill = gc.kill; out->live = gc.live; out->sm = gc.summary();
+}
+
+__global__ void __launch_bounds__(TILE_THREADS, KS_CORE_MINBLOCKS) scan_gather_core_kernel(const LevelArgs A) {
+  // every WARP scans its own tiles of 32 units (xf_log = 5): no barrier in the loop, so a warp that meets one of
+  // the slow chunks holds nobody up
+  __shared__ int64_t s_lut[CORE_ESCAPE];
+  __shared__ uint4 s_rec[2][CHUNK / 2][TILE_THREADS];  // [chunk of the unit = stage][pair i][thread]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int LUT_PER = (int)(CORE_ESCAPE + TILE_THREADS - 1) / TILE_THREADS;
+  int64_t pre_lut[LUT_PER];
+#pragma unroll
+  for (int i = 0; i < LUT_PER; ++i) {
+    const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
+    pre_lut[i] = (e < CORE_ESCAPE && e < A.lut_size) ? __ldg(&A.lut[e]) : 0;
+  }
+  const uint32_t cmask = A.kmask >> 2;
+  const int64_t w0 = A.dense_start >> 4;  // packed word of the first chunk of the launch (16-aligned start)
+  const int64_t G = (int64_t)gridDim.x * TILE_WARPS;  // warps of the grid
+
+  // packed words of this thread's unit in warp tile wt; chunks behind the end read as "every position breaks"
+  auto load_win = [&](int64_t wt) -> CoreFlight {
+    CoreWin w;
+    w.pk0 = w.pk1 = w.pk2 = 0u; w.b0 = w.b1 = w.b2 = 0xffffu;
+    const int64_t c0 = 2 * (wt * 32 + lane);
+    if (wt < A.xf_ntiles && c0 < A.total_chunks) {
+      const int64_t wq = w0 + c0;
+      w.pk0 = __ldg(&A.pk[wq - 1]); w.pk1 = __ldg(&A.pk[wq]);
+      w.b0 = __ldg(&A.brk[wq - 1]); w.b1 = __ldg(&A.brk[wq]);
+      if (c0 + 1 < A.total_chunks) { w.pk2 = __ldg(&A.pk[wq + 1]); w.b2 = __ldg(&A.brk[wq + 1]); }
+    }
+    CoreFlight f;  // scored positions as decode_scan finds them
+    f.X0 = ((uint64_t)w.pk0 << 32) | w.pk1;
+    f.X1 = ((uint64_t)w.pk1 << 32) | w.pk2;
+    const uint32_t sc0 = run_ending(~(w.b0 | (w.b1 << 16)), A.k + 1) >> 16;
+    const uint32_t sc1 = run_ending(~(w.b1 | (w.b2 << 16)), A.k + 1) >> 16;
+    f.scored = sc0 | (sc1 << 16);
+    return f;
+  };
+  // the 8 gathers of one chunk (window X, scored positions sc) into stage st
+  auto issue = [&](int st, uint64_t X, uint32_t sc) {
+#pragma unroll
+    for (int i = 0; i < CHUNK / 2; ++i) {
+      const bool need = ((sc >> (2 * i)) & 3u) != 0u;  // unscored pairs: zero fill, nothing read
+      const uint32_t idx = need ? ((uint32_t)(X >> (32 - 4 * i)) & cmask & ~1u) : 0u;
+      cp_async16_zfill(&s_rec[st][i][tid], &A.core[idx], need ? 16u : 0u);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int64_t wt = (int64_t)blockIdx.x * TILE_WARPS + warp;
+  CoreFlight cur = load_win(wt);
+  issue(0, cur.X0, cur.scored & 0xffffu);
+  CoreFlight nxt = load_win(wt + G);
+#pragma unroll
+  for (int i = 0; i < LUT_PER; ++i) {
+    const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
+    if (e < CORE_ESCAPE) s_lut[e] = pre_lut[i];
+  }
+  __syncthreads();
+  const int ashift = 2 * A.k + 30;  // a of pair i sits 2k - 2 bits above the low end of its code
+  for (; wt < A.xf_ntiles; wt += G) {
+    const int64_t q = wt * 32 + lane;
+    const int64_t left = A.total_chunks - 2 * q;
+    const int nreal = left >= 2 ? 2 : (left > 0 ? (int)left : 0);
+    UnitSummary unit;
+    unit.ta = 0; unit.tb = 0; unit.mn = 0; unit.mx = 0; unit.bm = 0;
+    unit.kill = 0; unit.all_live = 0; unit.am = 0; unit.bbeg = 0; unit.bpk = 0; unit.open = 0;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      // the next chunk's gathers go out before this one is worked on
+      if (h == 0) issue(1, cur.X1, cur.scored >> 16);
+      else if (wt + G < A.xf_ntiles) issue(0, nxt.X0, nxt.scored & 0xffffu);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // the gathers of THIS chunk have landed
+      if (h >= nreal) continue;
+      const uint64_t X = h ? cur.X1 : cur.X0;
+      const uint32_t scored = (cur.scored >> (16 * h)) & 0xffffu;
+      const uint4 *recs = &s_rec[h][0][tid];
+      CoreChunkOut o;
+      bool general = scored != 0xffffu;
+      if (!general) {  // every position scored: prefix-sum formulation (ks_chunk.cuh)
+        uint32_t c[CHUNK];
+        uint32_t esc = 0;
+#pragma unroll
+        for (int i = 0; i < CHUNK / 2; ++i) {
+          // the record of the pair's (k-1)-mer: the half of the 16-byte copy its lowest bit names
+          const uint32_t half = (uint32_t)(X >> (32 - 4 * i)) & 1u;
+          const uint2 rec =
+              *reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(recs + (size_t)i * TILE_THREADS) + 8 * half);
+          c[2 * i] = __byte_perm(rec.x, 0u, 0x4440u | ((uint32_t)(X >> (ashift - 4 * i)) & 3u));
+          c[2 * i + 1] = __byte_perm(rec.y, 0u, 0x4440u | ((uint32_t)(X >> (30 - 4 * i)) & 3u));
+          esc |= (c[2 * i] + 1u) | (c[2 * i + 1] + 1u);  // bit 8 set iff one of them is CORE_ESCAPE (255)
+        }
+        general = (esc & 0x100u) != 0u;  // rare: a class beyond the first 255 distinct counts
+        if (!general) {
+          FastChunk fc;
+          fc.init();
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) fc.step(j, s_lut[c[j]]);
+          general = fc.bad();
+          o.ta = fc.a(); o.tb = fc.b(); o.kill = 0; o.live = 0xffffu; o.sm = fc.summary();
+        }
+      }
+      if (general) core_chunk_general(A.cls, A.lut, A.kmask, A.k, s_lut, recs, X, scored, &o);
+      const UnitSummary uc = unit_from_chunk(o.ta, o.tb, o.kill, o.live, o.sm);
+      if (h == 0) unit = uc; else unit = unit_merge(unit, uc);
+    }
+    cur = nxt;
+    nxt = load_win(wt + 2 * G);
+    const bool head = q == 0 && A.dense_first;
+    Xf f;
+    f.a = (fx_t)unit.ta; f.b = (fx_t)unit.tb; f.kill = unit.kill;
+    if (head) { fx_t v = xf_apply(f, 0); f.kill = 1; f.a = 0; f.b = v; }
+    const bool vchunk = nreal == 0;  // padding behind the last real chunk: transparent
+    if (vchunk) f = xf_identity();
+    // ---- warp scan of the unit transforms ----
+    Xf inc = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      Xf y = shfl_xf(inc, (lane - o) & 31);
+      if (lane >= o) inc = xf_compose(y, inc);
+    }
+    Xf excl = shfl_xf(inc, (lane - 1) & 31);
+    if (lane == 0) excl = xf_identity();
+    if (lane == 31) {  // aggregate of the warp tile
+      XfRec rr;
+      rr.a = inc.a; rr.b = inc.b; rr.kill = inc.kill; rr.pad[0] = rr.pad[1] = rr.pad[2] = 0;
+      A.tile_xf[wt] = rr;
+    }
+    st_stream_fx(&A.st_ea[q], excl.a);
+    st_stream_fx(&A.st_eb[q], excl.b);
+    __stcs(&A.st_mn[q], (long long)unit.mn);
+    __stcs(&A.st_mx[q], (long long)unit.mx);
+    __stcs(&A.st_bm[q], (long long)unit.bm);
+    __stcs(&A.st_flags[q], (head ? FL_HEAD : 0u) | (excl.kill ? FL_KILL : 0u) | (vchunk ? FL_PAD : 0u) |
+                               unit_flag_bits(unit));
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // State entering every tile, in two tiny kernels: a warp scans the aggregates of 32 consecutive tiles
@@ -852,10 +1084,10 @@ constexpr int GROUP_TILES = 32;
 __global__ void __launch_bounds__(256) group_scan_kernel(const LevelArgs A) {
   const int lane = threadIdx.x & 31;
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (g >= A.ngroups) return;
+  if (g >= A.xf_ngroups) return;
   const int64_t t = g * GROUP_TILES + lane;
   Xf x = xf_identity();
-  if (t < A.ntiles) {
+  if (t < A.xf_ntiles) {
     XfRec r = A.tile_xf[t];
     x.a = r.a; x.b = r.b; x.kill = r.kill;
   }
@@ -867,7 +1099,7 @@ __global__ void __launch_bounds__(256) group_scan_kernel(const LevelArgs A) {
   }
   Xf excl = shfl_xf(inc, (lane - 1) & 31);
   if (lane == 0) excl = xf_identity();
-  if (t < A.ntiles) {
+  if (t < A.xf_ntiles) {
     XfRec r;
     r.a = excl.a; r.b = excl.b; r.kill = excl.kill; r.pad[0] = r.pad[1] = r.pad[2] = 0;
     A.tile_xf[t] = r;
@@ -883,8 +1115,8 @@ constexpr int TSCAN_THREADS = 256;
 __global__ void __launch_bounds__(TSCAN_THREADS) group_top_kernel(const LevelArgs A) {
   __shared__ Xf sh[TSCAN_THREADS];
   const int tid = threadIdx.x;
-  const int64_t per = (A.ngroups + TSCAN_THREADS - 1) / TSCAN_THREADS;
-  const int64_t t0 = per * tid, t1 = (t0 + per < A.ngroups) ? t0 + per : A.ngroups;
+  const int64_t per = (A.xf_ngroups + TSCAN_THREADS - 1) / TSCAN_THREADS;
+  const int64_t t0 = per * tid, t1 = (t0 + per < A.xf_ngroups) ? t0 + per : A.xf_ngroups;
   Xf f = xf_identity();
   for (int64_t t = t0; t < t1; ++t) {
     XfRec r = A.group_xf[t];
@@ -942,18 +1174,19 @@ struct StashScoresCls {  // class mode: 2-byte class from the stash, score from 
 template <int kLut, bool kTr = false>
 __global__ void __launch_bounds__(TILE_THREADS, kLut ? KS_WALK_MINBLOCKS : KS_WALK_MINBLOCKS_TABLE)
 scan_walk_kernel(const LevelArgs A) {
-  __shared__ Ex s_wex[TILE_WARPS + 1];
+  __shared__ Ex s_wex[TILE_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile = blockIdx.x;
   const int64_t q = tile * TILE_THREADS + tid;
   ScanParams prm;
   prm.min_width = A.prm->min_width;
   prm.min_units = fx_make((uint64_t)A.prm->min_hi, A.prm->min_lo);
-  fx_t S_tile;
+  fx_t S_tile;  // state entering the transform tile of this record
   {
-    XfRec r = A.tile_xf[tile];
+    const int64_t xt = q >> A.xf_log;
+    XfRec r = A.tile_xf[xt];
     Xf tx; tx.a = r.a; tx.b = r.b; tx.kill = r.kill;
-    S_tile = xf_apply(tx, A.group_S[tile / GROUP_TILES]);
+    S_tile = xf_apply(tx, A.group_S[xt / GROUP_TILES]);
   }
   const uint32_t fl = A.st_flags[q];
   const uint32_t live = fl & 0xffffu;
@@ -1002,24 +1235,15 @@ scan_walk_kernel(const LevelArgs A) {
   if (lane == 0) eexcl = ex_identity();
   if (lane == 31) s_wex[warp] = einc;
   __syncthreads();
-  if (warp == 0) {
-    Ex ti = lane < TILE_WARPS ? s_wex[lane] : ex_identity();
-#pragma unroll
-    for (int o = 1; o < TILE_WARPS; o <<= 1) {
-      Ex y = shfl_ex(ti, (lane - o) & 31);
-      if (lane >= o) ti = ex_combine(y, ti);
-    }
-    Ex te = shfl_ex(ti, (lane - 1) & 31);
-    if (lane == 0) te = ex_identity();
-    if (lane < TILE_WARPS) s_wex[lane] = te;
-    if (lane == TILE_WARPS - 1) {
-      ExRec rr;
-      rr.M = ti.M; rr.beg = ti.beg; rr.pk = ti.pk; rr.reset = ti.reset; rr.open = ti.open; rr.pad[0] = rr.pad[1] = 0;
-      A.tile_ex[tile] = rr;
-    }
+  Ex wpre = ex_identity();  // the warps before this one, folded by every warp for itself (one barrier)
+  for (int w = 0; w < warp; ++w) wpre = ex_combine(wpre, s_wex[w]);
+  if (warp == TILE_WARPS - 1 && lane == 31) {
+    const Ex ti = ex_combine(wpre, einc);
+    ExRec rr;
+    rr.M = ti.M; rr.beg = ti.beg; rr.pk = ti.pk; rr.reset = ti.reset; rr.open = ti.open; rr.pad[0] = rr.pad[1] = 0;
+    A.tile_ex[tile] = rr;
   }
-  __syncthreads();
-  eexcl = ex_combine(s_wex[warp], eexcl);
+  eexcl = ex_combine(wpre, eexcl);
   if (!head && S_in > 0 && first_zero >= 0) {
     if (eexcl.reset) {
       // the entering excursion started inside this tile: everything is known
@@ -1057,15 +1281,16 @@ scan_walk_kernel(const LevelArgs A) {
 //     scan_detail_kernel, which walks just those chunks position by position.
 template <bool kPair>
 __global__ void __launch_bounds__(TILE_THREADS, KS_WALKFAST_MINBLOCKS) scan_walk_fast_kernel(const LevelArgs A) {
-  __shared__ Ex s_wex[TILE_WARPS + 1];
+  __shared__ Ex s_wex[TILE_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t tile = blockIdx.x;
   const int64_t q = tile * TILE_THREADS + tid;
-  fx_t S_tile;
+  fx_t S_tile;  // state entering the transform tile of this record
   {
-    XfRec r = A.tile_xf[tile];
+    const int64_t xt = q >> A.xf_log;
+    XfRec r = A.tile_xf[xt];
     Xf tx; tx.a = r.a; tx.b = r.b; tx.kill = r.kill;
-    S_tile = xf_apply(tx, A.group_S[tile / GROUP_TILES]);
+    S_tile = xf_apply(tx, A.group_S[xt / GROUP_TILES]);
   }
   const uint32_t fl = A.st_flags[q];
   const bool all_live = kPair ? (fl & 1u) != 0 : (fl & 0xffffu) == 0xffffu;
@@ -1096,25 +1321,16 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_WALKFAST_MINBLOCKS) scan_walk
   if (lane == 0) eexcl = ex_identity();
   if (lane == 31) s_wex[warp] = einc;
   __syncthreads();
-  if (warp == 0) {
-    Ex ti = lane < TILE_WARPS ? s_wex[lane] : ex_identity();
-#pragma unroll
-    for (int o = 1; o < TILE_WARPS; o <<= 1) {
-      Ex y = shfl_ex(ti, (lane - o) & 31);
-      if (lane >= o) ti = ex_combine(y, ti);
-    }
-    Ex te = shfl_ex(ti, (lane - 1) & 31);
-    if (lane == 0) te = ex_identity();
-    if (lane < TILE_WARPS) s_wex[lane] = te;
-    if (lane == TILE_WARPS - 1) {
-      ExRec rr;
-      rr.M = ti.M; rr.beg = ti.beg; rr.pk = ti.pk; rr.reset = ti.reset; rr.open = ti.open; rr.pad[0] = rr.pad[1] = 0;
-      A.tile_ex[tile] = rr;
-    }
+  Ex wpre = ex_identity();  // the warps before this one, folded by every warp for itself (one barrier)
+  for (int w = 0; w < warp; ++w) wpre = ex_combine(wpre, s_wex[w]);
+  if (warp == TILE_WARPS - 1 && lane == 31) {
+    const Ex ti = ex_combine(wpre, einc);
+    ExRec rr;
+    rr.M = ti.M; rr.beg = ti.beg; rr.pk = ti.pk; rr.reset = ti.reset; rr.open = ti.open; rr.pad[0] = rr.pad[1] = 0;
+    A.tile_ex[tile] = rr;
   }
-  __syncthreads();
   if (!closing) return;
-  eexcl = ex_combine(s_wex[warp], eexcl);
+  eexcl = ex_combine(wpre, eexcl);
   if (eexcl.reset) {  // start known
     ScanParams prm;
     prm.min_width = A.prm->min_width;

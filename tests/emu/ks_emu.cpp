@@ -211,8 +211,8 @@ static int emu_scan_impl(const uint8_t *buf, int64_t ntot, int k, const double *
               FastChunk fc;
               fc.init();
               for (int j = 0; j < 16; ++j) fc.step(j, wfx[code[j]]);
-              general = fc.bad;
-              if (!fc.bad) { sm = fc.summary(); uc = unit_from_chunk(fc.a(), fc.b(), 0, 0xffffu, sm); }
+              general = fc.bad();
+              if (!fc.bad()) { sm = fc.summary(); uc = unit_from_chunk(fc.a(), fc.b(), 0, 0xffffu, sm); }
             }
             if (general) {
               GeneralChunk gc;
@@ -311,8 +311,8 @@ static int emu_scan_impl(const uint8_t *buf, int64_t ntot, int k, const double *
             FastChunk fc;
             fc.init();
             for (int j = 0; j < 16; ++j) fc.step(j, wfx[code[j]]);
-            general = fc.bad;
-            if (!fc.bad) { f.a = (fx_t)fc.a(); f.b = (fx_t)fc.b(); f.kill = 0; sm = fc.summary(); live2 = 0xffffu; }
+            general = fc.bad();
+            if (!fc.bad()) { f.a = (fx_t)fc.a(); f.b = (fx_t)fc.b(); f.kill = 0; sm = fc.summary(); live2 = 0xffffu; }
           }
           if (general) {
             GeneralChunk gc;
