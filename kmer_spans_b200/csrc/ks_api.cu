@@ -214,7 +214,7 @@ struct ks_ctx {
   DBuf cls, cls_dense, core;
   // rank order of the last ks_dev_scores(RANK): position of every k-mer, piece starts, bucket table (the pieces'
   // x0 / inc stay in sc_segx0 / sc_seginc); scan_ranks_impl gathers 4-byte positions instead of 8-byte scores
-  DBuf rk_pos, rk_p0, rk_blob, rk_tail;
+  DBuf rk_pos, rk_p0, rk_blob, rk_tail, rk_core;
   bool rk_valid = false;
   int rk_k = 0, rk_shift = 0;
   uint32_t rk_npieces = 0, rk_win_lo = 0, rk_win_len = 0, rk_n = 0;
@@ -383,7 +383,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->win_match, &ctx->win_cnt, &ctx->win_pre, &ctx->win_scratch, &ctx->win_codes, &ctx->win_fix,
                  &ctx->win_hist, &ctx->win_pos, &ctx->st_aux, &ctx->child_pk, &ctx->child_c, &ctx->child_count,
                  &ctx->tr_tables, &ctx->st_mn, &ctx->st_mx, &ctx->st_bm, &ctx->detail, &ctx->detail_count,
-                 &ctx->cls, &ctx->cls_dense, &ctx->core, &ctx->rk_pos, &ctx->rk_p0, &ctx->rk_blob, &ctx->rk_tail,
+                 &ctx->cls, &ctx->cls_dense, &ctx->core, &ctx->rk_pos, &ctx->rk_p0, &ctx->rk_blob, &ctx->rk_tail, &ctx->rk_core,
                  &ctx->bk_buf, &ctx->bk_cursor, &ctx->bk_table_a, &ctx->lg_slots, &ctx->lg_stats, &ctx->lg_comp_a, &ctx->lg_comp_b,
                  &ctx->lg_slot_a, &ctx->lg_slot_b, &ctx->lg_ranks, &ctx->lg_cnt_a, &ctx->lg_cnt_b, &ctx->lg_idx_a,
                  &ctx->lg_idx_b};
@@ -1808,6 +1808,7 @@ struct ScanTable {  // what scan_gather_kernel gathers from
   bool use_core = false; // ... gathered two positions at a time through ctx->core
   bool use_hash = false; // large k: 64-bit codes, scores in the slots of ctx->lg_slots
   bool use_rank = false; // rank mode: ctx->rk_pos + the linear pieces of the rank order
+  bool use_rank_core = false;  // ... gathered through the 32-byte records of ctx->rk_core (tables beyond L2)
   double rk_thr = 0;
   bool tr = false;  // transition-score scan: ctx->wfx = [trans | init], every close is re-scanned
 };
@@ -1900,6 +1901,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.kmask64 = k < 32 ? ((((uint64_t)1) << (2 * k)) - 1) : ~0ull;
     A.pk_first = s->win_lo / 16;
     A.rk_pos = ctx->rk_pos.as<uint32_t>();
+    A.rk_core = ctx->rk_core.as<uint32_t>();
     A.rk_p0 = ctx->rk_p0.as<uint32_t>();
     A.rk_x0 = ctx->sc_segx0.as<double>();
     A.rk_inc = ctx->sc_seginc.as<double>();
@@ -1982,6 +1984,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
 #define KS_GATHER(...) scan_gather_kernel<__VA_ARGS__><<<(unsigned)tiles, TILE_THREADS, 0, st>>>(A)
     if (tab.tr) KS_GATHER(0, true);
     else if (pair && tab.use_hash) KS_GATHER(4, false, true, false, true);
+    else if (pair && tab.use_rank_core) KS_GATHER(3, false, true, true, true);
     else if (pair && tab.use_rank) KS_GATHER(3, false, true, false, true);
     else if (core_pipe) {
       if (!ctx->core_attr_set) {  // 34 KB of shared memory per CTA: ask for the large carve-out once
@@ -1995,7 +1998,9 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     else if (pair) KS_GATHER(0, false, true, false, true);
     else if (fast && tab.use_hash) KS_GATHER(4, false, true);
     else if (tab.use_hash) KS_GATHER(4);
+    else if (fast && tab.use_rank_core) KS_GATHER(3, false, true, true);
     else if (fast && tab.use_rank) KS_GATHER(3, false, true);
+    else if (tab.use_rank_core) KS_GATHER(3, false, false, true);
     else if (tab.use_rank) KS_GATHER(3);
     else if (fast && tab.use_core) KS_GATHER(2, false, true, true);
     else if (fast && tab.use_cls) KS_GATHER(2, false, true);
@@ -2433,10 +2438,22 @@ static int scan_ranks_impl(ks_ctx *ctx, const ks_seqset *s, int k, double thr, i
       CK(cudaGetLastError());
     }
   }
-  ctx->prof_end(KS_PROF_WFX, pw);
   ScanTable tab;
   tab.use_rank = true;
   tab.rk_thr = thr;
+  // a position table far beyond L2 (4^13 x 4 B = 268 MB): regroup it by (k-1)-mer so that the two positions a pair of
+  // bases needs sit in one sector.  Rebuilt per scan: 0.3 ms at k = 13 against tens of ms of gathers.
+  int core_min_k = 13;
+  if (const char *e = getenv("KS_RANK_CORE_MIN_K")) core_min_k = atoi(e);
+  if (k >= core_min_k && k >= 2) {
+    const size_t ncore = (size_t)1 << (2 * k - 2);
+    CK(ctx->rk_core.ensure(ncore * 32));
+    rank_core_apply_kernel<<<grid_for(ncore, 256), 256, 0, st>>>(ctx->rk_pos.as<uint32_t>(), ncore, ctx->rk_core.as<uint4>());
+    LAUNCHED(1);
+    CK(cudaGetLastError());
+    tab.use_rank_core = true;
+  }
+  ctx->prof_end(KS_PROF_WFX, pw);
   return scan_core(ctx, s, k, tab, mw, nullptr, host_out, n_spans, sh);
 }
 

@@ -328,6 +328,7 @@ struct LevelArgs {
   // scan_gather_kernel (xf_log = TILE_LOG, xf_ntiles = ntiles) or the warp tiles of scan_gather_core_kernel (5)
   int xf_log;
   int64_t xf_ntiles, xf_ngroups;
+  const uint32_t *rk_core;  // rank mode, large tables: 32-byte records of the (k-1)-mers (rank_core_apply_kernel)
   ExRec *tile_ex;       // open-excursion aggregate per tile (scan_walk_kernel)
   ExRec *group_ex;      // the same per group of 32 tiles (group_ex_kernel)
   ExPending *pending;   // one slot per tile
@@ -552,16 +553,19 @@ __global__ void __launch_bounds__(TILE_THREADS,
                                           : ((kLut == 1 || kLut == 2) ? KS_GATHER_MINBLOCKS : KS_GATHER_MINBLOCKS_TABLE))
 scan_gather_kernel(const LevelArgs A) {
   static_assert(!kPair || (kSumm && !kTr), "units of two chunks exist for the summary walk only");
+  static_assert(!kCore || kLut == 2 || kLut == 3, "core records exist for the class table and the rank positions");
+  constexpr bool kClsCore = kCore && kLut == 2;  // class bytes + their scores in shared memory
+  constexpr bool kRankCore = kCore && kLut == 3; // rank positions of a.c / c.b side by side in one 32-byte sector
   __shared__ Xf s_wxf[TILE_WARPS];
-  __shared__ int64_t s_lut[kCore ? CORE_ESCAPE : 1];  // scores of the classes a core record can name
+  __shared__ int64_t s_lut[kClsCore ? CORE_ESCAPE : 1];  // scores of the classes a core record can name
   __shared__ typename std::conditional<kLut == 3, RankSmem, int>::type s_rk_store;  // rank mode only
   const RankSmem *s_rk = kLut == 3 ? reinterpret_cast<const RankSmem *>(&s_rk_store) : nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // small tables that go to shared memory: the loads are issued here, the stores (and the barrier) wait until the
   // gathers are in flight, so their latency hides behind the gathers instead of opening every CTA
-  constexpr int LUT_PER = kCore ? (int)(CORE_ESCAPE + TILE_THREADS - 1) / TILE_THREADS : 1;
+  constexpr int LUT_PER = kClsCore ? (int)(CORE_ESCAPE + TILE_THREADS - 1) / TILE_THREADS : 1;
   int64_t pre_lut[LUT_PER];
-  if (kCore) {
+  if (kClsCore) {
 #pragma unroll
     for (int i = 0; i < LUT_PER; ++i) {
       const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
@@ -579,7 +583,7 @@ scan_gather_kernel(const LevelArgs A) {
   constexpr int NSUB = kPair ? 2 : 1;
   // core mode on units: the gathers of BOTH chunks are issued before the first chunk is worked on, so a thread
   // waits for memory once per 32 positions (the other modes hold too many registers per chunk for that)
-  constexpr bool kAhead = kPair && kLut == 2 && kCore;
+  constexpr bool kAhead = kPair && kClsCore;
   const uint64_t keep = l2_policy_evict_last();
   // results of the record
   uint32_t live = 0, tkill = 0;
@@ -596,7 +600,7 @@ scan_gather_kernel(const LevelArgs A) {
   uint32_t scoreds[NSUB];
   uint32_t w_hi32s[NSUB];     // 64-bit codes: [p0 - 32, p0 + 16)
   uint64_t w_lo64s[NSUB];
-  uint2 recs[NSUB][kCore ? CHUNK / 2 : 1];            // core mode: record of the (k-1)-mer under positions 2i, 2i+1
+  uint2 recs[NSUB][kClsCore ? CHUNK / 2 : 1];            // core mode: record of the (k-1)-mer under positions 2i, 2i+1
   uint32_t cs[NSUB][(kLut == 1 || kLut == 2 || kLut == 3) ? CHUNK : 1];  // class / count / rank position
   int64_t svs[NSUB][(kLut == 0 || kLut == 4) ? CHUNK : 1];                // score (table mode, hash mode)
 
@@ -666,7 +670,19 @@ scan_gather_kernel(const LevelArgs A) {
     }
     Xs[h] = X;
     scoreds[h] = scored;
-    if (kLut == 2 && kCore) {
+    if (kRankCore) {
+      // the 4 x 4 B positions of a.c and the 4 x 4 B of c.b share one 32-byte record: the two loads of a pair of
+      // positions fetch ONE sector where the plain table costs two -- what counts when the table is far larger
+      // than L2 (k >= 13) and every sector comes from DRAM
+      const uint32_t cmask = A.kmask >> 2;
+      const int ashift = 2 * A.k - 2;
+#pragma unroll
+      for (int i = 0; i < CHUNK / 2; ++i) {
+        const uint32_t *rec = A.rk_core + ((size_t)(code[2 * i] & cmask) << 3);
+        cs[h][2 * i] = (scored & (1u << (2 * i))) ? __ldg(rec + (code[2 * i] >> ashift)) : 0u;
+        cs[h][2 * i + 1] = (scored & (2u << (2 * i))) ? __ldg(rec + 4 + (code[2 * i + 1] & 3u)) : 0u;
+      }
+    } else if (kClsCore) {
       // core mode: positions 2i and 2i+1 score the k-mers a.c and c.b around the same (k-1)-mer c (code[2i+1] >> 2
       // == code[2i] & cmask), and the record of c holds both classes: 8 gathers of 8 bytes per 16 positions
       const uint32_t cmask = A.kmask >> 2;
@@ -708,7 +724,7 @@ scan_gather_kernel(const LevelArgs A) {
     auto code_at = [&](int j) -> uint32_t { return (uint32_t)(X >> (32 - 2 * j)) & A.kmask; };
     uint32_t c[(kLut == 1 || kLut == 2 || kLut == 3) ? CHUNK : 1];
     bool big = false;  // core mode: a class beyond the shared-memory table was met
-    if (kLut == 2 && kCore) {
+    if (kClsCore) {
       const int ashift = 2 * A.k + 30;  // a of the pair i sits 2k - 2 bits above the low end of its code
       uint32_t esc = 0;
 #pragma unroll
@@ -730,7 +746,7 @@ scan_gather_kernel(const LevelArgs A) {
     }
     // value of a SCORED position (WFX_KILL = the table says "force the state to 0")
     auto value = [&](int j) -> int64_t {
-      if (kLut == 2 && kCore) return c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&A.lut[c[j]]);
+      if (kClsCore) return c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&A.lut[c[j]]);
       if (kLut == 2) return __ldg(&A.lut[c[j]]);
       if (kLut == 3) return rank_value(A, s_rk, c[j], rk_qs);
       if (kLut == 1) {
@@ -758,7 +774,7 @@ scan_gather_kernel(const LevelArgs A) {
     if (kSumm && !general) {  // every position scored: prefix-sum formulation (ks_chunk.cuh)
       FastChunk fc;
       fc.init();
-      if (kLut == 2 && kCore && !big) {  // every class in the shared-memory table: no test per position
+      if (kClsCore && !big) {  // every class in the shared-memory table: no test per position
 #pragma unroll
         for (int j = 0; j < CHUNK; ++j) fc.step(j, s_lut[c[j]]);
       } else {
@@ -807,7 +823,7 @@ scan_gather_kernel(const LevelArgs A) {
   for (int h = 0; h < NSUB; ++h)
     if (h == 0 || kAhead) issue(h);
   // the small tables: their loads were issued at the top, the gathers are in flight now
-  if (kCore) {
+  if (kClsCore) {
 #pragma unroll
     for (int i = 0; i < LUT_PER; ++i) {
       const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
@@ -1821,6 +1837,18 @@ __global__ void __launch_bounds__(256) core_apply_kernel(const uint16_t *__restr
 #pragma unroll
     for (int b = 0; b < 4; ++b) hi |= (b4[b] < CORE_ESCAPE ? b4[b] : CORE_ESCAPE) << (8 * b);
     core[c] = make_uint2(lo, hi);
+  }
+}
+
+// rank positions -> records of the (k-1)-mers (scan_gather_kernel<3, ..., kCore>): record of c = positions of a.c
+// (a = 0..3) then of c.b (b = 0..3), 32 bytes
+__global__ void __launch_bounds__(256) rank_core_apply_kernel(const uint32_t *__restrict__ rk_pos, size_t ncore,
+                                                              uint4 *__restrict__ core) {
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncore; c += (size_t)gridDim.x * blockDim.x) {
+    uint4 lo;
+    lo.x = rk_pos[c]; lo.y = rk_pos[ncore + c]; lo.z = rk_pos[2 * ncore + c]; lo.w = rk_pos[3 * ncore + c];
+    core[2 * c] = lo;
+    core[2 * c + 1] = *reinterpret_cast<const uint4 *>(rk_pos + 4 * c);
   }
 }
 

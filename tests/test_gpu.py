@@ -577,12 +577,18 @@ def test_fast_and_general_paths_agree_with_oracle(ctx, oracle, mode, monkeypatch
     seqs = [planted(rng, 400_000), planted(rng, 30_000), rand_seq(rng, 5000, p_n=0.2)]
     k = 6
     thr = 0.6 if mode == 0 else 0.0
-    for mw, ms in ((14, 2.0), (15, 2.0), (16, 0.0), (100, 5.0), (0, 8.0)):
+    for mw, ms in ((14, 2.0), (15, 2.0), (16, 0.0), (31, 1.0), (100, 5.0), (0, 8.0)):
         want = oracle.mode_regions(seqs, k, mode, mw, ms, thr=thr)
         for env in ({}, {"KS_NO_FAST_WALK": "1"}, {"KS_NO_CLASS_TABLE": "1"},
                     {"KS_NO_FAST_WALK": "1", "KS_NO_CLASS_TABLE": "1"}, {"KS_NO_CORE_TABLE": "1"},
-                    {"KS_NO_FAST_WALK": "1", "KS_NO_CORE_TABLE": "1"}):
-            for name in ("KS_NO_FAST_WALK", "KS_NO_CLASS_TABLE", "KS_NO_CORE_TABLE"):
+                    {"KS_NO_FAST_WALK": "1", "KS_NO_CORE_TABLE": "1"},
+                    # units of two chunks (min_width >= 31) off; the persistent core-record kernel off; rank
+                    # positions through the 32-byte records of the (k-1)-mers (default only for k >= 13)
+                    {"KS_NO_PAIR": "1"}, {"KS_NO_CORE_PIPE": "1"}, {"KS_RANK_CORE_MIN_K": "2"},
+                    {"KS_RANK_CORE_MIN_K": "2", "KS_NO_PAIR": "1"},
+                    {"KS_RANK_CORE_MIN_K": "2", "KS_NO_FAST_WALK": "1"}):
+            for name in ("KS_NO_FAST_WALK", "KS_NO_CLASS_TABLE", "KS_NO_CORE_TABLE", "KS_NO_PAIR", "KS_NO_CORE_PIPE",
+                         "KS_RANK_CORE_MIN_K"):
                 monkeypatch.delenv(name, raising=False)
             for name, val in env.items():
                 monkeypatch.setenv(name, val)
