@@ -486,13 +486,14 @@ struct CountRun {
     case 9: { constexpr int KK = 9; stmt; } break;   \
     case 10: { constexpr int KK = 10; stmt; } break; \
     case 11: { constexpr int KK = 11; stmt; } break; \
-    default: { constexpr int KK = 12; stmt; } break; \
+    case 12: { constexpr int KK = 12; stmt; } break; \
+    default: { constexpr int KK = 13; stmt; } break; \
   }
 extern "C++" {
 template <int K>
 static cudaError_t bucket_smem_attrs_k() {
   cudaError_t e = cudaFuncSetAttribute(bucket_scatter_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)BK_SCATTER_SMEM);
+                                       (int)bk_scatter_smem(K));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(bucket_count_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
 }
@@ -503,7 +504,8 @@ static cudaError_t bucket_smem_attrs() {
   if ((e = bucket_smem_attrs_k<9>()) != cudaSuccess) return e;
   if ((e = bucket_smem_attrs_k<10>()) != cudaSuccess) return e;
   if ((e = bucket_smem_attrs_k<11>()) != cudaSuccess) return e;
-  return bucket_smem_attrs_k<12>();
+  if ((e = bucket_smem_attrs_k<12>()) != cudaSuccess) return e;
+  return bucket_smem_attrs_k<13>();
 }
 
 // zeroes the table, the word count and (bucket path) the bucket fills; est_chunks sizes the bucket regions
@@ -516,11 +518,11 @@ static int count_begin(ks_ctx *ctx, int k, int32_t *d_counts, int64_t est_chunks
   count_parts(k, &run->nparts, &run->part_shift);
   int path = COUNT_DIRECT;
   if (k <= 7 && est_chunks >= (1 << 14)) path = COUNT_SMEM;
-  else if (k >= 8 && k <= 12 && est_chunks >= (1 << 18)) path = COUNT_BUCKET;
+  else if (k >= 8 && k <= 13 && est_chunks >= (1 << 18)) path = COUNT_BUCKET;
   if (const char *e = getenv("KS_COUNT_PATH")) {
     if (!strcmp(e, "direct")) path = COUNT_DIRECT;
     else if (!strcmp(e, "smem") && k <= 7) path = COUNT_SMEM;
-    else if (!strcmp(e, "bucket") && k >= 8 && k <= 12) path = COUNT_BUCKET;
+    else if (!strcmp(e, "bucket") && k >= 8 && k <= 13) path = COUNT_BUCKET;
   }
   run->path = path;
   if (!ctx->smem_attr_set) {
@@ -533,17 +535,18 @@ static int count_begin(ks_ctx *ctx, int k, int32_t *d_counts, int64_t est_chunks
   CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
   if (path == COUNT_BUCKET) {
     run->sub_bits = 2 * k - 8;  // one sub-key per pair of k-mers: rest of the core + a + b
-    uint64_t per = (uint64_t)(est_chunks > 0 ? est_chunks : 1) * 8 / BK_BUCKETS;  // pairs per bucket
+    const size_t nbuckets = (size_t)1 << bk_log(k);
+    uint64_t per = (uint64_t)(est_chunks > 0 ? est_chunks : 1) * 8 / nbuckets;  // pairs per bucket
     uint64_t gcap = per + per / 2 + 8192;  // spectrum skew; what does not fit overflows to the direct reduction
     if (const char *e = getenv("KS_BUCKET_CAP")) gcap = (uint64_t)atoll(e);  // tests: force the overflow path
     gcap = (gcap + 7) & ~7ull;
     if (gcap < 8) gcap = 8;
     if (gcap > 0xfffffff0ull) return ctx->fail(KS_ERR_ARG, "input too large for the bucketed count");
     run->gcap = (uint32_t)gcap;
-    CK(ctx->bk_buf.ensure((size_t)gcap * BK_BUCKETS * 2));
-    CK(ctx->bk_cursor.ensure(BK_BUCKETS * 4));
+    CK(ctx->bk_buf.ensure((size_t)gcap * nbuckets * 2));
+    CK(ctx->bk_cursor.ensure(BK_MAX_BUCKETS * 4));
     CK(ctx->bk_table_a.ensure(n * 4));
-    CK(cudaMemsetAsync(ctx->bk_cursor.p, 0, BK_BUCKETS * 4, st));
+    CK(cudaMemsetAsync(ctx->bk_cursor.p, 0, BK_MAX_BUCKETS * 4, st));
   }
   return KS_OK;
 }
@@ -560,9 +563,10 @@ static int count_chunks(ks_ctx *ctx, const ks_seqset *s, const CountRun &run, in
     pack_count_smem_kernel<<<grid, 256, smem, st>>>(s->d_buf, first, nchunks, run.k, run.kmask, s->d_pk, s->d_brk,
                                                    run.d_counts, nw);
   } else if (run.path == COUNT_BUCKET) {
-    const int64_t ntiles = (nchunks + BK_TILE_CHUNKS - 1) / BK_TILE_CHUNKS;
-    const unsigned grid = (unsigned)std::min<int64_t>(148 * 4, ntiles);
-    KS_BUCKET_K(run.k, (bucket_scatter_kernel<KK><<<grid, BK_THREADS, BK_SCATTER_SMEM, st>>>(
+    const int64_t tile_chunks = bk_tile_chunks(run.k);
+    const int64_t ntiles = (nchunks + tile_chunks - 1) / tile_chunks;
+    const unsigned grid = (unsigned)std::min<int64_t>(run.k >= 13 ? 148 : 148 * 4, ntiles);
+    KS_BUCKET_K(run.k, (bucket_scatter_kernel<KK><<<grid, bk_threads(KK), bk_scatter_smem(KK), st>>>(
         s->d_buf, first, nchunks, s->d_pk, s->d_brk, run.d_counts, nw, ctx->bk_buf.as<uint16_t>(),
         ctx->bk_cursor.as<uint32_t>(), run.gcap)));
   } else {
@@ -580,7 +584,7 @@ static int count_end(ks_ctx *ctx, const ks_seqset *s, const CountRun &run, int64
   cudaStream_t st = ctx->stream;
   if (run.path == COUNT_BUCKET) {
     const size_t nk = (size_t)1 << (2 * run.k);
-    KS_BUCKET_K(run.k, (bucket_count_kernel<KK><<<BK_BUCKETS, BK_COUNT_THREADS, 2 * (nk / BK_BUCKETS) * 4, st>>>(
+    KS_BUCKET_K(run.k, (bucket_count_kernel<KK><<<1 << bk_log(KK), BK_COUNT_THREADS, 2 * (nk >> bk_log(KK)) * 4, st>>>(
         ctx->bk_buf.as<uint16_t>(), ctx->bk_cursor.as<uint32_t>(), run.gcap, run.d_counts,
         ctx->bk_table_a.as<uint32_t>())));
     KS_BUCKET_K(run.k, (bucket_fold_kernel<KK><<<grid_for(nk / 4, 256, 148u * 8u), 256, 0, st>>>(

@@ -23,21 +23,23 @@
 
 namespace ks {
 
-constexpr int BK_LOG = 10;
-constexpr int BK_BUCKETS = 1 << BK_LOG;
+// buckets: 1024 for k <= 12; 4096 at k = 13, where 1024 would leave 18-bit sub-keys (one CTA of 1024 threads per SM
+// then holds the 4096 staging rows)
+constexpr int bk_log(int k) { return k >= 13 ? 12 : 10; }
+constexpr int bk_threads(int k) { return k >= 13 ? 1024 : 256; }
+constexpr int BK_MAX_BUCKETS = 1 << 12;
 constexpr int BK_CAP = 24;      // staged sub-keys per bucket and tile; rows of 48 bytes (8-byte aligned)
 constexpr int BK_ROUNDS = 6;    // chunks per thread and tile, loaded in two batches of three
 constexpr int BK_BATCH = 3;
-constexpr int BK_THREADS = 256;
-constexpr int BK_TILE_CHUNKS = BK_THREADS * BK_ROUNDS;  // 1536 chunks = 24 576 positions = 12 288 pairs, 12 per bucket
+constexpr int bk_tile_chunks(int k) { return bk_threads(k) * BK_ROUNDS; }  // 12 pairs per bucket and tile
 constexpr uint32_t BK_PAD = 0xffffu;  // filler of the last granule of a row; never a sub-key: an all-ones sub-key would
                                       // need k = 12 with rest, a, b all ones, which is filed as two direct reductions
-constexpr size_t BK_SCATTER_SMEM = BK_BUCKETS * 4 + (size_t)BK_BUCKETS * BK_CAP * 2;  // counters + rows
+constexpr size_t bk_scatter_smem(int k) { return ((size_t)4 + (size_t)BK_CAP * 2) << bk_log(k); }  // counters + rows
 
 __device__ __forceinline__ unsigned long long block_sum_to(unsigned long long local, unsigned long long *dst) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-  __shared__ unsigned long long sm_total[8];
+  __shared__ unsigned long long sm_total[32];
   if ((threadIdx.x & 31) == 0) sm_total[threadIdx.x >> 5] = local;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -120,12 +122,13 @@ __global__ void __launch_bounds__(256) pack_count_smem_kernel(const uint8_t *__r
 // so that phase 2 indexes its c.b table with sub & LOW and its a.c table with sub >> 2.
 template <int K>
 struct PairGeom {
-  static constexpr int REST = 2 * K - 12;
+  static constexpr int LOG = bk_log(K), NB = 1 << LOG, THREADS = bk_threads(K), TILE_CHUNKS = bk_tile_chunks(K);
+  static constexpr int REST = 2 * K - 2 - LOG;
   static constexpr uint32_t LOW = (1u << (REST + 2)) - 1u;
   static constexpr uint32_t KMASK = (uint32_t)(((uint64_t)1 << (2 * K)) - 1u);
-  static constexpr uint32_t ENTRIES = 1u << (REST + 2);  // per bucket and table = 4^K / 1024
-  __device__ static __forceinline__ uint32_t bucket4(uint32_t y) { return (y >> REST) & (1023u << 2); }  // bucket * 4
-  __device__ static __forceinline__ uint32_t sub(uint32_t y) { return (y & LOW) | ((y >> 10) & (3u << (REST + 2))); }
+  static constexpr uint32_t ENTRIES = 1u << (REST + 2);  // per bucket and table = 4^K / buckets
+  __device__ static __forceinline__ uint32_t bucket4(uint32_t y) { return (y >> REST) & ((uint32_t)(NB - 1) << 2); }  // bucket * 4
+  __device__ static __forceinline__ uint32_t sub(uint32_t y) { return (y & LOW) | ((y >> LOG) & (3u << (REST + 2))); }
   __device__ static __forceinline__ uint32_t code_ac(uint32_t bucket, uint32_t sub) {
     return ((sub >> (REST + 2)) << (2 * K - 2)) | (bucket << REST) | ((sub >> 2) & ((1u << REST) - 1u));
   }
@@ -163,7 +166,7 @@ __device__ __forceinline__ void pack16_lazy(const uint4 &raw, uint32_t &pk, uint
 }
 
 template <int K>
-__global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uint8_t *__restrict__ buf, int64_t first,
+__global__ void __launch_bounds__(bk_threads(K), K >= 13 ? 1 : 4) bucket_scatter_kernel(const uint8_t *__restrict__ buf, int64_t first,
                                                                       int64_t nchunks, uint32_t *__restrict__ pk_out,
                                                                       uint16_t *__restrict__ brk_out,
                                                                       int32_t *__restrict__ counts,
@@ -174,21 +177,21 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
   extern __shared__ __align__(16) unsigned char ks_dyn_smem[];
   uint32_t *s_cnt = reinterpret_cast<uint32_t *>(ks_dyn_smem);
   unsigned char *s_cnt_b = ks_dyn_smem;
-  uint16_t *s_stage = reinterpret_cast<uint16_t *>(ks_dyn_smem + BK_BUCKETS * 4);
-  unsigned char *s_stage_b = ks_dyn_smem + BK_BUCKETS * 4;
+  uint16_t *s_stage = reinterpret_cast<uint16_t *>(ks_dyn_smem + G::NB * 4);
+  unsigned char *s_stage_b = ks_dyn_smem + G::NB * 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t keep = l2_policy_evict_last();
   const int64_t end = first + nchunks;
   unsigned long long local = 0;
-  const int64_t ntiles = (nchunks + BK_TILE_CHUNKS - 1) / BK_TILE_CHUNKS;
-  constexpr int BPT = BK_BUCKETS / BK_THREADS;  // buckets per thread (flush)
-  for (int i = tid; i < BK_BUCKETS; i += BK_THREADS) s_cnt[i] = 0;
+  const int64_t ntiles = (nchunks + G::TILE_CHUNKS - 1) / G::TILE_CHUNKS;
+  constexpr int BPT = G::NB / G::THREADS;  // buckets per thread (flush)
+  for (int i = tid; i < G::NB; i += G::THREADS) s_cnt[i] = 0;
   __syncthreads();
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // a warp owns 32 * BK_ROUNDS consecutive chunks of the tile, 32 per round: the 16 positions before a chunk are
     // the neighbouring lane's chunk (one shuffle), those before lane 0 the last lane's of the round before, and only
     // the very first of the warp is packed a second time
-    const int64_t wbase = first + tile * BK_TILE_CHUNKS + (int64_t)warp * (32 * BK_ROUNDS);
+    const int64_t wbase = first + tile * G::TILE_CHUNKS + (int64_t)warp * (32 * BK_ROUNDS);
     uint32_t carry_pk = 0, carry_fl = 0;
     if (wbase < end) pack16_lazy(ld_stream_u4(reinterpret_cast<const uint4 *>(buf + 16 * wbase)), carry_pk, carry_fl);
 #pragma unroll 1
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
           const uint32_t y = __funnelshift_r(pkc, pkp, 28 - 4 * i);
           const uint32_t sub = G::sub(y);
           const bool staged = slot[i] < (uint32_t)BK_CAP;
-          const bool filler_like = (K == 12) && sub == BK_PAD;
+          const bool filler_like = (2 * K - 2 - G::LOG + 4 == 16) && sub == BK_PAD;
           if (staged)
             *reinterpret_cast<uint16_t *>(s_stage_b + G::bucket4(y) * (BK_CAP / 2) + slot[i] * 2) =
                 (uint16_t)(filler_like ? BK_PAD : sub);
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
     uint32_t fn[BPT], fg[BPT];
 #pragma unroll
     for (int q = 0; q < BPT; ++q) {  // the reservations first: BPT independent atomics in flight
-      const uint32_t b = (uint32_t)tid + (uint32_t)BK_THREADS * q;
+      const uint32_t b = (uint32_t)tid + (uint32_t)G::THREADS * q;
       uint32_t n = s_cnt[b];
       if (n > (uint32_t)BK_CAP) n = BK_CAP;
       fn[q] = n;
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bucket_scatter_kernel(const uin
     }
 #pragma unroll
     for (int q = 0; q < BPT; ++q) {
-      const uint32_t b = (uint32_t)tid + (uint32_t)BK_THREADS * q;
+      const uint32_t b = (uint32_t)tid + (uint32_t)G::THREADS * q;
       const uint32_t n = fn[q], g = fg[q];
       uint16_t *row = s_stage + b * BK_CAP;
       if (last_tile)

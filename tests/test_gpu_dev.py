@@ -182,11 +182,11 @@ def test_rank_position_gather_equals_rank_table_scan(ctx, oracle, monkeypatch): 
 @pytest.mark.parametrize("path", ["direct", "smem", "bucket"])
 def test_count_paths_match_oracle(ctx, oracle, path, monkeypatch):  # noqa: F811
     """the three counting kernels (direct global reductions, shared-memory table for k <= 7, 1024 buckets through
-    shared memory for 8 <= k <= 12) on ragged inputs, IUPAC bytes, poly-A / tandem arrays (staging rows overflow
+    shared memory for 8 <= k <= 12, 4096 buckets at k = 13) on ragged inputs, IUPAC bytes, poly-A / tandem arrays (staging rows overflow
     into the direct reduction) and with bucket regions forced to overflow"""
     monkeypatch.setenv("KS_COUNT_PATH", path)
     rng = np.random.default_rng(7500)
-    ks = {"direct": (2, 8, 11), "smem": (1, 3, 7), "bucket": (5, 8, 10, 12)}[path]
+    ks = {"direct": (2, 8, 11), "smem": (1, 3, 7), "bucket": (5, 8, 10, 12, 13)}[path]
     for k in ks:
         for trial in range(3):
             seqs = [rand_seq(rng, int(rng.integers(0, 40000)), p_n=float(rng.choice([0, 0.02, 0.3])),
@@ -200,20 +200,20 @@ def test_count_paths_match_oracle(ctx, oracle, path, monkeypatch):  # noqa: F811
     if path == "bucket":
         monkeypatch.setenv("KS_BUCKET_CAP", "64")  # almost everything overflows the bucket regions
         seqs = [planted(rng, 300_000), b"AC" * 50000]
-        for k in (8, 12):
+        for k in (8, 12, 13):
             n1, c1 = oracle.kmer_counts(seqs, k)
             g = ctx.kmer_counts(seqs, k, with_f=False)
             assert g["n"][1] == n1 and (g["counts"] == c1).all(), ("overflow", k)
 
 
 def test_count_paths_default_selection_large(ctx, oracle):  # noqa: F811
-    """inputs large enough for the default selection to take the bucketed path (>= 2^18 chunks) at k = 8, 10, 12,
+    """inputs large enough for the default selection to take the bucketed path (>= 2^18 chunks) at k = 8, 10, 12, 13,
     through the resident-set call, the sharded range call and the upload-with-count path"""
     import torch
     seq = synth.genome(6_000_000, 77, n_blocks=(3, 4000)).tobytes()
     seqs = [seq, b"ACGTTGCA" * 1000]
     ss = ctx.upload(seqs)
-    for k in (8, 10, 12):
+    for k in (8, 10, 12, 13):
         n1, c1 = oracle.kmer_counts(seqs, k)
         counts, _ = _tables(k)
         assert ctx.dev_count(ss, k, counts.data_ptr()) == n1
