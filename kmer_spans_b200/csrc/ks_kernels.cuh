@@ -581,9 +581,6 @@ scan_gather_kernel(const LevelArgs A) {
   const int64_t tile = blockIdx.x;
   const int64_t q = tile * TILE_THREADS + tid;  // record: one chunk, or a unit of two (kPair)
   constexpr int NSUB = kPair ? 2 : 1;
-  // core mode on units: the gathers of BOTH chunks are issued before the first chunk is worked on, so a thread
-  // waits for memory once per 32 positions (the other modes hold too many registers per chunk for that)
-  constexpr bool kAhead = kPair && kClsCore;
   const uint64_t keep = l2_policy_evict_last();
   // results of the record
   uint32_t live = 0, tkill = 0;
@@ -596,13 +593,13 @@ scan_gather_kernel(const LevelArgs A) {
   uint32_t tr_first = 0;
   int nreal = 0;
   // ---- per chunk: what the issue step leaves for the work step ----
-  uint64_t Xs[NSUB];          // packed window [p0 - 16, p0 + 16)
-  uint32_t scoreds[NSUB];
-  uint32_t w_hi32s[NSUB];     // 64-bit codes: [p0 - 32, p0 + 16)
-  uint64_t w_lo64s[NSUB];
-  uint2 recs[NSUB][kClsCore ? CHUNK / 2 : 1];            // core mode: record of the (k-1)-mer under positions 2i, 2i+1
-  uint32_t cs[NSUB][(kLut == 1 || kLut == 2 || kLut == 3) ? CHUNK : 1];  // class / count / rank position
-  int64_t svs[NSUB][(kLut == 0 || kLut == 4) ? CHUNK : 1];                // score (table mode, hash mode)
+  uint64_t Xs = 0;            // packed window [p0 - 16, p0 + 16)
+  uint32_t scoreds = 0;
+  uint32_t w_hi32s = 0;       // 64-bit codes: [p0 - 32, p0 + 16)
+  uint64_t w_lo64s = 0;
+  uint2 recs[kClsCore ? CHUNK / 2 : 1];            // core mode: record of the (k-1)-mer under positions 2i, 2i+1
+  uint32_t cs[(kLut == 1 || kLut == 2 || kLut == 3) ? CHUNK : 1];  // class / count / rank position
+  int64_t svs[(kLut == 0 || kLut == 4) ? CHUNK : 1];                // score (table mode, hash mode)
 
   // ---- issue: chunk -> position mapping, packed window, codes, gather (up to 16 independent loads) ----
   auto issue = [&](const int h) {
@@ -634,7 +631,7 @@ scan_gather_kernel(const LevelArgs A) {
     uint32_t code[CHUNK];
     if (kLut == 4) {
       uint64_t brk48;
-      load_window_wide(A.pk, A.brk, A.pk_first, cp0, w_hi32s[h], w_lo64s[h], brk48);
+      load_window_wide(A.pk, A.brk, A.pk_first, cp0, w_hi32s, w_lo64s, brk48);
       const uint32_t inside = n_in >= 16 ? 0xffffu : ((1u << n_in) - 1u);
       scored = (uint32_t)(run_ending64(~brk48, A.k + 1) >> 32) & inside;  // position and the k before it: no break
     } else {
@@ -668,8 +665,8 @@ scan_gather_kernel(const LevelArgs A) {
     } else {
       decode_scan(X, brk32, A.k, A.kmask, n_in, code, scored);
     }
-    Xs[h] = X;
-    scoreds[h] = scored;
+    Xs = X;
+    scoreds = scored;
     if (kRankCore) {
       // the 4 x 4 B positions of a.c and the 4 x 4 B of c.b share one 32-byte record: the two loads of a pair of
       // positions fetch ONE sector where the plain table costs two -- what counts when the table is far larger
@@ -679,8 +676,8 @@ scan_gather_kernel(const LevelArgs A) {
 #pragma unroll
       for (int i = 0; i < CHUNK / 2; ++i) {
         const uint32_t *rec = A.rk_core + ((size_t)(code[2 * i] & cmask) << 3);
-        cs[h][2 * i] = (scored & (1u << (2 * i))) ? __ldg(rec + (code[2 * i] >> ashift)) : 0u;
-        cs[h][2 * i + 1] = (scored & (2u << (2 * i))) ? __ldg(rec + 4 + (code[2 * i + 1] & 3u)) : 0u;
+        cs[2 * i] = (scored & (1u << (2 * i))) ? __ldg(rec + (code[2 * i] >> ashift)) : 0u;
+        cs[2 * i + 1] = (scored & (2u << (2 * i))) ? __ldg(rec + 4 + (code[2 * i + 1] & 3u)) : 0u;
       }
     } else if (kClsCore) {
       // core mode: positions 2i and 2i+1 score the k-mers a.c and c.b around the same (k-1)-mer c (code[2i+1] >> 2
@@ -688,38 +685,38 @@ scan_gather_kernel(const LevelArgs A) {
       const uint32_t cmask = A.kmask >> 2;
 #pragma unroll
       for (int i = 0; i < CHUNK / 2; ++i) {
-        recs[h][i] = make_uint2(0u, 0u);
-        if ((scored >> (2 * i)) & 3u) recs[h][i] = ldg_u32x2_keep(&A.core[code[2 * i] & cmask], keep);
+        recs[i] = make_uint2(0u, 0u);
+        if ((scored >> (2 * i)) & 3u) recs[i] = ldg_u32x2_keep(&A.core[code[2 * i] & cmask], keep);
       }
     } else if (kLut == 2) {
       // class mode: 2-byte gather (the 4^k x 2 B table stays L2 resident where the 4 B count table does not)
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j) cs[h][j] = (scored & (1u << j)) ? ldg_u16_keep(&A.cls[code[j]], keep) : 0u;
+      for (int j = 0; j < CHUNK; ++j) cs[j] = (scored & (1u << j)) ? ldg_u16_keep(&A.cls[code[j]], keep) : 0u;
     } else if (kLut == 3) {
       // rank mode: 4-byte position in the rank order (4^k x 4 B, L2 resident at k <= 12), not the 8-byte score
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j) cs[h][j] = (scored & (1u << j)) ? ldg_u32_keep(&A.rk_pos[code[j]], keep) : 0u;
+      for (int j = 0; j < CHUNK; ++j) cs[j] = (scored & (1u << j)) ? ldg_u32_keep(&A.rk_pos[code[j]], keep) : 0u;
     } else if (kLut == 4) {
       // large k: the k-mer ending at position j - 1 sits 32 - 2j bits above the low end of the 96-bit window
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j)
-        svs[h][j] = (scored & (1u << j))
-                        ? hash_lookup(A.hslots, A.hmask, wide_code(w_hi32s[h], w_lo64s[h], 32 - 2 * j, A.kmask64))
+        svs[j] = (scored & (1u << j))
+                        ? hash_lookup(A.hslots, A.hmask, wide_code(w_hi32s, w_lo64s, 32 - 2 * j, A.kmask64))
                         : WFX_KILL;
     } else if (kLut == 1) {
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j) cs[h][j] = (scored & (1u << j)) ? ldg_u32_keep(&A.counts[code[j]], keep) : 0u;
+      for (int j = 0; j < CHUNK; ++j) cs[j] = (scored & (1u << j)) ? ldg_u32_keep(&A.counts[code[j]], keep) : 0u;
     } else {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j)
-        svs[h][j] = (scored & (1u << j)) ? ldg_s64_keep(&A.wfx[code[j]], keep) : WFX_KILL;
+        svs[j] = (scored & (1u << j)) ? ldg_s64_keep(&A.wfx[code[j]], keep) : WFX_KILL;
     }
   };
 
   // ---- work: classes -> scores, chunk transform and summary, merged into the record ----
   auto work = [&](const int h) {
-    const uint64_t X = Xs[h];
-    const uint32_t scored = scoreds[h];
+    const uint64_t X = Xs;
+    const uint32_t scored = scoreds;
     // codes are needed again only off the beaten path (escape classes, in-scan counts)
     auto code_at = [&](int j) -> uint32_t { return (uint32_t)(X >> (32 - 2 * j)) & A.kmask; };
     uint32_t c[(kLut == 1 || kLut == 2 || kLut == 3) ? CHUNK : 1];
@@ -730,8 +727,8 @@ scan_gather_kernel(const LevelArgs A) {
 #pragma unroll
       for (int i = 0; i < CHUNK / 2; ++i) {
         // unscored positions pick a byte of an all-zero record or a class nobody looks at
-        c[2 * i] = __byte_perm(recs[h][i].x, 0u, 0x4440u | ((uint32_t)(X >> (ashift - 4 * i)) & 3u));
-        c[2 * i + 1] = __byte_perm(recs[h][i].y, 0u, 0x4440u | ((uint32_t)(X >> (30 - 4 * i)) & 3u));
+        c[2 * i] = __byte_perm(recs[i].x, 0u, 0x4440u | ((uint32_t)(X >> (ashift - 4 * i)) & 3u));
+        c[2 * i + 1] = __byte_perm(recs[i].y, 0u, 0x4440u | ((uint32_t)(X >> (30 - 4 * i)) & 3u));
         esc |= (c[2 * i] + 1u) | (c[2 * i + 1] + 1u);  // bit 8 set iff one of them is CORE_ESCAPE (255)
       }
       if (esc & 0x100u) {  // rare: very abundant k-mers (classes beyond the first 255 distinct counts)
@@ -742,7 +739,7 @@ scan_gather_kernel(const LevelArgs A) {
       }
     } else if (kLut == 1 || kLut == 2 || kLut == 3) {
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j) c[j] = cs[h][j];
+      for (int j = 0; j < CHUNK; ++j) c[j] = cs[j];
     }
     // value of a SCORED position (WFX_KILL = the table says "force the state to 0")
     auto value = [&](int j) -> int64_t {
@@ -758,7 +755,7 @@ scan_gather_kernel(const LevelArgs A) {
         }
         return __ldg(&A.sp_val[lo]);
       }
-      return svs[h][j];
+      return svs[j];
     };
     auto stash = [&](int j, int64_t v) {
       if (kSumm) return;  // the fast walk works on the chunk summary; scan_detail_kernel gathers again
@@ -766,6 +763,17 @@ scan_gather_kernel(const LevelArgs A) {
       else if (kLut == 1) __stcs(&A.st_c[(int64_t)j * A.Q + q], c[j]);
       else __stcs(&A.st_s[(int64_t)j * A.Q + q], v == WFX_KILL ? (int64_t)0 : v);
     };
+    // the 16 values once (the rank-mode lookup is long: one copy of it per position, not one per walk variant)
+    int64_t v[CHUNK];
+    if (kClsCore && !big && scored == 0xffffu) {  // every class in the shared-memory table: no test per position
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) v[j] = s_lut[c[j]];
+    } else {
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) v[j] = (scored & (1u << j)) ? value(j) : WFX_KILL;
+    }
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) stash(j, v[j]);
     uint32_t clive = 0, ckill = 0;
     int64_t cta = 0, ctb = -(1ll << 62);
     ChunkSummary csumm;
@@ -774,17 +782,8 @@ scan_gather_kernel(const LevelArgs A) {
     if (kSumm && !general) {  // every position scored: prefix-sum formulation (ks_chunk.cuh)
       FastChunk fc;
       fc.init();
-      if (kClsCore && !big) {  // every class in the shared-memory table: no test per position
 #pragma unroll
-        for (int j = 0; j < CHUNK; ++j) fc.step(j, s_lut[c[j]]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j) {
-          const int64_t v = value(j);
-          stash(j, v);
-          fc.step(j, v);
-        }
-      }
+      for (int j = 0; j < CHUNK; ++j) fc.step(j, v[j]);
       general = fc.bad();
       if (!fc.bad()) {
         clive = 0xffffu;
@@ -797,11 +796,7 @@ scan_gather_kernel(const LevelArgs A) {
       GeneralChunk gc;
       gc.init();
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j) {
-        const int64_t v = (scored & (1u << j)) ? value(j) : WFX_KILL;
-        stash(j, v);
-        gc.template step<kSumm>(j, v);
-      }
+      for (int j = 0; j < CHUNK; ++j) gc.template step<kSumm>(j, v[j]);
       clive = gc.live; cta = gc.ta; ctb = gc.tb; ckill = gc.kill;
       if (kSumm) csumm = gc.summary();
     }
@@ -819,25 +814,25 @@ scan_gather_kernel(const LevelArgs A) {
     }
   };
 
-#pragma unroll
-  for (int h = 0; h < NSUB; ++h)
-    if (h == 0 || kAhead) issue(h);
-  // the small tables: their loads were issued at the top, the gathers are in flight now
-  if (kClsCore) {
-#pragma unroll
-    for (int i = 0; i < LUT_PER; ++i) {
-      const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
-      if (e < CORE_ESCAPE) s_lut[e] = pre_lut[i];
-    }
-    __syncthreads();
-  }
-  if (kLut == 3) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-  }
-#pragma unroll
+  // rank mode keeps ONE copy of the chunk code for both chunks of a unit (its kernel otherwise outgrows the
+  // instruction cache: a fifth of the issue slots went to instruction fetch)
+#pragma unroll(kLut == 3 ? 1 : NSUB)
   for (int h = 0; h < NSUB; ++h) {
-    if (h > 0 && !kAhead) issue(h);
+    issue(h);
+    if (h == 0) {  // the small tables: their loads were issued at the top, the gathers are in flight now
+      if (kClsCore) {
+#pragma unroll
+        for (int i = 0; i < LUT_PER; ++i) {
+          const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
+          if (e < CORE_ESCAPE) s_lut[e] = pre_lut[i];
+        }
+        __syncthreads();
+      }
+      if (kLut == 3) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+      }
+    }
     work(h);
   }
   if (kPair) { ta = unit.ta; tb = unit.tb; tkill = unit.kill; }
@@ -890,7 +885,7 @@ scan_gather_kernel(const LevelArgs A) {
   }
   __stcs(&A.st_flags[q], flags);
   if (A.nseg != 0) __stcs(&A.st_p0[q], (long long)p0);
-  if (kTr) A.st_aux[q] = tr_first | (scoreds[0] << 16);
+  if (kTr) A.st_aux[q] = tr_first | (scoreds << 16);
 }
 
 // ------------------------------------------------------------------------------------------
