@@ -1122,7 +1122,7 @@ __global__ void __launch_bounds__(256) group_scan_kernel(const LevelArgs A) {
   }
 }
 
-constexpr int TSCAN_THREADS = 256;
+constexpr int TSCAN_THREADS = 1024;
 __global__ void __launch_bounds__(TSCAN_THREADS) group_top_kernel(const LevelArgs A) {
   __shared__ Xf sh[TSCAN_THREADS];
   const int tid = threadIdx.x;
