@@ -170,7 +170,8 @@ struct ks_ctx {
   DBuf sc_keys_a, sc_keys_b, sc_vals_a, sc_vals_b, sc_small, sc_gcount, sc_gstart, sc_segfirst, sc_segj0,
       sc_segx0, sc_seginc, sc_lut, sc_dense;
   // count -> score function of the last ks_dev_scores(LOG2 | SIGN): one value per distinct count
-  DBuf lut_fx, lut_spc, lut_spv;
+  DBuf lut_fx, lut_spc, lut_spv, core_lut, core_cc;
+  std::vector<uint32_t> core_groups;  // group (distinct count) behind every class byte of the core records
   bool lut_valid = false;
   int lut_k = 0;
   std::vector<uint32_t> lut_gcount;
@@ -209,7 +210,9 @@ struct ks_ctx {
                           HPIN_DENSE = 768u << 10, HPIN_LUT = 1280u << 10, HPIN_PRM = 1792u << 10,
                           HPIN_FX = 2048u << 10,  // the scan's per-class fixed-point table: its own region, because the
                                                   // score stage may still be copying out of HPIN_LUT when the scan starts
-                          HPIN_BYTES = 2560u << 10;
+                          HPIN_COREFX = 2560u << 10,  // scores of the classes the core records name (255 x 8 B)
+                          HPIN_CC = 2564u << 10,      // group -> core class bytes (<= 64 KiB)
+                          HPIN_BYTES = 2628u << 10;
   // class table of the last ks_dev_scores(LOG2 | SIGN): index of every k-mer's count among the distinct counts
   DBuf cls, cls_dense, core;
   // rank order of the last ks_dev_scores(RANK): position of every k-mer, piece starts, bucket table (the pieces'
@@ -379,7 +382,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
                  &ctx->out_score, &ctx->sc_keys_a, &ctx->sc_keys_b, &ctx->sc_vals_a, &ctx->sc_vals_b,
                  &ctx->sc_small, &ctx->sc_gcount, &ctx->sc_gstart, &ctx->sc_segfirst, &ctx->sc_segj0,
                  &ctx->sc_segx0, &ctx->sc_seginc, &ctx->sc_lut, &ctx->sc_dense, &ctx->tmp_counts, &ctx->tmp_scores,
-                 &ctx->tmp_inscan, &ctx->nwords, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->launch_rec, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv,
+                 &ctx->tmp_inscan, &ctx->nwords, &ctx->pending, &ctx->st_c, &ctx->st_s, &ctx->st_ea, &ctx->st_eb, &ctx->st_flags, &ctx->st_p0, &ctx->tile_xf, &ctx->tile_ex, &ctx->group_xf, &ctx->group_S, &ctx->group_ex, &ctx->launch_rec, &ctx->pending_list, &ctx->pending_count, &ctx->foc_hist, &ctx->foc_big, &ctx->lut_fx, &ctx->lut_spc, &ctx->lut_spv, &ctx->core_lut, &ctx->core_cc,
                  &ctx->win_match, &ctx->win_cnt, &ctx->win_pre, &ctx->win_scratch, &ctx->win_codes, &ctx->win_fix,
                  &ctx->win_hist, &ctx->win_pos, &ctx->st_aux, &ctx->child_pk, &ctx->child_c, &ctx->child_count,
                  &ctx->tr_tables, &ctx->st_mn, &ctx->st_mx, &ctx->st_bm, &ctx->detail, &ctx->detail_count,
@@ -1391,9 +1394,26 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
       // core records: one 8-byte gather serves two consecutive positions of the scan
       ctx->core_valid = false;
       if (getenv("KS_NO_CORE_TABLE") == nullptr) {
+        // a record names a class in one byte: the 255 groups that cover the most POSITIONS (count x number of
+        // k-mers with that count) get a byte of their own, whatever their counts; the rest escape to cls[]
+        std::vector<uint32_t> order(ng);
+        for (size_t g = 0; g < ng; ++g) order[g] = (uint32_t)g;
+        const size_t ncc = std::min<size_t>(ng, CORE_ESCAPE);
+        if (getenv("KS_CORE_BY_VALUE") == nullptr)
+          std::partial_sort(order.begin(), order.begin() + ncc, order.end(), [&](uint32_t a, uint32_t b) {
+            const unsigned __int128 wa = (unsigned __int128)gmult[a] * gcount[a], wb = (unsigned __int128)gmult[b] * gcount[b];
+            return wa != wb ? wa > wb : a < b;
+          });
+        ctx->core_groups.assign(order.begin(), order.begin() + ncc);
+        uint8_t *cc = reinterpret_cast<uint8_t *>(ctx->hpin + ks_ctx::HPIN_CC);
+        memset(cc, (int)CORE_ESCAPE, ng);
+        for (size_t i = 0; i < ncc; ++i) cc[ctx->core_groups[i]] = (uint8_t)i;
+        CK(ctx->core_cc.ensure(ng + 16));
+        CK(cudaMemcpyAsync(ctx->core_cc.p, cc, ng, cudaMemcpyHostToDevice, st));
         const size_t ncore = n / 4;
         CK(ctx->core.ensure(ncore * sizeof(uint2)));
-        core_apply_kernel<<<grid_for(ncore, 256), 256, 0, st>>>(ctx->cls.as<uint16_t>(), ncore, ctx->core.as<uint2>());
+        core_apply_kernel<<<grid_for(ncore, 256), 256, 0, st>>>(ctx->cls.as<uint16_t>(), ncore, ctx->core.as<uint2>(),
+                                                               ctx->core_cc.as<uint8_t>());
         LAUNCHED(1);
         CK(cudaGetLastError());
         ctx->core_valid = true;
@@ -1917,6 +1937,7 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     A.rk_shift = ctx->rk_shift;
     A.rk_thr = tab.rk_thr;
     A.lut = ctx->lut_fx.as<int64_t>();
+    A.core_lut = ctx->core_lut.as<int64_t>();
     A.lut_size = tab.lut_size;
     A.sp_count = ctx->lut_spc.as<uint32_t>();
     A.sp_val = ctx->lut_spv.as<int64_t>();
@@ -2010,7 +2031,6 @@ static int scan_core(ks_ctx *ctx, const ks_seqset *s, int k, const ScanTable &ta
     else if (fast && tab.use_cls) KS_GATHER(2, false, true);
     else if (fast && tab.use_lut) KS_GATHER(1, false, true);
     else if (fast) KS_GATHER(0, false, true);
-    else if (tab.use_core) KS_GATHER(2, false, false, true);
     else if (tab.use_cls) KS_GATHER(2);
     else if (tab.use_lut) KS_GATHER(1);
     else KS_GATHER(0);
@@ -2332,6 +2352,13 @@ static int scan_counts_impl(ks_ctx *ctx, const ks_seqset *s, int k, const int32_
     CK(ctx->lut_fx.ensure(ng * 8 + 8));
     CK(cudaMemcpyAsync(ctx->prm.p, hp_pin, sizeof hp, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->lut_fx.p, fx, ng * 8, cudaMemcpyHostToDevice, st));
+    if (ctx->core_valid) {  // the scores of the classes the core records name, in their byte order
+      int64_t *cfx = reinterpret_cast<int64_t *>(ctx->hpin + ks_ctx::HPIN_COREFX);
+      memset(cfx, 0, (size_t)CORE_ESCAPE * 8);
+      for (size_t i = 0; i < ctx->core_groups.size(); ++i) cfx[i] = fx[ctx->core_groups[i]];
+      CK(ctx->core_lut.ensure((size_t)CORE_ESCAPE * 8 + 8));
+      CK(cudaMemcpyAsync(ctx->core_lut.p, cfx, (size_t)CORE_ESCAPE * 8, cudaMemcpyHostToDevice, st));
+    }
     ctx->prof_end(KS_PROF_WFX, pw);
     ScanTable tab;
     tab.use_lut = true;

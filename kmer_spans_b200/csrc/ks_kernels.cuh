@@ -328,6 +328,7 @@ struct LevelArgs {
   // scan_gather_kernel (xf_log = TILE_LOG, xf_ntiles = ntiles) or the warp tiles of scan_gather_core_kernel (5)
   int xf_log;
   int64_t xf_ntiles, xf_ngroups;
+  const int64_t *core_lut;  // class mode through core records: score of every class byte (CORE_ESCAPE entries)
   const uint32_t *rk_core;  // rank mode, large tables: 32-byte records of the (k-1)-mers (rank_core_apply_kernel)
   ExRec *tile_ex;       // open-excursion aggregate per tile (scan_walk_kernel)
   ExRec *group_ex;      // the same per group of 32 tiles (group_ex_kernel)
@@ -554,6 +555,7 @@ __global__ void __launch_bounds__(TILE_THREADS,
 scan_gather_kernel(const LevelArgs A) {
   static_assert(!kPair || (kSumm && !kTr), "units of two chunks exist for the summary walk only");
   static_assert(!kCore || kLut == 2 || kLut == 3, "core records exist for the class table and the rank positions");
+  static_assert(!(kCore && kLut == 2) || kSumm, "class bytes of core records are not the classes the stash keeps");
   constexpr bool kClsCore = kCore && kLut == 2;  // class bytes + their scores in shared memory
   constexpr bool kRankCore = kCore && kLut == 3; // rank positions of a.c / c.b side by side in one 32-byte sector
   __shared__ Xf s_wxf[TILE_WARPS];
@@ -569,7 +571,7 @@ scan_gather_kernel(const LevelArgs A) {
 #pragma unroll
     for (int i = 0; i < LUT_PER; ++i) {
       const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
-      pre_lut[i] = (e < CORE_ESCAPE && e < A.lut_size) ? __ldg(&A.lut[e]) : 0;
+      pre_lut[i] = e < CORE_ESCAPE ? __ldg(&A.core_lut[e]) : 0;
     }
   }
   if (kLut == 3) {  // asynchronous copy of the rank-order tables: no registers held, done by the time they are needed
@@ -735,7 +737,7 @@ scan_gather_kernel(const LevelArgs A) {
         big = true;
 #pragma unroll
         for (int j = 0; j < CHUNK; ++j)
-          if (c[j] == CORE_ESCAPE && (scored & (1u << j))) c[j] = ldg_u16_keep(&A.cls[code_at(j)], keep);
+          if (c[j] == CORE_ESCAPE && (scored & (1u << j))) c[j] = 256u + ldg_u16_keep(&A.cls[code_at(j)], keep);
       }
     } else if (kLut == 1 || kLut == 2 || kLut == 3) {
 #pragma unroll
@@ -743,7 +745,7 @@ scan_gather_kernel(const LevelArgs A) {
     }
     // value of a SCORED position (WFX_KILL = the table says "force the state to 0")
     auto value = [&](int j) -> int64_t {
-      if (kClsCore) return c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&A.lut[c[j]]);
+      if (kClsCore) return c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&A.lut[c[j] - 256u]);  // byte, or 256 + group
       if (kLut == 2) return __ldg(&A.lut[c[j]]);
       if (kLut == 3) return rank_value(A, s_rk, c[j], rk_qs);
       if (kLut == 1) {
@@ -927,11 +929,12 @@ __device__ __noinline__ void core_chunk_general(const uint16_t *__restrict__ cls
   }
 #pragma unroll
   for (int j = 0; j < CHUNK; ++j)
-    if (c[j] == CORE_ESCAPE && (scored & (1u << j))) c[j] = ldg_u16_keep(&cls[(uint32_t)(X >> (32 - 2 * j)) & kmask], keep);
+    if (c[j] == CORE_ESCAPE && (scored & (1u << j)))  // class byte -> 256 + group
+      c[j] = 256u + ldg_u16_keep(&cls[(uint32_t)(X >> (32 - 2 * j)) & kmask], keep);
   int64_t v[CHUNK];
 #pragma unroll
   for (int j = 0; j < CHUNK; ++j)
-    v[j] = !(scored & (1u << j)) ? WFX_KILL : (c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&lut[c[j]]));
+    v[j] = !(scored & (1u << j)) ? WFX_KILL : (c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&lut[c[j] - 256u]));
   if (scored == 0xffffu) {
     FastChunk fc;
     fc.init();
@@ -960,7 +963,7 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_CORE_MINBLOCKS) scan_gather_c
 #pragma unroll
   for (int i = 0; i < LUT_PER; ++i) {
     const uint32_t e = (uint32_t)(tid + i * TILE_THREADS);
-    pre_lut[i] = (e < CORE_ESCAPE && e < A.lut_size) ? __ldg(&A.lut[e]) : 0;
+    pre_lut[i] = e < CORE_ESCAPE ? __ldg(&A.core_lut[e]) : 0;
   }
   const uint32_t cmask = A.kmask >> 2;
   const int64_t w0 = A.dense_start >> 4;  // packed word of the first chunk of the launch (16-aligned start)
@@ -1816,21 +1819,19 @@ __global__ void __launch_bounds__(256) class_apply_kernel(const uint32_t *__rest
   }
 }
 
-// class table -> core records (scan_gather_kernel, core mode): record of the (k-1)-mer c = classes of a.c (a = 0..3,
-// low word) and of c.b (b = 0..3, high word), one byte each, clamped to CORE_ESCAPE
+// class table -> core records (scan_gather_kernel, core mode): record of the (k-1)-mer c = class bytes of a.c
+// (a = 0..3, low word) and of c.b (b = 0..3, high word); cc[group] = the byte of the group (the host gives one to
+// the 255 groups that cover the most positions) or CORE_ESCAPE
 __global__ void __launch_bounds__(256) core_apply_kernel(const uint16_t *__restrict__ cls, size_t ncore,
-                                                         uint2 *__restrict__ core) {
+                                                         uint2 *__restrict__ core, const uint8_t *__restrict__ cc) {
   for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncore; c += (size_t)gridDim.x * blockDim.x) {
     uint32_t lo = 0, hi = 0;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const uint32_t v = cls[(size_t)a * ncore + c];
-      lo |= (v < CORE_ESCAPE ? v : CORE_ESCAPE) << (8 * a);
-    }
+    for (int a = 0; a < 4; ++a) lo |= (uint32_t)__ldg(&cc[cls[(size_t)a * ncore + c]]) << (8 * a);
     const uint2 q = *reinterpret_cast<const uint2 *>(cls + 4 * c);
     const uint32_t b4[4] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16};
 #pragma unroll
-    for (int b = 0; b < 4; ++b) hi |= (b4[b] < CORE_ESCAPE ? b4[b] : CORE_ESCAPE) << (8 * b);
+    for (int b = 0; b < 4; ++b) hi |= (uint32_t)__ldg(&cc[b4[b]]) << (8 * b);
     core[c] = make_uint2(lo, hi);
   }
 }
