@@ -561,6 +561,7 @@ scan_gather_kernel(const LevelArgs A) {
   __shared__ Xf s_wxf[TILE_WARPS];
   __shared__ int64_t s_lut[kClsCore ? CORE_ESCAPE : 1];  // scores of the classes a core record can name
   __shared__ typename std::conditional<kLut == 3, RankSmem, int>::type s_rk_store;  // rank mode only
+  __shared__ uint32_t s_pos[kLut == 3 ? CHUNK : 1][kLut == 3 ? TILE_THREADS : 1];    // rank mode: a chunk's positions
   const RankSmem *s_rk = kLut == 3 ? reinterpret_cast<const RankSmem *>(&s_rk_store) : nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // small tables that go to shared memory: the loads are issued here, the stores (and the barrier) wait until the
@@ -765,42 +766,65 @@ scan_gather_kernel(const LevelArgs A) {
       else if (kLut == 1) __stcs(&A.st_c[(int64_t)j * A.Q + q], c[j]);
       else __stcs(&A.st_s[(int64_t)j * A.Q + q], v == WFX_KILL ? (int64_t)0 : v);
     };
-    // the 16 values once (the rank-mode lookup is long: one copy of it per position, not one per walk variant)
-    int64_t v[CHUNK];
-    if (kClsCore && !big && scored == 0xffffu) {  // every class in the shared-memory table: no test per position
-#pragma unroll
-      for (int j = 0; j < CHUNK; ++j) v[j] = s_lut[c[j]];
-    } else {
-#pragma unroll
-      for (int j = 0; j < CHUNK; ++j) v[j] = (scored & (1u << j)) ? value(j) : WFX_KILL;
-    }
-#pragma unroll
-    for (int j = 0; j < CHUNK; ++j) stash(j, v[j]);
     uint32_t clive = 0, ckill = 0;
     int64_t cta = 0, ctb = -(1ll << 62);
     ChunkSummary csumm;
     csumm.mn = 0; csumm.mx = 0; csumm.bm = 0; csumm.bits = 0;
     bool general = !kSumm || scored != 0xffffu;
-    if (kSumm && !general) {  // every position scored: prefix-sum formulation (ks_chunk.cuh)
-      FastChunk fc;
-      fc.init();
+    if (kLut == 3) {
+      // rank mode: the lookup of one position is ~40 instructions; unrolled 16 times per walk variant the kernel
+      // was straight-line code that spent a fifth of its issue slots waiting for instructions.  The positions go
+      // through the thread's own shared-memory slots and ONE copy of the lookup runs in a loop.
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j) fc.step(j, v[j]);
-      general = fc.bad();
-      if (!fc.bad()) {
-        clive = 0xffffu;
-        cta = fc.a();
-        ctb = fc.b();
-        csumm = fc.summary();
+      for (int j = 0; j < CHUNK; ++j) s_pos[j][tid] = c[j];
+      if (kSumm && !general) {
+        FastChunk fc;
+        fc.init();
+#pragma unroll 1
+        for (int j = 0; j < CHUNK; ++j) fc.step(j, rank_value(A, s_rk, s_pos[j][tid], rk_qs));
+        general = fc.bad();
+        if (!general) { clive = 0xffffu; cta = fc.a(); ctb = fc.b(); csumm = fc.summary(); }
       }
-    }
-    if (general) {
-      GeneralChunk gc;
-      gc.init();
+      if (general) {
+        GeneralChunk gc;
+        gc.init();
+#pragma unroll 1
+        for (int j = 0; j < CHUNK; ++j) {
+          const int64_t vj = (scored & (1u << j)) ? rank_value(A, s_rk, s_pos[j][tid], rk_qs) : WFX_KILL;
+          if (!kSumm) __stcs(&A.st_s[(int64_t)j * A.Q + q], vj == WFX_KILL ? (int64_t)0 : vj);
+          gc.template step<kSumm>(j, vj);
+        }
+        clive = gc.live; cta = gc.ta; ctb = gc.tb; ckill = gc.kill;
+        if (kSumm) csumm = gc.summary();
+      }
+    } else {
+      // the 16 values once, then the walk variant that applies
+      int64_t v[CHUNK];
+      if (kClsCore && !big && scored == 0xffffu) {  // every class in the shared-memory table: no test per position
 #pragma unroll
-      for (int j = 0; j < CHUNK; ++j) gc.template step<kSumm>(j, v[j]);
-      clive = gc.live; cta = gc.ta; ctb = gc.tb; ckill = gc.kill;
-      if (kSumm) csumm = gc.summary();
+        for (int j = 0; j < CHUNK; ++j) v[j] = s_lut[c[j]];
+      } else {
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) v[j] = (scored & (1u << j)) ? value(j) : WFX_KILL;
+      }
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) stash(j, v[j]);
+      if (kSumm && !general) {  // every position scored: prefix-sum formulation (ks_chunk.cuh)
+        FastChunk fc;
+        fc.init();
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) fc.step(j, v[j]);
+        general = fc.bad();
+        if (!general) { clive = 0xffffu; cta = fc.a(); ctb = fc.b(); csumm = fc.summary(); }
+      }
+      if (general) {
+        GeneralChunk gc;
+        gc.init();
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) gc.template step<kSumm>(j, v[j]);
+        clive = gc.live; cta = gc.ta; ctb = gc.tb; ckill = gc.kill;
+        if (kSumm) csumm = gc.summary();
+      }
     }
     if (kLut != 4 && !kTr && A.inscan) {
 #pragma unroll
