@@ -990,6 +990,7 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_CORE_MINBLOCKS) scan_gather_c
     pre_lut[i] = e < CORE_ESCAPE ? __ldg(&A.core_lut[e]) : 0;
   }
   const uint32_t cmask = A.kmask >> 2;
+  const uint64_t keep = l2_policy_evict_last();
   const int64_t w0 = A.dense_start >> 4;  // packed word of the first chunk of the launch (16-aligned start)
   const int64_t G = (int64_t)gridDim.x * TILE_WARPS;  // warps of the grid
 
@@ -1067,15 +1068,23 @@ __global__ void __launch_bounds__(TILE_THREADS, KS_CORE_MINBLOCKS) scan_gather_c
           c[2 * i + 1] = __byte_perm(rec.y, 0u, 0x4440u | ((uint32_t)(X >> (30 - 4 * i)) & 3u));
           esc |= (c[2 * i] + 1u) | (c[2 * i + 1] + 1u);  // bit 8 set iff one of them is CORE_ESCAPE (255)
         }
-        general = (esc & 0x100u) != 0u;  // rare: a class beyond the first 255 distinct counts
-        if (!general) {
-          FastChunk fc;
-          fc.init();
+        // a class without a byte of its own (repeats; frequent once the table is the sum over many GPUs and holds
+        // thousands of distinct counts): the warp as a whole takes the variant that resolves them, so that its
+        // lanes do not run both
+        FastChunk fc;
+        fc.init();
+        if (!__any_sync(__activemask(), (esc & 0x100u) != 0u)) {
 #pragma unroll
           for (int j = 0; j < CHUNK; ++j) fc.step(j, s_lut[c[j]]);
-          general = fc.bad();
-          o.ta = fc.a(); o.tb = fc.b(); o.kill = 0; o.live = 0xffffu; o.sm = fc.summary();
+        } else {
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j)  // class byte -> 256 + group, all escapes of the chunk in flight together
+            if (c[j] == CORE_ESCAPE) c[j] = 256u + ldg_u16_keep(&A.cls[(uint32_t)(X >> (32 - 2 * j)) & A.kmask], keep);
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) fc.step(j, c[j] < CORE_ESCAPE ? s_lut[c[j]] : __ldg(&A.lut[c[j] - 256u]));
         }
+        general = fc.bad();
+        o.ta = fc.a(); o.tb = fc.b(); o.kill = 0; o.live = 0xffffu; o.sm = fc.summary();
       }
       if (general) core_chunk_general(A.cls, A.lut, A.kmask, A.k, s_lut, recs, X, scored, &o);
       const UnitSummary uc = unit_from_chunk(o.ta, o.tb, o.kill, o.live, o.sm);

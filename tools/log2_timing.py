@@ -7,7 +7,8 @@ from kmer_spans_b200 import api, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 250_000_000
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-seq = synth.config2(n, 2)[0]
+te = int(os.environ.get('KS_SYNTH_TANDEM_EVERY', '0'))
+seq = synth.genome(n, 2, tandem_every=te, n_blocks=(5, 50_000)) if te else synth.config2(n, 2)[0]
 ctx = api.Context(0)
 ss = ctx.upload([seq])
 counts = torch.zeros(4 ** k, dtype=torch.int32, device="cuda")
