@@ -178,7 +178,9 @@ struct ks_ctx {
   std::vector<double> lut_gval;
   // staging / misc
   cudaStream_t copy_stream = nullptr;     // H2D of the sequence / D2H of tables, overlapped with kernels
-  cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
+  cudaEvent_t ev_copy = nullptr, ev_compute = nullptr, ev_table = nullptr;
+  bool defer_table = false;    // ks_dev_pipeline: the score TABLE (an output the scan does not read) is written on the
+  bool table_pending = false;  // copy stream, next to the scan; joined before the call returns
   ks_seqset *host_set = nullptr;          // device buffers re-used by the host-buffer entry points
   void *pinned = nullptr;
   size_t pinned_cap = 0;
@@ -401,6 +403,7 @@ void ks_ctx_destroy(ks_ctx *ctx) {
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->ev_compute) cudaEventDestroy(ctx->ev_compute);
+  if (ctx->ev_table) cudaEventDestroy(ctx->ev_table);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1370,6 +1373,7 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
     // class table for the scan: 2 bytes per k-mer instead of the 4-byte count (stays L2 resident at k = 12)
     ctx->cls_counts = nullptr;
     ctx->core_valid = false;
+    bool gcount_on_device = false;
     if (ng && ng <= 65535 && getenv("KS_NO_CLASS_TABLE") == nullptr) {
       uint32_t ndense = std::min<uint32_t>(gcount[ng - 1] + 1, DENSE);
       // staged in pinned memory: every earlier copy out of it completed before the synchronisation above
@@ -1383,6 +1387,7 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
       CK(ctx->sc_gcount.ensure((ng + 1) * 4));
       CK(cudaMemcpyAsync(ctx->cls_dense.p, dense, (size_t)ndense * 2, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(ctx->sc_gcount.p, gc_pin, ng * 4, cudaMemcpyHostToDevice, st));
+      gcount_on_device = true;
       class_apply_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_counts), n,
                                                           ctx->cls_dense.as<uint16_t>(), ndense,
                                                           ctx->sc_gcount.as<uint32_t>(), (uint32_t)ng,
@@ -1441,15 +1446,30 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
       CK(ctx->sc_gcount.ensure((ng + 1) * 4));
       CK(ctx->sc_lut.ensure(ng * 8 + 8));
       CK(ctx->sc_dense.ensure(dense_n * 8));
-      CK(cudaMemcpyAsync(ctx->sc_gcount.p, gc_src, ng * 4, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(ctx->sc_lut.p, lut_src, ng * 8, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(ctx->sc_dense.p, dense, dense_n * 8, cudaMemcpyHostToDevice, st));
-      lut_apply_kernel<<<blocks_exact(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_counts), n,
+      // inside ks_dev_pipeline the table is written next to the scan, which reads counts and classes, not the table
+      const bool side = ctx->defer_table && staged && gcount_on_device;
+      cudaStream_t ts = st;
+      if (side) {
+        int rc2 = ensure_copy_stream(ctx);
+        if (rc2) return rc2;
+        ts = ctx->copy_stream;
+        CK(cudaEventRecord(ctx->ev_compute, st));  // counts final, sc_gcount uploaded
+        CK(cudaStreamWaitEvent(ts, ctx->ev_compute, 0));
+      }
+      if (!side) CK(cudaMemcpyAsync(ctx->sc_gcount.p, gc_src, ng * 4, cudaMemcpyHostToDevice, ts));
+      CK(cudaMemcpyAsync(ctx->sc_lut.p, lut_src, ng * 8, cudaMemcpyHostToDevice, ts));
+      CK(cudaMemcpyAsync(ctx->sc_dense.p, dense, dense_n * 8, cudaMemcpyHostToDevice, ts));
+      lut_apply_kernel<<<blocks_exact(n, 256), 256, 0, ts>>>(reinterpret_cast<const uint32_t *>(d_counts), n,
                                                              ctx->sc_dense.as<double>(), ndense,
                                                              ctx->sc_gcount.as<uint32_t>(), (uint32_t)ng,
                                                              ctx->sc_lut.as<double>(), d_scores);
       LAUNCHED(1);
       CK(cudaGetLastError());
+      if (side) {
+        if (!ctx->ev_table) CK(cudaEventCreateWithFlags(&ctx->ev_table, cudaEventDisableTiming));
+        CK(cudaEventRecord(ctx->ev_table, ts));
+        ctx->table_pending = true;
+      }
       if (!staged) CK(cudaStreamSynchronize(st));
     }
     return KS_OK;
@@ -2800,14 +2820,27 @@ int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double par
   // the word count is read back together with the first table the score stage needs on the host
   int rc = dev_count_impl(ctx, s, k, d_counts, nullptr, false);
   if (rc) return rc;
+  ctx->defer_table = getenv("KS_NO_SIDE_TABLE") == nullptr;
   rc = dev_scores_impl(ctx, k, d_counts, 0.0, true, mode, param, d_scores, &nw);
-  if (rc) return rc;
-  if (n_words) *n_words = nw;
-  if (mode == KS_MODE_LOG2 || mode == KS_MODE_SIGN)
-    return ks_dev_scan_counts(ctx, s, k, d_counts, thr, min_width, min_score, host_out, n_spans);
-  if (mode == KS_MODE_RANK && ctx->rk_valid)  // the score stage just left the rank order on this context
-    return ks_dev_scan_ranks(ctx, s, k, thr, min_width, min_score, host_out, n_spans);
-  return ks_dev_scan(ctx, s, k, d_scores, thr, min_width, min_score, nullptr, host_out, n_spans);
+  ctx->defer_table = false;
+  if (!rc) {
+    if (n_words) *n_words = nw;
+    if (mode == KS_MODE_LOG2 || mode == KS_MODE_SIGN)
+      rc = ks_dev_scan_counts(ctx, s, k, d_counts, thr, min_width, min_score, host_out, n_spans);
+    else if (mode == KS_MODE_RANK && ctx->rk_valid)  // the score stage just left the rank order on this context
+      rc = ks_dev_scan_ranks(ctx, s, k, thr, min_width, min_score, host_out, n_spans);
+    else
+      rc = ks_dev_scan(ctx, s, k, d_scores, thr, min_width, min_score, nullptr, host_out, n_spans);
+  }
+  if (ctx->table_pending) {  // the score table written next to the scan: part of this call, and of its stream order
+    ctx->table_pending = false;
+    cudaSetDevice(ctx->device);
+    cudaError_t e1 = cudaStreamWaitEvent(ctx->stream, ctx->ev_table, 0);
+    cudaError_t e2 = cudaEventSynchronize(ctx->ev_table);
+    if (!rc && (e1 != cudaSuccess || e2 != cudaSuccess))
+      rc = ctx->fail(KS_ERR_CUDA, "score table: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  }
+  return rc;
   KS_CATCH(ctx)
 }
 
