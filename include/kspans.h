@@ -60,6 +60,11 @@ void ks_ctx_destroy(ks_ctx *ctx);
 const char *ks_last_error(const ks_ctx *ctx); /* ctx may be NULL: error of the last failed ks_ctx_create */
 void *ks_ctx_stream(ks_ctx *ctx);             /* cudaStream_t all kernels of this ctx are launched on */
 int ks_ctx_sync(ks_ctx *ctx);
+/* on: ks_dev_scores (log2 / +-1 modes) writes the 4^k score TABLE -- an output the scan does not read -- on the
+ * context's copy stream, next to the scan that follows; the table is complete when the next ks_dev_scan_counts*
+ * call or ks_ctx_sync returns.  Off (default): complete in stream order.  ks_dev_pipeline always does this and
+ * joins before it returns. */
+void ks_ctx_side_table(ks_ctx *ctx, int on);
 /* kernels launched through this ctx since creation (or since the last reset) */
 uint64_t ks_ctx_launches(const ks_ctx *ctx);
 void ks_ctx_reset_launches(ks_ctx *ctx);

@@ -47,6 +47,7 @@ SIGNATURES = {
     "ks_ctx_timer_start": (_i, [_vp]),
     "ks_ctx_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
     "ks_ctx_set_profile": (None, [_vp, _i]),
+    "ks_ctx_side_table": (None, [_vp, _i]),
     "ks_ctx_profile_get": (_i, [_vp, _i, _pd, _pu64]),
     "ks_ctx_profile_reset": (None, [_vp]),
     "ks_kmer_counts": (_i, [_vp] + _SEQS + [_i, _vp, _pd]),

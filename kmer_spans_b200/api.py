@@ -169,6 +169,10 @@ class Context:
         self._ck(self.lib.ks_ctx_timer_stop(self.h, C.byref(ms)))
         return ms.value
 
+    def side_table(self, on=True):
+        """the score table of the log2 / +-1 stage is written next to the following scan (complete after it)"""
+        self.lib.ks_ctx_side_table(self.h, 1 if on else 0)
+
     def set_profile(self, on=True):
         self.lib.ks_ctx_set_profile(self.h, 1 if on else 0)
 

@@ -179,6 +179,7 @@ struct ks_ctx {
   // staging / misc
   cudaStream_t copy_stream = nullptr;     // H2D of the sequence / D2H of tables, overlapped with kernels
   cudaEvent_t ev_copy = nullptr, ev_compute = nullptr, ev_table = nullptr;
+  bool side_table_opt = false; // ks_ctx_side_table: the same for the stage calls (joined by the next scan / sync)
   bool defer_table = false;    // ks_dev_pipeline: the score TABLE (an output the scan does not read) is written on the
   bool table_pending = false;  // copy stream, next to the scan; joined before the call returns
   ks_seqset *host_set = nullptr;          // device buffers re-used by the host-buffer entry points
@@ -372,11 +373,14 @@ int ks_ctx_create(ks_ctx **out, int device) {
   KS_CATCH(((ks_ctx *)nullptr))
 }
 
+static int join_table(ks_ctx *ctx);
 void ks_ctx_destroy(ks_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->out_thread.joinable()) ctx->out_thread.join();
+  join_table(ctx);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   DBuf *all[] = {&ctx->wfx, &ctx->prm, &ctx->rec_beg, &ctx->rec_pk, &ctx->rec_c,
                  &ctx->rec_mhi, &ctx->rec_mlo, &ctx->rec_count, &ctx->seg_start, &ctx->seg_len,
                  &ctx->seg_chunks, &ctx->seg_chunk0, &ctx->scan_tmp, &ctx->sort_keys_a, &ctx->sort_keys_b,
@@ -410,13 +414,26 @@ void ks_ctx_destroy(ks_ctx *ctx) {
 
 const char *ks_last_error(const ks_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 void *ks_ctx_stream(ks_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+// the score table written on the copy stream (ks_dev_pipeline, ks_ctx_side_table): make it part of the compute
+// stream's order and wait for it
+static int join_table(ks_ctx *ctx) {
+  if (!ctx->table_pending) return KS_OK;
+  ctx->table_pending = false;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_table, 0));
+  CK(cudaEventSynchronize(ctx->ev_table));
+  return KS_OK;
+}
 int ks_ctx_sync(ks_ctx *ctx) {
   KS_TRY
   if (!ctx) return KS_ERR_ARG;
+  int rc = join_table(ctx);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   return KS_OK;
   KS_CATCH(ctx)
 }
+void ks_ctx_side_table(ks_ctx *ctx, int on) { if (ctx) ctx->side_table_opt = on != 0; }
 uint64_t ks_ctx_launches(const ks_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void ks_ctx_reset_launches(ks_ctx *ctx) { if (ctx) ctx->launches = 0; }
 void ks_ctx_scan_stats(const ks_ctx *ctx, int *levels, uint64_t *revisited_chunks) {
@@ -1256,6 +1273,10 @@ int ks_dev_scores_devtotal(ks_ctx *ctx, int k, const int32_t *d_counts, const ui
 static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double total, bool total_on_device,
                            int mode, double param, double *d_scores, double *total_out) {
   if (!ctx) return KS_ERR_ARG;
+  {  // a table still being written next to an earlier scan reads the staging areas this call is about to refill
+    const int rcj = join_table(ctx);
+    if (rcj) return rcj;
+  }
   if (total_on_device && mode != KS_MODE_LOG2 && mode != KS_MODE_SIGN) {
     unsigned long long nw = 0;
     CK(cudaMemcpyAsync(&nw, ctx->nwords.p, sizeof nw, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1447,7 +1468,7 @@ static int dev_scores_impl(ks_ctx *ctx, int k, const int32_t *d_counts, double t
       CK(ctx->sc_lut.ensure(ng * 8 + 8));
       CK(ctx->sc_dense.ensure(dense_n * 8));
       // inside ks_dev_pipeline the table is written next to the scan, which reads counts and classes, not the table
-      const bool side = ctx->defer_table && staged && gcount_on_device;
+      const bool side = (ctx->defer_table || ctx->side_table_opt) && staged && gcount_on_device;
       cudaStream_t ts = st;
       if (side) {
         int rc2 = ensure_copy_stream(ctx);
@@ -2385,7 +2406,9 @@ static int scan_counts_impl(ks_ctx *ctx, const ks_seqset *s, int k, const int32_
     tab.use_cls = true;
     tab.use_core = ctx->core_valid;
     tab.lut_size = (uint32_t)ng;
-    return scan_core(ctx, s, k, tab, mw, nullptr, host_out, n_spans, sh);
+    rc = scan_core(ctx, s, k, tab, mw, nullptr, host_out, n_spans, sh);
+    const int rcj = join_table(ctx);  // a score table written next to this scan (ks_ctx_side_table)
+    return rc ? rc : rcj;
   }
   uint32_t maxc = ng ? ctx->lut_gcount[ng - 1] : 0;
   uint32_t lut_size = maxc < (1u << 16) ? maxc + 1 : (1u << 16);
@@ -2832,15 +2855,8 @@ int ks_dev_pipeline(ks_ctx *ctx, const ks_seqset *s, int k, int mode, double par
     else
       rc = ks_dev_scan(ctx, s, k, d_scores, thr, min_width, min_score, nullptr, host_out, n_spans);
   }
-  if (ctx->table_pending) {  // the score table written next to the scan: part of this call, and of its stream order
-    ctx->table_pending = false;
-    cudaSetDevice(ctx->device);
-    cudaError_t e1 = cudaStreamWaitEvent(ctx->stream, ctx->ev_table, 0);
-    cudaError_t e2 = cudaEventSynchronize(ctx->ev_table);
-    if (!rc && (e1 != cudaSuccess || e2 != cudaSuccess))
-      rc = ctx->fail(KS_ERR_CUDA, "score table: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-  }
-  return rc;
+  const int rcj = join_table(ctx);  // the score table written next to the scan: part of this call
+  return rc ? rc : rcj;
   KS_CATCH(ctx)
 }
 

@@ -52,6 +52,7 @@ class GpuStages:
         self.torch = torch
         self.device = torch.device("cuda", device)
         self.ctx = api.Context(device)
+        self.ctx.side_table(True)  # the score table is read after the scan: let it be written next to it
         self.ss = None
 
     def load(self, seqs):
