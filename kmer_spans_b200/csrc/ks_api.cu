@@ -488,9 +488,9 @@ int ks_kmer_seq(int k, uint64_t code, char *out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage: count.  Three ways to count (ks_count.cuh): shared-memory table (k <= 7), 1024 buckets through shared
-// memory (8 <= k <= 12), direct global reductions (k >= 13 in slices of the table, and inputs too small to pay
-// for the extra launches).  KS_COUNT_PATH = direct | smem | bucket forces one (tests, measurements).
+// stage: count.  Three ways to count (ks_count.cuh): shared-memory table (k <= 7), buckets through shared memory
+// with one sub-key per two k-mers (8 <= k <= 13), direct global reductions (k >= 14 in slices of the table, and
+// inputs too small to pay for the extra launches).  KS_COUNT_PATH = direct | smem | bucket forces one (tests, measurements).
 namespace {
 enum { COUNT_DIRECT = 0, COUNT_SMEM = 1, COUNT_BUCKET = 2 };
 struct CountRun {
@@ -498,7 +498,7 @@ struct CountRun {
   int k = 0;
   int32_t *d_counts = nullptr;
   uint32_t kmask = 0, gcap = 0;
-  int sub_bits = 0, nparts = 1, part_shift = 32;
+  int nparts = 1, part_shift = 32;
 };
 }  // namespace
 
@@ -557,7 +557,6 @@ static int count_begin(ks_ctx *ctx, int k, int32_t *d_counts, int64_t est_chunks
   CK(cudaMemsetAsync(d_counts, 0, n * sizeof(int32_t), st));
   CK(cudaMemsetAsync(ctx->nwords.p, 0, sizeof(unsigned long long), st));
   if (path == COUNT_BUCKET) {
-    run->sub_bits = 2 * k - 8;  // one sub-key per pair of k-mers: rest of the core + a + b
     const size_t nbuckets = (size_t)1 << bk_log(k);
     uint64_t per = (uint64_t)(est_chunks > 0 ? est_chunks : 1) * 8 / nbuckets;  // pairs per bucket
     uint64_t gcap = per + per / 2 + 8192;  // spectrum skew; what does not fit overflows to the direct reduction

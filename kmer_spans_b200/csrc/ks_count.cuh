@@ -6,18 +6,19 @@
 // 64 KiB table at 1 630 G/s.  So:
 //   k <= 7   pack_count_smem_kernel: the whole 4^k table lives in the shared memory of every CTA (<= 64 KiB),
 //            one shared-memory atomic per base, one flush of the non-zero counters per CTA at the end.
-//   8..12    two phases over 1024 buckets, ONE SUB-KEY PER TWO K-MERS: the k-mers ending at positions 2i and 2i+1
-//            are a.c and c.b around the same (k-1)-mer c (the pairing the scan's core records use), so the pair is
-//            filed under the leading 10 bits of c and travels as one uint16 = (rest of c, a, b) = 2k - 8 bits.
+//   8..13    two phases over 1024 buckets (4096 at k = 13), ONE SUB-KEY PER TWO K-MERS: the k-mers ending at
+//            positions 2i and 2i+1 are a.c and c.b around the same (k-1)-mer c (the pairing the scan's core records
+//            use), so the pair is filed under the leading 10 (12) bits of c and travels as one uint16 =
+//            (a, rest of c, b) = 2k - 8 (2k - 10) bits.
 //            bucket_scatter_kernel (fused with the 2-bit packing of K1) ranks every pair of a 24 576-position tile
 //            inside its bucket with one shared-memory atomic, stages the sub-key in shared memory and appends each
 //            bucket's full 8-byte granules to the bucket's region in HBM (1 B written + 1 B read per base instead of
 //            a 32-byte-sector L2 atomic per base); bucket_count_kernel then counts one bucket per CTA in two
-//            shared-memory tables of 4^k / 1024 entries -- c.b lands in the bucket's own slice of the count table,
+//            shared-memory tables of 4^k / buckets entries -- c.b lands in the bucket's own slice of the count table,
 //            a.c in a second table owned by the same CTA -- and bucket_fold_kernel adds the second table in.
 //            A pair that does not fit its staging row (repeats, skewed spectra) or its bucket's region, and a
 //            k-mer without a partner (run boundaries), falls back to the direct global reduction: every input stays exact.
-//   >= 13    the direct kernel of ks_kernels.cuh in slices of the table (the table exceeds L2).
+//   >= 14    the direct kernel of ks_kernels.cuh in slices of the table (the table exceeds L2).
 #pragma once
 #include "ks_kernels.cuh"
 

@@ -66,11 +66,12 @@ class GpuStages:
         them over NVLink / NVSwitch peer memory (csrc/ks_xgpu.cuh); if that cannot be set up the tables are
         plain tensors and reduce_counts() uses NCCL."""
         t = self.torch
-        if getattr(self, "_tables_k", None) == k:
+        world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+        key = (k, world, id(dist.group.WORLD) if world > 1 else 0)
+        if getattr(self, "_tables_k", None) == key:
             return self.counts
         n = 4 ** k
         self._peer = None
-        world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
         if world > 1 and os.environ.get("KS_PEER_SUM", "1") != "0":
             try:
                 import torch.distributed._symmetric_memory as symm
@@ -87,12 +88,25 @@ class GpuStages:
             except Exception as e:  # no symmetric memory on this system: NCCL does the sum
                 self._peer = None
                 self._peer_error = repr(e)
+            # the ranks must agree on the path: one that fell back alone would sit in an NCCL all-reduce while the
+            # others wait at the symmetric-memory barrier.  [peer path ok, multicast ok], minimum over the ranks
+            flag = t.tensor([1 if self._peer is not None else 0,
+                             1 if (self._peer is not None and self._peer["mc"]) else 0],
+                            dtype=t.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok_peer, ok_mc = (int(v) for v in flag.tolist())
+            if not ok_peer:
+                if self._peer is not None:
+                    self._peer_error = "another rank could not map the symmetric buffer"
+                self._peer = None
+            elif not ok_mc:
+                self._peer["mc"] = 0
         if self._peer is None:
             self.counts = t.zeros(n, dtype=t.int32, device=self.device)
             self.nwords = t.zeros(1, dtype=t.int64, device=self.device)
         self.scores = t.empty(n, dtype=t.float64, device=self.device)
         t.cuda.synchronize(self.device)
-        self._tables_k = k
+        self._tables_k = key
         return self.counts
 
     def reduce_counts(self, dist, events=None):
