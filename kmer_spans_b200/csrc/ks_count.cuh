@@ -21,18 +21,12 @@
 //   >= 14    the direct kernel of ks_kernels.cuh in slices of the table (the table exceeds L2).
 #pragma once
 #include "ks_kernels.cuh"
+#include "ks_pairgeom.h"
 
 namespace ks {
 
-// buckets: 1024 for k <= 12; 4096 at k = 13, where 1024 would leave 18-bit sub-keys (one CTA of 1024 threads per SM
-// then holds the 4096 staging rows)
-constexpr int bk_log(int k) { return k >= 13 ? 12 : 10; }
-constexpr int bk_threads(int k) { return k >= 13 ? 1024 : 256; }
-constexpr int BK_MAX_BUCKETS = 1 << 12;
 constexpr int BK_CAP = 24;      // staged sub-keys per bucket and tile; rows of 48 bytes (8-byte aligned)
-constexpr int BK_ROUNDS = 6;    // chunks per thread and tile, loaded in two batches of three
 constexpr int BK_BATCH = 3;
-constexpr int bk_tile_chunks(int k) { return bk_threads(k) * BK_ROUNDS; }  // 12 pairs per bucket and tile
 constexpr uint32_t BK_PAD = 0xffffu;  // filler of the last granule of a row; never a sub-key: an all-ones sub-key would
                                       // need k = 12 with rest, a, b all ones, which is filed as two direct reductions
 constexpr size_t bk_scatter_smem(int k) { return ((size_t)4 + (size_t)BK_CAP * 2) << bk_log(k); }  // counters + rows
@@ -117,27 +111,6 @@ __global__ void __launch_bounds__(256) pack_count_smem_kernel(const uint8_t *__r
 // ------------------------------------------------------------------------------------------------------------
 // 8 <= k <= 12, phase 1: pack + scatter one sub-key per pair of consecutive k-mers into the buckets.
 //
-// The three bases around a pair, read straight from the packed window: Y = a.c.b (2k + 2 bits), c the shared (k-1)-mer.
-//   bucket  = leading 10 bits of c            = (Y >> (REST + 2)) & 1023,  REST = 2k - 12 bits of c remain
-//   sub-key = a | rest of c | b  (2k - 8 bits) = (Y & LOW) | ((Y >> 10) & (3 << (REST + 2))),  LOW = REST + 2 ones
-// so that phase 2 indexes its c.b table with sub & LOW and its a.c table with sub >> 2.
-template <int K>
-struct PairGeom {
-  static constexpr int LOG = bk_log(K), NB = 1 << LOG, THREADS = bk_threads(K), TILE_CHUNKS = bk_tile_chunks(K);
-  static constexpr int REST = 2 * K - 2 - LOG;
-  static constexpr uint32_t LOW = (1u << (REST + 2)) - 1u;
-  static constexpr uint32_t KMASK = (uint32_t)(((uint64_t)1 << (2 * K)) - 1u);
-  static constexpr uint32_t ENTRIES = 1u << (REST + 2);  // per bucket and table = 4^K / buckets
-  __device__ static __forceinline__ uint32_t bucket4(uint32_t y) { return (y >> REST) & ((uint32_t)(NB - 1) << 2); }  // bucket * 4
-  __device__ static __forceinline__ uint32_t sub(uint32_t y) { return (y & LOW) | ((y >> LOG) & (3u << (REST + 2))); }
-  __device__ static __forceinline__ uint32_t code_ac(uint32_t bucket, uint32_t sub) {
-    return ((sub >> (REST + 2)) << (2 * K - 2)) | (bucket << REST) | ((sub >> 2) & ((1u << REST) - 1u));
-  }
-  __device__ static __forceinline__ uint32_t code_cb(uint32_t bucket, uint32_t sub) {
-    return (bucket << (REST + 2)) | (sub & LOW);
-  }
-};
-
 // "does any of the 16 bytes break a run" (N, n, terminator): exact as a yes / no, a third of the work of the flags
 __device__ __forceinline__ uint32_t any_break16(const uint32_t w[4]) {
   uint32_t acc = 0;
@@ -380,12 +353,9 @@ template <int K>
 __global__ void __launch_bounds__(256) bucket_fold_kernel(int32_t *__restrict__ counts, const uint32_t *__restrict__ table_a) {
   typedef PairGeom<K> G;
   const size_t n4 = ((size_t)1 << (2 * K)) / 4;
-  constexpr uint32_t CMASK = G::KMASK >> 2, RESTMASK = (1u << G::REST) - 1u;
   int4 *c4 = reinterpret_cast<int4 *>(counts);
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t x = (uint32_t)(q * 4), a = x >> (2 * K - 2), c = x & CMASK;
-    const uint4 add = __ldcs(reinterpret_cast<const uint4 *>(
-        &table_a[(size_t)(c >> G::REST) * G::ENTRIES + ((size_t)a << G::REST) + (c & RESTMASK)]));
+    const uint4 add = __ldcs(reinterpret_cast<const uint4 *>(&table_a[G::fold_index((uint32_t)(q * 4))]));
     if (add.x | add.y | add.z | add.w) {
       int4 v = c4[q];
       v.x += (int)add.x; v.y += (int)add.y; v.z += (int)add.z; v.w += (int)add.w;

@@ -39,6 +39,17 @@ class Emu:
                            counts.ctypes.data_as(C.c_void_p), C.byref(n))
         return float(n.value), counts
 
+    def count_pairs(self, seqs, k, row_cap=24):
+        """the bucketed count (one sub-key per pair of k-mers, two tables per bucket, fold) on the host"""
+        buf, tot, starts = pack(seqs)
+        counts = np.zeros(4 ** k, np.int32)
+        n = C.c_uint64(0)
+        rc = self.lib.emu_count_pairs(buf.ctypes.data_as(C.c_void_p), C.c_int64(tot), C.c_int(k),
+                                      counts.ctypes.data_as(C.c_void_p), C.byref(n), C.c_uint32(row_cap))
+        if rc or n.value == 2 ** 64 - 1:
+            raise ValueError("emu_count_pairs: rc=%d (geometry round trip failed)" % rc)
+        return float(n.value), counts
+
     def rank(self, counts, k, total):
         counts = np.ascontiguousarray(counts, np.int32)
         ranks = np.zeros(4 ** k)

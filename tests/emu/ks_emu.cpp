@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../kmer_spans_b200/csrc/ks_chunk.cuh"
+#include "../../kmer_spans_b200/csrc/ks_pairgeom.h"
 #include "../../kmer_spans_b200/csrc/ks_layout.h"
 #include "../../kmer_spans_b200/csrc/ks_rankseg.h"
 
@@ -50,6 +51,49 @@ static void window(const Packed &P, int64_t p0, uint64_t &X, uint32_t &brk32, ui
   nul32 = (uint32_t)(n48 >> r);
 }
 
+// the bucketed count of ks_count.cuh folded on the host: one sub-key per pair of consecutive counted k-mers, filed
+// under the bucket PairGeom names; phase 2 = two tables per bucket (c.b in the bucket's slice of the count table,
+// a.c in a second table), then the fold.  Un-paired k-mers, and pairs beyond `row_cap` in their bucket (the staging
+// rows of the kernel are finite), are counted directly, decoded back from (bucket, sub-key) as the overflow path does.
+template <int K>
+static void count_pairs_k(const uint8_t *buf, int64_t ntot, int32_t *counts, uint64_t *nwords, uint32_t row_cap) {
+  typedef PairGeom<K> G;
+  const uint32_t kmask = G::KMASK;
+  const size_t nk = (size_t)kmask + 1;
+  std::vector<uint32_t> table_a(nk, 0), fill(G::NB, 0);
+  uint64_t n = 0;
+  Packed P = pack_buffer(buf, ntot);
+  for (int64_t p0 = 16; p0 < ntot; p0 += 16) {
+    uint32_t code[16], counted, brk32, nul32;
+    uint64_t X;
+    window(P, p0, X, brk32, nul32);
+    uint32_t next_nul = (p0 + 16 < ntot) ? (buf[p0 + 16] == 0) : 1;
+    decode_count(X, brk32, nul32, next_nul, K, kmask, code, counted);
+    n += (uint64_t)__builtin_popcount(counted);
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t m2 = (counted >> (2 * i)) & 3u;
+      if (m2 == 3u) {
+        const uint32_t y = (uint32_t)(X >> (28 - 4 * i));  // a.c.b, as the kernel reads it from the packed window
+        const uint32_t bucket = G::bucket4(y) >> 2, sub = G::sub(y);
+        if (G::code_ac(bucket, sub) != code[2 * i] || G::code_cb(bucket, sub) != code[2 * i + 1]) { *nwords = ~0ull; return; }
+        if (sub == 0xffffu || fill[bucket] >= row_cap) {  // filler look-alike / full row: directly
+          counts[G::code_ac(bucket, sub)]++;
+          counts[G::code_cb(bucket, sub)]++;
+        } else {
+          ++fill[bucket];
+          counts[(size_t)bucket * G::ENTRIES + (sub & G::LOW)]++;      // tabB -> the bucket's slice
+          table_a[(size_t)bucket * G::ENTRIES + (sub >> 2)]++;         // tabA -> second table
+        }
+      } else {
+        if (m2 & 1u) counts[code[2 * i]]++;
+        if (m2 & 2u) counts[code[2 * i + 1]]++;
+      }
+    }
+    if ((p0 & 0xfff0) == 0) std::fill(fill.begin(), fill.end(), 0u);  // a new "tile": the rows are empty again
+  }
+  for (size_t x = 0; x < nk; ++x) counts[x] += (int32_t)table_a[G::fold_index((uint32_t)x)];
+  *nwords = n;
+}
 extern "C" {
 
 int64_t emu_layout_total(const int64_t *lens, int nseq, int64_t *starts) {
@@ -71,6 +115,18 @@ void emu_count(const uint8_t *buf, int64_t ntot, int k, int32_t *counts, uint64_
       if (counted & (1u << j)) { counts[code[j]]++; ++n; }
   }
   *nwords = n;
+}
+
+int emu_count_pairs(const uint8_t *buf, int64_t ntot, int k, int32_t *counts, uint64_t *nwords, uint32_t row_cap) {
+  switch (k) {
+    case 8: count_pairs_k<8>(buf, ntot, counts, nwords, row_cap); return 0;
+    case 9: count_pairs_k<9>(buf, ntot, counts, nwords, row_cap); return 0;
+    case 10: count_pairs_k<10>(buf, ntot, counts, nwords, row_cap); return 0;
+    case 11: count_pairs_k<11>(buf, ntot, counts, nwords, row_cap); return 0;
+    case 12: count_pairs_k<12>(buf, ntot, counts, nwords, row_cap); return 0;
+    case 13: count_pairs_k<13>(buf, ntot, counts, nwords, row_cap); return 0;
+  }
+  return 1;
 }
 
 // exact ranks: stable order, run-length groups, linear pieces, closed-form evaluation

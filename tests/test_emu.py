@@ -161,6 +161,20 @@ def test_emu_config1_both_modes(emu, oracle):
     assert_spans(e, o, exact_scores=False)
 
 
+@pytest.mark.parametrize("k", [8, 10, 12, 13])
+def test_emu_pair_bucket_count_vs_oracle(emu, oracle, k):
+    """the bucketed count of ks_count.cuh (bucket and 16-bit sub-key of a PAIR of k-mers from PairGeom, two tables
+    per bucket, the fold) folded on the host gives the oracle's table; every (bucket, sub-key) is decoded back to
+    its two k-mers on the way, and tiny staging rows push most pairs through the overflow decode"""
+    rng = np.random.default_rng(5200 + k)
+    seqs = [planted(rng, 60_000), rand_seq(rng, 9000, p_n=0.05), b"A" * 5000, b"ACG" * 3000, b"ACGT"[:3], b"",
+            b"G" * k, b"T" * (k + 1)]
+    n1, c1 = oracle.kmer_counts(seqs, k)
+    for cap in (24, 2):
+        n2, c2 = emu.count_pairs(seqs, k, row_cap=cap)
+        assert n2 == n1 and (c2 == c1).all(), (k, cap)
+
+
 # ---- the summary-based ("fast") walk: chunk summaries, O(1) elements, few chunks walked in detail ----
 @pytest.mark.parametrize("k", [2, 5, 8])
 def test_emu_fast_walk_vs_oracle(emu, oracle, k):
